@@ -1,0 +1,188 @@
+/*
+ * nglod_b200 -- C ABI of the B200-native NGLOD hot path.
+ *
+ * One shared library (libnglod_b200.so), every entry point `extern "C"`, plain
+ * device pointers and sizes, an explicit cudaStream_t (passed as void*), no
+ * allocation, no hidden global state, no torch types.  Every function returns
+ * 0 on success or a non-zero code (a cudaError_t, or one of the NGLOD_E*
+ * values below for argument errors) -- it never prints and never aborts.  The
+ * host side (nglod_b200/_lib.py -> lib/...) converts a non-zero return into a
+ * Python RuntimeError.
+ *
+ * All device buffers are dense, row-major, fp32 unless stated; "borrowed"
+ * means the callee never frees or keeps the pointer past the call's stream
+ * work.  Outputs are caller-allocated (the torch-side shim allocates them the
+ * way the reference extensions allocate their return tensors).
+ *
+ * Each entry point cites the reference interface it replaces
+ * (paths relative to the nv-tlabs/nglod tree).
+ */
+#ifndef NGLOD_B200_H_
+#define NGLOD_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NGLOD_ABI_VERSION 1
+#define NGLOD_MAX_LODS 8
+
+/* argument-error codes (disjoint from cudaError_t values we can hit) */
+#define NGLOD_EINVAL 10001   /* null pointer / negative size / bad lod        */
+#define NGLOD_EUNSUPPORTED 10002 /* shape the kernels are not built for       */
+
+/*
+ * The OctreeSDF model, as the kernels see it.
+ * Replaces: sdf-net/lib/models/OctreeSDF.py:38-88 (FeatureVolume grids + per-LOD
+ * nn.Sequential(Linear(3+F,H), ReLU, Linear(H,1)) decoders).
+ *
+ * grids[i]: LOD i feature grid, CHANNELS-LAST: element (iz,iy,ix,c) at
+ *           ((iz*(R+1)+iy)*(R+1)+ix)*feature_dim + c, R = grid_res[i]
+ *           (this is the reference's fm[0,c,iz,iy,ix] held in
+ *           torch.channels_last_3d memory format, so one corner's F channels
+ *           are one contiguous, 16-byte-aligned run).
+ * w0[i]:    [hidden_dim, in_dim] row-major (torch Linear.weight), where
+ *           in_dim = feature_dim + (pos_invariant ? 0 : 3); xyz columns first.
+ * b0[i]:    [hidden_dim];  w1[i]: [hidden_dim] (Linear(H,1).weight);  b1[i]: [1].
+ * With a joint decoder all w0[i] (etc.) alias the same buffers.
+ */
+typedef struct nglod_net {
+    int32_t num_lods;
+    int32_t feature_dim;    /* 32 on the headline config                       */
+    int32_t hidden_dim;     /* 128 on the headline config                      */
+    int32_t pos_invariant;  /* 0: decoder input is [x,y,z,feat]; 1: [feat]     */
+    int32_t grid_res[NGLOD_MAX_LODS];
+    const float* grids[NGLOD_MAX_LODS];
+    const float* w0[NGLOD_MAX_LODS];
+    const float* b0[NGLOD_MAX_LODS];
+    const float* w1[NGLOD_MAX_LODS];
+    const float* b1[NGLOD_MAX_LODS];
+} nglod_net_t;
+
+/* Gradient buffers shaped exactly like the parameters in nglod_net_t
+ * (grids channels-last).  The kernels ACCUMULATE (+=) into them; the caller
+ * zeroes them (autograd semantics).  Null entries are skipped. */
+typedef struct nglod_net_grad {
+    float* grids[NGLOD_MAX_LODS];
+    float* w0[NGLOD_MAX_LODS];
+    float* b0[NGLOD_MAX_LODS];
+    float* w1[NGLOD_MAX_LODS];
+    float* b1[NGLOD_MAX_LODS];
+} nglod_net_grad_t;
+
+/* ---- introspection ------------------------------------------------------ */
+int nglod_abi_version(void);
+/* static string: build arch, flags; never null */
+const char* nglod_build_info(void);
+
+/* ---- ray vs unit cube ---------------------------------------------------
+ * Replaces: f_aabb / aabb_kernel, sdf-net/lib/extensions/sol_nglod/
+ * sol_nglod_kernel.cu:78-188 (exported to Python as sol_nglod.aabb, :190-192).
+ * ray_o, ray_d: [n,3].  Outputs: x [n,3] (entry point, or ray_o when no hit),
+ * t [n] (0 when no hit), hit [n] uint8 (0/1).  Rays whose origin is strictly
+ * inside the cube report hit=0, x=ray_o, t=0 exactly like the reference.
+ * Bit-exact with the reference kernel. */
+int nglod_aabb(const float* ray_o, const float* ray_d, int64_t n,
+               float* x, float* t, uint8_t* hit, void* stream);
+
+/* ---- OctreeSDF.sdf(x, lod) forward --------------------------------------
+ * Replaces: OctreeSDF.sdf, sdf-net/lib/models/OctreeSDF.py:94-155 with an
+ * integer `lod` (F.grid_sample per LOD :46-57, running sum :109-110,
+ * cat[x,feat] :115, louts[lod] :84-86).  x: [n,3] -> out: [n] (= [n,1]).
+ * FP32 throughout (|err| vs the PyTorch path ~1e-7). */
+int nglod_sdf_forward(const nglod_net_t* net, int32_t lod, const float* x,
+                      int64_t n, float* out, void* stream);
+
+/* Same model, all heads at once: out[l*n + i] = sdf(x_i, lod=l) for
+ * l = 0..num_lods-1 (OctreeSDF.sdf(x, return_lst=True), OctreeSDF.py:152-153). */
+int nglod_sdf_forward_all(const nglod_net_t* net, const float* x, int64_t n,
+                          float* out, void* stream);
+
+/* Summed interpolated features only (no decoder):
+ * out[i, c] = sum_{l<=lod} trilinear(grids[l], x_i)[c],  out: [n, feature_dim].
+ * Replaces: FeatureVolume.forward, sdf-net/lib/models/OctreeSDF.py:46-57 (one
+ * LOD: pass a net whose only grid is that LOD) and the running sum :109-110.
+ * Only grids / grid_res / num_lods / feature_dim of `net` are read. */
+int nglod_sdf_features(const nglod_net_t* net, int32_t lod, const float* x,
+                       int64_t n, float* out, void* stream);
+
+/* ---- backward of sdf(x, lod) --------------------------------------------
+ * Replaces: autograd of OctreeSDF.sdf driven from sdf-net/lib/trainer.py:339
+ * (grid_sampler_3d_backward + Linear grads).  grad_out: [n] = dL/dd.
+ * Accumulates dL/dgrids[i] (i<=lod) and dL/d{w0,b0,w1,b1}[lod] into `grad`;
+ * heads != lod are untouched.  grad_x: [n,3] or null (dL/dx incl. PyTorch's
+ * border-clip rule: the interpolation term is zeroed on an axis whose
+ * unclipped index is <=0 or >=R). */
+int nglod_sdf_backward(const nglod_net_t* net, int32_t lod, const float* x,
+                       int64_t n, const float* grad_out,
+                       const nglod_net_grad_t* grad, float* grad_x, void* stream);
+
+/* ---- fused multi-LOD training step (forward + L2 loss + backward) --------
+ * Replaces: Trainer.step_geometry's loss, sdf-net/lib/trainer.py:317-339:
+ *   loss = sum_{l in lod_mask} sum_i (sdf(x_i,l) - gt_i)^2 * loss_scale
+ * (the reference uses loss_scale = 1/batch).  Accumulates all gradients into
+ * `grad`, adds the (scaled) loss into *loss_out (device, fp32; may be null).
+ * lod_mask: bit l set <=> LOD l contributes. */
+int nglod_sdf_train_step(const nglod_net_t* net, uint32_t lod_mask,
+                         const float* x, const float* gt, int64_t n,
+                         float loss_scale, const nglod_net_grad_t* grad,
+                         float* loss_out, void* stream);
+
+/* ---- finite-difference gradient ------------------------------------------
+ * Replaces: gradient(x, f, 'finitediff'), sdf-net/lib/diffutils.py:61-70:
+ * out[i,k] = (sdf(x_i + h e_k) - sdf(x_i - h e_k)) / (2h), six evaluations,
+ * NOT normalised.  x: [n,3] -> out: [n,3]. */
+int nglod_sdf_finitediff(const nglod_net_t* net, int32_t lod, const float* x,
+                         int64_t n, float h, float* out, void* stream);
+
+/* ---- sphere tracer --------------------------------------------------------
+ * Replaces: SphereTracer.forward, sdf-net/lib/tracer/SphereTracer.py:41-132
+ * (aabb :53, march loop :74-115, box cull :119, finite-difference normals
+ * :128-130) as ONE persistent kernel with the SDF evaluated inline.
+ * Outputs: x [n,3], depth [n], hit [n] uint8, normal [n,3] (0 where !hit,
+ * else grad / max(|grad|, 1e-5)).
+ * queue: device int32[1] work counter, zeroed by the callee on `stream`.
+ * stats: optional device uint64[2] {sdf evaluations, march iterations},
+ *        accumulated (caller zeroes); may be null. */
+typedef struct nglod_trace_opts {
+    int32_t num_steps;       /* options.py:217  default 256                     */
+    int32_t compute_normals; /* 1: finitediff normals on hits; 0: normals = 0   */
+    /* doubles on purpose: these are Python floats in the reference; the callee
+     * rounds them to fp32 the way torch does when a tensor meets a Python
+     * scalar (e.g. the oscillation threshold is float32(min_dis*3.0)). */
+    double step_size;        /* options.py:219  default 1.0                     */
+    double min_dis;          /* options.py:221  default 3e-4                    */
+    double far;              /* camera_clamp[1], options.py:209 default 10      */
+    double normal_h;         /* diffutils.py:62  1/(64*3)                       */
+} nglod_trace_opts_t;
+
+int nglod_sphere_trace(const nglod_net_t* net, int32_t lod,
+                       const float* ray_o, const float* ray_d, int64_t n,
+                       const nglod_trace_opts_t* opts,
+                       float* x, float* depth, uint8_t* hit, float* normal,
+                       int32_t* queue, unsigned long long* stats, void* stream);
+
+/* ---- mesh -> signed distance ----------------------------------------------
+ * Replaces: mesh2sdf_gpu_fast_nopre -> kernel_mesh2sdf_quad + kernel_quad_aggr,
+ * sdf-net/lib/extensions/mesh2sdf_cuda/mesh2sdf_kernel.cu:307-616,895-927
+ * (exported as mesh2sdf.mesh2sdf_gpu, :1007-1012).
+ * points: [n,3]; tris: [T,3,3] (= V[F]); dist: [n] signed distance
+ * (negative iff all 13 stab directions see a triangle on both sides).
+ * No [64,n,26] temporaries: one pass, triangles staged through shared memory. */
+int nglod_mesh2sdf(const float* points, int64_t n, const float* tris,
+                   int64_t num_tris, float* dist, void* stream);
+
+/* ---- Adam on a flat fp32 parameter buffer ----------------------------------
+ * Replaces: torch.optim.Adam(lr) as set up by Trainer.set_optimizer,
+ * sdf-net/lib/trainer.py:178-189 (betas .9/.999, eps 1e-8, no weight decay).
+ * bias corrections are passed in by the host: bc1 = 1-beta1^t, bc2 = 1-beta2^t. */
+int nglod_adam_step(float* param, const float* grad, float* exp_avg,
+                    float* exp_avg_sq, int64_t n, float lr, float beta1,
+                    float beta2, float eps, float bc1, float bc2, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NGLOD_B200_H_ */

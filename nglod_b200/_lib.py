@@ -1,0 +1,116 @@
+"""ctypes binding of libnglod_b200.so -- the C ABI declared in include/nglod_b200.h.
+
+No torch types cross this boundary: callers pass `tensor.data_ptr()` integers,
+element counts and the raw `cudaStream_t` of torch's current stream.  There is
+NO fallback: if the library is missing or a call returns non-zero, this module
+raises.  (The reference's own extensions never check errors -- sol_nglod_kernel.cu,
+mesh2sdf_kernel.cu -- here every return code is turned into a RuntimeError.)
+"""
+import ctypes
+import os
+
+MAX_LODS = 8
+EINVAL = 10001
+EUNSUPPORTED = 10002
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libnglod_b200.so")
+
+c_void_p = ctypes.c_void_p
+c_int32 = ctypes.c_int32
+c_int64 = ctypes.c_int64
+
+
+class NetStruct(ctypes.Structure):
+    """nglod_net_t"""
+    _fields_ = [
+        ("num_lods", c_int32),
+        ("feature_dim", c_int32),
+        ("hidden_dim", c_int32),
+        ("pos_invariant", c_int32),
+        ("grid_res", c_int32 * MAX_LODS),
+        ("grids", c_void_p * MAX_LODS),
+        ("w0", c_void_p * MAX_LODS),
+        ("b0", c_void_p * MAX_LODS),
+        ("w1", c_void_p * MAX_LODS),
+        ("b1", c_void_p * MAX_LODS),
+    ]
+
+
+class NetGradStruct(ctypes.Structure):
+    """nglod_net_grad_t"""
+    _fields_ = [
+        ("grids", c_void_p * MAX_LODS),
+        ("w0", c_void_p * MAX_LODS),
+        ("b0", c_void_p * MAX_LODS),
+        ("w1", c_void_p * MAX_LODS),
+        ("b1", c_void_p * MAX_LODS),
+    ]
+
+
+class TraceOpts(ctypes.Structure):
+    """nglod_trace_opts_t"""
+    _fields_ = [
+        ("num_steps", c_int32),
+        ("compute_normals", c_int32),
+        ("step_size", ctypes.c_double),
+        ("min_dis", ctypes.c_double),
+        ("far", ctypes.c_double),
+        ("normal_h", ctypes.c_double),
+    ]
+
+
+# name -> (restype, argtypes); must list EVERY function include/nglod_b200.h declares
+SIGNATURES = {
+    "nglod_abi_version": (ctypes.c_int, []),
+    "nglod_build_info": (ctypes.c_char_p, []),
+    "nglod_aabb": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "nglod_sdf_forward": (ctypes.c_int, [ctypes.POINTER(NetStruct), c_int32, c_void_p, c_int64, c_void_p, c_void_p]),
+    "nglod_sdf_forward_all": (ctypes.c_int, [ctypes.POINTER(NetStruct), c_void_p, c_int64, c_void_p, c_void_p]),
+    "nglod_sdf_features": (ctypes.c_int, [ctypes.POINTER(NetStruct), c_int32, c_void_p, c_int64, c_void_p, c_void_p]),
+    "nglod_sdf_backward": (ctypes.c_int, [ctypes.POINTER(NetStruct), c_int32, c_void_p, c_int64, c_void_p,
+                                          ctypes.POINTER(NetGradStruct), c_void_p, c_void_p]),
+    "nglod_sdf_train_step": (ctypes.c_int, [ctypes.POINTER(NetStruct), ctypes.c_uint32, c_void_p, c_void_p, c_int64,
+                                            ctypes.c_float, ctypes.POINTER(NetGradStruct), c_void_p, c_void_p]),
+    "nglod_sdf_finitediff": (ctypes.c_int, [ctypes.POINTER(NetStruct), c_int32, c_void_p, c_int64, ctypes.c_float,
+                                            c_void_p, c_void_p]),
+    "nglod_sphere_trace": (ctypes.c_int, [ctypes.POINTER(NetStruct), c_int32, c_void_p, c_void_p, c_int64,
+                                          ctypes.POINTER(TraceOpts), c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_void_p, c_void_p, c_void_p]),
+    "nglod_mesh2sdf": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
+    "nglod_adam_step": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, ctypes.c_float,
+                                       ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                       ctypes.c_float, c_void_p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and type every entry point. Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m nglod_b200.build` "
+            "(nvcc, sm_100a). There is no CPU or PyTorch fallback for the NGLOD hot path.")
+    import torch  # noqa: F401  -- makes sure torch's libcudart.so.12 is the one we bind to
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the header and the .so disagree
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(code, what):
+    if code == 0:
+        return
+    if code == EINVAL:
+        raise RuntimeError(f"{what}: invalid argument (NGLOD_EINVAL)")
+    if code == EUNSUPPORTED:
+        raise RuntimeError(f"{what}: unsupported model shape -- the sm_100a kernels are built for "
+                           "feature_dim=32, hidden_dim=128 (NGLOD_EUNSUPPORTED)")
+    raise RuntimeError(f"{what}: CUDA error {code}")

@@ -1,0 +1,86 @@
+// nglod_b200 -- shared device/host helpers (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/nglod_b200.h"
+
+#define NGLOD_F 32        // feature channels the fast kernels are built for
+#define NGLOD_H 128       // decoder hidden width the fast kernels are built for
+#define NGLOD_KPAD 36     // decoder input padded: 32 feat + xyz + 1.0 (bias column)
+
+#define NGLOD_CUDA_TRY(expr)                        \
+    do {                                            \
+        cudaError_t _e = (expr);                    \
+        if (_e != cudaSuccess) return (int)_e;      \
+    } while (0)
+
+// Device-side view of the model for ONE decoder head (kernel parameter, by value).
+struct NetDev {
+    int num_lods;       // number of grids to sum (= lod + 1)
+    int pos_invariant;
+    int res[NGLOD_MAX_LODS];
+    const float* grids[NGLOD_MAX_LODS];
+    const float* w0;    // [H, in_dim]
+    const float* b0;    // [H]
+    const float* w1;    // [H]
+    const float* b1;    // [1]
+};
+
+struct GradDev {
+    float* grids[NGLOD_MAX_LODS];
+    float* w0;
+    float* b0;
+    float* w1;
+    float* b1;
+};
+
+static inline int nglod_check_net(const nglod_net_t* net, int lod) {
+    if (!net) return NGLOD_EINVAL;
+    if (net->num_lods < 1 || net->num_lods > NGLOD_MAX_LODS) return NGLOD_EINVAL;
+    if (lod < 0 || lod >= net->num_lods) return NGLOD_EINVAL;
+    if (net->feature_dim != NGLOD_F || net->hidden_dim != NGLOD_H) return NGLOD_EUNSUPPORTED;
+    for (int i = 0; i <= lod; ++i) {
+        if (!net->grids[i] || net->grid_res[i] < 1 || net->grid_res[i] > 1024) return NGLOD_EINVAL;
+        if ((reinterpret_cast<uintptr_t>(net->grids[i]) & 15u) != 0) return NGLOD_EINVAL;
+    }
+    if (!net->w0[lod] || !net->b0[lod] || !net->w1[lod] || !net->b1[lod]) return NGLOD_EINVAL;
+    return 0;
+}
+
+static inline NetDev nglod_make_netdev(const nglod_net_t* net, int lod) {
+    NetDev d;
+    d.num_lods = lod + 1;
+    d.pos_invariant = net->pos_invariant;
+    for (int i = 0; i < NGLOD_MAX_LODS; ++i) {
+        d.res[i] = i <= lod ? net->grid_res[i] : 1;
+        d.grids[i] = i <= lod ? net->grids[i] : nullptr;
+    }
+    d.w0 = net->w0[lod];
+    d.b0 = net->b0[lod];
+    d.w1 = net->w1[lod];
+    d.b1 = net->b1[lod];
+    return d;
+}
+
+// Cached device properties (SM count) -- read-only after first use.
+static inline int nglod_sm_count() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
+        sms = v;
+    }
+    return sms;
+}
+
+__device__ __forceinline__ float4 ldg_f4(const float* p) {
+    return __ldg(reinterpret_cast<const float4*>(p));
+}
+
+// 128-bit vector reduction (sm_90+): one L2 RED op for 4 consecutive floats.
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :: "l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}

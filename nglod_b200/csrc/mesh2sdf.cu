@@ -1,0 +1,215 @@
+// nglod_b200 -- brute-force mesh -> signed distance for the training sampler.
+//
+// Behavioural spec: kernel_mesh2sdf_quad + kernel_quad_aggr,
+// sdf-net/lib/extensions/mesh2sdf_cuda/mesh2sdf_kernel.cu:307-616 (entry :895-927):
+//   unsigned distance = sqrt(min over triangles of the edge / face squared distance)
+//   inside  <=>  for ALL 13 fixed stab directions the line through the point hits
+//                at least one triangle at t >= 0 AND at least one at t < 0.
+//
+// B200 design (not the reference's): one thread per point keeps its running
+// min and two 13-bit stab masks in registers; triangles are streamed through
+// shared memory in tiles of "records" holding everything that depends only on
+// the triangle -- edge vectors, the normal, the three edge-plane normals, the
+// four reciprocals and, per stab direction, pvec = dir x edge2 and 1/det --
+// computed once per CTA per tile instead of once per (point, triangle).  No
+// [64, N] distance / [64, N, 13, 2] flag temporaries (0.96 GB at N = 500k in the
+// reference), no second aggregation kernel.  All reads of a record are warp-
+// uniform shared-memory broadcasts.
+//
+// The per-pair arithmetic keeps the reference's expression shapes (dot products
+// left to right, a*x-b residuals, IEEE 1/x) so that nvcc's FMA contraction lands
+// on the same instruction sequence; the parity test compares against the
+// reference's own compiled kernel on the GPU.
+#include "common.cuh"
+
+namespace {
+
+constexpr int M2S_THREADS = 256;
+constexpr int M2S_TILE = 48;          // triangles per shared-memory tile
+constexpr int M2S_NDIR = 13;
+
+struct __align__(16) TriRecord {
+    float a[3], b[3], c[3];           // vertices
+    float v10[3], v21[3], v02[3];     // b-a, c-b, a-c
+    float nor[3];                     // v10 x v02
+    float c10[3], c21[3], c02[3];     // edge x nor
+    float inv10, inv21, inv02, invn;  // 1/|.|^2  (round-to-nearest reciprocal)
+    float pvec[M2S_NDIR][3];          // dir x edge2,  edge2 = -v02
+    float inv_det[M2S_NDIR];          // 1 / (edge1 . pvec), edge1 = v10
+    unsigned dir_ok;                  // bit k: |det_k| >= 1e-8 (else the reference skips the direction)
+    unsigned nondegenerate;           // nor != 0
+    unsigned pad[2];
+};
+
+__constant__ float c_stab_dir[M2S_NDIR][3] = {
+    {1.0f, 0.0f, 0.0f}, {0.0f, 1.0f, 0.0f}, {0.0f, 0.0f, 1.0f},
+    {0.0f, 0.707106781f, 0.707106781f}, {0.707106781f, 0.0f, 0.707106781f}, {0.707106781f, 0.707106781f, 0.0f},
+    {0.0f, 0.707106781f, -0.707106781f}, {0.707106781f, 0.0f, -0.707106781f}, {0.707106781f, -0.707106781f, 0.0f},
+    {0.577350269f, 0.577350269f, 0.577350269f}, {-0.577350269f, 0.577350269f, 0.577350269f},
+    {0.577350269f, -0.577350269f, 0.577350269f}, {0.577350269f, 0.577350269f, -0.577350269f}};
+
+__device__ __forceinline__ float dot3(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+__device__ __forceinline__ void cross3(const float* a, const float* b, float* r) {
+    r[0] = a[1] * b[2] - a[2] * b[1];
+    r[1] = a[2] * b[0] - a[0] * b[2];
+    r[2] = a[0] * b[1] - a[1] * b[0];
+}
+__device__ __forceinline__ float rcp_dot2(const float* a) { return __frcp_rn(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]); }
+__device__ __forceinline__ float clamp01(float f) { return fmaxf(0.0f, fminf(f, 1.0f)); }
+__device__ __forceinline__ float d2axmb(const float* a, float x, const float* b) {
+    const float t0 = a[0] * x - b[0];
+    const float t1 = a[1] * x - b[1];
+    const float t2 = a[2] * x - b[2];
+    return t0 * t0 + t1 * t1 + t2 * t2;
+}
+
+__device__ void build_record(const float* __restrict__ tri, TriRecord& r) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { r.a[k] = tri[k]; r.b[k] = tri[3 + k]; r.c[k] = tri[6 + k]; }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        r.v10[k] = r.b[k] - r.a[k];
+        r.v21[k] = r.c[k] - r.b[k];
+        r.v02[k] = r.a[k] - r.c[k];
+    }
+    cross3(r.v10, r.v02, r.nor);
+    cross3(r.v10, r.nor, r.c10);
+    cross3(r.v21, r.nor, r.c21);
+    cross3(r.v02, r.nor, r.c02);
+    r.inv10 = rcp_dot2(r.v10);
+    r.inv21 = rcp_dot2(r.v21);
+    r.inv02 = rcp_dot2(r.v02);
+    r.invn = rcp_dot2(r.nor);
+    r.nondegenerate = (r.nor[0] != 0.0f || r.nor[1] != 0.0f || r.nor[2] != 0.0f) ? 1u : 0u;
+    float edge2[3] = {-r.v02[0], -r.v02[1], -r.v02[2]};
+    unsigned ok = 0;
+    for (int k = 0; k < M2S_NDIR; ++k) {
+        float pv[3];
+        cross3(c_stab_dir[k], edge2, pv);
+        const float det = dot3(r.v10, pv);
+        r.pvec[k][0] = pv[0]; r.pvec[k][1] = pv[1]; r.pvec[k][2] = pv[2];
+        if (!(det > -1e-8 && det < 1e-8)) {       // note: double literals, as in the reference
+            ok |= 1u << k;
+            r.inv_det[k] = 1.0f / det;
+        } else {
+            r.inv_det[k] = 0.0f;
+        }
+    }
+    r.dir_ok = ok;
+    r.pad[0] = r.pad[1] = 0;
+}
+
+__global__ void __launch_bounds__(M2S_THREADS)
+mesh2sdf_kernel(const float* __restrict__ points, const long long n, const float* __restrict__ tris,
+                const long long num_tris, float* __restrict__ dist) {
+    __shared__ TriRecord rec[M2S_TILE];
+    const long long i = (long long)blockIdx.x * M2S_THREADS + threadIdx.x;
+    const bool active = i < n;
+    float P[3] = {0.f, 0.f, 0.f};
+    if (active) { P[0] = __ldg(points + 3 * i); P[1] = __ldg(points + 3 * i + 1); P[2] = __ldg(points + 3 * i + 2); }
+    float mind2 = INFINITY;
+    unsigned pos = 0, neg = 0;
+    const unsigned all_dirs = (1u << M2S_NDIR) - 1u;
+
+    for (long long t0 = 0; t0 < num_tris; t0 += M2S_TILE) {
+        const int cnt = (int)min((long long)M2S_TILE, num_tris - t0);
+        __syncthreads();
+        if (threadIdx.x < cnt) build_record(tris + (t0 + threadIdx.x) * 9, rec[threadIdx.x]);
+        __syncthreads();
+        if (!active) continue;
+#pragma unroll 1
+        for (int tt = 0; tt < cnt; ++tt) {
+            const TriRecord& r = rec[tt];
+            float p0[3], p1[3], p2[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { p0[k] = P[k] - r.a[k]; p1[k] = P[k] - r.b[k]; p2[k] = P[k] - r.c[k]; }
+            if (r.nondegenerate) {
+                const float s1 = copysignf(1.0f, dot3(r.c10, p0));
+                const float s2 = copysignf(1.0f, dot3(r.c21, p1));
+                const float s3 = copysignf(1.0f, dot3(r.c02, p2));
+                float d2;
+                if ((s1 + s2 + s3) < 2.0f) {
+                    const float e1 = d2axmb(r.v10, clamp01(dot3(r.v10, p0) * r.inv10), p0);
+                    const float e2 = d2axmb(r.v21, clamp01(dot3(r.v21, p1) * r.inv21), p1);
+                    const float e3 = d2axmb(r.v02, clamp01(dot3(r.v02, p2) * r.inv02), p2);
+                    d2 = fminf(e1, fminf(e2, e3));
+                } else {
+                    d2 = dot3(r.nor, p0) * dot3(r.nor, p0) * r.invn;
+                }
+                if (d2 < 0.0f) d2 = 0.0f;
+                mind2 = fminf(mind2, d2);
+            }
+            // 13 line stabs (Moller-Trumbore); qvec and edge2.qvec do not depend on the direction
+            if (r.dir_ok && ((pos & neg) != all_dirs)) {
+                float qvec[3];
+                cross3(p0, r.v10, qvec);
+                const float edge2[3] = {-r.v02[0], -r.v02[1], -r.v02[2]};
+                const float e2q = dot3(edge2, qvec);
+#pragma unroll
+                for (int k = 0; k < M2S_NDIR; ++k) {
+                    if (!((r.dir_ok >> k) & 1u)) continue;
+                    const float inv_det = r.inv_det[k];
+                    const float u = dot3(p0, r.pvec[k]) * inv_det;
+                    if (u < 0.0f || u > 1.0f) continue;
+                    const float v = dot3(c_stab_dir[k], qvec) * inv_det;
+                    if (v < 0.0f || u + v > 1.0f) continue;
+                    const float t = e2q * inv_det;
+                    if (t >= 0.0f) pos |= 1u << k; else neg |= 1u << k;
+                }
+            }
+        }
+    }
+    if (active) {
+        if (mind2 < 0.0f) mind2 = 0.0f;
+        float d = sqrtf(mind2);
+        if ((pos & neg) == all_dirs) d = -d;
+        dist[i] = d;
+    }
+}
+
+// Adam on a flat buffer (torch.optim.Adam semantics, no amsgrad / weight decay).
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+            const long long n, const float lr, const float b1, const float b2, const float eps,
+            const float bc1, const float bc2_sqrt) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const float step_size = lr / bc1;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float gi = g[i];
+        const float mi = m[i] + (gi - m[i]) * (1.f - b1);           // lerp, as torch's single-tensor Adam
+        const float vi = v[i] * b2 + gi * gi * (1.f - b2);
+        m[i] = mi; v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] = p[i] - step_size * (mi / denom);
+    }
+}
+
+}  // namespace
+
+extern "C" int nglod_mesh2sdf(const float* points, int64_t n, const float* tris, int64_t num_tris, float* dist,
+                              void* stream) {
+    if (n < 0 || num_tris < 0 || (n > 0 && (!points || !dist)) || (num_tris > 0 && !tris)) return NGLOD_EINVAL;
+    if (n == 0) return 0;
+    const long long grid = (n + M2S_THREADS - 1) / M2S_THREADS;
+    if (grid > 2147483647ll) return NGLOD_EINVAL;
+    mesh2sdf_kernel<<<(int)grid, M2S_THREADS, 0, (cudaStream_t)stream>>>(points, (long long)n, tris,
+                                                                         (long long)num_tris, dist);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int nglod_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                               float lr, float beta1, float beta2, float eps, float bc1, float bc2, void* stream) {
+    if (n < 0 || (n > 0 && (!param || !grad || !exp_avg || !exp_avg_sq))) return NGLOD_EINVAL;
+    if (n == 0) return 0;
+    long long grid = (n + 255) / 256;
+    const long long cap = (long long)nglod_sm_count() * 16;
+    if (grid > cap) grid = cap;
+    adam_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, (long long)n, lr,
+                                                             beta1, beta2, eps, bc1, sqrtf(bc2));
+    return (int)cudaGetLastError();
+}
+
+extern "C" int nglod_abi_version(void) { return NGLOD_ABI_VERSION; }
+extern "C" const char* nglod_build_info(void) {
+    return "nglod_b200 sm_100a (compute_100a) nvcc " __VERSION__ " built " __DATE__;
+}

@@ -1,0 +1,359 @@
+// nglod_b200 -- backward of OctreeSDF.sdf(x, lod) and the fused L2 training step.
+//
+// Reference behaviour: autograd through sdf-net/lib/models/OctreeSDF.py:94-146
+// (grid_sampler_3d_backward scatter + Linear grads), loss of
+// sdf-net/lib/trainer.py:317-339.
+//
+// One kernel, no saved activations (the forward is recomputed in-kernel, which
+// costs ~6k FMA/query but removes the ~0.8 kB/query of autograd state the
+// reference round-trips through HBM).  Per warp batch of 32 queries:
+//   A  gather: tile[q] = {feat, xyz, 1}                      (sdf_core.cuh)
+//   B  thread-per-query: pre[j] -> smem P[q][j]; d; g_d (given, or 2*(d-gt)*scale);
+//      g_in[k] = sum_j W0[j][k] * g_h[j]  with g_h[j] = g_d*W1[j]*[pre_j>0]
+//   C  lane owns hidden units {lane, lane+32, lane+64, lane+96}: 144 register
+//      accumulators of dW0 (incl. db0 as column 35), dW1, db1 summed over the
+//      warp's queries -- flushed ONCE per CTA at kernel end (smem, then RED)
+//   D  scatter: 8 lanes per corner, one red.global.add.v4.f32 per lane per
+//      corner (a full 128-byte line per corner per query), for every LOD <= lod;
+//      optional dL/dx with PyTorch's border-clip rule.
+#include "sdf_core.cuh"
+
+namespace {
+
+#define BWD_P_STRIDE (NGLOD_H + 1)                        // padded: lane q writes column j conflict-free
+#define BWD_P_FLOATS (32 * BWD_P_STRIDE)
+#define BWD_PER_WARP (SDF_SMEM_PER_WARP + BWD_P_FLOATS + 32)  // tile, idx, P, gd
+#define BWD_SMEM_BYTES ((SDF_SMEM_WARP_OFF + SDF_WARPS * BWD_PER_WARP) * 4)
+#define BWD_ACC_FLOATS (SDF_W0_FLOATS + NGLOD_H + 4)       // dW0|db0 (H x 36), dW1 (H), db1
+
+struct BwdAxis {
+    int i0, i1;
+    float w0, w1;
+    float mult;     // d(index)/d(p) : R/2 inside, 0 where grid_sample clips (u<=0 or u>=R)
+};
+
+__device__ __forceinline__ BwdAxis bwd_axis(float p, int R) {
+    BwdAxis a;
+    const float fR = (float)R;
+    const float u_raw = ((p + 1.f) * 0.5f) * fR;
+    a.mult = (u_raw > 0.f && u_raw < fR) ? fR * 0.5f : 0.f;
+    const float u = fminf(fR, fmaxf(u_raw, 0.f));
+    const float f0 = floorf(u);
+    a.i0 = (int)f0;
+    a.i1 = min(a.i0 + 1, R);
+    a.w0 = (f0 + 1.f) - u;
+    a.w1 = u - f0;
+    return a;
+}
+
+template <bool FUSED_LOSS, bool WITH_GX>
+__global__ void __launch_bounds__(SDF_THREADS, 1)
+sdf_backward_kernel(const NetDev net, const GradDev grad, const float* __restrict__ x, const long long n,
+                    const float* __restrict__ grad_out, const float* __restrict__ gt, const float loss_scale,
+                    float* __restrict__ grad_x, float* __restrict__ loss_out) {
+    extern __shared__ __align__(16) float smem[];
+    sdf_stage_weights(net, smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* wbase = smem + SDF_SMEM_WARP_OFF + warp * BWD_PER_WARP;
+    float* tile = wbase;
+    int* idx = reinterpret_cast<int*>(wbase + SDF_TILE_FLOATS);
+    float* P = wbase + SDF_SMEM_PER_WARP;
+    float* sgd = P + BWD_P_FLOATS;
+    for (int e = lane; e < BWD_PER_WARP; e += 32) wbase[e] = 0.f;
+    __syncthreads();
+
+    const float4* w4 = reinterpret_cast<const float4*>(smem);
+    const float* sw1 = smem + SDF_SMEM_W1_OFF;
+    const float sb1 = smem[SDF_SMEM_B1_OFF];
+
+    // phase-C accumulators: hidden units j = lane + 32*m
+    float accW0[4][NGLOD_KPAD];
+    float accW1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int k = 0; k < NGLOD_KPAD; ++k) accW0[m][k] = 0.f;
+    float acc_b1 = 0.f, acc_loss = 0.f;
+    float w1m[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) w1m[m] = sw1[lane + 32 * m];
+
+    const long long gwarp = (long long)blockIdx.x * SDF_WARPS + warp;
+    const long long nwarps = (long long)gridDim.x * SDF_WARPS;
+    for (long long base = gwarp * 32; base < n; base += nwarps * 32) {
+        const long long i = base + lane;
+        const bool active = i < n;
+        float px = 0.f, py = 0.f, pz = 0.f;
+        if (active) { px = __ldg(x + 3 * i); py = __ldg(x + 3 * i + 1); pz = __ldg(x + 3 * i + 2); }
+        // ---- A: gather
+        warp_gather_tile(net, px, py, pz, active, tile, idx, lane);
+        if (!active) {   // keep inactive rows finite and inert
+#pragma unroll
+            for (int k4 = 0; k4 < NGLOD_KPAD / 4; ++k4)
+                *reinterpret_cast<float4*>(tile + lane * NGLOD_KPAD + 4 * k4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        // ---- B: thread-per-query
+        float in[NGLOD_KPAD];
+#pragma unroll
+        for (int k4 = 0; k4 < NGLOD_KPAD / 4; ++k4) {
+            const float4 v = *reinterpret_cast<const float4*>(tile + lane * NGLOD_KPAD + 4 * k4);
+            in[4 * k4] = v.x; in[4 * k4 + 1] = v.y; in[4 * k4 + 2] = v.z; in[4 * k4 + 3] = v.w;
+        }
+        float gd = 0.f;
+        if (FUSED_LOSS) {
+            float d = sb1;
+#pragma unroll 2
+            for (int j = 0; j < NGLOD_H; ++j) {
+                float a = 0.f;
+#pragma unroll
+                for (int k4 = 0; k4 < NGLOD_KPAD / 4; ++k4) {
+                    const float4 w = w4[j * (NGLOD_KPAD / 4) + k4];
+                    a = fmaf(w.x, in[4 * k4], a); a = fmaf(w.y, in[4 * k4 + 1], a);
+                    a = fmaf(w.z, in[4 * k4 + 2], a); a = fmaf(w.w, in[4 * k4 + 3], a);
+                }
+                P[lane * BWD_P_STRIDE + j] = a;
+                d = fmaf(sw1[j], fmaxf(a, 0.f), d);
+            }
+            if (active) {
+                const float diff = d - __ldg(gt + i);
+                acc_loss = fmaf(diff * diff, loss_scale, acc_loss);
+                gd = 2.f * diff * loss_scale;
+            }
+        } else {
+            if (active) gd = __ldg(grad_out + i);
+        }
+        float gin[NGLOD_KPAD - 1];
+#pragma unroll
+        for (int k = 0; k < NGLOD_KPAD - 1; ++k) gin[k] = 0.f;
+#pragma unroll 2
+        for (int j = 0; j < NGLOD_H; ++j) {
+            float4 wr[NGLOD_KPAD / 4];
+#pragma unroll
+            for (int k4 = 0; k4 < NGLOD_KPAD / 4; ++k4) wr[k4] = w4[j * (NGLOD_KPAD / 4) + k4];
+            float a;
+            if (FUSED_LOSS) {
+                a = P[lane * BWD_P_STRIDE + j];
+            } else {
+                a = 0.f;
+#pragma unroll
+                for (int k4 = 0; k4 < NGLOD_KPAD / 4; ++k4) {
+                    a = fmaf(wr[k4].x, in[4 * k4], a); a = fmaf(wr[k4].y, in[4 * k4 + 1], a);
+                    a = fmaf(wr[k4].z, in[4 * k4 + 2], a); a = fmaf(wr[k4].w, in[4 * k4 + 3], a);
+                }
+                P[lane * BWD_P_STRIDE + j] = a;
+            }
+            const float gh = a > 0.f ? gd * sw1[j] : 0.f;
+#pragma unroll
+            for (int k4 = 0; k4 < NGLOD_F / 4; ++k4) {
+                gin[4 * k4] = fmaf(wr[k4].x, gh, gin[4 * k4]);
+                gin[4 * k4 + 1] = fmaf(wr[k4].y, gh, gin[4 * k4 + 1]);
+                gin[4 * k4 + 2] = fmaf(wr[k4].z, gh, gin[4 * k4 + 2]);
+                gin[4 * k4 + 3] = fmaf(wr[k4].w, gh, gin[4 * k4 + 3]);
+            }
+            if (WITH_GX) {
+                gin[32] = fmaf(wr[8].x, gh, gin[32]);
+                gin[33] = fmaf(wr[8].y, gh, gin[33]);
+                gin[34] = fmaf(wr[8].z, gh, gin[34]);
+            }
+        }
+        sgd[lane] = gd;
+        acc_b1 += gd;
+        __syncwarp();
+        // ---- C: head gradients, lane owns 4 hidden units
+#pragma unroll 1
+        for (int q = 0; q < 32; ++q) {
+            const float gdq = sgd[q];
+            if (gdq == 0.f) continue;            // warp-uniform (inactive rows, exact-zero upstream grads)
+            float gh[4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const float p = P[q * BWD_P_STRIDE + lane + 32 * m];
+                gh[m] = p > 0.f ? gdq * w1m[m] : 0.f;
+                accW1[m] = fmaf(gdq, fmaxf(p, 0.f), accW1[m]);
+            }
+#pragma unroll
+            for (int k4 = 0; k4 < NGLOD_KPAD / 4; ++k4) {
+                const float4 v = *reinterpret_cast<const float4*>(tile + q * NGLOD_KPAD + 4 * k4);
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    accW0[m][4 * k4] = fmaf(gh[m], v.x, accW0[m][4 * k4]);
+                    accW0[m][4 * k4 + 1] = fmaf(gh[m], v.y, accW0[m][4 * k4 + 1]);
+                    accW0[m][4 * k4 + 2] = fmaf(gh[m], v.z, accW0[m][4 * k4 + 2]);
+                    accW0[m][4 * k4 + 3] = fmaf(gh[m], v.w, accW0[m][4 * k4 + 3]);
+                }
+            }
+        }
+        __syncwarp();
+        // ---- D: scatter g_feat into the grids (and dL/dx)
+#pragma unroll
+        for (int k4 = 0; k4 < NGLOD_F / 4; ++k4)
+            *reinterpret_cast<float4*>(tile + lane * NGLOD_KPAD + 4 * k4) =
+                make_float4(gin[4 * k4], gin[4 * k4 + 1], gin[4 * k4 + 2], gin[4 * k4 + 3]);
+        __syncwarp();
+        {
+            const unsigned live = __ballot_sync(0xffffffffu, active);
+            const int n_live = __popc(live);
+            const int sub = lane >> 3, c = lane & 7;
+            float gx_out[3] = {0.f, 0.f, 0.f};    // valid in the query's own lane after the rounds
+            for (int r = 0; r * 4 < n_live; ++r) {
+                const int slot = r * 4 + sub;
+                const bool valid = slot < n_live;
+                const int q = idx[valid ? slot : 0];
+                const float qx = __shfl_sync(0xffffffffu, px, q);
+                const float qy = __shfl_sync(0xffffffffu, py, q);
+                const float qz = __shfl_sync(0xffffffffu, pz, q);
+                float sx = 0.f, sy = 0.f, sz = 0.f;
+                if (valid) {
+                    const float4 g = *reinterpret_cast<const float4*>(tile + q * NGLOD_KPAD + 4 * c);
+#pragma unroll
+                    for (int l = 0; l < NGLOD_MAX_LODS; ++l) {
+                        if (l >= net.num_lods) break;
+                        const int R = net.res[l], S = R + 1;
+                        const BwdAxis ax = bwd_axis(qx, R), ay = bwd_axis(qy, R), az = bwd_axis(qz, R);
+                        float* gg = grad.grids[l];
+                        float lx = 0.f, ly = 0.f, lz = 0.f;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const int ix = (k & 1) ? ax.i1 : ax.i0;
+                            const int iy = (k & 2) ? ay.i1 : ay.i0;
+                            const int iz = (k & 4) ? az.i1 : az.i0;
+                            const float wx = (k & 1) ? ax.w1 : ax.w0;
+                            const float wy = (k & 2) ? ay.w1 : ay.w0;
+                            const float wz = (k & 4) ? az.w1 : az.w0;
+                            const int off = ((iz * S + iy) * S + ix) * NGLOD_F + 4 * c;
+                            const float w = (wx * wy) * wz;
+                            if (gg) red_add_v4(gg + off, g.x * w, g.y * w, g.z * w, g.w * w);
+                            if (WITH_GX) {
+                                const float4 v = ldg_f4(net.grids[l] + off);
+                                const float dot = v.x * g.x + v.y * g.y + v.z * g.z + v.w * g.w;
+                                lx += ((k & 1) ? dot : -dot) * (wy * wz);
+                                ly += ((k & 2) ? dot : -dot) * (wx * wz);
+                                lz += ((k & 4) ? dot : -dot) * (wx * wy);
+                            }
+                        }
+                        if (WITH_GX) { sx = fmaf(lx, ax.mult, sx); sy = fmaf(ly, ay.mult, sy); sz = fmaf(lz, az.mult, sz); }
+                    }
+                }
+                if (WITH_GX) {
+                    // reduce the 8 channel-group partials of each sub-warp, hand the sum to the query's lane
+#pragma unroll
+                    for (int o = 4; o >= 1; o >>= 1) {
+                        sx += __shfl_xor_sync(0xffffffffu, sx, o);
+                        sy += __shfl_xor_sync(0xffffffffu, sy, o);
+                        sz += __shfl_xor_sync(0xffffffffu, sz, o);
+                    }
+                    if (valid && c == 0) {
+                        float* dst = tile + q * NGLOD_KPAD + NGLOD_F;   // xyz columns are free now
+                        dst[0] = sx; dst[1] = sy; dst[2] = sz;
+                    }
+                }
+            }
+            if (WITH_GX) {
+                __syncwarp();
+                if (active) {
+                    const float* src = tile + lane * NGLOD_KPAD + NGLOD_F;
+                    gx_out[0] = src[0] + gin[32]; gx_out[1] = src[1] + gin[33]; gx_out[2] = src[2] + gin[34];
+                    grad_x[3 * i] = gx_out[0]; grad_x[3 * i + 1] = gx_out[1]; grad_x[3 * i + 2] = gx_out[2];
+                }
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---- flush head gradients: registers -> CTA accumulator in smem -> one RED per CTA per element
+    __syncthreads();
+    float* cta_acc = smem + SDF_SMEM_WARP_OFF;       // per-warp regions are dead now
+    for (int e = threadIdx.x; e < BWD_ACC_FLOATS; e += blockDim.x) cta_acc[e] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const int j = lane + 32 * m;
+#pragma unroll
+        for (int k = 0; k < NGLOD_KPAD; ++k) atomicAdd(cta_acc + j * NGLOD_KPAD + k, accW0[m][k]);
+        atomicAdd(cta_acc + SDF_W0_FLOATS + j, accW1[m]);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        acc_b1 += __shfl_xor_sync(0xffffffffu, acc_b1, o);
+        acc_loss += __shfl_xor_sync(0xffffffffu, acc_loss, o);
+    }
+    if (lane == 0) {
+        atomicAdd(cta_acc + SDF_W0_FLOATS + NGLOD_H, acc_b1);
+        atomicAdd(cta_acc + SDF_W0_FLOATS + NGLOD_H + 1, acc_loss);
+    }
+    __syncthreads();
+    const int in_dim = net.pos_invariant ? NGLOD_F : NGLOD_F + 3;
+    for (int e = threadIdx.x; e < SDF_W0_FLOATS; e += blockDim.x) {
+        const int j = e / NGLOD_KPAD, k = e - j * NGLOD_KPAD;
+        const float v = cta_acc[e];
+        if (k < NGLOD_F) {
+            if (grad.w0) atomicAdd(grad.w0 + j * in_dim + (net.pos_invariant ? k : k + 3), v);
+        } else if (k < NGLOD_F + 3) {
+            if (grad.w0 && !net.pos_invariant) atomicAdd(grad.w0 + j * in_dim + (k - NGLOD_F), v);
+        } else {
+            if (grad.b0) atomicAdd(grad.b0 + j, v);
+        }
+    }
+    for (int e = threadIdx.x; e < NGLOD_H; e += blockDim.x)
+        if (grad.w1) atomicAdd(grad.w1 + e, cta_acc[SDF_W0_FLOATS + e]);
+    if (threadIdx.x == 0) {
+        if (grad.b1) atomicAdd(grad.b1, cta_acc[SDF_W0_FLOATS + NGLOD_H]);
+        if (FUSED_LOSS && loss_out) atomicAdd(loss_out, cta_acc[SDF_W0_FLOATS + NGLOD_H + 1]);
+    }
+}
+
+template <bool FUSED_LOSS, bool WITH_GX>
+int launch_backward(const nglod_net_t* net, int lod, const nglod_net_grad_t* grad, const float* x, int64_t n,
+                    const float* grad_out, const float* gt, float loss_scale, float* grad_x, float* loss_out,
+                    cudaStream_t st) {
+    auto kern = sdf_backward_kernel<FUSED_LOSS, WITH_GX>;
+    NGLOD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM_BYTES));
+    const NetDev nd = nglod_make_netdev(net, lod);
+    GradDev gdv;
+    for (int i = 0; i < NGLOD_MAX_LODS; ++i) gdv.grids[i] = (grad && i <= lod) ? grad->grids[i] : nullptr;
+    gdv.w0 = grad ? grad->w0[lod] : nullptr;
+    gdv.b0 = grad ? grad->b0[lod] : nullptr;
+    gdv.w1 = grad ? grad->w1[lod] : nullptr;
+    gdv.b1 = grad ? grad->b1[lod] : nullptr;
+    long long grid = nglod_sm_count();
+    const long long want = (n + SDF_THREADS - 1) / SDF_THREADS;
+    if (want < grid) grid = want;
+    kern<<<(int)grid, SDF_THREADS, BWD_SMEM_BYTES, st>>>(nd, gdv, x, (long long)n, grad_out, gt, loss_scale, grad_x,
+                                                         loss_out);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+extern "C" int nglod_sdf_backward(const nglod_net_t* net, int32_t lod, const float* x, int64_t n,
+                                  const float* grad_out, const nglod_net_grad_t* grad, float* grad_x,
+                                  void* stream) {
+    if (int e = nglod_check_net(net, lod)) return e;
+    if (n < 0 || (n > 0 && (!x || !grad_out))) return NGLOD_EINVAL;
+    if (n == 0) return 0;
+    for (int i = 0; grad && i <= lod; ++i)
+        if (grad->grids[i] && (reinterpret_cast<uintptr_t>(grad->grids[i]) & 15u)) return NGLOD_EINVAL;
+    if (grad_x)
+        return launch_backward<false, true>(net, lod, grad, x, n, grad_out, nullptr, 0.f, grad_x, nullptr,
+                                            (cudaStream_t)stream);
+    return launch_backward<false, false>(net, lod, grad, x, n, grad_out, nullptr, 0.f, nullptr, nullptr,
+                                         (cudaStream_t)stream);
+}
+
+extern "C" int nglod_sdf_train_step(const nglod_net_t* net, uint32_t lod_mask, const float* x, const float* gt,
+                                    int64_t n, float loss_scale, const nglod_net_grad_t* grad, float* loss_out,
+                                    void* stream) {
+    if (!net || !grad) return NGLOD_EINVAL;
+    if (n < 0 || (n > 0 && (!x || !gt))) return NGLOD_EINVAL;
+    if (n == 0) return 0;
+    for (int l = 0; l < net->num_lods; ++l) {
+        if (!(lod_mask & (1u << l))) continue;
+        if (int e = nglod_check_net(net, l)) return e;
+        for (int i = 0; i <= l; ++i)
+            if (grad->grids[i] && (reinterpret_cast<uintptr_t>(grad->grids[i]) & 15u)) return NGLOD_EINVAL;
+        if (int e = launch_backward<true, false>(net, l, grad, x, n, nullptr, gt, loss_scale, nullptr, loss_out,
+                                                 (cudaStream_t)stream))
+            return e;
+    }
+    return 0;
+}

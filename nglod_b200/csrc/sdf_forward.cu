@@ -1,0 +1,157 @@
+// nglod_b200 -- OctreeSDF.sdf forward, finite-difference gradient (FP32 path).
+// Reference behaviour: sdf-net/lib/models/OctreeSDF.py:94-155, sdf-net/lib/diffutils.py:61-70.
+#include "sdf_core.cuh"
+
+namespace {
+
+__device__ __forceinline__ void sdf_kernel_prologue(const NetDev& net, float* smem, float*& tile, int*& idx) {
+    sdf_stage_weights(net, smem);
+    const int warp = threadIdx.x >> 5;
+    float* wbase = smem + SDF_SMEM_WARP_OFF + warp * SDF_SMEM_PER_WARP;
+    for (int e = threadIdx.x & 31; e < SDF_SMEM_PER_WARP; e += 32) wbase[e] = 0.f;
+    tile = wbase;
+    idx = reinterpret_cast<int*>(wbase + SDF_TILE_FLOATS);
+    __syncthreads();
+}
+
+// Persistent: each warp strides over batches of 32 consecutive queries.
+__global__ void __launch_bounds__(SDF_THREADS, 2)
+sdf_forward_kernel(const NetDev net, const float* __restrict__ x, const long long n, float* __restrict__ out) {
+    extern __shared__ __align__(16) float smem[];
+    float* tile; int* idx;
+    sdf_kernel_prologue(net, smem, tile, idx);
+    const int lane = threadIdx.x & 31;
+    const long long gwarp = (long long)blockIdx.x * SDF_WARPS + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * SDF_WARPS;
+    for (long long base = gwarp * 32; base < n; base += nwarps * 32) {
+        const long long i = base + lane;
+        const bool active = i < n;
+        float px = 0.f, py = 0.f, pz = 0.f;
+        if (active) { px = __ldg(x + 3 * i); py = __ldg(x + 3 * i + 1); pz = __ldg(x + 3 * i + 2); }
+        const float d = warp_sdf_eval(net, smem, tile, idx, px, py, pz, active, lane);
+        if (active) out[i] = d;
+    }
+}
+
+// out[i,k] = (sdf(x_i + h e_k) - sdf(x_i - h e_k)) / (2h)
+__global__ void __launch_bounds__(SDF_THREADS, 2)
+sdf_finitediff_kernel(const NetDev net, const float* __restrict__ x, const long long n, const float h,
+                      float* __restrict__ out) {
+    extern __shared__ __align__(16) float smem[];
+    float* tile; int* idx;
+    sdf_kernel_prologue(net, smem, tile, idx);
+    const int lane = threadIdx.x & 31;
+    const long long gwarp = (long long)blockIdx.x * SDF_WARPS + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * SDF_WARPS;
+    const float two_h = 2.f * h;
+    for (long long base = gwarp * 32; base < n; base += nwarps * 32) {
+        const long long i = base + lane;
+        const bool active = i < n;
+        float p[3] = {0.f, 0.f, 0.f};
+        if (active) { p[0] = __ldg(x + 3 * i); p[1] = __ldg(x + 3 * i + 1); p[2] = __ldg(x + 3 * i + 2); }
+        float g[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            float q[3] = {p[0], p[1], p[2]};
+            q[k] = p[k] + h;
+            const float dp = warp_sdf_eval(net, smem, tile, idx, q[0], q[1], q[2], active, lane);
+            q[k] = p[k] - h;
+            const float dm = warp_sdf_eval(net, smem, tile, idx, q[0], q[1], q[2], active, lane);
+            g[k] = (dp - dm) / two_h;
+        }
+        if (active) { out[3 * i] = g[0]; out[3 * i + 1] = g[1]; out[3 * i + 2] = g[2]; }
+    }
+}
+
+// out[i, 0..31] = summed interpolated features (no decoder); no weights are staged.
+__global__ void __launch_bounds__(SDF_THREADS, 2)
+sdf_features_kernel(const NetDev net, const float* __restrict__ x, const long long n, float* __restrict__ out) {
+    extern __shared__ __align__(16) float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* tile = smem + SDF_SMEM_WARP_OFF + warp * SDF_SMEM_PER_WARP;
+    int* idx = reinterpret_cast<int*>(tile + SDF_TILE_FLOATS);
+    for (int e = lane; e < SDF_SMEM_PER_WARP; e += 32) tile[e] = 0.f;
+    __syncwarp();
+    const long long gwarp = (long long)blockIdx.x * SDF_WARPS + warp;
+    const long long nwarps = (long long)gridDim.x * SDF_WARPS;
+    for (long long base = gwarp * 32; base < n; base += nwarps * 32) {
+        const long long i = base + lane;
+        const bool active = i < n;
+        float px = 0.f, py = 0.f, pz = 0.f;
+        if (active) { px = __ldg(x + 3 * i); py = __ldg(x + 3 * i + 1); pz = __ldg(x + 3 * i + 2); }
+        warp_gather_tile(net, px, py, pz, active, tile, idx, lane);
+        if (active) {
+#pragma unroll
+            for (int k4 = 0; k4 < NGLOD_F / 4; ++k4)
+                *reinterpret_cast<float4*>(out + i * NGLOD_F + 4 * k4) =
+                    *reinterpret_cast<const float4*>(tile + lane * NGLOD_KPAD + 4 * k4);
+        }
+        __syncwarp();
+    }
+}
+
+int launch_grid(const void* kernel, long long n) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SDF_THREADS, SDF_SMEM_BYTES) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    const long long want = (n + SDF_THREADS - 1) / SDF_THREADS;
+    long long grid = (long long)nglod_sm_count() * per_sm;
+    if (want < grid) grid = want;
+    return (int)(grid < 1 ? 1 : grid);
+}
+
+}  // namespace
+
+extern "C" int nglod_sdf_forward(const nglod_net_t* net, int32_t lod, const float* x, int64_t n, float* out,
+                                 void* stream) {
+    if (int e = nglod_check_net(net, lod)) return e;
+    if (n < 0 || (n > 0 && (!x || !out))) return NGLOD_EINVAL;
+    if (n == 0) return 0;
+    NGLOD_CUDA_TRY(cudaFuncSetAttribute(sdf_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SDF_SMEM_BYTES));
+    const NetDev nd = nglod_make_netdev(net, lod);
+    const int grid = launch_grid((const void*)sdf_forward_kernel, n);
+    sdf_forward_kernel<<<grid, SDF_THREADS, SDF_SMEM_BYTES, (cudaStream_t)stream>>>(nd, x, (long long)n, out);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int nglod_sdf_forward_all(const nglod_net_t* net, const float* x, int64_t n, float* out, void* stream) {
+    if (!net) return NGLOD_EINVAL;
+    // One pass per head over the shared grids; heads differ in the LOD prefix they sum.
+    for (int l = 0; l < net->num_lods; ++l) {
+        if (int e = nglod_sdf_forward(net, l, x, n, out + (int64_t)l * n, stream)) return e;
+    }
+    return 0;
+}
+
+extern "C" int nglod_sdf_finitediff(const nglod_net_t* net, int32_t lod, const float* x, int64_t n, float h,
+                                    float* out, void* stream) {
+    if (int e = nglod_check_net(net, lod)) return e;
+    if (n < 0 || (n > 0 && (!x || !out))) return NGLOD_EINVAL;
+    if (n == 0) return 0;
+    NGLOD_CUDA_TRY(cudaFuncSetAttribute(sdf_finitediff_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SDF_SMEM_BYTES));
+    const NetDev nd = nglod_make_netdev(net, lod);
+    const int grid = launch_grid((const void*)sdf_finitediff_kernel, n);
+    sdf_finitediff_kernel<<<grid, SDF_THREADS, SDF_SMEM_BYTES, (cudaStream_t)stream>>>(nd, x, (long long)n, h, out);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int nglod_sdf_features(const nglod_net_t* net, int32_t lod, const float* x, int64_t n, float* out,
+                                  void* stream) {
+    if (!net || net->num_lods < 1 || net->num_lods > NGLOD_MAX_LODS || lod < 0 || lod >= net->num_lods) return NGLOD_EINVAL;
+    if (net->feature_dim != NGLOD_F) return NGLOD_EUNSUPPORTED;
+    if (n < 0 || (n > 0 && (!x || !out))) return NGLOD_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(out) & 15u) != 0) return NGLOD_EINVAL;
+    NetDev nd;
+    nd.num_lods = lod + 1; nd.pos_invariant = 0;
+    nd.w0 = nd.b0 = nd.w1 = nd.b1 = nullptr;
+    for (int i = 0; i < NGLOD_MAX_LODS; ++i) {
+        nd.res[i] = i <= lod ? net->grid_res[i] : 1;
+        nd.grids[i] = i <= lod ? net->grids[i] : nullptr;
+        if (i <= lod && (!nd.grids[i] || nd.res[i] < 1 || (reinterpret_cast<uintptr_t>(nd.grids[i]) & 15u))) return NGLOD_EINVAL;
+    }
+    if (n == 0) return 0;
+    NGLOD_CUDA_TRY(cudaFuncSetAttribute(sdf_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SDF_SMEM_BYTES));
+    const int grid = launch_grid((const void*)sdf_features_kernel, n);
+    sdf_features_kernel<<<grid, SDF_THREADS, SDF_SMEM_BYTES, (cudaStream_t)stream>>>(nd, x, (long long)n, out);
+    return (int)cudaGetLastError();
+}

@@ -1,0 +1,203 @@
+// nglod_b200 -- persistent-thread sphere tracer with the SDF evaluated inline.
+//
+// Behavioural spec: SphereTracer.forward, sdf-net/lib/tracer/SphereTracer.py:41-132,
+// restated as an independent per-ray state machine (the batch loop there has no
+// cross-ray coupling except a global early-out, which cannot change any ray's
+// result):
+//
+//   (x, t, live) = aabb(o, dir)                                   :53
+//   live:  d = dprev = sdf(x)                  [INIT]             :64-66
+//   for i in 0..num_steps-1:                                       :74
+//       flag  = |t| < far                                          :84
+//       live &= |d| > min_dis  &  |(d+dprev)/2| > 3*min_dis & flag :87-93
+//       live:  x = o + dir*t ; dprev = d                           :102-105
+//              d = sdf(x)*step_size ; t += d   [MARCH]             :109-114
+//   hit = flag & all(|x| <= 1)                                     :119
+//   hit:   normal = normalize(finitediff(x), eps=1e-5)  [N0..N5]   :128-130
+//
+// One warp = 32 ray slots.  Every round each occupied slot contributes one
+// query point (march position or one of the six normal taps); the warp
+// evaluates them cooperatively (sdf_core.cuh), each lane consumes its value
+// and advances its state machine.  Finished slots are refilled from a global
+// atomic queue (ballot + popc ranks), so lanes stay occupied until the frame
+// runs dry: no host round trip, no per-step launches, no cond.any() sync.
+#include "sdf_core.cuh"
+#include "aabb.cuh"
+
+namespace {
+
+enum : int { PH_EMPTY = 0, PH_INIT = 1, PH_MARCH = 2, PH_N0 = 3 };   // PH_N0..PH_N0+5: normal taps
+
+struct TraceParams {
+    int num_steps;
+    int compute_normals;
+    float step_size, min_dis, min_dis3, far, h, two_h;
+};
+
+__global__ void __launch_bounds__(SDF_THREADS, 2)
+sphere_trace_kernel(const NetDev net, const float* __restrict__ ray_o, const float* __restrict__ ray_d,
+                    const long long n, const TraceParams tp, float* __restrict__ out_x,
+                    float* __restrict__ out_t, uint8_t* __restrict__ out_hit, float* __restrict__ out_n,
+                    int* __restrict__ queue, unsigned long long* __restrict__ stats) {
+    extern __shared__ __align__(16) float smem[];
+    sdf_stage_weights(net, smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* tile = smem + SDF_SMEM_WARP_OFF + warp * SDF_SMEM_PER_WARP;
+    int* idx = reinterpret_cast<int*>(tile + SDF_TILE_FLOATS);
+    for (int e = lane; e < SDF_SMEM_PER_WARP; e += 32) tile[e] = 0.f;
+    __syncthreads();
+
+    // per-lane ray slot
+    int phase = PH_EMPTY, step = 0;
+    long long ray = -1;
+    float ox = 0.f, oy = 0.f, oz = 0.f, dx = 0.f, dy = 0.f, dz = 0.f;
+    float x = 0.f, y = 0.f, z = 0.f, t = 0.f, d = 0.f, dprev = 0.f;
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f, gtmp = 0.f;
+    bool flag = false;
+    bool exhausted = false;                     // warp-uniform: the queue has run past n
+    unsigned long long n_eval = 0, n_march = 0; // lane 0 only
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    auto retire = [&](bool hit, float nx, float ny, float nz) {
+        out_x[3 * ray] = x; out_x[3 * ray + 1] = y; out_x[3 * ray + 2] = z;
+        out_t[ray] = t;
+        out_hit[ray] = hit ? 1 : 0;
+        out_n[3 * ray] = nx; out_n[3 * ray + 1] = ny; out_n[3 * ray + 2] = nz;
+        phase = PH_EMPTY;
+    };
+    auto finish_march = [&]() {
+        const bool outside = (fabsf(x) > 1.0f) || (fabsf(y) > 1.0f) || (fabsf(z) > 1.0f);
+        const bool hit = flag && !outside;
+        if (hit && tp.compute_normals) phase = PH_N0;
+        else retire(hit, 0.f, 0.f, 0.f);
+    };
+    auto march_check = [&](bool live) {
+        if (step < tp.num_steps) {
+            flag = fabsf(t) < tp.far;
+            live = live && (fabsf(d) > tp.min_dis) && (fabsf((d + dprev) * 0.5f) > tp.min_dis3) && flag;
+            if (live) {
+                // torch.addcmul(ray_o, ray_d, t): product rounded, then added (no fma)
+                x = __fadd_rn(ox, __fmul_rn(dx, t));
+                y = __fadd_rn(oy, __fmul_rn(dy, t));
+                z = __fadd_rn(oz, __fmul_rn(dz, t));
+                dprev = d;
+                phase = PH_MARCH;
+                return;
+            }
+        }
+        finish_march();
+    };
+
+    for (;;) {
+        // ---- refill empty slots from the global queue
+#pragma unroll 1
+        for (int attempt = 0; attempt < 4 && !exhausted; ++attempt) {
+            const unsigned free_mask = __ballot_sync(0xffffffffu, phase == PH_EMPTY);
+            if (!free_mask) break;
+            const int nfree = __popc(free_mask);
+            int base = 0;
+            if (lane == 0) base = atomicAdd(queue, nfree);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if ((long long)base + nfree >= n) exhausted = true;
+            if (phase == PH_EMPTY) {
+                const long long i = (long long)base + __popc(free_mask & lt_mask);
+                if (i < n) {
+                    ray = i;
+                    ox = __ldg(ray_o + 3 * i); oy = __ldg(ray_o + 3 * i + 1); oz = __ldg(ray_o + 3 * i + 2);
+                    dx = __ldg(ray_d + 3 * i); dy = __ldg(ray_d + 3 * i + 1); dz = __ldg(ray_d + 3 * i + 2);
+                    const AabbResult r = ray_unit_cube(ox, oy, oz, dx, dy, dz);
+                    x = r.x; y = r.y; z = r.z; t = r.t;
+                    step = 0; flag = false; d = 0.f; dprev = 0.f;
+                    if (r.hit) phase = PH_INIT;
+                    else march_check(false);      // never marched: retire now or go take normals
+                }
+            }
+        }
+        const bool occupied = phase != PH_EMPTY;
+        const unsigned act = __ballot_sync(0xffffffffu, occupied);
+        if (!act) {
+            if (exhausted) break;
+            continue;
+        }
+        // ---- this round's query point
+        float qx = x, qy = y, qz = z;
+        if (phase >= PH_N0) {
+            const int m = phase - PH_N0;
+            const float e = (m & 1) ? -tp.h : tp.h;
+            const int axis = m >> 1;
+            if (axis == 0) qx = x + e; else if (axis == 1) qy = y + e; else qz = z + e;
+        }
+        const float dv = warp_sdf_eval(net, smem, tile, idx, qx, qy, qz, occupied, lane);
+        const unsigned march_mask = __ballot_sync(0xffffffffu, phase == PH_MARCH);
+        if (lane == 0) {
+            n_eval += __popc(act);
+            n_march += __popc(march_mask);
+        }
+        // ---- advance the state machines
+        if (phase == PH_INIT) {
+            d = dv; dprev = dv; step = 0;
+            march_check(true);
+        } else if (phase == PH_MARCH) {
+            d = dv * tp.step_size;
+            t = t + d;
+            ++step;
+            march_check(true);
+        } else if (phase >= PH_N0) {
+            const int m = phase - PH_N0;
+            if ((m & 1) == 0) {
+                gtmp = dv;
+                phase = phase + 1;
+            } else {
+                const float g = (gtmp - dv) / tp.two_h;
+                if (m == 1) g0 = g; else if (m == 3) g1 = g; else g2 = g;
+                if (m == 5) {
+                    // F.normalize(grad, p=2, dim=-1, eps=1e-5)
+                    const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(g0, g0), __fmul_rn(g1, g1)), __fmul_rn(g2, g2)));
+                    const float den = fmaxf(nrm, 1e-5f);
+                    retire(true, g0 / den, g1 / den, g2 / den);
+                } else {
+                    phase = phase + 1;
+                }
+            }
+        }
+    }
+    if (stats && lane == 0) {
+        atomicAdd(stats, n_eval);
+        atomicAdd(stats + 1, n_march);
+    }
+}
+
+}  // namespace
+
+extern "C" int nglod_sphere_trace(const nglod_net_t* net, int32_t lod, const float* ray_o, const float* ray_d,
+                                  int64_t n, const nglod_trace_opts_t* opts, float* x, float* depth,
+                                  uint8_t* hit, float* normal, int32_t* queue, unsigned long long* stats,
+                                  void* stream) {
+    if (int e = nglod_check_net(net, lod)) return e;
+    if (!opts || n < 0 || n > 2000000000ll) return NGLOD_EINVAL;
+    if (n == 0) return 0;
+    if (!ray_o || !ray_d || !x || !depth || !hit || !normal || !queue) return NGLOD_EINVAL;
+    if (opts->num_steps < 0) return NGLOD_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    NGLOD_CUDA_TRY(cudaFuncSetAttribute(sphere_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SDF_SMEM_BYTES));
+    NGLOD_CUDA_TRY(cudaMemsetAsync(queue, 0, sizeof(int32_t), st));
+    TraceParams tp;
+    tp.num_steps = opts->num_steps;
+    tp.compute_normals = opts->compute_normals;
+    tp.step_size = (float)opts->step_size;
+    tp.min_dis = (float)opts->min_dis;
+    tp.min_dis3 = (float)(opts->min_dis * 3.0);      // torch: tensor > (python float * 3) -> float32(min_dis*3)
+    tp.far = (float)opts->far;
+    tp.h = (float)opts->normal_h;
+    tp.two_h = (float)(opts->normal_h * 2.0);
+    const NetDev nd = nglod_make_netdev(net, lod);
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sphere_trace_kernel, SDF_THREADS, SDF_SMEM_BYTES) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    long long grid = (long long)nglod_sm_count() * per_sm;
+    const long long want = (n + SDF_THREADS - 1) / SDF_THREADS;
+    if (want < grid) grid = want;
+    sphere_trace_kernel<<<(int)grid, SDF_THREADS, SDF_SMEM_BYTES, st>>>(nd, ray_o, ray_d, (long long)n, tp, x, depth,
+                                                                        hit, normal, queue, stats);
+    return (int)cudaGetLastError();
+}

@@ -1,0 +1,85 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink on the box, gloo in CPU tests).
+
+The hot path shards trivially: every query, ray and training point is independent and the
+40 MB model is replicated.  So:
+  * queries / rays  -> contiguous ranges per rank, NO data-path collective; an optional final gather of results;
+    rays are x-major (ray = ix*H + iy), so a contiguous ray range is a vertical strip of the image;
+  * training        -> each rank takes its slice of the point batch, runs the fused step with the loss scaled by
+    the GLOBAL batch, then ONE all-reduce(sum) over the flat fp32 gradient buffer (40.6 MB), replicated Adam.
+The reference has no distributed code at all, so nothing here replaces reference lines.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def env_rank_world():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def init_from_env(backend=None):
+    """Initialise the default process group from torchrun's environment (no-op for world size 1)."""
+    rank, world, local = env_rank_world()
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kw = {}
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            kw["device_id"] = torch.device("cuda", local)
+        dist.init_process_group(backend=backend, **kw)
+    return rank, world, local
+
+
+def shard_range(n, rank, world, align=1):
+    """[start, end) of the contiguous shard `rank` of `n` items; boundaries are multiples of `align`
+    (use align=H to cut an x-major image on column boundaries).  Shards differ by at most one `align` unit."""
+    units = (n + align - 1) // align
+    base, rem = divmod(units, world)
+    u0 = rank * base + min(rank, rem)
+    u1 = u0 + base + (1 if rank < rem else 0)
+    return min(u0 * align, n), min(u1 * align, n)
+
+
+def interleaved_strips(n_cols, rank, world, strips_per_rank=4):
+    """Column ranges for load-balanced rendering: the image is cut into world*strips_per_rank vertical strips
+    dealt round-robin, so a rank gets both silhouette-heavy and empty regions.  Returns [(c0, c1), ...]."""
+    total = min(n_cols, world * strips_per_rank)
+    out = []
+    for s in range(rank, total, world):
+        c0, c1 = shard_range(n_cols, s, total)
+        if c1 > c0:
+            out.append((c0, c1))
+    return out
+
+
+def allreduce_sum_(flat):
+    """In-place sum over ranks of one flat buffer (the whole gradient in a single bucket)."""
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    return flat
+
+
+def gather_shards(local, n_total, rank, world, dst=0, align=1):
+    """Gather contiguous shards (as cut by shard_range) to rank `dst`; returns the full tensor there, else None.
+    Shards may differ in length, so they are padded to the longest and trimmed after the gather."""
+    if world == 1 or not dist.is_initialized():
+        return local
+    sizes = [shard_range(n_total, r, world, align) for r in range(world)]
+    longest = max(e - s for s, e in sizes)
+    pad = torch.zeros((longest,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    bufs = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+    dist.gather(pad, bufs, dst=dst)
+    if rank != dst:
+        return None
+    return torch.cat([b[: e - s] for b, (s, e) in zip(bufs, sizes)], dim=0)
+
+
+def max_over_ranks(value, device):
+    """Max of a python float over ranks (used for device-timed durations)."""
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())

@@ -1,0 +1,130 @@
+"""OctreeSDF -- the reference's public model class (sdf-net/lib/models/OctreeSDF.py:59-155)
+on top of the fused sm_100a kernels.
+
+Same constructor arguments, parameter names, shapes and init order as the
+reference (`features.{i}.fm` [1,F,R+1,R+1,R+1] with R = 2^(i+base_lod) drawn as
+randn*0.01, then `louts.{i}` = Linear(3+F,H)-ReLU-Linear(H,1)), so a reference
+checkpoint loads unchanged and the same seed gives the same weights.  What is
+different is how it runs: the grids are kept in torch.channels_last_3d memory
+format (one corner = one 128-byte line) and `sdf()` is ONE fused kernel
+(multi-LOD trilinear gather + running sum + decoder), with a recompute-based
+backward -- instead of the per-LOD grid_sample / cat / Linear launch chain.
+"""
+import torch
+import torch.nn as nn
+from torch.autograd.function import once_differentiable
+
+from .BaseLOD import BaseLOD
+from ... import ops
+
+
+class FeatureVolume(nn.Module):
+    """Dense (fsize+1)^3 x fdim feature grid (reference: OctreeSDF.py:38-57)."""
+
+    def __init__(self, fdim, fsize):
+        super().__init__()
+        self.fsize = fsize
+        self.fdim = fdim
+        fm = torch.randn(1, fdim, fsize + 1, fsize + 1, fsize + 1) * 0.01
+        self.fm = nn.Parameter(fm.contiguous(memory_format=torch.channels_last_3d))
+        self.sparse = None
+
+    def _apply(self, fn, *a, **kw):
+        out = super()._apply(fn, *a, **kw)
+        if not self.fm.data.is_contiguous(memory_format=torch.channels_last_3d):
+            self.fm.data = self.fm.data.contiguous(memory_format=torch.channels_last_3d)
+        return out
+
+    def forward(self, x):
+        """Trilinear sample of this LOD alone: [N,3] -> [N,fdim] ([N,K,3] -> [N,K,fdim])."""
+        view = ops.NetView.grids_only([self.fm.data])
+        return ops.sdf_features(view, 0, x.reshape(-1, 3)).reshape(*x.shape[:-1], self.fdim)
+
+
+class _SdfFunction(torch.autograd.Function):
+    """d = sdf(x, lod); backward recomputes the forward in-kernel (no saved activations)."""
+
+    @staticmethod
+    def forward(ctx, x, module, lod, *params):
+        view = module.net_view()
+        ctx.module, ctx.lod = module, lod
+        ctx.save_for_backward(x)
+        return ops.sdf_forward(view, lod, x)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_out):
+        (x,) = ctx.saved_tensors
+        module, lod = ctx.module, ctx.lod
+        view = module.net_view()
+        needs = ctx.needs_input_grad
+        n_grids = lod + 1
+        grid_grads = [torch.zeros_like(module.features[i].fm, memory_format=torch.preserve_format)
+                      if needs[3 + i] else None for i in range(n_grids)]
+        dec_params = module.decoder_params(lod)
+        dec_grads = [torch.zeros_like(p) if needs[3 + n_grids + k] else None for k, p in enumerate(dec_params)]
+        gx = ops.sdf_backward(view, lod, x, grad_out.contiguous(), grid_grads + [None] * (view.num_lods - n_grids),
+                              tuple(dec_grads), want_grad_x=needs[0])
+        return (gx, None, None, *grid_grads, *dec_grads)
+
+
+class OctreeSDF(BaseLOD):
+    def __init__(self, args, init=None):
+        super().__init__(args)
+        self.fdim = self.args.feature_dim
+        self.fsize = self.args.feature_size
+        self.hidden_dim = self.args.hidden_dim
+        self.pos_invariant = self.args.pos_invariant
+
+        self.features = nn.ModuleList(
+            [FeatureVolume(self.fdim, 2 ** (i + self.args.base_lod)) for i in range(self.args.num_lods)])
+        self.interpolate = self.args.interpolate
+
+        self.sdf_input_dim = self.fdim + (0 if self.pos_invariant else self.input_dim)
+        self.num_decoder = 1 if args.joint_decoder else self.args.num_lods
+        self.louts = nn.ModuleList([
+            nn.Sequential(nn.Linear(self.sdf_input_dim, self.hidden_dim, bias=True), nn.ReLU(),
+                          nn.Linear(self.hidden_dim, 1, bias=True))
+            for _ in range(self.num_decoder)])
+
+    # ------------------------------------------------------------------ kernel plumbing
+    def decoder_params(self, lod):
+        seq = self.louts[0 if self.num_decoder == 1 else lod]
+        return (seq[0].weight, seq[0].bias, seq[2].weight, seq[2].bias)
+
+    def net_view(self):
+        """Borrow the current parameters as an nglod_net_t (rebuilt per call: pointers may move)."""
+        grids = [f.fm.data for f in self.features]
+        decs = [tuple(p.data for p in self.decoder_params(i)) for i in range(self.num_lods)]
+        return ops.NetView(grids, decs, pos_invariant=self.pos_invariant)
+
+    def _eval_lod(self, x, lod):
+        shape = x.shape
+        x2 = x.reshape(-1, 3)
+        if x2.dtype != torch.float32:
+            x2 = x2.float()
+        if torch.is_grad_enabled() and (x2.requires_grad or any(p.requires_grad for p in self.parameters())):
+            params = [self.features[i].fm for i in range(lod + 1)] + list(self.decoder_params(lod))
+            d = _SdfFunction.apply(x2, self, lod, *params)
+        else:
+            d = ops.sdf_forward(self.net_view(), lod, x2)
+        return d.reshape(*shape[:-1], 1)
+
+    # ------------------------------------------------------------------ reference API
+    def encode(self, x):
+        return x   # encoding is disabled for OctreeSDF (OctreeSDF.py:90-92)
+
+    def sdf(self, x, lod=None, return_lst=False):
+        """Reference semantics (OctreeSDF.py:94-155): with an integer lod return that head's
+        distance [N,1]; with lod None (and self.lod None) evaluate every head, stash them in
+        `loss_preds` while training, and return the list or its last element."""
+        if lod is None:
+            lod = self.lod
+        if self.interpolate is not None and lod is not None:
+            raise NotImplementedError("--interpolate is broken in the reference (NameError at OctreeSDF.py:138)")
+        if lod is not None and 0 <= lod < self.num_lods:
+            return self._eval_lod(x, lod)
+        preds = [self._eval_lod(x, i) for i in range(self.num_lods)]
+        if self.training:
+            self.loss_preds = preds
+        return preds if return_lst else preds[-1]

@@ -1,0 +1,201 @@
+"""Renderer -- the reference's orchestration class (sdf-net/lib/renderer.py:40-331) over the
+fused tracer.  Public surface kept: ctor(tracer, args=None, **kwargs), render_lookat, render,
+shade_tensor, shade_images, sdf_slice / normal_slice / sdf_grad_slice; output layout (W,H,C).
+
+Differences from the reference are confined to where work runs, not what is computed:
+matcap lookup, the shadow-map blur and AO all stay on the device (the reference bounces through
+numpy/scipy on the host, renderer.py:279-305), and the 40 AO taps are evaluated on the compacted
+hit set with the fused SDF kernel.
+"""
+import time
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from .utils import PerfTimer, setparam
+from .diffutils import gradient
+from .geoutils import look_at, spherical_envmap, matcap_sampler, procedural_matcap, normalized_slice, \
+    gaussian_blur2d
+from .tracer import RenderBuffer
+
+
+class Renderer():
+    def __init__(self, tracer, args=None, render_res=None, camera_clamp=None, camera_proj=None,
+                 render_batch=None, shading_mode=None, matcap_path=None, shadow=None, ao=None, perf=None,
+                 device=None, ground_height=None):
+        self.args = args
+        self.tracer = tracer
+        self.camera_clamp = tracer.camera_clamp
+        self.render_res = setparam(args, render_res, "render_res")
+        self.camera_proj = setparam(args, camera_proj, "camera_proj")
+        self.render_batch = setparam(args, render_batch, "render_batch") or 0
+        self.shading_mode = setparam(args, shading_mode, "shading_mode")
+        self.matcap_path = setparam(args, matcap_path, "matcap_path")
+        self.shadow = setparam(args, shadow, "shadow")
+        self.ao = setparam(args, ao, "ao")
+        self.perf = setparam(args, perf, "perf")
+        self.device = setparam(args, device, "device")
+        if self.device is None:
+            self.device = "cuda"
+        self.width, self.height = self.render_res
+        self._matcap = None
+        if self.shadow:
+            gh = setparam(args, ground_height, "ground_height")
+            if not gh:
+                # the reference falls into an undefined `self.sdf_net` here (renderer.py:81)
+                raise ValueError("--shadow needs a non-zero --ground-height")
+            self.min_y = gh
+
+    # ------------------------------------------------------------------ camera
+    def render_lookat(self, net, f=[0, 0, 1], t=[0, 0, 0], fov=30.0, camera_proj="persp", device=None, mm=None):
+        device = device or self.device
+        ray_o, ray_d = look_at(f, t, self.width, self.height, fov=fov, mode=camera_proj, device=device)
+        if mm is not None:
+            mm = mm.to(ray_o.device)
+            ray_o = torch.mm(ray_o, mm)
+            ray_d = torch.mm(ray_d, mm)
+        return self.render(net, ray_o, ray_d)
+
+    # ------------------------------------------------------------------ trace + secondary passes
+    def _trace(self, net, ray_o, ray_d):
+        if self.render_batch > 0:
+            rb = RenderBuffer()
+            for o, d in zip(torch.split(ray_o, self.render_batch), torch.split(ray_d, self.render_batch)):
+                rb += self.tracer(net, o, d)
+            return rb
+        return self.tracer(net, ray_o, ray_d)
+
+    def render(self, net, ray_o, ray_d):
+        timer = PerfTimer(activate=bool(self.perf))
+        t0 = time.time()
+        with torch.no_grad():
+            rb = self._trace(net, ray_o, ray_d)
+            timer.check("trace")
+
+            plane_hit = None
+            if self.shadow:
+                # ground plane y = min_y, then a second trace towards the light (renderer.py:131-161)
+                rate = -ray_d[:, 1]
+                plane_t = (ray_o[:, 1] - self.min_y) / rate
+                plane_hit = (plane_t > 0) & (plane_t < 500) & (plane_t < rb.depth[..., 0])
+                rb.hit = rb.hit & ~plane_hit
+                rb.depth[plane_hit] = plane_t[plane_hit].unsqueeze(1)
+                rb.x[plane_hit] = ray_o[plane_hit] + ray_d[plane_hit] * plane_t[plane_hit].unsqueeze(1)
+                rb.normal[plane_hit] = 0
+                rb.normal[plane_hit, 1] = 1
+
+                light_o = torch.tensor([[-1.5, 4.5, -1.5]], device=ray_o.device)
+                s_o = rb.x + 0.1 * rb.normal
+                s_d = F.normalize(torch.zeros_like(rb.x).normal_(0.0, 0.01) + light_o - s_o, dim=1)
+                lit = (s_d * rb.normal).sum(-1) > 0.0
+                rb.shadow = self.tracer(net, s_o, s_d).hit
+                rb.shadow[~lit] = 0
+                timer.check("shadow")
+
+            rb.relative_depth = torch.clamp(rb.depth, 0.0, self.camera_clamp[1]) / self.camera_clamp[1]
+
+            if self.shading_mode == "rb" and rb.rgb is None:
+                rb.rgb = net.render(rb.x, ray_d, F.normalize(rb.normal))[..., :3]
+
+            if self.ao:
+                rb.ao = self._ambient_occlusion(net, rb, plane_hit)
+                timer.check("ao")
+
+        rb.view = ray_d
+        rb = rb.reshape(self.width, self.height, -1)
+        if self.perf:
+            print("Time Elapsed:{:.4f}".format(time.time() - t0))
+        return rb
+
+    def _ambient_occlusion(self, net, rb, plane_hit):
+        """40 taps along the normal (renderer.py:184-209), on the compacted hit / ground sets."""
+        acc = torch.zeros_like(rb.depth)
+        hit_idx = rb.hit.nonzero(as_tuple=True)[0]
+        xs, ns = rb.x[hit_idx], rb.normal[hit_idx]
+        acc_h = torch.zeros(hit_idx.shape[0], 1, device=acc.device)
+        if plane_hit is not None:
+            p_idx = plane_hit.nonzero(as_tuple=True)[0]
+            xp, np_ = rb.x[p_idx], rb.normal[p_idx]
+            acc_p = torch.zeros(p_idx.shape[0], 1, device=acc.device)
+        for i in range(40):
+            _d = 0.1 * 0.25 * (float(i + 1) / float(40 + 1)) ** 1.6
+            if hit_idx.numel():
+                acc_h += 3.5 * F.relu(_d - net(xs + ns * _d) - 0.0015)
+            if plane_hit is not None and p_idx.numel():
+                r = torch.minimum(net(xp + np_ * _d), torch.full_like(acc_p, _d))
+                acc_p += 3.5 * F.relu(_d - r - 0.0015)
+        acc[hit_idx] = acc_h
+        if plane_hit is not None:
+            acc[p_idx] = acc_p
+        ao = torch.clamp(1.0 - acc, 0.1, 1.0)
+        return ao * ao
+
+    # ------------------------------------------------------------------ shading
+    def _get_matcap(self, device):
+        if self._matcap is None:
+            try:
+                self._matcap = matcap_sampler(self.matcap_path, device=device)
+            except (FileNotFoundError, TypeError, AttributeError):
+                self._matcap = procedural_matcap(device=device)     # no assets ship with the repo
+        return self._matcap
+
+    def shade_tensor(self, net, f=[0, 0, 1], t=[0, 0, 0], fov=30.0, mm=None):
+        rb = self.render_lookat(net, f=f, t=t, fov=fov, mm=mm)
+        if self.shading_mode == "matcap":
+            view = rb.view.clone()
+            if mm is not None:
+                mm = mm.to(view.device)
+                view = torch.mm(view.reshape(-1, 3), mm.transpose(1, 0)).reshape(self.width, self.height, 3)
+            uv = spherical_envmap(view, rb.normal.clone())
+            rb.rgb = self._get_matcap(uv.device)(uv).reshape(self.width, self.height, -1)[..., :3] / 255.0
+        elif self.shading_mode == "rb":
+            assert rb.rgb is not None, "No rgb in buffer; change shading-mode"
+        else:
+            raise NotImplementedError
+        miss = ~rb.hit[..., 0]
+        rb.normal[miss] = 1.0
+        rb.rgb[miss] = 1.0
+        if self.shadow:
+            smap = torch.clamp(1.0 - rb.shadow.float() + 0.9, 0.0, 1.0)[..., 0]
+            rb.rgb[..., :3] *= gaussian_blur2d(smap, 2.0).unsqueeze(-1)
+        if self.ao:
+            rb.rgb[..., :3] *= rb.ao
+        return rb
+
+    def shade_images(self, net, f=[0, 0, 1], t=[0, 0, 0], fov=30.0, aa=1, mm=None):
+        """Returns a CPU RenderBuffer laid out (H,W,C).  As in the reference, `aa` only multisamples
+        when it is an int > 1 (sdf_renderer.py passes a bool, so the stock app never does)."""
+        if mm is None:
+            mm = torch.eye(3)
+        if aa > 1:
+            rb = RenderBuffer.mean(*[self.shade_tensor(net, f=f, t=t, fov=fov, mm=mm) for _ in range(aa)])
+        else:
+            rb = self.shade_tensor(net, f=f, t=t, fov=fov, mm=mm)
+        return rb.cpu().transpose()
+
+    # ------------------------------------------------------------------ 2-D slices
+    def sdf_slice(self, net, dim=0, depth=0):
+        pts = normalized_slice(self.width, self.height, dim=dim, depth=depth, device=self.device)
+        with torch.no_grad():
+            d = net.sdf(pts.reshape(-1, 3)).reshape(self.width, self.height).cpu().numpy()
+        d = np.clip((d + 1.0) / 2.0, 0.0, 1.0)
+        blue = np.clip((d - 0.5) * 2.0, 0.0, 1.0)
+        vis = np.zeros([*d.shape, 3])
+        vis[..., 2] = blue
+        vis += (1.0 - blue)[..., None] * np.array([0.4, 0.3, 0.0]) + 0.2
+        vis[d - 0.5 < 0] = np.array([1.0, 0.38, 0.0])
+        for i in range(50):
+            vis[np.abs(d - 0.02 * i) < 0.0015] = 0.8
+        vis[np.abs(d - 0.5) < 0.004] = 0.0
+        return vis
+
+    def normal_slice(self, net, dim=0, depth=0.0):
+        pts = normalized_slice(self.width, self.height, dim=dim, depth=depth, device=self.device).reshape(-1, 3)
+        n = (F.normalize(gradient(pts, net, method="finitediff").detach()) + 1.0) / 2.0
+        return n.reshape(self.width, self.height, 3).cpu().numpy()
+
+    def sdf_grad_slice(self, net, dim=0, depth=0):
+        pts = normalized_slice(self.width, self.height, dim=dim, depth=depth, device=self.device)
+        g = gradient(pts.reshape(-1, 3), net, method="finitediff").detach()
+        return g.norm(2, dim=-1).reshape(self.width, self.height, 1).cpu().numpy()

@@ -1,0 +1,100 @@
+"""RenderBuffer -- the tracer/renderer result container.
+
+Same twelve optional tensor fields, in the same order, and the same operations
+as the reference (sdf-net/lib/tracer/RenderBuffer.py:28-139): iteration yields
+the fields, `a + b` concatenates field-wise along dim 0 (a missing side passes
+the other through), `reshape/transpose/cpu/cuda/float/byte/numpy/detach` map
+over the present fields, `image()` builds the 8-bit-range preview buffers and
+`mean()` averages a list of buffers.
+"""
+from dataclasses import dataclass, fields
+from typing import Optional
+
+import torch
+
+
+@dataclass
+class RenderBuffer:
+    x: Optional[torch.Tensor] = None
+    min_x: Optional[torch.Tensor] = None
+    hit: Optional[torch.Tensor] = None
+    depth: Optional[torch.Tensor] = None
+    relative_depth: Optional[torch.Tensor] = None
+    normal: Optional[torch.Tensor] = None
+    rgb: Optional[torch.Tensor] = None
+    shadow: Optional[torch.Tensor] = None
+    ao: Optional[torch.Tensor] = None
+    view: Optional[torch.Tensor] = None
+    err: Optional[torch.Tensor] = None
+    albedo: Optional[torch.Tensor] = None
+
+    # -- structure
+    def _names(self):
+        return [f.name for f in fields(self)]
+
+    def __iter__(self):
+        return (getattr(self, n) for n in self._names())
+
+    def _apply(self, fn):
+        return type(self)(**{n: (None if getattr(self, n) is None else fn(getattr(self, n))) for n in self._names()})
+
+    def __add__(self, other):
+        merged = {}
+        for n in self._names():
+            a, b = getattr(self, n), getattr(other, n)
+            merged[n] = torch.cat((a, b)) if (a is not None and b is not None) else (a if a is not None else b)
+        return type(self)(**merged)
+
+    # -- element-wise maps
+    def cuda(self):
+        return self._apply(lambda t: t.cuda())
+
+    def cpu(self):
+        return self._apply(lambda t: t.cpu())
+
+    def detach(self):
+        return self._apply(lambda t: t.detach())
+
+    def byte(self):
+        return self._apply(lambda t: t.byte())
+
+    def float(self):
+        return self._apply(lambda t: t.float())
+
+    def numpy(self):
+        return self._apply(lambda t: t.numpy())
+
+    def reshape(self, *dims):
+        return self._apply(lambda t: t.reshape(*dims))
+
+    def transpose(self):
+        """(W,H,C) -> (H,W,C)"""
+        return self._apply(lambda t: t.permute(1, 0, 2))
+
+    # -- export helpers
+    def exrdict(self):
+        out = {n: getattr(self, n) for n in self._names() if getattr(self, n) is not None}
+        if "rgb" in out:
+            out["default"] = out.pop("rgb")
+        return out
+
+    def image(self):
+        """hit / relative depth replicated to 3 channels, normal mapped to [0,1], all scaled by 255."""
+        def grey(t):
+            return None if t is None else torch.cat([t, t, t], dim=-1) * 255.0
+        normal = None if self.normal is None else (self.normal + 1.0) / 2.0 * 255.0
+        rgb = None if self.rgb is None else self.rgb * 255.0
+        return type(self)(hit=grey(self.hit), normal=normal, rgb=rgb, depth=grey(self.relative_depth))
+
+    @staticmethod
+    def mean(*rblst):
+        count = float(len(rblst))
+        acc = RenderBuffer()
+        for rb in rblst:
+            for n in acc._names():
+                v, cur = getattr(rb, n), getattr(acc, n)
+                if cur is None:
+                    setattr(acc, n, v)
+                elif v is not None:
+                    setattr(acc, n, cur + v)
+        return acc._apply(lambda t: t / count)

@@ -1,0 +1,233 @@
+"""Torch-facing wrappers over the C ABI (include/nglod_b200.h).
+
+PyTorch here is plumbing only: it owns device memory and the stream; every op
+below hands raw pointers to a hand-written sm_100a kernel.  Outputs are
+allocated the way the reference extensions allocate theirs (new tensors on the
+inputs' device; sol_nglod_kernel.cu:167-173, mesh2sdf_kernel.cu:901-906).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import NetStruct, NetGradStruct, TraceOpts, MAX_LODS
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _f32c(t, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor -- nglod_b200 has no CPU path")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+class NetView:
+    """A borrowed view of an OctreeSDF's parameters as an nglod_net_t.
+
+    grids: list of [1, F, R+1, R+1, R+1] tensors in channels_last_3d memory
+    format (i.e. physically [z, y, x, F]); decoders: list of (w0, b0, w1, b1).
+    Keeps the tensors alive for as long as the view is.
+    """
+
+    def __init__(self, grids, decoders, pos_invariant=False):
+        self.grids = grids
+        self.decoders = decoders
+        n = len(grids)
+        if n < 1 or n > MAX_LODS:
+            raise RuntimeError(f"num_lods must be in [1, {MAX_LODS}]")
+        s = NetStruct()
+        s.num_lods = n
+        s.feature_dim = grids[0].shape[1]
+        s.hidden_dim = decoders[0][0].shape[0]
+        s.pos_invariant = 1 if pos_invariant else 0
+        for i, g in enumerate(grids):
+            if not g.is_cuda:
+                raise RuntimeError("OctreeSDF parameters must live on a CUDA device (no CPU path)")
+            if g.dtype != torch.float32 or not g.is_contiguous(memory_format=torch.channels_last_3d):
+                raise RuntimeError("feature grids must be fp32 in torch.channels_last_3d memory format")
+            s.grid_res[i] = g.shape[-1] - 1
+            s.grids[i] = g.data_ptr()
+        for i in range(n):
+            w0, b0, w1, b1 = decoders[i if len(decoders) > 1 else 0]
+            for t in (w0, b0, w1, b1):
+                if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                    raise RuntimeError("decoder parameters must be contiguous fp32 CUDA tensors")
+            s.w0[i], s.b0[i], s.w1[i], s.b1[i] = w0.data_ptr(), b0.data_ptr(), w1.data_ptr(), b1.data_ptr()
+        self.struct = s
+        self.device = grids[0].device
+
+    @classmethod
+    def grids_only(cls, grids):
+        """View that carries only feature grids (enough for nglod_sdf_features)."""
+        self = cls.__new__(cls)
+        s = NetStruct()
+        s.num_lods = len(grids)
+        s.feature_dim = grids[0].shape[1]
+        for i, g in enumerate(grids):
+            if not g.is_cuda or g.dtype != torch.float32 or not g.is_contiguous(memory_format=torch.channels_last_3d):
+                raise RuntimeError("feature grids must be fp32 CUDA tensors in channels_last_3d memory format")
+            s.grid_res[i] = g.shape[-1] - 1
+            s.grids[i] = g.data_ptr()
+        self.struct, self.grids, self.decoders, self.device = s, list(grids), [], grids[0].device
+        return self
+
+    @property
+    def num_lods(self):
+        return self.struct.num_lods
+
+
+def make_grad_struct(view, grid_grads, dec_grads):
+    """grid_grads[i] / dec_grads[i] = (gw0, gb0, gw1, gb1) or None entries."""
+    g = NetGradStruct()
+    for i in range(view.num_lods):
+        gg = grid_grads[i] if grid_grads is not None else None
+        g.grids[i] = gg.data_ptr() if gg is not None else 0
+        dg = dec_grads[i] if dec_grads is not None else None
+        if dg is not None:
+            g.w0[i], g.b0[i], g.w1[i], g.b1[i] = (t.data_ptr() if t is not None else 0 for t in dg)
+    return g
+
+
+# --------------------------------------------------------------------------- aabb
+def aabb(ray_o, ray_d):
+    """Drop-in for `sol_nglod.aabb` (sol_nglod_kernel.cu:161-192): returns (x [N,3], t [N,1], hit [N] bool)."""
+    lib = _lib.load()
+    ray_o = _f32c(ray_o, "ray_o")
+    ray_d = _f32c(ray_d, "ray_d")
+    n = ray_o.shape[0]
+    x = torch.empty_like(ray_o)
+    t = torch.empty(n, 1, device=ray_o.device, dtype=torch.float32)
+    hit = torch.empty(n, device=ray_o.device, dtype=torch.bool)
+    with torch.cuda.device(ray_o.device):
+        _lib.check(lib.nglod_aabb(_ptr(ray_o), _ptr(ray_d), n, _ptr(x), _ptr(t), _ptr(hit), _stream()), "nglod_aabb")
+    return x, t, hit
+
+
+# --------------------------------------------------------------------------- sdf
+def sdf_forward(view, lod, x):
+    lib = _lib.load()
+    x = _f32c(x, "x")
+    n = x.shape[0]
+    out = torch.empty(n, 1, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.nglod_sdf_forward(ctypes.byref(view.struct), lod, _ptr(x), n, _ptr(out), _stream()),
+                   "nglod_sdf_forward")
+    return out
+
+
+def sdf_forward_all(view, x):
+    lib = _lib.load()
+    x = _f32c(x, "x")
+    n = x.shape[0]
+    out = torch.empty(view.num_lods, n, 1, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.nglod_sdf_forward_all(ctypes.byref(view.struct), _ptr(x), n, _ptr(out), _stream()),
+                   "nglod_sdf_forward_all")
+    return out
+
+
+def sdf_features(view, lod, x):
+    lib = _lib.load()
+    x = _f32c(x, "x")
+    n = x.shape[0]
+    out = torch.empty(n, view.struct.feature_dim, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.nglod_sdf_features(ctypes.byref(view.struct), lod, _ptr(x), n, _ptr(out), _stream()),
+                   "nglod_sdf_features")
+    return out
+
+
+def sdf_backward(view, lod, x, grad_out, grid_grads, dec_grad, want_grad_x=False):
+    """Accumulate into grid_grads[0..lod] (channels_last_3d, like the params) and dec_grad=(gw0,gb0,gw1,gb1)."""
+    lib = _lib.load()
+    x = _f32c(x, "x")
+    grad_out = _f32c(grad_out, "grad_out").reshape(-1)
+    n = x.shape[0]
+    dec = [None] * view.num_lods
+    dec[lod] = dec_grad
+    gs = make_grad_struct(view, grid_grads, dec)
+    gx = torch.empty_like(x) if want_grad_x else None
+    with torch.cuda.device(x.device):
+        _lib.check(lib.nglod_sdf_backward(ctypes.byref(view.struct), lod, _ptr(x), n, _ptr(grad_out),
+                                          ctypes.byref(gs), _ptr(gx), _stream()), "nglod_sdf_backward")
+    return gx
+
+
+def sdf_train_step(view, lod_mask, x, gt, loss_scale, grid_grads, dec_grads, loss_out=None):
+    lib = _lib.load()
+    x = _f32c(x, "x")
+    gt = _f32c(gt, "gt").reshape(-1)
+    n = x.shape[0]
+    gs = make_grad_struct(view, grid_grads, dec_grads)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.nglod_sdf_train_step(ctypes.byref(view.struct), lod_mask, _ptr(x), _ptr(gt), n,
+                                            float(loss_scale), ctypes.byref(gs), _ptr(loss_out), _stream()),
+                   "nglod_sdf_train_step")
+
+
+def sdf_finitediff(view, lod, x, h=1.0 / (64.0 * 3.0)):
+    lib = _lib.load()
+    x = _f32c(x, "x")
+    n = x.shape[0]
+    out = torch.empty(n, 3, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.nglod_sdf_finitediff(ctypes.byref(view.struct), lod, _ptr(x), n, float(h), _ptr(out),
+                                            _stream()), "nglod_sdf_finitediff")
+    return out
+
+
+# --------------------------------------------------------------------------- tracer
+def sphere_trace(view, lod, ray_o, ray_d, num_steps=256, step_size=1.0, min_dis=0.0003, far=10.0,
+                 normal_h=1.0 / (64.0 * 3.0), compute_normals=True, stats=None):
+    """One persistent kernel: returns x [N,3], depth [N,1], hit [N] bool, normal [N,3]."""
+    lib = _lib.load()
+    ray_o = _f32c(ray_o, "ray_o")
+    ray_d = _f32c(ray_d, "ray_d")
+    n = ray_o.shape[0]
+    dev = ray_o.device
+    x = torch.empty(n, 3, device=dev, dtype=torch.float32)
+    depth = torch.empty(n, 1, device=dev, dtype=torch.float32)
+    hit = torch.empty(n, device=dev, dtype=torch.bool)
+    normal = torch.empty(n, 3, device=dev, dtype=torch.float32)
+    queue = torch.empty(1, device=dev, dtype=torch.int32)
+    opts = TraceOpts(int(num_steps), 1 if compute_normals else 0, float(step_size), float(min_dis), float(far),
+                     float(normal_h))
+    with torch.cuda.device(dev):
+        _lib.check(lib.nglod_sphere_trace(ctypes.byref(view.struct), lod, _ptr(ray_o), _ptr(ray_d), n,
+                                          ctypes.byref(opts), _ptr(x), _ptr(depth), _ptr(hit), _ptr(normal),
+                                          _ptr(queue), _ptr(stats), _stream()), "nglod_sphere_trace")
+    return x, depth, hit, normal
+
+
+# --------------------------------------------------------------------------- mesh2sdf / adam
+def mesh2sdf_gpu(points, mesh):
+    """Drop-in for `mesh2sdf.mesh2sdf_gpu(points, mesh)` (mesh2sdf_kernel.cu:895-927,1008): returns [dist [N]]."""
+    lib = _lib.load()
+    points = _f32c(points, "points")
+    mesh = _f32c(mesh, "mesh")
+    n = points.shape[0]
+    t = mesh.shape[0]
+    dist = torch.empty(n, device=points.device, dtype=torch.float32)
+    with torch.cuda.device(points.device):
+        _lib.check(lib.nglod_mesh2sdf(_ptr(points), n, _ptr(mesh), t, _ptr(dist), _stream()), "nglod_mesh2sdf")
+    return [dist]
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, step, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8):
+    lib = _lib.load()
+    n = param.numel()
+    bc1 = 1.0 - beta1 ** step
+    bc2 = 1.0 - beta2 ** step
+    with torch.cuda.device(param.device):
+        _lib.check(lib.nglod_adam_step(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), n, lr, beta1, beta2,
+                                       eps, bc1, bc2, _stream()), "nglod_adam_step")

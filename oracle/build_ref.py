@@ -1,0 +1,66 @@
+"""Recipe: compile the reference's OWN CUDA extensions, unmodified, into oracle/_ref/.
+
+TEST INFRASTRUCTURE ONLY. The sources are compiled where they lie under
+/root/reference (read-only, never copied into this repo); only the built
+shared objects land in oracle/_ref/ (git-ignored, but shipped to the GPU box
+by gpurun).  They give the `-m gpu` parity tests a *real* reference to compare
+against on the B200:
+
+  ref_sol_nglod.aabb            <- sdf-net/lib/extensions/sol_nglod/sol_nglod_kernel.cu:161-192
+  ref_mesh2sdf.mesh2sdf_gpu     <- sdf-net/lib/extensions/mesh2sdf_cuda/mesh2sdf_kernel.cu:895-1012
+
+The reference's setup.py pins -std=c++14, which torch 2.11 headers reject, so
+we drive torch.utils.cpp_extension.load() ourselves (ninja + nvcc, sm_100).
+Run here (no GPU needed, nvcc cross-compiles):  python oracle/build_ref.py
+"""
+import os
+import sys
+
+REF = os.environ.get("NGLOD_REFERENCE", "/root/reference")
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+EXTS = {
+    "ref_sol_nglod": "sdf-net/lib/extensions/sol_nglod/sol_nglod_kernel.cu",
+    "ref_mesh2sdf": "sdf-net/lib/extensions/mesh2sdf_cuda/mesh2sdf_kernel.cu",
+}
+
+
+def build(verbose=False):
+    if not os.path.isdir(REF):
+        print(f"[build_ref] {REF} absent - skipping (prebuilt files in {OUT} are used if present)")
+        return False
+    os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0")
+    from torch.utils.cpp_extension import load
+    ok = True
+    for name, rel in EXTS.items():
+        bdir = os.path.join(OUT, name)
+        os.makedirs(bdir, exist_ok=True)
+        so = os.path.join(bdir, name + ".so")
+        if os.path.exists(so):
+            print(f"[build_ref] {so} already built")
+            continue
+        try:
+            load(name=name, sources=[os.path.join(REF, rel)], build_directory=bdir,
+                 extra_cuda_cflags=["-O3"], verbose=verbose, is_python_module=False)
+            print(f"[build_ref] built {so}")
+        except Exception as e:  # noqa: BLE001
+            ok = False
+            print(f"[build_ref] FAILED {name}: {e}")
+    return ok
+
+
+def load_ref(name):
+    """Import a prebuilt reference extension from oracle/_ref (None if absent)."""
+    import importlib.util
+    import torch  # noqa: F401  (the .so links against libtorch)
+    so = os.path.join(OUT, name, name + ".so")
+    if not os.path.exists(so):
+        return None
+    spec = importlib.util.spec_from_file_location(name, so)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+if __name__ == "__main__":
+    sys.exit(0 if build(verbose="-v" in sys.argv) else 1)

@@ -1,0 +1,200 @@
+"""Generate golden vectors by running the UNMODIFIED reference (read-only at /root/reference).
+
+Run in the authoring container only:   python tests/golden/make_golden.py
+The reference ships no tests or fixtures, so these files are how parity is
+pinned: the reference's own classes (OctreeSDF, SphereTracer, Renderer, look_at, gradient) are
+imported in place, with empty stub modules for third-party packages that are not installed and are
+not on the path (polyscope, tinyobjloader, pyexr, moviepy, matplotlib), `lib.utils.PerfTimer`
+replaced (its constructor needs a CUDA driver), and `sol_nglod.aabb` -- which exists only as CUDA --
+provided by oracle/oracle.c (itself checked against the compiled reference kernel on the GPU box).
+
+Outputs (small .npz files next to this script):
+  rand5.npz  random-init 5-LOD model re-creatable from the seed: sdf at every LOD, return_lst,
+             gradients of the L2 loss, a 64x36 trace at lod 4, a mixed-origin ray set
+  fit3.npz   a 3-LOD model fitted for a few hundred Adam steps to a torus (weights stored):
+             sdf, 96x54 trace at lod 2, Renderer.render with AO
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.abspath(os.path.join(HERE, "..", ".."))
+REF = "/root/reference/sdf-net"
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+
+from oracle import nglod_oracle as O  # noqa: E402
+
+for m in ["polyscope", "tinyobjloader", "pyexr", "moviepy", "moviepy.editor", "matplotlib", "matplotlib.pyplot",
+          "sol_nglod", "mesh2sdf", "cv2"]:
+    sys.modules.setdefault(m, types.ModuleType(m))
+sys.modules["sol_nglod"].aabb = O.aabb
+
+import lib.utils  # noqa: E402
+
+
+class _NoTimer:
+    def __init__(self, activate=False):
+        pass
+
+    def check(self, name=None):
+        pass
+
+    def reset(self):
+        pass
+
+
+lib.utils.PerfTimer = _NoTimer
+from lib.options import parse_options  # noqa: E402
+from lib.models import OctreeSDF  # noqa: E402
+from lib.tracer import SphereTracer  # noqa: E402
+from lib.renderer import Renderer  # noqa: E402
+from lib.geoutils import look_at  # noqa: E402
+from lib.diffutils import gradient  # noqa: E402
+
+torch.set_num_threads(8)
+
+
+def make_args(extra):
+    return parse_options(return_parser=True).parse_args(["--net", "OctreeSDF", "--feature-dim", "32"] + extra)
+
+
+def torus_sdf(p, major=0.6, minor=0.25):
+    q = torch.sqrt(p[..., 0] ** 2 + p[..., 2] ** 2) - major
+    return torch.sqrt(q * q + p[..., 1] ** 2) - minor
+
+
+def trace_pack(prefix, rb, out):
+    out[prefix + "_x"] = rb.x.detach().numpy()
+    out[prefix + "_depth"] = rb.depth.detach().numpy()
+    out[prefix + "_hit"] = rb.hit.detach().numpy()
+    out[prefix + "_normal"] = rb.normal.detach().numpy()
+
+
+def rand5():
+    out = {}
+    args = make_args(["--num-lods", "5"])
+    torch.manual_seed(0)
+    net = OctreeSDF(args)
+    out["weights_checksum"] = np.array([float(sum(p.double().sum() for p in net.parameters())),
+                                        float(sum((p.double() ** 2).sum() for p in net.parameters()))])
+    g = torch.Generator().manual_seed(1)
+    x = (torch.rand(4096, 3, generator=g) * 2 - 1) * 1.2          # some points outside the unit box
+    x[:8] = torch.tensor([[1.0, 1.0, 1.0], [-1.0, -1.0, -1.0], [0.0, 0.0, 0.0], [1.0, 0.0, -1.0],
+                          [0.5, 0.5, 0.5], [-0.25, 0.75, 1.0], [2.0, -2.0, 0.3], [1.0 - 1e-7, 0.0, 0.0]])
+    out["x"] = x.numpy()
+    net.eval()
+    with torch.no_grad():
+        for l in range(5):
+            out[f"sdf_lod{l}"] = net.sdf(x, lod=l).numpy()
+        lst = net.sdf(x, return_lst=True)
+        out["sdf_lst"] = np.stack([t.numpy() for t in lst])
+        net.lod = 3
+        out["forward_lod3"] = net(x).numpy()
+        net.lod = None
+    # gradients of the reference training objective at lod 4 (trainer.py:317-339) and of a 2-LOD sum
+    gt = torus_sdf(x).unsqueeze(1)
+    out["gt"] = gt.numpy()
+    rng = np.random.RandomState(7)
+    for tag, lods in (("g4", [4]), ("g13", [1, 3])):
+        net.zero_grad()
+        loss = 0
+        for l in lods:
+            loss = loss + ((net.sdf(x, lod=l) - gt) ** 2).sum()
+        loss = loss / x.shape[0]
+        loss.backward()
+        out[f"{tag}_loss"] = np.array(loss.item())
+        for i in range(5):
+            gfm = net.features[i].fm.grad
+            if gfm is None:
+                continue
+            gl = gfm[0].permute(1, 2, 3, 0).contiguous().reshape(-1)     # channels-last flat, like the kernels
+            if i <= 1:
+                out[f"{tag}_fm{i}"] = gl.numpy()
+            else:
+                idx = rng.randint(0, gl.numel(), size=4096)
+                out[f"{tag}_fm{i}_idx"] = idx
+                out[f"{tag}_fm{i}_val"] = gl.numpy()[idx]
+            out[f"{tag}_fm{i}_sum"] = np.array([gl.double().sum().item(), gl.double().abs().sum().item()])
+        for l in lods:
+            for k in ("0.weight", "0.bias", "2.weight", "2.bias"):
+                out[f"{tag}_louts{l}.{k}"] = dict(net.louts[l].named_parameters())[k].grad.numpy()
+        out[f"{tag}_untouched_head_has_grad"] = np.array(
+            [net.louts[0][0].weight.grad is not None and float(net.louts[0][0].weight.grad.abs().sum()) > 0])
+    # autodiff d sdf / d x (diffutils.py:32-37) incl. the border-clip rule
+    xg = x[:512].clone()
+    net.lod = 4
+    out["autodiff_lod4"] = gradient(xg, net, method="autodiff").detach().numpy()
+    out["finitediff_lod4"] = gradient(x[:512].clone(), net, method="finitediff").detach().numpy()
+    # tracer, lod 4, default options, seeded jitter
+    tracer = SphereTracer(args)
+    torch.manual_seed(123)
+    ray_o, ray_d = look_at([-2.8, 2.8, -2.8], [0, 0, 0], 64, 36, fov=30.0, mode="persp", device="cpu")
+    out["t1_ray_o"], out["t1_ray_d"] = ray_o.numpy(), ray_d.numpy()
+    trace_pack("t1", tracer(net, ray_o, ray_d), out)
+    # mixed origins (inside / outside the box, quirk 6), short budget
+    g2 = torch.Generator().manual_seed(5)
+    ro = torch.rand(512, 3, generator=g2) * 3 - 1.5
+    rd = torch.nn.functional.normalize(torch.randn(512, 3, generator=g2), dim=1)
+    tr12 = SphereTracer(args, num_steps=12)
+    out["t2_ray_o"], out["t2_ray_d"] = ro.numpy(), rd.numpy()
+    trace_pack("t2", tr12(net, ro, rd), out)
+    np.savez_compressed(os.path.join(HERE, "rand5.npz"), **out)
+    print("rand5:", {k: v.shape for k, v in out.items() if k.startswith("t1_")}, "hits", out["t1_hit"].sum(), out["t2_hit"].sum())
+
+
+def fit3():
+    out = {}
+    args = make_args(["--num-lods", "3"])
+    torch.manual_seed(3)
+    net = OctreeSDF(args)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    net.train()
+    g = torch.Generator().manual_seed(11)
+    for it in range(400):
+        pts = torch.rand(8192, 3, generator=g) * 2 - 1
+        gt = torus_sdf(pts).unsqueeze(1)
+        opt.zero_grad()
+        preds = net.sdf(pts, return_lst=True)
+        loss = sum(((p - gt) ** 2).sum() for p in preds) / pts.shape[0]
+        loss.backward()
+        opt.step()
+        if it % 100 == 0:
+            print("fit3 it", it, loss.item())
+    net.eval()
+    for k, v in net.state_dict().items():
+        out["sd." + k] = v.numpy()
+    x = torch.rand(4096, 3, generator=g) * 2 - 1
+    out["x"] = x.numpy()
+    with torch.no_grad():
+        for l in range(3):
+            out[f"sdf_lod{l}"] = net.sdf(x, lod=l).numpy()
+    net.lod = 2
+    tracer = SphereTracer(args)
+    torch.manual_seed(321)
+    ray_o, ray_d = look_at([-2.8, 2.8, -2.8], [0, 0, 0], 96, 54, fov=30.0, mode="persp", device="cpu")
+    out["t1_ray_o"], out["t1_ray_d"] = ray_o.numpy(), ray_d.numpy()
+    rb = tracer(net, ray_o, ray_d)
+    trace_pack("t1", rb, out)
+    with torch.no_grad():
+        conv = (net(rb.x).abs() < 0.0003)[:, 0] & rb.hit
+    out["t1_converged"] = conv.numpy()
+    # Renderer.render with ambient occlusion (renderer.py:109-216), identical rays
+    rargs = make_args(["--num-lods", "3", "--render-res", "96", "54", "--ao"])
+    renderer = Renderer(SphereTracer(rargs), args=rargs, device="cpu")
+    rb2 = renderer.render(net, ray_o, ray_d)
+    out["r1_ao"] = rb2.ao.detach().numpy()
+    out["r1_relative_depth"] = rb2.relative_depth.detach().numpy()
+    out["r1_hit"] = rb2.hit.detach().numpy()
+    out["r1_normal"] = rb2.normal.detach().numpy()
+    np.savez_compressed(os.path.join(HERE, "fit3.npz"), **out)
+    print("fit3: hits", int(rb.hit.sum()), "converged", int(conv.sum()), "of", rb.hit.numel())
+
+
+if __name__ == "__main__":
+    rand5()
+    fit3()
