@@ -1,0 +1,450 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the NGLOD hot path on N B200s (one process per GPU).
+
+  python bench.py --gpus 1 --steps 20 --warmup 3
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+         bench.py --gpus N --steps K --warmup W
+  python bench.py --impl reference ...      # the reference's CPU path (oracle port) on the host cores
+
+Workload (BASELINE.json configs[1]): SphereTracer.forward over a 1280x720 perspective frame at lod 4 of a 5-LOD
+OctreeSDF (feature-dim 32, hidden 128) fitted IN-RUN to a procedural torus mesh (mesh2sdf-labelled samples).
+A "step" is one full frame (921 600 rays) per GPU; with N GPUs every rank traces its own frame (a different
+camera azimuth), no data-path collective -> "scaling": "weak"; value = N * 921600 / max-over-ranks time.
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+W, H = 1280, 720
+LOD = 4
+NUM_LODS = 5
+CAM_FROM, CAM_TO, FOV = [-2.8, 2.8, -2.8], [0.0, 0.0, 0.0], 30.0
+FIT_STEPS, FIT_BATCH = 300, 65536
+SDF_N = 1 << 20
+GATHER_BYTES_PER_QUERY = (LOD + 1) * 8 * 32 * 4          # fp32 grids: 5120 B  
+IO_BYTES_PER_QUERY = 16
+RAY_IO_BYTES = 24 + 12 + 4 + 1 + 12                        # ray_o, ray_d in; x, depth, hit, normal out
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            j = json.load(open(p))
+            return float(j["hbm_gbs"]), "measured"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback"
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock / throttle reasons during the timed region (NVML; falls back to one nvidia-smi poll)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._th = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.005)
+
+    def start(self):
+        if self.nv is not None:
+            self._th = threading.Thread(target=self._loop, daemon=True)
+            self._th.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._th is not None:
+            self._th.join()
+        if self.nv is None:
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", f"--id={self.index}", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits"],
+                    capture_output=True, text=True, timeout=10).stdout.strip().split(",")
+                self.samples, self.max_mhz = [int(out[0])], int(out[1])
+            except Exception:  # noqa: BLE001
+                pass
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------------- set-up
+def make_rays(device, azimuth_deg=0.0, seed=0):
+    """look_at rays for the 720p frame; the camera is rotated about y by `azimuth_deg` (rank-dependent)."""
+    from nglod_b200.lib.geoutils import look_at
+    a = math.radians(azimuth_deg)
+    f = [CAM_FROM[0] * math.cos(a) + CAM_FROM[2] * math.sin(a), CAM_FROM[1],
+         -CAM_FROM[0] * math.sin(a) + CAM_FROM[2] * math.cos(a)]
+    torch.manual_seed(1000 + seed)
+    return look_at(f, CAM_TO, W, H, mode="persp", fov=FOV, device=device)
+
+
+def build_and_fit(device, log):
+    """5-LOD OctreeSDF fitted in-run to a procedural torus mesh: samples from the MeshDataset recipe
+    (rand/near/near/trace/trace), labels from the mesh2sdf kernel, fused training step + Adam kernel."""
+    from nglod_b200.lib.options import parse_options
+    from nglod_b200.lib.models import OctreeSDF
+    from nglod_b200.lib.datasets import MeshDataset
+    from nglod_b200.lib.trainer import FusedTrainer
+    from nglod_b200.lib.torchgp import torus
+    args = parse_options(return_parser=True).parse_args(
+        ["--net", "OctreeSDF", "--num-lods", str(NUM_LODS), "--feature-dim", "32", "--lod", str(LOD),
+         "--render-res", str(W), str(H)])
+    torch.manual_seed(0)
+    net = OctreeSDF(args).to(device)
+    t0 = time.time()
+    ds = MeshDataset(args, mesh=torus(0.6, 0.25, 128, 64), device=device)       # 500 000 labelled points
+    torch.cuda.synchronize()
+    t_ds = time.time() - t0
+    trainer = FusedTrainer(net, lr=1e-3)
+    n = len(ds)
+    g = torch.Generator(device=device).manual_seed(7)
+    t0 = time.time()
+    last = None
+    for it in range(FIT_STEPS):
+        idx = torch.randint(0, n, (FIT_BATCH,), device=device, generator=g)
+        last = trainer.step(ds.pts[idx], ds.d[idx])
+    torch.cuda.synchronize()
+    log(f"fit: dataset {n} pts in {t_ds:.2f}s, {FIT_STEPS} steps x {FIT_BATCH} pts in {time.time() - t0:.2f}s, "
+        f"final loss {float(last):.3e}")
+    net.lod = LOD
+    net.eval()
+    return net, args
+
+
+def flush_l2(buf):
+    buf.zero_()
+
+
+# ----------------------------------------------------------------------------------------------- ours
+def run_ours(ns):
+    from nglod_b200 import dist as ndist
+    from nglod_b200 import ops
+    from nglod_b200.lib.tracer import SphereTracer
+    rank, world, local = ndist.init_from_env()
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+
+    def log(msg):
+        if rank == 0:
+            print("[bench] " + msg, file=sys.stderr, flush=True)
+
+    net, args = build_and_fit(device, log)
+    if world > 1:                       # identical weights on every rank
+        for p in net.parameters():
+            torch.distributed.broadcast(p.data, src=0)
+    tracer = SphereTracer(args)
+    ray_o, ray_d = make_rays(device, azimuth_deg=360.0 * rank / max(world, 1), seed=rank)
+    n_rays = ray_o.shape[0]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)      # 256 MB > 126 MB L2
+    view = net.net_view()
+
+    # one instrumented call: SDF evaluations per frame (for the algorithmic byte count)
+    stats = torch.zeros(2, dtype=torch.int64, device=device)
+    x, depth, hit, normal = ops.sphere_trace(view, LOD, ray_o, ray_d, stats=stats)
+    torch.cuda.synchronize()
+    n_eval, n_march = int(stats[0]), int(stats[1])
+    n_hit = int(hit.sum())
+    log(f"frame: {n_rays} rays, {n_hit} hits, {n_eval} sdf evals ({n_eval / n_rays:.2f}/ray), {n_march} march steps")
+
+    def step():
+        return tracer(net, ray_o, ray_d)
+
+    for _ in range(max(ns.warmup, 3)):
+        flush_l2(flush)
+        step()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local)
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    clocks.start()
+    evs = []
+    for _ in range(ns.steps):
+        flush_l2(flush)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step()
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = ndist.max_over_ranks(sum(step_ms), device)
+    kernel_ms = float(np.mean(step_ms))          # the step IS one sphere_trace_kernel launch (+ a 4-byte memset)
+
+    # ---- e2e: same frame through the public API with HOST buffers (pinned), copies inside the timed region
+    ho, hd = ray_o.cpu().pin_memory(), ray_d.cpu().pin_memory()
+    out_host = {k: torch.empty(s, dtype=dt).pin_memory() for k, s, dt in
+                (("x", (n_rays, 3), torch.float32), ("depth", (n_rays, 1), torch.float32),
+                 ("hit", (n_rays,), torch.bool), ("normal", (n_rays, 3), torch.float32))}
+
+    def e2e_step():
+        o = ho.to(device, non_blocking=True)
+        d = hd.to(device, non_blocking=True)
+        rb = tracer(net, o, d)
+        out_host["x"].copy_(rb.x, non_blocking=True)
+        out_host["depth"].copy_(rb.depth, non_blocking=True)
+        out_host["hit"].copy_(rb.hit, non_blocking=True)
+        out_host["normal"].copy_(rb.normal, non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(3):
+        e2e_step()
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(ns.steps):
+        e2e_step()
+    e2e_s = ndist.max_over_ranks(time.perf_counter() - t0, device)
+    clock_info = clocks.stop()
+
+    # ---- SDF query throughput (BASELINE.json configs[0]): 2^20 random points, lod 4, forward and forward+backward
+    g = torch.Generator(device=device).manual_seed(1)
+    xq = torch.rand(SDF_N, 3, device=device, generator=g) * 2 - 1
+    gq = torch.rand(SDF_N, device=device, generator=g)
+
+    def time_kernel(fn, iters):
+        for _ in range(3):
+            flush_l2(flush)
+            fn()
+        torch.cuda.synchronize()
+        ev = []
+        for _ in range(iters):
+            flush_l2(flush)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            ev.append((a, b))
+        torch.cuda.synchronize()
+        return float(np.mean([a.elapsed_time(b) for a, b in ev]))
+
+    fwd_ms = time_kernel(lambda: ops.sdf_forward(view, LOD, xq), max(ns.steps, 10))
+    grid_grads = [torch.zeros_like(f.fm.data, memory_format=torch.preserve_format) for f in net.features]
+    dec_grad = tuple(torch.zeros_like(p) for p in net.decoder_params(LOD))
+    bwd_ms = time_kernel(lambda: ops.sdf_backward(view, LOD, xq, gq, grid_grads, dec_grad), max(ns.steps // 2, 5))
+    fwd_ms = ndist.max_over_ranks(fwd_ms, device)
+    bwd_ms = ndist.max_over_ranks(bwd_ms, device)
+
+    if rank != 0:
+        return
+    peak, peak_src = load_peaks()
+    value = world * n_rays * ns.steps / (total_ms / 1e3)
+    alg_bytes = n_eval * (GATHER_BYTES_PER_QUERY + IO_BYTES_PER_QUERY) + n_rays * RAY_IO_BYTES
+    achieved = alg_bytes / (kernel_ms / 1e3) / 1e9
+    compulsory = (n_rays * RAY_IO_BYTES + sum(f.fm.numel() * 4 for f in net.features)) / (kernel_ms / 1e3) / 1e9
+    q_bytes = SDF_N * (GATHER_BYTES_PER_QUERY + IO_BYTES_PER_QUERY)
+    line = {
+        "metric": "sphere_traced_rays_per_sec_1280x720_lod4",
+        "value": value,
+        "unit": "rays/s",
+        "n_gpus": world,
+        "steps": ns.steps,
+        "warmup": max(ns.warmup, 3),
+        "ms_per_step": total_ms / ns.steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "SphereTracer.forward 1280x720 persp fov30 lod4, OctreeSDF num-lods=5 feature-dim=32 "
+                               "hidden=128 fitted in-run to a procedural torus mesh (BASELINE.json configs[1])",
+                   "rays_per_gpu_step": n_rays, "fps_per_gpu": 1e3 / (total_ms / ns.steps),
+                   "sdf_evals_per_ray": n_eval / n_rays, "hit_fraction": n_hit / n_rays,
+                   "num_steps": 256, "l2": "flushed between timed iterations (256 MB memset)",
+                   "parallelism": f"one frame per GPU x{world}, no collective"},
+        "e2e": {"value": world * n_rays * ns.steps / e2e_s, "unit": "rays/s",
+                "h2d_bytes_per_step": n_rays * 24, "d2h_bytes_per_step": n_rays * (12 + 4 + 1 + 12),
+                "ms_per_step": e2e_s / ns.steps * 1e3},
+        "gpu_launches": ns.steps,
+        "clocks": clock_info,
+        "roofline": {"bound": "hbm", "kernel": "sphere_trace_kernel", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms,
+                     "compulsory_GBs": compulsory,
+                     "note": "algorithmic bytes = sdf_evals x (5120 B gather + 16 B io) + rays x 53 B; the gather is "
+                             "served by L2/L1 (grids 40.5 MB < L2), so frac may exceed 1 (SURVEY.md 8d)"},
+        "sdf_queries": {"n": SDF_N, "lod": LOD,
+                        "forward_qps": world * SDF_N / (fwd_ms / 1e3), "forward_ms": fwd_ms,
+                        "forward_backward_qps": world * SDF_N / ((fwd_ms + bwd_ms) / 1e3), "backward_ms": bwd_ms,
+                        "roofline": {"bound": "hbm", "kernel": "sdf_forward_kernel",
+                                     "achieved": q_bytes / (fwd_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                                     "frac": q_bytes / (fwd_ms / 1e3) / 1e9 / peak, "traffic": None}},
+    }
+    if world == 1 and not ns.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_trace(net, ray_o.cpu(), ray_d.cpu(), budget_s=20.0, log=log)
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- CPU legs
+def subsample_rays(ray_o, ray_d, stride):
+    """Every `stride`-th column and row of the x-major frame (ray = ix*H + iy)."""
+    o = ray_o.reshape(W, H, 3)[::stride, ::stride].reshape(-1, 3).contiguous()
+    d = ray_d.reshape(W, H, 3)[::stride, ::stride].reshape(-1, 3).contiguous()
+    return o, d
+
+
+def cpu_trace_rate(onet, ray_o, ray_d, budget_s, log):
+    """Time the oracle's batch-loop tracer on the host; picks the largest sub-frame that fits the budget."""
+    from oracle import nglod_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    o, d = subsample_rays(ray_o, ray_d, 32)                 # 40x23 probe
+    t0 = time.perf_counter()
+    O.sphere_trace(onet, o, d)
+    probe = max(time.perf_counter() - t0, 1e-3)
+    per_ray = probe / o.shape[0]
+    stride = 32
+    for s in (16, 8, 4, 2, 1):
+        if per_ray * (W // s) * (H // s) * 0.6 <= budget_s:   # batches get more efficient as they grow
+            stride = s
+    o, d = subsample_rays(ray_o, ray_d, stride)
+    cnt = {}
+    t0 = time.perf_counter()
+    O.sphere_trace(onet, o, d, count=cnt)
+    dt = time.perf_counter() - t0
+    log(f"cpu tracer: {o.shape[0]} rays ({W // stride}x{H // stride}) in {dt:.2f}s on {torch.get_num_threads()} threads")
+    return o.shape[0] / dt, f"{W // stride}x{H // stride} sub-frame (every {stride}th row/col) of the same rays, {o.shape[0]} rays, 1 pass", dt
+
+
+def cpu_baseline_trace(net, ray_o, ray_d, budget_s, log):
+    from oracle import nglod_oracle as O
+    onet = O.OracleNet({k: v.detach().cpu() for k, v in net.state_dict().items()})
+    onet.lod = LOD
+    rate, sample, _ = cpu_trace_rate(onet, ray_o, ray_d, budget_s, log)
+    return {"value": rate, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample}
+
+
+def run_reference(ns):
+    """The reference's CPU path for the same metric/config: the oracle port (same ATen calls as the reference's
+    PyTorch path; the reference itself is Python under /root/reference, which does not exist on the GPU box)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import nglod_oracle as O
+
+    def log(msg):
+        print("[bench-ref] " + msg, file=sys.stderr, flush=True)
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    fit_dev = "cuda" if torch.cuda.is_available() else "cpu"
+    # untimed set-up: fit the same architecture to the same torus with plain torch autograd (on the GPU if present)
+    from nglod_b200.lib.options import parse_options
+    from nglod_b200.lib.models import OctreeSDF
+    args = parse_options(return_parser=True).parse_args(["--net", "OctreeSDF", "--num-lods", str(NUM_LODS)])
+    torch.manual_seed(0)
+    sd = OctreeSDF(args).state_dict()                     # parameter container only; no kernel is touched
+    onet = O.OracleNet(sd, device=fit_dev, requires_grad=True)
+    opt = torch.optim.Adam(onet.parameters(), lr=1e-3)
+    g = torch.Generator(device=fit_dev).manual_seed(7)
+    steps, batch = (FIT_STEPS, FIT_BATCH) if fit_dev == "cuda" else (60, 8192)
+    for _ in range(steps):
+        p = torch.rand(batch, 3, device=fit_dev, generator=g) * 2 - 1
+        surf = p[: batch // 2]
+        q = torch.sqrt(surf[:, 0] ** 2 + surf[:, 2] ** 2)
+        # half of the batch is pulled onto / near the torus surface, like the near/trace sample modes
+        ring = torch.stack([surf[:, 0] / q * 0.6, torch.zeros_like(q), surf[:, 2] / q * 0.6], dim=1)
+        dirv = torch.nn.functional.normalize(surf - ring, dim=1)
+        p = torch.cat([ring + dirv * (0.25 + 0.01 * torch.randn(batch // 2, 1, device=fit_dev, generator=g)), p[batch // 2:]])
+        qq = torch.sqrt(p[:, 0] ** 2 + p[:, 2] ** 2) - 0.6
+        gt = (torch.sqrt(qq * qq + p[:, 1] ** 2) - 0.25).unsqueeze(1)
+        O.l2_loss_and_grads(onet, p, gt, list(range(NUM_LODS)))
+        opt.step()
+    cpu_net = O.OracleNet({f"features.{i}.fm": t.detach().cpu() for i, t in enumerate(onet.fm)} |
+                          {f"louts.{i}.{k}": t.detach().cpu() for i, dct in enumerate(onet.dec)
+                           for k, t in zip(("0.weight", "0.bias", "2.weight", "2.bias"), dct)})
+    cpu_net.lod = LOD
+    # rays: the oracle's own look_at (same camera, seeded jitter)
+    torch.manual_seed(1000)
+    ray_o, ray_d = O.look_at(CAM_FROM, CAM_TO, W, H, mode="persp", fov=FOV)
+    total_steps = ns.steps + ns.warmup
+    budget = max(2.0, min(20.0, 150.0 / max(total_steps, 1)))
+    rate, sample, dt = cpu_trace_rate(cpu_net, ray_o, ray_d, budget, log)
+    o, d = None, None
+    # timed: W warm-up + K steps of the bounded sample
+    stride = W // int(sample.split("x")[0])
+    o, d = subsample_rays(ray_o, ray_d, stride)
+    for _ in range(ns.warmup):
+        O.sphere_trace(cpu_net, o, d)
+    t0 = time.perf_counter()
+    for _ in range(ns.steps):
+        O.sphere_trace(cpu_net, o, d)
+    el = time.perf_counter() - t0
+    value = o.shape[0] * ns.steps / el
+    line = {
+        "impl": "reference", "metric": "sphere_traced_rays_per_sec_1280x720_lod4", "value": value, "unit": "rays/s",
+        "n_gpus": ns.gpus, "steps": ns.steps, "warmup": ns.warmup, "ms_per_step": el / ns.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "SphereTracer.forward 1280x720 persp fov30 lod4, OctreeSDF num-lods=5 feature-dim=32 "
+                               "hidden=128 fitted in-run to a torus (BASELINE.json configs[1]); CPU: " + sample},
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample + f", x{ns.steps} steps"},
+        "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ns = ap.parse_args()
+    if ns.impl == "reference":
+        run_reference(ns)
+    else:
+        run_ours(ns)
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
