@@ -1,0 +1,224 @@
+"""CPU: host-side logic and the C-ABI surface (no compute calls -- there is no GPU here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import make_args, rand5_model
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    from nglod_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "nglod_b200.h")).read()
+    declared = set(re.findall(r"^\s*(?:int|const char\*)\s+(nglod_\w+)\s*\(", header, flags=re.M))
+    assert len(declared) >= 12
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.nglod_abi_version() == 1
+    assert b"sm_100a" in lib.nglod_build_info()
+    # struct layouts agree with the header (sizes computed from the declarations)
+    assert ctypes.sizeof(_lib.NetStruct) == 4 * 4 + 8 * 4 + 5 * 8 * 8
+    assert ctypes.sizeof(_lib.NetGradStruct) == 5 * 8 * 8
+    assert ctypes.sizeof(_lib.TraceOpts) == 8 + 4 * 8
+    # argument validation happens before any CUDA call, so it is testable without a device
+    assert lib.nglod_aabb(None, None, -1, None, None, None, None) == _lib.EINVAL
+    assert lib.nglod_sdf_forward(None, 0, None, 0, None, None) == _lib.EINVAL
+    assert lib.nglod_aabb(None, None, 0, None, None, None, None) == 0
+
+
+def test_no_cpu_fallback():
+    from nglod_b200 import ops
+    net, _ = rand5_model("cpu")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        net.sdf(torch.zeros(3, 3), lod=0)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.aabb(torch.zeros(3, 3), torch.ones(3, 3))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.mesh2sdf_gpu(torch.zeros(3, 3), torch.zeros(2, 3, 3))
+
+
+def test_product_never_imports_oracle():
+    for base, _, files in os.walk(os.path.join(ROOT, "nglod_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(base, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), os.path.join(base, f)
+
+
+def test_options_match_reference_defaults():
+    from nglod_b200.lib.options import parse_options, argparse_to_str
+    p = parse_options(return_parser=True)
+    a = p.parse_args([])
+    assert (a.net, a.feature_dim, a.num_lods, a.base_lod, a.hidden_dim) == ("OverfitSDF", 32, 1, 2, 128)
+    assert a.sample_mode == ["rand", "near", "near", "trace", "trace"] and a.num_samples == 100000
+    assert (a.num_steps, a.step_size, a.min_dis, a.camera_clamp) == (256, 1.0, 0.0003, [-5, 10])
+    assert a.camera_origin == [-2.8, 2.8, -2.8] and a.camera_fov == 30 and a.render_res == [512, 512]
+    assert a.grad_method == "finitediff" and a.tracer == "SphereTracer" and a.lod is None and a.lr == 0.001
+    a = p.parse_args("--net OctreeSDF --num-lods 5 --lod 4 --render-res 1280 720 --shadow --ao".split())
+    assert a.lod == 4 and a.render_res == [1280, 720] and a.shadow and a.ao
+    grp = p.add_argument_group("app")                 # apps extend the parser (sdf_renderer.py:59-82)
+    grp.add_argument("--img-dir", type=str, default="x")
+    args, txt = argparse_to_str(p, [])
+    assert txt.startswith("```") and "'renderer'" in txt and args.img_dir == "x"
+
+
+def test_setparam_and_tracer_ctor():
+    from nglod_b200.lib.utils import setparam
+    from nglod_b200.lib.tracer import SphereTracer
+    a = make_args()
+    assert setparam(a, None, "num_steps") == 256 and setparam(a, 12, "num_steps") == 12
+    assert setparam(None, None, "num_steps") is None
+    t = SphereTracer(a, num_steps=12)
+    assert t.num_steps == 12 and t.min_dis == 0.0003 and t.camera_clamp == [-5, 10] and t.grad_method == "finitediff"
+    t = SphereTracer(camera_clamp=[0, 5], step_size=0.5, grad_method="finitediff", num_steps=8, min_dis=1e-3)
+    assert t.step_size == 0.5 and t.inv_num_steps == 1 / 8
+
+
+def test_renderbuffer_semantics():
+    from nglod_b200.lib.tracer import RenderBuffer
+    a = RenderBuffer(x=torch.zeros(4, 3), hit=torch.ones(4, dtype=torch.bool))
+    b = RenderBuffer(x=torch.ones(2, 3), depth=torch.ones(2, 1))
+    c = a + b
+    assert c.x.shape == (6, 3) and c.hit.shape == (4,) and c.depth.shape == (2, 1) and c.normal is None
+    e = RenderBuffer()
+    e += a
+    assert e.x.shape == (4, 3)
+    assert len(list(a)) == 12
+    r = RenderBuffer(rgb=torch.rand(6, 3), hit=torch.ones(6, 1)).reshape(3, 2, -1).transpose()
+    assert r.rgb.shape == (2, 3, 3) and r.hit.shape == (2, 3, 1)
+    d = r.exrdict()
+    assert "default" in d and "rgb" not in d and "x" not in d
+    img = RenderBuffer(hit=torch.ones(2, 2, 1), normal=torch.zeros(2, 2, 3), rgb=torch.ones(2, 2, 3) * 0.5,
+                       relative_depth=torch.ones(2, 2, 1) * 0.2).image()
+    assert img.hit.shape == (2, 2, 3) and float(img.normal[0, 0, 0]) == 127.5 and float(img.depth[0, 0, 0]) == 51.0
+    m = RenderBuffer.mean(RenderBuffer(rgb=torch.zeros(2, 3)), RenderBuffer(rgb=torch.ones(2, 3)))
+    assert torch.allclose(m.rgb, torch.full((2, 3), 0.5))
+
+
+def test_reference_checkpoint_roundtrip():
+    """A reference-layout state_dict (contiguous NCDHW grids) loads; ours saves back with the same keys/shapes;
+    the grids stay channels-last physically."""
+    net, _ = rand5_model()
+    sd = {k: v.clone().contiguous() for k, v in net.state_dict().items()}
+    args = make_args(["--num-lods", "5"])
+    from nglod_b200.lib.models import OctreeSDF
+    net2 = OctreeSDF(args)
+    net2.load_state_dict(sd)
+    for i in range(5):
+        fm = net2.features[i].fm
+        assert fm.is_contiguous(memory_format=torch.channels_last_3d)
+        assert torch.equal(fm, sd[f"features.{i}.fm"])
+        assert torch.equal(fm.permute(0, 2, 3, 4, 1).contiguous()[0, 1, 2, 3], sd[f"features.{i}.fm"][0, :, 1, 2, 3])
+    assert list(net2.state_dict().keys()) == list(sd.keys())
+
+
+def test_octree_sdf_ctor_variants():
+    from nglod_b200.lib.models import OctreeSDF
+    n = OctreeSDF(make_args(["--num-lods", "3", "--joint-decoder"]))
+    assert len(n.louts) == 1 and n.num_decoder == 1
+    n = OctreeSDF(make_args(["--num-lods", "2", "--pos-invariant"]))
+    assert n.louts[0][0].weight.shape == (128, 32)
+    n = OctreeSDF(make_args(["--num-lods", "2", "--base-lod", "3"]))
+    assert n.features[0].fm.shape[-1] == 9
+    with pytest.raises(NotImplementedError):
+        OctreeSDF(make_args(["--num-lods", "2", "--pos-enc"]))
+    n = OctreeSDF(make_args(["--num-lods", "2", "--interpolate", "0.5"]))
+    n.lod = 0
+    with pytest.raises(NotImplementedError):
+        n.sdf(torch.zeros(1, 3))
+    n.freeze()
+    assert not any(p.requires_grad for p in n.parameters())
+
+
+def test_look_at_matches_oracle_with_same_seed():
+    from nglod_b200.lib.geoutils import look_at
+    from oracle import nglod_oracle as O
+    for mode in ("persp", "ortho"):
+        torch.manual_seed(9)
+        o1, d1 = look_at([-2.8, 2.8, -2.8], [0, 0, 0], 40, 30, mode=mode, fov=30.0, device="cpu")
+        torch.manual_seed(9)
+        o2, d2 = O.look_at([-2.8, 2.8, -2.8], [0, 0, 0], 40, 30, mode=mode, fov=30.0)
+        assert torch.equal(o1, o2) and torch.equal(d1, d2)
+    assert o1.shape == (1200, 3)
+    with pytest.raises(ValueError):
+        look_at([0, 0, 1], [0, 0, 0], 4, 4, mode="fisheye", device="cpu")
+
+
+def test_matcap_and_blur_match_scipy():
+    from scipy.interpolate import RegularGridInterpolator
+    from scipy.ndimage import gaussian_filter
+    from nglod_b200.lib.geoutils import MatcapSampler, gaussian_blur2d, spherical_envmap
+    rng = np.random.RandomState(0)
+    tex = rng.rand(17, 23, 3).astype(np.float32) * 255
+    uv = rng.rand(500, 2)
+    uv[:4] = [[0, 0], [1, 1], [0, 1], [1, 0]]
+    ref = RegularGridInterpolator((np.linspace(0, 1, 17), np.linspace(0, 1, 23)), tex)(uv)
+    got = MatcapSampler(torch.from_numpy(tex))(torch.from_numpy(uv).float()).numpy()
+    assert np.abs(got - ref).max() < 1e-2            # fp32 vs fp64 on values up to 255
+    img = rng.rand(31, 18).astype(np.float32)
+    assert np.abs(gaussian_blur2d(torch.from_numpy(img), 2.0).numpy() - gaussian_filter(img, sigma=2)).max() < 1e-6
+    small = rng.rand(5, 40).astype(np.float32)       # image narrower than the 8-pixel kernel radius
+    assert np.abs(gaussian_blur2d(torch.from_numpy(small), 2.0).numpy() - gaussian_filter(small, sigma=2)).max() < 1e-6
+    n = torch.nn.functional.normalize(torch.randn(50, 3), dim=1)
+    v = torch.nn.functional.normalize(torch.randn(50, 3), dim=1)
+    uvm = spherical_envmap(v, n)
+    assert uvm.shape == (50, 2) and float(uvm.min()) >= 0 and float(uvm.max()) <= 1
+
+
+def test_samplers_and_meshes():
+    from nglod_b200.lib.torchgp import (icosphere, torus, point_sample, sample_surface, normalize,
+                                        area_weighted_distribution, load_obj, write_obj)
+    V, F = icosphere(2)
+    assert V.shape == (162, 3) and F.shape == (320, 3)
+    assert torch.allclose(V.norm(dim=1), torch.ones(162), atol=1e-6)
+    tri = V[F]
+    nrm = torch.linalg.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0])
+    assert ((nrm * tri.mean(dim=1)).sum(-1) > 0).all()            # outward winding
+    Vt, Ft = torus(nu=16, nv=8)
+    assert Vt.shape == (128, 3) and Ft.shape == (256, 3)
+    # closed manifold: every edge is shared by exactly two triangles
+    e = torch.cat([Ft[:, [0, 1]], Ft[:, [1, 2]], Ft[:, [2, 0]]]).sort(dim=1)[0]
+    _, counts = torch.unique(e, dim=0, return_counts=True)
+    assert (counts == 2).all()
+    Vn, _ = normalize(Vt * 3 + 1.5, Ft)
+    assert abs(float(Vn.norm(dim=1).max()) - 1.0) < 1e-6
+    torch.manual_seed(0)
+    pts = point_sample(V, F, ["rand", "near", "trace"], 1000)
+    assert pts.shape == (3000, 3)
+    assert (pts[:1000].abs() <= 1).all()
+    assert (pts[2000:].norm(dim=1) <= 1 + 1e-6).all() and (pts[2000:].norm(dim=1) > 0.93).all()
+    s, n = sample_surface(V, F, 10)
+    assert s.shape == (10, 3) and n.shape == (10, 3)
+    dist = area_weighted_distribution(V, F)
+    assert abs(float(dist.probs.sum()) - 1) < 1e-5
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "m.obj")
+        write_obj(path, V, F)
+        V2, F2 = load_obj(path)
+        assert torch.allclose(V2, V, atol=1e-6) and torch.equal(F2, F)
+        with open(path, "a") as fh:
+            fh.write("f 1/1/1 2/2/2 3/3/3 4/4/4\n")              # a quad with v/vt/vn indices
+        _, F3 = load_obj(path)
+        assert F3.shape[0] == F.shape[0] + 2
+
+
+def test_shard_helpers():
+    from nglod_b200.dist import shard_range, interleaved_strips
+    for n, w, al in ((921600, 8, 720), (10, 4, 1), (7, 8, 1), (1000, 3, 16)):
+        cover = []
+        for r in range(w):
+            s, e = shard_range(n, r, w, al)
+            assert 0 <= s <= e <= n and (s % al == 0)
+            cover += list(range(s, e))
+        assert cover == list(range(n))
+    cols = sorted(c for r in range(4) for c0, c1 in interleaved_strips(1280, r, 4) for c in range(c0, c1))
+    assert cols == list(range(1280))
+    assert len(interleaved_strips(1280, 0, 4, strips_per_rank=4)) == 4
