@@ -26,8 +26,12 @@
 extern "C" {
 #endif
 
-#define NGLOD_ABI_VERSION 1
+#define NGLOD_ABI_VERSION 2
 #define NGLOD_MAX_LODS 8
+
+/* nglod_net_t.math_mode */
+#define NGLOD_MATH_TC3XTF32 0 /* tcgen05 tensor cores, 3-pass split TF32 (FP32-level accuracy, |err| ~1e-6) */
+#define NGLOD_MATH_FP32 1     /* CUDA cores, plain FP32 (|err| ~1e-7); the correctness anchor            */
 
 /* argument-error codes (disjoint from cudaError_t values we can hit) */
 #define NGLOD_EINVAL 10001   /* null pointer / negative size / bad lod        */
@@ -53,6 +57,8 @@ typedef struct nglod_net {
     int32_t feature_dim;    /* 32 on the headline config                       */
     int32_t hidden_dim;     /* 128 on the headline config                      */
     int32_t pos_invariant;  /* 0: decoder input is [x,y,z,feat]; 1: [feat]     */
+    int32_t math_mode;      /* NGLOD_MATH_* : how the 35->128 contraction runs  */
+    int32_t reserved_;      /* keeps the pointer arrays 8-byte aligned          */
     int32_t grid_res[NGLOD_MAX_LODS];
     const float* grids[NGLOD_MAX_LODS];
     const float* w0[NGLOD_MAX_LODS];
@@ -76,6 +82,10 @@ typedef struct nglod_net_grad {
 int nglod_abi_version(void);
 /* static string: build arch, flags; never null */
 const char* nglod_build_info(void);
+
+/* Self-test of the tensor-core plumbing: D[128,128] = A[128,40] * B[128,40]^T (row-major fp32 device
+ * buffers) through the same operand layout / descriptors / 3xTF32 sequence / TMEM read-back as the SDF kernels. */
+int nglod_debug_tc_gemm(const float* A, const float* B, float* D, void* stream);
 
 /* ---- ray vs unit cube ---------------------------------------------------
  * Replaces: f_aabb / aabb_kernel, sdf-net/lib/extensions/sol_nglod/

@@ -10,6 +10,8 @@ import ctypes
 import os
 
 MAX_LODS = 8
+MATH_TC3XTF32 = 0
+MATH_FP32 = 1
 EINVAL = 10001
 EUNSUPPORTED = 10002
 
@@ -28,6 +30,8 @@ class NetStruct(ctypes.Structure):
         ("feature_dim", c_int32),
         ("hidden_dim", c_int32),
         ("pos_invariant", c_int32),
+        ("math_mode", c_int32),
+        ("reserved_", c_int32),
         ("grid_res", c_int32 * MAX_LODS),
         ("grids", c_void_p * MAX_LODS),
         ("w0", c_void_p * MAX_LODS),
@@ -64,6 +68,7 @@ class TraceOpts(ctypes.Structure):
 SIGNATURES = {
     "nglod_abi_version": (ctypes.c_int, []),
     "nglod_build_info": (ctypes.c_char_p, []),
+    "nglod_debug_tc_gemm": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "nglod_aabb": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "nglod_sdf_forward": (ctypes.c_int, [ctypes.POINTER(NetStruct), c_int32, c_void_p, c_int64, c_void_p, c_void_p]),
     "nglod_sdf_forward_all": (ctypes.c_int, [ctypes.POINTER(NetStruct), c_void_p, c_int64, c_void_p, c_void_p]),

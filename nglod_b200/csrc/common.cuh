@@ -39,8 +39,9 @@ static inline int nglod_check_net(const nglod_net_t* net, int lod) {
     if (net->num_lods < 1 || net->num_lods > NGLOD_MAX_LODS) return NGLOD_EINVAL;
     if (lod < 0 || lod >= net->num_lods) return NGLOD_EINVAL;
     if (net->feature_dim != NGLOD_F || net->hidden_dim != NGLOD_H) return NGLOD_EUNSUPPORTED;
+    if (net->math_mode != NGLOD_MATH_TC3XTF32 && net->math_mode != NGLOD_MATH_FP32) return NGLOD_EINVAL;
     for (int i = 0; i <= lod; ++i) {
-        if (!net->grids[i] || net->grid_res[i] < 1 || net->grid_res[i] > 1024) return NGLOD_EINVAL;
+        if (!net->grids[i] || net->grid_res[i] < 1 || net->grid_res[i] > 256) return NGLOD_EINVAL;  // 32-bit element offsets
         if ((reinterpret_cast<uintptr_t>(net->grids[i]) & 15u) != 0) return NGLOD_EINVAL;
     }
     if (!net->w0[lod] || !net->b0[lod] || !net->w1[lod] || !net->b1[lod]) return NGLOD_EINVAL;

@@ -211,5 +211,7 @@ extern "C" int nglod_adam_step(float* param, const float* grad, float* exp_avg, 
 
 extern "C" int nglod_abi_version(void) { return NGLOD_ABI_VERSION; }
 extern "C" const char* nglod_build_info(void) {
-    return "nglod_b200 sm_100a (compute_100a) nvcc " __VERSION__ " built " __DATE__;
+#define NGLOD_STR2(x) #x
+#define NGLOD_STR(x) NGLOD_STR2(x)
+    return "nglod_b200 sm_100a (compute_100a) nvcc " NGLOD_STR(__CUDACC_VER_MAJOR__) "." NGLOD_STR(__CUDACC_VER_MINOR__) " built " __DATE__;
 }

@@ -1,6 +1,7 @@
 // nglod_b200 -- OctreeSDF.sdf forward, finite-difference gradient (FP32 path).
 // Reference behaviour: sdf-net/lib/models/OctreeSDF.py:94-155, sdf-net/lib/diffutils.py:61-70.
 #include "sdf_core.cuh"
+#include "internal.h"
 
 namespace {
 
@@ -107,8 +108,9 @@ extern "C" int nglod_sdf_forward(const nglod_net_t* net, int32_t lod, const floa
     if (int e = nglod_check_net(net, lod)) return e;
     if (n < 0 || (n > 0 && (!x || !out))) return NGLOD_EINVAL;
     if (n == 0) return 0;
-    NGLOD_CUDA_TRY(cudaFuncSetAttribute(sdf_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SDF_SMEM_BYTES));
     const NetDev nd = nglod_make_netdev(net, lod);
+    if (net->math_mode == NGLOD_MATH_TC3XTF32) return nglod_launch_sdf_forward_tc(nd, x, (long long)n, out, (cudaStream_t)stream);
+    NGLOD_CUDA_TRY(cudaFuncSetAttribute(sdf_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SDF_SMEM_BYTES));
     const int grid = launch_grid((const void*)sdf_forward_kernel, n);
     sdf_forward_kernel<<<grid, SDF_THREADS, SDF_SMEM_BYTES, (cudaStream_t)stream>>>(nd, x, (long long)n, out);
     return (int)cudaGetLastError();

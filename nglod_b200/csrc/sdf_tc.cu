@@ -1,0 +1,137 @@
+// nglod_b200 -- OctreeSDF.sdf forward with the decoder on tcgen05 tensor cores (3xTF32, TMEM accumulator).
+// See sdf_tc.cuh / tc_common.cuh for the scheme.  Reference behaviour: sdf-net/lib/models/OctreeSDF.py:94-146.
+#include "sdf_tc.cuh"
+#include "internal.h"
+
+namespace {
+
+constexpr int FWD_GROUPS = 3;                       // 3 x 128 threads per CTA, one CTA per SM
+constexpr int FWD_THREADS = FWD_GROUPS * TCG_THREADS;
+constexpr int FWD_SMEM = TC_SMEM_BYTES(FWD_GROUPS);
+
+__device__ __forceinline__ TcGroup tc_make_group(char* smem, int G, uint32_t tmem_base) {
+    TcGroup g;
+    const int warp = threadIdx.x >> 5;
+    const int grp = warp >> 2;
+    g.wq = warp & 3;
+    g.lane = threadIdx.x & 31;
+    g.a_hi = smem + TC_SMEM_A(grp);
+    g.a_lo = g.a_hi + TC_OPERAND_BYTES;
+    g.a_hi_s = smem_u32(g.a_hi);
+    g.a_lo_s = smem_u32(g.a_lo);
+    g.b_hi_s = smem_u32(smem + TC_SMEM_B_HI);
+    g.b_lo_s = smem_u32(smem + TC_SMEM_B_LO);
+    g.mbar_s = smem_u32(smem + TC_SMEM_MBAR(G) + 8 * grp);
+    g.tmem_acc = tmem_base + (uint32_t)(grp * TC_N);
+    g.tmem_row = g.tmem_acc + ((uint32_t)(g.wq * 32) << 16);
+    char* scratch = smem + TC_SMEM_SCRATCH(G) + warp * TC_WARP_SCRATCH_BYTES;
+    g.pack = reinterpret_cast<float4*>(scratch);
+    g.idx = reinterpret_cast<int*>(scratch + TC_PACK_LODS * 32 * 16);
+    g.w1 = reinterpret_cast<const float*>(smem + TC_SMEM_W1(G));
+    g.bar_id = 1 + grp;
+    g.parity = 0;
+    return g;
+}
+
+// Common prologue: zero the operand buffers, stage weights, init mbarriers, allocate TMEM.  Returns the TMEM base.
+__device__ __forceinline__ uint32_t tc_prologue(const NetDev& net, char* smem, int G) {
+    for (int e = threadIdx.x; e < (TC_SMEM_SCRATCH(G) + G * 4 * TC_WARP_SCRATCH_BYTES) / 16; e += blockDim.x)
+        reinterpret_cast<float4*>(smem)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    tc_stage_weights(net, smem, G);
+    if (threadIdx.x == 0) {
+        for (int g = 0; g < G; ++g) mbar_init(smem_u32(smem + TC_SMEM_MBAR(G) + 8 * g), 1);
+        mbar_fence_init();
+    }
+    if (threadIdx.x < 32) tmem_alloc(smem_u32(smem + TC_SMEM_TMEMPTR(G)), 512);
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    return *reinterpret_cast<volatile uint32_t*>(smem + TC_SMEM_TMEMPTR(G));
+}
+
+__device__ __forceinline__ void tc_epilogue_free(uint32_t tmem_base) {
+    tc_fence_before_sync();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(tmem_base, 512);
+}
+
+__global__ void __launch_bounds__(FWD_THREADS, 1)
+sdf_forward_tc_kernel(const NetDev net, const float* __restrict__ x, const long long n, float* __restrict__ out) {
+    extern __shared__ __align__(128) char smem_tc[];
+    const uint32_t tmem_base = tc_prologue(net, smem_tc, FWD_GROUPS);
+    TcGroup g = tc_make_group(smem_tc, FWD_GROUPS, tmem_base);
+    const long long ggroup = (long long)blockIdx.x * FWD_GROUPS + (threadIdx.x >> 7);
+    const long long ngroups = (long long)gridDim.x * FWD_GROUPS;
+    for (long long tile = ggroup; tile * TCG_THREADS < n; tile += ngroups) {
+        const long long i = tile * TCG_THREADS + g.wq * 32 + g.lane;
+        const bool active = i < n;
+        float px = 0.f, py = 0.f, pz = 0.f;
+        if (active) { px = __ldg(x + 3 * i); py = __ldg(x + 3 * i + 1); pz = __ldg(x + 3 * i + 2); }
+        const float d = tc_group_eval(net, g, px, py, pz, active);
+        if (active) out[i] = d;
+    }
+    tc_epilogue_free(tmem_base);
+}
+
+// Debug / self-test: D[128,128] = A[128,40] * B[128,40]^T through the exact operand layout, descriptors,
+// 3xTF32 issue sequence and TMEM read-back the SDF kernels use.
+__global__ void __launch_bounds__(128, 1)
+tc_gemm_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D) {
+    extern __shared__ __align__(128) char smem_tc[];
+    char* b_hi = smem_tc; char* b_lo = smem_tc + TC_OPERAND_BYTES;
+    char* a_hi = smem_tc + 2 * TC_OPERAND_BYTES; char* a_lo = a_hi + TC_OPERAND_BYTES;
+    char* misc = smem_tc + 4 * TC_OPERAND_BYTES;
+    for (int e = threadIdx.x; e < 128 * TC_K; e += 128) {
+        const int r = e / TC_K, k = e - r * TC_K;
+        const uint32_t off = tc_elem_offset(r, k);
+        float v = A[e], h = tf32_hi(v);
+        *reinterpret_cast<float*>(a_hi + off) = h; *reinterpret_cast<float*>(a_lo + off) = v - h;
+        v = B[e]; h = tf32_hi(v);
+        *reinterpret_cast<float*>(b_hi + off) = h; *reinterpret_cast<float*>(b_lo + off) = v - h;
+    }
+    const uint32_t mbar = smem_u32(misc);
+    if (threadIdx.x == 0) { mbar_init(mbar, 1); mbar_fence_init(); }
+    if (threadIdx.x < 32) tmem_alloc(smem_u32(misc + 8), 128);
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(misc + 8);
+    if (threadIdx.x == 0) {
+        tc_issue_tile(tmem_base, smem_u32(a_hi), smem_u32(a_lo), smem_u32(b_hi), smem_u32(b_lo));
+        tc_commit(mbar);
+    }
+    mbar_wait(mbar, 0);
+    tc_fence_after_sync();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int cb = 0; cb < 4; ++cb) {
+        float v[32];
+        tmem_ld32(trow + cb * 32, v);
+        for (int j = 0; j < 32; ++j) D[(warp * 32 + lane) * 128 + cb * 32 + j] = v[j];
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(tmem_base, 128);
+}
+
+}  // namespace
+
+int nglod_launch_sdf_forward_tc(const NetDev& nd, const float* x, long long n, float* out, cudaStream_t st) {
+    NGLOD_CUDA_TRY(cudaFuncSetAttribute(sdf_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+    long long grid = nglod_sm_count();
+    const long long want = (n + FWD_THREADS - 1) / FWD_THREADS;
+    if (want < grid) grid = want;
+    sdf_forward_tc_kernel<<<(int)grid, FWD_THREADS, FWD_SMEM, st>>>(nd, x, n, out);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int nglod_debug_tc_gemm(const float* A, const float* B, float* D, void* stream) {
+    if (!A || !B || !D) return NGLOD_EINVAL;
+    const int smem = 4 * TC_OPERAND_BYTES + 64;
+    NGLOD_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    tc_gemm_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D);
+    return (int)cudaGetLastError();
+}

@@ -15,7 +15,7 @@ import torch.nn as nn
 from torch.autograd.function import once_differentiable
 
 from .BaseLOD import BaseLOD
-from ... import ops
+from ... import ops, _lib
 
 
 class FeatureVolume(nn.Module):
@@ -79,6 +79,8 @@ class OctreeSDF(BaseLOD):
         self.features = nn.ModuleList(
             [FeatureVolume(self.fdim, 2 ** (i + self.args.base_lod)) for i in range(self.args.num_lods)])
         self.interpolate = self.args.interpolate
+        # how the 35->128 contraction runs: "tc" = tcgen05 3xTF32 (|err| ~1e-6), "fp32" = CUDA cores (|err| ~1e-7)
+        self.math_mode = getattr(args, "math_mode", None) or "fp32"
 
         self.sdf_input_dim = self.fdim + (0 if self.pos_invariant else self.input_dim)
         self.num_decoder = 1 if args.joint_decoder else self.args.num_lods
@@ -96,7 +98,8 @@ class OctreeSDF(BaseLOD):
         """Borrow the current parameters as an nglod_net_t (rebuilt per call: pointers may move)."""
         grids = [f.fm.data for f in self.features]
         decs = [tuple(p.data for p in self.decoder_params(i)) for i in range(self.num_lods)]
-        return ops.NetView(grids, decs, pos_invariant=self.pos_invariant)
+        return ops.NetView(grids, decs, pos_invariant=self.pos_invariant,
+                           math_mode=_lib.MATH_TC3XTF32 if self.math_mode == "tc" else _lib.MATH_FP32)
 
     def _eval_lod(self, x, lod):
         shape = x.shape

@@ -39,7 +39,7 @@ class NetView:
     Keeps the tensors alive for as long as the view is.
     """
 
-    def __init__(self, grids, decoders, pos_invariant=False):
+    def __init__(self, grids, decoders, pos_invariant=False, math_mode=0):
         self.grids = grids
         self.decoders = decoders
         n = len(grids)
@@ -50,6 +50,7 @@ class NetView:
         s.feature_dim = grids[0].shape[1]
         s.hidden_dim = decoders[0][0].shape[0]
         s.pos_invariant = 1 if pos_invariant else 0
+        s.math_mode = int(math_mode)
         for i, g in enumerate(grids):
             if not g.is_cuda:
                 raise RuntimeError("OctreeSDF parameters must live on a CUDA device (no CPU path)")

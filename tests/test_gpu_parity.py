@@ -374,3 +374,50 @@ def test_fails_loudly_instead_of_falling_back():
     assert lib.nglod_aabb(None, None, 5, None, None, None, None) == _lib.EINVAL
     assert lib.nglod_mesh2sdf(None, -1, None, 0, None, None) == _lib.EINVAL
     assert lib.nglod_aabb(None, None, 0, None, None, None, None) == 0
+
+
+# ------------------------------------------------------------------------------------------------ tensor-core path
+def test_tc_gemm_selftest():
+    """The tcgen05 plumbing in isolation: operand layout, descriptors, 3xTF32 sequence, TMEM read-back."""
+    from nglod_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(3)
+    A = torch.randn(128, 40, generator=g)
+    B = torch.randn(128, 40, generator=g)
+    A[:, 36:] = 0
+    D = torch.full((128, 128), float("nan"), device=DEV)
+    Ad, Bd = A.to(DEV), B.to(DEV)
+    rc = lib.nglod_debug_tc_gemm(ctypes.c_void_p(Ad.data_ptr()), ctypes.c_void_p(Bd.data_ptr()),
+                                 ctypes.c_void_p(D.data_ptr()), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    torch.cuda.synchronize()
+    ref = (A.double() @ B.double().T)
+    err = (D.cpu().double() - ref).abs().max().item()
+    print(f"tc gemm 3xTF32 max abs err {err:.3e} (|ref| max {ref.abs().max():.1f})")
+    assert err < 2e-5            # single-pass TF32 would be ~1e-2 here
+
+
+def test_sdf_forward_tensor_core_vs_golden(rand5, fit3):
+    net, _ = rand5_model(DEV)
+    net.math_mode = "tc"
+    x = torch.from_numpy(rand5["x"]).to(DEV)
+    with torch.no_grad():
+        for l in range(5):
+            err = np.abs(net.sdf(x, lod=l).cpu().numpy() - rand5[f"sdf_lod{l}"]).max()
+            print(f"tc sdf lod{l} max err {err:.2e}")
+            assert err < 5e-6
+    net3, _ = fit3_model(fit3, DEV)
+    net3.math_mode = "tc"
+    x3 = torch.from_numpy(fit3["x"]).to(DEV)
+    with torch.no_grad():
+        for l in range(3):
+            err = np.abs(net3.sdf(x3, lod=l).cpu().numpy() - fit3[f"sdf_lod{l}"]).max()
+            print(f"tc sdf fit3 lod{l} max err {err:.2e}")
+            assert err < 5e-6
+        for n in (1, 127, 129, 1000, 100001):
+            xx = torch.rand(n, 3, device=DEV) * 2.4 - 1.2
+            net3.math_mode = "tc"
+            a = net3.sdf(xx, lod=2)
+            net3.math_mode = "fp32"
+            b = net3.sdf(xx, lod=2)
+            assert (a - b).abs().max() < 5e-6
