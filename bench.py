@@ -34,6 +34,7 @@ NUM_LODS = 5
 CAM_FROM, CAM_TO, FOV = [-2.8, 2.8, -2.8], [0.0, 0.0, 0.0], 30.0
 FIT_STEPS, FIT_BATCH = 300, 65536
 SDF_N = 1 << 20
+MATH_MODE = os.environ.get("NGLOD_MATH", "tc")      # "tc" = tcgen05 3xTF32 decoder, "fp32" = CUDA cores
 GATHER_BYTES_PER_QUERY = (LOD + 1) * 8 * 32 * 4          # fp32 grids: 5120 B  
 IO_BYTES_PER_QUERY = 16
 RAY_IO_BYTES = 24 + 12 + 4 + 1 + 12                        # ray_o, ray_d in; x, depth, hit, normal out
@@ -136,6 +137,7 @@ def build_and_fit(device, log):
          "--render-res", str(W), str(H)])
     torch.manual_seed(0)
     net = OctreeSDF(args).to(device)
+    net.math_mode = MATH_MODE
     t0 = time.time()
     ds = MeshDataset(args, mesh=torus(0.6, 0.25, 128, 64), device=device)       # 500 000 labelled points
     torch.cuda.synchronize()
@@ -298,7 +300,7 @@ def run_ours(ns):
                                "hidden=128 fitted in-run to a procedural torus mesh (BASELINE.json configs[1])",
                    "rays_per_gpu_step": n_rays, "fps_per_gpu": 1e3 / (total_ms / ns.steps),
                    "sdf_evals_per_ray": n_eval / n_rays, "hit_fraction": n_hit / n_rays,
-                   "num_steps": 256, "l2": "flushed between timed iterations (256 MB memset)",
+                   "num_steps": 256, "math_mode": MATH_MODE, "l2": "flushed between timed iterations (256 MB memset)",
                    "parallelism": f"one frame per GPU x{world}, no collective"},
         "e2e": {"value": world * n_rays * ns.steps / e2e_s, "unit": "rays/s",
                 "h2d_bytes_per_step": n_rays * 24, "d2h_bytes_per_step": n_rays * (12 + 4 + 1 + 12),

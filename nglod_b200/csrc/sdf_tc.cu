@@ -9,54 +9,6 @@ constexpr int FWD_GROUPS = 3;                       // 3 x 128 threads per CTA, 
 constexpr int FWD_THREADS = FWD_GROUPS * TCG_THREADS;
 constexpr int FWD_SMEM = TC_SMEM_BYTES(FWD_GROUPS);
 
-__device__ __forceinline__ TcGroup tc_make_group(char* smem, int G, uint32_t tmem_base) {
-    TcGroup g;
-    const int warp = threadIdx.x >> 5;
-    const int grp = warp >> 2;
-    g.wq = warp & 3;
-    g.lane = threadIdx.x & 31;
-    g.a_hi = smem + TC_SMEM_A(grp);
-    g.a_lo = g.a_hi + TC_OPERAND_BYTES;
-    g.a_hi_s = smem_u32(g.a_hi);
-    g.a_lo_s = smem_u32(g.a_lo);
-    g.b_hi_s = smem_u32(smem + TC_SMEM_B_HI);
-    g.b_lo_s = smem_u32(smem + TC_SMEM_B_LO);
-    g.mbar_s = smem_u32(smem + TC_SMEM_MBAR(G) + 8 * grp);
-    g.tmem_acc = tmem_base + (uint32_t)(grp * TC_N);
-    g.tmem_row = g.tmem_acc + ((uint32_t)(g.wq * 32) << 16);
-    char* scratch = smem + TC_SMEM_SCRATCH(G) + warp * TC_WARP_SCRATCH_BYTES;
-    g.pack = reinterpret_cast<float4*>(scratch);
-    g.idx = reinterpret_cast<int*>(scratch + TC_PACK_LODS * 32 * 16);
-    g.w1 = reinterpret_cast<const float*>(smem + TC_SMEM_W1(G));
-    g.bar_id = 1 + grp;
-    g.parity = 0;
-    return g;
-}
-
-// Common prologue: zero the operand buffers, stage weights, init mbarriers, allocate TMEM.  Returns the TMEM base.
-__device__ __forceinline__ uint32_t tc_prologue(const NetDev& net, char* smem, int G) {
-    for (int e = threadIdx.x; e < (TC_SMEM_SCRATCH(G) + G * 4 * TC_WARP_SCRATCH_BYTES) / 16; e += blockDim.x)
-        reinterpret_cast<float4*>(smem)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
-    tc_stage_weights(net, smem, G);
-    if (threadIdx.x == 0) {
-        for (int g = 0; g < G; ++g) mbar_init(smem_u32(smem + TC_SMEM_MBAR(G) + 8 * g), 1);
-        mbar_fence_init();
-    }
-    if (threadIdx.x < 32) tmem_alloc(smem_u32(smem + TC_SMEM_TMEMPTR(G)), 512);
-    fence_proxy_async_smem();
-    tc_fence_before_sync();
-    __syncthreads();
-    tc_fence_after_sync();
-    return *reinterpret_cast<volatile uint32_t*>(smem + TC_SMEM_TMEMPTR(G));
-}
-
-__device__ __forceinline__ void tc_epilogue_free(uint32_t tmem_base) {
-    tc_fence_before_sync();
-    __syncthreads();
-    if (threadIdx.x < 32) tmem_dealloc(tmem_base, 512);
-}
-
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 sdf_forward_tc_kernel(const NetDev net, const float* __restrict__ x, const long long n, float* __restrict__ out) {
     extern __shared__ __align__(128) char smem_tc[];

@@ -188,3 +188,63 @@ __device__ __forceinline__ float tc_group_eval(const NetDev& net, TcGroup& g, fl
     tc_fence_after_sync();
     return tc_epilogue(g.tmem_row, g.w1);
 }
+
+__device__ __forceinline__ TcGroup tc_make_group(char* smem, int G, uint32_t tmem_base) {
+    TcGroup g;
+    const int warp = threadIdx.x >> 5;
+    const int grp = warp >> 2;
+    g.wq = warp & 3;
+    g.lane = threadIdx.x & 31;
+    g.a_hi = smem + TC_SMEM_A(grp);
+    g.a_lo = g.a_hi + TC_OPERAND_BYTES;
+    g.a_hi_s = smem_u32(g.a_hi);
+    g.a_lo_s = smem_u32(g.a_lo);
+    g.b_hi_s = smem_u32(smem + TC_SMEM_B_HI);
+    g.b_lo_s = smem_u32(smem + TC_SMEM_B_LO);
+    g.mbar_s = smem_u32(smem + TC_SMEM_MBAR(G) + 8 * grp);
+    g.tmem_acc = tmem_base + (uint32_t)(grp * TC_N);
+    g.tmem_row = g.tmem_acc + ((uint32_t)(g.wq * 32) << 16);
+    char* scratch = smem + TC_SMEM_SCRATCH(G) + warp * TC_WARP_SCRATCH_BYTES;
+    g.pack = reinterpret_cast<float4*>(scratch);
+    g.idx = reinterpret_cast<int*>(scratch + TC_PACK_LODS * 32 * 16);
+    g.w1 = reinterpret_cast<const float*>(smem + TC_SMEM_W1(G));
+    g.bar_id = 1 + grp;
+    g.parity = 0;
+    return g;
+}
+
+// Common prologue: zero the operand buffers, stage weights, init mbarriers, allocate TMEM.  Returns the TMEM base.
+__device__ __forceinline__ uint32_t tc_prologue(const NetDev& net, char* smem, int G) {
+    for (int e = threadIdx.x; e < (TC_SMEM_SCRATCH(G) + G * 4 * TC_WARP_SCRATCH_BYTES) / 16; e += blockDim.x)
+        reinterpret_cast<float4*>(smem)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    tc_stage_weights(net, smem, G);
+    if (threadIdx.x == 0) {
+        for (int g = 0; g < G; ++g) mbar_init(smem_u32(smem + TC_SMEM_MBAR(G) + 8 * g), 1);
+        mbar_fence_init();
+    }
+    if (threadIdx.x < 32) tmem_alloc(smem_u32(smem + TC_SMEM_TMEMPTR(G)), 512);
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    return *reinterpret_cast<volatile uint32_t*>(smem + TC_SMEM_TMEMPTR(G));
+}
+
+__device__ __forceinline__ void tc_epilogue_free(uint32_t tmem_base) {
+    tc_fence_before_sync();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(tmem_base, 512);
+}
+
+
+// OR-reduce a predicate over the 128 threads of a group (also a barrier).
+__device__ __forceinline__ bool tc_group_any(int bar_id, bool pred) {
+    uint32_t r;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+        "bar.red.or.pred p, %2, %3, q;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(r) : "r"((uint32_t)pred), "r"(bar_id), "r"(TCG_THREADS) : "memory");
+    return r != 0;
+}

@@ -22,6 +22,7 @@
 // atomic queue (ballot + popc ranks), so lanes stay occupied until the frame
 // runs dry: no host round trip, no per-step launches, no cond.any() sync.
 #include "sdf_core.cuh"
+#include "sdf_tc.cuh"
 #include "aabb.cuh"
 
 namespace {
@@ -34,18 +35,34 @@ struct TraceParams {
     float step_size, min_dis, min_dis3, far, h, two_h;
 };
 
-__global__ void __launch_bounds__(SDF_THREADS, 2)
+constexpr int TRACE_TC_GROUPS = 3;
+constexpr int TRACE_TC_THREADS = TRACE_TC_GROUPS * TCG_THREADS;
+constexpr int TRACE_TC_SMEM = TC_SMEM_BYTES(TRACE_TC_GROUPS);
+
+// TC = false: FP32 CUDA-core decoder, warps are independent (8 per CTA, 2 CTAs/SM).
+// TC = true : tcgen05 decoder; 4 warps form a 128-row MMA tile and advance in lock-step rounds (3 groups per CTA).
+template <bool TC>
+__global__ void __launch_bounds__(TC ? TRACE_TC_THREADS : SDF_THREADS, TC ? 1 : 2)
 sphere_trace_kernel(const NetDev net, const float* __restrict__ ray_o, const float* __restrict__ ray_d,
                     const long long n, const TraceParams tp, float* __restrict__ out_x,
                     float* __restrict__ out_t, uint8_t* __restrict__ out_hit, float* __restrict__ out_n,
                     int* __restrict__ queue, unsigned long long* __restrict__ stats) {
-    extern __shared__ __align__(16) float smem[];
-    sdf_stage_weights(net, smem);
+    extern __shared__ __align__(128) char smem_raw[];
+    float* smem = reinterpret_cast<float*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* tile = smem + SDF_SMEM_WARP_OFF + warp * SDF_SMEM_PER_WARP;
-    int* idx = reinterpret_cast<int*>(tile + SDF_TILE_FLOATS);
-    for (int e = lane; e < SDF_SMEM_PER_WARP; e += 32) tile[e] = 0.f;
-    __syncthreads();
+    float* tile = nullptr; int* idx = nullptr;
+    uint32_t tmem_base = 0;
+    TcGroup grp;
+    if constexpr (TC) {
+        tmem_base = tc_prologue(net, smem_raw, TRACE_TC_GROUPS);
+        grp = tc_make_group(smem_raw, TRACE_TC_GROUPS, tmem_base);
+    } else {
+        sdf_stage_weights(net, smem);
+        tile = smem + SDF_SMEM_WARP_OFF + warp * SDF_SMEM_PER_WARP;
+        idx = reinterpret_cast<int*>(tile + SDF_TILE_FLOATS);
+        for (int e = lane; e < SDF_SMEM_PER_WARP; e += 32) tile[e] = 0.f;
+        __syncthreads();
+    }
 
     // per-lane ray slot
     int phase = PH_EMPTY, step = 0;
@@ -115,9 +132,14 @@ sphere_trace_kernel(const NetDev net, const float* __restrict__ ray_o, const flo
         }
         const bool occupied = phase != PH_EMPTY;
         const unsigned act = __ballot_sync(0xffffffffu, occupied);
-        if (!act) {
-            if (exhausted) break;
-            continue;
+        if constexpr (TC) {
+            // the 4 warps of a tile leave together: keep going while any slot is occupied or any queue is not dry
+            if (!tc_group_any(grp.bar_id, occupied || !exhausted)) break;
+        } else {
+            if (!act) {
+                if (exhausted) break;
+                continue;
+            }
         }
         // ---- this round's query point
         float qx = x, qy = y, qz = z;
@@ -127,7 +149,9 @@ sphere_trace_kernel(const NetDev net, const float* __restrict__ ray_o, const flo
             const int axis = m >> 1;
             if (axis == 0) qx = x + e; else if (axis == 1) qy = y + e; else qz = z + e;
         }
-        const float dv = warp_sdf_eval(net, smem, tile, idx, qx, qy, qz, occupied, lane);
+        float dv;
+        if constexpr (TC) dv = tc_group_eval(net, grp, qx, qy, qz, occupied);
+        else dv = warp_sdf_eval(net, smem, tile, idx, qx, qy, qz, occupied, lane);
         const unsigned march_mask = __ballot_sync(0xffffffffu, phase == PH_MARCH);
         if (lane == 0) {
             n_eval += __popc(act);
@@ -165,6 +189,7 @@ sphere_trace_kernel(const NetDev net, const float* __restrict__ ray_o, const flo
         atomicAdd(stats, n_eval);
         atomicAdd(stats + 1, n_march);
     }
+    if constexpr (TC) tc_epilogue_free(tmem_base);
 }
 
 }  // namespace
@@ -179,7 +204,6 @@ extern "C" int nglod_sphere_trace(const nglod_net_t* net, int32_t lod, const flo
     if (!ray_o || !ray_d || !x || !depth || !hit || !normal || !queue) return NGLOD_EINVAL;
     if (opts->num_steps < 0) return NGLOD_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
-    NGLOD_CUDA_TRY(cudaFuncSetAttribute(sphere_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SDF_SMEM_BYTES));
     NGLOD_CUDA_TRY(cudaMemsetAsync(queue, 0, sizeof(int32_t), st));
     TraceParams tp;
     tp.num_steps = opts->num_steps;
@@ -191,13 +215,25 @@ extern "C" int nglod_sphere_trace(const nglod_net_t* net, int32_t lod, const flo
     tp.h = (float)opts->normal_h;
     tp.two_h = (float)(opts->normal_h * 2.0);
     const NetDev nd = nglod_make_netdev(net, lod);
+    if (net->math_mode == NGLOD_MATH_TC3XTF32) {
+        auto kern = sphere_trace_kernel<true>;
+        NGLOD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TRACE_TC_SMEM));
+        long long grid = nglod_sm_count();
+        const long long want = (n + TRACE_TC_THREADS - 1) / TRACE_TC_THREADS;
+        if (want < grid) grid = want;
+        kern<<<(int)grid, TRACE_TC_THREADS, TRACE_TC_SMEM, st>>>(nd, ray_o, ray_d, (long long)n, tp, x, depth, hit,
+                                                                 normal, queue, stats);
+        return (int)cudaGetLastError();
+    }
+    auto kern = sphere_trace_kernel<false>;
+    NGLOD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SDF_SMEM_BYTES));
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sphere_trace_kernel, SDF_THREADS, SDF_SMEM_BYTES) != cudaSuccess || per_sm < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SDF_THREADS, SDF_SMEM_BYTES) != cudaSuccess || per_sm < 1)
         per_sm = 1;
     long long grid = (long long)nglod_sm_count() * per_sm;
     const long long want = (n + SDF_THREADS - 1) / SDF_THREADS;
     if (want < grid) grid = want;
-    sphere_trace_kernel<<<(int)grid, SDF_THREADS, SDF_SMEM_BYTES, st>>>(nd, ray_o, ray_d, (long long)n, tp, x, depth,
-                                                                        hit, normal, queue, stats);
+    kern<<<(int)grid, SDF_THREADS, SDF_SMEM_BYTES, st>>>(nd, ray_o, ray_d, (long long)n, tp, x, depth, hit, normal,
+                                                         queue, stats);
     return (int)cudaGetLastError();
 }

@@ -80,7 +80,7 @@ class OctreeSDF(BaseLOD):
             [FeatureVolume(self.fdim, 2 ** (i + self.args.base_lod)) for i in range(self.args.num_lods)])
         self.interpolate = self.args.interpolate
         # how the 35->128 contraction runs: "tc" = tcgen05 3xTF32 (|err| ~1e-6), "fp32" = CUDA cores (|err| ~1e-7)
-        self.math_mode = getattr(args, "math_mode", None) or "fp32"
+        self.math_mode = getattr(args, "math_mode", None) or "tc"
 
         self.sdf_input_dim = self.fdim + (0 if self.pos_invariant else self.input_dim)
         self.num_decoder = 1 if args.joint_decoder else self.args.num_lods

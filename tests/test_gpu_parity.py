@@ -67,6 +67,7 @@ def test_reference_kernel_available():
 # ------------------------------------------------------------------------------------------------ sdf forward
 def test_sdf_forward_vs_golden_and_oracle(rand5, fit3):
     net, _ = rand5_model(DEV)
+    net.math_mode = "fp32"                      # the CUDA-core correctness anchor (tensor-core path: see below)
     x = torch.from_numpy(rand5["x"]).to(DEV)
     net.eval()
     with torch.no_grad():
@@ -79,6 +80,7 @@ def test_sdf_forward_vs_golden_and_oracle(rand5, fit3):
         net.lod = 3
         assert np.abs(net(x).cpu().numpy() - rand5["forward_lod3"]).max() < 2e-6
     net3, _ = fit3_model(fit3, DEV)
+    net3.math_mode = "fp32"
     x3 = torch.from_numpy(fit3["x"]).to(DEV)
     with torch.no_grad():
         for l in range(3):
@@ -92,8 +94,10 @@ def test_sdf_forward_ragged_sizes(n):
     g = torch.Generator().manual_seed(n)
     x = torch.rand(n, 3, generator=g) * 2.4 - 1.2
     with torch.no_grad():
-        d = net.sdf(x.to(DEV), lod=4).cpu()
-        assert (d - onet.sdf(x, lod=4)).abs().max() < 2e-6
+        ref = onet.sdf(x, lod=4)
+        for mode in ("fp32", "tc"):
+            net.math_mode = mode
+            assert (net.sdf(x.to(DEV), lod=4).cpu() - ref).abs().max() < 2e-6
 
 
 def test_sdf_empty_and_batched_shapes():
@@ -220,9 +224,11 @@ def _check_trace(rb, gold, prefix, conv=None):
     return depth, nerr
 
 
-def test_sphere_tracer_vs_golden(rand5, fit3):
+@pytest.mark.parametrize("math_mode", ["fp32", "tc"])
+def test_sphere_tracer_vs_golden(rand5, fit3, math_mode):
     from nglod_b200.lib.tracer import SphereTracer
     net, args = rand5_model(DEV)
+    net.math_mode = math_mode
     net.lod = 4
     tracer = SphereTracer(args)
     rb = tracer(net, torch.from_numpy(rand5["t1_ray_o"]).to(DEV), torch.from_numpy(rand5["t1_ray_d"]).to(DEV))
@@ -231,6 +237,7 @@ def test_sphere_tracer_vs_golden(rand5, fit3):
                                           torch.from_numpy(rand5["t2_ray_d"]).to(DEV))
     _check_trace(rb, rand5, "t2")
     net3, args3 = fit3_model(fit3, DEV)
+    net3.math_mode = math_mode
     net3.lod = 2
     rb = SphereTracer(args3)(net3, torch.from_numpy(fit3["t1_ray_o"]).to(DEV), torch.from_numpy(fit3["t1_ray_d"]).to(DEV))
     depth, nerr = _check_trace(rb, fit3, "t1", conv=fit3["t1_converged"])
@@ -240,13 +247,15 @@ def test_sphere_tracer_vs_golden(rand5, fit3):
           f"all-hit depth max {depth[hit].max():.2e}, normal max {nerr[hit].max():.2e}")
 
 
-def test_sphere_tracer_vs_batch_loop_720p(fit3):
+@pytest.mark.parametrize("math_mode", ["fp32", "tc"])
+def test_sphere_tracer_vs_batch_loop_720p(fit3, math_mode):
     """Full 1280x720 frame: the persistent kernel against the reference's batch loop expressed with torch ops on
     the device, with the SAME sdf kernel as `net`.  The only arithmetic difference is x = o + d*t: torch's CUDA
     addcmul contracts it into an fma, the kernel follows the CPU reference (rounded product, then add; the golden
     vectors are CPU), so positions differ by <= 1 ulp and the iterated march by float noise."""
     from nglod_b200.lib.tracer import SphereTracer
     net3, args3 = fit3_model(fit3, DEV)
+    net3.math_mode = math_mode
     net3.lod = 2
     torch.manual_seed(5)
     o, d = O.look_at([-2.8, 2.8, -2.8], [0, 0, 0], 1280, 720, fov=30.0)
