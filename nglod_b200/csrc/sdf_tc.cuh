@@ -63,6 +63,65 @@ __device__ __forceinline__ void tc_axis(float p, int R, int& i0, float& w1, bool
     has1 = i0 < R;
 }
 
+// Sum of NL LODs' trilinear samples for channels [4c,4c+4) of the query whose set-up records are pack[l*32+q].
+template <int NL>
+__device__ __forceinline__ float4 tc_gather_one(const NetDev& net, int l0, const float4* pack, int q, int c, float4 acc) {
+    float4 P[NL];
+#pragma unroll
+    for (int l = 0; l < NL; ++l) P[l] = pack[l * 32 + q];
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        const uint32_t pk = __float_as_uint(P[l].x);
+        const int S = net.res[l0 + l] + 1;
+        const int o0 = (int)(pk & ~31u) + 4 * c;
+        const int dx = (pk & 1u) ? NGLOD_F : 0;
+        const int dy = (pk & 2u) ? S * NGLOD_F : 0;
+        const int dz = (pk & 4u) ? S * S * NGLOD_F : 0;
+        const float wx1 = P[l].y, wy1 = P[l].z, wz1 = P[l].w;
+        const float wx0 = 1.f - wx1, wy0 = 1.f - wy1, wz0 = 1.f - wz1;   // == (floor+1) - u exactly
+        const float* g = net.grids[l0 + l];
+        const int o2 = o0 + dy, o4 = o0 + dz, o6 = o4 + dy;
+        float4 v[8];
+        v[0] = ldg_f4(g + o0); v[1] = ldg_f4(g + o0 + dx);
+        v[2] = ldg_f4(g + o2); v[3] = ldg_f4(g + o2 + dx);
+        v[4] = ldg_f4(g + o4); v[5] = ldg_f4(g + o4 + dx);
+        v[6] = ldg_f4(g + o6); v[7] = ldg_f4(g + o6 + dx);
+        const float w00 = wx0 * wy0, w10 = wx1 * wy0, w01 = wx0 * wy1, w11 = wx1 * wy1;
+        const float w[8] = {w00 * wz0, w10 * wz0, w01 * wz0, w11 * wz0, w00 * wz1, w10 * wz1, w01 * wz1, w11 * wz1};
+        float4 s;
+        s.x = v[0].x * w[0]; s.y = v[0].y * w[0]; s.z = v[0].z * w[0]; s.w = v[0].w * w[0];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) {
+            s.x = fmaf(v[k].x, w[k], s.x); s.y = fmaf(v[k].y, w[k], s.y);
+            s.z = fmaf(v[k].z, w[k], s.z); s.w = fmaf(v[k].w, w[k], s.w);
+        }
+        // running sum across LODs (OctreeSDF.py:109-110)
+        acc.x = s.x + acc.x; acc.y = s.y + acc.y; acc.z = s.z + acc.z; acc.w = s.w + acc.w;
+    }
+    return acc;
+}
+
+template <int NL>
+__device__ __forceinline__ void tc_gather_rounds(const NetDev& net, int l0, int n_live, char* a_hi, char* a_lo,
+                                                 int row0, const float4* pack, const int* idx, int lane) {
+    const int sub = lane >> 3, c = lane & 7;
+    for (int r = 0; r * 4 < n_live; ++r) {
+        const int slot = r * 4 + sub;
+        if (slot < n_live) {
+            const int q = idx[slot];
+            const uint32_t row_off = tc_elem_offset(row0 + q, 4 * c);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (l0 > 0) {       // more than TC_PACK_LODS grids: continue the running sum (hi + lo is exact)
+                const float4 h = *reinterpret_cast<const float4*>(a_hi + row_off);
+                const float4 lo = *reinterpret_cast<const float4*>(a_lo + row_off);
+                acc = make_float4(h.x + lo.x, h.y + lo.y, h.z + lo.z, h.w + lo.w);
+            }
+            acc = tc_gather_one<NL>(net, l0, pack, q, c, acc);
+            tc_store_split4(a_hi, a_lo, row_off, acc);
+        }
+    }
+}
+
 // Gather for the warp's 32 queries into rows [row0, row0+32) of the group's A operand.
 //   px,py,pz / active : this lane's query;   pack/idx : this warp's scratch.
 // Every lane of the warp must call (convergent).
@@ -76,7 +135,6 @@ __device__ __forceinline__ void tc_gather_rows(const NetDev& net, float px, floa
         // K chunk 8 = {x, y, z, 1}: the query's own lane writes it (no shuffles needed later)
         tc_store_split4(a_hi, a_lo, tc_elem_offset(row0 + lane, NGLOD_F), make_float4(px, py, pz, 1.f));
     }
-    const int sub = lane >> 3, c = lane & 7;
     for (int l0 = 0; l0 < net.num_lods; l0 += TC_PACK_LODS) {
         const int nl = min(TC_PACK_LODS, net.num_lods - l0);
         // ---- phase 1: per-LOD set-up, once per query (not once per lane of the query)
@@ -92,50 +150,14 @@ __device__ __forceinline__ void tc_gather_rows(const NetDev& net, float px, floa
             }
         }
         __syncwarp();
-        // ---- phase 2: 4 queries per round, 8 lanes per corner line
-        for (int r = 0; r * 4 < n_live; ++r) {
-            const int slot = r * 4 + sub;
-            if (slot < n_live) {
-                const int q = idx[slot];
-                const uint32_t row_off = tc_elem_offset(row0 + q, 4 * c);
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (l0 > 0) {       // more than TC_PACK_LODS grids: continue the running sum (hi + lo is exact)
-                    const float4 h = *reinterpret_cast<const float4*>(a_hi + row_off);
-                    const float4 lo = *reinterpret_cast<const float4*>(a_lo + row_off);
-                    acc = make_float4(h.x + lo.x, h.y + lo.y, h.z + lo.z, h.w + lo.w);
-                }
-#pragma unroll
-                for (int l = 0; l < TC_PACK_LODS; ++l) {
-                    if (l >= nl) break;
-                    const float4 P = pack[l * 32 + q];
-                    const uint32_t pk = __float_as_uint(P.x);
-                    const int S = net.res[l0 + l] + 1;
-                    const int o0 = (int)(pk & ~31u) + 4 * c;
-                    const int dx = (pk & 1u) ? NGLOD_F : 0;
-                    const int dy = (pk & 2u) ? S * NGLOD_F : 0;
-                    const int dz = (pk & 4u) ? S * S * NGLOD_F : 0;
-                    const float wx1 = P.y, wy1 = P.z, wz1 = P.w;
-                    const float wx0 = 1.f - wx1, wy0 = 1.f - wy1, wz0 = 1.f - wz1;   // == (floor+1) - u exactly
-                    const float* g = net.grids[l0 + l];
-                    const int o2 = o0 + dy, o4 = o0 + dz, o6 = o4 + dy;
-                    float4 v[8];
-                    v[0] = ldg_f4(g + o0); v[1] = ldg_f4(g + o0 + dx);
-                    v[2] = ldg_f4(g + o2); v[3] = ldg_f4(g + o2 + dx);
-                    v[4] = ldg_f4(g + o4); v[5] = ldg_f4(g + o4 + dx);
-                    v[6] = ldg_f4(g + o6); v[7] = ldg_f4(g + o6 + dx);
-                    const float w00 = wx0 * wy0, w10 = wx1 * wy0, w01 = wx0 * wy1, w11 = wx1 * wy1;
-                    const float w[8] = {w00 * wz0, w10 * wz0, w01 * wz0, w11 * wz0, w00 * wz1, w10 * wz1, w01 * wz1, w11 * wz1};
-                    float4 s;
-                    s.x = v[0].x * w[0]; s.y = v[0].y * w[0]; s.z = v[0].z * w[0]; s.w = v[0].w * w[0];
-#pragma unroll
-                    for (int k = 1; k < 8; ++k) {
-                        s.x = fmaf(v[k].x, w[k], s.x); s.y = fmaf(v[k].y, w[k], s.y);
-                        s.z = fmaf(v[k].z, w[k], s.z); s.w = fmaf(v[k].w, w[k], s.w);
-                    }
-                    acc.x = s.x + acc.x; acc.y = s.y + acc.y; acc.z = s.z + acc.z; acc.w = s.w + acc.w;
-                }
-                tc_store_split4(a_hi, a_lo, row_off, acc);
-            }
+        // ---- phase 2: 4 queries per round, 8 lanes per corner line (LOD count compile-time so the loads of
+        //      several LODs can be in flight together)
+        switch (nl) {
+            case 1: tc_gather_rounds<1>(net, l0, n_live, a_hi, a_lo, row0, pack, idx, lane); break;
+            case 2: tc_gather_rounds<2>(net, l0, n_live, a_hi, a_lo, row0, pack, idx, lane); break;
+            case 3: tc_gather_rounds<3>(net, l0, n_live, a_hi, a_lo, row0, pack, idx, lane); break;
+            case 4: tc_gather_rounds<4>(net, l0, n_live, a_hi, a_lo, row0, pack, idx, lane); break;
+            default: tc_gather_rounds<5>(net, l0, n_live, a_hi, a_lo, row0, pack, idx, lane); break;
         }
         __syncwarp();
     }
