@@ -5,7 +5,10 @@
 
 namespace {
 
-constexpr int FWD_GROUPS = 3;                       // 3 x 128 threads per CTA, one CTA per SM
+#ifndef NGLOD_FWD_GROUPS
+#define NGLOD_FWD_GROUPS 3
+#endif
+constexpr int FWD_GROUPS = NGLOD_FWD_GROUPS;   // groups of 128 threads per CTA, one CTA per SM
 constexpr int FWD_THREADS = FWD_GROUPS * TCG_THREADS;
 constexpr int FWD_SMEM = TC_SMEM_BYTES(FWD_GROUPS);
 

@@ -35,7 +35,10 @@ struct TraceParams {
     float step_size, min_dis, min_dis3, far, h, two_h;
 };
 
-constexpr int TRACE_TC_GROUPS = 3;
+#ifndef NGLOD_TRACE_GROUPS
+#define NGLOD_TRACE_GROUPS 3
+#endif
+constexpr int TRACE_TC_GROUPS = NGLOD_TRACE_GROUPS;
 constexpr int TRACE_TC_THREADS = TRACE_TC_GROUPS * TCG_THREADS;
 constexpr int TRACE_TC_SMEM = TC_SMEM_BYTES(TRACE_TC_GROUPS);
 
