@@ -22,6 +22,11 @@ NVCC_FLAGS = [
 ]
 
 
+def _flags():
+    """NVCC_FLAGS plus experiment knobs from $NGLOD_EXTRA_NVCC_FLAGS (e.g. "-DNGLOD_FWD_GROUPS=2")."""
+    return NVCC_FLAGS + os.environ.get("NGLOD_EXTRA_NVCC_FLAGS", "").split()
+
+
 def _nvcc():
     for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
         if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
@@ -37,7 +42,7 @@ def _digest():
                 with open(os.path.join(root, name), "rb") as f:
                     h.update(name.encode())
                     h.update(f.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(_flags()).encode())
     return h.hexdigest()
 
 
@@ -52,7 +57,7 @@ def build_library(force=False, verbose=False):
 
     def compile_one(src):
         obj = os.path.join(OBJ, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *_flags(), "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
