@@ -184,6 +184,39 @@ int nglod_sphere_trace(const nglod_net_t* net, int32_t lod,
 int nglod_mesh2sdf(const float* points, int64_t n, const float* tris,
                    int64_t num_tris, float* dist, void* stream);
 
+/* ---- sparse-octree (SPC) ray traversal -------------------------------------
+ * Replaces: spc_raytrace, sol-renderer/include/spc/spc/spc_raytrace_cuda.cpp:125-199 + kernels
+ * spc_raytrace_cuda_kernel.cu:51-265 (= Kaolin's unbatched_raytrace, sdf-net/app/spc/SPC.py:104-107).
+ * octree: child-mask bytes, breadth first; prefix: exclusive sum of their popcounts (int32, same length);
+ * points: [psize,4] int16 voxel coordinates of every level in Morton order; pyramid_sum: HOST int32[level+2],
+ * first point of each level; level: depth of the octree; target_level <= level.
+ * Output "nuggets" [total,2] int32 = (ray index, point index within target_level), sorted by ray, each ray's
+ * run front to back -- identical, nugget for nugget, to the reference's level-synchronous traversal.
+ * Two calls: _count writes offsets[n+1] (exclusive scan of per-ray nugget counts; offsets[n] = total) using
+ * scan_ws (int32[n/1024+2]); the caller reads the total, allocates, and _fill writes the nuggets. */
+int nglod_spc_raytrace_count(const uint8_t* octree, const int32_t* prefix, const int16_t* points,
+                             const int32_t* pyramid_sum, int32_t level, int32_t target_level,
+                             const float* ray_o, const float* ray_d, int64_t n,
+                             int32_t* offsets, int32_t* scan_ws, void* stream);
+int nglod_spc_raytrace_fill(const uint8_t* octree, const int32_t* prefix, const int16_t* points,
+                            const int32_t* pyramid_sum, int32_t level, int32_t target_level,
+                            const float* ray_o, const float* ray_d, int64_t n,
+                            const int32_t* offsets, int32_t* nuggets, void* stream);
+
+/* info[i] = 1 where nugget i starts a new ray's run.  Replaces: d_MarkUniqueRays, sol-renderer/sdfRenderer.cu:108-120
+ * (= Kaolin's mark_first_hit, sdf-net/app/spc/SPCTracer.py:56). */
+int nglod_spc_mark_first_hit(const int32_t* nuggets, int64_t m, int32_t* info, void* stream);
+
+/* First voxel of each ray's run that contains `query` (no advance) or that the ray enters (t += d, x = o + t*d);
+ * rays whose run is exhausted get cond = 0, t = 100.  Rays without nuggets (and rays with active[ray] == 0 when
+ * `active` is non-null) are left untouched.  level_points: the [*,4] int16 points of the nugget level.
+ * Replaces: ray_aabb_kernel / ray_aabb, sol-renderer/include/solr/solr/gfx/ray_aabb.cuh:42-192
+ * (= Kaolin's unbatched_ray_aabb, SPCTracer.py:62,99). */
+int nglod_spc_ray_aabb(const int32_t* nuggets, const int32_t* offsets, int64_t n_rays,
+                       const int16_t* level_points, int32_t level, const float* ray_o, const float* ray_d,
+                       const float* query, const uint8_t* active, float* x, float* t, uint8_t* cond,
+                       int32_t* pidx, void* stream);
+
 /* ---- Adam on a flat fp32 parameter buffer ----------------------------------
  * Replaces: torch.optim.Adam(lr) as set up by Trainer.set_optimizer,
  * sdf-net/lib/trainer.py:178-189 (betas .9/.999, eps 1e-8, no weight decay).

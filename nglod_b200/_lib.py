@@ -82,6 +82,13 @@ SIGNATURES = {
     "nglod_sphere_trace": (ctypes.c_int, [ctypes.POINTER(NetStruct), c_int32, c_void_p, c_void_p, c_int64,
                                           ctypes.POINTER(TraceOpts), c_void_p, c_void_p, c_void_p, c_void_p,
                                           c_void_p, c_void_p, c_void_p]),
+    "nglod_spc_raytrace_count": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_int32), c_int32, c_int32,
+                                                c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "nglod_spc_raytrace_fill": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_int32), c_int32, c_int32,
+                                               c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "nglod_spc_mark_first_hit": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "nglod_spc_ray_aabb": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_void_p, c_void_p,
+                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "nglod_mesh2sdf": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "nglod_adam_step": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, ctypes.c_float,
                                        ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,

@@ -1,0 +1,187 @@
+"""Sparse octree (SPC) of a mesh and ray traversal over it -- Kaolin-free.
+
+The reference's sparse path (sdf-net/app/spc) calls un-vendored Kaolin for every primitive; each has an in-tree twin
+that defines the behaviour.  This module provides them over torch tensor ops (octree
+build / decode: set-up work, done once per mesh) and the sm_100a kernels (ray traversal: per frame):
+
+  points_to_morton / morton_to_points   <- ToMorton / ToPoint, sol-renderer/include/spc/spc/SPC.h:65-97 (= lib/spc3d.py:24-40)
+  quantize_points                       <- kaolin.ops.spc.quantize_points (call site spc_utils.py:79)
+  points_to_octree                      <- SPC3D.points_to_nodes, sdf-net/lib/spc3d.py:224-255
+  octree_to_spc                         <- SPC::SetGeometry, sol-renderer/include/spc/spc/SPC.cu:148-238 (= scan_octrees + generate_points)
+  mesh_to_octree                        <- spc_utils.py:74-84
+  query                                 <- SPC3D.Identify, lib/spc3d.py:309-338 (= unbatched_query)
+  SPC.raytrace / mark_first_hit / ray_aabb  <- spc_raytrace, d_MarkUniqueRays, ray_aabb_kernel (see csrc/spc.cu)
+"""
+import ctypes
+
+import torch
+
+from .. import _lib
+from ..ops import _ptr, _stream, _f32c
+from .torchgp import sample_surface
+
+
+def points_to_morton(points):
+    """[N,3] integer voxel coordinates -> int64 Morton codes; x is the most significant bit of each triple."""
+    p = points.long()
+    code = torch.zeros(p.shape[0], dtype=torch.int64, device=p.device)
+    for i in range(16):
+        bit = 1 << i
+        code |= ((p[:, 0] & bit) << (2 * i + 2)) | ((p[:, 1] & bit) << (2 * i + 1)) | ((p[:, 2] & bit) << (2 * i))
+    return code
+
+
+def morton_to_points(morton):
+    m = morton.long()
+    p = torch.zeros(m.shape[0], 3, dtype=torch.int64, device=m.device)
+    for i in range(16):
+        p[:, 0] |= ((m >> (3 * i + 2)) & 1) << i
+        p[:, 1] |= ((m >> (3 * i + 1)) & 1) << i
+        p[:, 2] |= ((m >> (3 * i)) & 1) << i
+    return p.short()
+
+
+def quantize_points(x, level):
+    """[-1,1]^3 -> integer voxel coordinates in [0, 2^level)."""
+    res = 2 ** level
+    return torch.floor(torch.clamp(res * (x + 1.0) / 2.0, 0, res - 1.0)).short()
+
+
+def points_to_octree(points, level):
+    """Unique voxel coordinates at `level` (any order) -> uint8 child-mask bytes, breadth first (root first)."""
+    m = torch.unique(points_to_morton(points))            # sorted
+    levels = []
+    for _ in range(level):
+        parent = m >> 3
+        child = (m & 7)
+        uniq, inv = torch.unique(parent, return_inverse=True)
+        byte = torch.zeros(uniq.shape[0], dtype=torch.int64, device=m.device)
+        byte.scatter_add_(0, inv, (1 << child))           # children of one parent are distinct -> sum == OR
+        levels.append(byte.to(torch.uint8))
+        m = uniq
+    return torch.cat(levels[::-1]) if levels else torch.zeros(0, dtype=torch.uint8, device=points.device)
+
+
+def octree_to_spc(octree):
+    """child-mask bytes -> (points [psize,4] int16 of all levels in Morton order, pyramid [2, L+2] int32 on the
+    host (row 0: voxels per level, row 1: first point of each level), prefix int32 = exclusive popcount sum)."""
+    dev = octree.device
+    o = octree.long()
+    pop = torch.zeros_like(o)
+    for i in range(8):
+        pop += (o >> i) & 1
+    prefix = (torch.cumsum(pop, 0) - pop).int()
+    mortons = [torch.zeros(1, dtype=torch.int64, device=dev)]
+    counts = [1]
+    start = 0
+    while start < o.shape[0]:
+        n = counts[-1]
+        bytes_l = o[start:start + n]
+        cand = (mortons[-1].unsqueeze(1) * 8 + torch.arange(8, device=dev).unsqueeze(0))
+        keep = ((bytes_l.unsqueeze(1) >> torch.arange(8, device=dev).unsqueeze(0)) & 1).bool()
+        nxt = cand[keep]                                   # node-major, child index ascending == Morton order
+        mortons.append(nxt)
+        counts.append(int(nxt.shape[0]))
+        start += n
+    level = len(counts) - 1
+    pts3 = morton_to_points(torch.cat(mortons))
+    points = torch.zeros(pts3.shape[0], 4, dtype=torch.int16, device=dev)
+    points[:, :3] = pts3
+    pyramid = torch.zeros(2, level + 2, dtype=torch.int32)
+    s = 0
+    for l, c in enumerate(counts):
+        pyramid[0, l] = c
+        pyramid[1, l] = s
+        s += c
+    pyramid[1, level + 1] = s
+    return points, pyramid, prefix
+
+
+def mesh_to_octree(V, F, level, num_samples=1 << 24):
+    """Octree of the voxels a mesh surface touches (spc_utils.py:74-84): surface samples plus a half-voxel jittered
+    copy, quantised, de-duplicated.  The reference draws 1e8 samples; `num_samples` trades build time for coverage."""
+    samples = sample_surface(V, F, num_samples)[0]
+    samples = torch.cat([samples, samples + (torch.rand_like(samples) * 2.0 - 1.0) * (1.0 / (2 ** (level + 1)))], dim=0)
+    q = quantize_points(samples, level)
+    return points_to_octree(torch.unique(q.long(), dim=0), level)
+
+
+class SPC:
+    """Geometry of a sparse octree + ray traversal on the device (the geometric half of sdf-net/app/spc/SPC.py)."""
+
+    def __init__(self, octree):
+        self.octree = octree.contiguous()
+        self.points, self.pyramid, self.prefix = octree_to_spc(self.octree)
+        self.level = self.pyramid.shape[1] - 2
+        self._pyrsum = (ctypes.c_int32 * (self.level + 2))(*[int(v) for v in self.pyramid[1]])
+
+    def level_points(self, level):
+        return self.points[int(self.pyramid[1, level]):int(self.pyramid[1, level + 1])]
+
+    def query(self, qpts, level):
+        """Index (within `level`) of the voxel holding each integer point, -1 if unoccupied (spc3d.py:309-338)."""
+        q = qpts.long()
+        n = q.shape[0]
+        o = self.octree.long()
+        psum = self.prefix.long()
+        ordn = torch.zeros(n, dtype=torch.int64, device=q.device)
+        alive = ((q >= 0) & (q < (1 << level))).all(dim=1)
+        for l in range(level):
+            depth = level - l - 1
+            child = (((q[:, 0] >> depth) & 1) << 2) | (((q[:, 1] >> depth) & 1) << 1) | ((q[:, 2] >> depth) & 1)
+            bits = o[ordn.clamp(max=o.shape[0] - 1)]
+            has = ((bits >> child) & 1).bool() & alive
+            below = bits & ((2 << child) - 1)
+            cnt = torch.zeros_like(below)
+            for i in range(8):
+                cnt += (below >> i) & 1
+            ordn = torch.where(has, psum[ordn.clamp(max=o.shape[0] - 1)] + cnt, ordn)
+            alive = has
+        return torch.where(alive, ordn - int(self.pyramid[1, level]), torch.full_like(ordn, -1))
+
+    def raytrace(self, ray_o, ray_d, target_level, return_offsets=False):
+        """(ray, voxel) nuggets [M,2] int32 at `target_level`, sorted by ray, each ray's run front to back."""
+        lib = _lib.load()
+        ray_o, ray_d = _f32c(ray_o, "ray_o"), _f32c(ray_d, "ray_d")
+        n = ray_o.shape[0]
+        dev = ray_o.device
+        offsets = torch.empty(n + 1, dtype=torch.int32, device=dev)
+        ws = torch.empty(n // 1024 + 2, dtype=torch.int32, device=dev)
+        args = (_ptr(self.octree), _ptr(self.prefix), _ptr(self.points), self._pyrsum, self.level, int(target_level),
+                _ptr(ray_o), _ptr(ray_d), n)
+        with torch.cuda.device(dev):
+            _lib.check(lib.nglod_spc_raytrace_count(*args, _ptr(offsets), _ptr(ws), _stream()), "nglod_spc_raytrace_count")
+            total = int(offsets[-1])                         # the ONE host read of the traversal
+            nuggets = torch.empty(total, 2, dtype=torch.int32, device=dev)
+            if total:
+                _lib.check(lib.nglod_spc_raytrace_fill(*args, _ptr(offsets), _ptr(nuggets), _stream()),
+                           "nglod_spc_raytrace_fill")
+        return (nuggets, offsets) if return_offsets else nuggets
+
+
+def mark_first_hit(nuggets):
+    lib = _lib.load()
+    m = nuggets.shape[0]
+    info = torch.empty(m, dtype=torch.int32, device=nuggets.device)
+    with torch.cuda.device(nuggets.device):
+        _lib.check(lib.nglod_spc_mark_first_hit(_ptr(nuggets), m, _ptr(info), _stream()), "nglod_spc_mark_first_hit")
+    return info
+
+
+def ray_aabb(spc, nuggets, offsets, ray_o, ray_d, level, query=None, active=None, t=None):
+    """First occupied voxel per ray from `query` (default: the ray origins).  Returns (x, t, cond, pidx)."""
+    lib = _lib.load()
+    ray_o, ray_d = _f32c(ray_o, "ray_o"), _f32c(ray_d, "ray_d")
+    n = ray_o.shape[0]
+    dev = ray_o.device
+    query = ray_o if query is None else _f32c(query, "query")
+    x = query.clone()
+    t = torch.zeros(n, 1, device=dev) if t is None else t.clone()
+    cond = torch.zeros(n, dtype=torch.bool, device=dev) if active is None else active.clone()
+    pidx = torch.full((n,), -1, dtype=torch.int32, device=dev)
+    lp = spc.level_points(level).contiguous()
+    with torch.cuda.device(dev):
+        _lib.check(lib.nglod_spc_ray_aabb(_ptr(nuggets), _ptr(offsets), n, _ptr(lp), int(level), _ptr(ray_o), _ptr(ray_d),
+                                          _ptr(query), _ptr(active), _ptr(x), _ptr(t), _ptr(cond), _ptr(pidx), _stream()),
+                   "nglod_spc_ray_aabb")
+    return x, t, cond, pidx

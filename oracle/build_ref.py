@@ -8,6 +8,7 @@ against on the B200:
 
   ref_sol_nglod.aabb            <- sdf-net/lib/extensions/sol_nglod/sol_nglod_kernel.cu:161-192
   ref_mesh2sdf.mesh2sdf_gpu     <- sdf-net/lib/extensions/mesh2sdf_cuda/mesh2sdf_kernel.cu:895-1012
+  ref_spc.spc_raytrace          <- sol-renderer/include/spc/spc/spc_raytrace_cuda{.cpp,_kernel.cu}
 
 The reference's setup.py pins -std=c++14, which torch 2.11 headers reject, so
 we drive torch.utils.cpp_extension.load() ourselves (ninja + nvcc, sm_100).
@@ -20,9 +21,13 @@ REF = os.environ.get("NGLOD_REFERENCE", "/root/reference")
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 
 EXTS = {
-    "ref_sol_nglod": "sdf-net/lib/extensions/sol_nglod/sol_nglod_kernel.cu",
-    "ref_mesh2sdf": "sdf-net/lib/extensions/mesh2sdf_cuda/mesh2sdf_kernel.cu",
+    "ref_sol_nglod": ["sdf-net/lib/extensions/sol_nglod/sol_nglod_kernel.cu"],
+    "ref_mesh2sdf": ["sdf-net/lib/extensions/mesh2sdf_cuda/mesh2sdf_kernel.cu"],
+    # NOT buildable here: sol-renderer's SPC ray traversal (spc_raytrace_cuda_kernel.cu / spc_raytrace_cuda.cpp) needs
+    # CUDA-samples' helper_math.h (not vendored, spc_math.h:26) and a pre-2.0 CUB (CUB_NS_PREFIX without
+    # CUB_NS_QUALIFIER is an #error in the toolkit's CUB) -> the SPC oracle is a C restatement, parity unpinned.
 }
+HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def build(verbose=False):
@@ -40,7 +45,9 @@ def build(verbose=False):
             print(f"[build_ref] {so} already built")
             continue
         try:
-            load(name=name, sources=[os.path.join(REF, rel)], build_directory=bdir,
+            srcs = [os.path.join(HERE, r[1:]) if r.startswith("@") else os.path.join(REF, r) for r in rel]
+            load(name=name, sources=srcs, build_directory=bdir,
+                 extra_include_paths=[os.path.join(REF, "sol-renderer/include/spc/spc")],
                  extra_cuda_cflags=["-O3"], verbose=verbose, is_python_module=False)
             print(f"[build_ref] built {so}")
         except Exception as e:  # noqa: BLE001

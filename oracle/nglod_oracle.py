@@ -221,3 +221,44 @@ def l2_loss_and_grads(net, x, gt, lods):
     loss = loss / x.shape[0]
     loss.backward()
     return loss.detach()
+
+
+# --------------------------------------------------------------------------- SPC (sparse octree)
+def spc_raytrace(octree, prefix, points, pyramid, target, ray_o, ray_d):
+    """CPU restatement of the reference's level-synchronous traversal (oracle.c:oracle_spc_raytrace).
+    Returns nuggets [M,2] int32 and per-ray counts."""
+    lib = _clib()
+    lib.oracle_spc_raytrace.restype = ctypes.c_int64
+    o = octree.cpu().contiguous()
+    pf = prefix.cpu().int().contiguous()
+    pts = points.cpu().short().contiguous()
+    ps = pyramid[1].cpu().int().contiguous()
+    ro, rd = ray_o.cpu().float().contiguous(), ray_d.cpu().float().contiguous()
+    n = ro.shape[0]
+    counts = torch.zeros(n, dtype=torch.int32)
+    vp = ctypes.c_void_p
+    args = [vp(o.data_ptr()), vp(pf.data_ptr()), vp(pts.data_ptr()), vp(ps.data_ptr()), ctypes.c_int(int(target)),
+            vp(ro.data_ptr()), vp(rd.data_ptr()), ctypes.c_int64(n)]
+    total = lib.oracle_spc_raytrace(*args, vp(0), ctypes.c_int64(0), vp(counts.data_ptr()))
+    nug = torch.zeros(total, 2, dtype=torch.int32)
+    lib.oracle_spc_raytrace(*args, vp(nug.data_ptr()), ctypes.c_int64(total), vp(counts.data_ptr()))
+    return nug, counts
+
+
+def spc_ray_aabb(nuggets, level_points, level, ray_o, ray_d, query=None):
+    """oracle.c:oracle_spc_ray_aabb with init semantics; returns (x, t, cond, pidx)."""
+    lib = _clib()
+    lib.oracle_spc_ray_aabb.restype = None
+    nug = nuggets.cpu().int().contiguous()
+    lp = level_points.cpu().short().contiguous()
+    ro, rd = ray_o.cpu().float().contiguous(), ray_d.cpu().float().contiguous()
+    q = ro if query is None else query.cpu().float().contiguous()
+    n = ro.shape[0]
+    x, t = q.clone(), torch.zeros(n, 1)
+    cond = torch.zeros(n, dtype=torch.uint8)
+    pidx = torch.full((n,), -1, dtype=torch.int32)
+    vp = ctypes.c_void_p
+    lib.oracle_spc_ray_aabb(vp(nug.data_ptr()), ctypes.c_int64(nug.shape[0]), vp(lp.data_ptr()), ctypes.c_int(int(level)),
+                            vp(ro.data_ptr()), vp(rd.data_ptr()), vp(q.data_ptr()), vp(x.data_ptr()), vp(t.data_ptr()),
+                            vp(cond.data_ptr()), vp(pidx.data_ptr()))
+    return x, t, cond.bool(), pidx

@@ -195,6 +195,40 @@ def fit3():
     print("fit3: hits", int(rb.hit.sum()), "converged", int(conv.sum()), "of", rb.hit.numel())
 
 
+
+
+def spc_golden():
+    """Octree bytes / points / pyramid / point queries from the reference's numpy SPC (sdf-net/lib/spc3d.py), for a
+    sphere of radius 0.6 at level 4 (recursive construction :128-137, binary encoding :224-255, decoding :273-304,
+    Identify :309-338)."""
+    from lib.spc3d import SPC3D
+    level = 4
+    spc = SPC3D(level)
+    spc.construct(lambda x, y, z: np.sqrt(x * x + y * y + z * z) - 0.6)
+    n = spc.psize
+    leaf = spc.pdata[:n].copy()
+    osize = spc.points_to_nodes()
+    octree = np.array(spc.oroot[:osize], dtype=np.uint8).copy()
+    spc2 = SPC3D(level, nodebytes=octree.copy())
+    spc2.osize = octree.size
+    spc2.oroot = spc2.odata
+    num = spc2.nodes_to_points()
+    pyramid = np.array(spc2.pyramid[:level + 1]).copy()
+    total = int(pyramid.sum())
+    mort = np.array(spc2.mdata[:total]).copy()
+    rng = np.random.RandomState(3)
+    q = rng.randint(-1, 17, size=(300, 3))
+    ident = np.array([spc2.Identify(p) for p in q])
+    np.savez_compressed(os.path.join(HERE, "spc.npz"), level=np.array(level), leaf_points=leaf, octree=octree,
+                        pyramid=pyramid, morton_all=mort, query_pts=q, query_idx=ident)
+    print("spc:", n, "leaf voxels,", osize, "octree bytes, pyramid", pyramid, "queries hit", int((ident >= 0).sum()))
+
+
 if __name__ == "__main__":
-    rand5()
-    fit3()
+    which = sys.argv[1:] or ["rand5", "fit3", "spc"]
+    if "rand5" in which:
+        rand5()
+    if "fit3" in which:
+        fit3()
+    if "spc" in which:
+        spc_golden()
