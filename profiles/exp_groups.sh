@@ -1,8 +1,7 @@
-# experiment: groups (128-thread MMA tiles) per CTA -- more warps (3) vs more L1 (2)
+# experiment: groups (128-thread MMA tiles) per CTA -- more warps (3) vs more L1 (2, 1); binned queries
 cd /root/repo
-for G in 2 3; do
-  NGLOD_EXTRA_NVCC_FLAGS="-DNGLOD_TRACE_GROUPS=$G -DNGLOD_FWD_GROUPS=$G" python nglod_b200/build.py --force > /dev/null
-  echo "== groups $G"
-  timeout 200 python profiles/perf_fwd.py 2>&1 | tail -1
-  timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "import json,sys; j=json.loads(sys.stdin.read()); print('tracer ms', j['ms_per_step'])"
+for G in 1 2 3; do
+  NGLOD_EXTRA_NVCC_FLAGS="-DNGLOD_TRACE_GROUPS=3 -DNGLOD_FWD_GROUPS=$G" python nglod_b200/build.py --force > /dev/null
+  echo "== fwd groups $G"
+  ncu --metrics gpu__time_duration.sum,l1tex__t_sector_hit_rate.pct --clock-control none --csv --log-file gpurun_out/l.csv -k regex:"sdf_forward_tc" -s 5 -c 2 python profiles/perf_fwd.py > /dev/null 2>&1; python profiles/ncu_csv.py gpurun_out/l.csv
 done
