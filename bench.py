@@ -275,6 +275,7 @@ def run_ours(ns):
     fwd_ms = ndist.max_over_ranks(fwd_ms, device)
     bwd_ms = ndist.max_over_ranks(bwd_ms, device)
 
+    extras = {} if ns.no_extras else run_extras(net, args, device, rank, world, flush, log)
     if rank != 0:
         return
     peak, peak_src = load_peaks()
@@ -320,9 +321,95 @@ def run_ours(ns):
                                      "achieved": q_bytes / (fwd_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                                      "frac": q_bytes / (fwd_ms / 1e3) / 1e9 / peak, "traffic": None}},
     }
+    line["extras"] = extras
     if world == 1 and not ns.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_trace(net, ray_o.cpu(), ray_d.cpu(), budget_s=20.0, log=log)
     print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- other configs
+def run_extras(net, args, device, rank, world, flush, log):
+    """Side measurements for BASELINE.json configs 3-5 (device-timed, L2 flushed, a few iterations each).  They are
+    reported under "extras"; the headline value / roofline above are untouched by them."""
+    from nglod_b200 import dist as ndist
+    from nglod_b200 import ops
+    from nglod_b200.lib import spc as S
+    from nglod_b200.lib.datasets import MeshDataset
+    from nglod_b200.lib.renderer import Renderer
+    from nglod_b200.lib.tracer import SphereTracer
+    from nglod_b200.lib.trainer import FusedTrainer
+    from nglod_b200.lib.torchgp import torus, point_sample, normalize
+    from nglod_b200.lib.geoutils import look_at
+    out = {}
+
+    def timed(fn, iters=5, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(iters):
+            flush_l2(flush)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return ndist.max_over_ranks(float(np.mean(ts)), device)
+
+    # ---- config 3: training step on a 500 000-point batch sharded over the ranks (fused 5-head fwd+bwd, one
+    #      all-reduce of the flat gradient, Adam kernel) + the cost of producing the batch (sampling + mesh2sdf labels)
+    V, F = normalize(*[t.to(device) for t in torus(0.6, 0.25, 128, 64)])
+    per_rank = 500000 // world
+    modes = ["rand", "near", "near", "trace", "trace"]
+    tri = V[F].contiguous()
+
+    def make_batch():
+        pts = point_sample(V, F, modes, per_rank // 5)
+        return pts, ops.mesh2sdf_gpu(pts, tri)[0].unsqueeze(1)
+
+    sample_ms = timed(make_batch, iters=3, warm=1)
+    pts, gts = make_batch()
+    import copy
+    tnet = copy.deepcopy(net)
+    tnet.train()
+    trainer = FusedTrainer(tnet, lr=1e-3)
+    step_ms = timed(lambda: trainer.step(pts, gts, global_batch=per_rank * world), iters=5, warm=2)
+    out["train_step_500k"] = {"points_per_rank": pts.shape[0], "ms_per_step": step_ms,
+                              "points_per_s": world * pts.shape[0] / (step_ms / 1e3),
+                              "sample_and_label_ms": sample_ms, "mesh_triangles": int(tri.shape[0]),
+                              "mesh2sdf_pairs_per_s": world * pts.shape[0] * tri.shape[0] / (sample_ms / 1e3),
+                              "note": "fused fwd+loss+bwd for 5 LODs + flat-gradient all-reduce + Adam; labels by the mesh2sdf kernel"}
+    del trainer, tnet
+
+    # ---- config 4 (traversal half): sparse-octree ray traversal at 1920x1080, octree level 7 of the same mesh
+    torch.manual_seed(77 + rank)
+    octree = S.mesh_to_octree(V, F, 7, num_samples=1 << 22)
+    spc = S.SPC(octree)
+    ro, rd = look_at(CAM_FROM, CAM_TO, 1920, 1080, mode="persp", fov=FOV, device=device)
+    nug = spc.raytrace(ro, rd, 7)
+    trav_ms = timed(lambda: spc.raytrace(ro, rd, 7), iters=5, warm=1)
+    out["spc_raytrace_1080p_level7"] = {"rays": ro.shape[0], "nuggets": int(nug.shape[0]), "voxels": int(spc.pyramid[0, 7]),
+                                        "ms": trav_ms, "rays_per_s": world * ro.shape[0] / (trav_ms / 1e3),
+                                        "note": "count + scan + fill, includes the one 4-byte host read of the total"}
+    del nug, ro, rd
+
+    # ---- config 5: 3840x2160, shadows + normals, image cut into column strips over the ranks (x-major rays)
+    w4, h4 = 3840, 2160
+    torch.manual_seed(5)
+    ro, rd = look_at(CAM_FROM, CAM_TO, w4, h4, mode="persp", fov=FOV, device=device)
+    s0, s1 = ndist.shard_range(w4 * h4, rank, world, align=h4)
+    ro, rd = ro[s0:s1].contiguous(), rd[s0:s1].contiguous()
+    rargs = copy.copy(args)
+    rargs.shadow, rargs.ground_height, rargs.render_res = True, -0.4, [(s1 - s0) // h4, h4]
+    renderer = Renderer(SphereTracer(rargs), args=rargs, device=device)
+    r4_ms = timed(lambda: renderer.render(net, ro, rd), iters=3, warm=1)
+    out["render_4k_shadow"] = {"rays": w4 * h4, "rays_this_rank": s1 - s0, "ms": r4_ms, "fps": 1e3 / r4_ms,
+                               "note": "primary trace + ground plane + shadow trace + normals via Renderer.render; "
+                                       "ranks take contiguous column strips, no collective"}
+    log(f"extras: train {step_ms:.2f} ms/500k-pt step, sample+label {sample_ms:.1f} ms, spc 1080p {trav_ms:.2f} ms, "
+        f"4K+shadow {r4_ms:.1f} ms")
+    return out
 
 
 # ----------------------------------------------------------------------------------------------- CPU legs
@@ -367,6 +454,7 @@ def run_reference(ns):
     """The reference's CPU path for the same metric/config: the oracle port (same ATen calls as the reference's
     PyTorch path; the reference itself is Python under /root/reference, which does not exist on the GPU box)."""
     rank = int(os.environ.get("RANK", "0"))
+    extras = {} if ns.no_extras else run_extras(net, args, device, rank, world, flush, log)
     if rank != 0:
         return
     from oracle import nglod_oracle as O
@@ -439,6 +527,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config 3/4/5 side measurements")
     ns = ap.parse_args()
     if ns.impl == "reference":
         run_reference(ns)
