@@ -38,6 +38,8 @@ struct __align__(16) TriRecord {
     float inv_det[M2S_NDIR];          // 1 / (edge1 . pvec), edge1 = v10
     unsigned dir_ok;                  // bit k: |det_k| >= 1e-8 (else the reference skips the direction)
     unsigned nondegenerate;           // nor != 0
+    float cen[3];                     // bounding sphere (centroid, radius with slack): distance culling only
+    float rad;
     unsigned pad[2];
 };
 
@@ -96,18 +98,29 @@ __device__ void build_record(const float* __restrict__ tri, TriRecord& r) {
         }
     }
     r.dir_ok = ok;
+    float r2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) r.cen[k] = (r.a[k] + r.b[k] + r.c[k]) * (1.0f / 3.0f);
+    {
+        const float da[3] = {r.a[0] - r.cen[0], r.a[1] - r.cen[1], r.a[2] - r.cen[2]};
+        const float db[3] = {r.b[0] - r.cen[0], r.b[1] - r.cen[1], r.b[2] - r.cen[2]};
+        const float dc[3] = {r.c[0] - r.cen[0], r.c[1] - r.cen[1], r.c[2] - r.cen[2]};
+        r2 = fmaxf(dot3(da, da), fmaxf(dot3(db, db), dot3(dc, dc)));
+    }
+    r.rad = sqrtf(r2) * 1.0001f + 1e-7f;
     r.pad[0] = r.pad[1] = 0;
 }
 
 __global__ void __launch_bounds__(M2S_THREADS)
 mesh2sdf_kernel(const float* __restrict__ points, const long long n, const float* __restrict__ tris,
-                const long long num_tris, float* __restrict__ dist) {
+                const long long num_tris, float* __restrict__ dist, const int* __restrict__ perm) {
     __shared__ TriRecord rec[M2S_TILE];
     const long long i = (long long)blockIdx.x * M2S_THREADS + threadIdx.x;
     const bool active = i < n;
     float P[3] = {0.f, 0.f, 0.f};
     if (active) { P[0] = __ldg(points + 3 * i); P[1] = __ldg(points + 3 * i + 1); P[2] = __ldg(points + 3 * i + 2); }
     float mind2 = INFINITY;
+    float mind = INFINITY;              // sqrt(mind2), refreshed when mind2 improves (culling bound only)
     unsigned pos = 0, neg = 0;
     const unsigned all_dirs = (1u << M2S_NDIR) - 1u;
 
@@ -116,14 +129,23 @@ mesh2sdf_kernel(const float* __restrict__ points, const long long n, const float
         __syncthreads();
         if (threadIdx.x < cnt) build_record(tris + (t0 + threadIdx.x) * 9, rec[threadIdx.x]);
         __syncthreads();
-        if (!active) continue;
+        // All 32 lanes stay in the loop (inactive lanes carry P = 0 and never write): the rejections below are
+        // warp-votes, so the branches are uniform and most (triangle, direction) pairs cost 5 instructions.
 #pragma unroll 1
         for (int tt = 0; tt < cnt; ++tt) {
             const TriRecord& r = rec[tt];
-            float p0[3], p1[3], p2[3];
+            float p0[3];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) { p0[k] = P[k] - r.a[k]; p1[k] = P[k] - r.b[k]; p2[k] = P[k] - r.c[k]; }
-            if (r.nondegenerate) {
+            for (int k = 0; k < 3; ++k) p0[k] = P[k] - r.a[k];
+            // Exact-preserving cull: every point of the triangle is at least |P - cen| - rad away, so if that already
+            // exceeds the running minimum the edge/face distance (the expensive half) cannot lower it.
+            const float pc[3] = {P[0] - r.cen[0], P[1] - r.cen[1], P[2] - r.cen[2]};
+            const float reach = mind + r.rad;
+            const bool near = r.nondegenerate && !(dot3(pc, pc) > reach * reach * 1.00001f);
+            if (__any_sync(0xffffffffu, near)) {
+                float p1[3], p2[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { p1[k] = P[k] - r.b[k]; p2[k] = P[k] - r.c[k]; }
                 const float s1 = copysignf(1.0f, dot3(r.c10, p0));
                 const float s2 = copysignf(1.0f, dot3(r.c21, p1));
                 const float s3 = copysignf(1.0f, dot3(r.c02, p2));
@@ -137,24 +159,26 @@ mesh2sdf_kernel(const float* __restrict__ points, const long long n, const float
                     d2 = dot3(r.nor, p0) * dot3(r.nor, p0) * r.invn;
                 }
                 if (d2 < 0.0f) d2 = 0.0f;
-                mind2 = fminf(mind2, d2);
+                if (near && d2 < mind2) { mind2 = d2; mind = sqrtf(d2) * 1.00001f; }
             }
             // 13 line stabs (Moller-Trumbore); qvec and edge2.qvec do not depend on the direction
-            if (r.dir_ok && ((pos & neg) != all_dirs)) {
+            const bool undecided = (pos & neg) != all_dirs;
+            if (r.dir_ok && __any_sync(0xffffffffu, undecided)) {
                 float qvec[3];
                 cross3(p0, r.v10, qvec);
                 const float edge2[3] = {-r.v02[0], -r.v02[1], -r.v02[2]};
                 const float e2q = dot3(edge2, qvec);
 #pragma unroll
                 for (int k = 0; k < M2S_NDIR; ++k) {
-                    if (!((r.dir_ok >> k) & 1u)) continue;
+                    if (!((r.dir_ok >> k) & 1u)) continue;                 // uniform: a property of the triangle
                     const float inv_det = r.inv_det[k];
                     const float u = dot3(p0, r.pvec[k]) * inv_det;
-                    if (u < 0.0f || u > 1.0f) continue;
+                    const bool pu = !(u < 0.0f || u > 1.0f);
+                    if (!__any_sync(0xffffffffu, pu)) continue;            // no lane's line crosses this slab
                     const float v = dot3(c_stab_dir[k], qvec) * inv_det;
-                    if (v < 0.0f || u + v > 1.0f) continue;
+                    const bool pv = pu && !(v < 0.0f || u + v > 1.0f);
                     const float t = e2q * inv_det;
-                    if (t >= 0.0f) pos |= 1u << k; else neg |= 1u << k;
+                    if (pv) { if (t >= 0.0f) pos |= 1u << k; else neg |= 1u << k; }
                 }
             }
         }
@@ -163,7 +187,74 @@ mesh2sdf_kernel(const float* __restrict__ points, const long long n, const float
         if (mind2 < 0.0f) mind2 = 0.0f;
         float d = sqrtf(mind2);
         if ((pos & neg) == all_dirs) d = -d;
-        dist[i] = d;
+        dist[perm ? (long long)perm[i] : i] = d;
+    }
+}
+
+// ---- spatial counting sort of the query points (32^3 Morton bins) ------------------------------------------------
+// The rejections above are warp votes, so they only pay off when the 32 points of a warp are close together: then
+// almost every (triangle, warp) pair is dismissed by the bounding-sphere cull and almost every stab direction by the
+// first barycentric test.  The sampler hands points over in random spatial order, so they are grouped first
+// (histogram -> scan -> scatter on stream-ordered scratch); distances are written back through the permutation and
+// every value is unchanged.
+constexpr int M2S_BIN_RES = 32;
+constexpr int M2S_BINS = M2S_BIN_RES * M2S_BIN_RES * M2S_BIN_RES;
+
+__device__ __forceinline__ int m2s_bin(float x, float y, float z) {
+    const int bx = min(M2S_BIN_RES - 1, max(0, (int)floorf((x + 1.f) * (0.5f * M2S_BIN_RES))));
+    const int by = min(M2S_BIN_RES - 1, max(0, (int)floorf((y + 1.f) * (0.5f * M2S_BIN_RES))));
+    const int bz = min(M2S_BIN_RES - 1, max(0, (int)floorf((z + 1.f) * (0.5f * M2S_BIN_RES))));
+    int code = 0;
+#pragma unroll
+    for (int b = 0; b < 5; ++b) code |= (((bx >> b) & 1) << (3 * b + 2)) | (((by >> b) & 1) << (3 * b + 1)) | (((bz >> b) & 1) << (3 * b));
+    return code;
+}
+
+__global__ void __launch_bounds__(256)
+m2s_hist_kernel(const float* __restrict__ x, const long long n, int* __restrict__ hist) {
+    const long long stride = (long long)gridDim.x * 256;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += stride)
+        atomicAdd(hist + m2s_bin(__ldg(x + 3 * i), __ldg(x + 3 * i + 1), __ldg(x + 3 * i + 2)), 1);
+}
+
+__global__ void __launch_bounds__(1024)
+m2s_scan_kernel(int* __restrict__ hist) {      // in place: counts -> exclusive offsets (32768 bins, one block)
+    __shared__ int warp_sums[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < M2S_BINS; base += 1024) {
+        const int v = hist[base + threadIdx.x];
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = warp_sums[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+            warp_sums[lane] = w;
+        }
+        __syncthreads();
+        const int tot = incl + (warp ? warp_sums[warp - 1] : 0) + carry;
+        hist[base + threadIdx.x] = tot - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = tot;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+m2s_scatter_kernel(const float* __restrict__ x, const long long n, int* __restrict__ cursor, float* __restrict__ xs,
+                   int* __restrict__ perm) {
+    const long long stride = (long long)gridDim.x * 256;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) {
+        const float px = __ldg(x + 3 * i), py = __ldg(x + 3 * i + 1), pz = __ldg(x + 3 * i + 2);
+        const int pos = atomicAdd(cursor + m2s_bin(px, py, pz), 1);
+        xs[3 * (long long)pos] = px; xs[3 * (long long)pos + 1] = py; xs[3 * (long long)pos + 2] = pz;
+        perm[pos] = (int)i;
     }
 }
 
@@ -192,9 +283,29 @@ extern "C" int nglod_mesh2sdf(const float* points, int64_t n, const float* tris,
     if (n == 0) return 0;
     const long long grid = (n + M2S_THREADS - 1) / M2S_THREADS;
     if (grid > 2147483647ll) return NGLOD_EINVAL;
-    mesh2sdf_kernel<<<(int)grid, M2S_THREADS, 0, (cudaStream_t)stream>>>(points, (long long)n, tris,
-                                                                         (long long)num_tris, dist);
-    return (int)cudaGetLastError();
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n < 4096 || n >= 2000000000ll || num_tris < 64) {        // too small for the sort to pay
+        mesh2sdf_kernel<<<(int)grid, M2S_THREADS, 0, st>>>(points, (long long)n, tris, (long long)num_tris, dist, nullptr);
+        return (int)cudaGetLastError();
+    }
+    char* ws = nullptr;
+    const size_t perm_off = ((size_t)n * 12 + 255) & ~(size_t)255;
+    const size_t hist_off = (perm_off + (size_t)n * 4 + 255) & ~(size_t)255;
+    NGLOD_CUDA_TRY(cudaMallocAsync(&ws, hist_off + (size_t)M2S_BINS * 4, st));
+    float* xs = reinterpret_cast<float*>(ws);
+    int* perm = reinterpret_cast<int*>(ws + perm_off);
+    int* hist = reinterpret_cast<int*>(ws + hist_off);
+    int err = (int)cudaMemsetAsync(hist, 0, (size_t)M2S_BINS * 4, st);
+    if (!err) {
+        const int nb = (int)((n + 255) / 256 < (long long)nglod_sm_count() * 8 ? (n + 255) / 256 : (long long)nglod_sm_count() * 8);
+        m2s_hist_kernel<<<nb, 256, 0, st>>>(points, (long long)n, hist);
+        m2s_scan_kernel<<<1, 1024, 0, st>>>(hist);
+        m2s_scatter_kernel<<<nb, 256, 0, st>>>(points, (long long)n, hist, xs, perm);
+        mesh2sdf_kernel<<<(int)grid, M2S_THREADS, 0, st>>>(xs, (long long)n, tris, (long long)num_tris, dist, perm);
+        err = (int)cudaGetLastError();
+    }
+    const int ferr = (int)cudaFreeAsync(ws, st);
+    return err ? err : ferr;
 }
 
 extern "C" int nglod_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
