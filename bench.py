@@ -38,6 +38,10 @@ MATH_MODE = os.environ.get("NGLOD_MATH", "tc")      # "tc" = tcgen05 3xTF32 deco
 GATHER_BYTES_PER_QUERY = (LOD + 1) * 8 * 32 * 4          # fp32 grids: 5120 B  
 IO_BYTES_PER_QUERY = 16
 RAY_IO_BYTES = 24 + 12 + 4 + 1 + 12                        # ray_o, ray_d in; x, depth, hit, normal out
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE sphere_trace_kernel / sdf_forward_tc_kernel launch, from the
+# `ncu --set full` captures summarised in profiles/sphere_trace_tc_r1_v1.txt and profiles/sdf_forward_tc_r1_v1.txt
+NCU_TRAFFIC_TRACE_BYTES = 42155008 + 2635264
+NCU_TRAFFIC_SDF_FWD_BYTES = 53127680 + 1421568
 
 
 def load_peaks():
@@ -309,17 +313,20 @@ def run_ours(ns):
         "gpu_launches": ns.steps,
         "clocks": clock_info,
         "roofline": {"bound": "hbm", "kernel": "sphere_trace_kernel", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_TRACE_BYTES, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms,
                      "compulsory_GBs": compulsory,
                      "note": "algorithmic bytes = sdf_evals x (5120 B gather + 16 B io) + rays x 53 B; the gather is "
-                             "served by L2/L1 (grids 40.5 MB < L2), so frac may exceed 1 (SURVEY.md 8d)"},
+                             "served by L2/L1 (grids 40.5 MB < L2), so frac may exceed 1 (SURVEY.md 8d); DRAM traffic "
+                             "(ncu) is the compulsory 45 MB: grids once + ray I/O. The binding resource is the L1 data "
+                             "pipe (1 line-wavefront/clk/SM), see DESIGN.md section 4"},
         "sdf_queries": {"n": SDF_N, "lod": LOD,
                         "forward_qps": world * SDF_N / (fwd_ms / 1e3), "forward_ms": fwd_ms,
                         "forward_backward_qps": world * SDF_N / ((fwd_ms + bwd_ms) / 1e3), "backward_ms": bwd_ms,
-                        "roofline": {"bound": "hbm", "kernel": "sdf_forward_kernel",
+                        "roofline": {"bound": "hbm", "kernel": "sdf_forward_tc_kernel" if MATH_MODE == "tc" else "sdf_forward_kernel",
                                      "achieved": q_bytes / (fwd_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
-                                     "frac": q_bytes / (fwd_ms / 1e3) / 1e9 / peak, "traffic": None}},
+                                     "frac": q_bytes / (fwd_ms / 1e3) / 1e9 / peak,
+                                     "traffic": NCU_TRAFFIC_SDF_FWD_BYTES}},
     }
     line["extras"] = extras
     if world == 1 and not ns.no_cpu_baseline:
