@@ -217,6 +217,47 @@ int nglod_spc_ray_aabb(const int32_t* nuggets, const int32_t* offsets, int64_t n
                        const float* query, const uint8_t* active, float* x, float* t, uint8_t* cond,
                        int32_t* pidx, void* stream);
 
+/* ---- sparse OctreeSDF: in-voxel evaluation and tracing ---------------------------
+ * The model of the reference's real-time renderer (sol-renderer/SDF.cu:65-216): corner features + per-voxel
+ * 8-corner "trinkets" with a parent link, one 35->128->1 decoder per LOD.  All LODs concatenated, coarse first. */
+typedef struct nglod_sparse_net {
+    int32_t num_lods;
+    int32_t base_lod;        /* LOD l lives on octree level l + base_lod                          */
+    int32_t feature_dim;     /* 32                                                                 */
+    int32_t hidden_dim;      /* 128                                                                */
+    int32_t math_mode;       /* NGLOD_MATH_*                                                       */
+    int32_t reserved_;
+    int32_t lod_voxel_offset[NGLOD_MAX_LODS + 2]; /* first voxel row of each LOD (and one past the last)  */
+    const float* corner_feats;   /* [NC, feature_dim]                                              */
+    const int32_t* trinkets;     /* [NV, 8] rows of corner_feats; corner k = bx + 2*by + 4*bz      */
+    const int32_t* parents;      /* [NV] voxel row one LOD up, -1 at LOD 0                         */
+    const int16_t* voxels;       /* [NV, 4] integer voxel coordinates at the voxel's own level     */
+    const float* w0[NGLOD_MAX_LODS];
+    const float* b0[NGLOD_MAX_LODS];
+    const float* w1[NGLOD_MAX_LODS];
+    const float* b1[NGLOD_MAX_LODS];
+} nglod_sparse_net_t;
+
+/* out[i] = decoder_lod([x_i, sum_{l<=lod} trilinear(corner features of the voxel chain of pidx_i)]).
+ * pidx: voxel index within LOD `lod` (level-local, as in the nuggets).  Weights are NOT clamped: a point slightly
+ * outside its voxel extrapolates, as in the reference.
+ * Replaces: sparse_grid_sample_kernel + 2x torch::addmm, sol-renderer/include/solr/solr/sdf/sparse_grid_sample.cuh:31-109,
+ * SDF.cu:412-413 (Python twin: NeuralSPC.sdf / SPC.interpolate, sdf-net/app/spc/NeuralSPC.py:104-145, SPC.py:92-102). */
+int nglod_sparse_sdf_forward(const nglod_sparse_net_t* net, int32_t lod, const float* x, const int32_t* pidx,
+                             int64_t n, float* out, void* stream);
+
+/* In-voxel sphere tracing over the nuggets of nglod_spc_raytrace (level lod + base_lod), ONE persistent kernel:
+ * first voxel (ray_aabb) -> [sparse sdf -> step -> re-locate the voxel from the new position] x num_steps -> central-
+ * difference normals (h = normal_h, same voxel) on hits.  hit = |d| < min_dis or |d + dprev|/2 < 5*min_dis;
+ * a ray stays alive while t < far and it still finds a voxel; rays that run out of voxels get depth 100.
+ * Replaces: SDF::sphereTrace / getNormal, sol-renderer/SDF.cu:218-472 with step.cuh:31-86 and ray_aabb.cuh:104-192
+ * (Python twin: SPCTracer.forward, sdf-net/app/spc/SPCTracer.py:44-113).  opts->step_size is ignored (the reference
+ * renderer has none); pidx_out (optional) receives each ray's last voxel. */
+int nglod_spc_sphere_trace(const nglod_sparse_net_t* net, int32_t lod, const int32_t* nuggets, const int32_t* offsets,
+                           const float* ray_o, const float* ray_d, int64_t n, const nglod_trace_opts_t* opts,
+                           float* x, float* depth, uint8_t* hit, float* normal, int32_t* pidx_out,
+                           int32_t* queue, unsigned long long* stats, void* stream);
+
 /* ---- Adam on a flat fp32 parameter buffer ----------------------------------
  * Replaces: torch.optim.Adam(lr) as set up by Trainer.set_optimizer,
  * sdf-net/lib/trainer.py:178-189 (betas .9/.999, eps 1e-8, no weight decay).

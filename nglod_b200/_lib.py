@@ -41,6 +41,27 @@ class NetStruct(ctypes.Structure):
     ]
 
 
+class SparseNetStruct(ctypes.Structure):
+    """nglod_sparse_net_t"""
+    _fields_ = [
+        ("num_lods", c_int32),
+        ("base_lod", c_int32),
+        ("feature_dim", c_int32),
+        ("hidden_dim", c_int32),
+        ("math_mode", c_int32),
+        ("reserved_", c_int32),
+        ("lod_voxel_offset", c_int32 * (MAX_LODS + 2)),
+        ("corner_feats", c_void_p),
+        ("trinkets", c_void_p),
+        ("parents", c_void_p),
+        ("voxels", c_void_p),
+        ("w0", c_void_p * MAX_LODS),
+        ("b0", c_void_p * MAX_LODS),
+        ("w1", c_void_p * MAX_LODS),
+        ("b1", c_void_p * MAX_LODS),
+    ]
+
+
 class NetGradStruct(ctypes.Structure):
     """nglod_net_grad_t"""
     _fields_ = [
@@ -89,6 +110,11 @@ SIGNATURES = {
     "nglod_spc_mark_first_hit": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "nglod_spc_ray_aabb": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_void_p, c_void_p,
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "nglod_sparse_sdf_forward": (ctypes.c_int, [ctypes.POINTER(SparseNetStruct), c_int32, c_void_p, c_void_p, c_int64,
+                                                c_void_p, c_void_p]),
+    "nglod_spc_sphere_trace": (ctypes.c_int, [ctypes.POINTER(SparseNetStruct), c_int32, c_void_p, c_void_p, c_void_p,
+                                              c_void_p, c_int64, ctypes.POINTER(TraceOpts), c_void_p, c_void_p, c_void_p,
+                                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "nglod_mesh2sdf": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "nglod_adam_step": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, ctypes.c_float,
                                        ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,

@@ -185,3 +185,106 @@ def ray_aabb(spc, nuggets, offsets, ray_o, ray_d, level, query=None, active=None
                                           _ptr(query), _ptr(active), _ptr(x), _ptr(t), _ptr(cond), _ptr(pidx), _stream()),
                    "nglod_spc_ray_aabb")
     return x, t, cond, pidx
+
+
+# ----------------------------------------------------------------------------------------------- sparse OctreeSDF
+class SparseOctreeSDF:
+    """An OctreeSDF restricted to the voxels of a sparse octree -- the model the reference's real-time renderer
+    traces (sol-renderer/SDF.cu:65-216: corner features `cf`, voxel->8-corner `trinkets` with a `parent` link, one
+    35->128->1 decoder per LOD; produced from a trained OctreeSDF by SOL_NGLOD, lib/models/SOL_NGLOD.py:31-100).
+
+    For LOD l the voxels are the octree's level (l + base_lod); every corner of an occupied voxel keeps the dense
+    grid's feature vector, so inside occupied voxels `sdf(x, lod, pidx)` equals the dense `OctreeSDF.sdf(x, lod)`.
+    Device tables (all LODs concatenated, coarse first):
+      corner_feats [NC, F] fp32; trinkets [NV, 8] int32 rows of corner_feats, corner k = bx + 2*by + 4*bz;
+      parents [NV] int32 voxel row one LOD up (-1 at LOD 0); voxels [NV, 4] int16; lod_offset[l] = first voxel row.
+    """
+
+    def __init__(self, net, spc):
+        self.net, self.spc = net, spc
+        self.num_lods, self.base_lod = net.num_lods, net.args.base_lod
+        if spc.level < self.num_lods + self.base_lod - 1:
+            raise ValueError("octree is shallower than the finest LOD")
+        dev = spc.octree.device
+        feats, trinkets, parents, voxels, lod_offset = [], [], [], [], [0]
+        corner_base = 0
+        prev_morton = None
+        for l in range(self.num_lods):
+            level = l + self.base_lod
+            S = (1 << level) + 1
+            vox = spc.level_points(level)[:, :3].long()                       # Morton order
+            off = torch.tensor([[k & 1, (k >> 1) & 1, (k >> 2) & 1] for k in range(8)], device=dev)
+            cor = vox.unsqueeze(1) + off.unsqueeze(0)                         # [nv, 8, 3]
+            key = (cor[..., 2] * S + cor[..., 1]) * S + cor[..., 0]
+            uniq, inv = torch.unique(key.reshape(-1), return_inverse=True)
+            cz, cy, cx = uniq // (S * S), (uniq // S) % S, uniq % S
+            fm = net.features[l].fm.data                                      # [1, F, D, H, W]
+            feats.append(fm[0][:, cz, cy, cx].t().contiguous())
+            trinkets.append((inv.reshape(-1, 8) + corner_base).int())
+            morton = points_to_morton(vox)
+            if l == 0:
+                parents.append(torch.full((vox.shape[0],), -1, dtype=torch.int32, device=dev))
+            else:
+                pi = torch.searchsorted(prev_morton, morton >> 3)
+                parents.append((pi + lod_offset[l - 1]).int())
+            prev_morton = morton
+            v4 = torch.zeros(vox.shape[0], 4, dtype=torch.int16, device=dev)
+            v4[:, :3] = vox.short()
+            voxels.append(v4)
+            corner_base += uniq.shape[0]
+            lod_offset.append(lod_offset[-1] + vox.shape[0])
+        self.corner_feats = torch.cat(feats).contiguous()
+        self.trinkets = torch.cat(trinkets).contiguous()
+        self.parents = torch.cat(parents).contiguous()
+        self.voxels = torch.cat(voxels).contiguous()
+        self.lod_offset = lod_offset
+        self.math_mode = getattr(net, "math_mode", "tc")
+
+    def struct(self):
+        s = _lib.SparseNetStruct()
+        s.num_lods, s.base_lod = self.num_lods, self.base_lod
+        s.feature_dim, s.hidden_dim = self.corner_feats.shape[1], self.net.hidden_dim
+        s.math_mode = _lib.MATH_TC3XTF32 if self.math_mode == "tc" else _lib.MATH_FP32
+        s.corner_feats, s.trinkets = self.corner_feats.data_ptr(), self.trinkets.data_ptr()
+        s.parents, s.voxels = self.parents.data_ptr(), self.voxels.data_ptr()
+        for i, o in enumerate(self.lod_offset):
+            s.lod_voxel_offset[i] = o
+        self._keep = [tuple(p.data for p in self.net.decoder_params(i)) for i in range(self.num_lods)]
+        for i, (w0, b0, w1, b1) in enumerate(self._keep):
+            s.w0[i], s.b0[i], s.w1[i], s.b1[i] = w0.data_ptr(), b0.data_ptr(), w1.data_ptr(), b1.data_ptr()
+        return s
+
+    def sdf(self, x, lod, pidx):
+        """sdf at x inside (or near) voxel `pidx` (index within level lod + base_lod): [N,3], [N] -> [N,1]."""
+        lib = _lib.load()
+        x = _f32c(x, "x")
+        pidx = pidx.int().contiguous()
+        n = x.shape[0]
+        out = torch.empty(n, 1, device=x.device)
+        s = self.struct()
+        with torch.cuda.device(x.device):
+            _lib.check(lib.nglod_sparse_sdf_forward(ctypes.byref(s), int(lod), _ptr(x), _ptr(pidx), n, _ptr(out), _stream()),
+                       "nglod_sparse_sdf_forward")
+        return out
+
+    def trace(self, ray_o, ray_d, lod, num_steps=50, min_dis=0.0003, far=5.0, normal_h=0.001, stats=None):
+        """The reference renderer's frame: traverse -> first voxel -> in-voxel sphere trace with re-location
+        (sol-renderer/sdfRenderer.cu:176-260 + SDF.cu:297-472).  Returns (x, depth, hit, normal, pidx)."""
+        lib = _lib.load()
+        ray_o, ray_d = _f32c(ray_o, "ray_o"), _f32c(ray_d, "ray_d")
+        n, dev = ray_o.shape[0], ray_o.device
+        nuggets, offsets = self.spc.raytrace(ray_o, ray_d, lod + self.base_lod, return_offsets=True)
+        x = torch.empty(n, 3, device=dev)
+        depth = torch.empty(n, 1, device=dev)
+        hit = torch.empty(n, dtype=torch.bool, device=dev)
+        normal = torch.empty(n, 3, device=dev)
+        pidx = torch.empty(n, dtype=torch.int32, device=dev)
+        queue = torch.empty(1, dtype=torch.int32, device=dev)
+        opts = _lib.TraceOpts(int(num_steps), 1, 1.0, float(min_dis), float(far), float(normal_h))
+        s = self.struct()
+        with torch.cuda.device(dev):
+            _lib.check(lib.nglod_spc_sphere_trace(ctypes.byref(s), int(lod), _ptr(nuggets), _ptr(offsets), _ptr(ray_o),
+                                                  _ptr(ray_d), n, ctypes.byref(opts), _ptr(x), _ptr(depth), _ptr(hit),
+                                                  _ptr(normal), _ptr(pidx), _ptr(queue), _ptr(stats), _stream()),
+                       "nglod_spc_sphere_trace")
+        return x, depth, hit, normal, pidx

@@ -245,8 +245,9 @@ def spc_raytrace(octree, prefix, points, pyramid, target, ray_o, ray_d):
     return nug, counts
 
 
-def spc_ray_aabb(nuggets, level_points, level, ray_o, ray_d, query=None):
-    """oracle.c:oracle_spc_ray_aabb with init semantics; returns (x, t, cond, pidx)."""
+def spc_ray_aabb(nuggets, level_points, level, ray_o, ray_d, query=None, active=None, x=None, t=None, cond=None, pidx=None):
+    """oracle.c:oracle_spc_ray_aabb; with `active` (bool [n]) only those rays are re-located and x/t/cond/pidx are
+    updated in place from the given state.  Returns (x, t, cond, pidx)."""
     lib = _clib()
     lib.oracle_spc_ray_aabb.restype = None
     nug = nuggets.cpu().int().contiguous()
@@ -254,11 +255,92 @@ def spc_ray_aabb(nuggets, level_points, level, ray_o, ray_d, query=None):
     ro, rd = ray_o.cpu().float().contiguous(), ray_d.cpu().float().contiguous()
     q = ro if query is None else query.cpu().float().contiguous()
     n = ro.shape[0]
-    x, t = q.clone(), torch.zeros(n, 1)
-    cond = torch.zeros(n, dtype=torch.uint8)
-    pidx = torch.full((n,), -1, dtype=torch.int32)
+    x = q.clone() if x is None else x.float().contiguous().clone()
+    t = torch.zeros(n, 1) if t is None else t.float().contiguous().clone()
+    cond8 = torch.zeros(n, dtype=torch.uint8) if cond is None else cond.to(torch.uint8).contiguous().clone()
+    pidx = torch.full((n,), -1, dtype=torch.int32) if pidx is None else pidx.int().contiguous().clone()
+    act = None if active is None else active.to(torch.uint8).contiguous()
     vp = ctypes.c_void_p
     lib.oracle_spc_ray_aabb(vp(nug.data_ptr()), ctypes.c_int64(nug.shape[0]), vp(lp.data_ptr()), ctypes.c_int(int(level)),
-                            vp(ro.data_ptr()), vp(rd.data_ptr()), vp(q.data_ptr()), vp(x.data_ptr()), vp(t.data_ptr()),
-                            vp(cond.data_ptr()), vp(pidx.data_ptr()))
-    return x, t, cond.bool(), pidx
+                            vp(ro.data_ptr()), vp(rd.data_ptr()), vp(q.data_ptr()), vp(act.data_ptr() if act is not None else 0),
+                            vp(x.data_ptr()), vp(t.data_ptr()), vp(cond8.data_ptr()), vp(pidx.data_ptr()))
+    return x, t, cond8.bool(), pidx
+
+
+class OracleSparseNet:
+    """CPU twin of the sparse OctreeSDF tables (nglod_b200.lib.spc.SparseOctreeSDF): corner features, trinkets,
+    parents, voxel coordinates, decoders.  Follows sol-renderer/include/solr/solr/sdf/sparse_grid_sample.cuh:31-109
+    (parent-chain walk, un-clamped trilinear weights from the voxel's own coordinates) and SDF.cu:412-413."""
+
+    def __init__(self, corner_feats, trinkets, parents, voxels, lod_offset, base_lod, decoders):
+        self.cf = corner_feats.detach().cpu().float()
+        self.trinkets = trinkets.detach().cpu().long()
+        self.parents = parents.detach().cpu().long()
+        self.voxels = voxels.detach().cpu()[:, :3].float()
+        self.lod_offset, self.base_lod = list(lod_offset), base_lod
+        self.dec = [tuple(t.detach().cpu().float() for t in d) for d in decoders]
+
+    def features(self, x, lod, pidx):
+        v = pidx.long() + self.lod_offset[lod]
+        n = torch.addcmul(torch.full_like(x, 0.5), x, torch.full_like(x, 0.5))        # fmaf(x, .5, .5)
+        chain = []
+        for l in range(lod, -1, -1):
+            chain.append((l, v))
+            if l > 0:
+                v = self.parents[v]
+        feat = None
+        for l, v in reversed(chain):                                                   # coarse -> fine
+            res = float(1 << (l + self.base_lod))
+            f = n * res - self.voxels[v]
+            g = 1.0 - f
+            s = 0
+            for k in range(8):
+                w = (f[:, 0] if k & 1 else g[:, 0]) * (f[:, 1] if k & 2 else g[:, 1]) * (f[:, 2] if k & 4 else g[:, 2])
+                s = s + w.unsqueeze(1) * self.cf[self.trinkets[v, k]]
+            feat = s if feat is None else s + feat
+        return feat
+
+    def sdf(self, x, lod, pidx):
+        w0, b0, w1, b1 = self.dec[lod]
+        inp = torch.cat([x, self.features(x, lod, pidx)], dim=-1)
+        return F.linear(F.relu(F.linear(inp, w0, b0)), w1, b1)
+
+
+def spc_sphere_trace(snet, lod, nuggets, level_points, ray_o, ray_d, num_steps=50, min_dis=0.0003, far=5.0, h=0.001):
+    """SDF::sphereTrace + getNormal, sol-renderer/SDF.cu:218-472, as the batch loop it is there.
+    Returns dict(x, depth, hit, normal, pidx)."""
+    level = lod + snet.base_lod
+    n = ray_o.shape[0]
+    x, t, cond, pidx = spc_ray_aabb(nuggets, level_points, level, ray_o, ray_d)        # :353-371 (init)
+    has_run = torch.zeros(n, dtype=torch.bool)
+    has_run[nuggets[:, 0].long().unique()] = True
+    x = torch.where(has_run.unsqueeze(1), x, ray_o.float())
+    d = torch.zeros(n, 1)
+    dprev = torch.zeros(n, 1)
+    hit = torch.zeros(n, dtype=torch.bool)
+    for _ in range(num_steps):                                                         # :378
+        act = cond.nonzero()[:, 0]
+        if act.numel() == 0:
+            break
+        _d = snet.sdf(x[act], lod, pidx[act])                                          # :394-413
+        d[act] = _d                                                                     # step.cuh:53
+        t[act] = t[act] + _d
+        h_ = (_d.abs()[:, 0].double() < float(np.float32(min_dis))) | \
+             (((_d + dprev[act]).abs()[:, 0].double() * 0.5) < float(np.float32(min_dis * 5.0)))
+        hit[act] = h_
+        cond[act] = (t[act, 0] < far) & ~h_
+        x[act] = torch.addcmul(ray_o[act], ray_d[act], t[act])                        # fmaf in the kernel; 1 ulp apart
+        dprev[act] = _d
+        x, t, cond, pidx = spc_ray_aabb(nuggets, level_points, level, ray_o, ray_d, query=x, active=cond,
+                                        x=x, t=t, cond=cond, pidx=pidx)                # :442-460
+    normal = torch.zeros(n, 3)
+    hi = hit.nonzero()[:, 0]
+    if hi.numel():
+        g = []
+        for k in range(3):
+            e = torch.zeros(3)
+            e[k] = h
+            g.append(snet.sdf(x[hi] + e, lod, pidx[hi]) - snet.sdf(x[hi] - e, lod, pidx[hi]))
+        g = torch.cat(g, dim=1)
+        normal[hi] = g / g.norm(dim=1, keepdim=True).clamp_min(1e-30)
+    return dict(x=x, depth=t, hit=hit, normal=normal, pidx=pidx)

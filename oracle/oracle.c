@@ -237,12 +237,16 @@ static float spc_ray_aabb1(const float* q, const float* dir, const float* inv, c
  * query point (d = -r, no advance) or that the ray enters (d > 0, t += d).  Rays without a run are left untouched.
  * level_points: points of the nugget level [*,4] int16. */
 void oracle_spc_ray_aabb(const int32_t* nuggets, int64_t num_nuggets, const short* level_points, int level,
-                         const float* ray_o, const float* ray_d, const float* query, float* x, float* t,
-                         uint8_t* cond, int32_t* pidx) {
+                         const float* ray_o, const float* ray_d, const float* query, const uint8_t* active,
+                         float* x, float* t, uint8_t* cond, int32_t* pidx) {
     const float r = 1.0f / (float)(1 << level);
     int64_t i = 0;
     while (i < num_nuggets) {
         const int32_t ray = nuggets[2 * i];
+        if (active && !active[ray]) {                       /* `if (!cond[ridx] && !init) continue;` (:130) */
+            while (i < num_nuggets && nuggets[2 * i] == ray) ++i;
+            continue;
+        }
         const float* dir = ray_d + 3 * (int64_t)ray;
         const float inv[3] = {1.0f / dir[0], 1.0f / dir[1], 1.0f / dir[2]};
         const float sgn[3] = {signbit(dir[0]) ? 1.0f : -1.0f, signbit(dir[1]) ? 1.0f : -1.0f, signbit(dir[2]) ? 1.0f : -1.0f};

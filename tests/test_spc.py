@@ -156,3 +156,99 @@ def test_mesh_to_octree_on_device():
     assert 8000 < leaf.shape[0] < 40000
     q = S.quantize_points(V.cuda(), 6)
     assert (spc.query(q, 6) >= 0).all()                                        # every mesh vertex lies in an occupied voxel
+
+
+# ------------------------------------------------------------------------------------------------ sparse OctreeSDF (a18)
+def _fit3_sparse(fit3, device, level=4):
+    """fit3 model (3 LODs, base 2 -> levels 2..4) + the octree of its torus at level 4 + sparse tables."""
+    from helpers import fit3_model
+    from nglod_b200.lib.torchgp import torus, normalize
+    net, args = fit3_model(fit3, device)
+    V, F = torus(0.6, 0.25, 64, 32)
+    # shell of voxels around the analytic torus (deterministic, CPU-friendly): all level-4 voxels whose corner SDFs straddle 0
+    n = 1 << level
+    ax = torch.arange(n)
+    g = torch.stack(torch.meshgrid(ax, ax, ax, indexing="ij"), dim=-1).reshape(-1, 3)
+    lo = g.float() / n * 2 - 1
+    from helpers import torus_sdf
+    d = torch.stack([torus_sdf(lo + torch.tensor([i >> 2, (i >> 1) & 1, i & 1]).float() * (2.0 / n)) for i in range(8)], 0)
+    occ = (d.min(0)[0] <= 0.02) & (d.max(0)[0] >= -0.02)
+    octree = S.points_to_octree(g[occ], level).to(device)
+    spc = S.SPC(octree)
+    return net, args, spc, S.SparseOctreeSDF(net, spc)
+
+
+def _points_in_voxels(spc, level, count, seed, spread=1.0):
+    g = torch.Generator().manual_seed(seed)
+    lp = spc.level_points(level)[:, :3].cpu().float()
+    pidx = torch.randint(0, lp.shape[0], (count,), generator=g)
+    frac = 0.5 + (torch.rand(count, 3, generator=g) - 0.5) * spread
+    x = (lp[pidx] + frac) / (1 << level) * 2 - 1
+    return x, pidx
+
+
+def test_oracle_sparse_equals_dense_inside_voxels(fit3):
+    net, args, spc, sp = _fit3_sparse(fit3, "cpu")
+    osn = O.OracleSparseNet(sp.corner_feats, sp.trinkets, sp.parents, sp.voxels, sp.lod_offset, sp.base_lod,
+                            [net.decoder_params(i) for i in range(3)])
+    dense = O.OracleNet(net.state_dict())
+    for lod in (0, 1, 2):
+        x, pidx = _points_in_voxels(spc, lod + 2, 3000, lod)
+        with torch.no_grad():
+            assert (osn.sdf(x, lod, pidx) - dense.sdf(x, lod=lod)).abs().max() < 2e-6
+    # parents really are the enclosing voxels one level up
+    v = torch.arange(sp.lod_offset[2], sp.lod_offset[3])
+    assert torch.equal(sp.voxels[sp.parents[v].long(), :3].long(), sp.voxels[v, :3].long() >> 1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("math_mode", ["fp32", "tc"])
+def test_sparse_sdf_kernel_vs_dense_and_oracle(fit3, math_mode):
+    net, args, spc, sp = _fit3_sparse(fit3, "cuda")
+    net.math_mode = sp.math_mode = math_mode
+    osn = O.OracleSparseNet(sp.corner_feats, sp.trinkets, sp.parents, sp.voxels, sp.lod_offset, sp.base_lod,
+                            [net.decoder_params(i) for i in range(3)])
+    for lod, count in ((2, 50001), (1, 1000), (0, 33)):
+        x, pidx = _points_in_voxels(spc, lod + 2, count, 10 + lod)
+        with torch.no_grad():
+            got = sp.sdf(x.cuda(), lod, pidx.cuda()).cpu()
+            assert (got - net.sdf(x.cuda(), lod=lod).cpu()).abs().max() < 3e-6
+            assert (got - osn.sdf(x, lod, pidx)).abs().max() < 3e-6
+    # slightly outside the voxel: weights extrapolate (not clamped), like the reference kernel
+    x, pidx = _points_in_voxels(spc, 4, 2000, 99, spread=1.3)
+    with torch.no_grad():
+        assert (sp.sdf(x.cuda(), 2, pidx.cuda()).cpu() - osn.sdf(x, 2, pidx)).abs().max() < 3e-6
+    assert sp.sdf(x[:0].cuda(), 2, pidx[:0].cuda()).shape == (0, 1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("math_mode", ["fp32", "tc"])
+def test_spc_sphere_trace_vs_oracle(fit3, math_mode):
+    net, args, spc, sp = _fit3_sparse(fit3, "cuda")
+    net.math_mode = sp.math_mode = math_mode
+    osn = O.OracleSparseNet(sp.corner_feats, sp.trinkets, sp.parents, sp.voxels, sp.lod_offset, sp.base_lod,
+                            [net.decoder_params(i) for i in range(3)])
+    torch.manual_seed(8)
+    ro, rd = O.look_at([-2.8, 2.8, -2.8], [0, 0, 0], 160, 90, fov=30.0)
+    x, depth, hit, normal, pidx = sp.trace(ro.cuda(), rd.cuda(), 2)
+    nug = spc.raytrace(ro.cuda(), rd.cuda(), 4).cpu()
+    with torch.no_grad():
+        ref = O.spc_sphere_trace(osn, 2, nug, spc.level_points(4).cpu(), ro, rd)
+    h = ref["hit"]
+    mism = int((hit.cpu() != h).sum())
+    both = h & hit.cpu()
+    dd = (depth.cpu() - ref["depth"]).abs()[:, 0]
+    nn = (normal.cpu() - ref["normal"]).abs().max(dim=1)[0]
+    print(f"spc trace [{math_mode}]: {int(h.sum())} hits of {h.numel()} rays, {mism} hit mismatches, depth max "
+          f"{float(dd[both].max()):.2e}, normal max {float(nn[both].max()):.2e} (>1e-3: {int((nn[both] > 1e-3).sum())})")
+    assert int(h.sum()) > 800
+    assert mism <= 2
+    assert float((dd[both] > 2e-4).float().mean()) < 2e-3
+    assert float((nn[both] > 1e-3).float().mean()) < 1e-2
+    assert (normal.cpu()[~hit.cpu()] == 0).all()
+    # hits lie on the fitted surface: the dense model agrees the SDF is ~0 there
+    with torch.no_grad():
+        assert net.sdf(x[hit], lod=2).abs().max() < 5e-3
+    no_run = torch.ones(ro.shape[0], dtype=torch.bool)
+    no_run[nug[:, 0].long().unique()] = False
+    assert not hit.cpu()[no_run].any() and (depth.cpu()[no_run] == 0).all()
