@@ -399,7 +399,24 @@ def run_extras(net, args, device, rank, world, flush, log):
     out["spc_raytrace_1080p_level7"] = {"rays": ro.shape[0], "nuggets": int(nug.shape[0]), "voxels": int(spc.pyramid[0, 7]),
                                         "ms": trav_ms, "rays_per_s": world * ro.shape[0] / (trav_ms / 1e3),
                                         "note": "count + scan + fill, includes the one 4-byte host read of the total"}
-    del nug, ro, rd
+    del nug
+
+    # ---- config 4 (tracing half): sparse OctreeSDF of the fitted net over the level-6 octree, in-voxel sphere tracing
+    #      with voxel re-location, lods 1-4 (lod l <-> octree level l+2), 1920x1080
+    octree6 = S.mesh_to_octree(V, F, 6, num_samples=1 << 22)
+    sp = S.SparseOctreeSDF(net, S.SPC(octree6))
+    sweep = {}
+    for lod in (1, 2, 3, 4):
+        st = torch.zeros(2, dtype=torch.int64, device=device)
+        x_, t_, hit_, n_, p_ = sp.trace(ro, rd, lod, stats=st)
+        ms = timed(lambda: sp.trace(ro, rd, lod), iters=3, warm=1)
+        sweep[f"lod{lod}"] = {"ms": ms, "rays_per_s": world * ro.shape[0] / (ms / 1e3), "hits": int(hit_.sum()),
+                              "sdf_evals_per_ray": int(st[0]) / ro.shape[0]}
+    out["spc_sphere_trace_1080p"] = {"rays": ro.shape[0], "octree_level": 6, "voxels": int(sp.spc.pyramid[0, 6]),
+                                     "corner_rows": int(sp.corner_feats.shape[0]), "lods": sweep,
+                                     "note": "traverse + first voxel + in-voxel trace (50 steps, far 5) + normals, one "
+                                             "host read per frame (nugget total)"}
+    del ro, rd, sp
 
     # ---- config 5: 3840x2160, shadows + normals, image cut into column strips over the ranks (x-major rays)
     w4, h4 = 3840, 2160
