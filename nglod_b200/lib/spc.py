@@ -240,6 +240,35 @@ class SparseOctreeSDF:
         self.lod_offset = lod_offset
         self.math_mode = getattr(net, "math_mode", "tc")
 
+    def save(self, path):
+        """Write the reference's real-time renderer format (SOL_NGLOD.save, lib/models/SOL_NGLOD.py:80-100; read by
+        sol-renderer/SDF.cu:65-139): octree bytes, corner coordinates `cc` (uint8), corner features `cf` and the
+        decoders in fp16, and `pyramid` = corner rows per LOD."""
+        import numpy as np
+        cc, counts = [], []
+        row = 0
+        for l in range(self.num_lods):
+            v = slice(self.lod_offset[l], self.lod_offset[l + 1])
+            tr = self.trinkets[v].long()
+            nrows = int(tr.max()) + 1 - row
+            coords = torch.zeros(nrows, 3, dtype=torch.uint8, device=tr.device)
+            vox = self.voxels[v, :3].long()
+            for k in range(8):
+                off = torch.tensor([k & 1, (k >> 1) & 1, (k >> 2) & 1], device=tr.device)
+                coords[tr[:, k] - row] = (vox + off).to(torch.uint8)
+            cc.append(coords)
+            counts.append(nrows)
+            row += nrows
+        dec = [self.net.decoder_params(i) for i in range(self.num_lods)]
+        np.savez_compressed(
+            path, octree=self.spc.octree.cpu().numpy(), cc=torch.cat(cc).cpu().numpy(),
+            cf=self.corner_feats.half().cpu().numpy(),
+            w0=torch.stack([d[0].detach().half() for d in dec]).cpu().numpy(),
+            b0=torch.stack([d[1].detach().half() for d in dec]).cpu().numpy(),
+            w1=torch.stack([d[2].detach().half() for d in dec]).cpu().numpy(),
+            b1=torch.stack([d[3].detach().half() for d in dec]).cpu().numpy(),
+            pyramid=np.array(counts))
+
     def struct(self):
         s = _lib.SparseNetStruct()
         s.num_lods, s.base_lod = self.num_lods, self.base_lod

@@ -48,6 +48,7 @@ class FusedTrainer:
             self._grad_views[p] = gview
             off += sz
         self.loss = torch.zeros(1, device=dev)
+        self.lod_loss = torch.zeros(net.num_lods, device=dev)
 
     def _grad_lists(self):
         net = self.net
@@ -55,20 +56,238 @@ class FusedTrainer:
         dec_grads = [tuple(self._grad_views[p] for p in net.decoder_params(i)) for i in range(net.num_lods)]
         return grid_grads, dec_grads
 
-    def step(self, pts, gts, global_batch=None):
+    def step(self, pts, gts, global_batch=None, loss_lods=None):
         """One optimisation step on this rank's slice (pts [B,3], gts [B,1] on the device).
-        Returns the device scalar holding this rank's share of the loss (already divided by global_batch)."""
+        Returns the device scalar holding this rank's share of the loss (already divided by global_batch);
+        `self.lod_loss[l]` holds LOD l's share."""
         net = self.net
         batch = pts.shape[0] if global_batch is None else global_batch
+        lods = self.loss_lods if loss_lods is None else list(loss_lods)
         self.flat_grad.zero_()
-        self.loss.zero_()
-        mask = 0
-        for l in self.loss_lods:
-            mask |= 1 << l
+        self.lod_loss.zero_()
         grid_grads, dec_grads = self._grad_lists()
-        ops.sdf_train_step(net.net_view(), mask, pts, gts, 1.0 / batch, grid_grads, dec_grads, self.loss)
+        view = net.net_view()
+        for l in lods:          # one fused forward+loss+backward launch per LOD head, each with its own loss cell
+            ops.sdf_train_step(view, 1 << l, pts, gts, 1.0 / batch, grid_grads, dec_grads, self.lod_loss[l:l + 1])
+        torch.sum(self.lod_loss, dim=0, keepdim=True, out=self.loss)
         ndist.allreduce_sum_(self.flat_grad)
         self.step_count += 1
         ops.adam_step(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count, lr=self.lr,
                       beta1=self.betas[0], beta2=self.betas[1], eps=self.eps)
         return self.loss
+
+
+# ------------------------------------------------------------------------------------------------ Trainer
+import logging as log
+import os
+from datetime import datetime
+
+
+class Trainer(object):
+    """The reference's training loop (sdf-net/lib/trainer.py:89-502) around the fused step: same constructor
+    `(args, args_str)`, same hooks (`set_dataset/set_network/set_optimizer/set_renderer/set_logger`, `pre_epoch`,
+    `grow`, `iterate`, `step_geometry`, `post_epoch`, `log_tb`, `save_model`, `resample`, `train`), same LOD growth
+    strategies, resample cadence, loss bookkeeping and checkpoint naming -- so `app/main.py` runs unchanged.
+
+    What differs is where things live: the dataset stays on the device (no DataLoader / pinned-memory hop per
+    512-point batch), a step is the fused forward+loss+backward kernels + one Adam launch over flat buffers, losses
+    are accumulated on the device and read once per epoch (the reference calls `.item()` twice per iteration), and
+    with several ranks each takes a slice of every batch and the flat gradient is all-reduced once per step.
+    TensorBoard is used when importable; its absence only disables the image/scalar summaries.
+    """
+
+    def __init__(self, args, args_str=""):
+        self.args = args
+        self.args_str = args_str
+        self.args.epochs += 1                                     # trainer.py:99
+        if not torch.cuda.is_available():
+            raise RuntimeError("training needs a CUDA device (nglod_b200 has no CPU path)")
+        self.rank, self.world, local = ndist.init_from_env()
+        self.device = torch.device("cuda", local)
+        torch.cuda.set_device(self.device)
+        self.latents = None
+        self.dataset_size = None
+        self.log_dict = {}
+        self.loss_lods = list(range(self.args.num_lods))
+        self.set_dataset()
+        self.set_network()
+        self.set_optimizer()
+        self.set_renderer()
+        self.set_logger()
+
+    # -- construction hooks
+    def set_dataset(self):
+        from .datasets import MeshDataset
+        classes = {"MeshDataset": MeshDataset}
+        self.train_dataset = classes[self.args.mesh_dataset](self.args, device=self.device)
+        log.info("Dataset Size: {}".format(len(self.train_dataset)))
+
+    def set_network(self):
+        from . import models
+        self.net = getattr(models, self.args.net)(self.args)
+        if self.args.pretrained:
+            self.net.load_state_dict(torch.load(self.args.pretrained, map_location="cpu"))
+        self.net.to(self.device)
+        if self.world > 1:                                        # replicas start identical
+            for p in self.net.parameters():
+                torch.distributed.broadcast(p.data, src=0)
+        log.info("Total number of parameters: {}".format(sum(p.numel() for p in self.net.parameters())))
+
+    def set_optimizer(self):
+        if self.args.optimizer == "adam":
+            self.optimizer = FusedTrainer(self.net, lr=self.args.lr)
+        elif self.args.optimizer == "sgd":
+            self.optimizer = torch.optim.SGD(self.net.parameters(), lr=self.args.lr, momentum=0.8)
+        else:
+            raise ValueError("Invalid optimizer.")
+
+    def set_renderer(self):
+        from . import tracer as tracers
+        from .renderer import Renderer
+        self.log_tracer = getattr(tracers, self.args.tracer)(self.args)
+        self.renderer = Renderer(self.log_tracer, args=self.args, device=self.device)
+
+    def set_logger(self):
+        self.log_fname = self.args.exp_name if self.args.exp_name else datetime.now().strftime("%Y%m%d-%H%M%S")
+        self.log_dir = os.path.join(self.args.logs, self.log_fname)
+        self.writer = None
+        if self.rank == 0:
+            try:
+                from torch.utils.tensorboard import SummaryWriter
+                self.writer = SummaryWriter(self.log_dir, purge_step=0)
+                self.writer.add_text("Parameters", self.args_str)
+            except Exception:  # noqa: BLE001  -- tensorboard is optional
+                self.writer = None
+
+    # -- epoch hooks
+    def pre_epoch(self, epoch):
+        self.loss_lods = list(range(0, self.args.num_lods))
+        if self.args.grow_every > 0:
+            self.grow(epoch)
+        if self.args.only_last:
+            self.loss_lods = self.loss_lods[-1:]
+        if epoch % self.args.resample_every == 0:
+            self.resample(epoch)
+        if epoch == self.args.freeze:
+            self.net.freeze()
+        self.net.train()
+        self._epoch_loss = torch.zeros(2, device=self.device)      # [last-LOD l2 sum, total sum] (un-normalised)
+        self.log_dict["l2_loss"] = 0
+        self.log_dict["total_loss"] = 0
+        self.log_dict["total_iter_count"] = 0
+
+    def grow(self, epoch):
+        """Coarse-to-fine schedules (trainer.py:262-276)."""
+        n = self.args.num_lods
+        stage = min(n, (epoch // self.args.grow_every) + 1)
+        every = list(range(0, n))
+        strategy = self.args.growth_strategy
+        if strategy == "onebyone":
+            self.loss_lods = [stage - 1]
+        elif strategy == "increase":
+            self.loss_lods = every[:stage]
+        elif strategy == "shrink":
+            self.loss_lods = every[stage - 1:]
+        elif strategy == "finetocoarse":
+            self.loss_lods = every[n - stage:]
+        elif strategy == "onlylast":
+            self.loss_lods = every[-1:]
+        else:
+            raise NotImplementedError
+
+    def batches(self):
+        """Shuffled batches of the device-resident dataset (what DataLoader(shuffle=True) yields in the reference);
+        with several ranks every rank walks the same permutation and takes its slice of each batch."""
+        n = len(self.train_dataset)
+        g = torch.Generator(device=self.device)
+        g.manual_seed(int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) if self.world == 1 else 1234 + self._epoch)
+        perm = torch.randperm(n, device=self.device, generator=g)
+        bs = self.args.batch_size
+        for start in range(0, n, bs):
+            idx = perm[start:start + bs]
+            s, e = ndist.shard_range(idx.shape[0], self.rank, self.world)
+            yield self.train_dataset.pts[idx[s:e]], self.train_dataset.d[idx[s:e]], idx.shape[0]
+
+    def iterate(self, epoch):
+        self._epoch = epoch
+        self.dataset_size = (len(self.train_dataset) + self.args.batch_size - 1) // self.args.batch_size
+        for n_iter, data in enumerate(self.batches()):
+            self.step_geometry(epoch, n_iter, data)
+
+    def step_geometry(self, epoch, n_iter, data):
+        """loss = sum_{lod in loss_lods} sum_i (sdf_lod(x_i) - gt_i)^2 / batch; backward; optimizer step
+        (trainer.py:294-340).  `data` = (pts, gts, global batch size)."""
+        pts, gts, batch = data
+        if isinstance(self.optimizer, FusedTrainer):
+            self.optimizer.step(pts, gts, global_batch=batch, loss_lods=self.loss_lods)
+            lod_loss = self.optimizer.lod_loss
+            self._epoch_loss[0] += lod_loss[self.loss_lods[-1]] * batch
+            self._epoch_loss[1] += self.optimizer.loss[0] * batch
+        else:
+            self.net.zero_grad()
+            loss, last = 0, None
+            for lod in self.loss_lods:
+                last = ((self.net.sdf(pts, lod=lod) - gts) ** 2).sum()
+                loss = loss + last
+            self._epoch_loss[0] += last.detach()
+            self._epoch_loss[1] += loss.detach()
+            (loss / batch).backward()
+            if self.world > 1:
+                for p in self.net.parameters():
+                    if p.grad is not None:
+                        torch.distributed.all_reduce(p.grad)
+            self.optimizer.step()
+        self.log_dict["total_iter_count"] += batch
+
+    def post_epoch(self, epoch):
+        self.net.eval()
+        self.log_tb(epoch)
+        if epoch % self.args.save_every == 0 and self.rank == 0:
+            self.save_model(epoch)
+        if epoch % self.args.render_every == 0 and self.writer is not None:
+            self.render_tb(epoch)
+
+    def log_tb(self, epoch):
+        sums = self._epoch_loss.clone()
+        ndist.allreduce_sum_(sums)
+        l2, total = (float(v) for v in sums.cpu())               # the one host read of the epoch
+        self.log_dict["l2_loss"] = l2 / (self.log_dict["total_iter_count"] + 1e-6)
+        self.log_dict["total_loss"] = total / (self.log_dict["total_iter_count"] + 1e-6)
+        log.info("EPOCH {}/{} | total loss: {:>.3E} | l2 loss: {:>.3E}".format(
+            epoch + 1, self.args.epochs, self.log_dict["total_loss"], self.log_dict["l2_loss"]))
+        if self.writer is not None:
+            self.writer.add_scalar("Loss/l2_loss", self.log_dict["l2_loss"], epoch)
+            self.writer.add_scalar("Loss/total_loss", self.log_dict["total_loss"], epoch)
+
+    def render_tb(self, epoch):
+        for d in range(self.args.num_lods):
+            self.net.lod = d
+            out = self.renderer.shade_images(self.net, f=self.args.camera_origin, t=self.args.camera_lookat,
+                                             fov=self.args.camera_fov).image().byte().numpy()
+            for tag, img in (("Depth", out.depth), ("Hit", out.hit), ("Normal", out.normal), ("RGB", out.rgb)):
+                self.writer.add_image(f"{tag}/{d}", img.transpose(2, 0, 1), epoch)
+            self.net.lod = None
+
+    def save_model(self, epoch):
+        """Checkpoint naming of trainer.py:416-442: <model_path>/<exp>[-<epoch>].pth, state_dict unless --save-all."""
+        parts = self.log_fname.split("/")
+        os.makedirs(os.path.join(self.args.model_path, *parts[:-1]), exist_ok=True)
+        name = f"{self.log_fname}-{epoch}.pth" if self.args.save_as_new else f"{self.log_fname}.pth"
+        fname = os.path.join(self.args.model_path, name)
+        log.info(f"Saving model checkpoint to: {fname}")
+        if self.args.save_all:
+            torch.save(self.net, fname)
+        else:   # contiguous NCDHW copies: the file is byte-compatible with a reference checkpoint
+            torch.save({k: v.detach().cpu().contiguous() for k, v in self.net.state_dict().items()}, fname)
+        return fname
+
+    def resample(self, epoch):
+        self.train_dataset.resample()
+
+    def train(self):
+        for epoch in range(self.args.epochs):
+            self.pre_epoch(epoch)
+            self.iterate(epoch)
+            self.post_epoch(epoch)
+        if self.writer is not None:
+            self.writer.close()
