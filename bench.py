@@ -348,6 +348,7 @@ def run_extras(net, args, device, rank, world, flush, log):
     from nglod_b200.lib.torchgp import torus, point_sample, normalize
     from nglod_b200.lib.geoutils import look_at
     out = {}
+    import copy
 
     def timed(fn, iters=5, warm=2):
         for _ in range(warm):
@@ -364,6 +365,22 @@ def run_extras(net, args, device, rank, world, flush, log):
             ts.append(a.elapsed_time(b))
         return ndist.max_over_ranks(float(np.mean(ts)), device)
 
+    # ---- config 2, whole user-facing frame: Renderer.shade_images (rays from look_at + trace + matcap shading on the
+    #      device + every buffer copied to the host and transposed to (H,W,C)), wall clock
+    rargs2 = copy.copy(args)
+    rargs2.render_res = [W, H]
+    r2 = Renderer(SphereTracer(rargs2), args=rargs2, device=device)
+    for _ in range(2):
+        r2.shade_images(net, f=CAM_FROM, t=CAM_TO, fov=FOV)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        img = r2.shade_images(net, f=CAM_FROM, t=CAM_TO, fov=FOV)
+    shade_s = ndist.max_over_ranks((time.perf_counter() - t0) / 5, device)
+    out["shade_images_720p"] = {"ms": shade_s * 1e3, "fps": 1.0 / shade_s, "hit_pixels": int(img.hit.sum()),
+                                "note": "Renderer.shade_images end to end: look_at rays, sphere trace, matcap shading, "
+                                        "all RenderBuffer fields to host, (H,W,C) layout"}
+
     # ---- config 3: training step on a 500 000-point batch sharded over the ranks (fused 5-head fwd+bwd, one
     #      all-reduce of the flat gradient, Adam kernel) + the cost of producing the batch (sampling + mesh2sdf labels)
     V, F = normalize(*[t.to(device) for t in torus(0.6, 0.25, 128, 64)])
@@ -377,7 +394,6 @@ def run_extras(net, args, device, rank, world, flush, log):
 
     sample_ms = timed(make_batch, iters=3, warm=1)
     pts, gts = make_batch()
-    import copy
     tnet = copy.deepcopy(net)
     tnet.train()
     trainer = FusedTrainer(tnet, lr=1e-3)

@@ -258,6 +258,21 @@ int nglod_spc_sphere_trace(const nglod_sparse_net_t* net, int32_t lod, const int
                            float* x, float* depth, uint8_t* hit, float* normal, int32_t* pidx_out,
                            int32_t* queue, unsigned long long* stats, void* stream);
 
+/* ---- renderer entry-point helpers ------------------------------------------------
+ * Camera rays, x-major (ray = ix*height + iy).  origin/view/right/up: HOST float[3] (already normalised, as computed
+ * by look_at, sdf-net/lib/geoutils.py:180-188); window_x [width] / window_y [height]: DEVICE window coordinates
+ * including the per-column / per-row jitter of normalized_grid (geoutils.py:140-154).  ortho: 0 = perspective.
+ * Replaces the tensor expression of geoutils.py:189-204. */
+int nglod_generate_rays(const float* origin, const float* view, const float* right, const float* up,
+                        float tan_half_fov, int32_t ortho, const float* window_x, const float* window_y,
+                        int32_t width, int32_t height, float* ray_o, float* ray_d, void* stream);
+
+/* Matcap shading of a traced frame on the device: uv = spherical_envmap(view, normal) (geoutils.py:253-275),
+ * rgb = bilinear(matcap[nu,nv,nc], uv)/255 on hits; misses get rgb = 1 and normal = 1 (renderer.py:279-296, which
+ * does this lookup on the HOST through scipy).  view/normal/rgb: [n,3]; hit: [n] u8; matcap indexed [u][v][c]. */
+int nglod_shade_matcap(const float* view, float* normal, const uint8_t* hit, const float* matcap,
+                       int32_t nu, int32_t nv, int32_t nc, int64_t n, float* rgb, void* stream);
+
 /* ---- Adam on a flat fp32 parameter buffer ----------------------------------
  * Replaces: torch.optim.Adam(lr) as set up by Trainer.set_optimizer,
  * sdf-net/lib/trainer.py:178-189 (betas .9/.999, eps 1e-8, no weight decay).

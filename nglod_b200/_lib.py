@@ -115,6 +115,10 @@ SIGNATURES = {
     "nglod_spc_sphere_trace": (ctypes.c_int, [ctypes.POINTER(SparseNetStruct), c_int32, c_void_p, c_void_p, c_void_p,
                                               c_void_p, c_int64, ctypes.POINTER(TraceOpts), c_void_p, c_void_p, c_void_p,
                                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "nglod_generate_rays": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float)] * 4 + [ctypes.c_float, c_int32, c_void_p, c_void_p,
+                                           c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "nglod_shade_matcap": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int64,
+                                          c_void_p, c_void_p]),
     "nglod_mesh2sdf": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "nglod_adam_step": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, ctypes.c_float,
                                        ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,

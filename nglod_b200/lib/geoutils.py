@@ -35,8 +35,32 @@ def normalized_slice(width, height, dim=0, depth=0.0, device="cuda"):
     return pts
 
 
+def _window(width, height, device):
+    """normalized_grid's two jittered coordinate vectors (one torch.rand per column, then one per row)."""
+    wx = torch.linspace(-1, 1, steps=width, device=device) * (width / height)
+    wx += torch.rand(*wx.shape, device=device) * (1.0 / width)
+    wy = torch.linspace(1, -1, steps=height, device=device)
+    wy += torch.rand(*wy.shape, device=device) * (1.0 / height)
+    return wx, wy
+
+
 def look_at(f, t, width, height, mode="ortho", fov=90.0, device="cuda"):
-    """Ray origins / directions [W*H, 3] for a camera at `f` looking at `t` (reference :180-206)."""
+    """Ray origins / directions [W*H, 3] for a camera at `f` looking at `t` (reference :180-206).
+    On a CUDA device the [W,H] expansion is one kernel (nglod_generate_rays); the jitter is still drawn with
+    torch.rand on the device in the reference's order."""
+    if mode not in ("ortho", "persp"):
+        raise ValueError("Invalid camera mode!")
+    dev = torch.device(device)
+    if dev.type == "cuda":
+        from .. import ops
+        origin = torch.tensor(list(f), dtype=torch.float32)
+        view = F.normalize(torch.tensor(list(t), dtype=torch.float32) - origin, dim=0)
+        right = F.normalize(torch.linalg.cross(view, torch.tensor([0.0, 1.0, 0.0])), dim=0)
+        up = F.normalize(torch.linalg.cross(right, view), dim=0)
+        with torch.cuda.device(dev):
+            wx, wy = _window(width, height, dev)
+        tan = np.float32(np.tan(np.radians(fov / 2)))
+        return ops.generate_rays(origin.tolist(), view.tolist(), right.tolist(), up.tolist(), tan, mode == "ortho", wx, wy)
     origin = torch.tensor(list(f), dtype=torch.float32, device=device)
     view = F.normalize(torch.tensor(list(t), dtype=torch.float32, device=device) - origin, dim=0)
     world_up = torch.tensor([0.0, 1.0, 0.0], device=device)
@@ -50,11 +74,9 @@ def look_at(f, t, width, height, mode="ortho", fov=90.0, device="cuda"):
     if mode == "ortho":
         ray_d = F.normalize(view.unsqueeze(0).repeat(plane.shape[0], 1), dim=-1)
         ray_o = plane
-    elif mode == "persp":
+    else:
         ray_d = F.normalize(plane - origin, dim=-1)
         ray_o = origin.repeat(ray_d.shape[0], 1)
-    else:
-        raise ValueError("Invalid camera mode!")
     return ray_o, ray_d
 
 

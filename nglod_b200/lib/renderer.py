@@ -18,6 +18,7 @@ from .diffutils import gradient
 from .geoutils import look_at, spherical_envmap, matcap_sampler, procedural_matcap, normalized_slice, \
     gaussian_blur2d
 from .tracer import RenderBuffer
+from .. import ops
 
 
 class Renderer():
@@ -143,19 +144,28 @@ class Renderer():
     def shade_tensor(self, net, f=[0, 0, 1], t=[0, 0, 0], fov=30.0, mm=None):
         rb = self.render_lookat(net, f=f, t=t, fov=fov, mm=mm)
         if self.shading_mode == "matcap":
-            view = rb.view.clone()
+            view = rb.view
             if mm is not None:
                 mm = mm.to(view.device)
                 view = torch.mm(view.reshape(-1, 3), mm.transpose(1, 0)).reshape(self.width, self.height, 3)
-            uv = spherical_envmap(view, rb.normal.clone())
-            rb.rgb = self._get_matcap(uv.device)(uv).reshape(self.width, self.height, -1)[..., :3] / 255.0
+            matcap = self._get_matcap(view.device)
+            if view.is_cuda:
+                # envmap + bilinear lookup + "misses are white" (normals of misses -> 1) in one kernel
+                rb.normal = rb.normal.contiguous()
+                rb.rgb = ops.shade_matcap(view, rb.normal, rb.hit, matcap.tex)
+            else:
+                uv = spherical_envmap(view.clone(), rb.normal.clone())
+                rb.rgb = matcap(uv).reshape(self.width, self.height, -1)[..., :3] / 255.0
+                miss = ~rb.hit[..., 0]
+                rb.normal[miss] = 1.0
+                rb.rgb[miss] = 1.0
         elif self.shading_mode == "rb":
             assert rb.rgb is not None, "No rgb in buffer; change shading-mode"
+            miss = ~rb.hit[..., 0]
+            rb.normal[miss] = 1.0
+            rb.rgb[miss] = 1.0
         else:
             raise NotImplementedError
-        miss = ~rb.hit[..., 0]
-        rb.normal[miss] = 1.0
-        rb.rgb[miss] = 1.0
         if self.shadow:
             smap = torch.clamp(1.0 - rb.shadow.float() + 0.9, 0.0, 1.0)[..., 0]
             rb.rgb[..., :3] *= gaussian_blur2d(smap, 2.0).unsqueeze(-1)

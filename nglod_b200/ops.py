@@ -232,3 +232,35 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, step, lr=1e-3, beta1=0.9, beta2=
     with torch.cuda.device(param.device):
         _lib.check(lib.nglod_adam_step(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), n, lr, beta1, beta2,
                                        eps, bc1, bc2, _stream()), "nglod_adam_step")
+
+
+# --------------------------------------------------------------------------- renderer helpers
+def generate_rays(origin, view, right, up, tan_half_fov, ortho, window_x, window_y):
+    """[W*H,3] ray origins / directions (x-major) from a camera basis (host 3-vectors) and device window coordinates."""
+    lib = _lib.load()
+    w, h = window_x.shape[0], window_y.shape[0]
+    dev = window_x.device
+    ray_o = torch.empty(w * h, 3, device=dev, dtype=torch.float32)
+    ray_d = torch.empty(w * h, 3, device=dev, dtype=torch.float32)
+    vec = [(ctypes.c_float * 3)(*[float(c) for c in v]) for v in (origin, view, right, up)]
+    with torch.cuda.device(dev):
+        _lib.check(lib.nglod_generate_rays(vec[0], vec[1], vec[2], vec[3], float(tan_half_fov), 1 if ortho else 0,
+                                           _ptr(_f32c(window_x, "window_x")), _ptr(_f32c(window_y, "window_y")), w, h,
+                                           _ptr(ray_o), _ptr(ray_d), _stream()), "nglod_generate_rays")
+    return ray_o, ray_d
+
+
+def shade_matcap(view, normal, hit, matcap):
+    """In place on `normal` (misses -> 1); returns rgb with view's shape.  matcap: [U,V,C>=3] fp32 on the device."""
+    lib = _lib.load()
+    shape = view.shape
+    v = _f32c(view, "view").reshape(-1, 3)
+    if not (normal.is_contiguous() and normal.dtype == torch.float32):
+        raise RuntimeError("normal must be a contiguous fp32 tensor (shaded in place)")
+    h = hit.reshape(-1).contiguous()
+    tex = _f32c(matcap, "matcap")
+    rgb = torch.empty_like(v)
+    with torch.cuda.device(v.device):
+        _lib.check(lib.nglod_shade_matcap(_ptr(v), _ptr(normal), _ptr(h), _ptr(tex), tex.shape[0], tex.shape[1],
+                                          tex.shape[2], v.shape[0], _ptr(rgb), _stream()), "nglod_shade_matcap")
+    return rgb.reshape(shape)
