@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define NGLOD_ABI_VERSION 2
+#define NGLOD_ABI_VERSION 3
 #define NGLOD_MAX_LODS 8
 
 /* nglod_net_t.math_mode */
@@ -65,6 +65,21 @@ typedef struct nglod_net {
     const float* b0[NGLOD_MAX_LODS];
     const float* w1[NGLOD_MAX_LODS];
     const float* b1[NGLOD_MAX_LODS];
+    /* OPTIONAL inference accelerators, read by nglod_sdf_forward / nglod_sdf_finitediff / nglod_sphere_trace only
+     * (null = not provided; training, features and backward always use grids[]).
+     * summed[i]:      the "prefix-summed" grid of LOD i, same layout and resolution as grids[i]:
+     *                   summed[i][node] = sum_{l<=i} trilinear(grids[l], position of that node)
+     *                 (nglod_build_summed_grid).  The LOD grids nest (grid_res[i] is a multiple of every coarser
+     *                 grid_res[l]), so inside any cell of grid i every coarser interpolant is one trilinear polynomial
+     *                 and trilinear interpolation reproduces it from its corner values: for EVERY x
+     *                   trilinear(summed[i], x) == sum_{l<=i} trilinear(grids[l], x)
+     *                 exactly in real arithmetic, to rounding in fp32.  The running sum of OctreeSDF.py:109-110 thus
+     *                 costs ONE 8-corner gather instead of i+1 of them.
+     * summed_fp16[i]: summed[i] as fp16 "x-pair lines" (nglod_pack_grid_fp16), used instead of summed[i] by the
+     *                 tensor-core kernels when present.  The reference's own real-time format stores corner features
+     *                 in fp16 too (SOL_NGLOD.py:73, `features.half()`). */
+    const float* summed[NGLOD_MAX_LODS];
+    const void* summed_fp16[NGLOD_MAX_LODS];
 } nglod_net_t;
 
 /* Gradient buffers shaped exactly like the parameters in nglod_net_t
@@ -117,6 +132,17 @@ int nglod_sdf_forward_all(const nglod_net_t* net, const float* x, int64_t n,
  * Only grids / grid_res / num_lods / feature_dim of `net` are read. */
 int nglod_sdf_features(const nglod_net_t* net, int32_t lod, const float* x,
                        int64_t n, float* out, void* stream);
+
+/* summed[node] = sum_{l<=lod} trilinear(grids[l], node) for every node of grid `lod` (see nglod_net_t.summed).
+ * dst: [(R+1)^3, feature_dim] fp32 channels-last, R = grid_res[lod], 16-byte aligned.  Node weights are exact
+ * rationals ((ix mod k)/k with k = R / grid_res[l]).  NGLOD_EUNSUPPORTED if the grids do not nest. */
+int nglod_build_summed_grid(const nglod_net_t* net, int32_t lod, float* dst, void* stream);
+
+/* Build the half-precision gather layout of ONE grid: for every (z, y, x0 < R) a 128-byte line holding
+ * {corner(x0) ch 0..31, corner(x0+1) ch 0..31} in fp16, so the two x-neighbours a trilinear sample needs are one
+ * aligned line (one L1 wavefront) instead of two.  grid: channels-last fp32 [(R+1)^3, 32]; dst: (R+1)^2 * R * 128
+ * bytes, 128-byte aligned. */
+int nglod_pack_grid_fp16(const float* grid, int32_t grid_res, void* dst, void* stream);
 
 /* ---- backward of sdf(x, lod) --------------------------------------------
  * Replaces: autograd of OctreeSDF.sdf driven from sdf-net/lib/trainer.py:339

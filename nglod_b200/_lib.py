@@ -38,6 +38,8 @@ class NetStruct(ctypes.Structure):
         ("b0", c_void_p * MAX_LODS),
         ("w1", c_void_p * MAX_LODS),
         ("b1", c_void_p * MAX_LODS),
+        ("summed", c_void_p * MAX_LODS),
+        ("summed_fp16", c_void_p * MAX_LODS),
     ]
 
 
@@ -94,6 +96,8 @@ SIGNATURES = {
     "nglod_sdf_forward": (ctypes.c_int, [ctypes.POINTER(NetStruct), c_int32, c_void_p, c_int64, c_void_p, c_void_p]),
     "nglod_sdf_forward_all": (ctypes.c_int, [ctypes.POINTER(NetStruct), c_void_p, c_int64, c_void_p, c_void_p]),
     "nglod_sdf_features": (ctypes.c_int, [ctypes.POINTER(NetStruct), c_int32, c_void_p, c_int64, c_void_p, c_void_p]),
+    "nglod_build_summed_grid": (ctypes.c_int, [ctypes.POINTER(NetStruct), c_int32, c_void_p, c_void_p]),
+    "nglod_pack_grid_fp16": (ctypes.c_int, [c_void_p, c_int32, c_void_p, c_void_p]),
     "nglod_sdf_backward": (ctypes.c_int, [ctypes.POINTER(NetStruct), c_int32, c_void_p, c_int64, c_void_p,
                                           ctypes.POINTER(NetGradStruct), c_void_p, c_void_p]),
     "nglod_sdf_train_step": (ctypes.c_int, [ctypes.POINTER(NetStruct), ctypes.c_uint32, c_void_p, c_void_p, c_int64,

@@ -18,6 +18,7 @@
 struct NetDev {
     int num_lods;       // number of grids to sum (= lod + 1)
     int pos_invariant;
+    int half_pairs;     // 1: grids[0] is an fp16 x-pair-line grid (nglod_pack_grid_fp16); single-LOD inference views only
     int res[NGLOD_MAX_LODS];
     const float* grids[NGLOD_MAX_LODS];
     const float* w0;    // [H, in_dim]
@@ -45,6 +46,8 @@ static inline int nglod_check_net(const nglod_net_t* net, int lod) {
         if ((reinterpret_cast<uintptr_t>(net->grids[i]) & 15u) != 0) return NGLOD_EINVAL;
     }
     if (!net->w0[lod] || !net->b0[lod] || !net->w1[lod] || !net->b1[lod]) return NGLOD_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(net->summed[lod]) & 15u) || (reinterpret_cast<uintptr_t>(net->summed_fp16[lod]) & 127u))
+        return NGLOD_EINVAL;
     return 0;
 }
 
@@ -52,6 +55,7 @@ static inline NetDev nglod_make_netdev(const nglod_net_t* net, int lod) {
     NetDev d;
     d.num_lods = lod + 1;
     d.pos_invariant = net->pos_invariant;
+    d.half_pairs = 0;
     for (int i = 0; i < NGLOD_MAX_LODS; ++i) {
         d.res[i] = i <= lod ? net->grid_res[i] : 1;
         d.grids[i] = i <= lod ? net->grids[i] : nullptr;
@@ -60,6 +64,22 @@ static inline NetDev nglod_make_netdev(const nglod_net_t* net, int lod) {
     d.b0 = net->b0[lod];
     d.w1 = net->w1[lod];
     d.b1 = net->b1[lod];
+    return d;
+}
+
+// View for the inference kernels: when the caller supplied the prefix-summed grid of this LOD (nglod_net_t.summed),
+// gather that ONE grid instead of lod+1 of them; tensor-core mode prefers its fp16 x-pair copy when present.
+static inline NetDev nglod_make_netdev_infer(const nglod_net_t* net, int lod, bool allow_half = true) {
+    NetDev d = nglod_make_netdev(net, lod);
+    if (!net->summed[lod]) return d;
+    d.num_lods = 1;
+    d.res[0] = net->grid_res[lod];
+    d.grids[0] = net->summed[lod];
+    for (int i = 1; i < NGLOD_MAX_LODS; ++i) { d.res[i] = 1; d.grids[i] = nullptr; }
+    if (allow_half && net->math_mode == NGLOD_MATH_TC3XTF32 && net->summed_fp16[lod]) {
+        d.half_pairs = 1;
+        d.grids[0] = reinterpret_cast<const float*>(net->summed_fp16[lod]);
+    }
     return d;
 }
 

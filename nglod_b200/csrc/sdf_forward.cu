@@ -1,6 +1,7 @@
 // nglod_b200 -- OctreeSDF.sdf forward, finite-difference gradient (FP32 path).
 // Reference behaviour: sdf-net/lib/models/OctreeSDF.py:94-155, sdf-net/lib/diffutils.py:61-70.
 #include "sdf_core.cuh"
+#include <cuda_fp16.h>
 #include "internal.h"
 
 namespace {
@@ -91,6 +92,76 @@ sdf_features_kernel(const NetDev net, const float* __restrict__ x, const long lo
     }
 }
 
+// fp32 channels-last grid -> fp16 x-pair lines (see nglod_pack_grid_fp16 in the header).  One thread per 16-byte chunk:
+// chunk c of line (z, y, x0) = {corner x0 ch 4c..4c+3, corner x0+1 ch 4c..4c+3}, round-to-nearest-even.
+__global__ void __launch_bounds__(256)
+pack_grid_fp16_kernel(const float* __restrict__ grid, const int R, const long long n_chunks, uint4* __restrict__ dst) {
+    const int S = R + 1;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_chunks; e += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(e & 7);
+        const long long line = e >> 3;
+        const int x0 = (int)(line % R);
+        const long long zy = line / R;                         // z * S + y
+        const float* p0 = grid + ((zy * S + x0) * NGLOD_F + 4 * c);
+        const float4 a = ldg_f4(p0), b = ldg_f4(p0 + NGLOD_F);
+        const __half2 a01 = __floats2half2_rn(a.x, a.y), a23 = __floats2half2_rn(a.z, a.w);
+        const __half2 b01 = __floats2half2_rn(b.x, b.y), b23 = __floats2half2_rn(b.z, b.w);
+        uint4 o;
+        o.x = *reinterpret_cast<const uint32_t*>(&a01); o.y = *reinterpret_cast<const uint32_t*>(&a23);
+        o.z = *reinterpret_cast<const uint32_t*>(&b01); o.w = *reinterpret_cast<const uint32_t*>(&b23);
+        dst[e] = o;
+    }
+}
+
+// summed[node, 4c..4c+3] = sum_l trilinear(grid_l, node): one thread per (node, 16-byte chunk); the node's coordinates in
+// a coarser grid are the exact rationals ix/k, so the weights (ix mod k)/k are exact for power-of-two ratios.
+struct SummedArgs {
+    int n_src;
+    int R;
+    int res[NGLOD_MAX_LODS];
+    const float* grids[NGLOD_MAX_LODS];
+};
+__device__ __forceinline__ void node_axis(int i, int k, int Rl, int& i0, float& w1, bool& has1) {
+    i0 = i / k;
+    w1 = (float)(i - i0 * k) / (float)k;
+    has1 = i0 < Rl;
+}
+__global__ void __launch_bounds__(256)
+summed_grid_kernel(const SummedArgs a, const long long n_chunks, float4* __restrict__ dst) {
+    const int S = a.R + 1;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_chunks; e += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(e & 7);
+        long long node = e >> 3;
+        const int ix = (int)(node % S); node /= S;
+        const int iy = (int)(node % S);
+        const int iz = (int)(node / S);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int l = 0; l < a.n_src; ++l) {
+            const int Rl = a.res[l], Sl = Rl + 1, k = a.R / Rl;
+            int x0, y0, z0; float wx1, wy1, wz1; bool hx, hy, hz;
+            node_axis(ix, k, Rl, x0, wx1, hx);
+            node_axis(iy, k, Rl, y0, wy1, hy);
+            node_axis(iz, k, Rl, z0, wz1, hz);
+            const float wx0 = 1.f - wx1, wy0 = 1.f - wy1, wz0 = 1.f - wz1;
+            const float* g = a.grids[l] + ((long long)((z0 * Sl + y0) * Sl + x0) * NGLOD_F + 4 * c);
+            const int dx = hx ? NGLOD_F : 0, dy = hy ? Sl * NGLOD_F : 0, dz = hz ? Sl * Sl * NGLOD_F : 0;
+            const float w00 = wx0 * wy0, w10 = wx1 * wy0, w01 = wx0 * wy1, w11 = wx1 * wy1;
+            const float w[8] = {w00 * wz0, w10 * wz0, w01 * wz0, w11 * wz0, w00 * wz1, w10 * wz1, w01 * wz1, w11 * wz1};
+            const int off[8] = {0, dx, dy, dy + dx, dz, dz + dx, dz + dy, dz + dy + dx};
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (w[q] != 0.f) {          // a zero-weight corner contributes nothing (and may be the clamped duplicate)
+                    const float4 v = ldg_f4(g + off[q]);
+                    s.x = fmaf(v.x, w[q], s.x); s.y = fmaf(v.y, w[q], s.y); s.z = fmaf(v.z, w[q], s.z); s.w = fmaf(v.w, w[q], s.w);
+                }
+            }
+            acc.x += s.x; acc.y += s.y; acc.z += s.z; acc.w += s.w;
+        }
+        dst[e] = acc;
+    }
+}
+
 int launch_grid(const void* kernel, long long n) {
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SDF_THREADS, SDF_SMEM_BYTES) != cudaSuccess || per_sm < 1)
@@ -108,11 +179,47 @@ extern "C" int nglod_sdf_forward(const nglod_net_t* net, int32_t lod, const floa
     if (int e = nglod_check_net(net, lod)) return e;
     if (n < 0 || (n > 0 && (!x || !out))) return NGLOD_EINVAL;
     if (n == 0) return 0;
-    const NetDev nd = nglod_make_netdev(net, lod);
+    const NetDev nd = nglod_make_netdev_infer(net, lod);
     if (net->math_mode == NGLOD_MATH_TC3XTF32) return nglod_launch_sdf_forward_tc(nd, x, (long long)n, out, (cudaStream_t)stream);
     NGLOD_CUDA_TRY(cudaFuncSetAttribute(sdf_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SDF_SMEM_BYTES));
     const int grid = launch_grid((const void*)sdf_forward_kernel, n);
     sdf_forward_kernel<<<grid, SDF_THREADS, SDF_SMEM_BYTES, (cudaStream_t)stream>>>(nd, x, (long long)n, out);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int nglod_build_summed_grid(const nglod_net_t* net, int32_t lod, float* dst, void* stream) {
+    if (!net || !dst || (reinterpret_cast<uintptr_t>(dst) & 15u)) return NGLOD_EINVAL;
+    if (net->num_lods < 1 || net->num_lods > NGLOD_MAX_LODS || lod < 0 || lod >= net->num_lods) return NGLOD_EINVAL;
+    if (net->feature_dim != NGLOD_F) return NGLOD_EUNSUPPORTED;
+    SummedArgs a;
+    a.n_src = lod + 1;
+    a.R = net->grid_res[lod];
+    for (int i = 0; i < NGLOD_MAX_LODS; ++i) { a.res[i] = 1; a.grids[i] = nullptr; }
+    for (int i = 0; i <= lod; ++i) {
+        if (!net->grids[i] || net->grid_res[i] < 1 || net->grid_res[i] > 256) return NGLOD_EINVAL;
+        if (reinterpret_cast<uintptr_t>(net->grids[i]) & 15u) return NGLOD_EINVAL;
+        if (a.R % net->grid_res[i] != 0) return NGLOD_EUNSUPPORTED;      // the grids must nest
+        a.res[i] = net->grid_res[i];
+        a.grids[i] = net->grids[i];
+    }
+    const long long S = a.R + 1;
+    const long long n_chunks = S * S * S * 8;
+    long long blocks = (n_chunks + 255) / 256;
+    const long long cap = (long long)nglod_sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    summed_grid_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(a, n_chunks, reinterpret_cast<float4*>(dst));
+    return (int)cudaGetLastError();
+}
+
+extern "C" int nglod_pack_grid_fp16(const float* grid, int32_t grid_res, void* dst, void* stream) {
+    if (!grid || !dst || grid_res < 1 || grid_res > 1024) return NGLOD_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(grid) & 15u) || (reinterpret_cast<uintptr_t>(dst) & 127u)) return NGLOD_EINVAL;
+    const long long S = grid_res + 1;
+    const long long n_chunks = S * S * grid_res * 8;
+    long long blocks = (n_chunks + 255) / 256;
+    const long long cap = (long long)nglod_sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    pack_grid_fp16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(grid, grid_res, n_chunks, static_cast<uint4*>(dst));
     return (int)cudaGetLastError();
 }
 
@@ -131,7 +238,7 @@ extern "C" int nglod_sdf_finitediff(const nglod_net_t* net, int32_t lod, const f
     if (n < 0 || (n > 0 && (!x || !out))) return NGLOD_EINVAL;
     if (n == 0) return 0;
     NGLOD_CUDA_TRY(cudaFuncSetAttribute(sdf_finitediff_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SDF_SMEM_BYTES));
-    const NetDev nd = nglod_make_netdev(net, lod);
+    const NetDev nd = nglod_make_netdev_infer(net, lod, /*allow_half=*/false);      // CUDA-core kernel: fp32 lines only
     const int grid = launch_grid((const void*)sdf_finitediff_kernel, n);
     sdf_finitediff_kernel<<<grid, SDF_THREADS, SDF_SMEM_BYTES, (cudaStream_t)stream>>>(nd, x, (long long)n, h, out);
     return (int)cudaGetLastError();
@@ -144,7 +251,7 @@ extern "C" int nglod_sdf_features(const nglod_net_t* net, int32_t lod, const flo
     if (n < 0 || (n > 0 && (!x || !out))) return NGLOD_EINVAL;
     if ((reinterpret_cast<uintptr_t>(out) & 15u) != 0) return NGLOD_EINVAL;
     NetDev nd;
-    nd.num_lods = lod + 1; nd.pos_invariant = 0;
+    nd.num_lods = lod + 1; nd.pos_invariant = 0; nd.half_pairs = 0;
     nd.w0 = nd.b0 = nd.w1 = nd.b1 = nullptr;
     for (int i = 0; i < NGLOD_MAX_LODS; ++i) {
         nd.res[i] = i <= lod ? net->grid_res[i] : 1;

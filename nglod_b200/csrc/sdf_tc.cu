@@ -12,6 +12,7 @@ constexpr int FWD_GROUPS = NGLOD_FWD_GROUPS;   // groups of 128 threads per CTA,
 constexpr int FWD_THREADS = FWD_GROUPS * TCG_THREADS;
 constexpr int FWD_SMEM = TC_SMEM_BYTES(FWD_GROUPS);
 
+template <bool HALF>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 sdf_forward_tc_kernel(const NetDev net, const float* __restrict__ x, const long long n, float* __restrict__ out) {
     extern __shared__ __align__(128) char smem_tc[];
@@ -24,7 +25,7 @@ sdf_forward_tc_kernel(const NetDev net, const float* __restrict__ x, const long 
         const bool active = i < n;
         float px = 0.f, py = 0.f, pz = 0.f;
         if (active) { px = __ldg(x + 3 * i); py = __ldg(x + 3 * i + 1); pz = __ldg(x + 3 * i + 2); }
-        const float d = tc_group_eval(net, g, px, py, pz, active);
+        const float d = tc_group_eval<HALF>(net, g, px, py, pz, active);
         if (active) out[i] = d;
     }
     tc_epilogue_free(tmem_base);
@@ -75,11 +76,12 @@ tc_gemm_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B
 }  // namespace
 
 int nglod_launch_sdf_forward_tc(const NetDev& nd, const float* x, long long n, float* out, cudaStream_t st) {
-    NGLOD_CUDA_TRY(cudaFuncSetAttribute(sdf_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+    auto kern = nd.half_pairs ? sdf_forward_tc_kernel<true> : sdf_forward_tc_kernel<false>;
+    NGLOD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
     long long grid = nglod_sm_count();
     const long long want = (n + FWD_THREADS - 1) / FWD_THREADS;
     if (want < grid) grid = want;
-    sdf_forward_tc_kernel<<<(int)grid, FWD_THREADS, FWD_SMEM, st>>>(nd, x, n, out);
+    kern<<<(int)grid, FWD_THREADS, FWD_SMEM, st>>>(nd, x, n, out);
     return (int)cudaGetLastError();
 }
 

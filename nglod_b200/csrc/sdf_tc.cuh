@@ -9,6 +9,7 @@
 #pragma once
 #include "common.cuh"
 #include "tc_common.cuh"
+#include <cuda_fp16.h>
 
 #define TCG_THREADS 128                 // threads per group
 #define TC_PACK_LODS 5                  // LODs whose set-up records fit the per-warp scratch at once
@@ -63,44 +64,120 @@ __device__ __forceinline__ void tc_axis(float p, int R, int& i0, float& w1, bool
     has1 = i0 < R;
 }
 
-// Sum of NL LODs' trilinear samples for channels [4c,4c+4) of the query whose set-up records are pack[l*32+q].
-template <int NL>
-__device__ __forceinline__ float4 tc_gather_one(const NetDev& net, int l0, const float4* pack, int q, int c, float4 acc) {
-    float4 P[NL];
-#pragma unroll
-    for (int l = 0; l < NL; ++l) P[l] = pack[l * 32 + q];
-#pragma unroll
-    for (int l = 0; l < NL; ++l) {
-        const uint32_t pk = __float_as_uint(P[l].x);
-        const int S = net.res[l0 + l] + 1;
-        const int o0 = (int)(pk & ~31u) + 4 * c;
-        const int dx = (pk & 1u) ? NGLOD_F : 0;
-        const int dy = (pk & 2u) ? S * NGLOD_F : 0;
-        const int dz = (pk & 4u) ? S * S * NGLOD_F : 0;
-        const float wx1 = P[l].y, wy1 = P[l].z, wz1 = P[l].w;
-        const float wx0 = 1.f - wx1, wy0 = 1.f - wy1, wz0 = 1.f - wz1;   // == (floor+1) - u exactly
-        const float* g = net.grids[l0 + l];
-        const int o2 = o0 + dy, o4 = o0 + dz, o6 = o4 + dy;
-        float4 v[8];
-        v[0] = ldg_f4(g + o0); v[1] = ldg_f4(g + o0 + dx);
-        v[2] = ldg_f4(g + o2); v[3] = ldg_f4(g + o2 + dx);
-        v[4] = ldg_f4(g + o4); v[5] = ldg_f4(g + o4 + dx);
-        v[6] = ldg_f4(g + o6); v[7] = ldg_f4(g + o6 + dx);
-        const float w00 = wx0 * wy0, w10 = wx1 * wy0, w01 = wx0 * wy1, w11 = wx1 * wy1;
-        const float w[8] = {w00 * wz0, w10 * wz0, w01 * wz0, w11 * wz0, w00 * wz1, w10 * wz1, w01 * wz1, w11 * wz1};
-        float4 s;
-        s.x = v[0].x * w[0]; s.y = v[0].y * w[0]; s.z = v[0].z * w[0]; s.w = v[0].w * w[0];
-#pragma unroll
-        for (int k = 1; k < 8; ++k) {
-            s.x = fmaf(v[k].x, w[k], s.x); s.y = fmaf(v[k].y, w[k], s.y);
-            s.z = fmaf(v[k].z, w[k], s.z); s.w = fmaf(v[k].w, w[k], s.w);
-        }
-        // running sum across LODs (OctreeSDF.py:109-110)
-        acc.x = s.x + acc.x; acc.y = s.y + acc.y; acc.z = s.z + acc.z; acc.w = s.w + acc.w;
-    }
-    return acc;
+// ---- packed fp32x2 arithmetic (sm_100a FFMA2 / FMUL2 / FADD2: two IEEE fp32 results per instruction, each lane
+//      rounded exactly like the scalar op, so results are bit-identical to the scalar code they replace)
+__device__ __forceinline__ uint64_t f2_pack(float a, float b) {
+    uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& a, float& b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+    uint64_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+    uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+// two fp16 values in one 32-bit word -> packed fp32x2 (exact)
+__device__ __forceinline__ uint64_t h2_to_f2(uint32_t h) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h));
+    return f2_pack(f.x, f.y);
 }
 
+// ------------------------------------------------------------------------------------------------ gather
+// Set-up record of one (query, LOD): {packed offset+flags, wx1, wy1, wz1} (16 bytes, written once per query by its
+// own lane in tc_setup_record, read by the 8 lanes that gather the query).
+//   fp32 grids  : offset = element offset of corner (x0,y0,z0) (multiple of 32), bits 0..2 = "+1 corner exists" per axis
+//   fp16 x-pairs: offset = line index of (z0,y0,x0) << 2, bits 0..1 = "+1 exists" for y, z (x is folded into the line)
+template <bool HALF>
+__device__ __forceinline__ float4 tc_setup_record(float px, float py, float pz, int R) {
+    const int S = R + 1;
+    int x0, y0, z0; float wx, wy, wz; bool hx, hy, hz;
+    tc_axis(px, R, x0, wx, hx);
+    tc_axis(py, R, y0, wy, hy);
+    tc_axis(pz, R, z0, wz, hz);
+    uint32_t off;
+    if constexpr (HALF) {
+        // pair lines exist for x0 < R only: at the upper face (u == R) use the last pair with weight 1 on its x1
+        // corner -- the same value (the reference multiplies that corner by 1 and reads nothing else)
+        if (!hx) { x0 = R - 1; wx = 1.f; }
+        off = ((uint32_t)((z0 * S + y0) * R + x0) << 2) | (hy ? 1u : 0u) | (hz ? 2u : 0u);
+    } else {
+        off = (uint32_t)(((z0 * S + y0) * S + x0) * NGLOD_F) | (hx ? 1u : 0u) | (hy ? 2u : 0u) | (hz ? 4u : 0u);
+    }
+    return make_float4(__uint_as_float(off), wx, wy, wz);
+}
+
+// The line loads of one (query, LOD) for channels [4c, 4c+4): 8 corner lines (fp32) or 4 x-pair lines (fp16).
+template <bool HALF> struct TcLines { uint4 v[HALF ? 4 : 8]; };
+
+template <bool HALF>
+__device__ __forceinline__ void tc_issue_lines(const float* grid, int R, uint32_t pk, int c, TcLines<HALF>& t) {
+    const int S = R + 1;
+    if constexpr (HALF) {
+        const uint4* g = reinterpret_cast<const uint4*>(grid) + ((size_t)(pk >> 2) * 8 + c);
+        const int dy = (pk & 1u) ? R * 8 : 0;
+        const int dz = (pk & 2u) ? S * R * 8 : 0;
+        t.v[0] = __ldg(g); t.v[1] = __ldg(g + dy); t.v[2] = __ldg(g + dz); t.v[3] = __ldg(g + dz + dy);
+    } else {
+        const uint4* g = reinterpret_cast<const uint4*>(grid + (pk & ~31u)) + c;
+        const int dx = (pk & 1u) ? NGLOD_F / 4 : 0;
+        const int dy = (pk & 2u) ? S * (NGLOD_F / 4) : 0;
+        const int dz = (pk & 4u) ? S * S * (NGLOD_F / 4) : 0;
+        t.v[0] = __ldg(g);           t.v[1] = __ldg(g + dx);
+        t.v[2] = __ldg(g + dy);      t.v[3] = __ldg(g + dy + dx);
+        t.v[4] = __ldg(g + dz);      t.v[5] = __ldg(g + dz + dx);
+        t.v[6] = __ldg(g + dz + dy); t.v[7] = __ldg(g + dz + dy + dx);
+    }
+}
+
+__device__ __forceinline__ uint64_t u2_as_f2(uint32_t lo, uint32_t hi) { return (uint64_t)lo | ((uint64_t)hi << 32); }
+
+// acc += trilinear sample (channels 4c..4c+3 as two packed fp32 pairs).  All arithmetic is fp32 (FFMA2 rounds each half
+// exactly like a scalar fmaf); fp16 line values are converted exactly first.
+template <bool HALF>
+__device__ __forceinline__ void tc_consume_lines(const float4 P, const TcLines<HALF>& t, uint64_t& acc01, uint64_t& acc23) {
+    const float wx1 = P.y, wy1 = P.z, wz1 = P.w;
+    const float wx0 = 1.f - wx1, wy0 = 1.f - wy1, wz0 = 1.f - wz1;   // == (floor+1) - u exactly
+    uint64_t s01, s23;
+    if constexpr (HALF) {
+        const uint64_t wx = f2_pack(wx0, wx1);
+        const float wyz[4] = {wy0 * wz0, wy1 * wz0, wy0 * wz1, wy1 * wz1};
+        float a, b;
+        f2_unpack(f2_mul(wx, f2_pack(wyz[0], wyz[0])), a, b);
+        s01 = f2_mul(h2_to_f2(t.v[0].x), f2_pack(a, a));
+        s23 = f2_mul(h2_to_f2(t.v[0].y), f2_pack(a, a));
+        s01 = f2_fma(h2_to_f2(t.v[0].z), f2_pack(b, b), s01);
+        s23 = f2_fma(h2_to_f2(t.v[0].w), f2_pack(b, b), s23);
+#pragma unroll
+        for (int k = 1; k < 4; ++k) {
+            f2_unpack(f2_mul(wx, f2_pack(wyz[k], wyz[k])), a, b);
+            s01 = f2_fma(h2_to_f2(t.v[k].x), f2_pack(a, a), s01);
+            s23 = f2_fma(h2_to_f2(t.v[k].y), f2_pack(a, a), s23);
+            s01 = f2_fma(h2_to_f2(t.v[k].z), f2_pack(b, b), s01);
+            s23 = f2_fma(h2_to_f2(t.v[k].w), f2_pack(b, b), s23);
+        }
+    } else {
+        const float w00 = wx0 * wy0, w10 = wx1 * wy0, w01 = wx0 * wy1, w11 = wx1 * wy1;
+        const float w[8] = {w00 * wz0, w10 * wz0, w01 * wz0, w11 * wz0, w00 * wz1, w10 * wz1, w01 * wz1, w11 * wz1};
+        s01 = f2_mul(u2_as_f2(t.v[0].x, t.v[0].y), f2_pack(w[0], w[0]));
+        s23 = f2_mul(u2_as_f2(t.v[0].z, t.v[0].w), f2_pack(w[0], w[0]));
+#pragma unroll
+        for (int k = 1; k < 8; ++k) {
+            s01 = f2_fma(u2_as_f2(t.v[k].x, t.v[k].y), f2_pack(w[k], w[k]), s01);
+            s23 = f2_fma(u2_as_f2(t.v[k].z, t.v[k].w), f2_pack(w[k], w[k]), s23);
+        }
+    }
+    // running sum across LODs (OctreeSDF.py:109-110)
+    acc01 = f2_add(s01, acc01);
+    acc23 = f2_add(s23, acc23);
+}
+
+// Multi-LOD gather (fp32 grids): 4 queries per round, 8 lanes per corner line; the LOD count is compile-time so the
+// loads of several LODs are in flight together.
 template <int NL>
 __device__ __forceinline__ void tc_gather_rounds(const NetDev& net, int l0, int n_live, char* a_hi, char* a_lo,
                                                  int row0, const float4* pack, const int* idx, int lane) {
@@ -110,21 +187,75 @@ __device__ __forceinline__ void tc_gather_rounds(const NetDev& net, int l0, int 
         if (slot < n_live) {
             const int q = idx[slot];
             const uint32_t row_off = tc_elem_offset(row0 + q, 4 * c);
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            uint64_t acc01 = 0ull, acc23 = 0ull;
             if (l0 > 0) {       // more than TC_PACK_LODS grids: continue the running sum (hi + lo is exact)
                 const float4 h = *reinterpret_cast<const float4*>(a_hi + row_off);
                 const float4 lo = *reinterpret_cast<const float4*>(a_lo + row_off);
-                acc = make_float4(h.x + lo.x, h.y + lo.y, h.z + lo.z, h.w + lo.w);
+                acc01 = f2_pack(h.x + lo.x, h.y + lo.y); acc23 = f2_pack(h.z + lo.z, h.w + lo.w);
             }
-            acc = tc_gather_one<NL>(net, l0, pack, q, c, acc);
+            float4 P[NL];
+            TcLines<false> t[NL];
+#pragma unroll
+            for (int l = 0; l < NL; ++l) {
+                P[l] = pack[l * 32 + q];
+                tc_issue_lines<false>(net.grids[l0 + l], net.res[l0 + l], __float_as_uint(P[l].x), c, t[l]);
+            }
+#pragma unroll
+            for (int l = 0; l < NL; ++l) tc_consume_lines<false>(P[l], t[l], acc01, acc23);
+            float4 acc;
+            f2_unpack(acc01, acc.x, acc.y); f2_unpack(acc23, acc.z, acc.w);
             tc_store_split4(a_hi, a_lo, row_off, acc);
+        }
+    }
+}
+
+// Single-grid gather (the prefix-summed grid of the requested LOD, fp32 or fp16 x-pair lines), software-pipelined:
+// a round = 4 queries x 8 lanes; DEPTH rounds of line loads are kept in flight, and round r+DEPTH is issued as soon as
+// round r has been consumed, so a warp always has loads outstanding while it interpolates and splits.
+template <bool HALF>
+__device__ __forceinline__ void tc_gather_single(const NetDev& net, int n_live, char* a_hi, char* a_lo, int row0,
+                                                 const float4* pack, const int* idx, int lane) {
+    constexpr int DEPTH = HALF ? 4 : 3;          // 64 / 96 data registers in flight
+    const int sub = lane >> 3, c = lane & 7;
+    const int n_rounds = (n_live + 3) >> 2;      // <= 8
+    const float* grid = net.grids[0];
+    const int R = net.res[0];
+    TcLines<HALF> t[DEPTH];
+    int qs[DEPTH];
+    // slots past n_live shadow slot 0's query: their loads are harmless duplicates and nothing is stored for them
+#pragma unroll
+    for (int r = 0; r < DEPTH; ++r) {
+        if (r < n_rounds) {
+            const int slot = r * 4 + sub;
+            qs[r] = slot < n_live ? idx[slot] : -1;
+            tc_issue_lines<HALF>(grid, R, __float_as_uint(pack[qs[r] < 0 ? idx[0] : qs[r]].x), c, t[r]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        if (r < n_rounds) {                      // warp-uniform
+            const int b = r % DEPTH;
+            const int q = qs[b];
+            uint64_t acc01 = 0ull, acc23 = 0ull;
+            tc_consume_lines<HALF>(pack[q < 0 ? idx[0] : q], t[b], acc01, acc23);
+            if (r + DEPTH < n_rounds) {
+                const int slot = (r + DEPTH) * 4 + sub;
+                qs[b] = slot < n_live ? idx[slot] : -1;
+                tc_issue_lines<HALF>(grid, R, __float_as_uint(pack[qs[b] < 0 ? idx[0] : qs[b]].x), c, t[b]);
+            }
+            if (q >= 0) {
+                float4 acc;
+                f2_unpack(acc01, acc.x, acc.y); f2_unpack(acc23, acc.z, acc.w);
+                tc_store_split4(a_hi, a_lo, tc_elem_offset(row0 + q, 4 * c), acc);
+            }
         }
     }
 }
 
 // Gather for the warp's 32 queries into rows [row0, row0+32) of the group's A operand.
 //   px,py,pz / active : this lane's query;   pack/idx : this warp's scratch.
-// Every lane of the warp must call (convergent).
+// Every lane of the warp must call (convergent).  HALF kernels only ever see single-grid (summed) views.
+template <bool HALF>
 __device__ __forceinline__ void tc_gather_rows(const NetDev& net, float px, float py, float pz, bool active,
                                                char* a_hi, char* a_lo, int row0, float4* pack, int* idx, int lane) {
     const unsigned live = __ballot_sync(0xffffffffu, active);
@@ -135,31 +266,30 @@ __device__ __forceinline__ void tc_gather_rows(const NetDev& net, float px, floa
         // K chunk 8 = {x, y, z, 1}: the query's own lane writes it (no shuffles needed later)
         tc_store_split4(a_hi, a_lo, tc_elem_offset(row0 + lane, NGLOD_F), make_float4(px, py, pz, 1.f));
     }
-    for (int l0 = 0; l0 < net.num_lods; l0 += TC_PACK_LODS) {
-        const int nl = min(TC_PACK_LODS, net.num_lods - l0);
-        // ---- phase 1: per-LOD set-up, once per query (not once per lane of the query)
-        if (active) {
-            for (int l = 0; l < nl; ++l) {
-                const int R = net.res[l0 + l], S = R + 1;
-                int x0, y0, z0; float wx, wy, wz; bool hx, hy, hz;
-                tc_axis(px, R, x0, wx, hx);
-                tc_axis(py, R, y0, wy, hy);
-                tc_axis(pz, R, z0, wz, hz);
-                const uint32_t off = (uint32_t)(((z0 * S + y0) * S + x0) * NGLOD_F) | (hx ? 1u : 0u) | (hy ? 2u : 0u) | (hz ? 4u : 0u);
-                pack[l * 32 + lane] = make_float4(__uint_as_float(off), wx, wy, wz);
+    if (HALF || net.num_lods == 1) {
+        if (active) pack[lane] = tc_setup_record<HALF>(px, py, pz, net.res[0]);
+        __syncwarp();
+        tc_gather_single<HALF>(net, n_live, a_hi, a_lo, row0, pack, idx, lane);
+        __syncwarp();
+        return;
+    }
+    if constexpr (!HALF) {
+        for (int l0 = 0; l0 < net.num_lods; l0 += TC_PACK_LODS) {
+            const int nl = min(TC_PACK_LODS, net.num_lods - l0);
+            // ---- phase 1: per-LOD set-up, once per query (not once per lane of the query)
+            if (active)
+                for (int l = 0; l < nl; ++l) pack[l * 32 + lane] = tc_setup_record<false>(px, py, pz, net.res[l0 + l]);
+            __syncwarp();
+            // ---- phase 2
+            switch (nl) {
+                case 1: tc_gather_rounds<1>(net, l0, n_live, a_hi, a_lo, row0, pack, idx, lane); break;
+                case 2: tc_gather_rounds<2>(net, l0, n_live, a_hi, a_lo, row0, pack, idx, lane); break;
+                case 3: tc_gather_rounds<3>(net, l0, n_live, a_hi, a_lo, row0, pack, idx, lane); break;
+                case 4: tc_gather_rounds<4>(net, l0, n_live, a_hi, a_lo, row0, pack, idx, lane); break;
+                default: tc_gather_rounds<5>(net, l0, n_live, a_hi, a_lo, row0, pack, idx, lane); break;
             }
+            __syncwarp();
         }
-        __syncwarp();
-        // ---- phase 2: 4 queries per round, 8 lanes per corner line (LOD count compile-time so the loads of
-        //      several LODs can be in flight together)
-        switch (nl) {
-            case 1: tc_gather_rounds<1>(net, l0, n_live, a_hi, a_lo, row0, pack, idx, lane); break;
-            case 2: tc_gather_rounds<2>(net, l0, n_live, a_hi, a_lo, row0, pack, idx, lane); break;
-            case 3: tc_gather_rounds<3>(net, l0, n_live, a_hi, a_lo, row0, pack, idx, lane); break;
-            case 4: tc_gather_rounds<4>(net, l0, n_live, a_hi, a_lo, row0, pack, idx, lane); break;
-            default: tc_gather_rounds<5>(net, l0, n_live, a_hi, a_lo, row0, pack, idx, lane); break;
-        }
-        __syncwarp();
     }
 }
 
@@ -195,8 +325,9 @@ struct TcGroup {
     uint32_t parity;
 };
 
+template <bool HALF = false>
 __device__ __forceinline__ float tc_group_eval(const NetDev& net, TcGroup& g, float px, float py, float pz, bool active) {
-    tc_gather_rows(net, px, py, pz, active, g.a_hi, g.a_lo, g.wq * 32, g.pack, g.idx, g.lane);
+    tc_gather_rows<HALF>(net, px, py, pz, active, g.a_hi, g.a_lo, g.wq * 32, g.pack, g.idx, g.lane);
     fence_proxy_async_smem();                     // generic-proxy smem writes -> visible to the tensor core
     tc_fence_before_sync();                       // order the previous tile's TMEM loads before the next MMA
     named_bar_sync(g.bar_id, TCG_THREADS);

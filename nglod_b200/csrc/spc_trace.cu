@@ -347,7 +347,7 @@ int make_sparse_dev(const nglod_sparse_net_t* net, int lod, SparseDev& sn) {
         (reinterpret_cast<uintptr_t>(net->voxels) & 7u)) return NGLOD_EINVAL;
     if (!net->w0[lod] || !net->b0[lod] || !net->w1[lod] || !net->b1[lod]) return NGLOD_EINVAL;
     if (net->base_lod < 0 || net->base_lod + lod > 14) return NGLOD_EINVAL;
-    sn.dec.num_lods = 0; sn.dec.pos_invariant = 0;
+    sn.dec.num_lods = 0; sn.dec.pos_invariant = 0; sn.dec.half_pairs = 0;
     for (int i = 0; i < NGLOD_MAX_LODS; ++i) { sn.dec.res[i] = 1; sn.dec.grids[i] = nullptr; }
     sn.dec.w0 = net->w0[lod]; sn.dec.b0 = net->b0[lod]; sn.dec.w1 = net->w1[lod]; sn.dec.b1 = net->b1[lod];
     sn.cf = net->corner_feats; sn.trinkets = net->trinkets; sn.parents = net->parents;

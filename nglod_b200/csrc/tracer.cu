@@ -44,7 +44,8 @@ constexpr int TRACE_TC_SMEM = TC_SMEM_BYTES(TRACE_TC_GROUPS);
 
 // TC = false: FP32 CUDA-core decoder, warps are independent (8 per CTA, 2 CTAs/SM).
 // TC = true : tcgen05 decoder; 4 warps form a 128-row MMA tile and advance in lock-step rounds (3 groups per CTA).
-template <bool TC>
+// HALF (TC only): gather from the fp16 x-pair copy of the grids (nglod_pack_grid_fp16).
+template <bool TC, bool HALF>
 __global__ void __launch_bounds__(TC ? TRACE_TC_THREADS : SDF_THREADS, TC ? 1 : 2)
 sphere_trace_kernel(const NetDev net, const float* __restrict__ ray_o, const float* __restrict__ ray_d,
                     const long long n, const TraceParams tp, float* __restrict__ out_x,
@@ -153,7 +154,7 @@ sphere_trace_kernel(const NetDev net, const float* __restrict__ ray_o, const flo
             if (axis == 0) qx = x + e; else if (axis == 1) qy = y + e; else qz = z + e;
         }
         float dv;
-        if constexpr (TC) dv = tc_group_eval(net, grp, qx, qy, qz, occupied);
+        if constexpr (TC) dv = tc_group_eval<HALF>(net, grp, qx, qy, qz, occupied);
         else dv = warp_sdf_eval(net, smem, tile, idx, qx, qy, qz, occupied, lane);
         const unsigned march_mask = __ballot_sync(0xffffffffu, phase == PH_MARCH);
         if (lane == 0) {
@@ -217,9 +218,10 @@ extern "C" int nglod_sphere_trace(const nglod_net_t* net, int32_t lod, const flo
     tp.far = (float)opts->far;
     tp.h = (float)opts->normal_h;
     tp.two_h = (float)(opts->normal_h * 2.0);
-    const NetDev nd = nglod_make_netdev(net, lod);
+    const NetDev nd = nglod_make_netdev_infer(net, lod);
     if (net->math_mode == NGLOD_MATH_TC3XTF32) {
-        auto kern = sphere_trace_kernel<true>;
+        const bool half = nd.half_pairs != 0;
+        auto kern = half ? sphere_trace_kernel<true, true> : sphere_trace_kernel<true, false>;
         NGLOD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TRACE_TC_SMEM));
         long long grid = nglod_sm_count();
         const long long want = (n + TRACE_TC_THREADS - 1) / TRACE_TC_THREADS;
@@ -228,7 +230,7 @@ extern "C" int nglod_sphere_trace(const nglod_net_t* net, int32_t lod, const flo
                                                                  normal, queue, stats);
         return (int)cudaGetLastError();
     }
-    auto kern = sphere_trace_kernel<false>;
+    auto kern = sphere_trace_kernel<false, false>;
     NGLOD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SDF_SMEM_BYTES));
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SDF_THREADS, SDF_SMEM_BYTES) != cudaSuccess || per_sm < 1)

@@ -46,7 +46,7 @@ class _SdfFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, module, lod, *params):
-        view = module.net_view()
+        view = module.net_view(inference=False)
         ctx.module, ctx.lod = module, lod
         ctx.save_for_backward(x)
         return ops.sdf_forward(view, lod, x)
@@ -56,7 +56,7 @@ class _SdfFunction(torch.autograd.Function):
     def backward(ctx, grad_out):
         (x,) = ctx.saved_tensors
         module, lod = ctx.module, ctx.lod
-        view = module.net_view()
+        view = module.net_view(inference=False)
         needs = ctx.needs_input_grad
         n_grids = lod + 1
         grid_grads = [torch.zeros_like(module.features[i].fm, memory_format=torch.preserve_format)
@@ -81,6 +81,20 @@ class OctreeSDF(BaseLOD):
         self.interpolate = self.args.interpolate
         # how the 35->128 contraction runs: "tc" = tcgen05 3xTF32 (|err| ~1e-6), "fp32" = CUDA cores (|err| ~1e-7)
         self.math_mode = getattr(args, "math_mode", None) or "tc"
+        # How the inference kernels (no-grad sdf(), finite-difference normals, the tracers) read the grids.
+        #   sum_lods     True: they gather ONE grid -- the prefix sum of LODs 0..lod resampled at LOD lod's nodes.  The
+        #                LOD grids nest, so this is the same function as the reference's running sum of per-LOD samples
+        #                (OctreeSDF.py:109-110) exactly in real arithmetic, to fp32 rounding (~1e-8) in practice.
+        #                False: gather every LOD (what training / autograd always does).
+        #   grid_storage "fp32": summed grids in fp32;  "fp16": also as packed half-precision "x-pair lines" for the
+        #                tensor-core kernels (half the gather traffic; equals the fp32 kernels run on the fp16-rounded
+        #                summed grid; the reference's real-time export stores features as fp16 too, SOL_NGLOD.py:73).
+        # The derived copies are rebuilt whenever a grid changes (torch version counters; mark_grids_dirty() after
+        # writes that bypass them).
+        self.sum_lods = getattr(args, "sum_lods", None)
+        self.sum_lods = True if self.sum_lods is None else bool(self.sum_lods)
+        self.grid_storage = getattr(args, "grid_storage", None) or "fp32"
+        self._derived = None            # (key, summed list, half list)
 
         self.sdf_input_dim = self.fdim + (0 if self.pos_invariant else self.input_dim)
         self.num_decoder = 1 if args.joint_decoder else self.args.num_lods
@@ -94,12 +108,51 @@ class OctreeSDF(BaseLOD):
         seq = self.louts[0 if self.num_decoder == 1 else lod]
         return (seq[0].weight, seq[0].bias, seq[2].weight, seq[2].bias)
 
-    def net_view(self):
+    def _grids_nest(self):
+        res = [f.fsize for f in self.features]
+        return all(res[i] % res[j] == 0 for i in range(len(res)) for j in range(i))
+
+    def mark_grids_dirty(self):
+        """Call after writing the grids behind torch's back (`.data` / raw pointers, e.g. the fused Adam kernel)."""
+        self._derived = None
+
+    def _derived_grids(self):
+        """(summed, summed_half) for the inference kernels, rebuilt when a grid was written or moved."""
+        want_half = self.grid_storage == "fp16" and self.math_mode == "tc"
+        key = ([(f.fm._version, f.fm.data_ptr()) for f in self.features], want_half)
+        if self._derived is None or self._derived[0] != key:
+            grids = [f.fm.data for f in self.features]
+            base = ops.NetView.grids_only(grids)
+            old = self._derived[1] if self._derived is not None else [None] * len(grids)
+            summed = [ops.build_summed_grid(base, i, out=o if (o is not None and o.device == g.device) else None)
+                      for i, (g, o) in enumerate(zip(grids, old))]
+            half = [ops.pack_grid_fp16(sg) for sg in summed] if want_half else None
+            self._derived = (key, summed, half)
+        return self._derived[1], self._derived[2]
+
+    def summed_state_dict(self, lod=None):
+        """state_dict of the function the inference kernels evaluate for sdf(x, lod), in the reference's own format:
+        every `features.i.fm` zero except `features.{lod}.fm`, which holds the prefix-summed grid (rounded through fp16
+        when grid_storage == 'fp16').  A reference OctreeSDF loaded with it returns this model's sdf(x, lod)."""
+        lod = self.num_lods - 1 if lod is None else lod
+        summed, _ = self._derived_grids()
+        sd = {k: v.detach().clone() for k, v in self.state_dict().items()}
+        for i in range(self.num_lods):
+            sd[f"features.{i}.fm"] = torch.zeros_like(sd[f"features.{i}.fm"])
+        top = summed[lod].detach().clone()
+        sd[f"features.{lod}.fm"] = top.half().float() if self.grid_storage == "fp16" else top
+        return sd
+
+    def net_view(self, inference=True):
         """Borrow the current parameters as an nglod_net_t (rebuilt per call: pointers may move)."""
         grids = [f.fm.data for f in self.features]
         decs = [tuple(p.data for p in self.decoder_params(i)) for i in range(self.num_lods)]
+        summed = half = None
+        if inference and self.sum_lods and self._grids_nest():
+            summed, half = self._derived_grids()
         return ops.NetView(grids, decs, pos_invariant=self.pos_invariant,
-                           math_mode=_lib.MATH_TC3XTF32 if self.math_mode == "tc" else _lib.MATH_FP32)
+                           math_mode=_lib.MATH_TC3XTF32 if self.math_mode == "tc" else _lib.MATH_FP32,
+                           summed=summed, summed_half=half)
 
     def _eval_lod(self, x, lod):
         shape = x.shape

@@ -35,6 +35,10 @@ _FLAGS = [
     ("net", "--freeze", dict(type=int, default=-1)),
     ("net", "--pos-invariant", _S),
     ("net", "--joint-decoder", _S),
+    # not in the reference: kernel knobs of this implementation (defaults keep the reference's numerics)
+    ("net", "--math-mode", dict(type=str, default=None, choices=["tc", "fp32"])),
+    ("net", "--grid-storage", dict(type=str, default=None, choices=["fp32", "fp16"])),
+    ("net", "--no-sum-lods", dict(dest="sum_lods", action="store_false", default=None)),
     ("net", "--feat-sum", _S),
     # -------- dataset
     ("dataset", "--dataset-path", dict(type=str)),

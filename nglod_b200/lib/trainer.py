@@ -66,7 +66,7 @@ class FusedTrainer:
         self.flat_grad.zero_()
         self.lod_loss.zero_()
         grid_grads, dec_grads = self._grad_lists()
-        view = net.net_view()
+        view = net.net_view(inference=False)
         for l in lods:          # one fused forward+loss+backward launch per LOD head, each with its own loss cell
             ops.sdf_train_step(view, 1 << l, pts, gts, 1.0 / batch, grid_grads, dec_grads, self.lod_loss[l:l + 1])
         torch.sum(self.lod_loss, dim=0, keepdim=True, out=self.loss)
@@ -74,6 +74,7 @@ class FusedTrainer:
         self.step_count += 1
         ops.adam_step(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count, lr=self.lr,
                       beta1=self.betas[0], beta2=self.betas[1], eps=self.eps)
+        net.mark_grids_dirty()      # the Adam kernel writes the parameters behind torch's version counters
         return self.loss
 
 

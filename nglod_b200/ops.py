@@ -39,9 +39,10 @@ class NetView:
     Keeps the tensors alive for as long as the view is.
     """
 
-    def __init__(self, grids, decoders, pos_invariant=False, math_mode=0):
+    def __init__(self, grids, decoders, pos_invariant=False, math_mode=0, summed=None, summed_half=None):
         self.grids = grids
         self.decoders = decoders
+        self.summed, self.summed_half = summed, summed_half      # optional inference accelerators (kept alive here)
         n = len(grids)
         if n < 1 or n > MAX_LODS:
             raise RuntimeError(f"num_lods must be in [1, {MAX_LODS}]")
@@ -64,6 +65,22 @@ class NetView:
                 if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
                     raise RuntimeError("decoder parameters must be contiguous fp32 CUDA tensors")
             s.w0[i], s.b0[i], s.w1[i], s.b1[i] = w0.data_ptr(), b0.data_ptr(), w1.data_ptr(), b1.data_ptr()
+        for i, sg in enumerate(summed or []):
+            if sg is None:
+                continue
+            if sg.dtype != torch.float32 or not sg.is_cuda or sg.shape != grids[i].shape or \
+                    not sg.is_contiguous(memory_format=torch.channels_last_3d):
+                raise RuntimeError("summed[i] must look like grids[i] (fp32, channels_last_3d) -- see build_summed_grid")
+            s.summed[i] = sg.data_ptr()
+        for i, h in enumerate(summed_half or []):
+            if h is None:
+                continue
+            R = grids[i].shape[-1] - 1
+            if h.dtype != torch.uint8 or not h.is_cuda or h.numel() != (R + 1) * (R + 1) * R * 128 or h.data_ptr() % 128:
+                raise RuntimeError("summed_half[i] must be the 128-byte aligned uint8 buffer pack_grid_fp16 produced")
+            if not summed or summed[i] is None:
+                raise RuntimeError("summed_half[i] needs summed[i] (the CUDA-core kernels read the fp32 copy)")
+            s.summed_fp16[i] = h.data_ptr()
         self.struct = s
         self.device = grids[0].device
 
@@ -123,6 +140,34 @@ def sdf_forward(view, lod, x):
     with torch.cuda.device(x.device):
         _lib.check(lib.nglod_sdf_forward(ctypes.byref(view.struct), lod, _ptr(x), n, _ptr(out), _stream()),
                    "nglod_sdf_forward")
+    return out
+
+
+def build_summed_grid(view, lod, out=None):
+    """Prefix-summed grid of LOD `lod` (nglod_net_t.summed, nglod_build_summed_grid): a tensor shaped and laid out like
+    view.grids[lod] whose single trilinear sample equals the sum of the samples of grids 0..lod."""
+    lib = _lib.load()
+    g = view.grids[lod]
+    if out is None:
+        out = torch.empty_like(g, memory_format=torch.preserve_format)
+    with torch.cuda.device(g.device):
+        _lib.check(lib.nglod_build_summed_grid(ctypes.byref(view.struct), lod, _ptr(out), _stream()),
+                   "nglod_build_summed_grid")
+    return out
+
+
+def pack_grid_fp16(fm, out=None):
+    """fp16 "x-pair line" copy of one feature grid for the inference kernels (include/nglod_b200.h,
+    nglod_pack_grid_fp16): [1,F,S,S,S] channels_last_3d fp32 -> uint8 [S*S*(S-1)*128]."""
+    lib = _lib.load()
+    if not fm.is_cuda or fm.dtype != torch.float32 or not fm.is_contiguous(memory_format=torch.channels_last_3d):
+        raise RuntimeError("feature grids must be fp32 CUDA tensors in channels_last_3d memory format")
+    S = fm.shape[-1]
+    nbytes = S * S * (S - 1) * 128
+    if out is None:
+        out = torch.empty(nbytes, device=fm.device, dtype=torch.uint8)   # torch's allocator aligns to 512 B
+    with torch.cuda.device(fm.device):
+        _lib.check(lib.nglod_pack_grid_fp16(_ptr(fm), S - 1, _ptr(out), _stream()), "nglod_pack_grid_fp16")
     return out
 
 

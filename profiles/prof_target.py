@@ -16,6 +16,7 @@ from nglod_b200.lib.tracer import SphereTracer  # noqa: E402
 bench.FIT_STEPS = int(os.environ.get("PROF_FIT_STEPS", "150"))
 dev = torch.device("cuda", 0)
 net, args = bench.build_and_fit(dev, lambda m: print(m, file=sys.stderr))
+net.grid_storage = os.environ.get("PROF_STORAGE", "fp32")      # "fp16": the x-pair-line inference path
 view = net.net_view()
 ray_o, ray_d = bench.make_rays(dev)
 tracer = SphereTracer(args)

@@ -430,3 +430,124 @@ def test_sdf_forward_tensor_core_vs_golden(rand5, fit3):
             net3.math_mode = "fp32"
             b = net3.sdf(xx, lod=2)
             assert (a - b).abs().max() < 5e-6
+
+
+# ------------------------------------------------------------------------------------------------ fp16 grid storage
+def test_pack_grid_fp16_layout_bit_exact():
+    """nglod_pack_grid_fp16: line (z,y,x0), chunk c = {x0 ch 4c..4c+3, x1 ch 4c..4c+3}, round-to-nearest-even."""
+    from nglod_b200 import ops
+    for R in (1, 4, 7, 16):
+        S = R + 1
+        g = torch.Generator().manual_seed(R)
+        fm = (torch.randn(1, 32, S, S, S, generator=g) * 0.01).to(DEV).contiguous(memory_format=torch.channels_last_3d)
+        got = ops.pack_grid_fp16(fm).cpu().view(torch.float16).reshape(S, S, R, 8, 2, 4)
+        cl = fm[0].permute(1, 2, 3, 0).cpu()                                  # [z, y, x, 32]
+        a = cl[:, :, :-1].half().reshape(S, S, R, 8, 4)
+        b = cl[:, :, 1:].half().reshape(S, S, R, 8, 4)
+        assert torch.equal(got[..., 0, :], a) and torch.equal(got[..., 1, :], b)
+
+
+def test_summed_grid_identity(rand5):
+    """The prefix-summed grid: (1) its nodes hold sum_l trilinear(grid_l, node) (vs the oracle's grid_sample at the node
+    positions), (2) ONE trilinear sample of it equals the reference's running sum of per-LOD samples at arbitrary x,
+    including clamped points outside the box, (3) grids that do not nest are refused."""
+    from nglod_b200 import ops
+    net, _ = rand5_model(DEV)
+    onet = O.OracleNet(net.state_dict())
+    grids = [f.fm.data for f in net.features]
+    view = ops.NetView.grids_only(grids)
+    g = torch.Generator().manual_seed(11)
+    x = torch.cat([torch.rand(20000, 3, generator=g) * 2.4 - 1.2, torch.tensor([[1.0, 1.0, 1.0], [-1.0, 0.5, 1.0]])])
+    for lod in (0, 2, 4):
+        sg = ops.build_summed_grid(view, lod)
+        S = grids[lod].shape[-1]
+        lin = torch.arange(S, dtype=torch.float32) * (2.0 / (S - 1)) - 1.0
+        zz, yy, xx = torch.meshgrid(lin, lin, lin, indexing="ij")
+        nodes = torch.stack([xx, yy, zz], dim=-1).reshape(-1, 3)
+        want = sum(onet.sample(i, nodes) for i in range(lod + 1))                      # [S^3, 32], z-major like the grid
+        got = sg[0].permute(1, 2, 3, 0).reshape(-1, 32).cpu()
+        assert (got - want).abs().max() < 2e-8
+        ref = sum(onet.sample(i, x) for i in range(lod + 1))
+        one = ops.sdf_features(ops.NetView.grids_only([sg]), 0, x.to(DEV)).cpu()
+        err = (one - ref).abs().max().item()
+        print(f"summed grid lod{lod}: node err {(got - want).abs().max():.1e}; sample-vs-running-sum err {err:.1e}")
+        assert err < 3e-8
+    odd = [torch.zeros(1, 32, r + 1, r + 1, r + 1, device=DEV).contiguous(memory_format=torch.channels_last_3d) for r in (4, 6)]
+    with pytest.raises(RuntimeError):
+        ops.build_summed_grid(ops.NetView.grids_only(odd), 1)
+
+
+@pytest.mark.parametrize("math_mode", ["fp32", "tc"])
+def test_sdf_forward_without_lod_summing(rand5, math_mode):
+    """sum_lods=False keeps the per-LOD gather (what training uses): same golden tolerances."""
+    net, _ = rand5_model(DEV)
+    net.math_mode, net.sum_lods = math_mode, False
+    assert net.net_view().summed is None
+    x = torch.from_numpy(rand5["x"]).to(DEV)
+    with torch.no_grad():
+        for l in range(5):
+            assert np.abs(net.sdf(x, lod=l).cpu().numpy() - rand5[f"sdf_lod{l}"]).max() < 5e-6
+
+
+def test_sdf_forward_fp16_storage(rand5, fit3):
+    """grid_storage='fp16': (1) equals the oracle run on the model's own `summed_state_dict()` (the fp16-rounded summed
+    grid in the reference's format; fp32 arithmetic), (2) stays within BASELINE's 1e-4 of the reference on the unrounded
+    weights, (3) the derived grids are rebuilt when a grid changes."""
+    for maker, gold, nl in ((lambda: rand5_model(DEV), rand5, 5), (lambda: fit3_model(fit3, DEV), fit3, 3)):
+        net, _ = maker()
+        net.math_mode, net.grid_storage = "tc", "fp16"
+        assert net.net_view().summed_half is not None
+        x = torch.from_numpy(gold["x"])
+        edge = torch.tensor([[1.0, 1.0, 1.0], [-1.0, -1.0, -1.0], [1.0, -0.3, 0.2], [0.1, 1.0, -1.0], [1.5, 0.0, -2.0]])
+        xx = torch.cat([x, edge])
+        with torch.no_grad():
+            for l in range(nl):
+                d = net.sdf(xx.to(DEV), lod=l).cpu()
+                err_q = (d - O.OracleNet(net.summed_state_dict(l)).sdf(xx, lod=l)).abs().max().item()
+                err_ref = np.abs(d[:x.shape[0]].numpy() - gold[f"sdf_lod{l}"]).max()
+                print(f"fp16 storage lod{l}: vs oracle(summed, fp16-rounded) {err_q:.2e}; vs reference(fp32 weights) {err_ref:.2e}")
+                assert err_q < 5e-6
+                assert err_ref < 1e-4
+            # staleness: an in-place update of the Parameter is seen through torch's version counter; writes behind
+            # it (.data / raw pointers, e.g. the fused Adam kernel) need mark_grids_dirty()
+            before = net.sdf(x.to(DEV), lod=nl - 1)
+            net.features[nl - 1].fm.mul_(2.0)
+            after = net.sdf(x.to(DEV), lod=nl - 1)
+            ref2 = O.OracleNet(net.summed_state_dict()).sdf(x, lod=nl - 1)
+            assert (after.cpu() - ref2).abs().max() < 5e-6 and (after - before).abs().max() > 1e-5
+            net.features[0].fm.data.mul_(0.5)
+            net.mark_grids_dirty()
+            ref3 = O.OracleNet(net.summed_state_dict()).sdf(x, lod=nl - 1)
+            assert (net.sdf(x.to(DEV), lod=nl - 1).cpu() - ref3).abs().max() < 5e-6
+            # and the default fp32 storage follows the same updates, against the oracle on the ORIGINAL parameters
+            net.grid_storage = "fp32"
+            assert (net.sdf(x.to(DEV), lod=nl - 1).cpu() - O.OracleNet(net.state_dict()).sdf(x, lod=nl - 1)).abs().max() < 5e-6
+
+
+def test_sphere_tracer_fp16_storage_vs_oracle_on_quantized_grids(rand5, fit3):
+    from nglod_b200.lib.tracer import SphereTracer
+    net3, args3 = fit3_model(fit3, DEV)
+    net3.math_mode, net3.grid_storage, net3.lod = "tc", "fp16", 2
+    o, d = torch.from_numpy(fit3["t1_ray_o"]), torch.from_numpy(fit3["t1_ray_d"])
+    rb = SphereTracer(args3)(net3, o.to(DEV), d.to(DEV))
+    onet = O.OracleNet(net3.summed_state_dict(2))
+    onet.lod = 2
+    res = O.sphere_trace(onet, o, d)
+    hit = res["hit"].numpy()
+    got = rb.hit.cpu().numpy()
+    mism = int((got != hit).sum())
+    conv = (onet(res["x"]).abs() < 0.0003)[:, 0].numpy() & hit & got
+    dd = (rb.depth.cpu() - res["depth"]).abs()[:, 0].numpy()
+    nn = (rb.normal.cpu() - res["normal"]).abs().max(dim=1)[0].numpy()
+    print(f"fp16 tracer vs oracle(quantized): {int(hit.sum())} hits, {mism} mask mismatches, {int(conv.sum())} converged, "
+          f"depth max {dd[conv].max():.2e}, normal max {nn[conv].max():.2e} (>1e-3: {int((nn[conv] > 1e-3).sum())})")
+    assert mism <= 1
+    assert dd[conv].max() < 2e-4
+    assert (nn[conv] > 1e-3).mean() < 0.005
+    # and against the reference on the UNROUNDED weights (golden): BASELINE tolerances on converged hits
+    gh = fit3["t1_hit"]
+    both = fit3["t1_converged"] & got & gh
+    dg = np.abs(rb.depth.cpu().numpy() - fit3["t1_depth"])[:, 0]
+    ng = np.abs(rb.normal.cpu().numpy() - fit3["t1_normal"]).max(axis=1)
+    print(f"fp16 tracer vs reference(fp32 weights): mask mismatches {int((got != gh).sum())}, depth max {dg[both].max():.2e}, "
+          f"normal max {ng[both].max():.2e} (>1e-3: {int((ng[both] > 1e-3).sum())} of {int(both.sum())})")
