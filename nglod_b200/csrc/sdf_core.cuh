@@ -39,17 +39,25 @@
 // Stage one decoder head into shared memory (all threads of the CTA).
 __device__ __forceinline__ void sdf_stage_weights(const NetDev& net, float* smem) {
     const int in_dim = net.pos_invariant ? NGLOD_F : NGLOD_F + 3;
-    for (int e = threadIdx.x; e < SDF_W0_FLOATS; e += blockDim.x) {
-        const int j = e / NGLOD_KPAD, k = e - j * NGLOD_KPAD;
-        float v;
-        if (k < NGLOD_F) {
-            v = __ldg(net.w0 + j * in_dim + (net.pos_invariant ? k : k + 3));
-        } else if (k < NGLOD_F + 3) {
-            v = net.pos_invariant ? 0.f : __ldg(net.w0 + j * in_dim + (k - NGLOD_F));
-        } else {
-            v = __ldg(net.b0 + j);
+    // batches of 6 independent loads, then 6 stores: with a cold L2 a load-store loop pays the DRAM latency per iteration
+    for (int base = 0; base < SDF_W0_FLOATS; base += 6 * blockDim.x) {
+        float v[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const int e = base + threadIdx.x + i * blockDim.x;
+            const int j = e / NGLOD_KPAD, k = e - j * NGLOD_KPAD;
+            v[i] = 0.f;
+            if (e < SDF_W0_FLOATS) {
+                if (k < NGLOD_F) v[i] = __ldg(net.w0 + j * in_dim + (net.pos_invariant ? k : k + 3));
+                else if (k < NGLOD_F + 3) v[i] = net.pos_invariant ? 0.f : __ldg(net.w0 + j * in_dim + (k - NGLOD_F));
+                else v[i] = __ldg(net.b0 + j);
+            }
         }
-        smem[e] = v;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const int e = base + threadIdx.x + i * blockDim.x;
+            if (e < SDF_W0_FLOATS) smem[e] = v[i];
+        }
     }
     for (int e = threadIdx.x; e < NGLOD_H; e += blockDim.x) smem[SDF_SMEM_W1_OFF + e] = __ldg(net.w1 + e);
     if (threadIdx.x == 0) smem[SDF_SMEM_B1_OFF] = __ldg(net.b1);

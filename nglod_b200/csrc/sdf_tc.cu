@@ -6,29 +6,51 @@
 namespace {
 
 #ifndef NGLOD_FWD_GROUPS
-#define NGLOD_FWD_GROUPS 3
+#define NGLOD_FWD_GROUPS 3          // multi-LOD gather: groups of 128 threads per CTA, one CTA per SM
 #endif
-constexpr int FWD_GROUPS = NGLOD_FWD_GROUPS;   // groups of 128 threads per CTA, one CTA per SM
-constexpr int FWD_THREADS = FWD_GROUPS * TCG_THREADS;
-constexpr int FWD_SMEM = TC_SMEM_BYTES(FWD_GROUPS);
+#ifndef NGLOD_FWD_GROUPS_SINGLE
+#define NGLOD_FWD_GROUPS_SINGLE 4   // single-grid gather: no scratch, <=128 registers -> 16 warps, all 512 TMEM columns
+#endif
+constexpr int fwd_groups(int mode) { return mode == TC_MULTI ? NGLOD_FWD_GROUPS : NGLOD_FWD_GROUPS_SINGLE; }
+constexpr int fwd_smem(int mode) { return TC_SMEM_BYTES_W(fwd_groups(mode), tc_mode_scratch(mode)); }
 
-template <bool HALF>
-__global__ void __launch_bounds__(FWD_THREADS, 1)
+template <int MODE>
+__global__ void __launch_bounds__(fwd_groups(MODE) * TCG_THREADS, 1)
 sdf_forward_tc_kernel(const NetDev net, const float* __restrict__ x, const long long n, float* __restrict__ out) {
     extern __shared__ __align__(128) char smem_tc[];
-    const uint32_t tmem_base = tc_prologue(net, smem_tc, FWD_GROUPS);
-    TcGroup g = tc_make_group(smem_tc, FWD_GROUPS, tmem_base);
-    const long long ggroup = (long long)blockIdx.x * FWD_GROUPS + (threadIdx.x >> 7);
-    const long long ngroups = (long long)gridDim.x * FWD_GROUPS;
-    for (long long tile = ggroup; tile * TCG_THREADS < n; tile += ngroups) {
-        const long long i = tile * TCG_THREADS + g.wq * 32 + g.lane;
+    constexpr int G = fwd_groups(MODE), W = tc_mode_scratch(MODE);
+    const uint32_t tmem_base = tc_prologue(net, smem_tc, G, W);
+    TcGroup g = tc_make_group(smem_tc, G, tmem_base, W);
+    const long long ggroup = (long long)blockIdx.x * G + (threadIdx.x >> 7);
+    const long long ngroups = (long long)gridDim.x * G;
+    // the next tile's coordinates are fetched (from DRAM) while the current tile is evaluated
+    long long tile = ggroup;
+    long long i = tile * TCG_THREADS + g.wq * 32 + g.lane;
+    float px = 0.f, py = 0.f, pz = 0.f;
+    if (i < n) { px = __ldg(x + 3 * i); py = __ldg(x + 3 * i + 1); pz = __ldg(x + 3 * i + 2); }
+    for (; tile * TCG_THREADS < n; tile += ngroups) {
+        const long long i_next = i + ngroups * TCG_THREADS;
+        float nx = 0.f, ny = 0.f, nz = 0.f;
+        if (i_next < n) { nx = __ldg(x + 3 * i_next); ny = __ldg(x + 3 * i_next + 1); nz = __ldg(x + 3 * i_next + 2); }
         const bool active = i < n;
-        float px = 0.f, py = 0.f, pz = 0.f;
-        if (active) { px = __ldg(x + 3 * i); py = __ldg(x + 3 * i + 1); pz = __ldg(x + 3 * i + 2); }
-        const float d = tc_group_eval<HALF>(net, g, px, py, pz, active);
+        const float d = tc_group_eval<MODE>(net, g, px, py, pz, active);
         if (active) out[i] = d;
+        i = i_next; px = nx; py = ny; pz = nz;
     }
     tc_epilogue_free(tmem_base);
+}
+
+template <int MODE>
+int launch_fwd(const NetDev& nd, const float* x, long long n, float* out, cudaStream_t st) {
+    auto kern = sdf_forward_tc_kernel<MODE>;
+    constexpr int threads = fwd_groups(MODE) * TCG_THREADS, smem = fwd_smem(MODE);
+    static_assert(smem <= 232448, "shared memory budget");
+    NGLOD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    long long grid = nglod_sm_count();
+    const long long want = (n + threads - 1) / threads;
+    if (want < grid) grid = want;
+    kern<<<(int)grid, threads, smem, st>>>(nd, x, n, out);
+    return (int)cudaGetLastError();
 }
 
 // Debug / self-test: D[128,128] = A[128,40] * B[128,40]^T through the exact operand layout, descriptors,
@@ -76,13 +98,9 @@ tc_gemm_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B
 }  // namespace
 
 int nglod_launch_sdf_forward_tc(const NetDev& nd, const float* x, long long n, float* out, cudaStream_t st) {
-    auto kern = nd.half_pairs ? sdf_forward_tc_kernel<true> : sdf_forward_tc_kernel<false>;
-    NGLOD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
-    long long grid = nglod_sm_count();
-    const long long want = (n + FWD_THREADS - 1) / FWD_THREADS;
-    if (want < grid) grid = want;
-    kern<<<(int)grid, FWD_THREADS, FWD_SMEM, st>>>(nd, x, n, out);
-    return (int)cudaGetLastError();
+    if (nd.half_pairs) return launch_fwd<TC_SINGLE_HALF>(nd, x, n, out, st);
+    if (nd.num_lods == 1) return launch_fwd<TC_SINGLE_F32>(nd, x, n, out, st);
+    return launch_fwd<TC_MULTI>(nd, x, n, out, st);
 }
 
 extern "C" int nglod_debug_tc_gemm(const float* A, const float* B, float* D, void* stream) {

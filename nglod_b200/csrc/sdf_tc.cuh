@@ -21,27 +21,61 @@
 #define TC_SMEM_A(g) (2 * TC_OPERAND_BYTES + (g) * 2 * TC_OPERAND_BYTES)          // A_hi of group g; A_lo follows
 #define TC_SMEM_W1(G) (2 * TC_OPERAND_BYTES + (G) * 2 * TC_OPERAND_BYTES)           // 128 floats + b1 (+pad) = 528 B
 #define TC_SMEM_SCRATCH(G) (TC_SMEM_W1(G) + 528)
-#define TC_SMEM_MBAR(G) (TC_SMEM_SCRATCH(G) + (G) * 4 * TC_WARP_SCRATCH_BYTES)      // G mbarriers (8 B each)
-#define TC_SMEM_TMEMPTR(G) (TC_SMEM_MBAR(G) + 8 * (G))
-#define TC_SMEM_BYTES(G) (TC_SMEM_TMEMPTR(G) + 16)
+// W = per-warp scratch bytes: TC_WARP_SCRATCH_BYTES for kernels that stage set-up records (multi-LOD gather, sparse
+// tracer), 0 for the single-grid kernels (records travel by warp shuffle)
+#define TC_SMEM_MBAR_W(G, W) (TC_SMEM_SCRATCH(G) + (G) * 4 * (W))                   // G mbarriers (8 B each)
+#define TC_SMEM_TMEMPTR_W(G, W) (TC_SMEM_MBAR_W(G, W) + 8 * (G))
+#define TC_SMEM_BYTES_W(G, W) (TC_SMEM_TMEMPTR_W(G, W) + 16)
+#define TC_SMEM_BYTES(G) TC_SMEM_BYTES_W(G, TC_WARP_SCRATCH_BYTES)
 
-// Stage W0|b0 as the B operand (hi and lo), W1 and b1.  All threads of the CTA; followed by a __syncthreads by the caller.
-__device__ __forceinline__ void tc_stage_weights(const NetDev& net, char* smem, int G) {
+// which gather a kernel instance is built for (separate instances keep register allocation clean)
+enum : int { TC_MULTI = 0, TC_SINGLE_F32 = 1, TC_SINGLE_HALF = 2 };
+__host__ __device__ constexpr int tc_mode_scratch(int mode) { return mode == TC_MULTI ? TC_WARP_SCRATCH_BYTES : 0; }
+
+// Stage W0|b0 as the B operand (hi and lo), W1 and b1.  All threads of the CTA.  The global loads are issued as ONE
+// batch of independent coalesced loads before anything is written: with a cold L2 (first launch after the weights
+// changed, or a flushed cache) a load-store-load-store loop pays the DRAM latency once per iteration (~20 us per
+// launch, measured), the batch pays it once.
+__device__ __forceinline__ void tc_load_weights(const NetDev& net, int base, float (&v)[16]) {
     const int in_dim = net.pos_invariant ? NGLOD_F : NGLOD_F + 3;
-    for (int e = threadIdx.x; e < NGLOD_H * TC_K; e += blockDim.x) {
-        const int j = e / TC_K, k = e - j * TC_K;
-        float v = 0.f;
-        if (k < NGLOD_F) v = __ldg(net.w0 + j * in_dim + (net.pos_invariant ? k : k + 3));
-        else if (k < NGLOD_F + 3) v = net.pos_invariant ? 0.f : __ldg(net.w0 + j * in_dim + (k - NGLOD_F));
-        else if (k == NGLOD_F + 3) v = __ldg(net.b0 + j);
-        const float hi = tf32_hi(v);
-        const uint32_t off = tc_elem_offset(j, k);
-        *reinterpret_cast<float*>(smem + TC_SMEM_B_HI + off) = hi;
-        *reinterpret_cast<float*>(smem + TC_SMEM_B_LO + off) = v - hi;
+    const int n_w0 = NGLOD_H * in_dim;
+    const int total = n_w0 + 2 * NGLOD_H + 1;              // W0, b0, W1, b1 (each its own pointer)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int e = base + threadIdx.x + i * blockDim.x;
+        float x = 0.f;
+        if (e < n_w0) x = __ldg(net.w0 + e);
+        else if (e < n_w0 + NGLOD_H) x = __ldg(net.b0 + (e - n_w0));
+        else if (e < n_w0 + 2 * NGLOD_H) x = __ldg(net.w1 + (e - n_w0 - NGLOD_H));
+        else if (e < total) x = __ldg(net.b1);
+        v[i] = x;
     }
+}
+__device__ __forceinline__ void tc_scatter_weights(const NetDev& net, char* smem, int G, int base, const float (&v)[16]) {
+    const int in_dim = net.pos_invariant ? NGLOD_F : NGLOD_F + 3;
+    const int n_w0 = NGLOD_H * in_dim;
     float* w1 = reinterpret_cast<float*>(smem + TC_SMEM_W1(G));
-    for (int e = threadIdx.x; e < NGLOD_H; e += blockDim.x) w1[e] = __ldg(net.w1 + e);
-    if (threadIdx.x == 0) w1[NGLOD_H] = __ldg(net.b1);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int e = base + threadIdx.x + i * blockDim.x;
+        if (e < n_w0 + NGLOD_H) {
+            int j, k;                                        // B row (hidden unit), K column
+            if (e < n_w0) {
+                j = e / in_dim;
+                const int c = e - j * in_dim;                // torch column: xyz first (unless pos_invariant)
+                k = net.pos_invariant ? c : (c < 3 ? NGLOD_F + c : c - 3);
+            } else {
+                j = e - n_w0;
+                k = NGLOD_F + 3;                             // bias rides on the constant-1 column
+            }
+            const float hi = tf32_hi(v[i]);
+            const uint32_t off = tc_elem_offset(j, k);
+            *reinterpret_cast<float*>(smem + TC_SMEM_B_HI + off) = hi;
+            *reinterpret_cast<float*>(smem + TC_SMEM_B_LO + off) = v[i] - hi;
+        } else if (e < n_w0 + 2 * NGLOD_H + 1) {
+            w1[e - n_w0 - NGLOD_H] = v[i];                   // W1[0..127], then b1 at index 128
+        }
+    }
 }
 
 __device__ __forceinline__ void tc_store_split4(char* a_hi, char* a_lo, uint32_t off, float4 v) {
@@ -209,71 +243,72 @@ __device__ __forceinline__ void tc_gather_rounds(const NetDev& net, int l0, int 
     }
 }
 
-// Single-grid gather (the prefix-summed grid of the requested LOD, fp32 or fp16 x-pair lines), software-pipelined:
-// a round = 4 queries x 8 lanes; DEPTH rounds of line loads are kept in flight, and round r+DEPTH is issued as soon as
-// round r has been consumed, so a warp always has loads outstanding while it interpolates and splits.
+// Single-grid gather (the prefix-summed grid of the requested LOD, fp32 or fp16 x-pair lines).
+// A round = queries 4r..4r+3 of the warp x 8 lanes each.  No shared-memory staging: the query's own lane keeps its
+// set-up record in registers and the 8 gathering lanes fetch it with warp shuffles (a dependent LDS->LDS->LDG chain
+// per round was the #2 stall after the L2 latency itself).  Software-pipelined: DEPTH rounds of line loads are in
+// flight, round r+DEPTH is issued as soon as round r has been consumed.  Rounds whose 4 queries are all dead are
+// skipped (only the frame tail / the last partial tile have dead lanes, so no compaction is attempted).
 template <bool HALF>
-__device__ __forceinline__ void tc_gather_single(const NetDev& net, int n_live, char* a_hi, char* a_lo, int row0,
-                                                 const float4* pack, const int* idx, int lane) {
-    constexpr int DEPTH = HALF ? 4 : 3;          // 64 / 96 data registers in flight
+__device__ __forceinline__ void tc_gather_single(const NetDev& net, const float4 rec, const unsigned live, char* a_hi,
+                                                 char* a_lo, int row0, int lane) {
+#ifndef NGLOD_DEPTH_HALF
+#define NGLOD_DEPTH_HALF 2
+#endif
+#ifndef NGLOD_DEPTH_F32
+#define NGLOD_DEPTH_F32 1
+#endif
+    constexpr int DEPTH = HALF ? NGLOD_DEPTH_HALF : NGLOD_DEPTH_F32;     // 32 data registers in flight (deeper bought nothing: profiles/README.md)
     const int sub = lane >> 3, c = lane & 7;
-    const int n_rounds = (n_live + 3) >> 2;      // <= 8
     const float* grid = net.grids[0];
     const int R = net.res[0];
+    const uint32_t off_me = __float_as_uint(rec.x);          // dead lanes carry record 0 = corner (0,0,0), weights 0
     TcLines<HALF> t[DEPTH];
-    int qs[DEPTH];
-    // slots past n_live shadow slot 0's query: their loads are harmless duplicates and nothing is stored for them
 #pragma unroll
-    for (int r = 0; r < DEPTH; ++r) {
-        if (r < n_rounds) {
-            const int slot = r * 4 + sub;
-            qs[r] = slot < n_live ? idx[slot] : -1;
-            tc_issue_lines<HALF>(grid, R, __float_as_uint(pack[qs[r] < 0 ? idx[0] : qs[r]].x), c, t[r]);
-        }
-    }
+    for (int r = 0; r < DEPTH; ++r)
+        if ((live >> (4 * r)) & 0xFu) tc_issue_lines<HALF>(grid, R, __shfl_sync(0xffffffffu, off_me, 4 * r + sub), c, t[r]);
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-        if (r < n_rounds) {                      // warp-uniform
-            const int b = r % DEPTH;
-            const int q = qs[b];
+        if ((live >> (4 * r)) & 0xFu) {                      // warp-uniform
+            const int q = 4 * r + sub;
+            float4 P;
+            P.x = 0.f;
+            P.y = __shfl_sync(0xffffffffu, rec.y, q);
+            P.z = __shfl_sync(0xffffffffu, rec.z, q);
+            P.w = __shfl_sync(0xffffffffu, rec.w, q);
             uint64_t acc01 = 0ull, acc23 = 0ull;
-            tc_consume_lines<HALF>(pack[q < 0 ? idx[0] : q], t[b], acc01, acc23);
-            if (r + DEPTH < n_rounds) {
-                const int slot = (r + DEPTH) * 4 + sub;
-                qs[b] = slot < n_live ? idx[slot] : -1;
-                tc_issue_lines<HALF>(grid, R, __float_as_uint(pack[qs[b] < 0 ? idx[0] : qs[b]].x), c, t[b]);
-            }
-            if (q >= 0) {
+            tc_consume_lines<HALF>(P, t[r % DEPTH], acc01, acc23);
+            if ((live >> q) & 1u) {
                 float4 acc;
                 f2_unpack(acc01, acc.x, acc.y); f2_unpack(acc23, acc.z, acc.w);
                 tc_store_split4(a_hi, a_lo, tc_elem_offset(row0 + q, 4 * c), acc);
             }
         }
+        if (r + DEPTH < 8) {
+            if ((live >> (4 * (r + DEPTH))) & 0xFu)
+                tc_issue_lines<HALF>(grid, R, __shfl_sync(0xffffffffu, off_me, 4 * (r + DEPTH) + sub), c, t[r % DEPTH]);
+        }
     }
 }
 
 // Gather for the warp's 32 queries into rows [row0, row0+32) of the group's A operand.
-//   px,py,pz / active : this lane's query;   pack/idx : this warp's scratch.
-// Every lane of the warp must call (convergent).  HALF kernels only ever see single-grid (summed) views.
-template <bool HALF>
+//   px,py,pz / active : this lane's query;   pack/idx : this warp's scratch (TC_MULTI only).
+// Every lane of the warp must call (convergent).
+template <int MODE>
 __device__ __forceinline__ void tc_gather_rows(const NetDev& net, float px, float py, float pz, bool active,
                                                char* a_hi, char* a_lo, int row0, float4* pack, int* idx, int lane) {
     const unsigned live = __ballot_sync(0xffffffffu, active);
     const int n_live = __popc(live);
     if (n_live == 0) return;
-    if (active) {
-        idx[__popc(live & ((1u << lane) - 1u))] = lane;
-        // K chunk 8 = {x, y, z, 1}: the query's own lane writes it (no shuffles needed later)
-        tc_store_split4(a_hi, a_lo, tc_elem_offset(row0 + lane, NGLOD_F), make_float4(px, py, pz, 1.f));
-    }
-    if (HALF || net.num_lods == 1) {
-        if (active) pack[lane] = tc_setup_record<HALF>(px, py, pz, net.res[0]);
-        __syncwarp();
-        tc_gather_single<HALF>(net, n_live, a_hi, a_lo, row0, pack, idx, lane);
-        __syncwarp();
-        return;
-    }
-    if constexpr (!HALF) {
+    // K chunk 8 = {x, y, z, 1}: the query's own lane writes it (no shuffles needed later)
+    if (active) tc_store_split4(a_hi, a_lo, tc_elem_offset(row0 + lane, NGLOD_F), make_float4(px, py, pz, 1.f));
+    if constexpr (MODE != TC_MULTI) {
+        constexpr bool HALF = MODE == TC_SINGLE_HALF;
+        float4 rec = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active) rec = tc_setup_record<HALF>(px, py, pz, net.res[0]);
+        tc_gather_single<HALF>(net, rec, live, a_hi, a_lo, row0, lane);
+    } else {
+        if (active) idx[__popc(live & ((1u << lane) - 1u))] = lane;
         for (int l0 = 0; l0 < net.num_lods; l0 += TC_PACK_LODS) {
             const int nl = min(TC_PACK_LODS, net.num_lods - l0);
             // ---- phase 1: per-LOD set-up, once per query (not once per lane of the query)
@@ -325,9 +360,14 @@ struct TcGroup {
     uint32_t parity;
 };
 
-template <bool HALF = false>
+template <int MODE = TC_MULTI>
 __device__ __forceinline__ float tc_group_eval(const NetDev& net, TcGroup& g, float px, float py, float pz, bool active) {
-    tc_gather_rows<HALF>(net, px, py, pz, active, g.a_hi, g.a_lo, g.wq * 32, g.pack, g.idx, g.lane);
+#ifndef NGLOD_EXP_NO_GATHER      // timing experiments only (profiles/exp_parts.sh): results are garbage with these set
+    tc_gather_rows<MODE>(net, px, py, pz, active, g.a_hi, g.a_lo, g.wq * 32, g.pack, g.idx, g.lane);
+#endif
+#ifdef NGLOD_EXP_NO_MMA
+    return px + g.w1[g.lane];
+#endif
     fence_proxy_async_smem();                     // generic-proxy smem writes -> visible to the tensor core
     tc_fence_before_sync();                       // order the previous tile's TMEM loads before the next MMA
     named_bar_sync(g.bar_id, TCG_THREADS);
@@ -342,7 +382,7 @@ __device__ __forceinline__ float tc_group_eval(const NetDev& net, TcGroup& g, fl
     return tc_epilogue(g.tmem_row, g.w1);
 }
 
-__device__ __forceinline__ TcGroup tc_make_group(char* smem, int G, uint32_t tmem_base) {
+__device__ __forceinline__ TcGroup tc_make_group(char* smem, int G, uint32_t tmem_base, int W = TC_WARP_SCRATCH_BYTES) {
     TcGroup g;
     const int warp = threadIdx.x >> 5;
     const int grp = warp >> 2;
@@ -354,10 +394,10 @@ __device__ __forceinline__ TcGroup tc_make_group(char* smem, int G, uint32_t tme
     g.a_lo_s = smem_u32(g.a_lo);
     g.b_hi_s = smem_u32(smem + TC_SMEM_B_HI);
     g.b_lo_s = smem_u32(smem + TC_SMEM_B_LO);
-    g.mbar_s = smem_u32(smem + TC_SMEM_MBAR(G) + 8 * grp);
+    g.mbar_s = smem_u32(smem + TC_SMEM_MBAR_W(G, W) + 8 * grp);
     g.tmem_acc = tmem_base + (uint32_t)(grp * TC_N);
     g.tmem_row = g.tmem_acc + ((uint32_t)(g.wq * 32) << 16);
-    char* scratch = smem + TC_SMEM_SCRATCH(G) + warp * TC_WARP_SCRATCH_BYTES;
+    char* scratch = smem + TC_SMEM_SCRATCH(G) + warp * W;
     g.pack = reinterpret_cast<float4*>(scratch);
     g.idx = reinterpret_cast<int*>(scratch + TC_PACK_LODS * 32 * 16);
     g.w1 = reinterpret_cast<const float*>(smem + TC_SMEM_W1(G));
@@ -367,21 +407,27 @@ __device__ __forceinline__ TcGroup tc_make_group(char* smem, int G, uint32_t tme
 }
 
 // Common prologue: zero the operand buffers, stage weights, init mbarriers, allocate TMEM.  Returns the TMEM base.
-__device__ __forceinline__ uint32_t tc_prologue(const NetDev& net, char* smem, int G) {
-    for (int e = threadIdx.x; e < (TC_SMEM_SCRATCH(G) + G * 4 * TC_WARP_SCRATCH_BYTES) / 16; e += blockDim.x)
+__device__ __forceinline__ uint32_t tc_prologue(const NetDev& net, char* smem, int G, int W = TC_WARP_SCRATCH_BYTES) {
+    float wv[16];                        // one batch covers all 4737 values when blockDim >= 297 (3+ groups)
+    tc_load_weights(net, 0, wv);
+    for (int e = threadIdx.x; e < (TC_SMEM_SCRATCH(G) + G * 4 * W) / 16; e += blockDim.x)
         reinterpret_cast<float4*>(smem)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
-    tc_stage_weights(net, smem, G);
+    tc_scatter_weights(net, smem, G, 0, wv);
+    for (int base = 16 * blockDim.x; base < NGLOD_H * (NGLOD_F + 3) + 2 * NGLOD_H + 1; base += 16 * blockDim.x) {
+        tc_load_weights(net, base, wv);
+        tc_scatter_weights(net, smem, G, base, wv);
+    }
     if (threadIdx.x == 0) {
-        for (int g = 0; g < G; ++g) mbar_init(smem_u32(smem + TC_SMEM_MBAR(G) + 8 * g), 1);
+        for (int g = 0; g < G; ++g) mbar_init(smem_u32(smem + TC_SMEM_MBAR_W(G, W) + 8 * g), 1);
         mbar_fence_init();
     }
-    if (threadIdx.x < 32) tmem_alloc(smem_u32(smem + TC_SMEM_TMEMPTR(G)), 512);
+    if (threadIdx.x < 32) tmem_alloc(smem_u32(smem + TC_SMEM_TMEMPTR_W(G, W)), 512);
     fence_proxy_async_smem();
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
-    return *reinterpret_cast<volatile uint32_t*>(smem + TC_SMEM_TMEMPTR(G));
+    return *reinterpret_cast<volatile uint32_t*>(smem + TC_SMEM_TMEMPTR_W(G, W));
 }
 
 __device__ __forceinline__ void tc_epilogue_free(uint32_t tmem_base) {

@@ -38,15 +38,18 @@ struct TraceParams {
 #ifndef NGLOD_TRACE_GROUPS
 #define NGLOD_TRACE_GROUPS 3
 #endif
-constexpr int TRACE_TC_GROUPS = NGLOD_TRACE_GROUPS;
-constexpr int TRACE_TC_THREADS = TRACE_TC_GROUPS * TCG_THREADS;
-constexpr int TRACE_TC_SMEM = TC_SMEM_BYTES(TRACE_TC_GROUPS);
+#ifndef NGLOD_TRACE_GROUPS_SINGLE
+#define NGLOD_TRACE_GROUPS_SINGLE 4
+#endif
+constexpr int trace_groups(int mode) { return mode == TC_MULTI ? NGLOD_TRACE_GROUPS : NGLOD_TRACE_GROUPS_SINGLE; }
+constexpr int trace_tc_threads(int mode) { return trace_groups(mode) * TCG_THREADS; }
+constexpr int trace_tc_smem(int mode) { return TC_SMEM_BYTES_W(trace_groups(mode), tc_mode_scratch(mode)); }
 
 // TC = false: FP32 CUDA-core decoder, warps are independent (8 per CTA, 2 CTAs/SM).
-// TC = true : tcgen05 decoder; 4 warps form a 128-row MMA tile and advance in lock-step rounds (3 groups per CTA).
-// HALF (TC only): gather from the fp16 x-pair copy of the grids (nglod_pack_grid_fp16).
-template <bool TC, bool HALF>
-__global__ void __launch_bounds__(TC ? TRACE_TC_THREADS : SDF_THREADS, TC ? 1 : 2)
+// TC = true : tcgen05 decoder; 4 warps form a 128-row MMA tile and advance in lock-step rounds.  MODE picks the
+//             gather (sdf_tc.cuh): per-LOD fp32 grids, or ONE prefix-summed grid in fp32 / fp16 x-pair lines.
+template <bool TC, int MODE>
+__global__ void __launch_bounds__(TC ? trace_tc_threads(MODE) : SDF_THREADS, TC ? 1 : 2)
 sphere_trace_kernel(const NetDev net, const float* __restrict__ ray_o, const float* __restrict__ ray_d,
                     const long long n, const TraceParams tp, float* __restrict__ out_x,
                     float* __restrict__ out_t, uint8_t* __restrict__ out_hit, float* __restrict__ out_n,
@@ -58,8 +61,8 @@ sphere_trace_kernel(const NetDev net, const float* __restrict__ ray_o, const flo
     uint32_t tmem_base = 0;
     TcGroup grp;
     if constexpr (TC) {
-        tmem_base = tc_prologue(net, smem_raw, TRACE_TC_GROUPS);
-        grp = tc_make_group(smem_raw, TRACE_TC_GROUPS, tmem_base);
+        tmem_base = tc_prologue(net, smem_raw, trace_groups(MODE), tc_mode_scratch(MODE));
+        grp = tc_make_group(smem_raw, trace_groups(MODE), tmem_base, tc_mode_scratch(MODE));
     } else {
         sdf_stage_weights(net, smem);
         tile = smem + SDF_SMEM_WARP_OFF + warp * SDF_SMEM_PER_WARP;
@@ -154,7 +157,7 @@ sphere_trace_kernel(const NetDev net, const float* __restrict__ ray_o, const flo
             if (axis == 0) qx = x + e; else if (axis == 1) qy = y + e; else qz = z + e;
         }
         float dv;
-        if constexpr (TC) dv = tc_group_eval<HALF>(net, grp, qx, qy, qz, occupied);
+        if constexpr (TC) dv = tc_group_eval<MODE>(net, grp, qx, qy, qz, occupied);
         else dv = warp_sdf_eval(net, smem, tile, idx, qx, qy, qz, occupied, lane);
         const unsigned march_mask = __ballot_sync(0xffffffffu, phase == PH_MARCH);
         if (lane == 0) {
@@ -220,17 +223,18 @@ extern "C" int nglod_sphere_trace(const nglod_net_t* net, int32_t lod, const flo
     tp.two_h = (float)(opts->normal_h * 2.0);
     const NetDev nd = nglod_make_netdev_infer(net, lod);
     if (net->math_mode == NGLOD_MATH_TC3XTF32) {
-        const bool half = nd.half_pairs != 0;
-        auto kern = half ? sphere_trace_kernel<true, true> : sphere_trace_kernel<true, false>;
-        NGLOD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TRACE_TC_SMEM));
+        const int mode = nd.half_pairs ? TC_SINGLE_HALF : (nd.num_lods == 1 ? TC_SINGLE_F32 : TC_MULTI);
+        auto kern = mode == TC_SINGLE_HALF ? sphere_trace_kernel<true, TC_SINGLE_HALF>
+                  : mode == TC_SINGLE_F32 ? sphere_trace_kernel<true, TC_SINGLE_F32> : sphere_trace_kernel<true, TC_MULTI>;
+        const int threads = trace_tc_threads(mode), smem = trace_tc_smem(mode);
+        NGLOD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         long long grid = nglod_sm_count();
-        const long long want = (n + TRACE_TC_THREADS - 1) / TRACE_TC_THREADS;
+        const long long want = (n + threads - 1) / threads;
         if (want < grid) grid = want;
-        kern<<<(int)grid, TRACE_TC_THREADS, TRACE_TC_SMEM, st>>>(nd, ray_o, ray_d, (long long)n, tp, x, depth, hit,
-                                                                 normal, queue, stats);
+        kern<<<(int)grid, threads, smem, st>>>(nd, ray_o, ray_d, (long long)n, tp, x, depth, hit, normal, queue, stats);
         return (int)cudaGetLastError();
     }
-    auto kern = sphere_trace_kernel<false, false>;
+    auto kern = sphere_trace_kernel<false, TC_MULTI>;
     NGLOD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SDF_SMEM_BYTES));
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SDF_THREADS, SDF_SMEM_BYTES) != cudaSuccess || per_sm < 1)
