@@ -35,13 +35,20 @@ CAM_FROM, CAM_TO, FOV = [-2.8, 2.8, -2.8], [0.0, 0.0, 0.0], 30.0
 FIT_STEPS, FIT_BATCH = 300, 65536
 SDF_N = 1 << 20
 MATH_MODE = os.environ.get("NGLOD_MATH", "tc")      # "tc" = tcgen05 3xTF32 decoder, "fp32" = CUDA cores
-GATHER_BYTES_PER_QUERY = (LOD + 1) * 8 * 32 * 4          # fp32 grids: 5120 B  
+GRID_STORAGE = os.environ.get("NGLOD_GRID_STORAGE", "fp32")   # "fp32" (headline) | "fp16" x-pair lines (extras)
+SUM_LODS = os.environ.get("NGLOD_SUM_LODS", "1") != "0"        # inference gathers the prefix-summed grid of the LOD
+# Algorithmic gather bytes per SDF evaluation.  SURVEY.md 8d quotes the per-LOD formulation ((lod+1) x 8 corners x 32 ch
+# x 4 B = 5120 B); the inference kernels evaluate the same function from ONE prefix-summed grid,
+# so the bytes the algorithm has to move are 8 corner lines x 128 B = 1024 B (fp32) per evaluation.
+GATHER_BYTES_PER_QUERY_PER_LOD = (LOD + 1) * 8 * 32 * 4
+GATHER_BYTES_PER_QUERY = 8 * 32 * 4 if SUM_LODS else GATHER_BYTES_PER_QUERY_PER_LOD
 IO_BYTES_PER_QUERY = 16
 RAY_IO_BYTES = 24 + 12 + 4 + 1 + 12                        # ray_o, ray_d in; x, depth, hit, normal out
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE sphere_trace_kernel / sdf_forward_tc_kernel launch, from the
-# `ncu --set full` captures summarised in profiles/sphere_trace_tc_r1_v1.txt and profiles/sdf_forward_tc_r1_v1.txt
-NCU_TRAFFIC_TRACE_BYTES = 42155008 + 2635264
-NCU_TRAFFIC_SDF_FWD_BYTES = 53127680 + 1421568
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE sphere_trace_kernel / sdf_forward_tc_kernel launch (single-grid
+# fp32 instances), from the `ncu --set full` captures summarised in profiles/sphere_trace_sum_r1_v3.txt and
+# profiles/sdf_forward_sum_r1_v3.txt
+NCU_TRAFFIC_TRACE_BYTES = 38474240 + 1309696
+NCU_TRAFFIC_SDF_FWD_BYTES = 47820032 + 684032
 
 
 def load_peaks():
@@ -142,6 +149,7 @@ def build_and_fit(device, log):
     torch.manual_seed(0)
     net = OctreeSDF(args).to(device)
     net.math_mode = MATH_MODE
+    net.grid_storage, net.sum_lods = GRID_STORAGE, SUM_LODS
     t0 = time.time()
     ds = MeshDataset(args, mesh=torus(0.6, 0.25, 128, 64), device=device)       # 500 000 labelled points
     torch.cuda.synchronize()
@@ -279,7 +287,23 @@ def run_ours(ns):
     fwd_ms = ndist.max_over_ranks(fwd_ms, device)
     bwd_ms = ndist.max_over_ranks(bwd_ms, device)
 
+    variants = {}
+    if not ns.no_extras:
+        for tag, storage, summ in (("fp16_xpair_lines", "fp16", True), ("per_lod_gather", "fp32", False)):
+            net.grid_storage, net.sum_lods = storage, summ
+            v = net.net_view()
+            f_ms = ndist.max_over_ranks(time_kernel(lambda: ops.sdf_forward(v, LOD, xq), 10), device)
+            t_ms = ndist.max_over_ranks(time_kernel(lambda: tracer(net, ray_o, ray_d), 10), device)
+            variants[tag] = {"forward_qps": world * SDF_N / (f_ms / 1e3), "forward_ms": f_ms,
+                             "trace_rays_per_s": world * n_rays / (t_ms / 1e3), "trace_ms": t_ms}
+        net.grid_storage, net.sum_lods = GRID_STORAGE, SUM_LODS
+        xbig = torch.rand(1 << 23, 3, device=device, generator=g) * 2 - 1
+        big_ms = ndist.max_over_ranks(time_kernel(lambda: ops.sdf_forward(view, LOD, xbig), 5), device)
+        variants["forward_2^23_queries"] = {"forward_qps": world * (1 << 23) / (big_ms / 1e3), "forward_ms": big_ms}
+        del xbig
     extras = {} if ns.no_extras else run_extras(net, args, device, rank, world, flush, log)
+    if variants:
+        extras["inference_variants"] = variants
     if rank != 0:
         return
     peak, peak_src = load_peaks()
@@ -305,7 +329,9 @@ def run_ours(ns):
                                "hidden=128 fitted in-run to a procedural torus mesh (BASELINE.json configs[1])",
                    "rays_per_gpu_step": n_rays, "fps_per_gpu": 1e3 / (total_ms / ns.steps),
                    "sdf_evals_per_ray": n_eval / n_rays, "hit_fraction": n_hit / n_rays,
-                   "num_steps": 256, "math_mode": MATH_MODE, "l2": "flushed between timed iterations (256 MB memset)",
+                   "num_steps": 256, "math_mode": MATH_MODE, "grid_storage": GRID_STORAGE,
+                   "lod_sum": "prefix-summed grid (one 8-corner gather per evaluation)" if SUM_LODS else "per-LOD gather",
+                   "l2": "flushed between timed iterations (256 MB memset)",
                    "parallelism": f"one frame per GPU x{world}, no collective"},
         "e2e": {"value": world * n_rays * ns.steps / e2e_s, "unit": "rays/s",
                 "h2d_bytes_per_step": n_rays * 24, "d2h_bytes_per_step": n_rays * (12 + 4 + 1 + 12),
@@ -316,17 +342,24 @@ def run_ours(ns):
                      "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_TRACE_BYTES, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms,
                      "compulsory_GBs": compulsory,
-                     "note": "algorithmic bytes = sdf_evals x (5120 B gather + 16 B io) + rays x 53 B; the gather is "
-                             "served by L2/L1 (grids 40.5 MB < L2), so frac may exceed 1 (SURVEY.md 8d); DRAM traffic "
-                             "(ncu) is the compulsory 45 MB: grids once + ray I/O. The binding resource is the L1 data "
-                             "pipe (1 line-wavefront/clk/SM), see DESIGN.md section 4"},
+                     "per_lod_formulation_GBs": (n_eval * (GATHER_BYTES_PER_QUERY_PER_LOD + IO_BYTES_PER_QUERY)
+                                                 + n_rays * RAY_IO_BYTES) / (kernel_ms / 1e3) / 1e9,
+                     "note": f"algorithmic bytes = sdf_evals x ({GATHER_BYTES_PER_QUERY} B gather + 16 B io) + rays x 53 B; "
+                             "per_lod_formulation_GBs is the same count with SURVEY 8d's 5120 B (the reference's 5 "
+                             "separate gathers, which the summed grid replaces); the gather is "
+                             "served by L2/L1 (summed grid 35 MB < L2), so frac may exceed 1 (SURVEY.md 8d); DRAM traffic "
+                             "(ncu) is the compulsory ~40 MB: the grid once + ray I/O. The kernel is latency/sync "
+                             "bound (issue 37 %, L1 34 %, L2 8 %, tensor 24 %), see DESIGN.md section 4"},
         "sdf_queries": {"n": SDF_N, "lod": LOD,
                         "forward_qps": world * SDF_N / (fwd_ms / 1e3), "forward_ms": fwd_ms,
                         "forward_backward_qps": world * SDF_N / ((fwd_ms + bwd_ms) / 1e3), "backward_ms": bwd_ms,
                         "roofline": {"bound": "hbm", "kernel": "sdf_forward_tc_kernel" if MATH_MODE == "tc" else "sdf_forward_kernel",
                                      "achieved": q_bytes / (fwd_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                                      "frac": q_bytes / (fwd_ms / 1e3) / 1e9 / peak,
-                                     "traffic": NCU_TRAFFIC_SDF_FWD_BYTES}},
+                                     "traffic": NCU_TRAFFIC_SDF_FWD_BYTES,
+                                     "l2_to_sm_GBs": SDF_N * GATHER_BYTES_PER_QUERY / (fwd_ms / 1e3) / 1e9,
+                                     "note": "random queries miss L1 (hit 3 %), so the 1024 B/query gather is L2->SM "
+                                             "traffic; the L2 fabric tops out near 6300 B/clk (~11 TB/s at 1.8 GHz)"}},
     }
     line["extras"] = extras
     if world == 1 and not ns.no_cpu_baseline:
@@ -494,7 +527,23 @@ def run_reference(ns):
     """The reference's CPU path for the same metric/config: the oracle port (same ATen calls as the reference's
     PyTorch path; the reference itself is Python under /root/reference, which does not exist on the GPU box)."""
     rank = int(os.environ.get("RANK", "0"))
+    variants = {}
+    if not ns.no_extras:
+        for tag, storage, summ in (("fp16_xpair_lines", "fp16", True), ("per_lod_gather", "fp32", False)):
+            net.grid_storage, net.sum_lods = storage, summ
+            v = net.net_view()
+            f_ms = ndist.max_over_ranks(time_kernel(lambda: ops.sdf_forward(v, LOD, xq), 10), device)
+            t_ms = ndist.max_over_ranks(time_kernel(lambda: tracer(net, ray_o, ray_d), 10), device)
+            variants[tag] = {"forward_qps": world * SDF_N / (f_ms / 1e3), "forward_ms": f_ms,
+                             "trace_rays_per_s": world * n_rays / (t_ms / 1e3), "trace_ms": t_ms}
+        net.grid_storage, net.sum_lods = GRID_STORAGE, SUM_LODS
+        xbig = torch.rand(1 << 23, 3, device=device, generator=g) * 2 - 1
+        big_ms = ndist.max_over_ranks(time_kernel(lambda: ops.sdf_forward(view, LOD, xbig), 5), device)
+        variants["forward_2^23_queries"] = {"forward_qps": world * (1 << 23) / (big_ms / 1e3), "forward_ms": big_ms}
+        del xbig
     extras = {} if ns.no_extras else run_extras(net, args, device, rank, world, flush, log)
+    if variants:
+        extras["inference_variants"] = variants
     if rank != 0:
         return
     from oracle import nglod_oracle as O
