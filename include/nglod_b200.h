@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define NGLOD_ABI_VERSION 3
+#define NGLOD_ABI_VERSION 4
 #define NGLOD_MAX_LODS 8
 
 /* nglod_net_t.math_mode */
@@ -91,6 +91,13 @@ typedef struct nglod_net_grad {
     float* b0[NGLOD_MAX_LODS];
     float* w1[NGLOD_MAX_LODS];
     float* b1[NGLOD_MAX_LODS];
+    /* OPTIONAL scratch for the single-grid backward: summed[i] is shaped like grids[i] and must be ALL ZERO on entry;
+     * it is all zero again on return.  When net->summed[lod] and summed[0..lod] are given, nglod_sdf_backward /
+     * nglod_sdf_train_step recompute the forward from the prefix-summed grid, scatter dL/d(summed[lod]) (8 corners per
+     * query instead of 8*(lod+1)) into summed[lod] and then push it down the LOD chain with the transpose of the
+     * prefix sum (dense restriction kernels, level by level -- the hat functions nest), adding into grids[0..lod]:
+     * the same gradients as the per-LOD scatter, to fp32 rounding. */
+    float* summed[NGLOD_MAX_LODS];
 } nglod_net_grad_t;
 
 /* ---- introspection ------------------------------------------------------ */

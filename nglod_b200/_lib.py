@@ -72,6 +72,7 @@ class NetGradStruct(ctypes.Structure):
         ("b0", c_void_p * MAX_LODS),
         ("w1", c_void_p * MAX_LODS),
         ("b1", c_void_p * MAX_LODS),
+        ("summed", c_void_p * MAX_LODS),
     ]
 
 

@@ -302,15 +302,99 @@ sdf_backward_kernel(const NetDev net, const GradDev grad, const float* __restric
     }
 }
 
+// ---- transpose of the prefix sum: push dL/d(summed grid of level l) down to the LOD grids, level by level.
+// restrict: Tc[c] += sum over fine nodes n in the support of coarse node c's hat function of  w(n, c) * Tf[n],
+//           w = prod_axis (1 - |n_a - k c_a| / k), k = Rf / Rc  -- the weights nglod_build_summed_grid used, transposed.
+__global__ void __launch_bounds__(256)
+restrict_add_kernel(const float4* __restrict__ Tf, const int Rf, float4* __restrict__ Tc, const int Rc, const long long n_chunks) {
+    const int Sc = Rc + 1, Sf = Rf + 1, k = Rf / Rc;
+    const float inv_k = 1.f / (float)k;           // exact for the power-of-two ratios of an octree
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_chunks; e += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(e & 7);
+        long long node = e >> 3;
+        const int cx = (int)(node % Sc); node /= Sc;
+        const int cy = (int)(node % Sc);
+        const int cz = (int)(node / Sc);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int dz = -(k - 1); dz <= k - 1; ++dz) {
+            const int fz = cz * k + dz;
+            if (fz < 0 || fz > Rf) continue;
+            const float wz = 1.f - (float)abs(dz) * inv_k;
+            for (int dy = -(k - 1); dy <= k - 1; ++dy) {
+                const int fy = cy * k + dy;
+                if (fy < 0 || fy > Rf) continue;
+                const float wzy = wz * (1.f - (float)abs(dy) * inv_k);
+                for (int dx = -(k - 1); dx <= k - 1; ++dx) {
+                    const int fx = cx * k + dx;
+                    if (fx < 0 || fx > Rf) continue;
+                    const float w = wzy * (1.f - (float)abs(dx) * inv_k);
+                    const float4 v = __ldg(Tf + ((long long)(fz * Sf + fy) * Sf + fx) * 8 + c);
+                    acc.x = fmaf(v.x, w, acc.x); acc.y = fmaf(v.y, w, acc.y); acc.z = fmaf(v.z, w, acc.z); acc.w = fmaf(v.w, w, acc.w);
+                }
+            }
+        }
+        float4 t = Tc[e];
+        t.x += acc.x; t.y += acc.y; t.z += acc.z; t.w += acc.w;
+        Tc[e] = t;
+    }
+}
+
+// g += T (if g), T = 0
+__global__ void __launch_bounds__(256)
+accumulate_and_clear_kernel(float4* __restrict__ T, float4* __restrict__ g, const long long n4) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (long long)gridDim.x * blockDim.x) {
+        const float4 t = T[e];
+        if (g) {
+            float4 v = g[e];
+            v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+            g[e] = v;
+        }
+        T[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+int restrict_cascade(const nglod_net_t* net, int lod, const nglod_net_grad_t* grad, cudaStream_t st) {
+    const long long cap = (long long)nglod_sm_count() * 16;
+    for (int l = lod; l >= 0; --l) {
+        const long long S = net->grid_res[l] + 1;
+        const long long n4 = S * S * S * 8;
+        if (l > 0) {
+            const long long Sc = net->grid_res[l - 1] + 1;
+            const long long nc = Sc * Sc * Sc * 8;
+            long long blocks = (nc + 255) / 256;
+            if (blocks > cap) blocks = cap;
+            restrict_add_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(grad->summed[l]), net->grid_res[l],
+                                                             reinterpret_cast<float4*>(grad->summed[l - 1]), net->grid_res[l - 1], nc);
+        }
+        long long blocks = (n4 + 255) / 256;
+        if (blocks > cap) blocks = cap;
+        accumulate_and_clear_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<float4*>(grad->summed[l]),
+                                                                 reinterpret_cast<float4*>(grad->grids[l]), n4);
+    }
+    return (int)cudaGetLastError();
+}
+
+// the single-grid path needs the summed grid of this LOD, zeroed scratch for every level down the chain, nesting grids
+bool use_summed_backward(const nglod_net_t* net, int lod, const nglod_net_grad_t* grad) {
+    if (!net->summed[lod] || !grad) return false;
+    for (int i = 0; i <= lod; ++i) {
+        if (!grad->summed[i] || (reinterpret_cast<uintptr_t>(grad->summed[i]) & 15u)) return false;
+        if (i > 0 && net->grid_res[i] % net->grid_res[i - 1] != 0) return false;
+    }
+    return true;
+}
+
 template <bool FUSED_LOSS, bool WITH_GX>
 int launch_backward(const nglod_net_t* net, int lod, const nglod_net_grad_t* grad, const float* x, int64_t n,
                     const float* grad_out, const float* gt, float loss_scale, float* grad_x, float* loss_out,
-                    cudaStream_t st) {
+                    cudaStream_t st, bool cascade = true) {
     auto kern = sdf_backward_kernel<FUSED_LOSS, WITH_GX>;
     NGLOD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM_BYTES));
-    const NetDev nd = nglod_make_netdev(net, lod);
+    const bool single = use_summed_backward(net, lod, grad);
+    const NetDev nd = single ? nglod_make_netdev_infer(net, lod, /*allow_half=*/false) : nglod_make_netdev(net, lod);
     GradDev gdv;
-    for (int i = 0; i < NGLOD_MAX_LODS; ++i) gdv.grids[i] = (grad && i <= lod) ? grad->grids[i] : nullptr;
+    for (int i = 0; i < NGLOD_MAX_LODS; ++i) gdv.grids[i] = (grad && i <= lod && !single) ? grad->grids[i] : nullptr;
+    if (single) gdv.grids[0] = grad->summed[lod];
     gdv.w0 = grad ? grad->w0[lod] : nullptr;
     gdv.b0 = grad ? grad->b0[lod] : nullptr;
     gdv.w1 = grad ? grad->w1[lod] : nullptr;
@@ -320,7 +404,8 @@ int launch_backward(const nglod_net_t* net, int lod, const nglod_net_grad_t* gra
     if (want < grid) grid = want;
     kern<<<(int)grid, SDF_THREADS, BWD_SMEM_BYTES, st>>>(nd, gdv, x, (long long)n, grad_out, gt, loss_scale, grad_x,
                                                          loss_out);
-    return (int)cudaGetLastError();
+    if (int e = (int)cudaGetLastError()) return e;
+    return (single && cascade) ? restrict_cascade(net, lod, grad, st) : 0;
 }
 
 }  // namespace
@@ -346,14 +431,18 @@ extern "C" int nglod_sdf_train_step(const nglod_net_t* net, uint32_t lod_mask, c
     if (!net || !grad) return NGLOD_EINVAL;
     if (n < 0 || (n > 0 && (!x || !gt))) return NGLOD_EINVAL;
     if (n == 0) return 0;
+    // every head scatters into the scratch of its own level; ONE cascade from the top head then pushes the lot down
+    int top_single = -1;
     for (int l = 0; l < net->num_lods; ++l) {
         if (!(lod_mask & (1u << l))) continue;
         if (int e = nglod_check_net(net, l)) return e;
         for (int i = 0; i <= l; ++i)
             if (grad->grids[i] && (reinterpret_cast<uintptr_t>(grad->grids[i]) & 15u)) return NGLOD_EINVAL;
+        if (use_summed_backward(net, l, grad)) top_single = l;
         if (int e = launch_backward<true, false>(net, l, grad, x, n, nullptr, gt, loss_scale, nullptr, loss_out,
-                                                 (cudaStream_t)stream))
+                                                 (cudaStream_t)stream, /*cascade=*/false))
             return e;
     }
+    if (top_single >= 0) return restrict_cascade(net, top_single, grad, (cudaStream_t)stream);
     return 0;
 }

@@ -64,7 +64,8 @@ class _SdfFunction(torch.autograd.Function):
         dec_params = module.decoder_params(lod)
         dec_grads = [torch.zeros_like(p) if needs[3 + n_grids + k] else None for k, p in enumerate(dec_params)]
         gx = ops.sdf_backward(view, lod, x, grad_out.contiguous(), grid_grads + [None] * (view.num_lods - n_grids),
-                              tuple(dec_grads), want_grad_x=needs[0])
+                              tuple(dec_grads), want_grad_x=needs[0],
+                              summed_scratch=module.summed_grad_scratch() if view.summed is not None else None)
         return (gx, None, None, *grid_grads, *dec_grads)
 
 
@@ -116,19 +117,28 @@ class OctreeSDF(BaseLOD):
         """Call after writing the grids behind torch's back (`.data` / raw pointers, e.g. the fused Adam kernel)."""
         self._derived = None
 
-    def _derived_grids(self):
-        """(summed, summed_half) for the inference kernels, rebuilt when a grid was written or moved."""
-        want_half = self.grid_storage == "fp16" and self.math_mode == "tc"
-        key = ([(f.fm._version, f.fm.data_ptr()) for f in self.features], want_half)
+    def _derived_grids(self, want_half=False):
+        """(summed, summed_half) rebuilt when a grid was written or moved; the fp16 copy only when asked for."""
+        key = [(f.fm._version, f.fm.data_ptr()) for f in self.features]
         if self._derived is None or self._derived[0] != key:
             grids = [f.fm.data for f in self.features]
             base = ops.NetView.grids_only(grids)
             old = self._derived[1] if self._derived is not None else [None] * len(grids)
             summed = [ops.build_summed_grid(base, i, out=o if (o is not None and o.device == g.device) else None)
                       for i, (g, o) in enumerate(zip(grids, old))]
-            half = [ops.pack_grid_fp16(sg) for sg in summed] if want_half else None
-            self._derived = (key, summed, half)
-        return self._derived[1], self._derived[2]
+            self._derived = [key, summed, None]
+        if want_half and self._derived[2] is None:
+            self._derived[2] = [ops.pack_grid_fp16(sg) for sg in self._derived[1]]
+        return self._derived[1], (self._derived[2] if want_half else None)
+
+    def summed_grad_scratch(self):
+        """Zero-filled buffers shaped like the grids for the single-grid backward (nglod_net_grad_t.summed); the
+        kernels leave them zero, so they are allocated once."""
+        sc = getattr(self, "_summed_scratch", None)
+        if sc is None or any(t.device != f.fm.device for t, f in zip(sc, self.features)):
+            sc = [torch.zeros_like(f.fm.data, memory_format=torch.preserve_format) for f in self.features]
+            self._summed_scratch = sc
+        return sc
 
     def summed_state_dict(self, lod=None):
         """state_dict of the function the inference kernels evaluate for sdf(x, lod), in the reference's own format:
@@ -144,12 +154,13 @@ class OctreeSDF(BaseLOD):
         return sd
 
     def net_view(self, inference=True):
-        """Borrow the current parameters as an nglod_net_t (rebuilt per call: pointers may move)."""
+        """Borrow the current parameters as an nglod_net_t (rebuilt per call: pointers may move).  inference=False (the
+        autograd / training kernels) never attaches the half-precision copy."""
         grids = [f.fm.data for f in self.features]
         decs = [tuple(p.data for p in self.decoder_params(i)) for i in range(self.num_lods)]
         summed = half = None
-        if inference and self.sum_lods and self._grids_nest():
-            summed, half = self._derived_grids()
+        if self.sum_lods and self._grids_nest():
+            summed, half = self._derived_grids(want_half=inference and self.grid_storage == "fp16" and self.math_mode == "tc")
         return ops.NetView(grids, decs, pos_invariant=self.pos_invariant,
                            math_mode=_lib.MATH_TC3XTF32 if self.math_mode == "tc" else _lib.MATH_FP32,
                            summed=summed, summed_half=half)

@@ -66,9 +66,11 @@ class FusedTrainer:
         self.flat_grad.zero_()
         self.lod_loss.zero_()
         grid_grads, dec_grads = self._grad_lists()
-        view = net.net_view(inference=False)
+        view = net.net_view(inference=False)    # rebuilds the prefix-summed grids from this step's weights (~30 us)
+        scratch = net.summed_grad_scratch() if view.summed is not None else None
         for l in lods:          # one fused forward+loss+backward launch per LOD head, each with its own loss cell
-            ops.sdf_train_step(view, 1 << l, pts, gts, 1.0 / batch, grid_grads, dec_grads, self.lod_loss[l:l + 1])
+            ops.sdf_train_step(view, 1 << l, pts, gts, 1.0 / batch, grid_grads, dec_grads, self.lod_loss[l:l + 1],
+                               summed_scratch=scratch)
         torch.sum(self.lod_loss, dim=0, keepdim=True, out=self.loss)
         ndist.allreduce_sum_(self.flat_grad)
         self.step_count += 1

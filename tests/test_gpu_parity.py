@@ -147,11 +147,16 @@ def _check_grads(net, gold, tag, lods, tol=2e-4):
             assert seq[0].weight.grad is None
 
 
-def test_autograd_backward_vs_golden(rand5):
+@pytest.mark.parametrize("sum_lods", [True, False])
+def test_autograd_backward_vs_golden(rand5, sum_lods):
+    """sum_lods=True: forward from the prefix-summed grid, 8-corner scatter into its gradient, dense restriction down
+    the LOD chain; False: the per-LOD gather / scatter.  Same golden gradients, same tolerance."""
     x = torch.from_numpy(rand5["x"]).to(DEV)
     gt = torch.from_numpy(rand5["gt"]).to(DEV)
     for tag, lods in (("g4", [4]), ("g13", [1, 3])):
         net, _ = rand5_model(DEV)
+        net.sum_lods = sum_lods
+        assert (net.net_view(inference=False).summed is not None) == sum_lods
         loss = 0
         for l in lods:
             loss = loss + ((net.sdf(x, lod=l) - gt) ** 2).sum()
@@ -159,6 +164,8 @@ def test_autograd_backward_vs_golden(rand5):
         loss.backward()
         assert abs(loss.item() - float(rand5[f"{tag}_loss"])) < 1e-6
         _check_grads(net, rand5, tag, lods)
+        if sum_lods:        # the scratch of the single-grid backward is handed back zeroed
+            assert all(float(t.abs().max()) == 0.0 for t in net.summed_grad_scratch())
 
 
 def test_grad_x_autodiff_and_finitediff_vs_golden(rand5):
@@ -172,11 +179,13 @@ def test_grad_x_autodiff_and_finitediff_vs_golden(rand5):
     assert np.abs(gf - rand5["finitediff_lod4"]).max() < 1e-4
 
 
-def test_fused_train_step_vs_oracle_adam(rand5):
+@pytest.mark.parametrize("sum_lods", [True, False])
+def test_fused_train_step_vs_oracle_adam(rand5, sum_lods):
     """FusedTrainer (flat buffers, fused fwd+loss+bwd per LOD, Adam kernel) vs torch autograd + torch.optim.Adam
     on the oracle, two steps, all five heads in the loss."""
     from nglod_b200.lib.trainer import FusedTrainer
     net, _ = rand5_model(DEV)
+    net.sum_lods = sum_lods
     onet = O.OracleNet(net.state_dict(), requires_grad=True)
     opt = torch.optim.Adam(onet.parameters(), lr=1e-3)
     tr = FusedTrainer(net, lr=1e-3)
