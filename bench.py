@@ -239,14 +239,8 @@ def run_ours(ns):
                  ("hit", (n_rays,), torch.bool), ("normal", (n_rays, 3), torch.float32))}
 
     def e2e_step():
-        o = ho.to(device, non_blocking=True)
-        d = hd.to(device, non_blocking=True)
-        rb = tracer(net, o, d)
-        out_host["x"].copy_(rb.x, non_blocking=True)
-        out_host["depth"].copy_(rb.depth, non_blocking=True)
-        out_host["hit"].copy_(rb.hit, non_blocking=True)
-        out_host["normal"].copy_(rb.normal, non_blocking=True)
-        torch.cuda.synchronize()
+        # the user-facing host call: pinned rays in, pinned RenderBuffer fields out, copies pipelined with the trace
+        tracer.trace_host(net, ho, hd, out=out_host)
 
     for _ in range(3):
         e2e_step()

@@ -241,18 +241,27 @@ def sdf_finitediff(view, lod, x, h=1.0 / (64.0 * 3.0)):
 
 # --------------------------------------------------------------------------- tracer
 def sphere_trace(view, lod, ray_o, ray_d, num_steps=256, step_size=1.0, min_dis=0.0003, far=10.0,
-                 normal_h=1.0 / (64.0 * 3.0), compute_normals=True, stats=None):
-    """One persistent kernel: returns x [N,3], depth [N,1], hit [N] bool, normal [N,3]."""
+                 normal_h=1.0 / (64.0 * 3.0), compute_normals=True, stats=None, out=None, queue=None):
+    """One persistent kernel: returns x [N,3], depth [N,1], hit [N] bool, normal [N,3].
+    out=(x, depth, hit, normal): caller-provided contiguous device buffers (e.g. slices of a frame buffer)."""
     lib = _lib.load()
     ray_o = _f32c(ray_o, "ray_o")
     ray_d = _f32c(ray_d, "ray_d")
     n = ray_o.shape[0]
     dev = ray_o.device
-    x = torch.empty(n, 3, device=dev, dtype=torch.float32)
-    depth = torch.empty(n, 1, device=dev, dtype=torch.float32)
-    hit = torch.empty(n, device=dev, dtype=torch.bool)
-    normal = torch.empty(n, 3, device=dev, dtype=torch.float32)
-    queue = torch.empty(1, device=dev, dtype=torch.int32)
+    if out is None:
+        x = torch.empty(n, 3, device=dev, dtype=torch.float32)
+        depth = torch.empty(n, 1, device=dev, dtype=torch.float32)
+        hit = torch.empty(n, device=dev, dtype=torch.bool)
+        normal = torch.empty(n, 3, device=dev, dtype=torch.float32)
+    else:
+        x, depth, hit, normal = out
+        for t, shape, dt in ((x, (n, 3), torch.float32), (depth, (n, 1), torch.float32), (hit, (n,), torch.bool),
+                             (normal, (n, 3), torch.float32)):
+            if tuple(t.shape) != shape or t.dtype != dt or t.device != dev or not t.is_contiguous():
+                raise RuntimeError("sphere_trace: out buffers must be contiguous device tensors x[N,3] depth[N,1] hit[N] normal[N,3]")
+    if queue is None:
+        queue = torch.empty(1, device=dev, dtype=torch.int32)
     opts = TraceOpts(int(num_steps), 1 if compute_normals else 0, float(step_size), float(min_dis), float(far),
                      float(normal_h))
     with torch.cuda.device(dev):

@@ -560,3 +560,22 @@ def test_sphere_tracer_fp16_storage_vs_oracle_on_quantized_grids(rand5, fit3):
     ng = np.abs(rb.normal.cpu().numpy() - fit3["t1_normal"]).max(axis=1)
     print(f"fp16 tracer vs reference(fp32 weights): mask mismatches {int((got != gh).sum())}, depth max {dg[both].max():.2e}, "
           f"normal max {ng[both].max():.2e} (>1e-3: {int((ng[both] > 1e-3).sum())} of {int(both.sum())})")
+
+
+def test_trace_host_pipelined_equals_forward(fit3):
+    """SphereTracer.trace_host (pinned host rays in, host RenderBuffer out, 3-stream chunk pipeline) returns exactly
+    what forward() returns on the device: rays are independent, so chunking cannot change a single bit."""
+    from nglod_b200.lib.tracer import SphereTracer
+    net3, args3 = fit3_model(fit3, DEV)
+    net3.lod = 2
+    torch.manual_seed(5)
+    o, d = O.look_at([-2.8, 2.8, -2.8], [0, 0, 0], 320, 180, fov=30.0)
+    tr = SphereTracer(args3)
+    ref = tr(net3, o.to(DEV), d.to(DEV))
+    for chunks in (1, 3, 4):
+        rb = tr.trace_host(net3, o.pin_memory(), d.pin_memory(), chunks=chunks)
+        assert not rb.x.is_cuda
+        assert torch.equal(rb.hit, ref.hit.cpu()) and torch.equal(rb.depth, ref.depth.cpu())
+        assert torch.equal(rb.x, ref.x.cpu()) and torch.equal(rb.normal, ref.normal.cpu())
+    with pytest.raises(RuntimeError):
+        tr.trace_host(net3, o.to(DEV), d.to(DEV))
