@@ -329,8 +329,10 @@ __device__ __forceinline__ void tc_gather_rows(const NetDev& net, float px, floa
 }
 
 // d = b1 + sum_j W1[j] * relu(D[row, j]) for this lane's accumulator row (TMEM lane = 32*(warp%4) + lane).
+// Four interleaved partial sums: one 128-long dependent FFMA chain is 512 cycles of pure latency per tile, which is
+// what a sparsely occupied tracer tile (the frame's straggler rays) waits for every round.
 __device__ __forceinline__ float tc_epilogue(uint32_t taddr_row, const float* __restrict__ w1) {
-    float d = w1[NGLOD_H];
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
 #pragma unroll
     for (int cb = 0; cb < NGLOD_H / 32; ++cb) {
         float v[32];
@@ -338,13 +340,13 @@ __device__ __forceinline__ float tc_epilogue(uint32_t taddr_row, const float* __
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
             const float4 w = *reinterpret_cast<const float4*>(w1 + cb * 32 + 4 * j4);
-            d = fmaf(w.x, fmaxf(v[4 * j4], 0.f), d);
-            d = fmaf(w.y, fmaxf(v[4 * j4 + 1], 0.f), d);
-            d = fmaf(w.z, fmaxf(v[4 * j4 + 2], 0.f), d);
-            d = fmaf(w.w, fmaxf(v[4 * j4 + 3], 0.f), d);
+            d0 = fmaf(w.x, fmaxf(v[4 * j4], 0.f), d0);
+            d1 = fmaf(w.y, fmaxf(v[4 * j4 + 1], 0.f), d1);
+            d2 = fmaf(w.z, fmaxf(v[4 * j4 + 2], 0.f), d2);
+            d3 = fmaf(w.w, fmaxf(v[4 * j4 + 3], 0.f), d3);
         }
     }
-    return d;
+    return w1[NGLOD_H] + ((d0 + d1) + (d2 + d3));
 }
 
 // Per-group context + one full tile evaluation: gather -> MMA -> epilogue.  All 128 threads of the group call.
@@ -358,19 +360,50 @@ struct TcGroup {
     const float* w1;
     int wq, lane, bar_id;
     uint32_t parity;
+#ifdef NGLOD_TRACE_TIMING
+    long long tm[8];                            // [0] refill [1] gather [2] group barrier [3] mma wait [4] epilogue [5] state
+    long long t_last;
+#endif
 };
 
+// OR-reduce a predicate over the 128 threads of a group (also a barrier).
+__device__ __forceinline__ bool tc_group_any(int bar_id, bool pred) {
+    uint32_t r;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+        "bar.red.or.pred p, %2, %3, q;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(r) : "r"((uint32_t)pred), "r"(bar_id), "r"(TCG_THREADS) : "memory");
+    return r != 0;
+}
+
+// Phase timing for experiments (profiles/exp_phases.sh): -DNGLOD_TRACE_TIMING makes the tracer accumulate clock64()
+// deltas per phase into its stats buffer; compiled out otherwise.
+#ifdef NGLOD_TRACE_TIMING
+#define TC_TICK(i) do { const long long _t = clock64(); g.tm[i] += _t - g.t_last; g.t_last = _t; } while (0)
+#else
+#define TC_TICK(i) do { } while (0)
+#endif
+
+// One tile evaluation: gather -> MMA -> epilogue.  All 128 threads of the group call.
+// The group barrier between "A rows written" and "MMA issued" doubles as an OR-reduction of `keep`: a persistent
+// kernel whose warps must leave together passes "I still have work"; when no thread of the group has, nothing is issued
+// and the function returns false (for every thread of the group alike).
 template <int MODE = TC_MULTI>
-__device__ __forceinline__ float tc_group_eval(const NetDev& net, TcGroup& g, float px, float py, float pz, bool active) {
+__device__ __forceinline__ bool tc_group_eval_any(const NetDev& net, TcGroup& g, float px, float py, float pz, bool active,
+                                                  bool keep, float& d) {
 #ifndef NGLOD_EXP_NO_GATHER      // timing experiments only (profiles/exp_parts.sh): results are garbage with these set
     tc_gather_rows<MODE>(net, px, py, pz, active, g.a_hi, g.a_lo, g.wq * 32, g.pack, g.idx, g.lane);
 #endif
 #ifdef NGLOD_EXP_NO_MMA
-    return px + g.w1[g.lane];
+    d = px + g.w1[g.lane];
+    return tc_group_any(g.bar_id, keep);
 #endif
     fence_proxy_async_smem();                     // generic-proxy smem writes -> visible to the tensor core
     tc_fence_before_sync();                       // order the previous tile's TMEM loads before the next MMA
-    named_bar_sync(g.bar_id, TCG_THREADS);
+    TC_TICK(1);
+    if (!tc_group_any(g.bar_id, keep)) return false;
+    TC_TICK(2);
     if (g.wq == 0 && g.lane == 0) {
         tc_fence_after_sync();
         tc_issue_tile(g.tmem_acc, g.a_hi_s, g.a_lo_s, g.b_hi_s, g.b_lo_s);
@@ -379,7 +412,17 @@ __device__ __forceinline__ float tc_group_eval(const NetDev& net, TcGroup& g, fl
     mbar_wait(g.mbar_s, g.parity);
     g.parity ^= 1u;
     tc_fence_after_sync();
-    return tc_epilogue(g.tmem_row, g.w1);
+    TC_TICK(3);
+    d = tc_epilogue(g.tmem_row, g.w1);
+    TC_TICK(4);
+    return true;
+}
+
+template <int MODE = TC_MULTI>
+__device__ __forceinline__ float tc_group_eval(const NetDev& net, TcGroup& g, float px, float py, float pz, bool active) {
+    float d = 0.f;
+    tc_group_eval_any<MODE>(net, g, px, py, pz, active, true, d);
+    return d;
 }
 
 __device__ __forceinline__ TcGroup tc_make_group(char* smem, int G, uint32_t tmem_base, int W = TC_WARP_SCRATCH_BYTES) {
@@ -437,13 +480,3 @@ __device__ __forceinline__ void tc_epilogue_free(uint32_t tmem_base) {
 }
 
 
-// OR-reduce a predicate over the 128 threads of a group (also a barrier).
-__device__ __forceinline__ bool tc_group_any(int bar_id, bool pred) {
-    uint32_t r;
-    asm volatile(
-        "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
-        "bar.red.or.pred p, %2, %3, q;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(r) : "r"((uint32_t)pred), "r"(bar_id), "r"(TCG_THREADS) : "memory");
-    return r != 0;
-}

@@ -112,6 +112,12 @@ sphere_trace_kernel(const NetDev net, const float* __restrict__ ray_o, const flo
         finish_march();
     };
 
+#ifdef NGLOD_TRACE_TIMING
+    if constexpr (TC) { for (int i = 0; i < 8; ++i) grp.tm[i] = 0; grp.t_last = clock64(); }
+#define TR_TICK(i) do { if constexpr (TC) { TcGroup& g = grp; TC_TICK(i); } } while (0)
+#else
+#define TR_TICK(i) do { } while (0)
+#endif
     for (;;) {
         // ---- refill empty slots from the global queue
 #pragma unroll 1
@@ -137,12 +143,10 @@ sphere_trace_kernel(const NetDev net, const float* __restrict__ ray_o, const flo
                 }
             }
         }
+        TR_TICK(0);
         const bool occupied = phase != PH_EMPTY;
         const unsigned act = __ballot_sync(0xffffffffu, occupied);
-        if constexpr (TC) {
-            // the 4 warps of a tile leave together: keep going while any slot is occupied or any queue is not dry
-            if (!tc_group_any(grp.bar_id, occupied || !exhausted)) break;
-        } else {
+        if constexpr (!TC) {
             if (!act) {
                 if (exhausted) break;
                 continue;
@@ -156,9 +160,14 @@ sphere_trace_kernel(const NetDev net, const float* __restrict__ ray_o, const flo
             const int axis = m >> 1;
             if (axis == 0) qx = x + e; else if (axis == 1) qy = y + e; else qz = z + e;
         }
-        float dv;
-        if constexpr (TC) dv = tc_group_eval<MODE>(net, grp, qx, qy, qz, occupied);
-        else dv = warp_sdf_eval(net, smem, tile, idx, qx, qy, qz, occupied, lane);
+        float dv = 0.f;
+        if constexpr (TC) {
+            // the 4 warps of a tile leave together: keep going while any slot is occupied or any queue is not dry
+            // (the vote rides on the barrier that precedes the MMA, so a round costs one group barrier, not two)
+            if (!tc_group_eval_any<MODE>(net, grp, qx, qy, qz, occupied, occupied || !exhausted, dv)) break;
+        } else {
+            dv = warp_sdf_eval(net, smem, tile, idx, qx, qy, qz, occupied, lane);
+        }
         const unsigned march_mask = __ballot_sync(0xffffffffu, phase == PH_MARCH);
         if (lane == 0) {
             n_eval += __popc(act);
@@ -191,10 +200,14 @@ sphere_trace_kernel(const NetDev net, const float* __restrict__ ray_o, const flo
                 }
             }
         }
+        TR_TICK(5);
     }
     if (stats && lane == 0) {
         atomicAdd(stats, n_eval);
         atomicAdd(stats + 1, n_march);
+#ifdef NGLOD_TRACE_TIMING
+        if constexpr (TC) for (int i = 0; i < 6; ++i) atomicAdd(stats + 2 + i, (unsigned long long)grp.tm[i]);
+#endif
     }
     if constexpr (TC) tc_epilogue_free(tmem_base);
 }
