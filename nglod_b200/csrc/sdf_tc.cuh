@@ -358,6 +358,7 @@ struct TcGroup {
     uint32_t tmem_acc;                          // TMEM address of the accumulator (lane 0)
     float4* pack; int* idx;
     const float* w1;
+    const char* b_hi; const char* b_lo;         // generic pointers to the staged B operand (W0|b0 = hi + lo exactly)
     int wq, lane, bar_id;
     uint32_t parity;
 #ifdef NGLOD_TRACE_TIMING
@@ -390,31 +391,43 @@ __device__ __forceinline__ bool tc_group_any(int bar_id, bool pred) {
 // kernel whose warps must leave together passes "I still have work"; when no thread of the group has, nothing is issued
 // and the function returns false (for every thread of the group alike).
 template <int MODE = TC_MULTI>
-__device__ __forceinline__ bool tc_group_eval_any(const NetDev& net, TcGroup& g, float px, float py, float pz, bool active,
-                                                  bool keep, float& d) {
+__device__ __forceinline__ bool tc_group_issue(const NetDev& net, TcGroup& g, float px, float py, float pz, bool active, bool keep) {
 #ifndef NGLOD_EXP_NO_GATHER      // timing experiments only (profiles/exp_parts.sh): results are garbage with these set
     tc_gather_rows<MODE>(net, px, py, pz, active, g.a_hi, g.a_lo, g.wq * 32, g.pack, g.idx, g.lane);
-#endif
-#ifdef NGLOD_EXP_NO_MMA
-    d = px + g.w1[g.lane];
-    return tc_group_any(g.bar_id, keep);
 #endif
     fence_proxy_async_smem();                     // generic-proxy smem writes -> visible to the tensor core
     tc_fence_before_sync();                       // order the previous tile's TMEM loads before the next MMA
     TC_TICK(1);
     if (!tc_group_any(g.bar_id, keep)) return false;
     TC_TICK(2);
+#ifndef NGLOD_EXP_NO_MMA
     if (g.wq == 0 && g.lane == 0) {
         tc_fence_after_sync();
         tc_issue_tile(g.tmem_acc, g.a_hi_s, g.a_lo_s, g.b_hi_s, g.b_lo_s);
         tc_commit(g.mbar_s);
     }
+#endif
+    return true;
+}
+// Second half of a tile evaluation: wait for the MMAs issued by tc_group_issue, read this lane's row, finish the decoder.
+// Whatever the warp does between the two halves overlaps the tensor-core latency (~1000 cycles).
+__device__ __forceinline__ float tc_group_finish(TcGroup& g, float px) {
+#ifdef NGLOD_EXP_NO_MMA
+    return px + g.w1[g.lane];
+#endif
     mbar_wait(g.mbar_s, g.parity);
     g.parity ^= 1u;
     tc_fence_after_sync();
     TC_TICK(3);
-    d = tc_epilogue(g.tmem_row, g.w1);
+    const float d = tc_epilogue(g.tmem_row, g.w1);
     TC_TICK(4);
+    return d;
+}
+template <int MODE = TC_MULTI>
+__device__ __forceinline__ bool tc_group_eval_any(const NetDev& net, TcGroup& g, float px, float py, float pz, bool active,
+                                                  bool keep, float& d) {
+    if (!tc_group_issue<MODE>(net, g, px, py, pz, active, keep)) return false;
+    d = tc_group_finish(g, px);
     return true;
 }
 
@@ -435,8 +448,10 @@ __device__ __forceinline__ TcGroup tc_make_group(char* smem, int G, uint32_t tme
     g.a_lo = g.a_hi + TC_OPERAND_BYTES;
     g.a_hi_s = smem_u32(g.a_hi);
     g.a_lo_s = smem_u32(g.a_lo);
-    g.b_hi_s = smem_u32(smem + TC_SMEM_B_HI);
-    g.b_lo_s = smem_u32(smem + TC_SMEM_B_LO);
+    g.b_hi = smem + TC_SMEM_B_HI;
+    g.b_lo = smem + TC_SMEM_B_LO;
+    g.b_hi_s = smem_u32(g.b_hi);
+    g.b_lo_s = smem_u32(g.b_lo);
     g.mbar_s = smem_u32(smem + TC_SMEM_MBAR_W(G, W) + 8 * grp);
     g.tmem_acc = tmem_base + (uint32_t)(grp * TC_N);
     g.tmem_row = g.tmem_acc + ((uint32_t)(g.wq * 32) << 16);

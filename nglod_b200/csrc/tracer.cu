@@ -112,6 +112,46 @@ sphere_trace_kernel(const NetDev net, const float* __restrict__ ray_o, const flo
         finish_march();
     };
 
+    // this round's query point of the lane's ray: its march position or one of the six normal taps
+    auto query_point = [&](float& qx, float& qy, float& qz) {
+        qx = x; qy = y; qz = z;
+        if (phase >= PH_N0) {
+            const int m = phase - PH_N0;
+            const float e = (m & 1) ? -tp.h : tp.h;
+            const int axis = m >> 1;
+            if (axis == 0) qx = x + e; else if (axis == 1) qy = y + e; else qz = z + e;
+        }
+    };
+    // consume the value of that query and advance the lane's state machine
+    auto advance = [&](float dv) {
+        if (phase == PH_INIT) {
+            d = dv; dprev = dv; step = 0;
+            march_check(true);
+        } else if (phase == PH_MARCH) {
+            d = dv * tp.step_size;
+            t = t + d;
+            ++step;
+            march_check(true);
+        } else if (phase >= PH_N0) {
+            const int m = phase - PH_N0;
+            if ((m & 1) == 0) {
+                gtmp = dv;
+                phase = phase + 1;
+            } else {
+                const float g = (gtmp - dv) / tp.two_h;
+                if (m == 1) g0 = g; else if (m == 3) g1 = g; else g2 = g;
+                if (m == 5) {
+                    // F.normalize(grad, p=2, dim=-1, eps=1e-5)
+                    const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(g0, g0), __fmul_rn(g1, g1)), __fmul_rn(g2, g2)));
+                    const float den = fmaxf(nrm, 1e-5f);
+                    retire(true, g0 / den, g1 / den, g2 / den);
+                } else {
+                    phase = phase + 1;
+                }
+            }
+        }
+    };
+
 #ifdef NGLOD_TRACE_TIMING
     if constexpr (TC) { for (int i = 0; i < 8; ++i) grp.tm[i] = 0; grp.t_last = clock64(); }
 #define TR_TICK(i) do { if constexpr (TC) { TcGroup& g = grp; TC_TICK(i); } } while (0)
@@ -151,54 +191,22 @@ sphere_trace_kernel(const NetDev net, const float* __restrict__ ray_o, const flo
                 if (exhausted) break;
                 continue;
             }
-        }
-        // ---- this round's query point
-        float qx = x, qy = y, qz = z;
-        if (phase >= PH_N0) {
-            const int m = phase - PH_N0;
-            const float e = (m & 1) ? -tp.h : tp.h;
-            const int axis = m >> 1;
-            if (axis == 0) qx = x + e; else if (axis == 1) qy = y + e; else qz = z + e;
-        }
-        float dv = 0.f;
-        if constexpr (TC) {
-            // the 4 warps of a tile leave together: keep going while any slot is occupied or any queue is not dry
-            // (the vote rides on the barrier that precedes the MMA, so a round costs one group barrier, not two)
-            if (!tc_group_eval_any<MODE>(net, grp, qx, qy, qz, occupied, occupied || !exhausted, dv)) break;
+            float qx, qy, qz;
+            query_point(qx, qy, qz);
+            const float dv = warp_sdf_eval(net, smem, tile, idx, qx, qy, qz, occupied, lane);
+            const unsigned march_mask = __ballot_sync(0xffffffffu, phase == PH_MARCH);
+            if (lane == 0) { n_eval += __popc(act); n_march += __popc(march_mask); }
+            advance(dv);
         } else {
-            dv = warp_sdf_eval(net, smem, tile, idx, qx, qy, qz, occupied, lane);
-        }
-        const unsigned march_mask = __ballot_sync(0xffffffffu, phase == PH_MARCH);
-        if (lane == 0) {
-            n_eval += __popc(act);
-            n_march += __popc(march_mask);
-        }
-        // ---- advance the state machines
-        if (phase == PH_INIT) {
-            d = dv; dprev = dv; step = 0;
-            march_check(true);
-        } else if (phase == PH_MARCH) {
-            d = dv * tp.step_size;
-            t = t + d;
-            ++step;
-            march_check(true);
-        } else if (phase >= PH_N0) {
-            const int m = phase - PH_N0;
-            if ((m & 1) == 0) {
-                gtmp = dv;
-                phase = phase + 1;
-            } else {
-                const float g = (gtmp - dv) / tp.two_h;
-                if (m == 1) g0 = g; else if (m == 3) g1 = g; else g2 = g;
-                if (m == 5) {
-                    // F.normalize(grad, p=2, dim=-1, eps=1e-5)
-                    const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(g0, g0), __fmul_rn(g1, g1)), __fmul_rn(g2, g2)));
-                    const float den = fmaxf(nrm, 1e-5f);
-                    retire(true, g0 / den, g1 / den, g2 / den);
-                } else {
-                    phase = phase + 1;
-                }
-            }
+            float qx, qy, qz;
+            query_point(qx, qy, qz);
+            const unsigned march_mask = __ballot_sync(0xffffffffu, phase == PH_MARCH);
+            if (lane == 0) { n_eval += __popc(act); n_march += __popc(march_mask); }
+            // the 4 warps of a tile leave together: the vote (a slot still occupied, or a queue not yet dry) rides on
+            // the barrier that precedes the MMA, so a round costs one group barrier
+            float dv = 0.f;
+            if (!tc_group_eval_any<MODE>(net, grp, qx, qy, qz, occupied, occupied || !exhausted, dv)) break;
+            advance(dv);
         }
         TR_TICK(5);
     }
