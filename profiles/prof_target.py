@@ -28,7 +28,7 @@ dec_grad = tuple(torch.zeros_like(p) for p in net.decoder_params(bench.LOD))
 for _ in range(3):
     ops.aabb(ray_o, ray_d)
     ops.sdf_forward(view, bench.LOD, xq)
-    ops.sdf_backward(view, bench.LOD, xq, gq, grid_grads, dec_grad)
+    ops.sdf_backward(view, bench.LOD, xq, gq, grid_grads, dec_grad, summed_scratch=net.summed_grad_scratch())
     tracer(net, ray_o, ray_d)
 torch.cuda.synchronize()
 print("done", file=sys.stderr)
