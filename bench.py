@@ -521,23 +521,6 @@ def run_reference(ns):
     """The reference's CPU path for the same metric/config: the oracle port (same ATen calls as the reference's
     PyTorch path; the reference itself is Python under /root/reference, which does not exist on the GPU box)."""
     rank = int(os.environ.get("RANK", "0"))
-    variants = {}
-    if not ns.no_extras:
-        for tag, storage, summ in (("fp16_xpair_lines", "fp16", True), ("per_lod_gather", "fp32", False)):
-            net.grid_storage, net.sum_lods = storage, summ
-            v = net.net_view()
-            f_ms = ndist.max_over_ranks(time_kernel(lambda: ops.sdf_forward(v, LOD, xq), 10), device)
-            t_ms = ndist.max_over_ranks(time_kernel(lambda: tracer(net, ray_o, ray_d), 10), device)
-            variants[tag] = {"forward_qps": world * SDF_N / (f_ms / 1e3), "forward_ms": f_ms,
-                             "trace_rays_per_s": world * n_rays / (t_ms / 1e3), "trace_ms": t_ms}
-        net.grid_storage, net.sum_lods = GRID_STORAGE, SUM_LODS
-        xbig = torch.rand(1 << 23, 3, device=device, generator=g) * 2 - 1
-        big_ms = ndist.max_over_ranks(time_kernel(lambda: ops.sdf_forward(view, LOD, xbig), 5), device)
-        variants["forward_2^23_queries"] = {"forward_qps": world * (1 << 23) / (big_ms / 1e3), "forward_ms": big_ms}
-        del xbig
-    extras = {} if ns.no_extras else run_extras(net, args, device, rank, world, flush, log)
-    if variants:
-        extras["inference_variants"] = variants
     if rank != 0:
         return
     from oracle import nglod_oracle as O
@@ -557,6 +540,7 @@ def run_reference(ns):
     opt = torch.optim.Adam(onet.parameters(), lr=1e-3)
     g = torch.Generator(device=fit_dev).manual_seed(7)
     steps, batch = (FIT_STEPS, FIT_BATCH) if fit_dev == "cuda" else (60, 8192)
+    steps = int(os.environ.get("NGLOD_REF_FIT_STEPS", steps))       # tests shrink the (untimed) set-up
     for _ in range(steps):
         p = torch.rand(batch, 3, device=fit_dev, generator=g) * 2 - 1
         surf = p[: batch // 2]
@@ -577,7 +561,7 @@ def run_reference(ns):
     torch.manual_seed(1000)
     ray_o, ray_d = O.look_at(CAM_FROM, CAM_TO, W, H, mode="persp", fov=FOV)
     total_steps = ns.steps + ns.warmup
-    budget = max(2.0, min(20.0, 150.0 / max(total_steps, 1)))
+    budget = float(os.environ.get("NGLOD_REF_BUDGET_S", max(2.0, min(20.0, 150.0 / max(total_steps, 1)))))
     rate, sample, dt = cpu_trace_rate(cpu_net, ray_o, ray_d, budget, log)
     o, d = None, None
     # timed: W warm-up + K steps of the bounded sample
@@ -612,10 +596,17 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the config 3/4/5 side measurements")
     ns = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON: libraries that write to fd 1 (NCCL prints its version banner there)
+    # are sent to stderr for the duration of the run; print() below still reaches the real stdout
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     if ns.impl == "reference":
         run_reference(ns)
     else:
         run_ours(ns)
+    sys.stdout.flush()
     if torch.distributed.is_available() and torch.distributed.is_initialized():
         torch.distributed.destroy_process_group()
 

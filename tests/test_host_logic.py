@@ -222,3 +222,20 @@ def test_shard_helpers():
     cols = sorted(c for r in range(4) for c0, c1 in interleaved_strips(1280, r, 4) for c in range(c0, c1))
     assert cols == list(range(1280))
     assert len(interleaved_strips(1280, 0, 4, strips_per_rank=4)) == 4
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) must run without a GPU and print exactly
+    one JSON line on stdout carrying the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, NGLOD_REF_FIT_STEPS="2", NGLOD_REF_BUDGET_S="0.05", CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["unit"] == "rays/s" and j["value"] > 0
+    assert j["cpu_baseline"]["kind"] == "port" and j["e2e"]["h2d_bytes_per_step"] == 0
