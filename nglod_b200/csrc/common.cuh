@@ -100,6 +100,23 @@ __device__ __forceinline__ float4 ldg_f4(const float* p) {
     return __ldg(reinterpret_cast<const float4*>(p));
 }
 
+// ---- packed fp32x2 arithmetic (sm_100a FFMA2 / FMUL2 / FADD2: two IEEE fp32 results per instruction, each lane
+//      rounded exactly like the scalar op, so results are bit-identical to the scalar code they replace)
+__device__ __forceinline__ uint64_t f2_pack(float a, float b) {
+    uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& a, float& b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+    uint64_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+    uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
 // 128-bit vector reduction (sm_90+): one L2 RED op for 4 consecutive floats.
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"

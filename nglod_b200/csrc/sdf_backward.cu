@@ -23,7 +23,9 @@ namespace {
 #define BWD_P_STRIDE (NGLOD_H + 1)                        // padded: lane q writes column j conflict-free
 #define BWD_P_FLOATS (32 * BWD_P_STRIDE)
 #define BWD_PER_WARP (SDF_SMEM_PER_WARP + BWD_P_FLOATS + 32)  // tile, idx, P, gd
-#define BWD_SMEM_BYTES ((SDF_SMEM_WARP_OFF + SDF_WARPS * BWD_PER_WARP) * 4)
+#define BWD_W2_OFF (SDF_SMEM_WARP_OFF + SDF_WARPS * BWD_PER_WARP)   // W0|b0 again, hidden units interleaved in pairs:
+                                                                   // W2[j/2][k] = {W[j][k], W[j+1][k]} (for FFMA2 over j)
+#define BWD_SMEM_BYTES ((BWD_W2_OFF + SDF_W0_FLOATS) * 4)
 #define BWD_ACC_FLOATS (SDF_W0_FLOATS + NGLOD_H + 4)       // dW0|db0 (H x 36), dW1 (H), db1
 
 struct BwdAxis {
@@ -61,18 +63,25 @@ sdf_backward_kernel(const NetDev net, const GradDev grad, const float* __restric
     float* sgd = P + BWD_P_FLOATS;
     for (int e = lane; e < BWD_PER_WARP; e += 32) wbase[e] = 0.f;
     __syncthreads();
+    for (int e = threadIdx.x; e < SDF_W0_FLOATS; e += blockDim.x) {
+        const int j = e / NGLOD_KPAD, k = e - j * NGLOD_KPAD;
+        smem[BWD_W2_OFF + ((j >> 1) * NGLOD_KPAD + k) * 2 + (j & 1)] = smem[e];
+    }
+    __syncthreads();
+    const float4* w2v = reinterpret_cast<const float4*>(smem + BWD_W2_OFF);   // [j/2][k/2] -> {W[j][k], W[j+1][k], W[j][k+1], W[j+1][k+1]}
 
     const float4* w4 = reinterpret_cast<const float4*>(smem);
     const float* sw1 = smem + SDF_SMEM_W1_OFF;
     const float sb1 = smem[SDF_SMEM_B1_OFF];
 
     // phase-C accumulators: hidden units j = lane + 32*m
-    float accW0[4][NGLOD_KPAD];
+    // (packed pairs over k: every FMA below is an FFMA2, each half rounded like the scalar fmaf it replaces)
+    uint64_t accW0[4][NGLOD_KPAD / 2];
     float accW1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int m = 0; m < 4; ++m)
 #pragma unroll
-        for (int k = 0; k < NGLOD_KPAD; ++k) accW0[m][k] = 0.f;
+        for (int k = 0; k < NGLOD_KPAD / 2; ++k) accW0[m][k] = 0ull;
     float acc_b1 = 0.f, acc_loss = 0.f;
     float w1m[4];
 #pragma unroll
@@ -100,19 +109,27 @@ sdf_backward_kernel(const NetDev net, const GradDev grad, const float* __restric
             in[4 * k4] = v.x; in[4 * k4 + 1] = v.y; in[4 * k4 + 2] = v.z; in[4 * k4 + 3] = v.w;
         }
         float gd = 0.f;
+        // pre-activations a_j = W0[j].in for two hidden units per FFMA2 (interleaved copy of W0), same k order as before
+        auto pre_pair = [&](int jp, float& a0, float& a1) {
+            uint64_t a = 0ull;
+#pragma unroll
+            for (int k2 = 0; k2 < NGLOD_KPAD / 2; ++k2) {
+                const float4 w = w2v[jp * (NGLOD_KPAD / 2) + k2];
+                a = f2_fma(f2_pack(w.x, w.y), f2_pack(in[2 * k2], in[2 * k2]), a);
+                a = f2_fma(f2_pack(w.z, w.w), f2_pack(in[2 * k2 + 1], in[2 * k2 + 1]), a);
+            }
+            f2_unpack(a, a0, a1);
+        };
         if (FUSED_LOSS) {
             float d = sb1;
 #pragma unroll 2
-            for (int j = 0; j < NGLOD_H; ++j) {
-                float a = 0.f;
-#pragma unroll
-                for (int k4 = 0; k4 < NGLOD_KPAD / 4; ++k4) {
-                    const float4 w = w4[j * (NGLOD_KPAD / 4) + k4];
-                    a = fmaf(w.x, in[4 * k4], a); a = fmaf(w.y, in[4 * k4 + 1], a);
-                    a = fmaf(w.z, in[4 * k4 + 2], a); a = fmaf(w.w, in[4 * k4 + 3], a);
-                }
-                P[lane * BWD_P_STRIDE + j] = a;
-                d = fmaf(sw1[j], fmaxf(a, 0.f), d);
+            for (int jp = 0; jp < NGLOD_H / 2; ++jp) {
+                float a0, a1;
+                pre_pair(jp, a0, a1);
+                P[lane * BWD_P_STRIDE + 2 * jp] = a0;
+                P[lane * BWD_P_STRIDE + 2 * jp + 1] = a1;
+                d = fmaf(sw1[2 * jp], fmaxf(a0, 0.f), d);
+                d = fmaf(sw1[2 * jp + 1], fmaxf(a1, 0.f), d);
             }
             if (active) {
                 const float diff = d - __ldg(gt + i);
@@ -122,40 +139,43 @@ sdf_backward_kernel(const NetDev net, const GradDev grad, const float* __restric
         } else {
             if (active) gd = __ldg(grad_out + i);
         }
-        float gin[NGLOD_KPAD - 1];
+        // g_in[k] = sum_j W0[j][k] * g_h[j], pairs over k
+        uint64_t gin2[NGLOD_F / 2];
+        float gx0 = 0.f, gx1 = 0.f, gx2 = 0.f;
 #pragma unroll
-        for (int k = 0; k < NGLOD_KPAD - 1; ++k) gin[k] = 0.f;
+        for (int k = 0; k < NGLOD_F / 2; ++k) gin2[k] = 0ull;
 #pragma unroll 2
-        for (int j = 0; j < NGLOD_H; ++j) {
-            float4 wr[NGLOD_KPAD / 4];
-#pragma unroll
-            for (int k4 = 0; k4 < NGLOD_KPAD / 4; ++k4) wr[k4] = w4[j * (NGLOD_KPAD / 4) + k4];
-            float a;
+        for (int jp = 0; jp < NGLOD_H / 2; ++jp) {
+            float apair[2];
             if (FUSED_LOSS) {
-                a = P[lane * BWD_P_STRIDE + j];
+                apair[0] = P[lane * BWD_P_STRIDE + 2 * jp];
+                apair[1] = P[lane * BWD_P_STRIDE + 2 * jp + 1];
             } else {
-                a = 0.f;
+                pre_pair(jp, apair[0], apair[1]);
+                P[lane * BWD_P_STRIDE + 2 * jp] = apair[0];
+                P[lane * BWD_P_STRIDE + 2 * jp + 1] = apair[1];
+            }
 #pragma unroll
-                for (int k4 = 0; k4 < NGLOD_KPAD / 4; ++k4) {
-                    a = fmaf(wr[k4].x, in[4 * k4], a); a = fmaf(wr[k4].y, in[4 * k4 + 1], a);
-                    a = fmaf(wr[k4].z, in[4 * k4 + 2], a); a = fmaf(wr[k4].w, in[4 * k4 + 3], a);
+            for (int jj = 0; jj < 2; ++jj) {
+                const int j = 2 * jp + jj;
+                const float gh = apair[jj] > 0.f ? gd * sw1[j] : 0.f;
+                const uint64_t gh2 = f2_pack(gh, gh);
+#pragma unroll
+                for (int k4 = 0; k4 < NGLOD_F / 4; ++k4) {
+                    const float4 wr = w4[j * (NGLOD_KPAD / 4) + k4];
+                    gin2[2 * k4] = f2_fma(f2_pack(wr.x, wr.y), gh2, gin2[2 * k4]);
+                    gin2[2 * k4 + 1] = f2_fma(f2_pack(wr.z, wr.w), gh2, gin2[2 * k4 + 1]);
                 }
-                P[lane * BWD_P_STRIDE + j] = a;
-            }
-            const float gh = a > 0.f ? gd * sw1[j] : 0.f;
-#pragma unroll
-            for (int k4 = 0; k4 < NGLOD_F / 4; ++k4) {
-                gin[4 * k4] = fmaf(wr[k4].x, gh, gin[4 * k4]);
-                gin[4 * k4 + 1] = fmaf(wr[k4].y, gh, gin[4 * k4 + 1]);
-                gin[4 * k4 + 2] = fmaf(wr[k4].z, gh, gin[4 * k4 + 2]);
-                gin[4 * k4 + 3] = fmaf(wr[k4].w, gh, gin[4 * k4 + 3]);
-            }
-            if (WITH_GX) {
-                gin[32] = fmaf(wr[8].x, gh, gin[32]);
-                gin[33] = fmaf(wr[8].y, gh, gin[33]);
-                gin[34] = fmaf(wr[8].z, gh, gin[34]);
+                if (WITH_GX) {
+                    const float4 wr = w4[j * (NGLOD_KPAD / 4) + 8];
+                    gx0 = fmaf(wr.x, gh, gx0); gx1 = fmaf(wr.y, gh, gx1); gx2 = fmaf(wr.z, gh, gx2);
+                }
             }
         }
+        float gin[NGLOD_KPAD - 1];
+#pragma unroll
+        for (int k = 0; k < NGLOD_F / 2; ++k) f2_unpack(gin2[k], gin[2 * k], gin[2 * k + 1]);
+        gin[32] = gx0; gin[33] = gx1; gin[34] = gx2;
         sgd[lane] = gd;
         acc_b1 += gd;
         __syncwarp();
@@ -174,12 +194,12 @@ sdf_backward_kernel(const NetDev net, const GradDev grad, const float* __restric
 #pragma unroll
             for (int k4 = 0; k4 < NGLOD_KPAD / 4; ++k4) {
                 const float4 v = *reinterpret_cast<const float4*>(tile + q * NGLOD_KPAD + 4 * k4);
+                const uint64_t v01 = f2_pack(v.x, v.y), v23 = f2_pack(v.z, v.w);
 #pragma unroll
                 for (int m = 0; m < 4; ++m) {
-                    accW0[m][4 * k4] = fmaf(gh[m], v.x, accW0[m][4 * k4]);
-                    accW0[m][4 * k4 + 1] = fmaf(gh[m], v.y, accW0[m][4 * k4 + 1]);
-                    accW0[m][4 * k4 + 2] = fmaf(gh[m], v.z, accW0[m][4 * k4 + 2]);
-                    accW0[m][4 * k4 + 3] = fmaf(gh[m], v.w, accW0[m][4 * k4 + 3]);
+                    const uint64_t g2 = f2_pack(gh[m], gh[m]);
+                    accW0[m][2 * k4] = f2_fma(g2, v01, accW0[m][2 * k4]);
+                    accW0[m][2 * k4 + 1] = f2_fma(g2, v23, accW0[m][2 * k4 + 1]);
                 }
             }
         }
@@ -269,7 +289,12 @@ sdf_backward_kernel(const NetDev net, const GradDev grad, const float* __restric
     for (int m = 0; m < 4; ++m) {
         const int j = lane + 32 * m;
 #pragma unroll
-        for (int k = 0; k < NGLOD_KPAD; ++k) atomicAdd(cta_acc + j * NGLOD_KPAD + k, accW0[m][k]);
+        for (int k = 0; k < NGLOD_KPAD / 2; ++k) {
+            float a0, a1;
+            f2_unpack(accW0[m][k], a0, a1);
+            atomicAdd(cta_acc + j * NGLOD_KPAD + 2 * k, a0);
+            atomicAdd(cta_acc + j * NGLOD_KPAD + 2 * k + 1, a1);
+        }
         atomicAdd(cta_acc + SDF_W0_FLOATS + j, accW1[m]);
     }
 #pragma unroll

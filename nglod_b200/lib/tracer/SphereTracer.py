@@ -36,13 +36,14 @@ class SphereTracer(BaseTracer):
             return RenderBuffer(x=x, depth=depth, hit=hit, normal=normal)
         return self._forward_generic(net, ray_o, ray_d, track_min=False)
 
-    def trace_host(self, net, ray_o, ray_d, out=None, chunks=4):
+    def trace_host(self, net, ray_o, ray_d, out=None, chunks=3, streams=2, fractions=None):
         """`forward` for rays that live in (pinned) HOST memory, results into (pinned) host memory: the frame is cut
         into `chunks` contiguous ray ranges and the host->device copy of range i+1, the trace of range i and the
         device->host copy of range i-1 run concurrently (PCIe is full duplex; the ranges are independent because
         rays are).  Consecutive ranges are traced on two alternating streams so that the next range's CTAs fill the
         SMs the previous launch leaves idle in its tail (its slowest rays): back-to-back launches on ONE stream cost
-        +40 % (measured).  Returns a RenderBuffer of CPU tensors (`out`, if given, is reused: a dict
+        +40 % (measured).  3 ranges on 2 streams measured best for a 720p frame (profiles/exp_e2e_chunks.py); `fractions`
+        gives explicit cumulative split points instead of equal ranges.  Returns a RenderBuffer of CPU tensors (`out`, if given, is reused: a dict
         with pinned x [N,3], depth [N,1], hit [N] bool, normal [N,3]).  Synchronises before returning."""
         if not (_is_octree(net) and self.grad_method == "finitediff" and getattr(net, "interpolate", None) is None):
             raise RuntimeError("trace_host: only the fused OctreeSDF tracer has a pipelined host path")
@@ -63,7 +64,7 @@ class SphereTracer(BaseTracer):
                   "hit": torch.empty(n, dtype=torch.bool, device=dev), "normal": torch.empty(n, 3, device=dev),
                   "queue": torch.empty(max(chunks, 1), dtype=torch.int32, device=dev),
                   "s_in": torch.cuda.Stream(dev), "s_out": torch.cuda.Stream(dev),
-                  "s_c": [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]}
+                  "s_c": [torch.cuda.Stream(dev) for _ in range(4)]}
             self._host_ws = ws
         if ws["queue"].numel() < chunks:
             ws["queue"] = torch.empty(chunks, dtype=torch.int32, device=dev)
@@ -74,7 +75,11 @@ class SphereTracer(BaseTracer):
         for sc in ws["s_c"]:
             sc.wait_stream(cur)
         chunks = max(1, min(chunks, n)) if n > 0 else 1
-        bounds = [(n * i) // chunks for i in range(chunks + 1)]
+        if fractions is not None:       # explicit cumulative split points in (0, 1), e.g. (0.4, 0.7, 0.9)
+            bounds = [0] + [int(n * f) for f in fractions] + [n]
+            chunks = len(bounds) - 1
+        else:
+            bounds = [(n * i) // chunks for i in range(chunks + 1)]
         ev_in = []
         with torch.cuda.stream(s_in):
             for i in range(chunks):
@@ -88,7 +93,7 @@ class SphereTracer(BaseTracer):
             a, b = bounds[i], bounds[i + 1]
             if b == a:
                 continue
-            sc = ws["s_c"][i % 2]
+            sc = ws["s_c"][i % max(1, min(streams, 4))]
             sc.wait_event(ev_in[i])
             with torch.cuda.stream(sc):
                 ops.sphere_trace(view, lod, ws["o"][a:b], ws["d"][a:b], num_steps=self.num_steps,
