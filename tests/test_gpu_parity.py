@@ -579,3 +579,40 @@ def test_trace_host_pipelined_equals_forward(fit3):
         assert torch.equal(rb.x, ref.x.cpu()) and torch.equal(rb.normal, ref.normal.cpu())
     with pytest.raises(RuntimeError):
         tr.trace_host(net3, o.to(DEV), d.to(DEV))
+
+
+# ------------------------------------------------------------------------------------------------ full-size properties
+def test_full_size_properties_2pow20(rand5):
+    """BASELINE configs[0] size (2^20 random points, lod 4), checked through size-independent properties:
+    (1) the summed-grid and the per-LOD formulations agree, and so do the tensor-core and CUDA-core decoders;
+    (2) queries are independent: evaluating two halves separately is bit-identical to one call;
+    (3) backward: db1 == sum(grad_out), and -- trilinear weights and the restriction cascade are both partitions of
+        unity -- the per-channel sum of dL/dfm_l is the same for EVERY l <= lod (it equals sum_q dL/dfeat_q)."""
+    from nglod_b200 import ops
+    net, _ = rand5_model(DEV)
+    g = torch.Generator(device=DEV).manual_seed(1)
+    n = 1 << 20
+    x = torch.rand(n, 3, device=DEV, generator=g) * 2 - 1
+    with torch.no_grad():
+        net.math_mode, net.sum_lods = "tc", True
+        a = net.sdf(x, lod=4)
+        halves = torch.cat([net.sdf(x[: n // 2 + 17], lod=4), net.sdf(x[n // 2 + 17:], lod=4)])
+        assert torch.equal(a, halves)
+        net.sum_lods = False
+        b = net.sdf(x, lod=4)
+        net.math_mode, net.sum_lods = "fp32", True
+        c = net.sdf(x, lod=4)
+        print(f"2^20: summed vs per-LOD {float((a - b).abs().max()):.2e}; tc vs fp32 decoder {float((a - c).abs().max()):.2e}")
+        assert (a - b).abs().max() < 2e-6 and (a - c).abs().max() < 5e-6
+    net.math_mode, net.sum_lods = "tc", True
+    go = torch.randn(n, 1, device=DEV, generator=g)
+    for p in net.parameters():
+        p.grad = None
+    net.sdf(x, lod=4).backward(go)
+    db1 = net.louts[4][2].bias.grad
+    assert abs(float(db1) - float(go.double().sum())) < 1e-3 * float(go.abs().sum()) ** 0.5 + 1e-2
+    sums = [net.features[l].fm.grad.double().sum(dim=(0, 2, 3, 4)) for l in range(5)]      # per channel
+    scale = float(sums[4].abs().max())
+    for l in range(4):
+        assert float((sums[l] - sums[4]).abs().max()) < 2e-4 * scale + 1e-6, (l, float((sums[l] - sums[4]).abs().max()), scale)
+    assert all(float(t.abs().max()) == 0.0 for t in net.summed_grad_scratch())
