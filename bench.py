@@ -277,7 +277,9 @@ def run_ours(ns):
     fwd_ms = time_kernel(lambda: ops.sdf_forward(view, LOD, xq), max(ns.steps, 10))
     grid_grads = [torch.zeros_like(f.fm.data, memory_format=torch.preserve_format) for f in net.features]
     dec_grad = tuple(torch.zeros_like(p) for p in net.decoder_params(LOD))
-    bwd_ms = time_kernel(lambda: ops.sdf_backward(view, LOD, xq, gq, grid_grads, dec_grad), max(ns.steps // 2, 5))
+    scratch = net.summed_grad_scratch() if view.summed is not None else None     # single-grid backward
+    bwd_ms = time_kernel(lambda: ops.sdf_backward(view, LOD, xq, gq, grid_grads, dec_grad, summed_scratch=scratch),
+                         max(ns.steps // 2, 5))
     fwd_ms = ndist.max_over_ranks(fwd_ms, device)
     bwd_ms = ndist.max_over_ranks(bwd_ms, device)
 

@@ -269,6 +269,11 @@ typedef struct nglod_sparse_net {
     const float* b0[NGLOD_MAX_LODS];
     const float* w1[NGLOD_MAX_LODS];
     const float* b1[NGLOD_MAX_LODS];
+    /* OPTIONAL [NC, feature_dim], same rows as corner_feats: the row of a LOD-l corner holds
+     *   sum_{k<=l} trilinear(corner features of the level-k ancestor voxel, position of that corner)
+     * (the sparse twin of nglod_net_t.summed: octree levels nest, so ONE 8-corner sample of the requested LOD's voxel
+     * equals the sum over its parent chain).  When given, the kernels read it and never touch `parents`. */
+    const float* corner_feats_summed;
 } nglod_sparse_net_t;
 
 /* out[i] = decoder_lod([x_i, sum_{l<=lod} trilinear(corner features of the voxel chain of pidx_i)]).

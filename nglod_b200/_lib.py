@@ -61,6 +61,7 @@ class SparseNetStruct(ctypes.Structure):
         ("b0", c_void_p * MAX_LODS),
         ("w1", c_void_p * MAX_LODS),
         ("b1", c_void_p * MAX_LODS),
+        ("corner_feats_summed", c_void_p),
     ]
 
 

@@ -19,6 +19,7 @@ struct SparseDev {
     const int* parents;
     const short4* voxels;
     int lod;                    // LOD being evaluated
+    int first_lod;              // first level to sample: 0 (walk the parent chain) or lod (cf = prefix-summed rows)
     int base_lod;
     int vox_off;                // first voxel row of `lod`
 };
@@ -30,9 +31,9 @@ __device__ __forceinline__ float4 sparse_gather4(const SparseDev& sn, float qx, 
         int v = vrow;
 #pragma unroll
         for (int l = NGLOD_MAX_LODS - 1; l >= 0; --l) {
-            if (l > sn.lod) continue;
+            if (l > sn.lod || l < sn.first_lod) continue;
             chain[l] = v;
-            if (l > 0) v = __ldg(sn.parents + v);
+            if (l > sn.first_lod) v = __ldg(sn.parents + v);
         }
     }
     const float nx = fmaf(qx, 0.5f, 0.5f), ny = fmaf(qy, 0.5f, 0.5f), nz = fmaf(qz, 0.5f, 0.5f);
@@ -40,6 +41,7 @@ __device__ __forceinline__ float4 sparse_gather4(const SparseDev& sn, float qx, 
 #pragma unroll
     for (int l = 0; l < NGLOD_MAX_LODS; ++l) {
         if (l > sn.lod) break;
+        if (l < sn.first_lod) continue;
         const int v = chain[l];
         const float res = (float)(1 << (l + sn.base_lod));
         const short4 vc = __ldg(sn.voxels + v);
@@ -350,7 +352,10 @@ int make_sparse_dev(const nglod_sparse_net_t* net, int lod, SparseDev& sn) {
     sn.dec.num_lods = 0; sn.dec.pos_invariant = 0; sn.dec.half_pairs = 0;
     for (int i = 0; i < NGLOD_MAX_LODS; ++i) { sn.dec.res[i] = 1; sn.dec.grids[i] = nullptr; }
     sn.dec.w0 = net->w0[lod]; sn.dec.b0 = net->b0[lod]; sn.dec.w1 = net->w1[lod]; sn.dec.b1 = net->b1[lod];
-    sn.cf = net->corner_feats; sn.trinkets = net->trinkets; sn.parents = net->parents;
+    if (reinterpret_cast<uintptr_t>(net->corner_feats_summed) & 15u) return NGLOD_EINVAL;
+    sn.cf = net->corner_feats_summed ? net->corner_feats_summed : net->corner_feats;
+    sn.first_lod = net->corner_feats_summed ? lod : 0;
+    sn.trinkets = net->trinkets; sn.parents = net->parents;
     sn.voxels = reinterpret_cast<const short4*>(net->voxels);
     sn.lod = lod; sn.base_lod = net->base_lod; sn.vox_off = net->lod_voxel_offset[lod];
     return 0;

@@ -206,7 +206,11 @@ class SparseOctreeSDF:
         if spc.level < self.num_lods + self.base_lod - 1:
             raise ValueError("octree is shallower than the finest LOD")
         dev = spc.octree.device
-        feats, trinkets, parents, voxels, lod_offset = [], [], [], [], [0]
+        feats, feats_summed, trinkets, parents, voxels, lod_offset = [], [], [], [], [], [0]
+        # prefix-summed corner rows (nglod_sparse_net_t.corner_feats_summed): the dense model's summed grids sampled at
+        # the same corners, so one 8-corner sample of the requested LOD's voxel replaces the walk up the parent chain
+        self.sum_lods = bool(getattr(net, "sum_lods", True)) and net._grids_nest() and dev.type == "cuda"
+        summed = net._derived_grids()[0] if self.sum_lods else None
         corner_base = 0
         prev_morton = None
         for l in range(self.num_lods):
@@ -220,6 +224,8 @@ class SparseOctreeSDF:
             cz, cy, cx = uniq // (S * S), (uniq // S) % S, uniq % S
             fm = net.features[l].fm.data                                      # [1, F, D, H, W]
             feats.append(fm[0][:, cz, cy, cx].t().contiguous())
+            if summed is not None:
+                feats_summed.append(summed[l][0][:, cz, cy, cx].t().contiguous())
             trinkets.append((inv.reshape(-1, 8) + corner_base).int())
             morton = points_to_morton(vox)
             if l == 0:
@@ -234,6 +240,7 @@ class SparseOctreeSDF:
             corner_base += uniq.shape[0]
             lod_offset.append(lod_offset[-1] + vox.shape[0])
         self.corner_feats = torch.cat(feats).contiguous()
+        self.corner_feats_summed = torch.cat(feats_summed).contiguous() if summed is not None else None
         self.trinkets = torch.cat(trinkets).contiguous()
         self.parents = torch.cat(parents).contiguous()
         self.voxels = torch.cat(voxels).contiguous()
@@ -276,6 +283,8 @@ class SparseOctreeSDF:
         s.math_mode = _lib.MATH_TC3XTF32 if self.math_mode == "tc" else _lib.MATH_FP32
         s.corner_feats, s.trinkets = self.corner_feats.data_ptr(), self.trinkets.data_ptr()
         s.parents, s.voxels = self.parents.data_ptr(), self.voxels.data_ptr()
+        if self.sum_lods and self.corner_feats_summed is not None:
+            s.corner_feats_summed = self.corner_feats_summed.data_ptr()
         for i, o in enumerate(self.lod_offset):
             s.lod_voxel_offset[i] = o
         self._keep = [tuple(p.data for p in self.net.decoder_params(i)) for i in range(self.num_lods)]

@@ -202,10 +202,14 @@ def test_oracle_sparse_equals_dense_inside_voxels(fit3):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("math_mode", ["fp32", "tc"])
-def test_sparse_sdf_kernel_vs_dense_and_oracle(fit3, math_mode):
+@pytest.mark.parametrize("math_mode,sum_lods", [("fp32", True), ("tc", True), ("tc", False)])
+def test_sparse_sdf_kernel_vs_dense_and_oracle(fit3, math_mode, sum_lods):
+    """sum_lods=True: the kernels read the prefix-summed corner rows and sample only the requested LOD's voxel;
+    False: they walk the parent chain like the reference.  Same oracle (which walks the chain), same tolerance."""
     net, args, spc, sp = _fit3_sparse(fit3, "cuda")
     net.math_mode = sp.math_mode = math_mode
+    assert sp.corner_feats_summed is not None
+    sp.sum_lods = sum_lods
     osn = O.OracleSparseNet(sp.corner_feats, sp.trinkets, sp.parents, sp.voxels, sp.lod_offset, sp.base_lod,
                             [net.decoder_params(i) for i in range(3)])
     for lod, count in ((2, 50001), (1, 1000), (0, 33)):
