@@ -19,6 +19,19 @@ __global__ void __launch_bounds__(fwd_groups(MODE) * TCG_THREADS, 1)
 sdf_forward_tc_kernel(const NetDev net, const float* __restrict__ x, const long long n, float* __restrict__ out) {
     extern __shared__ __align__(128) char smem_tc[];
     constexpr int G = fwd_groups(MODE), W = tc_mode_scratch(MODE);
+    if constexpr (MODE != TC_MULTI) {
+        // A big batch touches every line of the grid many times, but after a cold start (new weights / flushed L2) the
+        // first tiles would fetch their lines from DRAM one dependent round at a time (~10 us before the L2 is warm):
+        // stream the grid into L2 at HBM speed while the prologue stages the weights.
+        if (n >= (1ll << 17)) {
+            const long long S = net.res[0] + 1;
+            const long long bytes = MODE == TC_SINGLE_HALF ? S * S * net.res[0] * 128 : S * S * S * NGLOD_F * 4;
+            const char* base = reinterpret_cast<const char*>(net.grids[0]);
+            for (long long off = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 128; off < bytes;
+                 off += (long long)gridDim.x * blockDim.x * 128)
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(base + off));
+        }
+    }
     const uint32_t tmem_base = tc_prologue(net, smem_tc, G, W);
     TcGroup g = tc_make_group(smem_tc, G, tmem_base, W);
     const long long ggroup = (long long)blockIdx.x * G + (threadIdx.x >> 7);
