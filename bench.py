@@ -476,6 +476,16 @@ def run_extras(net, args, device, rank, world, flush, log):
     out["render_4k_shadow"] = {"rays": w4 * h4, "rays_this_rank": s1 - s0, "ms": r4_ms, "fps": 1e3 / r4_ms,
                                "note": "primary trace + ground plane + shadow trace + normals via Renderer.render; "
                                        "ranks take contiguous column strips, no collective"}
+    # ---- the headless real-time loop (ray generation -> trace -> matcap shading, frame stays on the device)
+    from nglod_b200.app import realtime
+    rt = {}
+    for tag, kw in (("dense_1080p_lod4", dict(lod=LOD)), ("sparse_level6_1080p_lod4", dict(lod=LOD, spc_level=6))):
+        r = realtime.run(net, 1920, 1080, frames=24, **kw)
+        steady = r["ms"][3:]
+        rt[tag] = {"ms_per_frame": ndist.max_over_ranks(float(np.mean(steady)), device), "fps": 1e3 / float(np.mean(steady)),
+                   "hit_pixels_last_frame": int(r["hit"].sum())}
+    out["realtime_loop"] = dict(rt, note="app/realtime.py: orbiting camera, nglod_generate_rays -> tracer -> "
+                                         "nglod_shade_matcap into a device RGB buffer; CUDA-event time per frame, no L2 flush")
     log(f"extras: train {step_ms:.2f} ms/500k-pt step, sample+label {sample_ms:.1f} ms, spc 1080p {trav_ms:.2f} ms, "
         f"4K+shadow {r4_ms:.1f} ms")
     return out

@@ -616,3 +616,31 @@ def test_full_size_properties_2pow20(rand5):
     for l in range(4):
         assert float((sums[l] - sums[4]).abs().max()) < 2e-4 * scale + 1e-6, (l, float((sums[l] - sums[4]).abs().max()), scale)
     assert all(float(t.abs().max()) == 0.0 for t in net.summed_grad_scratch())
+
+
+def test_realtime_loop_dense_and_sparse(fit3):
+    """The headless display() loop (app/realtime.py): frame 0 uses the reference's default camera, so its hit mask must
+    equal SphereTracer.forward on look_at rays with the same jittered window; the sparse mode must see the same object."""
+    from nglod_b200.app import realtime
+    from nglod_b200.lib.tracer import SphereTracer
+    net3, args3 = fit3_model(fit3, DEV)
+    torch.manual_seed(3)
+    out = realtime.run(net3, 160, 90, frames=4, lod=2)
+    assert len(out["ms"]) == 4 and out["rgb"].shape == (160 * 90, 3) and out["fps"] > 0
+    torch.manual_seed(3)
+    one = realtime.run(net3, 160, 90, frames=1, lod=2)
+    torch.manual_seed(3)
+    from nglod_b200.lib.geoutils import look_at
+    o, d = look_at([-2.8, 2.8, -2.8], [0, 0, 0], 160, 90, mode="persp", fov=30.0, device=DEV)
+    net3.lod = 2
+    ref = SphereTracer(args3)(net3, o, d)
+    assert int((one["hit"] != ref.hit).sum()) <= 2          # eye = radius*(cos, sin) of 225 deg vs the literal (-2.8, -2.8)
+    assert int(ref.hit.sum()) > 300
+    rgb = one["rgb"]
+    assert float(rgb.min()) >= 0.0 and float(rgb.max()) <= 1.0 + 1e-6
+    assert bool((rgb[~one["hit"]] == 1.0).all())
+    torch.manual_seed(3)
+    sp = realtime.run(net3, 160, 90, frames=2, lod=2, spc_level=4)
+    assert "sparse" in sp["mode"]
+    inter = int((sp["hit"] & out["hit"]).sum()) if sp["hit"].shape == out["hit"].shape else 0
+    assert int(sp["hit"].sum()) > 300
