@@ -2,10 +2,14 @@
 //
 // A "group" is 4 consecutive warps (128 threads) that own one 128-row MMA tile: every lane owns one query = one
 // A row = one TMEM lane.  Per tile:
-//   1. tc_gather_rows   features (8 lanes per corner line, per-LOD set-up computed ONCE per query and shared through
-//                       a 16-byte smem record) -> split hi/lo TF32 -> A_hi / A_lo rows in the UMMA smem layout
-//   2. fence.proxy.async + group barrier; one thread issues 15 tcgen05.mma (3xTF32) + tcgen05.commit -> mbarrier
+//   1. tc_gather_rows   features, 8 lanes per 128-byte line, FFMA2 interpolation -> split hi/lo TF32 -> A_hi / A_lo rows
+//                       in the UMMA smem layout.  Three kernel flavours (TC_MULTI / TC_SINGLE_F32 / TC_SINGLE_HALF):
+//                       per-LOD fp32 grids (set-up records staged in smem once per query), or ONE prefix-summed grid
+//                       in fp32 corner lines or fp16 x-pair lines (set-up records travel by warp shuffle, no scratch)
+//   2. fence.proxy.async + group barrier (bar.red.or: doubles as the "anyone still working?" vote of the persistent
+//      tracer); one thread issues 15 tcgen05.mma (3xTF32) + tcgen05.commit -> mbarrier            [tc_group_issue]
 //   3. tc_epilogue      each lane reads its 128 accumulator columns from TMEM, d = b1 + sum_j W1[j]*relu(D[j])
+//                                                                                                  [tc_group_finish]
 #pragma once
 #include "common.cuh"
 #include "tc_common.cuh"
