@@ -17,6 +17,7 @@
 //      corner (a full 128-byte line per corner per query), for every LOD <= lod;
 //      optional dL/dx with PyTorch's border-clip rule.
 #include "sdf_core.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -327,6 +328,270 @@ sdf_backward_kernel(const NetDev net, const GradDev grad, const float* __restric
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Backward, second generation (no dL/dx): 16 warps per CTA, head gradients on the tensor cores.
+//
+// The first-generation kernel above keeps dW0|db0 as 144 register accumulators per lane (255 registers -> 8 warps per
+// SM, latency-bound at 39 % issue).  Here the only state a query leaves behind for the head gradients is its upstream
+// gradient g_d and the 128 ReLU mask bits:
+//     T[h][k]  = sum_q g_d(q) [pre_qh > 0] in_qk           (k = 0..35, in_q35 = 1)       <- one GEMM over the queries
+//     dW0[h][k] = w1[h] T[h][k],  db0[h] = w1[h] T[h][35],  dW1[h] = sum_k W0ext[h][k] T[h][k]   (pre = W0ext . in)
+// and T is accumulated CTA-wide with mma.sync.m16n8k8 TF32 (rna-rounded operands, fp32 accumulate): warp w owns hidden
+// units [16 (w%8), +16) and the queries of warps [8 (w/8), +8) of the batch -> 20 accumulator registers.  The rest
+// (forward recompute with FFMA2 pairs, dL/d(features), scatter) is the first generation's code; with ~110 registers
+// 16 warps fit, which is what the CUDA-core part needed.
+#define BW2_WARPS 16
+#define BW2_THREADS (BW2_WARPS * 32)
+#define BW2_PER_WARP (SDF_SMEM_PER_WARP + 32 * 4 + 32)           // tile, idx, mask words [32][4], gd[32]
+#define BW2_W2_OFF (SDF_SMEM_WARP_OFF + BW2_WARPS * BW2_PER_WARP)
+#define BW2_SMEM_BYTES ((BW2_W2_OFF + SDF_W0_FLOATS) * 4)
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r;
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <bool FUSED_LOSS>
+__global__ void __launch_bounds__(BW2_THREADS, 1)
+sdf_backward_mma_kernel(const NetDev net, const GradDev grad, const float* __restrict__ x, const long long n,
+                        const float* __restrict__ grad_out, const float* __restrict__ gt, const float loss_scale,
+                        float* __restrict__ loss_out) {
+    extern __shared__ __align__(16) float smem[];
+    sdf_stage_weights(net, smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* wbase = smem + SDF_SMEM_WARP_OFF + warp * BW2_PER_WARP;
+    float* tile = wbase;
+    int* idx = reinterpret_cast<int*>(wbase + SDF_TILE_FLOATS);
+    uint32_t* maskw = reinterpret_cast<uint32_t*>(wbase + SDF_SMEM_PER_WARP);
+    float* sgd = wbase + SDF_SMEM_PER_WARP + 32 * 4;
+    for (int e = lane; e < BW2_PER_WARP; e += 32) wbase[e] = 0.f;
+    __syncthreads();
+    for (int e = threadIdx.x; e < SDF_W0_FLOATS; e += blockDim.x) {
+        const int j = e / NGLOD_KPAD, k = e - j * NGLOD_KPAD;
+        smem[BW2_W2_OFF + ((j >> 1) * NGLOD_KPAD + k) * 2 + (j & 1)] = smem[e];
+    }
+    __syncthreads();
+    const float4* w4 = reinterpret_cast<const float4*>(smem);
+    const float4* w2v = reinterpret_cast<const float4*>(smem + BW2_W2_OFF);
+    const float* sw1 = smem + SDF_SMEM_W1_OFF;
+    const float sb1 = smem[SDF_SMEM_B1_OFF];
+
+    // phase-C ownership: hidden units [16 mt, 16 mt + 16), queries of warps [8 qh, 8 qh + 8) of every CTA batch
+    const int mt = warp & 7, qh = warp >> 3;
+    const int g = lane >> 2, t = lane & 3;
+    float accT[5][4];
+#pragma unroll
+    for (int nt = 0; nt < 5; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) accT[nt][i] = 0.f;
+    float acc_b1 = 0.f, acc_loss = 0.f;
+
+    const long long batch = (long long)BW2_THREADS;
+    for (long long base0 = (long long)blockIdx.x * batch; base0 < n; base0 += (long long)gridDim.x * batch) {
+        const long long i = base0 + warp * 32 + lane;
+        const bool active = i < n;
+        float px = 0.f, py = 0.f, pz = 0.f;
+        if (active) { px = __ldg(x + 3 * i); py = __ldg(x + 3 * i + 1); pz = __ldg(x + 3 * i + 2); }
+        // ---- A: gather
+        warp_gather_tile(net, px, py, pz, active, tile, idx, lane);
+        if (!active) {   // keep inactive rows finite and inert
+#pragma unroll
+            for (int k4 = 0; k4 < NGLOD_KPAD / 4; ++k4)
+                *reinterpret_cast<float4*>(tile + lane * NGLOD_KPAD + 4 * k4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        // ---- B: thread-per-query: pre-activations (two hidden units per FFMA2), d, g_d, ReLU mask bits
+        float in[NGLOD_KPAD];
+#pragma unroll
+        for (int k4 = 0; k4 < NGLOD_KPAD / 4; ++k4) {
+            const float4 v = *reinterpret_cast<const float4*>(tile + lane * NGLOD_KPAD + 4 * k4);
+            in[4 * k4] = v.x; in[4 * k4 + 1] = v.y; in[4 * k4 + 2] = v.z; in[4 * k4 + 3] = v.w;
+        }
+        uint32_t mbits[4] = {0u, 0u, 0u, 0u};
+        float d = sb1;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+#pragma unroll 2
+            for (int jq = 0; jq < 16; ++jq) {
+                const int jp = w * 16 + jq;
+                uint64_t a = 0ull;
+#pragma unroll
+                for (int k2 = 0; k2 < NGLOD_KPAD / 2; ++k2) {
+                    const float4 wv = w2v[jp * (NGLOD_KPAD / 2) + k2];
+                    a = f2_fma(f2_pack(wv.x, wv.y), f2_pack(in[2 * k2], in[2 * k2]), a);
+                    a = f2_fma(f2_pack(wv.z, wv.w), f2_pack(in[2 * k2 + 1], in[2 * k2 + 1]), a);
+                }
+                float a0, a1;
+                f2_unpack(a, a0, a1);
+                if (FUSED_LOSS) {
+                    d = fmaf(sw1[2 * jp], fmaxf(a0, 0.f), d);
+                    d = fmaf(sw1[2 * jp + 1], fmaxf(a1, 0.f), d);
+                }
+                mbits[w] |= (a0 > 0.f ? 1u : 0u) << (2 * jq);
+                mbits[w] |= (a1 > 0.f ? 1u : 0u) << (2 * jq + 1);
+            }
+        }
+        float gd = 0.f;
+        if (active) {
+            if (FUSED_LOSS) {
+                const float diff = d - __ldg(gt + i);
+                acc_loss = fmaf(diff * diff, loss_scale, acc_loss);
+                gd = 2.f * diff * loss_scale;
+            } else {
+                gd = __ldg(grad_out + i);
+            }
+        }
+        acc_b1 += gd;
+        // g_in[k] = sum_j W0[j][k] * g_h[j], pairs over k
+        uint64_t gin2[NGLOD_F / 2];
+#pragma unroll
+        for (int k = 0; k < NGLOD_F / 2; ++k) gin2[k] = 0ull;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+#pragma unroll 4
+            for (int jb = 0; jb < 32; ++jb) {
+                const int j = w * 32 + jb;
+                const float gh = ((mbits[w] >> jb) & 1u) ? gd * sw1[j] : 0.f;
+                const uint64_t gh2 = f2_pack(gh, gh);
+#pragma unroll
+                for (int k4 = 0; k4 < NGLOD_F / 4; ++k4) {
+                    const float4 wr = w4[j * (NGLOD_KPAD / 4) + k4];
+                    gin2[2 * k4] = f2_fma(f2_pack(wr.x, wr.y), gh2, gin2[2 * k4]);
+                    gin2[2 * k4 + 1] = f2_fma(f2_pack(wr.z, wr.w), gh2, gin2[2 * k4 + 1]);
+                }
+            }
+        }
+        *reinterpret_cast<uint4*>(maskw + lane * 4) = make_uint4(mbits[0], mbits[1], mbits[2], mbits[3]);
+        sgd[lane] = gd;
+        __syncthreads();
+        // ---- C: T[h][k] += sum_q g_d(q) mask(q,h) in(q,k) on the tensor cores
+#pragma unroll 2
+        for (int ks = 0; ks < 32; ++ks) {
+            const int wq = qh * 8 + (ks >> 2);                        // warp that owns these 8 queries
+            const int r0 = (ks & 3) * 8;                              // their first row in that warp's tile
+            const float* wb = smem + SDF_SMEM_WARP_OFF + wq * BW2_PER_WARP;
+            const uint32_t* mq = reinterpret_cast<const uint32_t*>(wb + SDF_SMEM_PER_WARP);
+            const float* gq = wb + SDF_SMEM_PER_WARP + 32 * 4;
+            const float gd0 = gq[r0 + t], gd1 = gq[r0 + t + 4];
+            const uint32_t m0 = mq[(r0 + t) * 4 + (mt >> 1)] >> ((mt & 1) * 16);
+            const uint32_t m1 = mq[(r0 + t + 4) * 4 + (mt >> 1)] >> ((mt & 1) * 16);
+            uint32_t a[4];
+            a[0] = to_tf32(((m0 >> g) & 1u) ? gd0 : 0.f);
+            a[1] = to_tf32(((m0 >> (g + 8)) & 1u) ? gd0 : 0.f);
+            a[2] = to_tf32(((m1 >> g) & 1u) ? gd1 : 0.f);
+            a[3] = to_tf32(((m1 >> (g + 8)) & 1u) ? gd1 : 0.f);
+            if (!__any_sync(0xffffffffu, (gd0 != 0.f) | (gd1 != 0.f))) continue;       // 8 inert queries (warp-uniform)
+#pragma unroll
+            for (int nt = 0; nt < 5; ++nt) {
+                uint32_t b[2];
+                const int k = 8 * nt + g;
+                const bool ok = k < NGLOD_KPAD;
+                b[0] = to_tf32(ok ? wb[(r0 + t) * NGLOD_KPAD + k] : 0.f);
+                b[1] = to_tf32(ok ? wb[(r0 + t + 4) * NGLOD_KPAD + k] : 0.f);
+                mma_tf32_16x8x8(accT[nt], a, b);
+            }
+        }
+        __syncthreads();
+        // ---- D: scatter g_feat into the grids
+#pragma unroll
+        for (int k4 = 0; k4 < NGLOD_F / 4; ++k4) {
+            float4 v;
+            f2_unpack(gin2[2 * k4], v.x, v.y);
+            f2_unpack(gin2[2 * k4 + 1], v.z, v.w);
+            *reinterpret_cast<float4*>(tile + lane * NGLOD_KPAD + 4 * k4) = v;
+        }
+        __syncwarp();
+        {
+            const unsigned live = __ballot_sync(0xffffffffu, active);
+            const int n_live = __popc(live);
+            const int sub = lane >> 3, c = lane & 7;
+            for (int r = 0; r * 4 < n_live; ++r) {
+                const int slot = r * 4 + sub;
+                const bool valid = slot < n_live;
+                const int q = idx[valid ? slot : 0];
+                const float qx = __shfl_sync(0xffffffffu, px, q);
+                const float qy = __shfl_sync(0xffffffffu, py, q);
+                const float qz = __shfl_sync(0xffffffffu, pz, q);
+                if (valid) {
+                    const float4 gq4 = *reinterpret_cast<const float4*>(tile + q * NGLOD_KPAD + 4 * c);
+#pragma unroll
+                    for (int l = 0; l < NGLOD_MAX_LODS; ++l) {
+                        if (l >= net.num_lods) break;
+                        const int R = net.res[l], S = R + 1;
+                        const BwdAxis ax = bwd_axis(qx, R), ay = bwd_axis(qy, R), az = bwd_axis(qz, R);
+                        float* gg = grad.grids[l];
+                        if (!gg) continue;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const int ix = (k & 1) ? ax.i1 : ax.i0;
+                            const int iy = (k & 2) ? ay.i1 : ay.i0;
+                            const int iz = (k & 4) ? az.i1 : az.i0;
+                            const float wx = (k & 1) ? ax.w1 : ax.w0;
+                            const float wy = (k & 2) ? ay.w1 : ay.w0;
+                            const float wz = (k & 4) ? az.w1 : az.w0;
+                            const int off = ((iz * S + iy) * S + ix) * NGLOD_F + 4 * c;
+                            const float w = (wx * wy) * wz;
+                            red_add_v4(gg + off, gq4.x * w, gq4.y * w, gq4.z * w, gq4.w * w);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();      // tiles / masks are rewritten by the next batch
+    }
+
+    // ---- flush: T fragments -> CTA accumulator in smem -> head gradients -> one RED per CTA per element
+    __syncthreads();
+    float* cta_T = smem + SDF_SMEM_WARP_OFF;             // [128][40] (per-warp regions are dead now), then db1, loss
+    for (int e = threadIdx.x; e < NGLOD_H * 40 + 4; e += blockDim.x) cta_T[e] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int nt = 0; nt < 5; ++nt) {
+        const int h = 16 * mt + g, k = 8 * nt + 2 * t;
+        atomicAdd(cta_T + h * 40 + k, accT[nt][0]);
+        atomicAdd(cta_T + h * 40 + k + 1, accT[nt][1]);
+        atomicAdd(cta_T + (h + 8) * 40 + k, accT[nt][2]);
+        atomicAdd(cta_T + (h + 8) * 40 + k + 1, accT[nt][3]);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        acc_b1 += __shfl_xor_sync(0xffffffffu, acc_b1, o);
+        acc_loss += __shfl_xor_sync(0xffffffffu, acc_loss, o);
+    }
+    if (lane == 0) {
+        atomicAdd(cta_T + NGLOD_H * 40, acc_b1);
+        atomicAdd(cta_T + NGLOD_H * 40 + 1, acc_loss);
+    }
+    __syncthreads();
+    const int in_dim = net.pos_invariant ? NGLOD_F : NGLOD_F + 3;
+    if (threadIdx.x < NGLOD_H) {
+        const int h = threadIdx.x;
+        const float w1h = sw1[h];
+        float dw1 = 0.f;
+#pragma unroll 4
+        for (int k = 0; k < NGLOD_KPAD; ++k) {
+            const float tv = cta_T[h * 40 + k];
+            dw1 = fmaf(smem[h * NGLOD_KPAD + k], tv, dw1);           // staged W0ext row: {32 feat, x, y, z, b0}
+            const float v = w1h * tv;
+            if (k < NGLOD_F) {
+                if (grad.w0) atomicAdd(grad.w0 + h * in_dim + (net.pos_invariant ? k : k + 3), v);
+            } else if (k < NGLOD_F + 3) {
+                if (grad.w0 && !net.pos_invariant) atomicAdd(grad.w0 + h * in_dim + (k - NGLOD_F), v);
+            } else {
+                if (grad.b0) atomicAdd(grad.b0 + h, v);
+            }
+        }
+        if (grad.w1) atomicAdd(grad.w1 + h, dw1);
+    }
+    if (threadIdx.x == 0) {
+        if (grad.b1) atomicAdd(grad.b1, cta_T[NGLOD_H * 40]);
+        if (FUSED_LOSS && loss_out) atomicAdd(loss_out, cta_T[NGLOD_H * 40 + 1]);
+    }
+}
+
 // ---- transpose of the prefix sum: push dL/d(summed grid of level l) down to the LOD grids, level by level.
 // restrict: Tc[c] += sum over fine nodes n in the support of coarse node c's hat function of  w(n, c) * Tf[n],
 //           w = prod_axis (1 - |n_a - k c_a| / k), k = Rf / Rc  -- the weights nglod_build_summed_grid used, transposed.
@@ -413,8 +678,6 @@ template <bool FUSED_LOSS, bool WITH_GX>
 int launch_backward(const nglod_net_t* net, int lod, const nglod_net_grad_t* grad, const float* x, int64_t n,
                     const float* grad_out, const float* gt, float loss_scale, float* grad_x, float* loss_out,
                     cudaStream_t st, bool cascade = true) {
-    auto kern = sdf_backward_kernel<FUSED_LOSS, WITH_GX>;
-    NGLOD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM_BYTES));
     const bool single = use_summed_backward(net, lod, grad);
     const NetDev nd = single ? nglod_make_netdev_infer(net, lod, /*allow_half=*/false) : nglod_make_netdev(net, lod);
     GradDev gdv;
@@ -425,6 +688,21 @@ int launch_backward(const nglod_net_t* net, int lod, const nglod_net_grad_t* gra
     gdv.w1 = grad ? grad->w1[lod] : nullptr;
     gdv.b1 = grad ? grad->b1[lod] : nullptr;
     long long grid = nglod_sm_count();
+    if constexpr (!WITH_GX) {
+        // second-generation kernel: 16 warps, head gradients on the tensor cores (NGLOD_BWD_GEN1=1 keeps the first)
+        static const bool gen1 = getenv("NGLOD_BWD_GEN1") != nullptr;
+        if (!gen1) {
+            auto k2 = sdf_backward_mma_kernel<FUSED_LOSS>;
+            NGLOD_CUDA_TRY(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, BW2_SMEM_BYTES));
+            const long long want2 = (n + BW2_THREADS - 1) / BW2_THREADS;
+            if (want2 < grid) grid = want2;
+            k2<<<(int)grid, BW2_THREADS, BW2_SMEM_BYTES, st>>>(nd, gdv, x, (long long)n, grad_out, gt, loss_scale, loss_out);
+            if (int e = (int)cudaGetLastError()) return e;
+            return (single && cascade) ? restrict_cascade(net, lod, grad, st) : 0;
+        }
+    }
+    auto kern = sdf_backward_kernel<FUSED_LOSS, WITH_GX>;
+    NGLOD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM_BYTES));
     const long long want = (n + SDF_THREADS - 1) / SDF_THREADS;
     if (want < grid) grid = want;
     kern<<<(int)grid, SDF_THREADS, BWD_SMEM_BYTES, st>>>(nd, gdv, x, (long long)n, grad_out, gt, loss_scale, grad_x,
