@@ -337,14 +337,15 @@ sdf_backward_kernel(const NetDev net, const GradDev grad, const float* __restric
 //     T[h][k]  = sum_q g_d(q) [pre_qh > 0] in_qk           (k = 0..35, in_q35 = 1)       <- one GEMM over the queries
 //     dW0[h][k] = w1[h] T[h][k],  db0[h] = w1[h] T[h][35],  dW1[h] = sum_k W0ext[h][k] T[h][k]   (pre = W0ext . in)
 // and T is accumulated CTA-wide with mma.sync.m16n8k8 TF32 (rna-rounded operands, fp32 accumulate): warp w owns hidden
-// units [16 (w%8), +16) and the queries of warps [8 (w/8), +8) of the batch -> 20 accumulator registers.  The rest
-// (forward recompute with FFMA2 pairs, dL/d(features), scatter) is the first generation's code; with ~110 registers
-// 16 warps fit, which is what the CUDA-core part needed.
+// units [16 (w%8), +16) and the queries of warps [8 (w/8), +8) of the batch -> 20 accumulator registers.  The two
+// per-query GEMMs run on mma.sync as well, 16 queries at a time per warp: the forward recompute pre = in . W0ext^T in
+// 3xTF32 (d feeds the loss gradient, so it keeps fp32-level accuracy), dL/d(features) = g_h . W0 likewise (its terms cancel heavily),
+// with its A fragments built in registers from the mask bits of the pre fragments.  128 registers, 16 warps per SM.
 #define BW2_WARPS 16
 #define BW2_THREADS (BW2_WARPS * 32)
 #define BW2_PER_WARP (SDF_SMEM_PER_WARP + 32 * 4 + 32)           // tile, idx, mask words [32][4], gd[32]
-#define BW2_W2_OFF (SDF_SMEM_WARP_OFF + BW2_WARPS * BW2_PER_WARP)
-#define BW2_SMEM_BYTES ((BW2_W2_OFF + SDF_W0_FLOATS) * 4)
+#define BW2_WLO_OFF (SDF_SMEM_WARP_OFF + BW2_WARPS * BW2_PER_WARP)   // TF32 low parts of W0ext (the staged copy keeps the high parts)
+#define BW2_SMEM_BYTES ((BW2_WLO_OFF + SDF_W0_FLOATS) * 4)
 
 __device__ __forceinline__ uint32_t to_tf32(float x) {
     uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r;
@@ -370,13 +371,15 @@ sdf_backward_mma_kernel(const NetDev net, const GradDev grad, const float* __res
     float* sgd = wbase + SDF_SMEM_PER_WARP + 32 * 4;
     for (int e = lane; e < BW2_PER_WARP; e += 32) wbase[e] = 0.f;
     __syncthreads();
+    // split the staged W0ext once: smem[e] = TF32 high part, wlo[e] = TF32 of the remainder (B fragments of the 3xTF32 GEMMs)
+    float* wlo = smem + BW2_WLO_OFF;
     for (int e = threadIdx.x; e < SDF_W0_FLOATS; e += blockDim.x) {
-        const int j = e / NGLOD_KPAD, k = e - j * NGLOD_KPAD;
-        smem[BW2_W2_OFF + ((j >> 1) * NGLOD_KPAD + k) * 2 + (j & 1)] = smem[e];
+        const float w = smem[e];
+        const float hi = __uint_as_float(to_tf32(w));
+        smem[e] = hi;
+        wlo[e] = __uint_as_float(to_tf32(w - hi));
     }
     __syncthreads();
-    const float4* w4 = reinterpret_cast<const float4*>(smem);
-    const float4* w2v = reinterpret_cast<const float4*>(smem + BW2_W2_OFF);
     const float* sw1 = smem + SDF_SMEM_W1_OFF;
     const float sb1 = smem[SDF_SMEM_B1_OFF];
 
@@ -403,69 +406,121 @@ sdf_backward_mma_kernel(const NetDev net, const GradDev grad, const float* __res
             for (int k4 = 0; k4 < NGLOD_KPAD / 4; ++k4)
                 *reinterpret_cast<float4*>(tile + lane * NGLOD_KPAD + 4 * k4) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        // ---- B: thread-per-query: pre-activations (two hidden units per FFMA2), d, g_d, ReLU mask bits
-        float in[NGLOD_KPAD];
+        // ---- B: the decoder's two GEMMs on the tensor cores (mma.sync m16n8k8 TF32), 16 queries (one m-tile) at a time:
+        //      pre[q][h] = in[q] . W0ext[h]   3xTF32 (A_lo B_hi + A_hi B_lo + A_hi B_hi: d feeds the loss gradient)
+        //      g_in[q][f] = sum_h g_h[q][h] W0[h][f]   single TF32 pass; its A fragments are built in registers from the
+        //      ReLU mask bits of the pre fragments (hidden units of a k-step permuted identically in A and B)
+        __syncwarp();
+        float ginf[2][4][4];
 #pragma unroll
-        for (int k4 = 0; k4 < NGLOD_KPAD / 4; ++k4) {
-            const float4 v = *reinterpret_cast<const float4*>(tile + lane * NGLOD_KPAD + 4 * k4);
-            in[4 * k4] = v.x; in[4 * k4 + 1] = v.y; in[4 * k4 + 2] = v.z; in[4 * k4 + 3] = v.w;
-        }
-        uint32_t mbits[4] = {0u, 0u, 0u, 0u};
-        float d = sb1;
+        for (int m = 0; m < 2; ++m) {
+            const int rA = 16 * m + g, rB = rA + 8;                   // this lane's two query rows of the m-tile
+            uint32_t ahi[5][4], alo[5][4];
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
-#pragma unroll 2
-            for (int jq = 0; jq < 16; ++jq) {
-                const int jp = w * 16 + jq;
-                uint64_t a = 0ull;
+            for (int ks = 0; ks < 5; ++ks) {
+                const int k0 = 8 * ks + t, k1 = k0 + 4;
+                const float v[4] = {tile[rA * NGLOD_KPAD + k0], tile[rB * NGLOD_KPAD + k0],
+                                    k1 < NGLOD_KPAD ? tile[rA * NGLOD_KPAD + k1] : 0.f,
+                                    k1 < NGLOD_KPAD ? tile[rB * NGLOD_KPAD + k1] : 0.f};
 #pragma unroll
-                for (int k2 = 0; k2 < NGLOD_KPAD / 2; ++k2) {
-                    const float4 wv = w2v[jp * (NGLOD_KPAD / 2) + k2];
-                    a = f2_fma(f2_pack(wv.x, wv.y), f2_pack(in[2 * k2], in[2 * k2]), a);
-                    a = f2_fma(f2_pack(wv.z, wv.w), f2_pack(in[2 * k2 + 1], in[2 * k2 + 1]), a);
+                for (int e = 0; e < 4; ++e) {
+                    ahi[ks][e] = to_tf32(v[e]);
+                    alo[ks][e] = to_tf32(v[e] - __uint_as_float(ahi[ks][e]));
                 }
-                float a0, a1;
-                f2_unpack(a, a0, a1);
-                if (FUSED_LOSS) {
-                    d = fmaf(sw1[2 * jp], fmaxf(a0, 0.f), d);
-                    d = fmaf(sw1[2 * jp + 1], fmaxf(a1, 0.f), d);
-                }
-                mbits[w] |= (a0 > 0.f ? 1u : 0u) << (2 * jq);
-                mbits[w] |= (a1 > 0.f ? 1u : 0u) << (2 * jq + 1);
             }
-        }
-        float gd = 0.f;
-        if (active) {
+            uint32_t bitsA = 0u, bitsB = 0u;                          // bit 2n+e: pre(row, hidden 8n + 2t + e) > 0
+            float dA = 0.f, dB = 0.f;
+#pragma unroll
+            for (int nc = 0; nc < 2; ++nc) {
+                float acc[8][4];
+#pragma unroll
+                for (int n8 = 0; n8 < 8; ++n8)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) acc[n8][e] = 0.f;
+#pragma unroll
+                for (int ks = 0; ks < 5; ++ks) {
+                    const int k0 = 8 * ks + t, k1 = k0 + 4;
+#pragma unroll
+                    for (int n8 = 0; n8 < 8; ++n8) {
+                        const int h = 8 * (8 * nc + n8) + g;
+                        uint32_t bhi[2], blo[2];
+                        bhi[0] = __float_as_uint(smem[h * NGLOD_KPAD + k0]);
+                        blo[0] = __float_as_uint(wlo[h * NGLOD_KPAD + k0]);
+                        bhi[1] = k1 < NGLOD_KPAD ? __float_as_uint(smem[h * NGLOD_KPAD + k1]) : 0u;
+                        blo[1] = k1 < NGLOD_KPAD ? __float_as_uint(wlo[h * NGLOD_KPAD + k1]) : 0u;
+                        mma_tf32_16x8x8(acc[n8], alo[ks], bhi);
+                        mma_tf32_16x8x8(acc[n8], ahi[ks], blo);
+                        mma_tf32_16x8x8(acc[n8], ahi[ks], bhi);
+                    }
+                }
+#pragma unroll
+                for (int n8 = 0; n8 < 8; ++n8) {
+                    const int n = 8 * nc + n8;
+                    const float2 w1p = *reinterpret_cast<const float2*>(sw1 + 8 * n + 2 * t);
+                    if (FUSED_LOSS) {
+                        dA = fmaf(w1p.x, fmaxf(acc[n8][0], 0.f), dA); dA = fmaf(w1p.y, fmaxf(acc[n8][1], 0.f), dA);
+                        dB = fmaf(w1p.x, fmaxf(acc[n8][2], 0.f), dB); dB = fmaf(w1p.y, fmaxf(acc[n8][3], 0.f), dB);
+                    }
+                    bitsA |= ((acc[n8][0] > 0.f ? 1u : 0u) | (acc[n8][1] > 0.f ? 2u : 0u)) << (2 * n);
+                    bitsB |= ((acc[n8][2] > 0.f ? 1u : 0u) | (acc[n8][3] > 0.f ? 2u : 0u)) << (2 * n);
+                }
+            }
+            // d of the two rows (sum over the 4 lanes that share a row), upstream gradients
+            const long long iA = base0 + warp * 32 + rA, iB = iA + 8;
+            float gdA = 0.f, gdB = 0.f;
             if (FUSED_LOSS) {
-                const float diff = d - __ldg(gt + i);
-                acc_loss = fmaf(diff * diff, loss_scale, acc_loss);
-                gd = 2.f * diff * loss_scale;
+                dA += __shfl_xor_sync(0xffffffffu, dA, 1); dA += __shfl_xor_sync(0xffffffffu, dA, 2);
+                dB += __shfl_xor_sync(0xffffffffu, dB, 1); dB += __shfl_xor_sync(0xffffffffu, dB, 2);
+                if (iA < n) { const float diff = (dA + sb1) - __ldg(gt + iA); gdA = 2.f * diff * loss_scale;
+                              if (t == 0) acc_loss = fmaf(diff * diff, loss_scale, acc_loss); }
+                if (iB < n) { const float diff = (dB + sb1) - __ldg(gt + iB); gdB = 2.f * diff * loss_scale;
+                              if (t == 0) acc_loss = fmaf(diff * diff, loss_scale, acc_loss); }
             } else {
-                gd = __ldg(grad_out + i);
+                if (iA < n) gdA = __ldg(grad_out + iA);
+                if (iB < n) gdB = __ldg(grad_out + iB);
             }
-        }
-        acc_b1 += gd;
-        // g_in[k] = sum_j W0[j][k] * g_h[j], pairs over k
-        uint64_t gin2[NGLOD_F / 2];
+            if (t == 0) { acc_b1 += gdA + gdB; sgd[rA] = gdA; sgd[rB] = gdB; }
+            // ReLU mask words for phase C: word w = hidden [32w, 32w+32); this lane holds the bit pairs (2t, 2t+1) of
+            // every 8-wide block; OR over the 4 lanes of the row
 #pragma unroll
-        for (int k = 0; k < NGLOD_F / 2; ++k) gin2[k] = 0ull;
+            for (int w = 0; w < 4; ++w) {
+                uint32_t wa = 0u, wb = 0u;
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
+                for (int nn = 0; nn < 4; ++nn) {
+                    wa |= ((bitsA >> (8 * w + 2 * nn)) & 3u) << (8 * nn + 2 * t);
+                    wb |= ((bitsB >> (8 * w + 2 * nn)) & 3u) << (8 * nn + 2 * t);
+                }
+                wa |= __shfl_xor_sync(0xffffffffu, wa, 1); wa |= __shfl_xor_sync(0xffffffffu, wa, 2);
+                wb |= __shfl_xor_sync(0xffffffffu, wb, 1); wb |= __shfl_xor_sync(0xffffffffu, wb, 2);
+                if (t == 0) { maskw[rA * 4 + w] = wa; maskw[rB * 4 + w] = wb; }
+            }
+            // g_in of the m-tile
+#pragma unroll
+            for (int nf = 0; nf < 4; ++nf)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) ginf[m][nf][e] = 0.f;
 #pragma unroll 4
-            for (int jb = 0; jb < 32; ++jb) {
-                const int j = w * 32 + jb;
-                const float gh = ((mbits[w] >> jb) & 1u) ? gd * sw1[j] : 0.f;
-                const uint64_t gh2 = f2_pack(gh, gh);
+            for (int n = 0; n < 16; ++n) {
+                const int h0 = 8 * n + 2 * t;                                  // A/B "column t" = h0, "column t+4" = h0 + 1
+                const float2 w1p = *reinterpret_cast<const float2*>(sw1 + h0);
+                const float av[4] = {((bitsA >> (2 * n)) & 1u) ? gdA * w1p.x : 0.f, ((bitsB >> (2 * n)) & 1u) ? gdB * w1p.x : 0.f,
+                                     ((bitsA >> (2 * n + 1)) & 1u) ? gdA * w1p.y : 0.f, ((bitsB >> (2 * n + 1)) & 1u) ? gdB * w1p.y : 0.f};
+                uint32_t a[4], al[4];
 #pragma unroll
-                for (int k4 = 0; k4 < NGLOD_F / 4; ++k4) {
-                    const float4 wr = w4[j * (NGLOD_KPAD / 4) + k4];
-                    gin2[2 * k4] = f2_fma(f2_pack(wr.x, wr.y), gh2, gin2[2 * k4]);
-                    gin2[2 * k4 + 1] = f2_fma(f2_pack(wr.z, wr.w), gh2, gin2[2 * k4 + 1]);
+                for (int e = 0; e < 4; ++e) { a[e] = to_tf32(av[e]); al[e] = to_tf32(av[e] - __uint_as_float(a[e])); }
+#pragma unroll
+                for (int nf = 0; nf < 4; ++nf) {
+                    uint32_t bb[2], bl[2];
+                    bb[0] = __float_as_uint(smem[h0 * NGLOD_KPAD + 8 * nf + g]);
+                    bl[0] = __float_as_uint(wlo[h0 * NGLOD_KPAD + 8 * nf + g]);
+                    bb[1] = __float_as_uint(smem[(h0 + 1) * NGLOD_KPAD + 8 * nf + g]);
+                    bl[1] = __float_as_uint(wlo[(h0 + 1) * NGLOD_KPAD + 8 * nf + g]);
+                    mma_tf32_16x8x8(ginf[m][nf], al, bb);        // 3xTF32: the terms of g_in cancel heavily, a single pass
+                    mma_tf32_16x8x8(ginf[m][nf], a, bl);         // left 2.4e-4 of max|grad| on the grid gradients
+                    mma_tf32_16x8x8(ginf[m][nf], a, bb);
                 }
             }
         }
-        *reinterpret_cast<uint4*>(maskw + lane * 4) = make_uint4(mbits[0], mbits[1], mbits[2], mbits[3]);
-        sgd[lane] = gd;
         __syncthreads();
         // ---- C: T[h][k] += sum_q g_d(q) mask(q,h) in(q,k) on the tensor cores
 #pragma unroll 2
@@ -495,14 +550,14 @@ sdf_backward_mma_kernel(const NetDev net, const GradDev grad, const float* __res
             }
         }
         __syncthreads();
-        // ---- D: scatter g_feat into the grids
+        // ---- D: scatter g_feat into the grids (fragments -> the warp's tile rows -> 8 lanes per corner line)
 #pragma unroll
-        for (int k4 = 0; k4 < NGLOD_F / 4; ++k4) {
-            float4 v;
-            f2_unpack(gin2[2 * k4], v.x, v.y);
-            f2_unpack(gin2[2 * k4 + 1], v.z, v.w);
-            *reinterpret_cast<float4*>(tile + lane * NGLOD_KPAD + 4 * k4) = v;
-        }
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int nf = 0; nf < 4; ++nf) {
+                *reinterpret_cast<float2*>(tile + (16 * m + g) * NGLOD_KPAD + 8 * nf + 2 * t) = make_float2(ginf[m][nf][0], ginf[m][nf][1]);
+                *reinterpret_cast<float2*>(tile + (16 * m + g + 8) * NGLOD_KPAD + 8 * nf + 2 * t) = make_float2(ginf[m][nf][2], ginf[m][nf][3]);
+            }
         __syncwarp();
         {
             const unsigned live = __ballot_sync(0xffffffffu, active);
@@ -574,7 +629,7 @@ sdf_backward_mma_kernel(const NetDev net, const GradDev grad, const float* __res
 #pragma unroll 4
         for (int k = 0; k < NGLOD_KPAD; ++k) {
             const float tv = cta_T[h * 40 + k];
-            dw1 = fmaf(smem[h * NGLOD_KPAD + k], tv, dw1);           // staged W0ext row: {32 feat, x, y, z, b0}
+            dw1 = fmaf(smem[h * NGLOD_KPAD + k] + wlo[h * NGLOD_KPAD + k], tv, dw1);   // W0ext row {32 feat, x, y, z, b0} = hi + lo
             const float v = w1h * tv;
             if (k < NGLOD_F) {
                 if (grad.w0) atomicAdd(grad.w0 + h * in_dim + (net.pos_invariant ? k : k + 3), v);
