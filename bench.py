@@ -45,10 +45,10 @@ GATHER_BYTES_PER_QUERY = 8 * 32 * 4 if SUM_LODS else GATHER_BYTES_PER_QUERY_PER_
 IO_BYTES_PER_QUERY = 16
 RAY_IO_BYTES = 24 + 12 + 4 + 1 + 12                        # ray_o, ray_d in; x, depth, hit, normal out
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE sphere_trace_kernel / sdf_forward_tc_kernel launch (single-grid
-# fp32 instances), from the `ncu --set full` captures summarised in profiles/sphere_trace_sum_r1_v3.txt and
-# profiles/sdf_forward_sum_r1_v3.txt
-NCU_TRAFFIC_TRACE_BYTES = 38474240 + 1309696
-NCU_TRAFFIC_SDF_FWD_BYTES = 47820032 + 684032
+# fp32 instances), from the `ncu --set full` captures summarised in profiles/sphere_trace_sum_r1_v4.txt and
+# profiles/sdf_forward_sum_r1_v4.txt
+NCU_TRAFFIC_TRACE_BYTES = 38498048 + 2459392
+NCU_TRAFFIC_SDF_FWD_BYTES = 47828992 + 575744
 
 
 def load_peaks():
