@@ -142,7 +142,9 @@ int nglod_sdf_features(const nglod_net_t* net, int32_t lod, const float* x,
 
 /* summed[node] = sum_{l<=lod} trilinear(grids[l], node) for every node of grid `lod` (see nglod_net_t.summed).
  * dst: [(R+1)^3, feature_dim] fp32 channels-last, R = grid_res[lod], 16-byte aligned.  Node weights are exact
- * rationals ((ix mod k)/k with k = R / grid_res[l]).  NGLOD_EUNSUPPORTED if the grids do not nest. */
+ * rationals ((ix mod k)/k with k = R / grid_res[l]).  NGLOD_EUNSUPPORTED if the grids do not nest.
+ * If net->summed[lod-1] is set (the previous level, already built) the level is computed as its prolongation plus
+ * grids[lod] -- build the levels in ascending order to get all of them for the price of the last. */
 int nglod_build_summed_grid(const nglod_net_t* net, int32_t lod, float* dst, void* stream);
 
 /* Build the half-precision gather layout of ONE grid: for every (z, y, x0 < R) a 128-byte line holding

@@ -202,6 +202,15 @@ extern "C" int nglod_build_summed_grid(const nglod_net_t* net, int32_t lod, floa
         a.res[i] = net->grid_res[i];
         a.grids[i] = net->grids[i];
     }
+    // Level by level: when the summed grid of the previous LOD is already there (net->summed[lod-1], != dst), this
+    // level is its prolongation plus the LOD's own grid -- two sources instead of lod+1 (all five levels of the
+    // headline model: 5 x 35 us -> ~15 us, which the trainer pays every step).
+    if (lod > 0 && net->summed[lod - 1] && net->summed[lod - 1] != dst &&
+        !(reinterpret_cast<uintptr_t>(net->summed[lod - 1]) & 15u)) {
+        a.n_src = 2;
+        a.res[0] = net->grid_res[lod - 1]; a.grids[0] = net->summed[lod - 1];
+        a.res[1] = net->grid_res[lod];     a.grids[1] = net->grids[lod];
+    }
     const long long S = a.R + 1;
     const long long n_chunks = S * S * S * 8;
     long long blocks = (n_chunks + 255) / 256;

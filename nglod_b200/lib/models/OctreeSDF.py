@@ -124,8 +124,11 @@ class OctreeSDF(BaseLOD):
             grids = [f.fm.data for f in self.features]
             base = ops.NetView.grids_only(grids)
             old = self._derived[1] if self._derived is not None else [None] * len(grids)
-            summed = [ops.build_summed_grid(base, i, out=o if (o is not None and o.device == g.device) else None)
-                      for i, (g, o) in enumerate(zip(grids, old))]
+            summed = []
+            for i, (g, o) in enumerate(zip(grids, old)):      # ascending: level i = prolongation of level i-1 + grid i
+                if i > 0:
+                    base.struct.summed[i - 1] = summed[i - 1].data_ptr()
+                summed.append(ops.build_summed_grid(base, i, out=o if (o is not None and o.device == g.device) else None))
             self._derived = [key, summed, None]
         if want_half and self._derived[2] is None:
             self._derived[2] = [ops.pack_grid_fp16(sg) for sg in self._derived[1]]

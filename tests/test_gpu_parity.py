@@ -481,6 +481,10 @@ def test_summed_grid_identity(rand5):
         err = (one - ref).abs().max().item()
         print(f"summed grid lod{lod}: node err {(got - want).abs().max():.1e}; sample-vs-running-sum err {err:.1e}")
         assert err < 3e-8
+    # the model builds its levels in ascending order, each as the prolongation of the previous one + its own grid
+    # (nglod_net_t.summed[lod-1] given): same grids as the direct builds
+    for lod, sg in enumerate(net.net_view().summed):
+        assert (sg - ops.build_summed_grid(view, lod)).abs().max() < 2e-8
     odd = [torch.zeros(1, 32, r + 1, r + 1, r + 1, device=DEV).contiguous(memory_format=torch.channels_last_3d) for r in (4, 6)]
     with pytest.raises(RuntimeError):
         ops.build_summed_grid(ops.NetView.grids_only(odd), 1)
