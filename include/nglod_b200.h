@@ -169,7 +169,9 @@ int nglod_sdf_backward(const nglod_net_t* net, int32_t lod, const float* x,
  *   loss = sum_{l in lod_mask} sum_i (sdf(x_i,l) - gt_i)^2 * loss_scale
  * (the reference uses loss_scale = 1/batch).  Accumulates all gradients into
  * `grad`, adds the (scaled) loss into *loss_out (device, fp32; may be null).
- * lod_mask: bit l set <=> LOD l contributes. */
+ * lod_mask: bit l set <=> LOD l contributes; with NGLOD_LOSS_PER_LOD or'ed in, head l's loss goes to loss_out[l]
+ * (an array of num_lods floats) instead of all heads summing into loss_out[0]. */
+#define NGLOD_LOSS_PER_LOD 0x80000000u
 int nglod_sdf_train_step(const nglod_net_t* net, uint32_t lod_mask,
                          const float* x, const float* gt, int64_t n,
                          float loss_scale, const nglod_net_grad_t* grad,

@@ -10,6 +10,7 @@ import ctypes
 import os
 
 MAX_LODS = 8
+LOSS_PER_LOD = 0x80000000
 MATH_TC3XTF32 = 0
 MATH_FP32 = 1
 EINVAL = 10001

@@ -797,7 +797,8 @@ extern "C" int nglod_sdf_train_step(const nglod_net_t* net, uint32_t lod_mask, c
         for (int i = 0; i <= l; ++i)
             if (grad->grids[i] && (reinterpret_cast<uintptr_t>(grad->grids[i]) & 15u)) return NGLOD_EINVAL;
         if (use_summed_backward(net, l, grad)) top_single = l;
-        if (int e = launch_backward<true, false>(net, l, grad, x, n, nullptr, gt, loss_scale, nullptr, loss_out,
+        float* lo = (loss_out && (lod_mask & NGLOD_LOSS_PER_LOD)) ? loss_out + l : loss_out;
+        if (int e = launch_backward<true, false>(net, l, grad, x, n, nullptr, gt, loss_scale, nullptr, lo,
                                                  (cudaStream_t)stream, /*cascade=*/false))
             return e;
     }

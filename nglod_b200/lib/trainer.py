@@ -11,7 +11,7 @@ channels-last), with a matching flat gradient buffer and flat Adam moments:
 """
 import torch
 
-from .. import ops
+from .. import ops, _lib
 from .. import dist as ndist
 
 
@@ -68,9 +68,13 @@ class FusedTrainer:
         grid_grads, dec_grads = self._grad_lists()
         view = net.net_view(inference=False)    # rebuilds the prefix-summed grids from this step's weights (~30 us)
         scratch = net.summed_grad_scratch() if view.summed is not None else None
-        for l in lods:          # one fused forward+loss+backward launch per LOD head, each with its own loss cell
-            ops.sdf_train_step(view, 1 << l, pts, gts, 1.0 / batch, grid_grads, dec_grads, self.lod_loss[l:l + 1],
-                               summed_scratch=scratch)
+        # one call: a fused forward+loss+backward launch per LOD head (each with its own loss cell), then ONE restriction
+        # cascade for all of them
+        mask = 0
+        for l in lods:
+            mask |= 1 << l
+        ops.sdf_train_step(view, mask | _lib.LOSS_PER_LOD, pts, gts, 1.0 / batch, grid_grads, dec_grads, self.lod_loss,
+                           summed_scratch=scratch)
         torch.sum(self.lod_loss, dim=0, keepdim=True, out=self.loss)
         ndist.allreduce_sum_(self.flat_grad)
         self.step_count += 1
