@@ -15,6 +15,7 @@ import torch.nn.functional as F
 
 from oracle import nglod_oracle as O
 from helpers import rand5_model, fit3_model, cl_flat, make_args, torus_sdf
+from nglod_b200.lib.models import OctreeSDF as OctreeSDF_cls
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -648,3 +649,59 @@ def test_realtime_loop_dense_and_sparse(fit3):
     assert "sparse" in sp["mode"]
     inter = int((sp["hit"] & out["hit"]).sum()) if sp["hit"].shape == out["hit"].shape else 0
     assert int(sp["hit"].sum()) > 300
+
+
+# ------------------------------------------------------------------------------------------------ model variants
+@pytest.mark.parametrize("flags,kw", [
+    (["--num-lods", "3", "--pos-invariant"], dict(pos_invariant=True)),
+    (["--num-lods", "4", "--joint-decoder"], {}),
+    (["--num-lods", "3", "--base-lod", "1"], {}),
+    (["--num-lods", "2", "--base-lod", "3"], {}),
+    (["--num-lods", "7", "--base-lod", "0"], {}),         # R = 1 .. 64: more grids than one set-up batch (TC_PACK_LODS = 5)
+])
+def test_model_variants_forward_backward_trace(flags, kw):
+    """The reference's other OctreeSDF shapes (--pos-invariant, --joint-decoder, --base-lod, up to 7 LODs) through every
+    path: both decoders x (summed grid | per-LOD gather), autograd backward on both scatter paths, a short trace."""
+    from nglod_b200.lib.tracer import SphereTracer
+    args = make_args(flags)
+    torch.manual_seed(3)
+    net = OctreeSDF_cls(args).to(DEV)
+    for f in net.features:                       # larger features than the 0.01 init so every LOD matters
+        f.fm.data.mul_(20.0)
+    net.mark_grids_dirty()
+    onet = O.OracleNet(net.state_dict(), requires_grad=True, **kw)
+    g = torch.Generator().manual_seed(5)
+    x = torch.cat([torch.rand(3001, 3, generator=g) * 2.3 - 1.15, torch.tensor([[1.0, 1.0, 1.0], [-1.0, -1.0, 1.0]])])
+    top = net.num_lods - 1
+    with torch.no_grad():
+        for lod in sorted({0, top // 2, top}):
+            ref = onet.sdf(x, lod=lod)
+            for mode in ("tc", "fp32"):
+                for summ in (True, False):
+                    net.math_mode, net.sum_lods = mode, summ
+                    err = (net.sdf(x.to(DEV), lod=lod).cpu() - ref).abs().max().item()
+                    assert err < 1e-5, (flags, lod, mode, summ, err)
+    net.math_mode = "tc"
+    gt = torch.rand(x.shape[0], 1, generator=g) - 0.5
+    loss_ref = ((onet.sdf(x, lod=top) - gt) ** 2).mean()
+    loss_ref.backward()
+    for summ in (True, False):
+        net.sum_lods = summ
+        for p in net.parameters():
+            p.grad = None
+        loss = ((net.sdf(x.to(DEV), lod=top) - gt.to(DEV)) ** 2).mean()
+        loss.backward()
+        assert abs(loss.item() - loss_ref.item()) < 1e-5 * max(1.0, abs(loss_ref.item()))
+        for i in range(net.num_lods):
+            a, b = net.features[i].fm.grad.cpu(), onet.fm[i].grad
+            assert (a - b).abs().max() / b.abs().max() < 3e-4, (flags, summ, i)
+        dec = net.decoder_params(top)
+        for a, b in zip(dec, onet.decoder(top)):
+            assert (a.grad.cpu() - b.grad).abs().max() / b.grad.abs().max() < 3e-4, (flags, summ)
+    net.sum_lods, net.lod, onet.lod = True, top, top
+    torch.manual_seed(4)
+    o, d = O.look_at([-2.8, 2.8, -2.8], [0, 0, 0], 64, 36, fov=30.0)
+    rb = SphereTracer(args, num_steps=24)(net, o.to(DEV), d.to(DEV))
+    with torch.no_grad():
+        ref = O.sphere_trace(onet, o, d, num_steps=24)
+    assert int((rb.hit.cpu() != ref["hit"]).sum()) <= 2
