@@ -111,10 +111,20 @@ __device__ void build_record(const float* __restrict__ tri, TriRecord& r) {
     r.pad[0] = r.pad[1] = 0;
 }
 
+// Records are built ONCE per call into stream-ordered scratch (384 B per triangle, L2-resident): building them per
+// CTA per tile made two warps of every CTA redo ~500 instructions per triangle while the other six waited at the
+// barrier -- half of the kernel's time at 500 k points x 16 k triangles.
+__global__ void __launch_bounds__(128)
+m2s_records_kernel(const float* __restrict__ tris, const long long num_tris, TriRecord* __restrict__ recs) {
+    const long long t = (long long)blockIdx.x * 128 + threadIdx.x;
+    if (t < num_tris) build_record(tris + t * 9, recs[t]);
+}
+
 __global__ void __launch_bounds__(M2S_THREADS)
-mesh2sdf_kernel(const float* __restrict__ points, const long long n, const float* __restrict__ tris,
+mesh2sdf_kernel(const float* __restrict__ points, const long long n, const TriRecord* __restrict__ recs,
                 const long long num_tris, float* __restrict__ dist, const int* __restrict__ perm) {
     __shared__ TriRecord rec[M2S_TILE];
+    static_assert(sizeof(TriRecord) % 16 == 0, "records are copied as 16-byte words");
     const long long i = (long long)blockIdx.x * M2S_THREADS + threadIdx.x;
     const bool active = i < n;
     float P[3] = {0.f, 0.f, 0.f};
@@ -127,7 +137,11 @@ mesh2sdf_kernel(const float* __restrict__ points, const long long n, const float
     for (long long t0 = 0; t0 < num_tris; t0 += M2S_TILE) {
         const int cnt = (int)min((long long)M2S_TILE, num_tris - t0);
         __syncthreads();
-        if (threadIdx.x < cnt) build_record(tris + (t0 + threadIdx.x) * 9, rec[threadIdx.x]);
+        {
+            const uint4* src = reinterpret_cast<const uint4*>(recs + t0);
+            uint4* dst = reinterpret_cast<uint4*>(rec);
+            for (int e = threadIdx.x; e < cnt * (int)(sizeof(TriRecord) / 16); e += M2S_THREADS) dst[e] = __ldg(src + e);
+        }
         __syncthreads();
         // All 32 lanes stay in the loop (inactive lanes carry P = 0 and never write): the rejections below are
         // warp-votes, so the branches are uniform and most (triangle, direction) pairs cost 5 instructions.
@@ -284,25 +298,35 @@ extern "C" int nglod_mesh2sdf(const float* points, int64_t n, const float* tris,
     const long long grid = (n + M2S_THREADS - 1) / M2S_THREADS;
     if (grid > 2147483647ll) return NGLOD_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
-    if (n < 4096 || n >= 2000000000ll || num_tris < 64) {        // too small for the sort to pay
-        mesh2sdf_kernel<<<(int)grid, M2S_THREADS, 0, st>>>(points, (long long)n, tris, (long long)num_tris, dist, nullptr);
+    if (num_tris == 0) {            // no surface: the reference's min over nothing -- keep the old kernel's answer (+inf)
+        mesh2sdf_kernel<<<(int)grid, M2S_THREADS, 0, st>>>(points, (long long)n, nullptr, 0ll, dist, nullptr);
         return (int)cudaGetLastError();
     }
+    const bool sort = !(n < 4096 || n >= 2000000000ll || num_tris < 64);      // else too small for the sort to pay
     char* ws = nullptr;
-    const size_t perm_off = ((size_t)n * 12 + 255) & ~(size_t)255;
-    const size_t hist_off = (perm_off + (size_t)n * 4 + 255) & ~(size_t)255;
-    NGLOD_CUDA_TRY(cudaMallocAsync(&ws, hist_off + (size_t)M2S_BINS * 4, st));
-    float* xs = reinterpret_cast<float*>(ws);
-    int* perm = reinterpret_cast<int*>(ws + perm_off);
-    int* hist = reinterpret_cast<int*>(ws + hist_off);
-    int err = (int)cudaMemsetAsync(hist, 0, (size_t)M2S_BINS * 4, st);
-    if (!err) {
-        const int nb = (int)((n + 255) / 256 < (long long)nglod_sm_count() * 8 ? (n + 255) / 256 : (long long)nglod_sm_count() * 8);
-        m2s_hist_kernel<<<nb, 256, 0, st>>>(points, (long long)n, hist);
-        m2s_scan_kernel<<<1, 1024, 0, st>>>(hist);
-        m2s_scatter_kernel<<<nb, 256, 0, st>>>(points, (long long)n, hist, xs, perm);
-        mesh2sdf_kernel<<<(int)grid, M2S_THREADS, 0, st>>>(xs, (long long)n, tris, (long long)num_tris, dist, perm);
+    const size_t rec_bytes = ((size_t)num_tris * sizeof(TriRecord) + 255) & ~(size_t)255;
+    const size_t perm_off = rec_bytes + (sort ? (((size_t)n * 12 + 255) & ~(size_t)255) : 0);
+    const size_t hist_off = perm_off + (sort ? (((size_t)n * 4 + 255) & ~(size_t)255) : 0);
+    NGLOD_CUDA_TRY(cudaMallocAsync(&ws, hist_off + (sort ? (size_t)M2S_BINS * 4 : 0) + 256, st));
+    TriRecord* recs = reinterpret_cast<TriRecord*>(ws);
+    m2s_records_kernel<<<(int)((num_tris + 127) / 128), 128, 0, st>>>(tris, (long long)num_tris, recs);
+    int err = (int)cudaGetLastError();
+    if (!err && !sort) {
+        mesh2sdf_kernel<<<(int)grid, M2S_THREADS, 0, st>>>(points, (long long)n, recs, (long long)num_tris, dist, nullptr);
         err = (int)cudaGetLastError();
+    } else if (!err) {
+        float* xs = reinterpret_cast<float*>(ws + rec_bytes);
+        int* perm = reinterpret_cast<int*>(ws + perm_off);
+        int* hist = reinterpret_cast<int*>(ws + hist_off);
+        err = (int)cudaMemsetAsync(hist, 0, (size_t)M2S_BINS * 4, st);
+        if (!err) {
+            const int nb = (int)((n + 255) / 256 < (long long)nglod_sm_count() * 8 ? (n + 255) / 256 : (long long)nglod_sm_count() * 8);
+            m2s_hist_kernel<<<nb, 256, 0, st>>>(points, (long long)n, hist);
+            m2s_scan_kernel<<<1, 1024, 0, st>>>(hist);
+            m2s_scatter_kernel<<<nb, 256, 0, st>>>(points, (long long)n, hist, xs, perm);
+            mesh2sdf_kernel<<<(int)grid, M2S_THREADS, 0, st>>>(xs, (long long)n, recs, (long long)num_tris, dist, perm);
+            err = (int)cudaGetLastError();
+        }
     }
     const int ferr = (int)cudaFreeAsync(ws, st);
     return err ? err : ferr;
