@@ -424,16 +424,17 @@ def run_extras(net, args, device, rank, world, flush, log):
     rargs2 = copy.copy(args)
     rargs2.render_res = [W, H]
     r2 = Renderer(SphereTracer(rargs2), args=rargs2, device=device)
-    for _ in range(2):
-        r2.shade_images(net, f=CAM_FROM, t=CAM_TO, fov=FOV)
+    img = None
+    for _ in range(5):      # the first calls page-lock their host buffers (~100 ms per new 52 MB set); steady state reuses them
+        img = r2.shade_images(net, f=CAM_FROM, t=CAM_TO, fov=FOV)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(5):
+    for _ in range(10):
         img = r2.shade_images(net, f=CAM_FROM, t=CAM_TO, fov=FOV)
-    shade_s = ndist.max_over_ranks((time.perf_counter() - t0) / 5, device)
+    shade_s = ndist.max_over_ranks((time.perf_counter() - t0) / 10, device)
     out["shade_images_720p"] = {"ms": shade_s * 1e3, "fps": 1.0 / shade_s, "hit_pixels": int(img.hit.sum()),
-                                "note": "Renderer.shade_images end to end: look_at rays, sphere trace, matcap shading, "
-                                        "all RenderBuffer fields to host, (H,W,C) layout"}
+                                "note": "Renderer.shade_images end to end, steady state (after the host buffers are page-locked): look_at "
+                                        "rays, sphere trace, matcap shading, all RenderBuffer fields to host, (H,W,C) layout"}
 
     # ---- config 3: training step on a 500 000-point batch sharded over the ranks (fused 5-head fwd+bwd, one
     #      all-reduce of the flat gradient, Adam kernel) + the cost of producing the batch (sampling + mesh2sdf labels)
