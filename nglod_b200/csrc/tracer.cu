@@ -158,8 +158,8 @@ sphere_trace_kernel(const NetDev net, const float* __restrict__ ray_o, const flo
 #else
 #define TR_TICK(i) do { } while (0)
 #endif
-    for (;;) {
-        // ---- refill empty slots from the global queue
+    // refill empty slots from the global queue (ballot + popc ranks; rays that miss the box retire on the spot)
+    auto refill = [&]() {
 #pragma unroll 1
         for (int attempt = 0; attempt < 4 && !exhausted; ++attempt) {
             const unsigned free_mask = __ballot_sync(0xffffffffu, phase == PH_EMPTY);
@@ -183,6 +183,9 @@ sphere_trace_kernel(const NetDev net, const float* __restrict__ ray_o, const flo
                 }
             }
         }
+    };
+    for (;;) {
+        refill();
         TR_TICK(0);
         const bool occupied = phase != PH_EMPTY;
         const unsigned act = __ballot_sync(0xffffffffu, occupied);
