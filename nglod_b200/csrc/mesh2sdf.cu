@@ -133,6 +133,33 @@ mesh2sdf_kernel(const float* __restrict__ points, const long long n, const TriRe
     float mind = INFINITY;              // sqrt(mind2), refreshed when mind2 improves (culling bound only)
     unsigned pos = 0, neg = 0;
     const unsigned all_dirs = (1u << M2S_NDIR) - 1u;
+    // Bounding sphere of the warp's points (they are neighbours after the spatial sort): the 13 stab lines of all 32
+    // points in direction k lie inside a cylinder of radius wr around the line through wc, so a triangle whose own
+    // bounding sphere stays clear of that cylinder cannot be hit by any of them.  Lane k < 13 tests direction k for the
+    // whole warp; only the directions that survive run the exact (reference-order) barycentric tests below.  The cull is
+    // conservative (generous slack), so every decision and every distance is unchanged.
+    const int lane = threadIdx.x & 31;
+    float wc[3], wr;
+    {
+        const unsigned am = __ballot_sync(0xffffffffu, active);
+        const float cnt = (float)max(__popc(am), 1);
+        float sx = active ? P[0] : 0.f, sy = active ? P[1] : 0.f, sz = active ? P[2] : 0.f;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            sx += __shfl_xor_sync(0xffffffffu, sx, o); sy += __shfl_xor_sync(0xffffffffu, sy, o); sz += __shfl_xor_sync(0xffffffffu, sz, o);
+        }
+        wc[0] = sx / cnt; wc[1] = sy / cnt; wc[2] = sz / cnt;
+        const float ex = P[0] - wc[0], ey = P[1] - wc[1], ez = P[2] - wc[2];
+        float r2 = active ? ex * ex + ey * ey + ez * ez : 0.f;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) r2 = fmaxf(r2, __shfl_xor_sync(0xffffffffu, r2, o));
+        wr = sqrtf(r2) * 1.001f + 1e-6f;
+    }
+    float dk[3] = {0.f, 0.f, 0.f}, inv_dk2 = 0.f;            // this lane's direction (lanes >= 13: none)
+    if (lane < M2S_NDIR) {
+        dk[0] = c_stab_dir[lane][0]; dk[1] = c_stab_dir[lane][1]; dk[2] = c_stab_dir[lane][2];
+        inv_dk2 = 1.0f / dot3(dk, dk);
+    }
 
     for (long long t0 = 0; t0 < num_tris; t0 += M2S_TILE) {
         const int cnt = (int)min((long long)M2S_TILE, num_tris - t0);
@@ -178,13 +205,24 @@ mesh2sdf_kernel(const float* __restrict__ points, const long long n, const TriRe
             // 13 line stabs (Moller-Trumbore); qvec and edge2.qvec do not depend on the direction
             const bool undecided = (pos & neg) != all_dirs;
             if (r.dir_ok && __any_sync(0xffffffffu, undecided)) {
+                // warp-cylinder cull, one direction per lane
+                bool maybe = false;
+                if (lane < M2S_NDIR) {
+                    const float vx = r.cen[0] - wc[0], vy = r.cen[1] - wc[1], vz = r.cen[2] - wc[2];
+                    const float proj = vx * dk[0] + vy * dk[1] + vz * dk[2];
+                    const float perp2 = (vx * vx + vy * vy + vz * vz) - proj * proj * inv_dk2;
+                    const float reach = (r.rad + wr) * 1.001f + 1e-5f;
+                    maybe = !(perp2 > reach * reach);
+                }
+                const unsigned dirs = __ballot_sync(0xffffffffu, maybe) & r.dir_ok;
+                if (!dirs) continue;
                 float qvec[3];
                 cross3(p0, r.v10, qvec);
                 const float edge2[3] = {-r.v02[0], -r.v02[1], -r.v02[2]};
                 const float e2q = dot3(edge2, qvec);
 #pragma unroll
                 for (int k = 0; k < M2S_NDIR; ++k) {
-                    if (!((r.dir_ok >> k) & 1u)) continue;                 // uniform: a property of the triangle
+                    if (!((dirs >> k) & 1u)) continue;                     // warp-uniform
                     const float inv_det = r.inv_det[k];
                     const float u = dot3(p0, r.pvec[k]) * inv_det;
                     const bool pu = !(u < 0.0f || u > 1.0f);
@@ -211,7 +249,11 @@ mesh2sdf_kernel(const float* __restrict__ points, const long long n, const TriRe
 // first barycentric test.  The sampler hands points over in random spatial order, so they are grouped first
 // (histogram -> scan -> scatter on stream-ordered scratch); distances are written back through the permutation and
 // every value is unchanged.
-constexpr int M2S_BIN_RES = 32;
+#ifndef NGLOD_M2S_BIN_BITS
+#define NGLOD_M2S_BIN_BITS 5
+#endif
+constexpr int M2S_BIN_BITS = NGLOD_M2S_BIN_BITS;
+constexpr int M2S_BIN_RES = 1 << M2S_BIN_BITS;
 constexpr int M2S_BINS = M2S_BIN_RES * M2S_BIN_RES * M2S_BIN_RES;
 
 __device__ __forceinline__ int m2s_bin(float x, float y, float z) {
@@ -220,7 +262,7 @@ __device__ __forceinline__ int m2s_bin(float x, float y, float z) {
     const int bz = min(M2S_BIN_RES - 1, max(0, (int)floorf((z + 1.f) * (0.5f * M2S_BIN_RES))));
     int code = 0;
 #pragma unroll
-    for (int b = 0; b < 5; ++b) code |= (((bx >> b) & 1) << (3 * b + 2)) | (((by >> b) & 1) << (3 * b + 1)) | (((bz >> b) & 1) << (3 * b));
+    for (int b = 0; b < M2S_BIN_BITS; ++b) code |= (((bx >> b) & 1) << (3 * b + 2)) | (((by >> b) & 1) << (3 * b + 1)) | (((bz >> b) & 1) << (3 * b));
     return code;
 }
 
