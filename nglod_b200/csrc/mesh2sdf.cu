@@ -27,6 +27,10 @@ namespace {
 constexpr int M2S_THREADS = 256;
 constexpr int M2S_TILE = 48;          // triangles per shared-memory tile
 constexpr int M2S_NDIR = 13;
+#ifndef NGLOD_M2S_UNROLL
+#define NGLOD_M2S_UNROLL 1
+#endif
+constexpr int M2S_UNROLL = NGLOD_M2S_UNROLL;      // triangles per loop iteration of the main kernel
 
 struct __align__(16) TriRecord {
     float a[3], b[3], c[3];           // vertices
@@ -172,7 +176,7 @@ mesh2sdf_kernel(const float* __restrict__ points, const long long n, const TriRe
         __syncthreads();
         // All 32 lanes stay in the loop (inactive lanes carry P = 0 and never write): the rejections below are
         // warp-votes, so the branches are uniform and most (triangle, direction) pairs cost 5 instructions.
-#pragma unroll 1
+#pragma unroll (M2S_UNROLL)
         for (int tt = 0; tt < cnt; ++tt) {
             const TriRecord& r = rec[tt];
             float p0[3];
