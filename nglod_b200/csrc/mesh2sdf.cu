@@ -126,7 +126,11 @@ m2s_records_kernel(const float* __restrict__ tris, const long long num_tris, Tri
 
 __global__ void __launch_bounds__(M2S_THREADS)
 mesh2sdf_kernel(const float* __restrict__ points, const long long n, const TriRecord* __restrict__ recs,
-                const long long num_tris, float* __restrict__ dist, const int* __restrict__ perm) {
+                const long long num_tris, float* __restrict__ dist, const int* __restrict__ perm,
+                uint3* __restrict__ partial) {
+    // gridDim.y > 1: the triangle range is cut into gridDim.y slices (small batches would otherwise leave most SMs
+    // waiting on a few CTAs that each walk every triangle); slices merge their running minimum and stab masks through
+    // `partial` (atomicMin on the bits of the non-negative squared distance, atomicOr) and m2s_finish_kernel signs them.
     __shared__ TriRecord rec[M2S_TILE];
     static_assert(sizeof(TriRecord) % 16 == 0, "records are copied as 16-byte words");
     const long long i = (long long)blockIdx.x * M2S_THREADS + threadIdx.x;
@@ -165,8 +169,11 @@ mesh2sdf_kernel(const float* __restrict__ points, const long long n, const TriRe
         inv_dk2 = 1.0f / dot3(dk, dk);
     }
 
-    for (long long t0 = 0; t0 < num_tris; t0 += M2S_TILE) {
-        const int cnt = (int)min((long long)M2S_TILE, num_tris - t0);
+    const long long per_slice = ((num_tris + gridDim.y - 1) / gridDim.y + M2S_TILE - 1) / M2S_TILE * M2S_TILE;
+    const long long t_begin = (long long)blockIdx.y * per_slice;
+    const long long t_end = min(num_tris, t_begin + per_slice);
+    for (long long t0 = t_begin; t0 < t_end; t0 += M2S_TILE) {
+        const int cnt = (int)min((long long)M2S_TILE, t_end - t0);
         __syncthreads();
         {
             const uint4* src = reinterpret_cast<const uint4*>(recs + t0);
@@ -241,10 +248,32 @@ mesh2sdf_kernel(const float* __restrict__ points, const long long n, const TriRe
     }
     if (active) {
         if (mind2 < 0.0f) mind2 = 0.0f;
+        if (partial) {
+            atomicMin(&partial[i].x, __float_as_uint(mind2));
+            if (pos) atomicOr(&partial[i].y, pos);
+            if (neg) atomicOr(&partial[i].z, neg);
+            return;
+        }
         float d = sqrtf(mind2);
         if ((pos & neg) == all_dirs) d = -d;
         dist[perm ? (long long)perm[i] : i] = d;
     }
+}
+
+__global__ void __launch_bounds__(256)
+m2s_init_kernel(uint3* __restrict__ partial, const long long n) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i < n) partial[i] = make_uint3(0x7f800000u, 0u, 0u);       // {+inf, no stab hits}
+}
+
+__global__ void __launch_bounds__(256)
+m2s_finish_kernel(const uint3* __restrict__ partial, const long long n, float* __restrict__ dist, const int* __restrict__ perm) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const uint3 p = partial[i];
+    float d = sqrtf(__uint_as_float(p.x));
+    if ((p.y & p.z) == (1u << M2S_NDIR) - 1u) d = -d;
+    dist[perm ? (long long)perm[i] : i] = d;
 }
 
 // ---- spatial counting sort of the query points (32^3 Morton bins) ------------------------------------------------
@@ -345,34 +374,60 @@ extern "C" int nglod_mesh2sdf(const float* points, int64_t n, const float* tris,
     if (grid > 2147483647ll) return NGLOD_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     if (num_tris == 0) {            // no surface: the reference's min over nothing -- keep the old kernel's answer (+inf)
-        mesh2sdf_kernel<<<(int)grid, M2S_THREADS, 0, st>>>(points, (long long)n, nullptr, 0ll, dist, nullptr);
+        mesh2sdf_kernel<<<(int)grid, M2S_THREADS, 0, st>>>(points, (long long)n, nullptr, 0ll, dist, nullptr, nullptr);
         return (int)cudaGetLastError();
     }
     const bool sort = !(n < 4096 || n >= 2000000000ll || num_tris < 64);      // else too small for the sort to pay
+    // slices of the triangle range: enough CTAs for ~4 waves of the machine, at least 4 tiles per slice
+    int slices = 1;
+    {
+        const long long ctas_per_wave = (long long)nglod_sm_count() * 5;
+        long long want = (4 * ctas_per_wave + grid - 1) / grid;
+        const long long max_slices = num_tris / (4 * M2S_TILE);
+        if (want > max_slices) want = max_slices;
+        if (want > 32) want = 32;
+        if (want > 1) slices = (int)want;
+    }
     char* ws = nullptr;
     const size_t rec_bytes = ((size_t)num_tris * sizeof(TriRecord) + 255) & ~(size_t)255;
-    const size_t perm_off = rec_bytes + (sort ? (((size_t)n * 12 + 255) & ~(size_t)255) : 0);
+    const size_t part_off = rec_bytes;
+    const size_t part_bytes = slices > 1 ? (((size_t)n * sizeof(uint3) + 255) & ~(size_t)255) : 0;
+    const size_t xs_off = part_off + part_bytes;
+    const size_t perm_off = xs_off + (sort ? (((size_t)n * 12 + 255) & ~(size_t)255) : 0);
     const size_t hist_off = perm_off + (sort ? (((size_t)n * 4 + 255) & ~(size_t)255) : 0);
     NGLOD_CUDA_TRY(cudaMallocAsync(&ws, hist_off + (sort ? (size_t)M2S_BINS * 4 : 0) + 256, st));
     TriRecord* recs = reinterpret_cast<TriRecord*>(ws);
+    uint3* partial = slices > 1 ? reinterpret_cast<uint3*>(ws + part_off) : nullptr;
     m2s_records_kernel<<<(int)((num_tris + 127) / 128), 128, 0, st>>>(tris, (long long)num_tris, recs);
     int err = (int)cudaGetLastError();
-    if (!err && !sort) {
-        mesh2sdf_kernel<<<(int)grid, M2S_THREADS, 0, st>>>(points, (long long)n, recs, (long long)num_tris, dist, nullptr);
+    if (!err && partial) {
+        m2s_init_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(partial, (long long)n);
         err = (int)cudaGetLastError();
-    } else if (!err) {
-        float* xs = reinterpret_cast<float*>(ws + rec_bytes);
-        int* perm = reinterpret_cast<int*>(ws + perm_off);
+    }
+    const dim3 g2((unsigned)grid, (unsigned)slices);
+    const float* pts = points;
+    const int* perm = nullptr;
+    if (!err && sort) {
+        float* xs = reinterpret_cast<float*>(ws + xs_off);
+        int* pm = reinterpret_cast<int*>(ws + perm_off);
         int* hist = reinterpret_cast<int*>(ws + hist_off);
         err = (int)cudaMemsetAsync(hist, 0, (size_t)M2S_BINS * 4, st);
         if (!err) {
             const int nb = (int)((n + 255) / 256 < (long long)nglod_sm_count() * 8 ? (n + 255) / 256 : (long long)nglod_sm_count() * 8);
             m2s_hist_kernel<<<nb, 256, 0, st>>>(points, (long long)n, hist);
             m2s_scan_kernel<<<1, 1024, 0, st>>>(hist);
-            m2s_scatter_kernel<<<nb, 256, 0, st>>>(points, (long long)n, hist, xs, perm);
-            mesh2sdf_kernel<<<(int)grid, M2S_THREADS, 0, st>>>(xs, (long long)n, recs, (long long)num_tris, dist, perm);
+            m2s_scatter_kernel<<<nb, 256, 0, st>>>(points, (long long)n, hist, xs, pm);
             err = (int)cudaGetLastError();
+            pts = xs; perm = pm;
         }
+    }
+    if (!err) {
+        mesh2sdf_kernel<<<g2, M2S_THREADS, 0, st>>>(pts, (long long)n, recs, (long long)num_tris, dist, perm, partial);
+        err = (int)cudaGetLastError();
+    }
+    if (!err && partial) {
+        m2s_finish_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(partial, (long long)n, dist, perm);
+        err = (int)cudaGetLastError();
     }
     const int ferr = (int)cudaFreeAsync(ws, st);
     return err ? err : ferr;
