@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define NGLOD_ABI_VERSION 4
+#define NGLOD_ABI_VERSION 5
 #define NGLOD_MAX_LODS 8
 
 /* nglod_net_t.math_mode */
