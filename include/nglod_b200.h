@@ -263,7 +263,8 @@ typedef struct nglod_sparse_net {
     int32_t feature_dim;     /* 32                                                                 */
     int32_t hidden_dim;      /* 128                                                                */
     int32_t math_mode;       /* NGLOD_MATH_*                                                       */
-    int32_t reserved_;
+    int32_t pos_invariant;   /* 1: decoders take the features only (the reference's NeuralSPC, app/spc/NeuralSPC.py:91-95);
+                                0: [x, y, z, features] like OctreeSDF                                  */
     int32_t lod_voxel_offset[NGLOD_MAX_LODS + 2]; /* first voxel row of each LOD (and one past the last)  */
     const float* corner_feats;   /* [NC, feature_dim]                                              */
     const int32_t* trinkets;     /* [NV, 8] rows of corner_feats; corner k = bx + 2*by + 4*bz      */
@@ -287,6 +288,14 @@ typedef struct nglod_sparse_net {
  * SDF.cu:412-413 (Python twin: NeuralSPC.sdf / SPC.interpolate, sdf-net/app/spc/NeuralSPC.py:104-145, SPC.py:92-102). */
 int nglod_sparse_sdf_forward(const nglod_sparse_net_t* net, int32_t lod, const float* x, const int32_t* pidx,
                              int64_t n, float* out, void* stream);
+
+/* Backward of nglod_sparse_sdf_forward for training a natively sparse model (the reference's app/spc: NeuralSPC.sdf under
+ * autograd, NeuralSPC.py:104-145).  grad_out: [n] = dL/dd.  ACCUMULATES dL/d(corner_feats) into grad_corner_feats
+ * ([NC, feature_dim], every level of the query's parent chain) and dL/d{w0,b0,w1,b1}[lod] into gw0..gb1 (null = skip).
+ * Always walks the parent chain (corner_feats_summed is an inference-only accelerator). */
+int nglod_sparse_sdf_backward(const nglod_sparse_net_t* net, int32_t lod, const float* x, const int32_t* pidx, int64_t n,
+                              const float* grad_out, float* grad_corner_feats, float* gw0, float* gb0, float* gw1,
+                              float* gb1, void* stream);
 
 /* In-voxel sphere tracing over the nuggets of nglod_spc_raytrace (level lod + base_lod), ONE persistent kernel:
  * first voxel (ray_aabb) -> [sparse sdf -> step -> re-locate the voxel from the new position] x num_steps -> central-

@@ -52,7 +52,7 @@ class SparseNetStruct(ctypes.Structure):
         ("feature_dim", c_int32),
         ("hidden_dim", c_int32),
         ("math_mode", c_int32),
-        ("reserved_", c_int32),
+        ("pos_invariant", c_int32),
         ("lod_voxel_offset", c_int32 * (MAX_LODS + 2)),
         ("corner_feats", c_void_p),
         ("trinkets", c_void_p),
@@ -119,6 +119,8 @@ SIGNATURES = {
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "nglod_sparse_sdf_forward": (ctypes.c_int, [ctypes.POINTER(SparseNetStruct), c_int32, c_void_p, c_void_p, c_int64,
                                                 c_void_p, c_void_p]),
+    "nglod_sparse_sdf_backward": (ctypes.c_int, [ctypes.POINTER(SparseNetStruct), c_int32, c_void_p, c_void_p, c_int64,
+                                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "nglod_spc_sphere_trace": (ctypes.c_int, [ctypes.POINTER(SparseNetStruct), c_int32, c_void_p, c_void_p, c_void_p,
                                               c_void_p, c_int64, ctypes.POINTER(TraceOpts), c_void_p, c_void_p, c_void_p,
                                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -17,6 +17,7 @@
 //      corner (a full 128-byte line per corner per query), for every LOD <= lod;
 //      optional dL/dx with PyTorch's border-clip rule.
 #include "sdf_core.cuh"
+#include "sparse_core.cuh"
 #include <cstdlib>
 
 namespace {
@@ -356,11 +357,19 @@ __device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-template <bool FUSED_LOSS>
+// SPARSE: the features come from (and their gradients go to) the corner rows of a sparse octree model -- gather and
+// scatter walk the query's parent chain (sparse_core.cuh); `net` is then sp.sn.dec, the decoder of the LOD.
+struct SparseBwd {
+    SparseDev sn;
+    const int* pidx;        // [n] voxel index within the LOD's level
+    float* grad_cf;         // [NC, F]
+};
+
+template <bool FUSED_LOSS, bool SPARSE>
 __global__ void __launch_bounds__(BW2_THREADS, 1)
 sdf_backward_mma_kernel(const NetDev net, const GradDev grad, const float* __restrict__ x, const long long n,
                         const float* __restrict__ grad_out, const float* __restrict__ gt, const float loss_scale,
-                        float* __restrict__ loss_out) {
+                        float* __restrict__ loss_out, const SparseBwd sp) {
     extern __shared__ __align__(16) float smem[];
     sdf_stage_weights(net, smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -400,7 +409,30 @@ sdf_backward_mma_kernel(const NetDev net, const GradDev grad, const float* __res
         float px = 0.f, py = 0.f, pz = 0.f;
         if (active) { px = __ldg(x + 3 * i); py = __ldg(x + 3 * i + 1); pz = __ldg(x + 3 * i + 2); }
         // ---- A: gather
-        warp_gather_tile(net, px, py, pz, active, tile, idx, lane);
+        int vrow = 0;
+        if constexpr (SPARSE) {
+            vrow = sp.sn.vox_off + (active ? __ldg(sp.pidx + i) : 0);
+            const unsigned live = __ballot_sync(0xffffffffu, active);
+            const int n_live = __popc(live);
+            if (active) {
+                idx[__popc(live & ((1u << lane) - 1u))] = lane;
+                *reinterpret_cast<float4*>(tile + lane * NGLOD_KPAD + NGLOD_F) = make_float4(px, py, pz, 1.f);
+            }
+            __syncwarp();
+            const int sub = lane >> 3, c = lane & 7;
+            for (int r = 0; r * 4 < n_live; ++r) {
+                const int slot = r * 4 + sub;
+                const bool valid = slot < n_live;
+                const int q = idx[valid ? slot : 0];
+                const float qx = __shfl_sync(0xffffffffu, px, q), qy = __shfl_sync(0xffffffffu, py, q);
+                const float qz = __shfl_sync(0xffffffffu, pz, q);
+                const int qv = __shfl_sync(0xffffffffu, vrow, q);
+                if (valid) *reinterpret_cast<float4*>(tile + q * NGLOD_KPAD + 4 * c) = sparse_gather4(sp.sn, qx, qy, qz, qv, c);
+            }
+            __syncwarp();
+        } else {
+            warp_gather_tile(net, px, py, pz, active, tile, idx, lane);
+        }
         if (!active) {   // keep inactive rows finite and inert
 #pragma unroll
             for (int k4 = 0; k4 < NGLOD_KPAD / 4; ++k4)
@@ -570,7 +602,12 @@ sdf_backward_mma_kernel(const NetDev net, const GradDev grad, const float* __res
                 const float qx = __shfl_sync(0xffffffffu, px, q);
                 const float qy = __shfl_sync(0xffffffffu, py, q);
                 const float qz = __shfl_sync(0xffffffffu, pz, q);
-                if (valid) {
+                const int qv = __shfl_sync(0xffffffffu, vrow, q);
+                if (valid && SPARSE) {
+                    const float4 gq4 = *reinterpret_cast<const float4*>(tile + q * NGLOD_KPAD + 4 * c);
+                    if (sp.grad_cf) sparse_scatter4(sp.sn, sp.grad_cf, qx, qy, qz, qv, c, gq4);
+                }
+                if (valid && !SPARSE) {
                     const float4 gq4 = *reinterpret_cast<const float4*>(tile + q * NGLOD_KPAD + 4 * c);
 #pragma unroll
                     for (int l = 0; l < NGLOD_MAX_LODS; ++l) {
@@ -747,11 +784,12 @@ int launch_backward(const nglod_net_t* net, int lod, const nglod_net_grad_t* gra
         // second-generation kernel: 16 warps, head gradients on the tensor cores (NGLOD_BWD_GEN1=1 keeps the first)
         static const bool gen1 = getenv("NGLOD_BWD_GEN1") != nullptr;
         if (!gen1) {
-            auto k2 = sdf_backward_mma_kernel<FUSED_LOSS>;
+            auto k2 = sdf_backward_mma_kernel<FUSED_LOSS, false>;
             NGLOD_CUDA_TRY(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, BW2_SMEM_BYTES));
             const long long want2 = (n + BW2_THREADS - 1) / BW2_THREADS;
             if (want2 < grid) grid = want2;
-            k2<<<(int)grid, BW2_THREADS, BW2_SMEM_BYTES, st>>>(nd, gdv, x, (long long)n, grad_out, gt, loss_scale, loss_out);
+            k2<<<(int)grid, BW2_THREADS, BW2_SMEM_BYTES, st>>>(nd, gdv, x, (long long)n, grad_out, gt, loss_scale, loss_out,
+                                                               SparseBwd{});
             if (int e = (int)cudaGetLastError()) return e;
             return (single && cascade) ? restrict_cascade(net, lod, grad, st) : 0;
         }
@@ -781,6 +819,29 @@ extern "C" int nglod_sdf_backward(const nglod_net_t* net, int32_t lod, const flo
                                             (cudaStream_t)stream);
     return launch_backward<false, false>(net, lod, grad, x, n, grad_out, nullptr, 0.f, nullptr, nullptr,
                                          (cudaStream_t)stream);
+}
+
+extern "C" int nglod_sparse_sdf_backward(const nglod_sparse_net_t* net, int32_t lod, const float* x, const int32_t* pidx,
+                                         int64_t n, const float* grad_out, float* grad_corner_feats, float* gw0,
+                                         float* gb0, float* gw1, float* gb1, void* stream) {
+    SparseBwd sp;
+    if (int e = make_sparse_dev(net, lod, sp.sn, /*allow_summed=*/false)) return e;
+    if (n < 0 || (n > 0 && (!x || !pidx || !grad_out))) return NGLOD_EINVAL;
+    if (reinterpret_cast<uintptr_t>(grad_corner_feats) & 15u) return NGLOD_EINVAL;
+    if (n == 0) return 0;
+    sp.pidx = pidx;
+    sp.grad_cf = grad_corner_feats;
+    GradDev gdv;
+    for (int i = 0; i < NGLOD_MAX_LODS; ++i) gdv.grids[i] = nullptr;
+    gdv.w0 = gw0; gdv.b0 = gb0; gdv.w1 = gw1; gdv.b1 = gb1;
+    auto k2 = sdf_backward_mma_kernel<false, true>;
+    NGLOD_CUDA_TRY(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, BW2_SMEM_BYTES));
+    long long grid = nglod_sm_count();
+    const long long want = (n + BW2_THREADS - 1) / BW2_THREADS;
+    if (want < grid) grid = want;
+    k2<<<(int)grid, BW2_THREADS, BW2_SMEM_BYTES, (cudaStream_t)stream>>>(sp.sn.dec, gdv, x, (long long)n, grad_out, nullptr,
+                                                                         0.f, nullptr, sp);
+    return (int)cudaGetLastError();
 }
 
 extern "C" int nglod_sdf_train_step(const nglod_net_t* net, uint32_t lod_mask, const float* x, const float* gt,

@@ -247,6 +247,9 @@ class SparseOctreeSDF:
         self.lod_offset = lod_offset
         self.math_mode = getattr(net, "math_mode", "tc")
 
+    def _decoder_params(self, lod):
+        return self.net.decoder_params(lod)
+
     def save(self, path):
         """Write the reference's real-time renderer format (SOL_NGLOD.save, lib/models/SOL_NGLOD.py:80-100; read by
         sol-renderer/SDF.cu:65-139): octree bytes, corner coordinates `cc` (uint8), corner features `cf` and the
@@ -279,15 +282,16 @@ class SparseOctreeSDF:
     def struct(self):
         s = _lib.SparseNetStruct()
         s.num_lods, s.base_lod = self.num_lods, self.base_lod
-        s.feature_dim, s.hidden_dim = self.corner_feats.shape[1], self.net.hidden_dim
+        s.feature_dim, s.hidden_dim = self.corner_feats.shape[1], self._decoder_params(0)[0].shape[0]
         s.math_mode = _lib.MATH_TC3XTF32 if self.math_mode == "tc" else _lib.MATH_FP32
+        s.pos_invariant = 1 if getattr(self, "pos_invariant", False) else 0
         s.corner_feats, s.trinkets = self.corner_feats.data_ptr(), self.trinkets.data_ptr()
         s.parents, s.voxels = self.parents.data_ptr(), self.voxels.data_ptr()
-        if self.sum_lods and self.corner_feats_summed is not None:
+        if self.sum_lods and getattr(self, "corner_feats_summed", None) is not None:
             s.corner_feats_summed = self.corner_feats_summed.data_ptr()
         for i, o in enumerate(self.lod_offset):
             s.lod_voxel_offset[i] = o
-        self._keep = [tuple(p.data for p in self.net.decoder_params(i)) for i in range(self.num_lods)]
+        self._keep = [tuple(p.data for p in self._decoder_params(i)) for i in range(self.num_lods)]
         for i, (w0, b0, w1, b1) in enumerate(self._keep):
             s.w0[i], s.b0[i], s.w1[i], s.b1[i] = w0.data_ptr(), b0.data_ptr(), w1.data_ptr(), b1.data_ptr()
         return s
@@ -326,3 +330,117 @@ class SparseOctreeSDF:
                                                   _ptr(normal), _ptr(pidx), _ptr(queue), _ptr(stats), _stream()),
                        "nglod_spc_sphere_trace")
         return x, depth, hit, normal, pidx
+
+
+# ------------------------------------------------------------------------------------------------ sparse training
+def build_sparse_tables(spc, num_lods, base_lod):
+    """The reference's create_dual / create_trinkets (app/spc/spc_utils.py:91-150, a CPU dict + pandas join) as device
+    ops: per LOD l (octree level l + base_lod) the unique corners of the occupied voxels (sort + unique), every voxel's 8
+    corner rows (`trinkets`, corner k = bx + 2 by + 4 bz), its parent voxel one LOD up (binary search on Morton codes)
+    and its integer coordinates.  Returns (corner_counts, trinkets [NV,8] i32, parents [NV] i32, voxels [NV,4] i16,
+    lod_offset, corner_xyz [NC,3] long)."""
+    dev = spc.octree.device
+    trinkets, parents, voxels, counts, cxyz, lod_offset = [], [], [], [], [], [0]
+    corner_base, prev_morton = 0, None
+    off = torch.tensor([[k & 1, (k >> 1) & 1, (k >> 2) & 1] for k in range(8)], device=dev)
+    for l in range(num_lods):
+        level = l + base_lod
+        S = (1 << level) + 1
+        vox = spc.level_points(level)[:, :3].long()
+        cor = vox.unsqueeze(1) + off.unsqueeze(0)
+        key = (cor[..., 2] * S + cor[..., 1]) * S + cor[..., 0]
+        uniq, inv = torch.unique(key.reshape(-1), return_inverse=True)
+        cxyz.append(torch.stack([uniq % S, (uniq // S) % S, uniq // (S * S)], dim=1))
+        trinkets.append((inv.reshape(-1, 8) + corner_base).int())
+        morton = points_to_morton(vox)
+        if l == 0:
+            parents.append(torch.full((vox.shape[0],), -1, dtype=torch.int32, device=dev))
+        else:
+            parents.append((torch.searchsorted(prev_morton, morton >> 3) + lod_offset[l - 1]).int())
+        prev_morton = morton
+        v4 = torch.zeros(vox.shape[0], 4, dtype=torch.int16, device=dev)
+        v4[:, :3] = vox.short()
+        voxels.append(v4)
+        counts.append(int(uniq.shape[0]))
+        corner_base += int(uniq.shape[0])
+        lod_offset.append(lod_offset[-1] + vox.shape[0])
+    return (counts, torch.cat(trinkets).contiguous(), torch.cat(parents).contiguous(), torch.cat(voxels).contiguous(),
+            lod_offset, torch.cat(cxyz).contiguous())
+
+
+class _SparseSdfFunction(torch.autograd.Function):
+    """d = NeuralSPC.sdf(x, lod, pidx): sparse forward kernel; the backward recomputes it in-kernel and scatters
+    dL/d(corner features) along each query's parent chain (nglod_sparse_sdf_backward)."""
+
+    @staticmethod
+    def forward(ctx, x, pidx, module, lod, corner_feats, w0, b0, w1, b1):
+        ctx.module, ctx.lod = module, lod
+        ctx.save_for_backward(x, pidx)
+        return SparseOctreeSDF.sdf(module, x, lod, pidx)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        x, pidx = ctx.saved_tensors
+        m, lod = ctx.module, ctx.lod
+        lib = _lib.load()
+        needs = ctx.needs_input_grad
+        g_cf = torch.zeros_like(m.corner_feats) if needs[4] else None
+        gd = [torch.zeros_like(p) if needs[5 + k] else None for k, p in enumerate(m._decoder_params(lod))]
+        s = m.struct()
+        xx = _f32c(x, "x")
+        go = _f32c(grad_out, "grad_out").reshape(-1)
+        with torch.cuda.device(xx.device):
+            _lib.check(lib.nglod_sparse_sdf_backward(ctypes.byref(s), int(lod), _ptr(xx), _ptr(pidx.int().contiguous()),
+                                                     xx.shape[0], _ptr(go), _ptr(g_cf), _ptr(gd[0]), _ptr(gd[1]),
+                                                     _ptr(gd[2]), _ptr(gd[3]), _stream()), "nglod_sparse_sdf_backward")
+        return (None, None, None, None, g_cf, *gd)
+
+
+class NeuralSPC(torch.nn.Module, SparseOctreeSDF):
+    """A natively sparse, trainable OctreeSDF -- the model of the reference's app/spc (NeuralSPC.py:39-145, SPC.py:35-107):
+    features live ONLY on the corners of the occupied voxels of an octree (`corner_feats`, one nn.Parameter, all LODs
+    concatenated coarse first, N(0, feature_std) init), one decoder per LOD.  `sdf(x, lod, pidx)` sums the trilinear
+    samples along the voxel's parent chain and decodes; it is differentiable (parameters only) through the sparse
+    kernels.  `pos_invariant=True` gives the reference's feature-only decoders (BasicDecoder(feature_dim -> 1));
+    the default concatenates [x, features] like OctreeSDF.  The level-7+ models this enables have no dense grid at all."""
+
+    def __init__(self, spc, num_lods, base_lod=2, feature_dim=32, hidden_dim=128, feature_std=0.01, pos_invariant=False,
+                 math_mode="tc"):
+        torch.nn.Module.__init__(self)
+        if spc.level < num_lods + base_lod - 1:
+            raise ValueError("octree is shallower than the finest LOD")
+        self.spc, self.num_lods, self.base_lod = spc, num_lods, base_lod
+        self.pos_invariant, self.math_mode, self.sum_lods = pos_invariant, math_mode, False
+        self.corner_feats_summed = None
+        counts, self.trinkets, self.parents, self.voxels, self.lod_offset, self.corner_xyz = \
+            build_sparse_tables(spc, num_lods, base_lod)
+        self.corner_counts = counts
+        dev = spc.octree.device
+        self.corner_feats = torch.nn.Parameter(torch.randn(sum(counts), feature_dim, device=dev) * feature_std)
+        in_dim = feature_dim + (0 if pos_invariant else 3)
+        self.louts = torch.nn.ModuleList([
+            torch.nn.Sequential(torch.nn.Linear(in_dim, hidden_dim), torch.nn.ReLU(), torch.nn.Linear(hidden_dim, 1))
+            for _ in range(num_lods)]).to(dev)
+        self.lod = None
+
+    def _decoder_params(self, lod):
+        seq = self.louts[lod]
+        return (seq[0].weight, seq[0].bias, seq[2].weight, seq[2].bias)
+
+    def query(self, x, lod):
+        """Voxel index (within LOD `lod`'s level) containing each point, -1 outside the octree (SPC.query, SPC.py:86-90)."""
+        level = lod + self.base_lod
+        return self.spc.query(quantize_points(x, level), level)
+
+    def sdf(self, x, lod=None, pidx=None):
+        lod = (self.num_lods - 1 if self.lod is None else self.lod) if lod is None else lod
+        if pidx is None:
+            pidx = self.query(x, lod)
+        params = self._decoder_params(lod)
+        if torch.is_grad_enabled() and (self.corner_feats.requires_grad or any(p.requires_grad for p in params)):
+            return _SparseSdfFunction.apply(x, pidx, self, lod, self.corner_feats, *params)
+        return SparseOctreeSDF.sdf(self, x, lod, pidx)
+
+    def forward(self, x):
+        return self.sdf(x)

@@ -272,7 +272,8 @@ class OracleSparseNet:
     parents, voxel coordinates, decoders.  Follows sol-renderer/include/solr/solr/sdf/sparse_grid_sample.cuh:31-109
     (parent-chain walk, un-clamped trilinear weights from the voxel's own coordinates) and SDF.cu:412-413."""
 
-    def __init__(self, corner_feats, trinkets, parents, voxels, lod_offset, base_lod, decoders):
+    def __init__(self, corner_feats, trinkets, parents, voxels, lod_offset, base_lod, decoders, pos_invariant=False):
+        self.pos_invariant = pos_invariant           # feature-only decoders (the reference's NeuralSPC.py:91-95)
         self.cf = corner_feats.detach().cpu().float()
         self.trinkets = trinkets.detach().cpu().long()
         self.parents = parents.detach().cpu().long()
@@ -302,7 +303,8 @@ class OracleSparseNet:
 
     def sdf(self, x, lod, pidx):
         w0, b0, w1, b1 = self.dec[lod]
-        inp = torch.cat([x, self.features(x, lod, pidx)], dim=-1)
+        feat = self.features(x, lod, pidx)
+        inp = feat if self.pos_invariant else torch.cat([x, feat], dim=-1)
         return F.linear(F.relu(F.linear(inp, w0, b0)), w1, b1)
 
 

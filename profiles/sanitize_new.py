@@ -35,5 +35,10 @@ V, F = icosphere(2)
 sp = S.SparseOctreeSDF(net, S.SPC(S.mesh_to_octree(V.to(dev), F.to(dev), 4, num_samples=1 << 16)))
 sp.trace(ro, rd, 2)
 realtime.run(net, 48, 27, frames=2, lod=2)
+nspc = S.NeuralSPC(sp.spc, num_lods=3, base_lod=2)
+lp = sp.spc.level_points(4)[:, :3].float()
+pidx = torch.randint(0, lp.shape[0], (700,), device=dev)
+xs = (lp[pidx] + torch.rand(700, 3, device=dev)) / 16 * 2 - 1
+nspc.sdf(xs, 2, pidx).sum().backward()
 torch.cuda.synchronize()
 print("sanitize target done")
