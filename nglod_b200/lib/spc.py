@@ -411,7 +411,7 @@ class NeuralSPC(torch.nn.Module, SparseOctreeSDF):
         if spc.level < num_lods + base_lod - 1:
             raise ValueError("octree is shallower than the finest LOD")
         self.spc, self.num_lods, self.base_lod = spc, num_lods, base_lod
-        self.pos_invariant, self.math_mode, self.sum_lods = pos_invariant, math_mode, False
+        self.pos_invariant, self.math_mode, self.sum_lods = pos_invariant, math_mode, True
         self.corner_feats_summed = None
         counts, self.trinkets, self.parents, self.voxels, self.lod_offset, self.corner_xyz = \
             build_sparse_tables(spc, num_lods, base_lod)
@@ -427,6 +427,43 @@ class NeuralSPC(torch.nn.Module, SparseOctreeSDF):
     def _decoder_params(self, lod):
         seq = self.louts[lod]
         return (seq[0].weight, seq[0].bias, seq[2].weight, seq[2].bias)
+
+    def summed_rows(self):
+        """Prefix-summed corner rows (nglod_sparse_net_t.corner_feats_summed): row of a LOD-l corner = sum over k <= l of the
+        level-k interpolant at that corner, built level by level (each corner is evaluated in the parent of a voxel that
+        owns it; voxels sharing a corner agree because the coarser field is continuous across occupied voxels)."""
+        cf = self.corner_feats.data
+        out = cf.clone()
+        dev = cf.device
+        off = torch.tensor([[k & 1, (k >> 1) & 1, (k >> 2) & 1] for k in range(8)], device=dev)
+        for l in range(1, self.num_lods):
+            v0, v1 = self.lod_offset[l], self.lod_offset[l + 1]
+            tr = self.trinkets[v0:v1].long()
+            par = self.parents[v0:v1].long()
+            vox = self.voxels[v0:v1, :3].long()
+            pvox = self.voxels[par, :3].long()
+            ptr = self.trinkets[par].long()                               # parent's 8 corner rows (already summed)
+            pval = out[ptr]                                               # [nv, 8, F]
+            for k in range(8):
+                f = ((vox + off[k]) - 2 * pvox).float() * 0.5             # position of corner k in the parent, in {0, .5, 1}^3
+                g = 1.0 - f
+                acc = 0
+                for j in range(8):
+                    w = (f[:, 0] if j & 1 else g[:, 0]) * (f[:, 1] if j & 2 else g[:, 1]) * (f[:, 2] if j & 4 else g[:, 2])
+                    acc = acc + w.unsqueeze(1) * pval[:, j]
+                out[tr[:, k]] = cf[tr[:, k]] + acc
+        return out
+
+    def struct(self):
+        # inference (eval mode, no autograd): sample ONE level from the prefix-summed rows, rebuilt when the features change
+        if self.sum_lods and not self.training and not torch.is_grad_enabled():
+            key = (self.corner_feats._version, self.corner_feats.data_ptr())
+            if getattr(self, "_summed_key", None) != key:
+                self.corner_feats_summed, self._summed_key = self.summed_rows(), key
+        else:
+            self.corner_feats_summed = None
+            self._summed_key = None
+        return SparseOctreeSDF.struct(self)
 
     def query(self, x, lod):
         """Voxel index (within LOD `lod`'s level) containing each point, -1 outside the octree (SPC.query, SPC.py:86-90)."""

@@ -335,3 +335,16 @@ def test_neural_spc_trains_and_traces():
         x, depth, hit, normal, _ = net.trace(ro.cuda(), rd.cuda(), 2)
     assert int(hit.sum()) > 500
     assert torus_sdf(x[hit]).abs().max() < 0.03
+    # inference in eval mode samples one level of the prefix-summed corner rows: same function as the parent-chain walk
+    net.eval()
+    xs, pidx = _points_in_voxels(spc, 5, 5000, 7)
+    with torch.no_grad():
+        a = net.sdf(xs.cuda(), 2, pidx.cuda())
+        assert net.corner_feats_summed is not None
+        net.sum_lods = False
+        b = net.sdf(xs.cuda(), 2, pidx.cuda())
+        assert net.corner_feats_summed is None
+        net.sum_lods = True
+        x2, depth2, hit2, normal2, _ = net.trace(ro.cuda(), rd.cuda(), 2)
+    assert (a - b).abs().max() < 2e-6
+    assert int((hit2 != hit).sum()) <= 2
