@@ -502,6 +502,28 @@ def run_extras(net, args, device, rank, world, flush, log):
     out["render_4k_shadow"] = {"rays": w4 * h4, "rays_this_rank": s1 - s0, "ms": r4_ms, "fps": 1e3 / r4_ms,
                                "note": "primary trace + ground plane + shadow trace + normals via Renderer.render; "
                                        "ranks take contiguous column strips, no collective"}
+    # ---- a natively sparse model (features on the corners of the level-7 octree only: 128^3 has no dense grid
+    #      here) trained with autograd through the sparse kernels + torch Adam, 500 000 points inside occupied voxels
+    nspc = S.NeuralSPC(spc, num_lods=6, base_lod=2)
+    opt = torch.optim.Adam(nspc.parameters(), lr=1e-3)
+    lp7 = spc.level_points(7)[:, :3].float()
+    gs = torch.Generator(device=device).manual_seed(11 + rank)
+    pv = torch.randint(0, lp7.shape[0], (500000 // world,), device=device, generator=gs)
+    xs7 = ((lp7[pv] + torch.rand(pv.shape[0], 3, device=device, generator=gs)) / 128 * 2 - 1).contiguous()
+    gt7 = (torch.sqrt((torch.sqrt(xs7[:, 0] ** 2 + xs7[:, 2] ** 2) - 0.6) ** 2 + xs7[:, 1] ** 2) - 0.25).unsqueeze(1)
+
+    def sparse_step():
+        opt.zero_grad(set_to_none=True)
+        loss = ((nspc.sdf(xs7, 5, pv) - gt7) ** 2).mean()
+        loss.backward()
+        opt.step()
+    sp_ms = timed(sparse_step, iters=5, warm=2)
+    out["neural_spc_train_step_500k"] = {"ms_per_step": sp_ms, "points_per_s": world * pv.shape[0] / (sp_ms / 1e3),
+                                         "voxels_level7": int(lp7.shape[0]), "corner_rows": int(nspc.corner_feats.shape[0]),
+                                         "note": "NeuralSPC (6 LODs, levels 2-7), head 5: sparse forward + gen-2 sparse "
+                                                 "backward through the parent chain + torch Adam; no gradient all-reduce"}
+    del nspc, opt
+
     # ---- the headless real-time loop (ray generation -> trace -> matcap shading, frame stays on the device)
     from nglod_b200.app import realtime
     rt = {}
