@@ -66,8 +66,6 @@ class SphereTracer(BaseTracer):
                   "s_in": torch.cuda.Stream(dev), "s_out": torch.cuda.Stream(dev),
                   "s_c": [torch.cuda.Stream(dev) for _ in range(4)]}
             self._host_ws = ws
-        if ws["queue"].numel() < chunks:
-            ws["queue"] = torch.empty(chunks, dtype=torch.int32, device=dev)
         view, lod = net.net_view(), _trace_lod(net)
         cur = torch.cuda.current_stream(dev)
         s_in, s_out = ws["s_in"], ws["s_out"]
@@ -80,6 +78,8 @@ class SphereTracer(BaseTracer):
             chunks = len(bounds) - 1
         else:
             bounds = [(n * i) // chunks for i in range(chunks + 1)]
+        if ws["queue"].numel() < chunks:
+            ws["queue"] = torch.empty(chunks, dtype=torch.int32, device=dev)
         ev_in = []
         with torch.cuda.stream(s_in):
             for i in range(chunks):

@@ -11,7 +11,7 @@ n = o.shape[0]
 out = {"x": torch.empty(n, 3).pin_memory(), "depth": torch.empty(n, 1).pin_memory(), "hit": torch.empty(n, dtype=torch.bool).pin_memory(), "normal": torch.empty(n, 3).pin_memory()}
 ref = tr(net, o, d)
 import itertools
-cfgs = [dict(chunks=c, streams=s) for c in (3, 4, 5, 6) for s in (2, 3)] + [dict(fractions=f, streams=s) for f in ((0.35, 0.65, 0.85), (0.3, 0.55, 0.75, 0.9), (0.4, 0.7)) for s in (2, 3)]
+cfgs = [dict(chunks=3, streams=2)] + [dict(fractions=f, streams=2) for f in ((0.1, 0.45, 0.8), (0.15, 0.5, 0.8), (0.2, 0.6), (0.08, 0.3, 0.6, 0.85), (0.25, 0.6, 0.9))]
 for cfg in cfgs:
     ch = cfg
     for _ in range(3): rb = tr.trace_host(net, ho, hd, out=out, **cfg)

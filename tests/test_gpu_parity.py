@@ -582,6 +582,8 @@ def test_trace_host_pipelined_equals_forward(fit3):
         assert not rb.x.is_cuda
         assert torch.equal(rb.hit, ref.hit.cpu()) and torch.equal(rb.depth, ref.depth.cpu())
         assert torch.equal(rb.x, ref.x.cpu()) and torch.equal(rb.normal, ref.normal.cpu())
+    rb = tr.trace_host(net3, o.pin_memory(), d.pin_memory(), fractions=(0.1, 0.3, 0.55, 0.8, 0.95), streams=3)
+    assert torch.equal(rb.hit, ref.hit.cpu()) and torch.equal(rb.depth, ref.depth.cpu())
     with pytest.raises(RuntimeError):
         tr.trace_host(net3, o.to(DEV), d.to(DEV))
 
