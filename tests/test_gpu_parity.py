@@ -683,6 +683,13 @@ def test_model_variants_forward_backward_trace(flags, kw):
                     net.math_mode, net.sum_lods = mode, summ
                     err = (net.sdf(x.to(DEV), lod=lod).cpu() - ref).abs().max().item()
                     assert err < 1e-5, (flags, lod, mode, summ, err)
+    # fp16 x-pair lines of the summed grid (grids as small as R = 1): equals the oracle on the model's summed_state_dict
+    net.math_mode, net.sum_lods, net.grid_storage = "tc", True, "fp16"
+    with torch.no_grad():
+        for lod in sorted({0, top}):
+            oq = O.OracleNet(net.summed_state_dict(lod), **kw)
+            assert (net.sdf(x.to(DEV), lod=lod).cpu() - oq.sdf(x, lod=lod)).abs().max() < 1e-5, (flags, lod, "fp16")
+    net.grid_storage = "fp32"
     net.math_mode = "tc"
     gt = torch.rand(x.shape[0], 1, generator=g) - 0.5
     loss_ref = ((onet.sdf(x, lod=top) - gt) ** 2).mean()
