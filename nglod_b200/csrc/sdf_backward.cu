@@ -369,7 +369,9 @@ template <bool FUSED_LOSS, bool SPARSE>
 __global__ void __launch_bounds__(BW2_THREADS, 1)
 sdf_backward_mma_kernel(const NetDev net, const GradDev grad, const float* __restrict__ x, const long long n,
                         const float* __restrict__ grad_out, const float* __restrict__ gt, const float loss_scale,
-                        float* __restrict__ loss_out, const SparseBwd sp) {
+                        float* __restrict__ loss_out, const SparseBwd sp, const int lpw) {
+    // lpw = queries per warp per batch: 32, or 8 when the whole call is too small to give every SM a 512-query batch
+    // (a batch is then 128 queries: the kernel's serial phases are 3-4x shorter and 4x as many CTAs share the work)
     extern __shared__ __align__(16) float smem[];
     sdf_stage_weights(net, smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -402,10 +404,10 @@ sdf_backward_mma_kernel(const NetDev net, const GradDev grad, const float* __res
         for (int i = 0; i < 4; ++i) accT[nt][i] = 0.f;
     float acc_b1 = 0.f, acc_loss = 0.f;
 
-    const long long batch = (long long)BW2_THREADS;
+    const long long batch = (long long)BW2_WARPS * lpw;
     for (long long base0 = (long long)blockIdx.x * batch; base0 < n; base0 += (long long)gridDim.x * batch) {
-        const long long i = base0 + warp * 32 + lane;
-        const bool active = i < n;
+        const long long i = base0 + warp * lpw + lane;
+        const bool active = lane < lpw && i < n;
         float px = 0.f, py = 0.f, pz = 0.f;
         if (active) { px = __ldg(x + 3 * i); py = __ldg(x + 3 * i + 1); pz = __ldg(x + 3 * i + 2); }
         // ---- A: gather
@@ -446,6 +448,13 @@ sdf_backward_mma_kernel(const NetDev net, const GradDev grad, const float* __res
         float ginf[2][4][4];
 #pragma unroll
         for (int m = 0; m < 2; ++m) {
+            if (16 * m >= lpw) {                                      // no query rows in this m-tile (warp-uniform)
+#pragma unroll
+                for (int nf = 0; nf < 4; ++nf)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) ginf[m][nf][e] = 0.f;
+                continue;
+            }
             const int rA = 16 * m + g, rB = rA + 8;                   // this lane's two query rows of the m-tile
             uint32_t ahi[5][4], alo[5][4];
 #pragma unroll
@@ -498,7 +507,7 @@ sdf_backward_mma_kernel(const NetDev net, const GradDev grad, const float* __res
                 }
             }
             // d of the two rows (sum over the 4 lanes that share a row), upstream gradients
-            const long long iA = base0 + warp * 32 + rA, iB = iA + 8;
+            const long long iA = rA < lpw ? base0 + warp * lpw + rA : n, iB = rB < lpw ? base0 + warp * lpw + rB : n;
             float gdA = 0.f, gdB = 0.f;
             if (FUSED_LOSS) {
                 dA += __shfl_xor_sync(0xffffffffu, dA, 1); dA += __shfl_xor_sync(0xffffffffu, dA, 2);
@@ -786,10 +795,11 @@ int launch_backward(const nglod_net_t* net, int lod, const nglod_net_grad_t* gra
         if (!gen1) {
             auto k2 = sdf_backward_mma_kernel<FUSED_LOSS, false>;
             NGLOD_CUDA_TRY(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, BW2_SMEM_BYTES));
-            const long long want2 = (n + BW2_THREADS - 1) / BW2_THREADS;
+            const int lpw = n > (long long)grid * BW2_WARPS * 8 ? 32 : 8;     // 128-query batches only while they fit one wave
+            const long long want2 = (n + BW2_WARPS * lpw - 1) / (BW2_WARPS * lpw);
             if (want2 < grid) grid = want2;
             k2<<<(int)grid, BW2_THREADS, BW2_SMEM_BYTES, st>>>(nd, gdv, x, (long long)n, grad_out, gt, loss_scale, loss_out,
-                                                               SparseBwd{});
+                                                               SparseBwd{}, lpw);
             if (int e = (int)cudaGetLastError()) return e;
             return (single && cascade) ? restrict_cascade(net, lod, grad, st) : 0;
         }
@@ -837,10 +847,11 @@ extern "C" int nglod_sparse_sdf_backward(const nglod_sparse_net_t* net, int32_t 
     auto k2 = sdf_backward_mma_kernel<false, true>;
     NGLOD_CUDA_TRY(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, BW2_SMEM_BYTES));
     long long grid = nglod_sm_count();
-    const long long want = (n + BW2_THREADS - 1) / BW2_THREADS;
+    const int lpw = n > (long long)grid * BW2_WARPS * 8 ? 32 : 8;     // 128-query batches only while they fit one wave
+    const long long want = (n + BW2_WARPS * lpw - 1) / (BW2_WARPS * lpw);
     if (want < grid) grid = want;
     k2<<<(int)grid, BW2_THREADS, BW2_SMEM_BYTES, (cudaStream_t)stream>>>(sp.sn.dec, gdv, x, (long long)n, grad_out, nullptr,
-                                                                         0.f, nullptr, sp);
+                                                                         0.f, nullptr, sp, lpw);
     return (int)cudaGetLastError();
 }
 

@@ -114,8 +114,10 @@ class OctreeSDF(BaseLOD):
         return all(res[i] % res[j] == 0 for i in range(len(res)) for j in range(i))
 
     def mark_grids_dirty(self):
-        """Call after writing the grids behind torch's back (`.data` / raw pointers, e.g. the fused Adam kernel)."""
-        self._derived = None
+        """Call after writing the grids behind torch's back (`.data` / raw pointers, e.g. the fused Adam kernel).  The
+        derived buffers themselves are kept (a captured CUDA graph of the training step rebuilds them in place)."""
+        if self._derived is not None:
+            self._derived[0] = None
 
     def _derived_grids(self, want_half=False):
         """(summed, summed_half) rebuilt when a grid was written or moved; the fp16 copy only when asked for."""
@@ -124,14 +126,18 @@ class OctreeSDF(BaseLOD):
             grids = [f.fm.data for f in self.features]
             base = ops.NetView.grids_only(grids)
             old = self._derived[1] if self._derived is not None else [None] * len(grids)
+            old_half = self._derived[2] if self._derived is not None else None
             summed = []
             for i, (g, o) in enumerate(zip(grids, old)):      # ascending: level i = prolongation of level i-1 + grid i
                 if i > 0:
                     base.struct.summed[i - 1] = summed[i - 1].data_ptr()
                 summed.append(ops.build_summed_grid(base, i, out=o if (o is not None and o.device == g.device) else None))
-            self._derived = [key, summed, None]
+            self._derived = [key, summed, None, old_half]
         if want_half and self._derived[2] is None:
-            self._derived[2] = [ops.pack_grid_fp16(sg) for sg in self._derived[1]]
+            oh = self._derived[3] if len(self._derived) > 3 and self._derived[3] is not None else [None] * len(self._derived[1])
+            self._derived[2] = [ops.pack_grid_fp16(sg, out=o if (o is not None and o.device == sg.device) else None)
+                                for sg, o in zip(self._derived[1], oh)]
+            self._derived[3] = None
         return self._derived[1], (self._derived[2] if want_half else None)
 
     def summed_grad_scratch(self):
@@ -156,13 +162,14 @@ class OctreeSDF(BaseLOD):
         sd[f"features.{lod}.fm"] = top.half().float() if self.grid_storage == "fp16" else top
         return sd
 
-    def net_view(self, inference=True):
+    def net_view(self, inference=True, use_summed=True):
         """Borrow the current parameters as an nglod_net_t (rebuilt per call: pointers may move).  inference=False (the
-        autograd / training kernels) never attaches the half-precision copy."""
+        autograd / training kernels) never attaches the half-precision copy; use_summed=False leaves the prefix-summed
+        grids out (small training batches: rebuilding them costs more than five short gathers)."""
         grids = [f.fm.data for f in self.features]
         decs = [tuple(p.data for p in self.decoder_params(i)) for i in range(self.num_lods)]
         summed = half = None
-        if self.sum_lods and self._grids_nest():
+        if use_summed and self.sum_lods and self._grids_nest():
             summed, half = self._derived_grids(want_half=inference and self.grid_storage == "fp16" and self.math_mode == "tc")
         return ops.NetView(grids, decs, pos_invariant=self.pos_invariant,
                            math_mode=_lib.MATH_TC3XTF32 if self.math_mode == "tc" else _lib.MATH_FP32,
