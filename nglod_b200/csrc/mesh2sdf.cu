@@ -27,6 +27,7 @@ namespace {
 constexpr int M2S_THREADS = 256;
 constexpr int M2S_TILE = 48;          // triangles per shared-memory tile
 constexpr int M2S_NDIR = 13;
+constexpr int M2S_PATCH = 32;         // triangles per patch of the culling hierarchy (one lane each)
 #ifndef NGLOD_M2S_UNROLL
 #define NGLOD_M2S_UNROLL 1
 #endif
@@ -119,9 +120,114 @@ __device__ void build_record(const float* __restrict__ tri, TriRecord& r) {
 // CTA per tile made two warps of every CTA redo ~500 instructions per triangle while the other six waited at the
 // barrier -- half of the kernel's time at 500 k points x 16 k triangles.
 __global__ void __launch_bounds__(128)
-m2s_records_kernel(const float* __restrict__ tris, const long long num_tris, TriRecord* __restrict__ recs) {
+m2s_records_kernel(const float* __restrict__ tris, const long long num_tris, TriRecord* __restrict__ recs,
+                   const int* __restrict__ tri_perm, float4* __restrict__ tsph, unsigned* __restrict__ tflags) {
     const long long t = (long long)blockIdx.x * 128 + threadIdx.x;
-    if (t < num_tris) build_record(tris + t * 9, recs[t]);
+    if (t >= num_tris) return;
+    TriRecord& r = recs[t];
+    build_record(tris + (tri_perm ? (long long)tri_perm[t] : t) * 9, r);
+    if (tsph) {                 // compact copy of what the culling levels read: bounding sphere, usable directions
+        tsph[t] = make_float4(r.cen[0], r.cen[1], r.cen[2], r.rad);
+        tflags[t] = r.dir_ok | (r.nondegenerate ? 0x80000000u : 0u);
+    }
+}
+
+// Centroids of the triangles, as input of the same counting sort the query points go through: after it a patch of
+// M2S_PATCH consecutive records is a small piece of the surface and one bounding sphere describes it well.
+__global__ void __launch_bounds__(128)
+m2s_centroid_kernel(const float* __restrict__ tris, const long long num_tris, float* __restrict__ cen) {
+    const long long t = (long long)blockIdx.x * 128 + threadIdx.x;
+    if (t >= num_tris) return;
+    const float* v = tris + t * 9;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) cen[3 * t + k] = (__ldg(v + k) + __ldg(v + 3 + k) + __ldg(v + 6 + k)) * (1.0f / 3.0f);
+}
+
+// One bounding sphere per patch: {centre, radius}; the radius is negated when the patch holds no triangle a distance
+// can come from (all degenerate), so that it cannot serve as an upper bound.  Culling only.
+__global__ void __launch_bounds__(128)
+m2s_patch_sphere_kernel(const float4* __restrict__ tsph, const unsigned* __restrict__ tflags, const long long num_tris,
+                        float4* __restrict__ spheres, const long long num_patches) {
+    const long long patch = (long long)blockIdx.x * 128 + threadIdx.x;
+    if (patch >= num_patches) return;
+    const long long t0 = patch * M2S_PATCH;
+    const int cnt = (int)min((long long)M2S_PATCH, num_tris - t0);
+    float c[3] = {0.f, 0.f, 0.f};
+    for (int j = 0; j < cnt; ++j) { const float4 s = tsph[t0 + j]; c[0] += s.x; c[1] += s.y; c[2] += s.z; }
+    const float inv = 1.0f / (float)cnt;
+    c[0] *= inv; c[1] *= inv; c[2] *= inv;
+    float rad = 0.f;
+    bool any_nondeg = false;
+    for (int j = 0; j < cnt; ++j) {
+        const float4 s = tsph[t0 + j];
+        const float e[3] = {s.x - c[0], s.y - c[1], s.z - c[2]};
+        rad = fmaxf(rad, sqrtf(dot3(e, e)) * 1.0001f + s.w);
+        any_nondeg |= (tflags[t0 + j] >> 31) != 0;
+    }
+    rad = rad * 1.0001f + 1e-6f;
+    if (!(rad == rad) || !(c[0] == c[0]) || !(c[1] == c[1]) || !(c[2] == c[2])) {       // NaN vertices: never culled
+        c[0] = c[1] = c[2] = 0.f; rad = INFINITY; any_nondeg = false;
+    }
+    spheres[patch] = make_float4(c[0], c[1], c[2], any_nondeg ? rad : -rad);
+}
+
+// ---- the exact per-(point, triangle) arithmetic, shared by both kernels ------------------------------------------
+// squared distance to the triangle (edge / face branch as in the reference)
+__device__ __forceinline__ float m2s_tri_dist2(const TriRecord& r, const float* P, const float* p0) {
+    float p1[3], p2[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { p1[k] = P[k] - r.b[k]; p2[k] = P[k] - r.c[k]; }
+    const float s1 = copysignf(1.0f, dot3(r.c10, p0));
+    const float s2 = copysignf(1.0f, dot3(r.c21, p1));
+    const float s3 = copysignf(1.0f, dot3(r.c02, p2));
+    float d2;
+    if ((s1 + s2 + s3) < 2.0f) {
+        const float e1 = d2axmb(r.v10, clamp01(dot3(r.v10, p0) * r.inv10), p0);
+        const float e2 = d2axmb(r.v21, clamp01(dot3(r.v21, p1) * r.inv21), p1);
+        const float e3 = d2axmb(r.v02, clamp01(dot3(r.v02, p2) * r.inv02), p2);
+        d2 = fminf(e1, fminf(e2, e3));
+    } else {
+        d2 = dot3(r.nor, p0) * dot3(r.nor, p0) * r.invn;
+    }
+    if (d2 < 0.0f) d2 = 0.0f;
+    return d2;
+}
+
+// Moller-Trumbore line stabs for the directions in `dirs` (warp-uniform); qvec and edge2.qvec do not depend on the direction
+__device__ __forceinline__ void m2s_tri_stabs(const TriRecord& r, const float* p0, const unsigned dirs, unsigned& pos, unsigned& neg) {
+    float qvec[3];
+    cross3(p0, r.v10, qvec);
+    const float edge2[3] = {-r.v02[0], -r.v02[1], -r.v02[2]};
+    const float e2q = dot3(edge2, qvec);
+#pragma unroll
+    for (int k = 0; k < M2S_NDIR; ++k) {
+        if (!((dirs >> k) & 1u)) continue;                     // warp-uniform
+        const float inv_det = r.inv_det[k];
+        const float u = dot3(p0, r.pvec[k]) * inv_det;
+        const bool pu = !(u < 0.0f || u > 1.0f);
+        if (!__any_sync(0xffffffffu, pu)) continue;            // no lane's line crosses this slab
+        const float v = dot3(c_stab_dir[k], qvec) * inv_det;
+        const bool pv = pu && !(v < 0.0f || u + v > 1.0f);
+        const float t = e2q * inv_det;
+        if (pv) { if (t >= 0.0f) pos |= 1u << k; else neg |= 1u << k; }
+    }
+}
+
+// Bounding sphere of a warp's points (neighbours after the spatial sort).
+__device__ __forceinline__ void m2s_warp_sphere(const float* P, const bool active, float* wc, float& wr) {
+    const unsigned am = __ballot_sync(0xffffffffu, active);
+    const float cnt = (float)max(__popc(am), 1);
+    float sx = active ? P[0] : 0.f, sy = active ? P[1] : 0.f, sz = active ? P[2] : 0.f;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        sx += __shfl_xor_sync(0xffffffffu, sx, o); sy += __shfl_xor_sync(0xffffffffu, sy, o); sz += __shfl_xor_sync(0xffffffffu, sz, o);
+    }
+    wc[0] = sx / cnt; wc[1] = sy / cnt; wc[2] = sz / cnt;
+    const float ex = P[0] - wc[0], ey = P[1] - wc[1], ez = P[2] - wc[2];
+    float r2 = active ? ex * ex + ey * ey + ez * ez : 0.f;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) r2 = fmaxf(r2, __shfl_xor_sync(0xffffffffu, r2, o));
+    wr = sqrtf(r2) * 1.001f + 1e-6f;
 }
 
 __global__ void __launch_bounds__(M2S_THREADS)
@@ -148,21 +254,7 @@ mesh2sdf_kernel(const float* __restrict__ points, const long long n, const TriRe
     // conservative (generous slack), so every decision and every distance is unchanged.
     const int lane = threadIdx.x & 31;
     float wc[3], wr;
-    {
-        const unsigned am = __ballot_sync(0xffffffffu, active);
-        const float cnt = (float)max(__popc(am), 1);
-        float sx = active ? P[0] : 0.f, sy = active ? P[1] : 0.f, sz = active ? P[2] : 0.f;
-#pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) {
-            sx += __shfl_xor_sync(0xffffffffu, sx, o); sy += __shfl_xor_sync(0xffffffffu, sy, o); sz += __shfl_xor_sync(0xffffffffu, sz, o);
-        }
-        wc[0] = sx / cnt; wc[1] = sy / cnt; wc[2] = sz / cnt;
-        const float ex = P[0] - wc[0], ey = P[1] - wc[1], ez = P[2] - wc[2];
-        float r2 = active ? ex * ex + ey * ey + ez * ez : 0.f;
-#pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) r2 = fmaxf(r2, __shfl_xor_sync(0xffffffffu, r2, o));
-        wr = sqrtf(r2) * 1.001f + 1e-6f;
-    }
+    m2s_warp_sphere(P, active, wc, wr);
     float dk[3] = {0.f, 0.f, 0.f}, inv_dk2 = 0.f;            // this lane's direction (lanes >= 13: none)
     if (lane < M2S_NDIR) {
         dk[0] = c_stab_dir[lane][0]; dk[1] = c_stab_dir[lane][1]; dk[2] = c_stab_dir[lane][2];
@@ -195,22 +287,7 @@ mesh2sdf_kernel(const float* __restrict__ points, const long long n, const TriRe
             const float reach = mind + r.rad;
             const bool near = r.nondegenerate && !(dot3(pc, pc) > reach * reach * 1.00001f);
             if (__any_sync(0xffffffffu, near)) {
-                float p1[3], p2[3];
-#pragma unroll
-                for (int k = 0; k < 3; ++k) { p1[k] = P[k] - r.b[k]; p2[k] = P[k] - r.c[k]; }
-                const float s1 = copysignf(1.0f, dot3(r.c10, p0));
-                const float s2 = copysignf(1.0f, dot3(r.c21, p1));
-                const float s3 = copysignf(1.0f, dot3(r.c02, p2));
-                float d2;
-                if ((s1 + s2 + s3) < 2.0f) {
-                    const float e1 = d2axmb(r.v10, clamp01(dot3(r.v10, p0) * r.inv10), p0);
-                    const float e2 = d2axmb(r.v21, clamp01(dot3(r.v21, p1) * r.inv21), p1);
-                    const float e3 = d2axmb(r.v02, clamp01(dot3(r.v02, p2) * r.inv02), p2);
-                    d2 = fminf(e1, fminf(e2, e3));
-                } else {
-                    d2 = dot3(r.nor, p0) * dot3(r.nor, p0) * r.invn;
-                }
-                if (d2 < 0.0f) d2 = 0.0f;
+                const float d2 = m2s_tri_dist2(r, P, p0);
                 if (near && d2 < mind2) { mind2 = d2; mind = sqrtf(d2) * 1.00001f; }
             }
             // 13 line stabs (Moller-Trumbore); qvec and edge2.qvec do not depend on the direction
@@ -227,22 +304,7 @@ mesh2sdf_kernel(const float* __restrict__ points, const long long n, const TriRe
                 }
                 const unsigned dirs = __ballot_sync(0xffffffffu, maybe) & r.dir_ok;
                 if (!dirs) continue;
-                float qvec[3];
-                cross3(p0, r.v10, qvec);
-                const float edge2[3] = {-r.v02[0], -r.v02[1], -r.v02[2]};
-                const float e2q = dot3(edge2, qvec);
-#pragma unroll
-                for (int k = 0; k < M2S_NDIR; ++k) {
-                    if (!((dirs >> k) & 1u)) continue;                     // warp-uniform
-                    const float inv_det = r.inv_det[k];
-                    const float u = dot3(p0, r.pvec[k]) * inv_det;
-                    const bool pu = !(u < 0.0f || u > 1.0f);
-                    if (!__any_sync(0xffffffffu, pu)) continue;            // no lane's line crosses this slab
-                    const float v = dot3(c_stab_dir[k], qvec) * inv_det;
-                    const bool pv = pu && !(v < 0.0f || u + v > 1.0f);
-                    const float t = e2q * inv_det;
-                    if (pv) { if (t >= 0.0f) pos |= 1u << k; else neg |= 1u << k; }
-                }
+                m2s_tri_stabs(r, p0, dirs, pos, neg);
             }
         }
     }
@@ -257,6 +319,210 @@ mesh2sdf_kernel(const float* __restrict__ points, const long long n, const TriRe
         float d = sqrtf(mind2);
         if ((pos & neg) == all_dirs) d = -d;
         dist[perm ? (long long)perm[i] : i] = d;
+    }
+}
+
+// ---- large batches: distance and sign by two output-sensitive kernels ---------------------------------------------
+// The brute-force walk above spends almost all of its time dismissing (warp, triangle) pairs one triangle at a time.
+// For large batches the two halves of the answer are computed separately, each touching only the pairs that matter;
+// the exact per-pair arithmetic is the same code, and min / OR do not depend on which dismissed pairs were skipped or on
+// the order, so every distance and every sign equals the brute-force walk bit for bit (A/B test in tests/).
+//
+// (1) DISTANCE, point-driven.  The records are sorted along a Morton curve (a patch of 32 consecutive records is a small
+//     piece of surface).  A warp, on its own (no shared memory, no barriers): one PATCH per lane -- keep it if its sphere
+//     could hold a closer triangle for one of the warp's points; for every kept patch one TRIANGLE per lane, the same test
+//     on the triangle's sphere; the survivors, one after the other, through the exact arithmetic.  The bound starts from
+//     an upper bound read off the patch spheres and tightens as the warp goes.
+//
+// (2) SIGN, triangle-driven.  A line through P along stab direction k hits a triangle only if P's projection along k
+//     falls inside the triangle's projection.  For each of the 13 directions the points are binned on a G x G grid of the
+//     plane across it (one counting sort over all 13 x G x G cells; exactly 13 n entries, so the scratch is bounded
+//     without a host round trip).  One warp per (triangle, direction) walks the cells under the triangle's projected
+//     bounding box -- widened by the worst rounding error of the exact test, which grows as the line grazes the
+//     triangle's plane -- and runs the exact test on the points binned there, one point per lane, OR-ing the 13-bit
+//     masks of the points it hits.
+constexpr int M2S_WARP_THREADS = 128;
+#ifndef NGLOD_M2S_HIER_MIN
+#define NGLOD_M2S_HIER_MIN 16384
+#endif
+constexpr long long M2S_HIER_MIN_POINTS = NGLOD_M2S_HIER_MIN;
+constexpr float M2S_PROJ_R = 1.8f;          // the projected grids span [-R, R]^2 (> sqrt(3)); points beyond clamp to the rim
+
+__global__ void __launch_bounds__(M2S_WARP_THREADS)
+mesh2sdf_dist_kernel(const float* __restrict__ points, const long long n, const TriRecord* __restrict__ recs,
+                     const float4* __restrict__ tsph, const unsigned* __restrict__ tflags,
+                     const float4* __restrict__ patches, const long long num_tris, uint3* __restrict__ partial) {
+    const long long i = (long long)blockIdx.x * M2S_WARP_THREADS + threadIdx.x;
+    const bool active = i < n;
+    const int lane = threadIdx.x & 31;
+    float P[3] = {0.f, 0.f, 0.f};
+    if (active) { P[0] = __ldg(points + 3 * i); P[1] = __ldg(points + 3 * i + 1); P[2] = __ldg(points + 3 * i + 2); }
+    {   // lanes past the end shadow the warp's first point: they never write and must not widen the votes below
+        const unsigned am = __ballot_sync(0xffffffffu, active);
+        if (am == 0u) return;
+        const int src = __ffs(am) - 1;
+        const float q0 = __shfl_sync(0xffffffffu, P[0], src), q1 = __shfl_sync(0xffffffffu, P[1], src), q2 = __shfl_sync(0xffffffffu, P[2], src);
+        if (!active) { P[0] = q0; P[1] = q1; P[2] = q2; }
+    }
+    float wc[3], wr;
+    m2s_warp_sphere(P, true, wc, wr);
+    float mind2 = INFINITY;
+    const long long num_patches = (num_tris + M2S_PATCH - 1) / M2S_PATCH;
+    float mind;                     // culling bound: starts as an upper bound of every lane's distance
+    {
+        float ub = INFINITY;
+        for (long long pt = lane; pt < num_patches; pt += 32) {
+            const float4 s = __ldg(patches + pt);
+            const float v[3] = {s.x - wc[0], s.y - wc[1], s.z - wc[2]};
+            if (s.w >= 0.0f) ub = fminf(ub, sqrtf(dot3(v, v)) + s.w);
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) ub = fminf(ub, __shfl_xor_sync(0xffffffffu, ub, o));
+        mind = (ub + wr) * 1.0001f + 1e-6f;
+    }
+    // gridDim.y slices of the patch range: points near the medial axis (the centre of a sphere, the axis of a torus) are
+    // equally far from a large part of the surface, no bound can dismiss it, and the few warps holding them would walk
+    // tens of thousands of triangles while the machine idles; sliced, that walk is spread over gridDim.y warps.
+    const long long per_slice = (num_patches + gridDim.y - 1) / gridDim.y;
+    const long long patch_begin = (long long)blockIdx.y * per_slice;
+    const long long patch_end = min(num_patches, patch_begin + per_slice);
+    float wmind = mind;             // loosest running bound in the warp
+    for (long long pbase = patch_begin; pbase < patch_end; pbase += 32) {
+        bool keep = false;
+        if (pbase + lane < patch_end) {
+            const float4 s = __ldg(patches + pbase + lane);
+            const float v[3] = {s.x - wc[0], s.y - wc[1], s.z - wc[2]};
+            const float reach = (wmind + fabsf(s.w) + wr) * 1.001f + 1e-5f;
+            keep = !(dot3(v, v) > reach * reach);
+        }
+        unsigned pmask = __ballot_sync(0xffffffffu, keep);
+        while (pmask) {
+            const int pb = __ffs(pmask) - 1;
+            pmask &= pmask - 1;
+            const long long t0 = (pbase + pb) * M2S_PATCH;
+            bool near_l = false;
+            if (t0 + lane < num_tris && (__ldg(tflags + t0 + lane) >> 31)) {
+                const float4 s = __ldg(tsph + t0 + lane);
+                const float v[3] = {s.x - wc[0], s.y - wc[1], s.z - wc[2]};
+                const float reach = (wmind + s.w + wr) * 1.001f + 1e-5f;
+                near_l = !(dot3(v, v) > reach * reach);
+            }
+            unsigned surv = __ballot_sync(0xffffffffu, near_l);
+            if (!surv) continue;
+            while (surv) {
+                const int j = __ffs(surv) - 1;
+                surv &= surv - 1;
+                const TriRecord& r = recs[t0 + j];
+                const float pc[3] = {P[0] - r.cen[0], P[1] - r.cen[1], P[2] - r.cen[2]};
+                const float reach = mind + r.rad;
+                const bool near = !(dot3(pc, pc) > reach * reach * 1.00001f);
+                if (__any_sync(0xffffffffu, near)) {
+                    float p0[3];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) p0[k] = P[k] - r.a[k];
+                    const float d2 = m2s_tri_dist2(r, P, p0);
+                    if (near && d2 < mind2) { mind2 = d2; mind = fminf(mind, sqrtf(d2) * 1.00001f); }
+                }
+            }
+            wmind = mind;
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) wmind = fmaxf(wmind, __shfl_xor_sync(0xffffffffu, wmind, o));
+        }
+    }
+    if (active && mind2 < INFINITY) atomicMin(&partial[i].x, __float_as_uint(mind2));       // .y / .z belong to the stab kernel
+}
+
+// two unit vectors across stab direction k (any fixed pair works: points and triangles use the same one)
+__device__ __forceinline__ void m2s_stab_basis(const int k, float* e1, float* e2) {
+    const float d[3] = {c_stab_dir[k][0], c_stab_dir[k][1], c_stab_dir[k][2]};
+    const float ax = fabsf(d[0]), ay = fabsf(d[1]), az = fabsf(d[2]);
+    float a[3] = {0.f, 0.f, 0.f};
+    if (ax <= ay && ax <= az) a[0] = 1.f; else if (ay <= az) a[1] = 1.f; else a[2] = 1.f;
+    cross3(d, a, e1);
+    const float n1 = 1.0f / sqrtf(dot3(e1, e1));
+    e1[0] *= n1; e1[1] *= n1; e1[2] *= n1;
+    cross3(d, e1, e2);
+    const float n2 = 1.0f / sqrtf(dot3(e2, e2));
+    e2[0] *= n2; e2[1] *= n2; e2[2] *= n2;
+}
+
+// cell coordinate of a projected coordinate: monotone in c, clamped to the grid (NaN -> 0)
+__device__ __forceinline__ int m2s_proj_cell(const float c, const float inv_h, const int G) {
+    const float f = floorf((c + M2S_PROJ_R) * inv_h);
+    return (int)fminf(fmaxf(f, 0.0f), (float)(G - 1));
+}
+
+// pass 1 (cursor == counts, pidx == nullptr): histogram of the 13 projected cells of every point;
+// pass 2 (cursor == exclusive offsets): scatter the point indices; afterwards cursor[c] is the END of cell c.
+__global__ void __launch_bounds__(256)
+m2s_proj_bin_kernel(const float* __restrict__ x, const long long n, const int G, int* __restrict__ cursor,
+                    int* __restrict__ pidx) {
+    __shared__ float basis[M2S_NDIR][6];
+    if (threadIdx.x < M2S_NDIR) m2s_stab_basis(threadIdx.x, basis[threadIdx.x], basis[threadIdx.x] + 3);
+    __syncthreads();
+    const float inv_h = (float)G / (2.0f * M2S_PROJ_R);
+    const long long stride = (long long)gridDim.x * 256;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) {
+        const float P[3] = {__ldg(x + 3 * i), __ldg(x + 3 * i + 1), __ldg(x + 3 * i + 2)};
+#pragma unroll 1
+        for (int k = 0; k < M2S_NDIR; ++k) {
+            const int cx = m2s_proj_cell(dot3(P, basis[k]), inv_h, G);
+            const int cy = m2s_proj_cell(dot3(P, basis[k] + 3), inv_h, G);
+            const int slot = atomicAdd(cursor + ((long long)k * G + cy) * G + cx, 1);
+            if (pidx) pidx[slot] = (int)i;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(M2S_WARP_THREADS)
+mesh2sdf_stab_kernel(const float* __restrict__ points, const TriRecord* __restrict__ recs, const long long num_tris,
+                     const int G, const int* __restrict__ cell_end, const int* __restrict__ pidx,
+                     uint3* __restrict__ partial) {
+    const int lane = threadIdx.x & 31;
+    const long long task = (long long)blockIdx.x * (M2S_WARP_THREADS / 32) + (threadIdx.x >> 5);
+    const long long t = task / M2S_NDIR;
+    const int k = (int)(task - t * M2S_NDIR);
+    if (t >= num_tris) return;
+    const TriRecord& r = recs[t];
+    if (!((r.dir_ok >> k) & 1u)) return;
+    float e1[3], e2[3];
+    m2s_stab_basis(k, e1, e2);
+    const float inv_det = r.inv_det[k];
+    // widest rounding error of u / v, as a displacement along the edges: ~eps |p0| |v10| |v02| / |det|  (|p0| <= ~4)
+    float m = (1e-5f + 2e-6f * sqrtf(dot3(r.v10, r.v10) * dot3(r.v02, r.v02)) * fabsf(inv_det)) * 1.01f;
+    if (!(m < 8.0f)) m = 8.0f;                                   // also catches NaN: walk the whole grid
+    const float xa = dot3(r.a, e1), xb = dot3(r.b, e1), xc = dot3(r.c, e1);
+    const float ya = dot3(r.a, e2), yb = dot3(r.b, e2), yc = dot3(r.c, e2);
+    const float inv_h = (float)G / (2.0f * M2S_PROJ_R);
+    int cx0 = m2s_proj_cell(fminf(xa, fminf(xb, xc)) - m, inv_h, G), cx1 = m2s_proj_cell(fmaxf(xa, fmaxf(xb, xc)) + m, inv_h, G);
+    int cy0 = m2s_proj_cell(fminf(ya, fminf(yb, yc)) - m, inv_h, G), cy1 = m2s_proj_cell(fmaxf(ya, fmaxf(yb, yc)) + m, inv_h, G);
+    if (!(xa == xa && xb == xb && xc == xc && ya == ya && yb == yb && yc == yc)) { cx0 = cy0 = 0; cx1 = cy1 = G - 1; }
+    const float edge2[3] = {-r.v02[0], -r.v02[1], -r.v02[2]};
+    const float pv[3] = {r.pvec[k][0], r.pvec[k][1], r.pvec[k][2]};
+    const float a[3] = {r.a[0], r.a[1], r.a[2]};
+    const float v10[3] = {r.v10[0], r.v10[1], r.v10[2]};
+    const unsigned bit = 1u << k;
+    for (int cy = cy0; cy <= cy1; ++cy) {
+        const long long c0 = ((long long)k * G + cy) * G + cx0, c1 = ((long long)k * G + cy) * G + cx1;
+        const int begin = c0 ? __ldg(cell_end + c0 - 1) : 0;
+        const int end = __ldg(cell_end + c1);
+        for (int jj = begin + lane; jj < end; jj += 32) {
+            const long long i = __ldg(pidx + jj);
+            const float P[3] = {__ldg(points + 3 * i), __ldg(points + 3 * i + 1), __ldg(points + 3 * i + 2)};
+            float p0[3];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) p0[q] = P[q] - a[q];
+            // the same expressions as m2s_tri_stabs
+            const float u = dot3(p0, pv) * inv_det;
+            if (u < 0.0f || u > 1.0f) continue;
+            float qvec[3];
+            cross3(p0, v10, qvec);
+            const float e2q = dot3(edge2, qvec);
+            const float v = dot3(c_stab_dir[k], qvec) * inv_det;
+            if (v < 0.0f || u + v > 1.0f) continue;
+            const float tt = e2q * inv_det;
+            if (tt >= 0.0f) atomicOr(&partial[i].y, bit); else atomicOr(&partial[i].z, bit);
+        }
     }
 }
 
@@ -307,13 +573,13 @@ m2s_hist_kernel(const float* __restrict__ x, const long long n, int* __restrict_
 }
 
 __global__ void __launch_bounds__(1024)
-m2s_scan_kernel(int* __restrict__ hist) {      // in place: counts -> exclusive offsets (32768 bins, one block)
+m2s_scan_kernel(int* __restrict__ hist, const int nbins) {      // in place: counts -> exclusive offsets (nbins % 1024 == 0, one block)
     __shared__ int warp_sums[32];
     __shared__ int carry;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int base = 0; base < M2S_BINS; base += 1024) {
+    for (int base = 0; base < nbins; base += 1024) {
         const int v = hist[base + threadIdx.x];
         int incl = v;
 #pragma unroll
@@ -333,6 +599,35 @@ m2s_scan_kernel(int* __restrict__ hist) {      // in place: counts -> exclusive 
         if (threadIdx.x == 1023) carry = tot;
         __syncthreads();
     }
+}
+
+// Large bin counts (the 13 projected grids): 1024 bins per block, then the block totals through the one-block scan above.
+__global__ void __launch_bounds__(1024)
+m2s_scan_local_kernel(int* __restrict__ hist, int* __restrict__ block_sums) {       // gridDim.x * 1024 bins
+    __shared__ int warp_sums[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long idx = (long long)blockIdx.x * 1024 + threadIdx.x;
+    const int v = hist[idx];
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = warp_sums[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+        warp_sums[lane] = w;
+    }
+    __syncthreads();
+    const int tot = incl + (warp ? warp_sums[warp - 1] : 0);
+    hist[idx] = tot - v;
+    if (threadIdx.x == 1023) block_sums[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(1024)
+m2s_scan_add_kernel(int* __restrict__ hist, const int* __restrict__ block_offsets) {
+    hist[(long long)blockIdx.x * 1024 + threadIdx.x] += block_offsets[blockIdx.x];
 }
 
 __global__ void __launch_bounds__(256)
@@ -378,9 +673,18 @@ extern "C" int nglod_mesh2sdf(const float* points, int64_t n, const float* tris,
         return (int)cudaGetLastError();
     }
     const bool sort = !(n < 4096 || n >= 2000000000ll || num_tris < 64);      // else too small for the sort to pay
-    // slices of the triangle range: enough CTAs for ~4 waves of the machine, at least 4 tiles per slice
+    // Large batches: distance and sign by the two output-sensitive kernels.  Their set-up (two more counting sorts, the
+    // 13 projected grids) costs a fixed ~0.5 ms, so small batches keep the sliced brute-force walk.
+    // NGLOD_M2S_BRUTE=1 forces the walk: the A/B switch of the parity test.
+    const bool hier = getenv("NGLOD_M2S_BRUTE") == nullptr && sort && n >= M2S_HIER_MIN_POINTS &&
+                      num_tris >= 4 * M2S_PATCH && num_tris < 100000000ll && n * M2S_NDIR < 2000000000ll;
+    const long long num_patches = (num_tris + M2S_PATCH - 1) / M2S_PATCH;
+    int G = 32;                                                              // projected grid: ~sqrt(#triangles) cells a side
+    while (G < 256 && (long long)G * G < num_tris) G *= 2;
+    const long long proj_bins = (long long)M2S_NDIR * G * G;                 // a multiple of 1024
+    // slices of the triangle range (walk only): enough CTAs for ~4 waves of the machine, at least 4 tiles per slice
     int slices = 1;
-    {
+    if (!hier) {
         const long long ctas_per_wave = (long long)nglod_sm_count() * 5;
         long long want = (4 * ctas_per_wave + grid - 1) / grid;
         const long long max_slices = num_tris / (4 * M2S_TILE);
@@ -388,40 +692,106 @@ extern "C" int nglod_mesh2sdf(const float* points, int64_t n, const float* tris,
         if (want > 32) want = 32;
         if (want > 1) slices = (int)want;
     }
+    size_t ws_bytes = 0;
+    auto reserve = [&ws_bytes](size_t bytes) { const size_t off = ws_bytes; ws_bytes += (bytes + 255) & ~(size_t)255; return off; };
+    const size_t rec_off = reserve((size_t)num_tris * sizeof(TriRecord));
+    const size_t part_off = reserve(slices > 1 || hier ? (size_t)n * sizeof(uint3) : 0);
+    const size_t xs_off = reserve(sort ? (size_t)n * 12 : 0);
+    const size_t perm_off = reserve(sort ? (size_t)n * 4 : 0);
+    const size_t hist_off = reserve(sort ? (size_t)M2S_BINS * 4 : 0);
+    const size_t tcen_off = reserve(hier ? (size_t)num_tris * 12 : 0);
+    const size_t tcs_off = reserve(hier ? (size_t)num_tris * 12 : 0);
+    const size_t tperm_off = reserve(hier ? (size_t)num_tris * 4 : 0);
+    const size_t tsph_off = reserve(hier ? (size_t)num_tris * sizeof(float4) : 0);
+    const size_t tfl_off = reserve(hier ? (size_t)num_tris * 4 : 0);
+    const size_t psph_off = reserve(hier ? (size_t)num_patches * sizeof(float4) : 0);
+    const size_t pbin_off = reserve(hier ? (size_t)proj_bins * 4 : 0);
+    const size_t pidx_off = reserve(hier ? (size_t)n * M2S_NDIR * 4 : 0);
+    const int bsum_n = (int)((proj_bins / 1024 + 1023) / 1024 * 1024);
+    const size_t bsum_off = reserve(hier ? (size_t)bsum_n * 4 : 0);
+    long long dist_slices = num_patches / 64;                                 // >= 64 patches (2 rounds of level 1) per slice
+    if (dist_slices > 8) dist_slices = 8;
+    if (dist_slices < 1) dist_slices = 1;
     char* ws = nullptr;
-    const size_t rec_bytes = ((size_t)num_tris * sizeof(TriRecord) + 255) & ~(size_t)255;
-    const size_t part_off = rec_bytes;
-    const size_t part_bytes = slices > 1 ? (((size_t)n * sizeof(uint3) + 255) & ~(size_t)255) : 0;
-    const size_t xs_off = part_off + part_bytes;
-    const size_t perm_off = xs_off + (sort ? (((size_t)n * 12 + 255) & ~(size_t)255) : 0);
-    const size_t hist_off = perm_off + (sort ? (((size_t)n * 4 + 255) & ~(size_t)255) : 0);
-    NGLOD_CUDA_TRY(cudaMallocAsync(&ws, hist_off + (sort ? (size_t)M2S_BINS * 4 : 0) + 256, st));
-    TriRecord* recs = reinterpret_cast<TriRecord*>(ws);
-    uint3* partial = slices > 1 ? reinterpret_cast<uint3*>(ws + part_off) : nullptr;
-    m2s_records_kernel<<<(int)((num_tris + 127) / 128), 128, 0, st>>>(tris, (long long)num_tris, recs);
-    int err = (int)cudaGetLastError();
+    NGLOD_CUDA_TRY(cudaMallocAsync(&ws, ws_bytes + 256, st));
+    TriRecord* recs = reinterpret_cast<TriRecord*>(ws + rec_off);
+    uint3* partial = (slices > 1 || hier) ? reinterpret_cast<uint3*>(ws + part_off) : nullptr;
+    int* hist = reinterpret_cast<int*>(ws + hist_off);
+    const long long sm8 = (long long)nglod_sm_count() * 8;
+    int err = 0;
+    const int* tri_perm = nullptr;
+    float4* tsph = hier ? reinterpret_cast<float4*>(ws + tsph_off) : nullptr;
+    unsigned* tflags = hier ? reinterpret_cast<unsigned*>(ws + tfl_off) : nullptr;
+    float4* patches = hier ? reinterpret_cast<float4*>(ws + psph_off) : nullptr;
+    if (hier) {                     // triangles along a Morton curve (the same counting sort, on their centroids)
+        float* tcen = reinterpret_cast<float*>(ws + tcen_off);
+        int* tp = reinterpret_cast<int*>(ws + tperm_off);
+        err = (int)cudaMemsetAsync(hist, 0, (size_t)M2S_BINS * 4, st);
+        if (!err) {
+            const int nb = (int)std::min<long long>((num_tris + 255) / 256, sm8);
+            m2s_centroid_kernel<<<(int)((num_tris + 127) / 128), 128, 0, st>>>(tris, (long long)num_tris, tcen);
+            m2s_hist_kernel<<<nb, 256, 0, st>>>(tcen, (long long)num_tris, hist);
+            m2s_scan_kernel<<<1, 1024, 0, st>>>(hist, M2S_BINS);
+            m2s_scatter_kernel<<<nb, 256, 0, st>>>(tcen, (long long)num_tris, hist, reinterpret_cast<float*>(ws + tcs_off), tp);
+            err = (int)cudaGetLastError();
+            tri_perm = tp;
+        }
+    }
+    if (!err) {
+        m2s_records_kernel<<<(int)((num_tris + 127) / 128), 128, 0, st>>>(tris, (long long)num_tris, recs, tri_perm, tsph, tflags);
+        err = (int)cudaGetLastError();
+    }
+    if (!err && hier) {
+        m2s_patch_sphere_kernel<<<(int)((num_patches + 127) / 128), 128, 0, st>>>(tsph, tflags, (long long)num_tris, patches, num_patches);
+        err = (int)cudaGetLastError();
+    }
     if (!err && partial) {
         m2s_init_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(partial, (long long)n);
         err = (int)cudaGetLastError();
     }
-    const dim3 g2((unsigned)grid, (unsigned)slices);
     const float* pts = points;
     const int* perm = nullptr;
     if (!err && sort) {
         float* xs = reinterpret_cast<float*>(ws + xs_off);
         int* pm = reinterpret_cast<int*>(ws + perm_off);
-        int* hist = reinterpret_cast<int*>(ws + hist_off);
         err = (int)cudaMemsetAsync(hist, 0, (size_t)M2S_BINS * 4, st);
         if (!err) {
-            const int nb = (int)((n + 255) / 256 < (long long)nglod_sm_count() * 8 ? (n + 255) / 256 : (long long)nglod_sm_count() * 8);
+            const int nb = (int)std::min<long long>((n + 255) / 256, sm8);
             m2s_hist_kernel<<<nb, 256, 0, st>>>(points, (long long)n, hist);
-            m2s_scan_kernel<<<1, 1024, 0, st>>>(hist);
+            m2s_scan_kernel<<<1, 1024, 0, st>>>(hist, M2S_BINS);
             m2s_scatter_kernel<<<nb, 256, 0, st>>>(points, (long long)n, hist, xs, pm);
             err = (int)cudaGetLastError();
             pts = xs; perm = pm;
         }
     }
-    if (!err) {
+    if (!err && hier) {
+        int* pbin = reinterpret_cast<int*>(ws + pbin_off);
+        int* pidx = reinterpret_cast<int*>(ws + pidx_off);
+        const dim3 gd((unsigned)((n + M2S_WARP_THREADS - 1) / M2S_WARP_THREADS), (unsigned)dist_slices);
+        mesh2sdf_dist_kernel<<<gd, M2S_WARP_THREADS, 0, st>>>(pts, (long long)n, recs, tsph, tflags, patches,
+                                                              (long long)num_tris, partial);
+        err = (int)cudaGetLastError();
+        if (!err) err = (int)cudaMemsetAsync(pbin, 0, (size_t)proj_bins * 4, st);
+        if (!err) {
+            const int nb = (int)std::min<long long>((n + 255) / 256, sm8);
+            m2s_proj_bin_kernel<<<nb, 256, 0, st>>>(pts, (long long)n, G, pbin, nullptr);
+            {   // exclusive scan of the 13 G^2 counts: per 1024-bin block, then the block totals, then add back
+                int* bsum = reinterpret_cast<int*>(ws + bsum_off);
+                const int nblk = (int)(proj_bins / 1024);
+                cudaMemsetAsync(bsum, 0, (size_t)bsum_n * 4, st);
+                m2s_scan_local_kernel<<<nblk, 1024, 0, st>>>(pbin, bsum);
+                m2s_scan_kernel<<<1, 1024, 0, st>>>(bsum, bsum_n);
+                m2s_scan_add_kernel<<<nblk, 1024, 0, st>>>(pbin, bsum);
+            }
+            m2s_proj_bin_kernel<<<nb, 256, 0, st>>>(pts, (long long)n, G, pbin, pidx);
+            const long long tasks = (long long)num_tris * M2S_NDIR;
+            const long long wpc = M2S_WARP_THREADS / 32;
+            mesh2sdf_stab_kernel<<<(int)((tasks + wpc - 1) / wpc), M2S_WARP_THREADS, 0, st>>>(
+                pts, recs, (long long)num_tris, G, pbin, pidx, partial);
+            err = (int)cudaGetLastError();
+        }
+    } else if (!err) {
+        const dim3 g2((unsigned)grid, (unsigned)slices);
         mesh2sdf_kernel<<<g2, M2S_THREADS, 0, st>>>(pts, (long long)n, recs, (long long)num_tris, dist, perm, partial);
         err = (int)cudaGetLastError();
     }

@@ -333,6 +333,44 @@ def test_mesh2sdf_vs_reference_kernel_and_oracle():
     assert ops.mesh2sdf_gpu(pts[:0], V[Fc].to(DEV))[0].shape == (0,)
 
 
+def test_mesh2sdf_hierarchy_is_bit_identical():
+    """The Morton-sorted patches + per-warp patch / triangle culls only skip pairs the exact tests dismiss anyway:
+    every distance and sign equals the brute-force walk bit for bit (shuffled, duplicated and degenerate triangles, points
+    outside the box, all batch-size regimes: unsorted / sorted / sliced)."""
+    import os
+    from nglod_b200 import ops
+    from nglod_b200.lib.torchgp import icosphere, torus, normalize, point_sample
+    g = torch.Generator().manual_seed(5)
+    V, Fc = normalize(*[t.to(DEV) for t in torus(0.6, 0.25, 96, 48)])
+    tri = V[Fc].contiguous()
+    extra = torch.cat([tri[:64], tri[:32, :1].expand(-1, 3, -1)], 0)          # duplicates + zero-area triangles
+    tri = torch.cat([tri, extra], 0)[torch.randperm(tri.shape[0] + 96, generator=g).to(DEV)].contiguous()
+    near = point_sample(V, Fc, ["near", "trace"], 60000)
+    box = (torch.rand(80000, 3, generator=g) * 2.4 - 1.2).to(DEV)
+    pts = torch.cat([near, box], 0)[torch.randperm(200000, generator=g).to(DEV)].contiguous()
+
+    def run(p, cull):
+        if cull:
+            os.environ.pop("NGLOD_M2S_BRUTE", None)
+        else:
+            os.environ["NGLOD_M2S_BRUTE"] = "1"
+        try:
+            return ops.mesh2sdf_gpu(p, tri)[0]
+        finally:
+            os.environ.pop("NGLOD_M2S_BRUTE", None)
+
+    for n in (200000, 30000, 3000, 37):
+        p = pts[:n].contiguous()
+        a, b = run(p, True), run(p, False)
+        assert torch.equal(a.view(torch.int32), b.view(torch.int32)), n
+        assert int((a < 0).sum()) > 0 or n < 100
+    # a mesh too small for tiles takes the plain walk
+    Vs, Fs = icosphere(1)
+    ts = Vs[Fs].to(DEV).contiguous()
+    d = ops.mesh2sdf_gpu(pts[:5000].contiguous(), ts)[0]
+    assert torch.isfinite(d).all()
+
+
 def test_mesh_dataset_protocol():
     from nglod_b200.lib.datasets import MeshDataset
     from nglod_b200.lib.torchgp import torus
