@@ -45,8 +45,9 @@ struct __align__(16) TriRecord {
     unsigned nondegenerate;           // nor != 0
     float cen[3];                     // bounding sphere (centroid, radius with slack): distance culling only
     float rad;
-    unsigned pad[2];
+    unsigned pad[4];                  // to 384 B with every word written (the tiles are staged as whole 16-byte words)
 };
+static_assert(sizeof(TriRecord) == 384, "record layout");
 
 __constant__ float c_stab_dir[M2S_NDIR][3] = {
     {1.0f, 0.0f, 0.0f}, {0.0f, 1.0f, 0.0f}, {0.0f, 0.0f, 1.0f},
@@ -113,7 +114,7 @@ __device__ void build_record(const float* __restrict__ tri, TriRecord& r) {
         r2 = fmaxf(dot3(da, da), fmaxf(dot3(db, db), dot3(dc, dc)));
     }
     r.rad = sqrtf(r2) * 1.0001f + 1e-7f;
-    r.pad[0] = r.pad[1] = 0;
+    r.pad[0] = r.pad[1] = r.pad[2] = r.pad[3] = 0;
 }
 
 // Records are built ONCE per call into stream-ordered scratch (384 B per triangle, L2-resident): building them per

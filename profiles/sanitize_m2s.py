@@ -1,10 +1,13 @@
+"""mesh2sdf through compute-sanitizer: the brute-force walk (unsorted / sorted / sliced) and the large-batch path
+(distance hierarchy + projected-bin stabs), with duplicated and zero-area triangles and points outside the box."""
 import sys, torch
 sys.path.insert(0, "/root/repo")
 from nglod_b200 import ops
 from nglod_b200.lib.torchgp import icosphere
 V, F = icosphere(3)
 tri = V.cuda()[F.cuda()].contiguous()
-for n in (100, 5000, 20000):
-    p = torch.rand(n, 3, device="cuda") * 2 - 1
+tri = torch.cat([tri, tri[:40], tri[:20, :1].expand(-1, 3, -1)], 0).contiguous()
+for n in (100, 5000, 20000, 40001):
+    p = torch.rand(n, 3, device="cuda") * 2.6 - 1.3
     d = ops.mesh2sdf_gpu(p, tri)[0]
 torch.cuda.synchronize(); print("done", tri.shape, float(d.min()), float(d.max()))
