@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define NGLOD_ABI_VERSION 5
+#define NGLOD_ABI_VERSION 6
 #define NGLOD_MAX_LODS 8
 
 /* nglod_net_t.math_mode */
@@ -220,6 +220,29 @@ int nglod_sphere_trace(const nglod_net_t* net, int32_t lod,
  * No [64,n,26] temporaries: one pass, triangles staged through shared memory. */
 int nglod_mesh2sdf(const float* points, int64_t n, const float* tris,
                    int64_t num_tris, float* dist, void* stream);
+
+/* ---- training-point sampler -------------------------------------------------
+ * Replaces the host-side torch samplers of sdf-net/lib/torchgp/: area_weighted_distribution.py:26-45,
+ * random_face.py:27-47, sample_surface.py:27-52, sample_near_surface.py:27-45, sample_uniform.py:25-31 and
+ * their driver point_sample.py:29-57 (called from MeshDataset.resample, MeshDataset.py:71-93).
+ * nglod_mesh_area_cdf: V [#V,3] fp32, F [num_faces,3] int64 -> cdf [num_faces] fp32, the inclusive cumulative
+ *   face areas (non-decreasing; accumulated in double), built once per mesh.
+ * nglod_sample_mesh: `techniques` is a HOST array of num_techniques (<= 32) codes; writes
+ *   pts [num_techniques * samples_per_technique, 3], technique-major in the order given (point_sample's
+ *   concatenation); face_idx (nullable) [same count] int32 = the face a surface sample lies on (-1 for RAND),
+ *   from which the caller gathers per-face normals (sample_surface returns them).
+ *   RAND: U[-1,1)^3.  TRACE: face ~ area, u = sqrt(r1), v = r2, p = (1-u) a + u (1-v) b + u v c.
+ *   NEAR: TRACE + N(0,1) * variance per coordinate (the reference multiplies by `variance`, default 0.01).
+ *   Randoms come from Philox-4x32-10 keyed by `seed`, counter = sample index: the same seed reproduces the same
+ *   points; streams differ from torch's, so parity with the reference is distributional.
+ *   V / F / cdf may be NULL when every technique is RAND. */
+#define NGLOD_SAMPLE_RAND 0
+#define NGLOD_SAMPLE_NEAR 1
+#define NGLOD_SAMPLE_TRACE 2
+int nglod_mesh_area_cdf(const float* V, const int64_t* F, int64_t num_faces, float* cdf, void* stream);
+int nglod_sample_mesh(const float* V, const int64_t* F, int64_t num_faces, const float* cdf,
+                      const int* techniques, int num_techniques, int64_t samples_per_technique,
+                      float variance, uint64_t seed, float* pts, int* face_idx, void* stream);
 
 /* ---- sparse-octree (SPC) ray traversal -------------------------------------
  * Replaces: spc_raytrace, sol-renderer/include/spc/spc/spc_raytrace_cuda.cpp:125-199 + kernels

@@ -129,6 +129,9 @@ SIGNATURES = {
     "nglod_shade_matcap": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int64,
                                           c_void_p, c_void_p]),
     "nglod_mesh2sdf": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
+    "nglod_mesh_area_cdf": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "nglod_sample_mesh": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.c_int,
+                                         c_int64, ctypes.c_float, ctypes.c_uint64, c_void_p, c_void_p, c_void_p]),
     "nglod_adam_step": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, ctypes.c_float,
                                        ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                        ctypes.c_float, c_void_p]),

@@ -710,8 +710,8 @@ extern "C" int nglod_mesh2sdf(const float* points, int64_t n, const float* tris,
     const size_t pidx_off = reserve(hier ? (size_t)n * M2S_NDIR * 4 : 0);
     const int bsum_n = (int)((proj_bins / 1024 + 1023) / 1024 * 1024);
     const size_t bsum_off = reserve(hier ? (size_t)bsum_n * 4 : 0);
-    long long dist_slices = num_patches / 64;                                 // >= 64 patches (2 rounds of level 1) per slice
-    if (dist_slices > 8) dist_slices = 8;
+    long long dist_slices = num_patches / 32;                                 // >= 32 patches (one round of level 1) per slice
+    if (dist_slices > 32) dist_slices = 32;                                   // sweep 4 .. 64 in profiles/README.md: 16-32 is the flat optimum
     if (dist_slices < 1) dist_slices = 1;
     char* ws = nullptr;
     NGLOD_CUDA_TRY(cudaMallocAsync(&ws, ws_bytes + 256, st));

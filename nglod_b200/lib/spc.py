@@ -16,7 +16,7 @@ import ctypes
 
 import torch
 
-from .. import _lib
+from .. import _lib, ops
 from ..ops import _ptr, _stream, _f32c
 from .torchgp import sample_surface
 
@@ -100,7 +100,10 @@ def octree_to_spc(octree):
 def mesh_to_octree(V, F, level, num_samples=1 << 24):
     """Octree of the voxels a mesh surface touches (spc_utils.py:74-84): surface samples plus a half-voxel jittered
     copy, quantised, de-duplicated.  The reference draws 1e8 samples; `num_samples` trades build time for coverage."""
-    samples = sample_surface(V, F, num_samples)[0]
+    if V.is_cuda:           # points only: skip the per-sample normal gather of sample_surface
+        samples = ops.sample_mesh(V, F.long(), ops.mesh_area_cdf(V, F.long()), ["trace"], num_samples)
+    else:
+        samples = sample_surface(V, F, num_samples)[0]
     samples = torch.cat([samples, samples + (torch.rand_like(samples) * 2.0 - 1.0) * (1.0 / (2 ** (level + 1)))], dim=0)
     q = quantize_points(samples, level)
     return points_to_octree(torch.unique(q.long(), dim=0), level)

@@ -7,8 +7,21 @@ surface + N(0, variance) (sample_near_surface.py:43-44), uniform = U[-1,1]^3
 (sample_uniform.py:31), mesh normalisation into the unit sphere (normalize.py:24-38).
 All tensors stay on V's device (the reference samples on the host and copies
 500k points to the GPU for every resample, MeshDataset.py:85).
+
+On a CUDA mesh `point_sample`, `sample_surface` and `sample_near_surface` run as ONE kernel
+(`nglod_sample_mesh`, csrc/sample_mesh.cu: Philox streams keyed by a seed drawn from torch's CPU
+generator, binary search in the cumulative-area table); host tensors keep the reference's torch
+recipe below, which is also what the kernel's distribution tests compare against.
 """
 import torch
+
+from ... import ops
+
+
+def _cdf(V, F, distrib):
+    """Cumulative-area table of the kernel path; `distrib` may carry a cached one (see area_weighted_distribution)."""
+    cdf = getattr(distrib, "_nglod_cdf", None)
+    return cdf if cdf is not None else ops.mesh_area_cdf(V, F.long())
 
 
 def per_face_normals(V, F):
@@ -21,7 +34,10 @@ def area_weighted_distribution(V, F, normals=None):
         normals = per_face_normals(V, F)
     areas = torch.norm(normals, p=2, dim=1) * 0.5
     areas = areas / (torch.sum(areas) + 1e-10)
-    return torch.distributions.Categorical(areas.view(-1))
+    distrib = torch.distributions.Categorical(areas.view(-1))
+    if V.is_cuda:
+        distrib._nglod_cdf = ops.mesh_area_cdf(V, F.long())
+    return distrib
 
 
 def random_face(V, F, num_samples, distrib=None):
@@ -33,6 +49,9 @@ def random_face(V, F, num_samples, distrib=None):
 
 
 def sample_surface(V, F, num_samples, distrib=None):
+    if V.is_cuda:
+        pts, faces = ops.sample_mesh(V, F.long(), _cdf(V, F, distrib), ["trace"], num_samples, return_faces=True)
+        return pts, per_face_normals(V, F)[faces.long()]
     if distrib is None:
         distrib = area_weighted_distribution(V, F)
     fidx, normals = random_face(V, F, num_samples, distrib)
@@ -44,6 +63,8 @@ def sample_surface(V, F, num_samples, distrib=None):
 
 
 def sample_near_surface(V, F, num_samples, variance=0.01, distrib=None):
+    if V.is_cuda:
+        return ops.sample_mesh(V, F.long(), _cdf(V, F, distrib), ["near"], num_samples, variance=variance)
     if distrib is None:
         distrib = area_weighted_distribution(V, F)
     samples = sample_surface(V, F, num_samples, distrib)[0]
@@ -56,6 +77,10 @@ def sample_uniform(num_samples, device="cpu"):
 
 def point_sample(V, F, techniques, num_samples):
     """`num_samples` points per technique ('trace' = on-surface, 'near', 'rand'), concatenated in order."""
+    if V.is_cuda:
+        known = [t for t in techniques if t in ops.SAMPLE_CODES]          # the reference skips unknown names silently
+        surface = any(t != "rand" for t in known)
+        return ops.sample_mesh(V, F.long(), ops.mesh_area_cdf(V, F.long()) if surface else None, known, num_samples)
     distrib = None
     if "trace" in techniques or "near" in techniques:
         distrib = area_weighted_distribution(V, F)

@@ -285,6 +285,43 @@ def mesh2sdf_gpu(points, mesh):
     return [dist]
 
 
+SAMPLE_CODES = {"rand": 0, "near": 1, "trace": 2}
+
+
+def mesh_area_cdf(V, F):
+    """Inclusive cumulative face areas [#F] fp32 of the mesh (V [#V,3] fp32, F [#F,3] int64), for `sample_mesh`."""
+    lib = _lib.load()
+    V = _f32c(V, "V")
+    if F.dtype != torch.int64 or not F.is_cuda:
+        raise TypeError("F: expected a CUDA int64 tensor")
+    F = F.contiguous()
+    cdf = torch.empty(F.shape[0], device=V.device, dtype=torch.float32)
+    with torch.cuda.device(V.device):
+        _lib.check(lib.nglod_mesh_area_cdf(_ptr(V), _ptr(F), F.shape[0], _ptr(cdf), _stream()), "nglod_mesh_area_cdf")
+    return cdf
+
+
+def sample_mesh(V, F, cdf, techniques, num_samples, variance=0.01, seed=None, return_faces=False):
+    """`num_samples` points per technique ('rand' | 'near' | 'trace'), concatenated in order (point_sample.py:29-57), by
+    one kernel.  `seed`: Philox key; default draws one from torch's CPU generator (so `torch.manual_seed` reproduces)."""
+    import ctypes
+    lib = _lib.load()
+    codes = [SAMPLE_CODES[t] for t in techniques]
+    if seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    dev = V.device
+    V = _f32c(V, "V")
+    F = F.contiguous()
+    n = len(codes) * int(num_samples)
+    pts = torch.empty(n, 3, device=dev, dtype=torch.float32)
+    faces = torch.empty(n, device=dev, dtype=torch.int32) if return_faces else None
+    arr = (ctypes.c_int * max(len(codes), 1))(*codes)
+    with torch.cuda.device(dev):
+        _lib.check(lib.nglod_sample_mesh(_ptr(V), _ptr(F), F.shape[0], _ptr(cdf), arr, len(codes), int(num_samples),
+                                         float(variance), int(seed), _ptr(pts), _ptr(faces), _stream()), "nglod_sample_mesh")
+    return (pts, faces) if return_faces else pts
+
+
 def adam_step(param, grad, exp_avg, exp_avg_sq, step, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8):
     lib = _lib.load()
     n = param.numel()

@@ -371,6 +371,68 @@ def test_mesh2sdf_hierarchy_is_bit_identical():
     assert torch.isfinite(d).all()
 
 
+def test_sample_mesh_kernel_distribution():
+    """nglod_sample_mesh vs the reference recipe (torchgp/*.py): parity is distributional (RNG streams differ), so check the
+    moments the recipe fixes -- face frequency ~ area, uniform barycentric density, noise std, cube range -- and the exact
+    things: technique-major order, points on their face, determinism by seed."""
+    from nglod_b200 import ops, _lib
+    from nglod_b200.lib.torchgp import torus, normalize, per_face_normals
+    V, Fc = normalize(*[t.to(DEV) for t in torus(0.6, 0.25, 24, 12)])
+    # make the areas very unequal and add a zero-area face that must never be drawn
+    Fc = torch.cat([Fc, Fc[:1, [0, 0, 1]]], 0)
+    cdf = ops.mesh_area_cdf(V, Fc)
+    tri = V[Fc]
+    area = 0.5 * torch.linalg.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]).norm(dim=1)
+    assert torch.allclose(cdf, torch.cumsum(area.double(), 0).float(), rtol=1e-5, atol=1e-7)
+    assert (cdf[1:] >= cdf[:-1]).all()
+    S = 400000
+    pts, faces = ops.sample_mesh(V, Fc, cdf, ["rand", "near", "trace"], S, variance=0.01, seed=1234, return_faces=True)
+    assert pts.shape == (3 * S, 3) and faces.shape == (3 * S,)
+    rand, near, trace = pts[:S], pts[S:2 * S], pts[2 * S:]
+    # rand: U[-1,1)^3
+    assert (faces[:S] == -1).all() and rand.min() >= -1 and rand.max() < 1
+    assert rand.mean(0).abs().max() < 0.01 and ((rand.var(0) - 1.0 / 3).abs() < 0.01).all()
+    # trace: on the drawn face (barycentric coordinates in [0,1], zero plane distance), faces ~ area
+    ft = faces[2 * S:].long()
+    assert ft.min() >= 0 and ft.max() < Fc.shape[0] - 1                         # the zero-area face never comes up
+    a, b, c = tri[ft, 0], tri[ft, 1], tri[ft, 2]
+    n = torch.nn.functional.normalize(torch.linalg.cross(b - a, c - a), dim=1)
+    assert ((trace - a) * n).sum(1).abs().max() < 1e-6
+    freq = torch.bincount(ft, minlength=Fc.shape[0]).double() / S
+    p = (area / area.sum()).double()
+    sigma = torch.sqrt(p * (1 - p) / S) + 1e-9
+    assert ((freq - p).abs() / sigma).max() < 6.0                              # every face within 6 sigma of its area share
+    # uniform on the triangle: mean of the barycentric weights is 1/3 each
+    e1, e2, dd = b - a, c - a, trace - a
+    d11, d12, d22, r1, r2 = (e1 * e1).sum(1), (e1 * e2).sum(1), (e2 * e2).sum(1), (dd * e1).sum(1), (dd * e2).sum(1)
+    det = d11 * d22 - d12 * d12
+    w12 = torch.stack([(d22 * r1 - d12 * r2) / det, (d11 * r2 - d12 * r1) / det], 1)
+    assert (w12.mean(0) - 1.0 / 3).abs().max() < 3e-3 and w12.min() > -1e-4 and w12.sum(1).max() < 1 + 1e-4
+    # near: surface point + N(0, 0.01^2) per coordinate, isotropic and uncorrelated
+    fn = faces[S:2 * S].long()
+    an, nn = tri[fn, 0], torch.nn.functional.normalize(per_face_normals(V, Fc)[fn], dim=1)
+    off = ((near - an) * nn).sum(1)                                             # normal component of the noise
+    assert abs(off.mean().item()) < 1e-4 and abs(off.std().item() - 0.01) < 2e-4
+    kurt = ((off / off.std()) ** 4).mean().item()
+    assert abs(kurt - 3.0) < 0.1                                                # gaussian, not uniform
+    # determinism / seeds
+    again = ops.sample_mesh(V, Fc, cdf, ["rand", "near", "trace"], S, variance=0.01, seed=1234)
+    assert torch.equal(again, pts)
+    other = ops.sample_mesh(V, Fc, cdf, ["rand", "near", "trace"], S, variance=0.01, seed=1235)
+    assert not torch.equal(other, pts)
+    # host wrappers: manual_seed reproduces, sample_surface returns the faces' (unnormalised) normals
+    from nglod_b200.lib.torchgp import point_sample, sample_surface
+    torch.manual_seed(3); p1 = point_sample(V, Fc, ["rand", "near", "near", "trace", "trace"], 1000)
+    torch.manual_seed(3); p2 = point_sample(V, Fc, ["rand", "near", "near", "trace", "trace"], 1000)
+    assert p1.shape == (5000, 3) and torch.equal(p1, p2)
+    assert not torch.equal(p1[1000:2000], p1[2000:3000])                        # the two 'near' blocks are different draws
+    sp, sn = sample_surface(V, Fc, 2000)
+    assert sp.shape == (2000, 3) and sn.shape == (2000, 3)
+    assert point_sample(V, Fc, ["rand"], 10).shape == (10, 3) and point_sample(V, Fc, [], 10).shape == (0, 3)
+    lib = _lib.load()
+    assert lib.nglod_sample_mesh(None, None, 0, None, None, 40, 1, 0.0, 0, None, None, None) == _lib.EINVAL
+
+
 def test_mesh_dataset_protocol():
     from nglod_b200.lib.datasets import MeshDataset
     from nglod_b200.lib.torchgp import torus
