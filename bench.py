@@ -447,7 +447,7 @@ def run_extras(net, args, device, rank, world, flush, log):
         pts = point_sample(V, F, modes, per_rank // 5)
         return pts, ops.mesh2sdf_gpu(pts, tri)[0].unsqueeze(1)
 
-    sample_ms = timed(make_batch, iters=3, warm=1)
+    sample_ms = timed(make_batch, iters=5, warm=2)
     pts, gts = make_batch()
     tnet = copy.deepcopy(net)
     tnet.train()
@@ -457,7 +457,11 @@ def run_extras(net, args, device, rank, world, flush, log):
                               "points_per_s": world * pts.shape[0] / (step_ms / 1e3),
                               "sample_and_label_ms": sample_ms, "mesh_triangles": int(tri.shape[0]),
                               "mesh2sdf_pairs_per_s": world * pts.shape[0] * tri.shape[0] / (sample_ms / 1e3),
-                              "note": "fused fwd+loss+bwd for 5 LODs + flat-gradient all-reduce + Adam; labels by the mesh2sdf kernel"}
+                              "config3_step_ms": step_ms + sample_ms,
+                              "config3_points_per_s": world * pts.shape[0] / ((step_ms + sample_ms) / 1e3),
+                              "note": "fused fwd+loss+bwd for 5 LODs + flat-gradient all-reduce + Adam; a fresh batch per step "
+                                      "(SURVEY 8d config 3) adds sample_and_label_ms: the sampler kernel + mesh2sdf labels; "
+                                      "mesh2sdf_pairs_per_s counts all N x T pairs although the large-batch path visits few of them"}
     del trainer, tnet
 
     # ---- config 4 (traversal half): sparse-octree ray traversal at 1920x1080, octree level 7 of the same mesh
