@@ -371,6 +371,69 @@ def test_mesh2sdf_hierarchy_is_bit_identical():
     assert torch.isfinite(d).all()
 
 
+def _cube_mesh(k=8):
+    """Axis-aligned cube [-0.5, 0.5]^3, k x k quads per face (12 k^2 triangles)."""
+    g = torch.linspace(-0.5, 0.5, k + 1)
+    u, v = torch.meshgrid(g, g, indexing="ij")
+    tris = []
+    for axis in range(3):
+        for side in (-0.5, 0.5):
+            P = torch.zeros(k + 1, k + 1, 3)
+            P[..., axis] = side
+            P[..., (axis + 1) % 3] = u
+            P[..., (axis + 2) % 3] = v
+            a, b, c, d = P[:-1, :-1], P[1:, :-1], P[1:, 1:], P[:-1, 1:]
+            tris.append(torch.stack([a, b, c], -2).reshape(-1, 3, 3))
+            tris.append(torch.stack([a, c, d], -2).reshape(-1, 3, 3))
+    return torch.cat(tris, 0)
+
+
+def test_mesh2sdf_hierarchy_grazing_and_grid_sizes():
+    """The sign half bins points under each triangle's projection widened by the rounding error of the exact test, which
+    blows up when a stab line grazes the triangle's plane: cubes whose faces are parallel to three stab directions
+    (determinant exactly 0: direction skipped) and rotated off them by 1e-6 .. 1e-2 rad (determinants down to the 1e-8
+    threshold) must still match the brute-force walk bit for bit.  Also every projected-grid size (32 .. 256 cells a side)."""
+    import math
+    import os
+    from nglod_b200 import ops
+    from nglod_b200.lib.torchgp import icosphere
+    g = torch.Generator().manual_seed(9)
+
+    def both(p, tri):
+        os.environ.pop("NGLOD_M2S_BRUTE", None)
+        a = ops.mesh2sdf_gpu(p, tri)[0]
+        os.environ["NGLOD_M2S_BRUTE"] = "1"
+        try:
+            b = ops.mesh2sdf_gpu(p, tri)[0]
+        finally:
+            os.environ.pop("NGLOD_M2S_BRUTE", None)
+        return a, b
+
+    cube = _cube_mesh(8)
+    pts = (torch.rand(40000, 3, generator=g) * 2 - 1).to(DEV)
+    # points exactly on the planes / lines the cube's faces and edges span, where the barycentric tests sit on their limits
+    snap = pts[:8000].clone()
+    snap[:4000, 0] = 0.5
+    snap[4000:, 1] = (snap[4000:, 1] * 8).round() / 8
+    pts = torch.cat([pts, snap], 0).contiguous()
+    for angle in (0.0, 1e-6, 1e-4, 1e-2, 0.3):
+        ax = torch.tensor([0.3, 0.5, 0.81]); ax = ax / ax.norm()
+        K = torch.tensor([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+        R = torch.eye(3) + math.sin(angle) * K + (1 - math.cos(angle)) * (K @ K)
+        tri = (cube @ R.T).to(DEV).contiguous()
+        a, b = both(pts, tri)
+        assert torch.equal(a.view(torch.int32), b.view(torch.int32)), angle
+        if angle == 0.3:
+            inside = (pts @ R.to(DEV)).abs().max(dim=1).values < 0.5 - 1e-4       # rotate back: inside the cube
+            assert (a[inside] < 0).all()
+    for sub, n in ((2, 20000), (3, 20000), (4, 30000), (6, 50000)):              # 320 .. 81 920 triangles: G = 32 .. 256
+        V, Fc = icosphere(sub)
+        tri = V[Fc].to(DEV).contiguous()
+        p = (torch.rand(n, 3, generator=g) * 2.2 - 1.1).to(DEV)
+        a, b = both(p, tri)
+        assert torch.equal(a.view(torch.int32), b.view(torch.int32)), sub
+
+
 def test_sample_mesh_kernel_distribution():
     """nglod_sample_mesh vs the reference recipe (torchgp/*.py): parity is distributional (RNG streams differ), so check the
     moments the recipe fixes -- face frequency ~ area, uniform barycentric density, noise std, cube range -- and the exact
