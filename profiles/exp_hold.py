@@ -19,10 +19,10 @@ def timed(fn, it=20):
         tot += a.elapsed_time(b)
     return tot / it * 1e3
 ref = None
-for lod in (4, 2):
+for lod in (4,):
     net.lod = lod
     ref = None
-    for hold in (0, 24, 32, 40, 48, 64, 80, 96, 128):
+    for hold in (0, 64, 80, 96, 112, 128, 160, 192, 0):
         os.environ["NGLOD_TRACE_HOLD"] = str(hold)
         rb = tracer(net, ray_o, ray_d)
         out = (rb.x.clone(), rb.depth.clone(), rb.hit.clone(), rb.normal.clone())
