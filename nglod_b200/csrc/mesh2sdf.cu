@@ -6,6 +6,10 @@
 //   inside  <=>  for ALL 13 fixed stab directions the line through the point hits
 //                at least one triangle at t >= 0 AND at least one at t < 0.
 //
+// Two paths, bit-identical to each other (tests/): the brute-force walk described next, for small batches and small
+// meshes, and -- further down -- an output-sensitive pair of kernels for large batches (distance through a sphere
+// hierarchy over Morton-sorted triangles, sign through 13 projected point grids).
+//
 // B200 design (not the reference's): one thread per point keeps its running
 // min and two 13-bit stab masks in registers; triangles are streamed through
 // shared memory in tiles of "records" holding everything that depends only on
