@@ -666,6 +666,15 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 
 }  // namespace
 
+// exclusive scan of nbins counts in place (nbins % 1024 == 0): per 1024-bin block, the block totals, add back
+static void m2s_scan(int* bins, long long nbins, int* bsum, int bsum_n, cudaStream_t st) {
+    const int nblk = (int)(nbins / 1024);
+    cudaMemsetAsync(bsum, 0, (size_t)bsum_n * 4, st);
+    m2s_scan_local_kernel<<<nblk, 1024, 0, st>>>(bins, bsum);
+    m2s_scan_kernel<<<1, 1024, 0, st>>>(bsum, bsum_n);
+    m2s_scan_add_kernel<<<nblk, 1024, 0, st>>>(bins, bsum);
+}
+
 extern "C" int nglod_mesh2sdf(const float* points, int64_t n, const float* tris, int64_t num_tris, float* dist,
                               void* stream) {
     if (n < 0 || num_tris < 0 || (n > 0 && (!points || !dist)) || (num_tris > 0 && !tris)) return NGLOD_EINVAL;
@@ -712,8 +721,8 @@ extern "C" int nglod_mesh2sdf(const float* points, int64_t n, const float* tris,
     const size_t psph_off = reserve(hier ? (size_t)num_patches * sizeof(float4) : 0);
     const size_t pbin_off = reserve(hier ? (size_t)proj_bins * 4 : 0);
     const size_t pidx_off = reserve(hier ? (size_t)n * M2S_NDIR * 4 : 0);
-    const int bsum_n = (int)((proj_bins / 1024 + 1023) / 1024 * 1024);
-    const size_t bsum_off = reserve(hier ? (size_t)bsum_n * 4 : 0);
+    const int bsum_n = (int)((std::max<long long>(proj_bins, M2S_BINS) / 1024 + 1023) / 1024 * 1024);
+    const size_t bsum_off = reserve((size_t)bsum_n * 4);
     long long dist_slices = num_patches / 32;                                 // >= 32 patches (one round of level 1) per slice
     if (dist_slices > 32) dist_slices = 32;                                   // sweep 4 .. 64 in profiles/README.md: 16-32 is the flat optimum
     if (dist_slices < 1) dist_slices = 1;
@@ -736,7 +745,7 @@ extern "C" int nglod_mesh2sdf(const float* points, int64_t n, const float* tris,
             const int nb = (int)std::min<long long>((num_tris + 255) / 256, sm8);
             m2s_centroid_kernel<<<(int)((num_tris + 127) / 128), 128, 0, st>>>(tris, (long long)num_tris, tcen);
             m2s_hist_kernel<<<nb, 256, 0, st>>>(tcen, (long long)num_tris, hist);
-            m2s_scan_kernel<<<1, 1024, 0, st>>>(hist, M2S_BINS);
+            m2s_scan(hist, M2S_BINS, reinterpret_cast<int*>(ws + bsum_off), bsum_n, st);
             m2s_scatter_kernel<<<nb, 256, 0, st>>>(tcen, (long long)num_tris, hist, reinterpret_cast<float*>(ws + tcs_off), tp);
             err = (int)cudaGetLastError();
             tri_perm = tp;
@@ -763,7 +772,7 @@ extern "C" int nglod_mesh2sdf(const float* points, int64_t n, const float* tris,
         if (!err) {
             const int nb = (int)std::min<long long>((n + 255) / 256, sm8);
             m2s_hist_kernel<<<nb, 256, 0, st>>>(points, (long long)n, hist);
-            m2s_scan_kernel<<<1, 1024, 0, st>>>(hist, M2S_BINS);
+            m2s_scan(hist, M2S_BINS, reinterpret_cast<int*>(ws + bsum_off), bsum_n, st);
             m2s_scatter_kernel<<<nb, 256, 0, st>>>(points, (long long)n, hist, xs, pm);
             err = (int)cudaGetLastError();
             pts = xs; perm = pm;
@@ -780,14 +789,7 @@ extern "C" int nglod_mesh2sdf(const float* points, int64_t n, const float* tris,
         if (!err) {
             const int nb = (int)std::min<long long>((n + 255) / 256, sm8);
             m2s_proj_bin_kernel<<<nb, 256, 0, st>>>(pts, (long long)n, G, pbin, nullptr);
-            {   // exclusive scan of the 13 G^2 counts: per 1024-bin block, then the block totals, then add back
-                int* bsum = reinterpret_cast<int*>(ws + bsum_off);
-                const int nblk = (int)(proj_bins / 1024);
-                cudaMemsetAsync(bsum, 0, (size_t)bsum_n * 4, st);
-                m2s_scan_local_kernel<<<nblk, 1024, 0, st>>>(pbin, bsum);
-                m2s_scan_kernel<<<1, 1024, 0, st>>>(bsum, bsum_n);
-                m2s_scan_add_kernel<<<nblk, 1024, 0, st>>>(pbin, bsum);
-            }
+            m2s_scan(pbin, proj_bins, reinterpret_cast<int*>(ws + bsum_off), bsum_n, st);
             m2s_proj_bin_kernel<<<nb, 256, 0, st>>>(pts, (long long)n, G, pbin, pidx);
             const long long tasks = (long long)num_tris * M2S_NDIR;
             const long long wpc = M2S_WARP_THREADS / 32;
