@@ -347,6 +347,7 @@ sdf_backward_kernel(const NetDev net, const GradDev grad, const float* __restric
 #define BW2_PER_WARP (SDF_SMEM_PER_WARP + 32 * 4 + 32)           // tile, idx, mask words [32][4], gd[32]
 #define BW2_WLO_OFF (SDF_SMEM_WARP_OFF + BW2_WARPS * BW2_PER_WARP)   // TF32 low parts of W0ext (the staged copy keeps the high parts)
 #define BW2_SMEM_BYTES ((BW2_WLO_OFF + SDF_W0_FLOATS) * 4)
+#define BW2_SMEM_GRID_MAX 4000      // floats: a 5^3 x 32 grid (R = 4) accumulated per CTA in shared memory
 
 __device__ __forceinline__ uint32_t to_tf32(float x) {
     uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r;
@@ -369,7 +370,7 @@ template <bool FUSED_LOSS, bool SPARSE>
 __global__ void __launch_bounds__(BW2_THREADS, 1)
 sdf_backward_mma_kernel(const NetDev net, const GradDev grad, const float* __restrict__ x, const long long n,
                         const float* __restrict__ grad_out, const float* __restrict__ gt, const float loss_scale,
-                        float* __restrict__ loss_out, const SparseBwd sp, const int lpw) {
+                        float* __restrict__ loss_out, const SparseBwd sp, const int lpw, const int smem_grid_floats) {
     // lpw = queries per warp per batch: 32, or 8 when the whole call is too small to give every SM a 512-query batch
     // (a batch is then 128 queries: the kernel's serial phases are 3-4x shorter and 4x as many CTAs share the work)
     extern __shared__ __align__(16) float smem[];
@@ -381,6 +382,11 @@ sdf_backward_mma_kernel(const NetDev net, const GradDev grad, const float* __res
     uint32_t* maskw = reinterpret_cast<uint32_t*>(wbase + SDF_SMEM_PER_WARP);
     float* sgd = wbase + SDF_SMEM_PER_WARP + 32 * 4;
     for (int e = lane; e < BW2_PER_WARP; e += 32) wbase[e] = 0.f;
+    // A grid of R = 4 has 125 nodes: half a million queries scattering into its 16 KB serialise in the L2 atomic units (the
+    // LOD-0 launch of a training step took 0.79 ms against 0.37 ms for every other level).  Such a grid (smem_grid_floats
+    // > 0, level 0 only) is accumulated in shared memory and flushed once per CTA.
+    float* sgrid = smem + BW2_SMEM_BYTES / 4;
+    for (int e = threadIdx.x; e < smem_grid_floats; e += blockDim.x) sgrid[e] = 0.f;
     __syncthreads();
     // split the staged W0ext once: smem[e] = TF32 high part, wlo[e] = TF32 of the remainder (B fragments of the 3xTF32 GEMMs)
     float* wlo = smem + BW2_WLO_OFF;
@@ -635,7 +641,12 @@ sdf_backward_mma_kernel(const NetDev net, const GradDev grad, const float* __res
                             const float wz = (k & 4) ? az.w1 : az.w0;
                             const int off = ((iz * S + iy) * S + ix) * NGLOD_F + 4 * c;
                             const float w = (wx * wy) * wz;
-                            red_add_v4(gg + off, gq4.x * w, gq4.y * w, gq4.z * w, gq4.w * w);
+                            if (l == 0 && smem_grid_floats > 0) {
+                                atomicAdd(sgrid + off, gq4.x * w); atomicAdd(sgrid + off + 1, gq4.y * w);
+                                atomicAdd(sgrid + off + 2, gq4.z * w); atomicAdd(sgrid + off + 3, gq4.w * w);
+                            } else {
+                                red_add_v4(gg + off, gq4.x * w, gq4.y * w, gq4.z * w, gq4.w * w);
+                            }
                         }
                     }
                 }
@@ -646,6 +657,13 @@ sdf_backward_mma_kernel(const NetDev net, const GradDev grad, const float* __res
 
     // ---- flush: T fragments -> CTA accumulator in smem -> head gradients -> one RED per CTA per element
     __syncthreads();
+    if constexpr (!SPARSE) {
+        if (smem_grid_floats > 0 && grad.grids[0])
+            for (int e = threadIdx.x * 4; e < smem_grid_floats; e += blockDim.x * 4) {
+                const float4 v = *reinterpret_cast<const float4*>(sgrid + e);
+                if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) red_add_v4(grad.grids[0] + e, v.x, v.y, v.z, v.w);
+            }
+    }
     float* cta_T = smem + SDF_SMEM_WARP_OFF;             // [128][40] (per-warp regions are dead now), then db1, loss
     for (int e = threadIdx.x; e < NGLOD_H * 40 + 4; e += blockDim.x) cta_T[e] = 0.f;
     __syncthreads();
@@ -794,12 +812,18 @@ int launch_backward(const nglod_net_t* net, int lod, const nglod_net_grad_t* gra
         static const bool gen1 = getenv("NGLOD_BWD_GEN1") != nullptr;
         if (!gen1) {
             auto k2 = sdf_backward_mma_kernel<FUSED_LOSS, false>;
-            NGLOD_CUDA_TRY(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, BW2_SMEM_BYTES));
+            NGLOD_CUDA_TRY(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, BW2_SMEM_BYTES + BW2_SMEM_GRID_MAX * 4));
             const int lpw = n > (long long)grid * BW2_WARPS * 8 ? 32 : 8;     // 128-query batches only while they fit one wave
             const long long want2 = (n + BW2_WARPS * lpw - 1) / (BW2_WARPS * lpw);
             if (want2 < grid) grid = want2;
-            k2<<<(int)grid, BW2_THREADS, BW2_SMEM_BYTES, st>>>(nd, gdv, x, (long long)n, grad_out, gt, loss_scale, loss_out,
-                                                               SparseBwd{}, lpw);
+            // level 0 of the launch small enough (R = 4) and busy enough to be worth a per-CTA copy in shared memory
+            int sg = 0;
+            {
+                const long long nodes = (long long)(nd.res[0] + 1) * (nd.res[0] + 1) * (nd.res[0] + 1) * NGLOD_F;
+                if (gdv.grids[0] && nodes <= BW2_SMEM_GRID_MAX && n >= 16 * nodes) sg = (int)nodes;
+            }
+            k2<<<(int)grid, BW2_THREADS, BW2_SMEM_BYTES + sg * 4, st>>>(nd, gdv, x, (long long)n, grad_out, gt, loss_scale, loss_out,
+                                                                        SparseBwd{}, lpw, sg);
             if (int e = (int)cudaGetLastError()) return e;
             return (single && cascade) ? restrict_cascade(net, lod, grad, st) : 0;
         }
@@ -851,7 +875,7 @@ extern "C" int nglod_sparse_sdf_backward(const nglod_sparse_net_t* net, int32_t 
     const long long want = (n + BW2_WARPS * lpw - 1) / (BW2_WARPS * lpw);
     if (want < grid) grid = want;
     k2<<<(int)grid, BW2_THREADS, BW2_SMEM_BYTES, (cudaStream_t)stream>>>(sp.sn.dec, gdv, x, (long long)n, grad_out, nullptr,
-                                                                         0.f, nullptr, sp, lpw);
+                                                                         0.f, nullptr, sp, lpw, 0);
     return (int)cudaGetLastError();
 }
 
