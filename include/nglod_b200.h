@@ -217,7 +217,11 @@ int nglod_sphere_trace(const nglod_net_t* net, int32_t lod,
  * (exported as mesh2sdf.mesh2sdf_gpu, :1007-1012).
  * points: [n,3]; tris: [T,3,3] (= V[F]); dist: [n] signed distance
  * (negative iff all 13 stab directions see a triangle on both sides).
- * No [64,n,26] temporaries: one pass, triangles staged through shared memory. */
+ * No [64,n,26] temporaries.  Small batches walk all n x T pairs with the triangles staged through shared memory;
+ * batches >= 16 k points take an output-sensitive path (nearest triangle through a sphere hierarchy over
+ * Morton-sorted triangles, sign through 13 projected point grids) whose results are bit-identical to the walk.
+ * Scratch (records, bins: ~100 B per point + 400 B per triangle) is stream-ordered, from a memory pool the
+ * library keeps per device; no host synchronisation. */
 int nglod_mesh2sdf(const float* points, int64_t n, const float* tris,
                    int64_t num_tris, float* dist, void* stream);
 

@@ -25,6 +25,7 @@
 // on the same instruction sequence; the parity test compares against the
 // reference's own compiled kernel on the GPU.
 #include "common.cuh"
+#include <mutex>
 
 namespace {
 
@@ -666,6 +667,32 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 
 }  // namespace
 
+// Stream-ordered scratch comes from a pool of the library's own, one per device, that keeps what it is handed back: the
+// device's default pool trims itself at every synchronisation, and a resample that re-allocates its ~50-150 MB of
+// records / bins after each trim cost 3 ms on top of 2.5 ms of kernels.
+static int m2s_scratch_pool(cudaMemPool_t* out) {
+    static cudaMemPool_t pools[64] = {};
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    int dev = 0;
+    NGLOD_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return NGLOD_EINVAL;
+    if (!pools[dev]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        cudaMemPool_t p = nullptr;
+        NGLOD_CUDA_TRY(cudaMemPoolCreate(&p, &props));
+        unsigned long long keep = ~0ull;
+        NGLOD_CUDA_TRY(cudaMemPoolSetAttribute(p, cudaMemPoolAttrReleaseThreshold, &keep));
+        pools[dev] = p;
+    }
+    *out = pools[dev];
+    return 0;
+}
+
 // exclusive scan of nbins counts in place (nbins % 1024 == 0): per 1024-bin block, the block totals, add back
 static void m2s_scan(int* bins, long long nbins, int* bsum, int bsum_n, cudaStream_t st) {
     const int nblk = (int)(nbins / 1024);
@@ -727,7 +754,9 @@ extern "C" int nglod_mesh2sdf(const float* points, int64_t n, const float* tris,
     if (dist_slices > 32) dist_slices = 32;                                   // sweep 4 .. 64 in profiles/README.md: 16-32 is the flat optimum
     if (dist_slices < 1) dist_slices = 1;
     char* ws = nullptr;
-    NGLOD_CUDA_TRY(cudaMallocAsync(&ws, ws_bytes + 256, st));
+    cudaMemPool_t pool = nullptr;
+    if (int e = m2s_scratch_pool(&pool)) return e;
+    NGLOD_CUDA_TRY(cudaMallocFromPoolAsync(&ws, ws_bytes + 256, pool, st));
     TriRecord* recs = reinterpret_cast<TriRecord*>(ws + rec_off);
     uint3* partial = (slices > 1 || hier) ? reinterpret_cast<uint3*>(ws + part_off) : nullptr;
     int* hist = reinterpret_cast<int*>(ws + hist_off);
