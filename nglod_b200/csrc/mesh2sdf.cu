@@ -354,6 +354,74 @@ constexpr int M2S_WARP_THREADS = 128;
 constexpr long long M2S_HIER_MIN_POINTS = NGLOD_M2S_HIER_MIN;
 constexpr float M2S_PROJ_R = 1.8f;          // the projected grids span [-R, R]^2 (> sqrt(3)); points beyond clamp to the rim
 
+// Pre-pass of the distance half: every point's exact distance to the triangles of the two patches nearest to its warp.
+// That is a true candidate of the minimum (it goes into partial[].x like any other) and a tight culling bound for
+// every slice of the walk below from its first patch on -- with the bound read off the patch spheres alone, a slice
+// that does not contain the near part of the surface kept every triangle within (distance + patch radius + 2 warp
+// radii) alive for the whole slice.
+__global__ void __launch_bounds__(M2S_WARP_THREADS)
+mesh2sdf_bound_kernel(const float* __restrict__ points, const long long n, const TriRecord* __restrict__ recs,
+                      const unsigned* __restrict__ tflags, const float4* __restrict__ patches,
+                      const long long num_tris, uint3* __restrict__ partial) {
+    const long long i = (long long)blockIdx.x * M2S_WARP_THREADS + threadIdx.x;
+    const bool active = i < n;
+    const int lane = threadIdx.x & 31;
+    float P[3] = {0.f, 0.f, 0.f};
+    if (active) { P[0] = __ldg(points + 3 * i); P[1] = __ldg(points + 3 * i + 1); P[2] = __ldg(points + 3 * i + 2); }
+    {
+        const unsigned am = __ballot_sync(0xffffffffu, active);
+        if (am == 0u) return;
+        const int src = __ffs(am) - 1;
+        const float q0 = __shfl_sync(0xffffffffu, P[0], src), q1 = __shfl_sync(0xffffffffu, P[1], src), q2 = __shfl_sync(0xffffffffu, P[2], src);
+        if (!active) { P[0] = q0; P[1] = q1; P[2] = q2; }
+    }
+    float wc[3], wr;
+    m2s_warp_sphere(P, true, wc, wr);
+    const long long num_patches = (num_tris + M2S_PATCH - 1) / M2S_PATCH;
+    // the two patches whose spheres come closest to the warp's centre (only patches a distance can come from)
+    float k1 = INFINITY, k2 = INFINITY;
+    long long p1 = -1, p2 = -1;
+    for (long long pt = lane; pt < num_patches; pt += 32) {
+        const float4 s = __ldg(patches + pt);
+        if (!(s.w >= 0.0f)) continue;
+        const float v[3] = {s.x - wc[0], s.y - wc[1], s.z - wc[2]};
+        const float key = sqrtf(dot3(v, v)) - s.w;
+        if (key < k1) { k2 = k1; p2 = p1; k1 = key; p1 = pt; }
+        else if (key < k2) { k2 = key; p2 = pt; }
+    }
+    long long pick[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        float bk = k1; long long bp = p1;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            const float ok = __shfl_xor_sync(0xffffffffu, bk, o);
+            const long long op = __shfl_xor_sync(0xffffffffu, bp, o);
+            if (ok < bk || (ok == bk && op >= 0 && (bp < 0 || op < bp))) { bk = ok; bp = op; }
+        }
+        pick[r] = bp;
+        if (bp >= 0 && bp == p1) { k1 = k2; p1 = p2; k2 = INFINITY; p2 = -1; }      // the owner moves on to its runner-up
+    }
+    float mind2 = INFINITY;
+#pragma unroll 1
+    for (int r = 0; r < 2; ++r) {
+        if (pick[r] < 0) continue;
+        const long long t0 = pick[r] * M2S_PATCH;
+        const unsigned fl = (t0 + lane < num_tris) ? __ldg(tflags + t0 + lane) : 0u;
+        unsigned todo = __ballot_sync(0xffffffffu, (fl >> 31) != 0u);
+        while (todo) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const TriRecord& rr = recs[t0 + j];
+            float p0[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) p0[k] = P[k] - rr.a[k];
+            mind2 = fminf(mind2, m2s_tri_dist2(rr, P, p0));
+        }
+    }
+    if (active && mind2 < INFINITY) partial[i].x = __float_as_uint(mind2);       // after m2s_init_kernel, before the walk
+}
+
 __global__ void __launch_bounds__(M2S_WARP_THREADS)
 mesh2sdf_dist_kernel(const float* __restrict__ points, const long long n, const TriRecord* __restrict__ recs,
                      const float4* __restrict__ tsph, const unsigned* __restrict__ tflags,
@@ -374,17 +442,14 @@ mesh2sdf_dist_kernel(const float* __restrict__ points, const long long n, const 
     m2s_warp_sphere(P, true, wc, wr);
     float mind2 = INFINITY;
     const long long num_patches = (num_tris + M2S_PATCH - 1) / M2S_PATCH;
-    float mind;                     // culling bound: starts as an upper bound of every lane's distance
+    // culling bound: the lane's distance to the triangles the pre-pass looked at (a true candidate, hence an upper bound)
+    float mind;
     {
-        float ub = INFINITY;
-        for (long long pt = lane; pt < num_patches; pt += 32) {
-            const float4 s = __ldg(patches + pt);
-            const float v[3] = {s.x - wc[0], s.y - wc[1], s.z - wc[2]};
-            if (s.w >= 0.0f) ub = fminf(ub, sqrtf(dot3(v, v)) + s.w);
-        }
-#pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) ub = fminf(ub, __shfl_xor_sync(0xffffffffu, ub, o));
-        mind = (ub + wr) * 1.0001f + 1e-6f;
+        const unsigned am = __ballot_sync(0xffffffffu, active);
+        float m0 = active ? __uint_as_float(partial[i].x) : 0.f;
+        const float ms = __shfl_sync(0xffffffffu, m0, __ffs(am) - 1);
+        if (!active) m0 = ms;
+        mind = sqrtf(m0) * 1.00001f + 1e-7f;
     }
     // gridDim.y slices of the patch range: points near the medial axis (the centre of a sphere, the axis of a torus) are
     // equally far from a large part of the surface, no bound can dismiss it, and the few warps holding them would walk
@@ -393,6 +458,8 @@ mesh2sdf_dist_kernel(const float* __restrict__ points, const long long n, const 
     const long long patch_begin = (long long)blockIdx.y * per_slice;
     const long long patch_end = min(num_patches, patch_begin + per_slice);
     float wmind = mind;             // loosest running bound in the warp
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) wmind = fmaxf(wmind, __shfl_xor_sync(0xffffffffu, wmind, o));
     for (long long pbase = patch_begin; pbase < patch_end; pbase += 32) {
         bool keep = false;
         if (pbase + lane < patch_end) {
@@ -810,6 +877,8 @@ extern "C" int nglod_mesh2sdf(const float* points, int64_t n, const float* tris,
     if (!err && hier) {
         int* pbin = reinterpret_cast<int*>(ws + pbin_off);
         int* pidx = reinterpret_cast<int*>(ws + pidx_off);
+        mesh2sdf_bound_kernel<<<(int)((n + M2S_WARP_THREADS - 1) / M2S_WARP_THREADS), M2S_WARP_THREADS, 0, st>>>(
+            pts, (long long)n, recs, tflags, patches, (long long)num_tris, partial);
         const dim3 gd((unsigned)((n + M2S_WARP_THREADS - 1) / M2S_WARP_THREADS), (unsigned)dist_slices);
         mesh2sdf_dist_kernel<<<gd, M2S_WARP_THREADS, 0, st>>>(pts, (long long)n, recs, tsph, tflags, patches,
                                                               (long long)num_tris, partial);
