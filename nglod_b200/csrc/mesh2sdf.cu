@@ -787,8 +787,8 @@ extern "C" int nglod_mesh2sdf(const float* points, int64_t n, const float* tris,
     const bool hier = getenv("NGLOD_M2S_BRUTE") == nullptr && sort && n >= M2S_HIER_MIN_POINTS &&
                       num_tris >= 4 * M2S_PATCH && num_tris < 100000000ll && n * M2S_NDIR < 2000000000ll;
     const long long num_patches = (num_tris + M2S_PATCH - 1) / M2S_PATCH;
-    int G = 32;                                                              // projected grid: ~sqrt(#triangles) cells a side
-    while (G < 256 && (long long)G * G < num_tris) G *= 2;
+    int G = 32;                                                              // projected grid: ~2 sqrt(#triangles) cells a side
+    while (G < 512 && (long long)G * G < 4 * num_tris) G *= 2;               // sweep x1 / x4 / x16 / x64 in profiles/README.md
     const long long proj_bins = (long long)M2S_NDIR * G * G;                 // a multiple of 1024
     // slices of the triangle range (walk only): enough CTAs for ~4 waves of the machine, at least 4 tiles per slice
     int slices = 1;
