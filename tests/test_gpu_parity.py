@@ -392,7 +392,7 @@ def test_mesh2sdf_hierarchy_grazing_and_grid_sizes():
     """The sign half bins points under each triangle's projection widened by the rounding error of the exact test, which
     blows up when a stab line grazes the triangle's plane: cubes whose faces are parallel to three stab directions
     (determinant exactly 0: direction skipped) and rotated off them by 1e-6 .. 1e-2 rad (determinants down to the 1e-8
-    threshold) must still match the brute-force walk bit for bit.  Also every projected-grid size (32 .. 256 cells a side)."""
+    threshold) must still match the brute-force walk bit for bit.  Also every projected-grid size (32 .. 512 cells a side)."""
     import math
     import os
     from nglod_b200 import ops
@@ -426,7 +426,9 @@ def test_mesh2sdf_hierarchy_grazing_and_grid_sizes():
         if angle == 0.3:
             inside = (pts @ R.to(DEV)).abs().max(dim=1).values < 0.5 - 1e-4       # rotate back: inside the cube
             assert (a[inside] < 0).all()
-    for sub, n in ((2, 20000), (3, 20000), (4, 30000), (6, 50000)):              # 320 .. 81 920 triangles: G = 32 .. 256
+    a, b = both(pts, (_cube_mesh(4) * 1.3).to(DEV).contiguous())                 # 192 triangles: the smallest grid, G = 32
+    assert torch.equal(a.view(torch.int32), b.view(torch.int32))
+    for sub, n in ((2, 20000), (3, 20000), (4, 30000), (6, 50000)):              # 320 .. 81 920 triangles: G = 64 .. 512
         V, Fc = icosphere(sub)
         tri = V[Fc].to(DEV).contiguous()
         p = (torch.rand(n, 3, generator=g) * 2.2 - 1.1).to(DEV)
