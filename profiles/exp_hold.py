@@ -1,4 +1,5 @@
-"""Straggler hold (NGLOD_TRACE_HOLD = march steps after which a group stops refilling): frame time and identical output."""
+"""[historical: the NGLOD_TRACE_HOLD knob existed only for this sweep; the result is recorded in profiles/README.md]
+Straggler hold (NGLOD_TRACE_HOLD = march steps after which a group stops refilling): frame time and identical output."""
 import os, sys, torch
 sys.path.insert(0, '/root/repo')
 import bench

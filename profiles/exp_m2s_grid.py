@@ -1,4 +1,5 @@
-"""Projected-grid resolution sweep for the stab half (NGLOD_M2S_GRID_MULT: G^2 >= mult * #triangles)."""
+"""[historical: the NGLOD_M2S_GRID_MULT knob existed only for this sweep; the result is recorded in profiles/README.md]
+Projected-grid resolution sweep for the stab half (NGLOD_M2S_GRID_MULT: G^2 >= mult * #triangles)."""
 import os, sys, torch
 sys.path.insert(0, '/root/repo')
 from nglod_b200 import ops

@@ -1,4 +1,5 @@
-"""Distance-kernel slices sweep (NGLOD_M2S_DIST_SLICES), fixed seed, 500 k points."""
+"""[historical: the NGLOD_M2S_DIST_SLICES knob existed only for this sweep; the result is recorded in profiles/README.md]
+Distance-kernel slices sweep (NGLOD_M2S_DIST_SLICES), fixed seed, 500 k points."""
 import os, sys, torch
 sys.path.insert(0, '/root/repo')
 from nglod_b200 import ops
