@@ -341,7 +341,8 @@ mesh2sdf_kernel(const float* __restrict__ points, const long long n, const TriRe
 //     an upper bound read off the patch spheres and tightens as the warp goes.
 //
 // (2) SIGN, triangle-driven.  A line through P along stab direction k hits a triangle only if P's projection along k
-//     falls inside the triangle's projection.  For each of the 13 directions the points are binned on a G x G grid of the
+//     falls inside the triangle's projection.  For each of the 13 directions the points are binned on a G x G grid (spanning
+//     the extent of the call's points and vertices) of the
 //     plane across it (one counting sort over all 13 x G x G cells; exactly 13 n entries, so the scratch is bounded
 //     without a host round trip).  One warp per (triangle, direction) walks the cells under the triangle's projected
 //     bounding box -- widened by the worst rounding error of the exact test, which grows as the line grazes the
@@ -352,7 +353,27 @@ constexpr int M2S_WARP_THREADS = 128;
 #define NGLOD_M2S_HIER_MIN 16384
 #endif
 constexpr long long M2S_HIER_MIN_POINTS = NGLOD_M2S_HIER_MIN;
-constexpr float M2S_PROJ_R = 1.8f;          // the projected grids span [-R, R]^2 (> sqrt(3)); points beyond clamp to the rim
+constexpr float M2S_UNIT_R = 1.8f;          // scene radius the rounding-error constants below were derived for (unit cube: sqrt(3))
+
+// The projected grids span [-R, R]^2 with R = the largest |point| or |vertex| of the call (a device-side value: no host
+// round trip), so a mesh that was not normalised into the unit sphere still spreads over the cells.
+__global__ void __launch_bounds__(256)
+m2s_extent_kernel(const float* __restrict__ points, const long long n, const float* __restrict__ tris, const long long num_tris,
+                  unsigned* __restrict__ ext2_bits) {
+    const long long total = n + 3 * num_tris;
+    float m = 0.f;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const float* v = i < n ? points + 3 * i : tris + 3 * (i - n);
+        const float r2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+        if (r2 == r2) m = fmaxf(m, r2);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(ext2_bits, __float_as_uint(m));      // non-negative floats order like their bits
+}
+__device__ __forceinline__ float m2s_proj_radius(const unsigned* __restrict__ ext2_bits) {
+    return fmaxf(sqrtf(__uint_as_float(__ldg(ext2_bits))) * 1.001f, 1e-3f);
+}
 
 // Pre-pass of the distance half: every point's exact distance to the triangles of the two patches nearest to its warp.
 // That is a true candidate of the minimum (it goes into partial[].x like any other) and a tight culling bound for
@@ -520,27 +541,28 @@ __device__ __forceinline__ void m2s_stab_basis(const int k, float* e1, float* e2
 }
 
 // cell coordinate of a projected coordinate: monotone in c, clamped to the grid (NaN -> 0)
-__device__ __forceinline__ int m2s_proj_cell(const float c, const float inv_h, const int G) {
-    const float f = floorf((c + M2S_PROJ_R) * inv_h);
+__device__ __forceinline__ int m2s_proj_cell(const float c, const float R, const float inv_h, const int G) {
+    const float f = floorf((c + R) * inv_h);
     return (int)fminf(fmaxf(f, 0.0f), (float)(G - 1));
 }
 
 // pass 1 (cursor == counts, pidx == nullptr): histogram of the 13 projected cells of every point;
 // pass 2 (cursor == exclusive offsets): scatter the point indices; afterwards cursor[c] is the END of cell c.
 __global__ void __launch_bounds__(256)
-m2s_proj_bin_kernel(const float* __restrict__ x, const long long n, const int G, int* __restrict__ cursor,
-                    int* __restrict__ pidx) {
+m2s_proj_bin_kernel(const float* __restrict__ x, const long long n, const int G, const unsigned* __restrict__ ext2_bits,
+                    int* __restrict__ cursor, int* __restrict__ pidx) {
     __shared__ float basis[M2S_NDIR][6];
     if (threadIdx.x < M2S_NDIR) m2s_stab_basis(threadIdx.x, basis[threadIdx.x], basis[threadIdx.x] + 3);
     __syncthreads();
-    const float inv_h = (float)G / (2.0f * M2S_PROJ_R);
+    const float R = m2s_proj_radius(ext2_bits);
+    const float inv_h = (float)G / (2.0f * R);
     const long long stride = (long long)gridDim.x * 256;
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) {
         const float P[3] = {__ldg(x + 3 * i), __ldg(x + 3 * i + 1), __ldg(x + 3 * i + 2)};
 #pragma unroll 1
         for (int k = 0; k < M2S_NDIR; ++k) {
-            const int cx = m2s_proj_cell(dot3(P, basis[k]), inv_h, G);
-            const int cy = m2s_proj_cell(dot3(P, basis[k] + 3), inv_h, G);
+            const int cx = m2s_proj_cell(dot3(P, basis[k]), R, inv_h, G);
+            const int cy = m2s_proj_cell(dot3(P, basis[k] + 3), R, inv_h, G);
             const int slot = atomicAdd(cursor + ((long long)k * G + cy) * G + cx, 1);
             if (pidx) pidx[slot] = (int)i;
         }
@@ -549,8 +571,8 @@ m2s_proj_bin_kernel(const float* __restrict__ x, const long long n, const int G,
 
 __global__ void __launch_bounds__(M2S_WARP_THREADS)
 mesh2sdf_stab_kernel(const float* __restrict__ points, const TriRecord* __restrict__ recs, const long long num_tris,
-                     const int G, const int* __restrict__ cell_end, const int* __restrict__ pidx,
-                     uint3* __restrict__ partial) {
+                     const int G, const unsigned* __restrict__ ext2_bits, const int* __restrict__ cell_end,
+                     const int* __restrict__ pidx, uint3* __restrict__ partial) {
     const int lane = threadIdx.x & 31;
     const long long task = (long long)blockIdx.x * (M2S_WARP_THREADS / 32) + (threadIdx.x >> 5);
     const long long t = task / M2S_NDIR;
@@ -561,14 +583,17 @@ mesh2sdf_stab_kernel(const float* __restrict__ points, const TriRecord* __restri
     float e1[3], e2[3];
     m2s_stab_basis(k, e1, e2);
     const float inv_det = r.inv_det[k];
-    // widest rounding error of u / v, as a displacement along the edges: ~eps |p0| |v10| |v02| / |det|  (|p0| <= ~4)
-    float m = (1e-5f + 2e-6f * sqrtf(dot3(r.v10, r.v10) * dot3(r.v02, r.v02)) * fabsf(inv_det)) * 1.01f;
-    if (!(m < 8.0f)) m = 8.0f;                                   // also catches NaN: walk the whole grid
+    // widest rounding error of u / v, as a displacement along the edges: ~eps |p0| |v10| |v02| / |det|; the constants are
+    // for |p0| <= ~4 (unit cube) and scale with the radius of the scene
+    const float R = m2s_proj_radius(ext2_bits);
+    const float scale = fmaxf(1.0f, R * (1.0f / M2S_UNIT_R));
+    float m = (1e-5f + 2e-6f * sqrtf(dot3(r.v10, r.v10) * dot3(r.v02, r.v02)) * fabsf(inv_det)) * 1.01f * scale;
+    if (!(m < 4.0f * R)) m = 4.0f * R;                           // also catches NaN: walk the whole grid
     const float xa = dot3(r.a, e1), xb = dot3(r.b, e1), xc = dot3(r.c, e1);
     const float ya = dot3(r.a, e2), yb = dot3(r.b, e2), yc = dot3(r.c, e2);
-    const float inv_h = (float)G / (2.0f * M2S_PROJ_R);
-    int cx0 = m2s_proj_cell(fminf(xa, fminf(xb, xc)) - m, inv_h, G), cx1 = m2s_proj_cell(fmaxf(xa, fmaxf(xb, xc)) + m, inv_h, G);
-    int cy0 = m2s_proj_cell(fminf(ya, fminf(yb, yc)) - m, inv_h, G), cy1 = m2s_proj_cell(fmaxf(ya, fmaxf(yb, yc)) + m, inv_h, G);
+    const float inv_h = (float)G / (2.0f * R);
+    int cx0 = m2s_proj_cell(fminf(xa, fminf(xb, xc)) - m, R, inv_h, G), cx1 = m2s_proj_cell(fmaxf(xa, fmaxf(xb, xc)) + m, R, inv_h, G);
+    int cy0 = m2s_proj_cell(fminf(ya, fminf(yb, yc)) - m, R, inv_h, G), cy1 = m2s_proj_cell(fmaxf(ya, fmaxf(yb, yc)) + m, R, inv_h, G);
     if (!(xa == xa && xb == xb && xc == xc && ya == ya && yb == yb && yc == yc)) { cx0 = cy0 = 0; cx1 = cy1 = G - 1; }
     const float edge2[3] = {-r.v02[0], -r.v02[1], -r.v02[2]};
     const float pv[3] = {r.pvec[k][0], r.pvec[k][1], r.pvec[k][2]};
@@ -815,6 +840,7 @@ extern "C" int nglod_mesh2sdf(const float* points, int64_t n, const float* tris,
     const size_t psph_off = reserve(hier ? (size_t)num_patches * sizeof(float4) : 0);
     const size_t pbin_off = reserve(hier ? (size_t)proj_bins * 4 : 0);
     const size_t pidx_off = reserve(hier ? (size_t)n * M2S_NDIR * 4 : 0);
+    const size_t ext_off = reserve(hier ? 4 : 0);
     const int bsum_n = (int)((std::max<long long>(proj_bins, M2S_BINS) / 1024 + 1023) / 1024 * 1024);
     const size_t bsum_off = reserve((size_t)bsum_n * 4);
     long long dist_slices = num_patches / 32;                                 // >= 32 patches (one round of level 1) per slice
@@ -883,16 +909,19 @@ extern "C" int nglod_mesh2sdf(const float* points, int64_t n, const float* tris,
         mesh2sdf_dist_kernel<<<gd, M2S_WARP_THREADS, 0, st>>>(pts, (long long)n, recs, tsph, tflags, patches,
                                                               (long long)num_tris, partial);
         err = (int)cudaGetLastError();
+        unsigned* ext = reinterpret_cast<unsigned*>(ws + ext_off);
         if (!err) err = (int)cudaMemsetAsync(pbin, 0, (size_t)proj_bins * 4, st);
+        if (!err) err = (int)cudaMemsetAsync(ext, 0, 4, st);
         if (!err) {
             const int nb = (int)std::min<long long>((n + 255) / 256, sm8);
-            m2s_proj_bin_kernel<<<nb, 256, 0, st>>>(pts, (long long)n, G, pbin, nullptr);
+            m2s_extent_kernel<<<nb, 256, 0, st>>>(pts, (long long)n, tris, (long long)num_tris, ext);
+            m2s_proj_bin_kernel<<<nb, 256, 0, st>>>(pts, (long long)n, G, ext, pbin, nullptr);
             m2s_scan(pbin, proj_bins, reinterpret_cast<int*>(ws + bsum_off), bsum_n, st);
-            m2s_proj_bin_kernel<<<nb, 256, 0, st>>>(pts, (long long)n, G, pbin, pidx);
+            m2s_proj_bin_kernel<<<nb, 256, 0, st>>>(pts, (long long)n, G, ext, pbin, pidx);
             const long long tasks = (long long)num_tris * M2S_NDIR;
             const long long wpc = M2S_WARP_THREADS / 32;
             mesh2sdf_stab_kernel<<<(int)((tasks + wpc - 1) / wpc), M2S_WARP_THREADS, 0, st>>>(
-                pts, recs, (long long)num_tris, G, pbin, pidx, partial);
+                pts, recs, (long long)num_tris, G, ext, pbin, pidx, partial);
             err = (int)cudaGetLastError();
         }
     } else if (!err) {

@@ -426,6 +426,11 @@ def test_mesh2sdf_hierarchy_grazing_and_grid_sizes():
         if angle == 0.3:
             inside = (pts @ R.to(DEV)).abs().max(dim=1).values < 0.5 - 1e-4       # rotate back: inside the cube
             assert (a[inside] < 0).all()
+    # a scene that was not normalised into the unit cube (x5.3, off-centre): the projected grids and the rounding margin
+    # follow the extent of the call; the spatial sorts clamp, so this is slow but must stay exact
+    V5, F5 = icosphere(3)
+    a, b = both((pts[:20000] * 5.3 + 0.7).contiguous(), ((V5[F5] * 5.3 * 0.8) + 0.7).to(DEV).contiguous())
+    assert torch.equal(a.view(torch.int32), b.view(torch.int32)) and int((a < 0).sum()) > 1000
     a, b = both(pts, (_cube_mesh(4) * 1.3).to(DEV).contiguous())                 # 192 triangles: the smallest grid, G = 32
     assert torch.equal(a.view(torch.int32), b.view(torch.int32))
     for sub, n in ((2, 20000), (3, 20000), (4, 30000), (6, 50000)):              # 320 .. 81 920 triangles: G = 64 .. 512
