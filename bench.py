@@ -522,10 +522,19 @@ def run_extras(net, args, device, rank, world, flush, log):
         loss.backward()
         opt.step()
     sp_ms = timed(sparse_step, iters=5, warm=2)
-    out["neural_spc_train_step_500k"] = {"ms_per_step": sp_ms, "points_per_s": world * pv.shape[0] / (sp_ms / 1e3),
+
+    def sparse_step_fused():          # one kernel: forward + loss + backward of the head (NeuralSPC.loss_backward)
+        opt.zero_grad(set_to_none=False)
+        nspc.loss_backward(xs7, gt7, lods=[5], pidx=[pv])
+        opt.step()
+    spf_ms = timed(sparse_step_fused, iters=5, warm=2)
+    out["neural_spc_train_step_500k"] = {"ms_per_step": spf_ms, "points_per_s": world * pv.shape[0] / (spf_ms / 1e3),
+                                         "autograd_ms_per_step": sp_ms,
                                          "voxels_level7": int(lp7.shape[0]), "corner_rows": int(nspc.corner_feats.shape[0]),
-                                         "note": "NeuralSPC (6 LODs, levels 2-7), head 5: sparse forward + gen-2 sparse "
-                                                 "backward through the parent chain + torch Adam; no gradient all-reduce"}
+                                         "note": "NeuralSPC (6 LODs, levels 2-7), head 5: fused sparse forward + loss + gen-2 "
+                                                 "backward through the parent chain (nglod_sparse_sdf_train_step) + torch Adam; "
+                                                 "autograd_ms_per_step = the same step as separate forward / loss / backward; "
+                                                 "no gradient all-reduce"}
     del nspc, opt
 
     # ---- the headless real-time loop (ray generation -> trace -> matcap shading, frame stays on the device)

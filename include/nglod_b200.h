@@ -324,6 +324,14 @@ int nglod_sparse_sdf_backward(const nglod_sparse_net_t* net, int32_t lod, const 
                               const float* grad_out, float* grad_corner_feats, float* gw0, float* gb0, float* gw1,
                               float* gb1, void* stream);
 
+/* Fused training step of one head of a natively sparse model: forward of LOD `lod`, L = loss_scale * sum_i (d_i - gt_i)^2
+ * ADDED to *loss_out (nullable), and the backward of nglod_sparse_sdf_backward with dL/dd = 2 loss_scale (d - gt), in ONE
+ * kernel - the sparse twin of nglod_sdf_train_step.  Replaces, per head, NeuralSPC.sdf + the L2 loss + autograd of the
+ * reference's sparse trainer (sdf-net/app/spc/NeuralSPC.py:104-145, the loss of lib/trainer.py:317-327). */
+int nglod_sparse_sdf_train_step(const nglod_sparse_net_t* net, int32_t lod, const float* x, const int32_t* pidx,
+                                const float* gt, int64_t n, float loss_scale, float* grad_corner_feats,
+                                float* gw0, float* gb0, float* gw1, float* gb1, float* loss_out, void* stream);
+
 /* In-voxel sphere tracing over the nuggets of nglod_spc_raytrace (level lod + base_lod), ONE persistent kernel:
  * first voxel (ray_aabb) -> [sparse sdf -> step -> re-locate the voxel from the new position] x num_steps -> central-
  * difference normals (h = normal_h, same voxel) on hits.  hit = |d| < min_dis or |d + dprev|/2 < 5*min_dis;

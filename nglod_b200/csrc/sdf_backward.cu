@@ -855,12 +855,13 @@ extern "C" int nglod_sdf_backward(const nglod_net_t* net, int32_t lod, const flo
                                          (cudaStream_t)stream);
 }
 
-extern "C" int nglod_sparse_sdf_backward(const nglod_sparse_net_t* net, int32_t lod, const float* x, const int32_t* pidx,
-                                         int64_t n, const float* grad_out, float* grad_corner_feats, float* gw0,
-                                         float* gb0, float* gw1, float* gb1, void* stream) {
+template <bool FUSED_LOSS>
+static int launch_sparse_backward(const nglod_sparse_net_t* net, int32_t lod, const float* x, const int32_t* pidx, int64_t n,
+                                  const float* grad_out, const float* gt, float loss_scale, float* grad_corner_feats,
+                                  float* gw0, float* gb0, float* gw1, float* gb1, float* loss_out, void* stream) {
     SparseBwd sp;
     if (int e = make_sparse_dev(net, lod, sp.sn, /*allow_summed=*/false)) return e;
-    if (n < 0 || (n > 0 && (!x || !pidx || !grad_out))) return NGLOD_EINVAL;
+    if (n < 0 || (n > 0 && (!x || !pidx || !(FUSED_LOSS ? gt : grad_out)))) return NGLOD_EINVAL;
     if (reinterpret_cast<uintptr_t>(grad_corner_feats) & 15u) return NGLOD_EINVAL;
     if (n == 0) return 0;
     sp.pidx = pidx;
@@ -868,15 +869,29 @@ extern "C" int nglod_sparse_sdf_backward(const nglod_sparse_net_t* net, int32_t 
     GradDev gdv;
     for (int i = 0; i < NGLOD_MAX_LODS; ++i) gdv.grids[i] = nullptr;
     gdv.w0 = gw0; gdv.b0 = gb0; gdv.w1 = gw1; gdv.b1 = gb1;
-    auto k2 = sdf_backward_mma_kernel<false, true>;
+    auto k2 = sdf_backward_mma_kernel<FUSED_LOSS, true>;
     NGLOD_CUDA_TRY(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, BW2_SMEM_BYTES));
     long long grid = nglod_sm_count();
     const int lpw = n > (long long)grid * BW2_WARPS * 8 ? 32 : 8;     // 128-query batches only while they fit one wave
     const long long want = (n + BW2_WARPS * lpw - 1) / (BW2_WARPS * lpw);
     if (want < grid) grid = want;
-    k2<<<(int)grid, BW2_THREADS, BW2_SMEM_BYTES, (cudaStream_t)stream>>>(sp.sn.dec, gdv, x, (long long)n, grad_out, nullptr,
-                                                                         0.f, nullptr, sp, lpw, 0);
+    k2<<<(int)grid, BW2_THREADS, BW2_SMEM_BYTES, (cudaStream_t)stream>>>(sp.sn.dec, gdv, x, (long long)n, grad_out, gt,
+                                                                         loss_scale, loss_out, sp, lpw, 0);
     return (int)cudaGetLastError();
+}
+
+extern "C" int nglod_sparse_sdf_backward(const nglod_sparse_net_t* net, int32_t lod, const float* x, const int32_t* pidx,
+                                         int64_t n, const float* grad_out, float* grad_corner_feats, float* gw0,
+                                         float* gb0, float* gw1, float* gb1, void* stream) {
+    return launch_sparse_backward<false>(net, lod, x, pidx, n, grad_out, nullptr, 0.f, grad_corner_feats, gw0, gb0, gw1, gb1,
+                                         nullptr, stream);
+}
+
+extern "C" int nglod_sparse_sdf_train_step(const nglod_sparse_net_t* net, int32_t lod, const float* x, const int32_t* pidx,
+                                           const float* gt, int64_t n, float loss_scale, float* grad_corner_feats,
+                                           float* gw0, float* gb0, float* gw1, float* gb1, float* loss_out, void* stream) {
+    return launch_sparse_backward<true>(net, lod, x, pidx, n, nullptr, gt, loss_scale, grad_corner_feats, gw0, gb0, gw1, gb1,
+                                        loss_out, stream);
 }
 
 extern "C" int nglod_sdf_train_step(const nglod_net_t* net, uint32_t lod_mask, const float* x, const float* gt,

@@ -482,5 +482,35 @@ class NeuralSPC(torch.nn.Module, SparseOctreeSDF):
             return _SparseSdfFunction.apply(x, pidx, self, lod, self.corner_feats, *params)
         return SparseOctreeSDF.sdf(self, x, lod, pidx)
 
+    def loss_backward(self, x, gt, lods=None, pidx=None, global_batch=None):
+        """Fused training step without the optimiser: for every head in `lods` (default: all) ONE kernel evaluates
+        d = sdf(x, lod), adds sum((d - gt)^2) / global_batch to the loss and accumulates dL/d(corner_feats) and
+        dL/d(decoder of that head) into the parameters' `.grad` (nglod_sparse_sdf_train_step) -- what
+        `sum(((net.sdf(x, l) - gt) ** 2).sum() for l in lods) / B` followed by `.backward()` computes through autograd,
+        minus the separate forward launch, the loss kernels and the saved tensors.  Points outside the octree (pidx < 0)
+        must be filtered by the caller, as for `sdf`.  Returns the per-head losses [len(lods)]."""
+        lods = list(range(self.num_lods)) if lods is None else list(lods)
+        lib = _lib.load()
+        xx = _f32c(x, "x")
+        g = _f32c(gt, "gt").reshape(-1)
+        n = xx.shape[0]
+        scale = 1.0 / float(global_batch if global_batch is not None else max(n, 1))
+        if self.corner_feats.grad is None:
+            self.corner_feats.grad = torch.zeros_like(self.corner_feats)
+        losses = torch.zeros(len(lods), device=xx.device, dtype=torch.float32)
+        s = self.struct()
+        with torch.cuda.device(xx.device):
+            for k, lod in enumerate(lods):
+                pi = (self.query(xx, lod) if pidx is None else pidx[k]).int().contiguous()
+                params = self._decoder_params(lod)
+                for p in params:
+                    if p.grad is None:
+                        p.grad = torch.zeros_like(p)
+                _lib.check(lib.nglod_sparse_sdf_train_step(ctypes.byref(s), int(lod), _ptr(xx), _ptr(pi), _ptr(g), n, scale,
+                                                           _ptr(self.corner_feats.grad), _ptr(params[0].grad),
+                                                           _ptr(params[1].grad), _ptr(params[2].grad), _ptr(params[3].grad),
+                                                           _ptr(losses[k:k + 1]), _stream()), "nglod_sparse_sdf_train_step")
+        return losses
+
     def forward(self, x):
         return self.sdf(x)

@@ -306,6 +306,45 @@ def test_neural_spc_forward_backward_vs_oracle(pos_invariant):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("pos_invariant", [False, True])
+def test_neural_spc_fused_loss_backward_equals_autograd(pos_invariant):
+    """NeuralSPC.loss_backward (one fused kernel per head: forward + L2 loss + backward, nglod_sparse_sdf_train_step) against
+    the same loss through autograd (separate sparse forward, torch loss, nglod_sparse_sdf_backward): losses and every
+    gradient, two heads accumulated into the same corner-feature gradient."""
+    spc = S.SPC(_shell_octree(5, "cuda"))
+    torch.manual_seed(4)
+    net = S.NeuralSPC(spc, num_lods=3, base_lod=3, feature_std=0.2, pos_invariant=pos_invariant)
+    x, _ = _points_in_voxels(spc, 5, 6007, 11)            # inside level-5 voxels, hence inside their ancestors too
+    x = x.cuda()
+    gt = (torch.rand(x.shape[0], 1, generator=torch.Generator().manual_seed(5)) - 0.5).cuda()
+    lods = [0, 2]
+    for p in net.parameters():
+        p.grad = None
+    ref_losses = []
+    total = 0
+    for lod in lods:
+        l = ((net.sdf(x, lod) - gt) ** 2).sum() / x.shape[0]
+        ref_losses.append(l.item())
+        total = total + l
+    total.backward()
+    ref = {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}
+    for p in net.parameters():
+        p.grad = None
+    losses = net.loss_backward(x, gt, lods=lods)
+    for a, b in zip(losses.tolist(), ref_losses):
+        assert abs(a - b) < 1e-5 * max(1.0, abs(b))
+    got = {k: p.grad for k, p in net.named_parameters() if p.grad is not None}
+    for k, r in ref.items():
+        assert (got[k] - r).abs().max() / r.abs().max() < 3e-4, k
+    for k, g in got.items():                              # heads that were not trained: zero gradient, not garbage
+        if k not in ref:
+            assert not g.any(), k
+    # accumulates: a second call doubles the gradient
+    net.loss_backward(x, gt, lods=lods)
+    assert (net.corner_feats.grad - 2 * ref["corner_feats"]).abs().max() / ref["corner_feats"].abs().max() < 6e-4
+
+
+@pytest.mark.gpu
 def test_neural_spc_trains_and_traces():
     """A few hundred Adam steps on points inside the occupied voxels of a torus shell: the loss drops by >10x, and the
     in-voxel tracer renders the fitted surface (hits lie on the analytic torus)."""
