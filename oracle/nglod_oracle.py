@@ -346,3 +346,23 @@ def spc_sphere_trace(snet, lod, nuggets, level_points, ray_o, ray_d, num_steps=5
         g = torch.cat(g, dim=1)
         normal[hi] = g / g.norm(dim=1, keepdim=True).clamp_min(1e-30)
     return dict(x=x, depth=t, hit=hit, normal=normal, pidx=pidx)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Philox-4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11) -- the counter-based
+# generator of the mesh sampler kernel (csrc/sample_mesh.cu).  The reference draws its samples with torch's host RNG
+# (sdf-net/lib/torchgp/sample_surface.py:47-50, sample_uniform.py:31), so sampler parity is distributional; this
+# restatement pins the kernel's stream to the published algorithm (Random123 known-answer vectors, tests/).
+def philox4x32_10(counter, key):
+    c, k = [int(v) & 0xffffffff for v in counter], [int(v) & 0xffffffff for v in key]
+    for _ in range(10):
+        p0, p1 = 0xD2511F53 * c[0], 0xCD9E8D57 * c[2]
+        c = [(p1 >> 32) ^ c[1] ^ k[0], p1 & 0xffffffff, (p0 >> 32) ^ c[3] ^ k[1], p0 & 0xffffffff]
+        k = [(k[0] + 0x9E3779B9) & 0xffffffff, (k[1] + 0xBB67AE85) & 0xffffffff]
+    return c
+
+
+def sample_uniform_philox(seed, index):
+    """The 'rand' sample `index` of nglod_sample_mesh for Philox key `seed`: (word >> 8) * 2^-24 * 2 - 1 per coordinate."""
+    r = philox4x32_10([index & 0xffffffff, index >> 32, 0, 0], [seed & 0xffffffff, seed >> 32])
+    return [((w >> 8) / 16777216.0) * 2.0 - 1.0 for w in r[:3]]

@@ -503,6 +503,19 @@ def test_sample_mesh_kernel_distribution():
     assert lib.nglod_sample_mesh(None, None, 0, None, None, 40, 1, 0.0, 0, None, None, None) == _lib.EINVAL
 
 
+def test_sample_mesh_stream_is_philox():
+    """The sampler's random stream is Philox-4x32-10 with counter = sample index, key = seed: 'rand' samples equal the
+    oracle's restatement of the published algorithm exactly (which test_philox_known_answers pins to Random123's vectors)."""
+    from nglod_b200 import ops
+    V = torch.zeros(3, 3, device=DEV)
+    Fc = torch.tensor([[0, 1, 2]], device=DEV)
+    for seed in (0, 1, 0x299f31d0a4093822, 2 ** 62 - 1):
+        pts = ops.sample_mesh(V, Fc, None, ["rand"], 5000, seed=seed).cpu()
+        for i in (0, 1, 2, 31, 32, 255, 4999):
+            want = torch.tensor(O.sample_uniform_philox(seed, i), dtype=torch.float32)
+            assert torch.equal(pts[i], want), (seed, i)
+
+
 def test_mesh_dataset_protocol():
     from nglod_b200.lib.datasets import MeshDataset
     from nglod_b200.lib.torchgp import torus

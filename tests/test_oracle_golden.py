@@ -132,3 +132,11 @@ def test_oracle_mesh2sdf_on_sphere():
     far = (r - 1).abs() > 0.06                                      # outside the faceting band
     assert torch.equal(d[far] < 0, (r < 1)[far])
     assert ((d - (r - 1)).abs() < 0.06).all()
+
+
+def test_philox_known_answers():
+    """Random123's published known-answer vectors for philox4x32-10 (kat_vectors): the generator the sampler kernel uses."""
+    assert O.philox4x32_10([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert O.philox4x32_10([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert O.philox4x32_10([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
