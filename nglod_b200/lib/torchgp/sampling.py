@@ -75,6 +75,15 @@ def sample_uniform(num_samples, device="cpu"):
     return torch.rand(num_samples, 3, device=device) * 2.0 - 1.0
 
 
+def sample_spc(corners, level, num_samples):
+    """`num_samples` uniform points inside each voxel whose low corner is in `corners` [M,3] (integer coordinates at
+    `level`), in [-1,1]^3 (sample_spc.py:26-43)."""
+    res = 2.0 ** level
+    samples = torch.rand(corners.shape[0], num_samples, 3, device=corners.device)
+    samples = (corners[..., None, :3].float() + samples).reshape(-1, 3) / res
+    return samples * 2.0 - 1.0
+
+
 def point_sample(V, F, techniques, num_samples):
     """`num_samples` points per technique ('trace' = on-surface, 'near', 'rand'), concatenated in order."""
     if V.is_cuda:

@@ -305,6 +305,57 @@ def test_neural_spc_forward_backward_vs_oracle(pos_invariant):
             assert (a.grad.cpu() - b.grad).abs().max() / b.grad.abs().max() < 3e-4
 
 
+def test_spc_dataset_protocol_on_cpu():
+    """SPCDataset (SPCDataset.py:51-224) host logic, on the CPU with the oracle's mesh2sdf as the labeller: the pool holds
+    samples_per_voxel points per occupied voxel plus twice as many surface points, only samples inside occupied voxels
+    survive, labels are the labeller's, blocks partition the voxels by Morton range, resample shuffles and truncates."""
+    import types
+    from nglod_b200.lib.datasets import SPCDataset
+    from nglod_b200.lib.torchgp import torus, normalize
+    level = 4
+    spc = S.SPC(_shell_octree(level, "cpu"))
+    net = types.SimpleNamespace(spc=spc, base_lod=2, num_lods=3)              # finest level = 2 + 3 - 1 = 4
+    V, F = torus(0.6, 0.25, 24, 12)
+    calls = []
+
+    def labeller(Vn, Fn, p):
+        calls.append(p.shape[0])
+        return O.mesh2sdf(p, Vn[Fn])
+
+    torch.manual_seed(0)
+    ds = SPCDataset(net, args=None, sample_mode=["rand"], get_normals=False, num_samples=3000, samples_per_voxel=4,
+                    block_res=7, mesh=(V, F), sdf_fn=labeller)
+    assert ds.get_block_idxes(lod=2) == [0]                                   # level 4 <= block_res: one block
+    ds.init()
+    nvox = spc.level_points(level).shape[0]
+    assert sum(calls) == 3 * 4 * nvox                                         # voxel samples + near + trace
+    q = spc.query(S.quantize_points(ds.pts_, level), level)
+    assert (q > -1).all() and ds.pts_.shape[0] == int((ds.pidx > -1).sum())
+    assert ds.pts_.shape[0] >= 4 * nvox                                       # every in-voxel sample survives
+    Vn, Fn = normalize(V, F)
+    assert torch.equal(ds.d_[:500, 0], O.mesh2sdf(ds.pts_[:500], Vn[Fn]))
+    ds.resample(lod=2, idx=0)
+    assert len(ds) == 3000 and ds.num_shapes() == 1
+    p0, d0 = ds[0]
+    assert p0.shape == (3,) and d0.shape == (1,)
+    first = ds.pts.clone()
+    ds.resample(lod=2, idx=0)
+    assert not torch.equal(first, ds.pts)                                      # a new permutation
+    # finer than block_res: blocks of 2^(3 block_res) Morton codes, each resample stays inside its block
+    ds2 = SPCDataset(net, args=None, sample_mode=["rand"], get_normals=False, num_samples=10 ** 9, samples_per_voxel=2,
+                     block_res=3, mesh=(V, F), sdf_fn=labeller)
+    blocks = ds2.get_block_idxes(lod=2)
+    mort = S.points_to_morton(spc.level_points(level)[:, :3])
+    assert blocks == sorted(set((mort >> 9).tolist())) and len(blocks) > 1
+    ds2.init(block_idx=blocks[1])
+    vq = spc.level_points(level)[spc.query(S.quantize_points(ds2.pts_, level), level), :3]
+    inside = (S.points_to_morton(vq) >> 9) == blocks[1]
+    assert inside.sum() >= 2 * int((mort >> 9 == blocks[1]).sum())            # the block's voxel samples (+ surface samples in it)
+    ds2.resample(lod=2, idx=blocks[1])
+    vq = spc.level_points(level)[spc.query(S.quantize_points(ds2.pts, level), level), :3]
+    assert ((S.points_to_morton(vq) >> 9) == blocks[1]).all() and len(ds2) == int(inside.sum())
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("pos_invariant", [False, True])
 def test_neural_spc_fused_loss_backward_equals_autograd(pos_invariant):
