@@ -13,6 +13,7 @@ Outputs (small .npz files next to this script):
              gradients of the L2 loss, a 64x36 trace at lod 4, a mixed-origin ray set
   fit3.npz   a 3-LOD model fitted for a few hundred Adam steps to a torus (weights stored):
              sdf, 96x54 trace at lod 2, Renderer.render with AO
+  samplers.npz  lib/torchgp's host sampling recipe under fixed torch seeds
 """
 import os
 import sys
@@ -224,8 +225,35 @@ def spc_golden():
     print("spc:", n, "leaf voxels,", osize, "octree bytes, pyramid", pyramid, "queries hit", int((ident >= 0).sum()))
 
 
+def samplers():
+    """The host sampling recipe of the reference (sdf-net/lib/torchgp: normalize, per_face_normals, point_sample,
+    sample_surface, sample_near_surface, sample_spc) on a small procedural torus, under fixed torch seeds: the CPU path
+    of nglod_b200.lib.torchgp must reproduce these bit for bit; the sampler KERNEL is compared with this recipe
+    distributionally (its random stream is Philox, not torch's)."""
+    import lib.torchgp as R
+    from nglod_b200.lib.torchgp import torus
+    V, F = torus(0.6, 0.25, 16, 8)
+    V = V * 1.7 + 0.3                                           # not normalised yet
+    Vn, Fn = R.normalize(V.clone(), F.clone())
+    out = {"V": V.numpy(), "F": F.numpy(), "Vn": Vn.numpy(), "face_normals": R.per_face_normals(Vn, Fn).numpy()}
+    torch.manual_seed(7)
+    out["point_sample"] = R.point_sample(Vn, Fn, ["rand", "near", "trace", "near"], 64).numpy()
+    torch.manual_seed(8)
+    sp, sn = R.sample_surface(Vn, Fn, 50)
+    out["surface_pts"], out["surface_nrm"] = sp.numpy(), sn.numpy()
+    torch.manual_seed(9)
+    out["near"] = R.sample_near_surface(Vn, Fn, 50, variance=0.02).numpy()
+    corners = torch.tensor([[0, 0, 0], [7, 7, 7], [3, 1, 6], [2, 2, 2]], dtype=torch.int16)
+    torch.manual_seed(10)
+    out["spc_corners"], out["spc_samples"] = corners.numpy(), R.sample_spc(corners, 3, 6).numpy()
+    np.savez_compressed(os.path.join(HERE, "samplers.npz"), **out)
+    print("samplers:", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["rand5", "fit3", "spc"]
+    which = sys.argv[1:] or ["rand5", "fit3", "spc", "samplers"]
+    if "samplers" in which:
+        samplers()
     if "rand5" in which:
         rand5()
     if "fit3" in which:

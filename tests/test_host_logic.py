@@ -210,6 +210,30 @@ def test_samplers_and_meshes():
         assert F3.shape[0] == F.shape[0] + 2
 
 
+def test_host_samplers_reproduce_the_reference_under_equal_seeds():
+    """tests/golden/samplers.npz was produced by the reference's own lib/torchgp functions (imported in place) under fixed
+    torch seeds; the CPU path of nglod_b200.lib.torchgp is the same recipe and must give the same bits.  (The sampler
+    kernel draws from Philox instead and is compared with this recipe distributionally in the GPU tests.)"""
+    import os
+    import numpy as np
+    from nglod_b200.lib.torchgp import (normalize, per_face_normals, point_sample, sample_surface, sample_near_surface,
+                                        sample_spc)
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "samplers.npz"))
+    V, F = torch.from_numpy(g["V"]), torch.from_numpy(g["F"])
+    Vn, Fn = normalize(V.clone(), F.clone())
+    assert np.array_equal(Vn.numpy(), g["Vn"])
+    assert np.array_equal(per_face_normals(Vn, Fn).numpy(), g["face_normals"])
+    torch.manual_seed(7)
+    assert np.array_equal(point_sample(Vn, Fn, ["rand", "near", "trace", "near"], 64).numpy(), g["point_sample"])
+    torch.manual_seed(8)
+    sp, sn = sample_surface(Vn, Fn, 50)
+    assert np.array_equal(sp.numpy(), g["surface_pts"]) and np.array_equal(sn.numpy(), g["surface_nrm"])
+    torch.manual_seed(9)
+    assert np.array_equal(sample_near_surface(Vn, Fn, 50, variance=0.02).numpy(), g["near"])
+    torch.manual_seed(10)
+    assert np.array_equal(sample_spc(torch.from_numpy(g["spc_corners"]), 3, 6).numpy(), g["spc_samples"])
+
+
 def test_shard_helpers():
     from nglod_b200.dist import shard_range, interleaved_strips
     for n, w, al in ((921600, 8, 720), (10, 4, 1), (7, 8, 1), (1000, 3, 16)):
