@@ -347,7 +347,9 @@ sdf_backward_kernel(const NetDev net, const GradDev grad, const float* __restric
 #define BW2_PER_WARP (SDF_SMEM_PER_WARP + 32 * 4 + 32)           // tile, idx, mask words [32][4], gd[32]
 #define BW2_WLO_OFF (SDF_SMEM_WARP_OFF + BW2_WARPS * BW2_PER_WARP)   // TF32 low parts of W0ext (the staged copy keeps the high parts)
 #define BW2_SMEM_BYTES ((BW2_WLO_OFF + SDF_W0_FLOATS) * 4)
+#ifndef BW2_SMEM_GRID_MAX           // -DBW2_SMEM_GRID_MAX=23328 also takes R = 8 (93 KB): untested, see profiles/NEXT.md
 #define BW2_SMEM_GRID_MAX 4000      // floats: a 5^3 x 32 grid (R = 4) accumulated per CTA in shared memory
+#endif
 
 __device__ __forceinline__ uint32_t to_tf32(float x) {
     uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r;
