@@ -338,13 +338,13 @@ mesh2sdf_kernel(const float* __restrict__ points, const long long n, const TriRe
 //     piece of surface).  A warp, on its own (no shared memory, no barriers): one PATCH per lane -- keep it if its sphere
 //     could hold a closer triangle for one of the warp's points; for every kept patch one TRIANGLE per lane, the same test
 //     on the triangle's sphere; the survivors, one after the other, through the exact arithmetic.  The bound starts from
-//     an upper bound read off the patch spheres and tightens as the warp goes.
+//     a pre-pass (each point's exact distance to the triangles of the two patches nearest to its warp) and tightens as the
+//     warp goes; the patch range is cut into slices over gridDim.y and the slices merge by atomicMin.
 //
 // (2) SIGN, triangle-driven.  A line through P along stab direction k hits a triangle only if P's projection along k
-//     falls inside the triangle's projection.  For each of the 13 directions the points are binned on a G x G grid (spanning
-//     the extent of the call's points and vertices) of the
-//     plane across it (one counting sort over all 13 x G x G cells; exactly 13 n entries, so the scratch is bounded
-//     without a host round trip).  One warp per (triangle, direction) walks the cells under the triangle's projected
+//     falls inside the triangle's projection.  For each of the 13 directions the points are binned on a G x G grid of the
+//     plane across it, spanning the extent of the call's points and vertices (one counting sort over all 13 x G x G
+//     cells; exactly 13 n entries, so the scratch is bounded without a host round trip).  One warp per (triangle, direction) walks the cells under the triangle's projected
 //     bounding box -- widened by the worst rounding error of the exact test, which grows as the line grazes the
 //     triangle's plane -- and runs the exact test on the points binned there, one point per lane, OR-ing the 13-bit
 //     masks of the points it hits.
