@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define NGLOD_ABI_VERSION 6
+#define NGLOD_ABI_VERSION 7
 #define NGLOD_MAX_LODS 8
 
 /* nglod_net_t.math_mode */
@@ -108,6 +108,15 @@ const char* nglod_build_info(void);
 /* Self-test of the tensor-core plumbing: D[128,128] = A[128,40] * B[128,40]^T (row-major fp32 device
  * buffers) through the same operand layout / descriptors / 3xTF32 sequence / TMEM read-back as the SDF kernels. */
 int nglod_debug_tc_gemm(const float* A, const float* B, float* D, void* stream);
+
+/* Measurement probe (bench.py's roofline denominator for the gather-bound kernels): reads, for n_queries pseudo-random
+ * cells of a channels-last fp32 [(R+1)^3, 32] grid at `buf` (128-byte aligned), the 8 corner lines of the cell with
+ * 8 lanes x 16 B per line -- the address stream of the SDF kernels' gather, no arithmetic (structured = 1) -- or
+ * 8 * n_queries independent random 128-byte lines of the same buffer (structured = 0).  in_flight = 1..3: 8, 16 or 24
+ * line loads in flight per lane.  Bytes moved L2 -> SM: n_queries * 1024.  sink: device uint32[1], never written in
+ * practice.  No reference counterpart (the reference has no measurement hooks). */
+int nglod_probe_gather(const void* buf, int32_t grid_res, int64_t n_queries, int32_t in_flight,
+                       int32_t structured, uint32_t seed, uint32_t* sink, void* stream);
 
 /* ---- ray vs unit cube ---------------------------------------------------
  * Replaces: f_aabb / aabb_kernel, sdf-net/lib/extensions/sol_nglod/

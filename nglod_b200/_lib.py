@@ -10,6 +10,7 @@ import ctypes
 import os
 
 MAX_LODS = 8
+EXPECTED_ABI = 7        # include/nglod_b200.h NGLOD_ABI_VERSION the ctypes structs below were written against
 LOSS_PER_LOD = 0x80000000
 MATH_TC3XTF32 = 0
 MATH_FP32 = 1
@@ -95,6 +96,7 @@ SIGNATURES = {
     "nglod_abi_version": (ctypes.c_int, []),
     "nglod_build_info": (ctypes.c_char_p, []),
     "nglod_debug_tc_gemm": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "nglod_probe_gather": (ctypes.c_int, [c_void_p, c_int32, c_int64, c_int32, c_int32, ctypes.c_uint32, c_void_p, c_void_p]),
     "nglod_aabb": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "nglod_sdf_forward": (ctypes.c_int, [ctypes.POINTER(NetStruct), c_int32, c_void_p, c_int64, c_void_p, c_void_p]),
     "nglod_sdf_forward_all": (ctypes.c_int, [ctypes.POINTER(NetStruct), c_void_p, c_int64, c_void_p, c_void_p]),
@@ -158,6 +160,9 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the header and the .so disagree
         fn.restype = res
         fn.argtypes = args
+    if lib.nglod_abi_version() != EXPECTED_ABI:
+        raise RuntimeError(f"{LIB_PATH} has ABI version {lib.nglod_abi_version()}, this package binds version "
+                           f"{EXPECTED_ABI}: stale build -- run `python -m nglod_b200.build`")
     _lib = lib
     return lib
 

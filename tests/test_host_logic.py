@@ -21,7 +21,7 @@ def test_cabi_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.nglod_abi_version() == 6
+    assert lib.nglod_abi_version() == _lib.EXPECTED_ABI
     assert b"sm_100a" in lib.nglod_build_info()
     # struct layouts agree with the header (sizes computed from the declarations)
     assert ctypes.sizeof(_lib.NetStruct) == 6 * 4 + 8 * 4 + 7 * 8 * 8
