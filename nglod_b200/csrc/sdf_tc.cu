@@ -66,6 +66,160 @@ int launch_fwd(const NetDev& nd, const float* x, long long n, float* out, cudaSt
     return (int)cudaGetLastError();
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Warp-specialised forward (single-grid gathers).  The kernel above runs gather -> barrier -> 15 UMMAs -> epilogue
+// serially inside each 4-warp group, so a warp has loads in flight only ~40 % of the time and the SM pulls ~35 B/clk
+// out of L2 where the probe (probe.cu) measures ~69 B/clk for the same address stream.  Here the three phases run on
+// different warps and overlap tile by tile:
+//   producers (NP warps): 32 queries each -> set-up, 8 corner lines per query (8 lanes x LDG.128), FFMA2 interpolation,
+//                         hi/lo split, A rows into stage s of a 4-stage ring          -> mbarrier full[s] (4 arrivals)
+//   MMA warp (1 thread) : waits full[s] and acc_free[s], issues the 15 tcgen05.mma of the tile into TMEM accumulator s,
+//                         tcgen05.commit -> mbarrier mma_done[s]  (frees the A stage AND publishes the accumulator)
+//   epilogue (4 warps)  : waits mma_done[s], tcgen05.ld its 32 rows, d = b1 + W1.relu(.), stores out -> acc_free[s]
+// Tiles are assigned statically: CTA-local tile T = global tile T*gridDim.x + blockIdx.x, stage/accumulator T % 4,
+// row block (T, q) by producer warp (4T + q) % NP -- every role derives the same mapping, nothing is communicated but
+// the barriers.  Same arithmetic as the kernel above (tc_gather_single / tc_issue_tile / tc_epilogue): results are
+// bit-identical.
+#ifndef NGLOD_WS_PRODUCERS
+#define NGLOD_WS_PRODUCERS 16
+#endif
+#define WS_STAGES 4
+#define WS_WARPS (4 + 1 + NGLOD_WS_PRODUCERS)
+#define WS_THREADS (WS_WARPS * 32)
+#define WS_SMEM_A(s) (2 * TC_OPERAND_BYTES + (s) * 2 * TC_OPERAND_BYTES)
+#define WS_SMEM_W1 TC_SMEM_W1(WS_STAGES)
+#define WS_SMEM_BAR (WS_SMEM_W1 + 528)                 // full[4], mma_done[4], acc_free[4]
+#define WS_SMEM_TMEMPTR (WS_SMEM_BAR + 3 * WS_STAGES * 8)
+#define WS_SMEM_BYTES (WS_SMEM_TMEMPTR + 16)
+static_assert(WS_SMEM_BYTES <= 232448, "shared memory budget");
+
+template <int MODE>
+__global__ void __launch_bounds__(WS_THREADS, 1)
+sdf_forward_ws_kernel(const NetDev net, const float* __restrict__ x, const long long n, float* __restrict__ out) {
+    extern __shared__ __align__(128) char smem_tc[];
+    constexpr bool HALF = MODE == TC_SINGLE_HALF;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (n >= (1ll << 17)) {        // cold start: stream the grid into L2 at HBM speed while the prologue runs
+        const long long S = net.res[0] + 1;
+        const long long bytes = HALF ? S * S * net.res[0] * 128 : S * S * S * NGLOD_F * 4;
+        const char* base = reinterpret_cast<const char*>(net.grids[0]);
+        for (long long off = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 128; off < bytes;
+             off += (long long)gridDim.x * blockDim.x * 128)
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(base + off));
+    }
+    // ---- prologue: zero the operand ring, stage W0|b0 (hi/lo), W1, b1; barriers; TMEM
+    {
+        float wv[16];
+        tc_load_weights(net, 0, wv);
+        for (int e = threadIdx.x; e < WS_SMEM_BAR / 16; e += blockDim.x)
+            reinterpret_cast<float4*>(smem_tc)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncthreads();
+        tc_scatter_weights(net, smem_tc, WS_STAGES, 0, wv);
+        for (int base = 16 * blockDim.x; base < NGLOD_H * (NGLOD_F + 3) + 2 * NGLOD_H + 1; base += 16 * blockDim.x) {
+            tc_load_weights(net, base, wv);
+            tc_scatter_weights(net, smem_tc, WS_STAGES, base, wv);
+        }
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < WS_STAGES; ++s) {
+                mbar_init(smem_u32(smem_tc + WS_SMEM_BAR + 8 * s), 4);                       // full: 4 producer warps
+                mbar_init(smem_u32(smem_tc + WS_SMEM_BAR + 8 * (WS_STAGES + s)), 1);         // mma_done: tcgen05.commit
+                mbar_init(smem_u32(smem_tc + WS_SMEM_BAR + 8 * (2 * WS_STAGES + s)), 4);     // acc_free: 4 epilogue warps
+            }
+            mbar_fence_init();
+        }
+        if (warp == 0) tmem_alloc(smem_u32(smem_tc + WS_SMEM_TMEMPTR), 512);
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        __syncthreads();
+        tc_fence_after_sync();
+    }
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_tc + WS_SMEM_TMEMPTR);
+    const uint32_t bar0 = smem_u32(smem_tc + WS_SMEM_BAR);
+    auto full_bar = [&](int s) { return bar0 + 8u * (uint32_t)s; };
+    auto done_bar = [&](int s) { return bar0 + 8u * (uint32_t)(WS_STAGES + s); };
+    auto free_bar = [&](int s) { return bar0 + 8u * (uint32_t)(2 * WS_STAGES + s); };
+    // CTA-local tiles: global tile gt = T * gridDim.x + blockIdx.x while gt * 128 < n
+    const long long total_tiles = (n + TC_TILE_ROWS - 1) / TC_TILE_ROWS;
+    const int ntiles = (int)((total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+
+    if (warp >= 5) {
+        // ------------------------------------------------------------------ producers
+        const int p = warp - 5;
+        int rb = p;                                                   // row block = 4 * T + q
+        auto rb_query = [&](int r) { return ((long long)(r >> 2) * gridDim.x + blockIdx.x) * TC_TILE_ROWS + (r & 3) * 32 + lane; };
+        float px = 0.f, py = 0.f, pz = 0.f;
+        long long i = rb_query(rb);
+        if (rb < 4 * ntiles && i < n) { px = __ldg(x + 3 * i); py = __ldg(x + 3 * i + 1); pz = __ldg(x + 3 * i + 2); }
+        for (; rb < 4 * ntiles; rb += NGLOD_WS_PRODUCERS) {
+            const int T = rb >> 2, q = rb & 3, s = T & (WS_STAGES - 1), k = T / WS_STAGES;
+            const bool active = i < n;
+            // next row block's coordinates (DRAM) while this one is gathered
+            const long long i_next = rb_query(rb + NGLOD_WS_PRODUCERS);
+            float nx = 0.f, ny = 0.f, nz = 0.f;
+            if (rb + NGLOD_WS_PRODUCERS < 4 * ntiles && i_next < n) {
+                nx = __ldg(x + 3 * i_next); ny = __ldg(x + 3 * i_next + 1); nz = __ldg(x + 3 * i_next + 2);
+            }
+            float4 rec = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (active) rec = tc_setup_record<HALF>(px, py, pz, net.res[0]);
+            const unsigned live = __ballot_sync(0xffffffffu, active);
+            char* a_hi = smem_tc + WS_SMEM_A(s);
+            char* a_lo = a_hi + TC_OPERAND_BYTES;
+            // the stage is free once the MMAs of its previous tile have read it
+            if (k > 0) mbar_wait(done_bar(s), (uint32_t)((k - 1) & 1));
+            if (live) {
+                if (active) tc_store_split4(a_hi, a_lo, tc_elem_offset(q * 32 + lane, NGLOD_F), make_float4(px, py, pz, 1.f));
+                tc_gather_single<HALF>(net, rec, live, a_hi, a_lo, q * 32, lane);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_bar(s));
+            i = i_next; px = nx; py = ny; pz = nz;
+        }
+    } else if (warp == 4) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t b_hi = smem_u32(smem_tc + TC_SMEM_B_HI), b_lo = smem_u32(smem_tc + TC_SMEM_B_LO);
+            for (int T = 0; T < ntiles; ++T) {
+                const int s = T & (WS_STAGES - 1), k = T / WS_STAGES;
+                mbar_wait(full_bar(s), (uint32_t)(k & 1));
+                if (k > 0) mbar_wait(free_bar(s), (uint32_t)((k - 1) & 1));
+                tc_fence_after_sync();
+                const uint32_t a_hi = smem_u32(smem_tc + WS_SMEM_A(s));
+                tc_issue_tile(tmem_base + (uint32_t)(s * TC_N), a_hi, a_hi + TC_OPERAND_BYTES, b_hi, b_lo);
+                tc_commit(done_bar(s));
+            }
+        }
+        __syncwarp();               // reconverge before the CTA-wide barrier of the epilogue
+    } else {
+        // ------------------------------------------------------------------ epilogue
+        const float* w1 = reinterpret_cast<const float*>(smem_tc + WS_SMEM_W1);
+        for (int T = 0; T < ntiles; ++T) {
+            const int s = T & (WS_STAGES - 1), k = T / WS_STAGES;
+            mbar_wait(done_bar(s), (uint32_t)(k & 1));
+            tc_fence_after_sync();
+            const float d = tc_epilogue(tmem_base + (uint32_t)(s * TC_N) + ((uint32_t)(warp * 32) << 16), w1);
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(free_bar(s));
+            const long long i = ((long long)T * gridDim.x + blockIdx.x) * TC_TILE_ROWS + warp * 32 + lane;
+            if (i < n) out[i] = d;
+        }
+    }
+    tc_epilogue_free(tmem_base);
+}
+
+template <int MODE>
+int launch_fwd_ws(const NetDev& nd, const float* x, long long n, float* out, cudaStream_t st) {
+    auto kern = sdf_forward_ws_kernel<MODE>;
+    NGLOD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES));
+    long long grid = nglod_sm_count();
+    const long long want = (n + TC_TILE_ROWS - 1) / TC_TILE_ROWS;
+    if (want < grid) grid = want;
+    kern<<<(int)grid, WS_THREADS, WS_SMEM_BYTES, st>>>(nd, x, n, out);
+    return (int)cudaGetLastError();
+}
+
 // Debug / self-test: D[128,128] = A[128,40] * B[128,40]^T through the exact operand layout, descriptors,
 // 3xTF32 issue sequence and TMEM read-back the SDF kernels use.
 __global__ void __launch_bounds__(128, 1)
@@ -111,6 +265,13 @@ tc_gemm_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B
 }  // namespace
 
 int nglod_launch_sdf_forward_tc(const NetDev& nd, const float* x, long long n, float* out, cudaStream_t st) {
+#ifndef NGLOD_FWD_WS
+#define NGLOD_FWD_WS 1          // 0: the serial-group kernel for the single-grid gathers too (A/B experiments)
+#endif
+#if NGLOD_FWD_WS
+    if (nd.half_pairs) return launch_fwd_ws<TC_SINGLE_HALF>(nd, x, n, out, st);
+    if (nd.num_lods == 1) return launch_fwd_ws<TC_SINGLE_F32>(nd, x, n, out, st);
+#endif
     if (nd.half_pairs) return launch_fwd<TC_SINGLE_HALF>(nd, x, n, out, st);
     if (nd.num_lods == 1) return launch_fwd<TC_SINGLE_F32>(nd, x, n, out, st);
     return launch_fwd<TC_MULTI>(nd, x, n, out, st);

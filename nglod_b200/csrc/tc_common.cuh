@@ -90,6 +90,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t saddr, uint32_t parity) {
         :: "r"(saddr), "r"(parity) : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(uint32_t saddr) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(saddr) : "memory");
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
 }
