@@ -415,13 +415,18 @@ sdf_backward_mma_kernel(const NetDev net, const GradDev grad, const float* __res
     const long long batch = (long long)BW2_WARPS * lpw;
     for (long long base0 = (long long)blockIdx.x * batch; base0 < n; base0 += (long long)gridDim.x * batch) {
         const long long i = base0 + warp * lpw + lane;
-        const bool active = lane < lpw && i < n;
+        bool active = lane < lpw && i < n;
+        int pv = 0;
+        if constexpr (SPARSE) {      // pidx < 0 (point outside the octree): the row is inert -- no gather, no loss, no gradient
+            if (active) pv = __ldg(sp.pidx + i);
+            active = active && pv >= 0;
+        }
         float px = 0.f, py = 0.f, pz = 0.f;
         if (active) { px = __ldg(x + 3 * i); py = __ldg(x + 3 * i + 1); pz = __ldg(x + 3 * i + 2); }
         // ---- A: gather
         int vrow = 0;
         if constexpr (SPARSE) {
-            vrow = sp.sn.vox_off + (active ? __ldg(sp.pidx + i) : 0);
+            vrow = sp.sn.vox_off + (active ? pv : 0);
             const unsigned live = __ballot_sync(0xffffffffu, active);
             const int n_live = __popc(live);
             if (active) {

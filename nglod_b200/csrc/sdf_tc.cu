@@ -70,23 +70,28 @@ int launch_fwd(const NetDev& nd, const float* x, long long n, float* out, cudaSt
 // ------------------------------------------------------------------------------------------------------------------
 // Warp-specialised forward (single-grid gathers).  The kernel above runs gather -> barrier -> 15 UMMAs -> epilogue
 // serially inside each 4-warp group, so a warp has loads in flight only ~40 % of the time and the SM pulls ~35 B/clk
-// out of L2 where the probe (probe.cu) measures ~69 B/clk for the same address stream.  Here the three phases run on
+// out of L2 where the probe (probe.cu) measures ~69 B/clk for the same address stream.  Here the phases run on
 // different warps and overlap tile by tile:
-//   producers (NP warps): 32 queries each -> set-up, 8 corner lines per query (8 lanes x LDG.128), FFMA2 interpolation,
-//                         hi/lo split, A rows into stage s of a 4-stage ring          -> mbarrier full[s] (4 arrivals)
-//   MMA warp (1 thread) : waits full[s] and acc_free[s], issues the 15 tcgen05.mma of the tile into TMEM accumulator s,
-//                         tcgen05.commit -> mbarrier mma_done[s]  (frees the A stage AND publishes the accumulator)
+//   producers (16 warps): ALL of them work on the same 128-query tile: warp p owns rows 8p..8p+7 (two gather rounds of
+//                         4 queries x 8 lanes: set-up, 8 corner lines per query as 8 lanes x LDG.128, FFMA2
+//                         interpolation, hi/lo split, A rows into stage s of a 4-stage ring) -> mbarrier full[s] (16
+//                         arrivals).  A tile is filled in two load latencies, so a stage is re-used only four tile
+//                         times after its MMAs were issued and no producer ever waits for the tensor core.
+//   MMA issue           : lane 0 of the last producer warp, one tile behind its own gather (the tile's other 15 warps
+//                         have long arrived): waits full[s] and acc_free[s], issues the 15 tcgen05.mma of the tile into
+//                         TMEM accumulator s, tcgen05.commit -> mbarrier mma_done[s] (frees the A stage AND publishes
+//                         the accumulator)
 //   epilogue (4 warps)  : waits mma_done[s], tcgen05.ld its 32 rows, d = b1 + W1.relu(.), stores out -> acc_free[s]
-// Tiles are assigned statically: CTA-local tile T = global tile T*gridDim.x + blockIdx.x, stage/accumulator T % 4,
-// row block (T, q) by producer warp (4T + q) % NP -- every role derives the same mapping, nothing is communicated but
-// the barriers.  Same arithmetic as the kernel above (tc_gather_single / tc_issue_tile / tc_epilogue): results are
-// bit-identical.
-#ifndef NGLOD_WS_PRODUCERS
-#define NGLOD_WS_PRODUCERS 16
-#endif
+// Tiles are assigned statically: CTA-local tile T = global tile T*gridDim.x + blockIdx.x, stage/accumulator T % 4 --
+// every role derives the same mapping, nothing is communicated but the barriers.  Same arithmetic as the kernel above
+// (tc_setup_record / tc_issue_lines / tc_consume_lines / tc_issue_tile / tc_epilogue): results are bit-identical.
+#define WS_PRODUCERS 16
 #define WS_STAGES 4
-#define WS_WARPS (4 + 1 + NGLOD_WS_PRODUCERS)
+#define WS_WARPS (4 + WS_PRODUCERS)
 #define WS_THREADS (WS_WARPS * 32)
+#ifndef NGLOD_WS_DEPTH
+#define NGLOD_WS_DEPTH 1            // 2: both gather rounds of a tile in flight at once (64 data registers)
+#endif
 #define WS_SMEM_A(s) (2 * TC_OPERAND_BYTES + (s) * 2 * TC_OPERAND_BYTES)
 #define WS_SMEM_W1 TC_SMEM_W1(WS_STAGES)
 #define WS_SMEM_BAR (WS_SMEM_W1 + 528)                 // full[4], mma_done[4], acc_free[4]
@@ -122,7 +127,7 @@ sdf_forward_ws_kernel(const NetDev net, const float* __restrict__ x, const long 
         }
         if (threadIdx.x == 0) {
             for (int s = 0; s < WS_STAGES; ++s) {
-                mbar_init(smem_u32(smem_tc + WS_SMEM_BAR + 8 * s), 4);                       // full: 4 producer warps
+                mbar_init(smem_u32(smem_tc + WS_SMEM_BAR + 8 * s), WS_PRODUCERS);            // full: every producer warp
                 mbar_init(smem_u32(smem_tc + WS_SMEM_BAR + 8 * (WS_STAGES + s)), 1);         // mma_done: tcgen05.commit
                 mbar_init(smem_u32(smem_tc + WS_SMEM_BAR + 8 * (2 * WS_STAGES + s)), 4);     // acc_free: 4 epilogue warps
             }
@@ -143,54 +148,75 @@ sdf_forward_ws_kernel(const NetDev net, const float* __restrict__ x, const long 
     const long long total_tiles = (n + TC_TILE_ROWS - 1) / TC_TILE_ROWS;
     const int ntiles = (int)((total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
 
-    if (warp >= 5) {
-        // ------------------------------------------------------------------ producers
-        const int p = warp - 5;
-        int rb = p;                                                   // row block = 4 * T + q
-        auto rb_query = [&](int r) { return ((long long)(r >> 2) * gridDim.x + blockIdx.x) * TC_TILE_ROWS + (r & 3) * 32 + lane; };
-        float px = 0.f, py = 0.f, pz = 0.f;
-        long long i = rb_query(rb);
-        if (rb < 4 * ntiles && i < n) { px = __ldg(x + 3 * i); py = __ldg(x + 3 * i + 1); pz = __ldg(x + 3 * i + 2); }
-        for (; rb < 4 * ntiles; rb += NGLOD_WS_PRODUCERS) {
-            const int T = rb >> 2, q = rb & 3, s = T & (WS_STAGES - 1), k = T / WS_STAGES;
-            const bool active = i < n;
-            // next row block's coordinates (DRAM) while this one is gathered
-            const long long i_next = rb_query(rb + NGLOD_WS_PRODUCERS);
-            float nx = 0.f, ny = 0.f, nz = 0.f;
-            if (rb + NGLOD_WS_PRODUCERS < 4 * ntiles && i_next < n) {
-                nx = __ldg(x + 3 * i_next); ny = __ldg(x + 3 * i_next + 1); nz = __ldg(x + 3 * i_next + 2);
-            }
-            float4 rec = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (active) rec = tc_setup_record<HALF>(px, py, pz, net.res[0]);
-            const unsigned live = __ballot_sync(0xffffffffu, active);
+    if (warp >= 4) {
+        // ------------------------------------------------------------------ producers (+ MMA issue on the last one)
+        const int p = warp - 4, sub = lane >> 3, c = lane & 7;
+        const float* grid = net.grids[0];
+        const int R = net.res[0];
+        const uint32_t b_hi = smem_u32(smem_tc + TC_SMEM_B_HI), b_lo = smem_u32(smem_tc + TC_SMEM_B_LO);
+        auto issue_mma = [&](int T) {                     // one thread
+            const int s = T & (WS_STAGES - 1), k = T / WS_STAGES;
+            mbar_wait(full_bar(s), (uint32_t)(k & 1));
+            if (k > 0) mbar_wait(free_bar(s), (uint32_t)((k - 1) & 1));
+            tc_fence_after_sync();
+            const uint32_t a_hi = smem_u32(smem_tc + WS_SMEM_A(s));
+            tc_issue_tile(tmem_base + (uint32_t)(s * TC_N), a_hi, a_hi + TC_OPERAND_BYTES, b_hi, b_lo);
+            tc_commit(done_bar(s));
+        };
+        const int row0 = p * 8 + sub;                     // this lane's two rows of every tile: row0, row0 + 4
+        const long long tile_stride = (long long)gridDim.x * TC_TILE_ROWS;
+        long long i0 = (long long)blockIdx.x * TC_TILE_ROWS + row0;
+        float qx[2] = {0.f, 0.f}, qy[2] = {0.f, 0.f}, qz[2] = {0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const long long i = i0 + 4 * j;
+            if (ntiles > 0 && i < n) { qx[j] = __ldg(x + 3 * i); qy[j] = __ldg(x + 3 * i + 1); qz[j] = __ldg(x + 3 * i + 2); }
+        }
+        for (int T = 0; T < ntiles; ++T, i0 += tile_stride) {
+            const int s = T & (WS_STAGES - 1), k = T / WS_STAGES;
             char* a_hi = smem_tc + WS_SMEM_A(s);
             char* a_lo = a_hi + TC_OPERAND_BYTES;
-            // the stage is free once the MMAs of its previous tile have read it
+            float4 rec[2];
+            float px[2], py[2], pz[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                px[j] = qx[j]; py[j] = qy[j]; pz[j] = qz[j];
+                // rows past n carry record 0 (corner 0, weights 0): harmless loads, their accumulator rows are never read
+                rec[j] = (i0 + 4 * j < n) ? tc_setup_record<HALF>(px[j], py[j], pz[j], R) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            TcLines<HALF> t[NGLOD_WS_DEPTH];
+            tc_issue_lines<HALF>(grid, R, __float_as_uint(rec[0].x), c, t[0]);
+            if (NGLOD_WS_DEPTH == 2) tc_issue_lines<HALF>(grid, R, __float_as_uint(rec[1].x), c, t[NGLOD_WS_DEPTH - 1]);
+            // next tile's coordinates (DRAM) while this one is gathered
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const long long i = i0 + tile_stride + 4 * j;
+                qx[j] = qy[j] = qz[j] = 0.f;
+                if (T + 1 < ntiles && i < n) { qx[j] = __ldg(x + 3 * i); qy[j] = __ldg(x + 3 * i + 1); qz[j] = __ldg(x + 3 * i + 2); }
+            }
+            // the stage is free once the MMAs of its previous tile (four tiles ago) have read it
             if (k > 0) mbar_wait(done_bar(s), (uint32_t)((k - 1) & 1));
-            if (live) {
-                if (active) tc_store_split4(a_hi, a_lo, tc_elem_offset(q * 32 + lane, NGLOD_F), make_float4(px, py, pz, 1.f));
-                tc_gather_single<HALF>(net, rec, live, a_hi, a_lo, q * 32, lane);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                uint64_t acc01 = 0ull, acc23 = 0ull;
+                tc_consume_lines<HALF>(rec[j], t[NGLOD_WS_DEPTH == 2 ? j : 0], acc01, acc23);
+                if (NGLOD_WS_DEPTH == 1 && j == 0) tc_issue_lines<HALF>(grid, R, __float_as_uint(rec[1].x), c, t[0]);
+                float4 acc;
+                f2_unpack(acc01, acc.x, acc.y); f2_unpack(acc23, acc.z, acc.w);
+                const int row = row0 + 4 * j;
+                tc_store_split4(a_hi, a_lo, tc_elem_offset(row, 4 * c), acc);
+                if (c == 0) tc_store_split4(a_hi, a_lo, tc_elem_offset(row, NGLOD_F), make_float4(px[j], py[j], pz[j], 1.f));
             }
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(full_bar(s));
-            i = i_next; px = nx; py = ny; pz = nz;
-        }
-    } else if (warp == 4) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            const uint32_t b_hi = smem_u32(smem_tc + TC_SMEM_B_HI), b_lo = smem_u32(smem_tc + TC_SMEM_B_LO);
-            for (int T = 0; T < ntiles; ++T) {
-                const int s = T & (WS_STAGES - 1), k = T / WS_STAGES;
-                mbar_wait(full_bar(s), (uint32_t)(k & 1));
-                if (k > 0) mbar_wait(free_bar(s), (uint32_t)((k - 1) & 1));
-                tc_fence_after_sync();
-                const uint32_t a_hi = smem_u32(smem_tc + WS_SMEM_A(s));
-                tc_issue_tile(tmem_base + (uint32_t)(s * TC_N), a_hi, a_hi + TC_OPERAND_BYTES, b_hi, b_lo);
-                tc_commit(done_bar(s));
+            if (lane == 0) {
+                mbar_arrive(full_bar(s));
+                if (p == WS_PRODUCERS - 1 && T > 0) issue_mma(T - 1);
             }
+            __syncwarp();
         }
-        __syncwarp();               // reconverge before the CTA-wide barrier of the epilogue
+        if (p == WS_PRODUCERS - 1 && lane == 0 && ntiles > 0) issue_mma(ntiles - 1);
+        __syncwarp();
     } else {
         // ------------------------------------------------------------------ epilogue
         const float* w1 = reinterpret_cast<const float*>(smem_tc + WS_SMEM_W1);

@@ -120,11 +120,13 @@ sparse_sdf_forward_kernel(const SparseDev sn, const float* __restrict__ x, const
     const long long nunits = (long long)gridDim.x * (TC ? SP_TC_GROUPS : SDF_WARPS);
     for (long long base = unit * TILE; base < n; base += nunits * TILE) {
         const long long i = base + (TC ? ((threadIdx.x >> 5) & 3) * 32 : 0) + lane;
-        const bool active = i < n;
+        // pidx < 0 = "no voxel holds this point" (SPC.query): such rows read no table and evaluate to 0
+        const int pv = i < n ? __ldg(pidx + i) : -1;
+        const bool active = pv >= 0;
         float px = 0.f, py = 0.f, pz = 0.f; int v = sn.vox_off;
-        if (active) { px = __ldg(x + 3 * i); py = __ldg(x + 3 * i + 1); pz = __ldg(x + 3 * i + 2); v = sn.vox_off + __ldg(pidx + i); }
+        if (active) { px = __ldg(x + 3 * i); py = __ldg(x + 3 * i + 1); pz = __ldg(x + 3 * i + 2); v = sn.vox_off + pv; }
         const float d = eval_sparse<TC>(sn, smem_raw, e, px, py, pz, v, active);
-        if (active) out[i] = d;
+        if (i < n) out[i] = active ? d : 0.f;
     }
     if constexpr (TC) tc_epilogue_free(e.tmem_base);
 }
