@@ -38,22 +38,6 @@ struct TraceParams {
 #ifndef NGLOD_TRACE_GROUPS
 #define NGLOD_TRACE_GROUPS 3
 #endif
-// EXPERIMENT, off by default (the default build compiles none of it): hand rays that reach `hand_off_step` march steps
-// over to the last `express_ctas` CTAs of the grid, which take no fresh rays and therefore run short, sparse tile rounds
-// (profiles/NEXT.md item 1; profiles/README.md: a round costs 1.9 us for one ray, 5.7 us on a full SM, and the frame is
-// as long as the chain of rounds of its longest ray).  Which rays share a tile never changes a ray's result.
-#ifndef NGLOD_TRACE_EXPRESS
-#define NGLOD_TRACE_EXPRESS 0
-#endif
-#if NGLOD_TRACE_EXPRESS
-struct LateQueue {
-    int* counters;            // [0] entries reserved by producers, [1] entries claimed by consumers, [2] producer warps done
-    int* ray;                 // [cap] ray id of entry i, -1 until the entry is published (written last)
-    float4* state;            // [cap][2]: {x, y, z, t}, {d, dprev, step bits, flag}
-    int express_ctas, hand_off_step, total_main_warps;
-};
-__device__ __forceinline__ int ld_volatile_i32(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
-#endif
 #ifndef NGLOD_TRACE_GROUPS_SINGLE
 #define NGLOD_TRACE_GROUPS_SINGLE 4
 #endif
@@ -70,9 +54,6 @@ sphere_trace_kernel(const NetDev net, const float* __restrict__ ray_o, const flo
                     const long long n, const TraceParams tp, float* __restrict__ out_x,
                     float* __restrict__ out_t, uint8_t* __restrict__ out_hit, float* __restrict__ out_n,
                     int* __restrict__ queue, unsigned long long* __restrict__ stats
-#if NGLOD_TRACE_EXPRESS
-                    , const LateQueue lq
-#endif
                     ) {
     extern __shared__ __align__(128) char smem_raw[];
     float* smem = reinterpret_cast<float*>(smem_raw);
@@ -179,74 +160,7 @@ sphere_trace_kernel(const NetDev net, const float* __restrict__ ray_o, const flo
 #define TR_TICK(i) do { } while (0)
 #endif
     // refill empty slots from the global queue (ballot + popc ranks; rays that miss the box retire on the spot)
-#if NGLOD_TRACE_EXPRESS
-    const bool express = TC && lq.ray != nullptr && (int)blockIdx.x >= (int)gridDim.x - lq.express_ctas;
-    // express warps: claim published entries of the late list instead of fresh rays
-    auto refill_express = [&]() {
-#pragma unroll 1
-        for (int attempt = 0; attempt < 2 && !exhausted; ++attempt) {
-            const unsigned free_mask = __ballot_sync(0xffffffffu, phase == PH_EMPTY);
-            if (!free_mask) break;
-            const int nfree = __popc(free_mask);
-            int base = -1, take = 0;
-            if (lane == 0) {
-                const int h = ld_volatile_i32(lq.counters + 1), r = ld_volatile_i32(lq.counters);
-                take = min(nfree, r - h);
-                if (take > 0) {
-                    if (atomicCAS(lq.counters + 1, h, h + take) == h) base = h; else take = 0;     // lost the race: next round
-                } else {
-                    take = 0;
-                    if (ld_volatile_i32(lq.counters + 2) == lq.total_main_warps) {                 // producers are all gone,
-                        __threadfence();
-                        if (ld_volatile_i32(lq.counters + 1) >= ld_volatile_i32(lq.counters)) take = -1;   // and nothing is left
-                    }
-                }
-            }
-            base = __shfl_sync(0xffffffffu, base, 0);
-            take = __shfl_sync(0xffffffffu, take, 0);
-            if (take < 0) { exhausted = true; break; }
-            if (take == 0) break;
-            if (phase == PH_EMPTY) {
-                const int rank = __popc(free_mask & lt_mask);
-                if (rank < take) {
-                    const int e = base + rank;
-                    int rid;
-                    do { rid = ld_volatile_i32(lq.ray + e); } while (rid < 0);     // reserved entries are published within a few instructions
-                    __threadfence();
-                    const float4 s0 = __ldcg(lq.state + 2 * e), s1 = __ldcg(lq.state + 2 * e + 1);   // not through L1: a neighbour's
-                                                                                                      // earlier read may have cached the line
-                    ray = rid;
-                    ox = __ldg(ray_o + 3 * ray); oy = __ldg(ray_o + 3 * ray + 1); oz = __ldg(ray_o + 3 * ray + 2);
-                    dx = __ldg(ray_d + 3 * ray); dy = __ldg(ray_d + 3 * ray + 1); dz = __ldg(ray_d + 3 * ray + 2);
-                    x = s0.x; y = s0.y; z = s0.z; t = s0.w;
-                    d = s1.x; dprev = s1.y; step = __float_as_int(s1.z); flag = s1.w != 0.f;
-                    phase = PH_MARCH;
-                }
-            }
-        }
-    };
-    // main warps: a ray that has just completed its hand_off_step-th march step moves to the late list
-    auto hand_off = [&]() {
-        const bool push = phase == PH_MARCH && step == lq.hand_off_step;
-        const unsigned pm = __ballot_sync(0xffffffffu, push);
-        if (!pm) return;
-        int base = 0;
-        if (lane == 0) base = atomicAdd(lq.counters, __popc(pm));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (push) {
-            const int e = base + __popc(pm & lt_mask);
-            lq.state[2 * e] = make_float4(x, y, z, t);
-            lq.state[2 * e + 1] = make_float4(d, dprev, __int_as_float(step), flag ? 1.f : 0.f);
-            __threadfence();
-            *reinterpret_cast<volatile int*>(lq.ray + e) = (int)ray;
-            phase = PH_EMPTY;
-        }
-    };
-#endif
     auto refill = [&]() {
-#if NGLOD_TRACE_EXPRESS
-        if (express) { refill_express(); return; }
-#endif
 #pragma unroll 1
         for (int attempt = 0; attempt < 4 && !exhausted; ++attempt) {
             const unsigned free_mask = __ballot_sync(0xffffffffu, phase == PH_EMPTY);
@@ -297,15 +211,9 @@ sphere_trace_kernel(const NetDev net, const float* __restrict__ ray_o, const flo
             float dv = 0.f;
             if (!tc_group_eval_any<MODE>(net, grp, qx, qy, qz, occupied, occupied || !exhausted, dv)) break;
             advance(dv);
-#if NGLOD_TRACE_EXPRESS
-            if (lq.ray != nullptr && !express) hand_off();
-#endif
         }
         TR_TICK(5);
     }
-#if NGLOD_TRACE_EXPRESS
-    if (TC && lq.ray != nullptr && !express && lane == 0) { __threadfence(); atomicAdd(lq.counters + 2, 1); }
-#endif
     if (stats && lane == 0) {
         atomicAdd(stats, n_eval);
         atomicAdd(stats + 1, n_march);
@@ -348,34 +256,8 @@ extern "C" int nglod_sphere_trace(const nglod_net_t* net, int32_t lod, const flo
         long long grid = nglod_sm_count();
         const long long want = (n + threads - 1) / threads;
         if (want < grid) grid = want;
-#if NGLOD_TRACE_EXPRESS
-        LateQueue lq = {};
-        char* ws = nullptr;
-        {
-            const char* e1 = getenv("NGLOD_TRACE_EXPRESS_CTAS");
-            const char* e2 = getenv("NGLOD_TRACE_HANDOFF");
-            const int ectas = e1 ? atoi(e1) : 16, hstep = e2 ? atoi(e2) : 32;
-            if (ectas > 0 && hstep > 0 && hstep < opts->num_steps && grid > 4ll * ectas) {
-                const size_t cnt_bytes = 256, ray_bytes = ((size_t)n * 4 + 255) & ~(size_t)255, st_bytes = (size_t)n * 32;
-                NGLOD_CUDA_TRY(cudaMallocAsync(&ws, cnt_bytes + ray_bytes + st_bytes, st));
-                NGLOD_CUDA_TRY(cudaMemsetAsync(ws, 0, cnt_bytes, st));
-                NGLOD_CUDA_TRY(cudaMemsetAsync(ws + cnt_bytes, 0xff, ray_bytes, st));
-                lq.counters = reinterpret_cast<int*>(ws);
-                lq.ray = reinterpret_cast<int*>(ws + cnt_bytes);
-                lq.state = reinterpret_cast<float4*>(ws + cnt_bytes + ray_bytes);
-                lq.express_ctas = ectas;
-                lq.hand_off_step = hstep;
-                lq.total_main_warps = (int)(grid - ectas) * (threads / 32);
-            }
-        }
-        kern<<<(int)grid, threads, smem, st>>>(nd, ray_o, ray_d, (long long)n, tp, x, depth, hit, normal, queue, stats, lq);
-        int lerr = (int)cudaGetLastError();
-        if (ws) { const int ferr = (int)cudaFreeAsync(ws, st); if (!lerr) lerr = ferr; }
-        return lerr;
-#else
         kern<<<(int)grid, threads, smem, st>>>(nd, ray_o, ray_d, (long long)n, tp, x, depth, hit, normal, queue, stats);
         return (int)cudaGetLastError();
-#endif
     }
     auto kern = sphere_trace_kernel<false, TC_MULTI>;
     NGLOD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SDF_SMEM_BYTES));
@@ -387,9 +269,6 @@ extern "C" int nglod_sphere_trace(const nglod_net_t* net, int32_t lod, const flo
     if (want < grid) grid = want;
     kern<<<(int)grid, SDF_THREADS, SDF_SMEM_BYTES, st>>>(nd, ray_o, ray_d, (long long)n, tp, x, depth, hit, normal,
                                                          queue, stats
-#if NGLOD_TRACE_EXPRESS
-                                                         , LateQueue{}
-#endif
                                                          );
     return (int)cudaGetLastError();
 }
