@@ -77,11 +77,13 @@ int launch_fwd(const NetDev& nd, const float* x, long long n, float* out, cudaSt
 //                         interpolation, hi/lo split, A rows into stage s of a 4-stage ring) -> mbarrier full[s] (16
 //                         arrivals).  A tile is filled in two load latencies, so a stage is re-used only four tile
 //                         times after its MMAs were issued and no producer ever waits for the tensor core.
-//   MMA issue           : lane 0 of the last producer warp, one tile behind its own gather (the tile's other 15 warps
-//                         have long arrived): waits full[s] and acc_free[s], issues the 15 tcgen05.mma of the tile into
-//                         TMEM accumulator s, tcgen05.commit -> mbarrier mma_done[s] (frees the A stage AND publishes
-//                         the accumulator)
-//   epilogue (4 warps)  : waits mma_done[s], tcgen05.ld its 32 rows, d = b1 + W1.relu(.), stores out -> acc_free[s]
+//   MMA issue           : whichever producer warp arrives LAST at the tile (a monotonic shared counter, 16 arrivals per
+//                         tile): its lane 0 waits acc_free[s], issues the 15 tcgen05.mma of the tile into TMEM
+//                         accumulator s and tcgen05.commit -> mbarrier mma_done[s] (frees the A stage AND publishes the
+//                         accumulator).  No warp is parked on a barrier for it and the MMAs start the moment the tile is full.
+//   epilogue (4 warps)  : the four HIGHEST warp ids (the issue arbiter prefers high warp ids: the short, latency-critical
+//                         role must not starve behind 16 producers): waits mma_done[s], tcgen05.ld its 32 rows,
+//                         d = b1 + W1.relu(.), stores out -> acc_free[s]
 // Tiles are assigned statically: CTA-local tile T = global tile T*gridDim.x + blockIdx.x, stage/accumulator T % 4 --
 // every role derives the same mapping, nothing is communicated but the barriers.  Same arithmetic as the kernel above
 // (tc_setup_record / tc_issue_lines / tc_consume_lines / tc_issue_tile / tc_epilogue): results are bit-identical.
@@ -94,7 +96,7 @@ int launch_fwd(const NetDev& nd, const float* x, long long n, float* out, cudaSt
 #endif
 #define WS_SMEM_A(s) (2 * TC_OPERAND_BYTES + (s) * 2 * TC_OPERAND_BYTES)
 #define WS_SMEM_W1 TC_SMEM_W1(WS_STAGES)
-#define WS_SMEM_BAR (WS_SMEM_W1 + 528)                 // full[4], mma_done[4], acc_free[4]
+#define WS_SMEM_BAR (WS_SMEM_W1 + 528)                 // arrival counters[4] (u32, padded to 8 B), mma_done[4], acc_free[4]
 #define WS_SMEM_TMEMPTR (WS_SMEM_BAR + 3 * WS_STAGES * 8)
 #define WS_SMEM_BYTES (WS_SMEM_TMEMPTR + 16)
 static_assert(WS_SMEM_BYTES <= 232448, "shared memory budget");
@@ -127,7 +129,7 @@ sdf_forward_ws_kernel(const NetDev net, const float* __restrict__ x, const long 
         }
         if (threadIdx.x == 0) {
             for (int s = 0; s < WS_STAGES; ++s) {
-                mbar_init(smem_u32(smem_tc + WS_SMEM_BAR + 8 * s), WS_PRODUCERS);            // full: every producer warp
+                *reinterpret_cast<volatile unsigned long long*>(smem_tc + WS_SMEM_BAR + 8 * s) = 0ull;    // arrival counter
                 mbar_init(smem_u32(smem_tc + WS_SMEM_BAR + 8 * (WS_STAGES + s)), 1);         // mma_done: tcgen05.commit
                 mbar_init(smem_u32(smem_tc + WS_SMEM_BAR + 8 * (2 * WS_STAGES + s)), 4);     // acc_free: 4 epilogue warps
             }
@@ -141,22 +143,28 @@ sdf_forward_ws_kernel(const NetDev net, const float* __restrict__ x, const long 
     }
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_tc + WS_SMEM_TMEMPTR);
     const uint32_t bar0 = smem_u32(smem_tc + WS_SMEM_BAR);
-    auto full_bar = [&](int s) { return bar0 + 8u * (uint32_t)s; };
+    auto arrive_cnt = [&](int s) { return reinterpret_cast<unsigned*>(smem_tc + WS_SMEM_BAR + 8 * s); };
     auto done_bar = [&](int s) { return bar0 + 8u * (uint32_t)(WS_STAGES + s); };
     auto free_bar = [&](int s) { return bar0 + 8u * (uint32_t)(2 * WS_STAGES + s); };
     // CTA-local tiles: global tile gt = T * gridDim.x + blockIdx.x while gt * 128 < n
     const long long total_tiles = (n + TC_TILE_ROWS - 1) / TC_TILE_ROWS;
     const int ntiles = (int)((total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
 
-    if (warp >= 4) {
-        // ------------------------------------------------------------------ producers (+ MMA issue on the last one)
-        const int p = warp - 4, sub = lane >> 3, c = lane & 7;
+#ifdef NGLOD_WS_EPI_LOW          // experiment: epilogue on the four LOWEST warp ids
+    const bool producer = warp >= 4;
+    const int p = warp - 4, ew = warp;
+#else
+    const bool producer = warp < WS_PRODUCERS;
+    const int p = warp, ew = warp - WS_PRODUCERS;
+#endif
+    if (producer) {
+        // ------------------------------------------------------------------ producers (the last to arrive issues the MMAs)
+        const int sub = lane >> 3, c = lane & 7;
         const float* grid = net.grids[0];
         const int R = net.res[0];
         const uint32_t b_hi = smem_u32(smem_tc + TC_SMEM_B_HI), b_lo = smem_u32(smem_tc + TC_SMEM_B_LO);
-        auto issue_mma = [&](int T) {                     // one thread
+        auto issue_mma = [&](int T) {                     // one thread, after the tile's last arrival
             const int s = T & (WS_STAGES - 1), k = T / WS_STAGES;
-            mbar_wait(full_bar(s), (uint32_t)(k & 1));
             if (k > 0) mbar_wait(free_bar(s), (uint32_t)((k - 1) & 1));
             tc_fence_after_sync();
             const uint32_t a_hi = smem_u32(smem_tc + WS_SMEM_A(s));
@@ -210,13 +218,15 @@ sdf_forward_ws_kernel(const NetDev net, const float* __restrict__ x, const long 
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-                mbar_arrive(full_bar(s));
-                if (p == WS_PRODUCERS - 1 && T > 0) issue_mma(T - 1);
+                __threadfence_block();                                           // release: this warp's A rows
+                const unsigned old = atomicAdd(arrive_cnt(s), 1u);               // monotonic: 16 arrivals per use of the stage
+                if ((old & (WS_PRODUCERS - 1)) == WS_PRODUCERS - 1) {
+                    __threadfence_block();                                       // acquire: everybody's A rows
+                    issue_mma(T);
+                }
             }
             __syncwarp();
         }
-        if (p == WS_PRODUCERS - 1 && lane == 0 && ntiles > 0) issue_mma(ntiles - 1);
-        __syncwarp();
     } else {
         // ------------------------------------------------------------------ epilogue
         const float* w1 = reinterpret_cast<const float*>(smem_tc + WS_SMEM_W1);
@@ -224,11 +234,11 @@ sdf_forward_ws_kernel(const NetDev net, const float* __restrict__ x, const long 
             const int s = T & (WS_STAGES - 1), k = T / WS_STAGES;
             mbar_wait(done_bar(s), (uint32_t)(k & 1));
             tc_fence_after_sync();
-            const float d = tc_epilogue(tmem_base + (uint32_t)(s * TC_N) + ((uint32_t)(warp * 32) << 16), w1);
+            const float d = tc_epilogue(tmem_base + (uint32_t)(s * TC_N) + ((uint32_t)(ew * 32) << 16), w1);
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(free_bar(s));
-            const long long i = ((long long)T * gridDim.x + blockIdx.x) * TC_TILE_ROWS + warp * 32 + lane;
+            const long long i = ((long long)T * gridDim.x + blockIdx.x) * TC_TILE_ROWS + ew * 32 + lane;
             if (i < n) out[i] = d;
         }
     }
