@@ -113,10 +113,13 @@ int nglod_debug_tc_gemm(const float* A, const float* B, float* D, void* stream);
  * cells of a channels-last fp32 [(R+1)^3, 32] grid at `buf` (128-byte aligned), the 8 corner lines of the cell with
  * 8 lanes x 16 B per line -- the address stream of the SDF kernels' gather, no arithmetic (structured = 1) -- or
  * 8 * n_queries independent random 128-byte lines of the same buffer (structured = 0).  in_flight = 1..3: 8, 16 or 24
- * line loads in flight per lane.  Bytes moved L2 -> SM: n_queries * 1024.  sink: device uint32[1], never written in
- * practice.  No reference counterpart (the reference has no measurement hooks). */
+ * line loads in flight per lane.  Launch shape: 512-thread CTAs, as many per SM as fit next to smem_bytes of unused
+ * dynamic shared memory each (the carve-out a real kernel would take from L1), at most ctas_per_sm (0 = no cap).
+ * Bytes moved L2 -> SM: n_queries * 1024.  sink: device uint32[1], never written in practice.  No reference
+ * counterpart (the reference has no measurement hooks). */
 int nglod_probe_gather(const void* buf, int32_t grid_res, int64_t n_queries, int32_t in_flight,
-                       int32_t structured, uint32_t seed, uint32_t* sink, void* stream);
+                       int32_t structured, int32_t smem_bytes, int32_t ctas_per_sm, uint32_t seed,
+                       uint32_t* sink, void* stream);
 
 /* ---- ray vs unit cube ---------------------------------------------------
  * Replaces: f_aabb / aabb_kernel, sdf-net/lib/extensions/sol_nglod/

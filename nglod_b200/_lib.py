@@ -96,7 +96,8 @@ SIGNATURES = {
     "nglod_abi_version": (ctypes.c_int, []),
     "nglod_build_info": (ctypes.c_char_p, []),
     "nglod_debug_tc_gemm": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
-    "nglod_probe_gather": (ctypes.c_int, [c_void_p, c_int32, c_int64, c_int32, c_int32, ctypes.c_uint32, c_void_p, c_void_p]),
+    "nglod_probe_gather": (ctypes.c_int, [c_void_p, c_int32, c_int64, c_int32, c_int32, c_int32, c_int32, ctypes.c_uint32,
+                                          c_void_p, c_void_p]),
     "nglod_aabb": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "nglod_sdf_forward": (ctypes.c_int, [ctypes.POINTER(NetStruct), c_int32, c_void_p, c_int64, c_void_p, c_void_p]),
     "nglod_sdf_forward_all": (ctypes.c_int, [ctypes.POINTER(NetStruct), c_void_p, c_int64, c_void_p, c_void_p]),

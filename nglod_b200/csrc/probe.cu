@@ -72,19 +72,30 @@ probe_lines_kernel(const uint4* __restrict__ buf, const long long n_lines_buf, c
     if (acc == 0x9e3779b9u) sink[0] = acc;
 }
 
+// Launch shape: as many 512-thread CTAs per SM as fit next to `smem` bytes of (unused) dynamic shared memory each -- the
+// carve-out decides how much of the 228 KB is left to L1, which is where the in-flight lines of a gather live.
 template <typename K>
-int probe_grid(K kern, int ctas_per_sm_cap) {
+int probe_grid(K kern, int smem, int ctas_per_sm_cap) {
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 512, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 512, smem) != cudaSuccess || per_sm < 1) return -1;
     if (ctas_per_sm_cap > 0 && per_sm > ctas_per_sm_cap) per_sm = ctas_per_sm_cap;
     return nglod_sm_count() * per_sm;
 }
+#define PROBE_LAUNCH(KERN, ...)                                                      \
+    do {                                                                             \
+        const int g_ = probe_grid(KERN, smem_bytes, ctas_per_sm);                    \
+        if (g_ < 1) return NGLOD_EINVAL;                                             \
+        KERN<<<g_, 512, smem_bytes, st>>>(__VA_ARGS__);                              \
+    } while (0)
 
 }  // namespace
 
 extern "C" int nglod_probe_gather(const void* buf, int32_t grid_res, int64_t n_queries, int32_t in_flight,
-                                  int32_t structured, uint32_t seed, uint32_t* sink, void* stream) {
+                                  int32_t structured, int32_t smem_bytes, int32_t ctas_per_sm, uint32_t seed,
+                                  uint32_t* sink, void* stream) {
     if (!buf || !sink || grid_res < 1 || grid_res > 256 || n_queries < 0) return NGLOD_EINVAL;
+    if (smem_bytes < 0 || smem_bytes > 232448 || ctas_per_sm < 0) return NGLOD_EINVAL;
     if ((reinterpret_cast<uintptr_t>(buf) & 127u) != 0) return NGLOD_EINVAL;
     if (n_queries == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
@@ -92,17 +103,17 @@ extern "C" int nglod_probe_gather(const void* buf, int32_t grid_res, int64_t n_q
     const long long S = grid_res + 1;
     if (structured) {
         switch (in_flight) {
-            case 1: probe_gather_kernel<1><<<probe_grid(probe_gather_kernel<1>, 0), 512, 0, st>>>(g, grid_res, n_queries, seed, sink); break;
-            case 2: probe_gather_kernel<2><<<probe_grid(probe_gather_kernel<2>, 0), 512, 0, st>>>(g, grid_res, n_queries, seed, sink); break;
-            case 3: probe_gather_kernel<3><<<probe_grid(probe_gather_kernel<3>, 0), 512, 0, st>>>(g, grid_res, n_queries, seed, sink); break;
+            case 1: PROBE_LAUNCH(probe_gather_kernel<1>, g, grid_res, n_queries, seed, sink); break;
+            case 2: PROBE_LAUNCH(probe_gather_kernel<2>, g, grid_res, n_queries, seed, sink); break;
+            case 3: PROBE_LAUNCH(probe_gather_kernel<3>, g, grid_res, n_queries, seed, sink); break;
             default: return NGLOD_EINVAL;
         }
     } else {
         const long long lines = S * S * S, reads = (long long)n_queries * 8;
         switch (in_flight) {
-            case 1: probe_lines_kernel<8><<<probe_grid(probe_lines_kernel<8>, 0), 512, 0, st>>>(g, lines, reads, seed, sink); break;
-            case 2: probe_lines_kernel<16><<<probe_grid(probe_lines_kernel<16>, 0), 512, 0, st>>>(g, lines, reads, seed, sink); break;
-            case 3: probe_lines_kernel<24><<<probe_grid(probe_lines_kernel<24>, 0), 512, 0, st>>>(g, lines, reads, seed, sink); break;
+            case 1: PROBE_LAUNCH(probe_lines_kernel<8>, g, lines, reads, seed, sink); break;
+            case 2: PROBE_LAUNCH(probe_lines_kernel<16>, g, lines, reads, seed, sink); break;
+            case 3: PROBE_LAUNCH(probe_lines_kernel<24>, g, lines, reads, seed, sink); break;
             default: return NGLOD_EINVAL;
         }
     }

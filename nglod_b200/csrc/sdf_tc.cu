@@ -160,30 +160,46 @@ sdf_forward_ws_kernel(const NetDev net, const float* __restrict__ x, const long 
         const int row0 = warp * 8 + sub;                  // this lane's two rows of every tile: row0, row0 + 4
         const uint32_t rec_off0 = tc_elem_offset(row0, WS_REC_COL), rec_off1 = tc_elem_offset(row0 + 4, WS_REC_COL);
         const uint32_t st_off0 = tc_elem_offset(row0, 4 * c), st_off1 = tc_elem_offset(row0 + 4, 4 * c);
+        // software-pipelined across tiles: the 16 line loads of tile T+1 are issued while tile T is interpolated and
+        // stored, so the L2 latency hides behind ~200 instructions of arithmetic instead of being waited for
+        float4 rec0 = make_float4(0.f, 0.f, 0.f, 0.f), rec1 = rec0;
+        TcLines<HALF> t0, t1;
+        if (ntiles > 0) {
+            mbar_wait(rec_bar(0), 0u);
+            rec0 = *reinterpret_cast<const float4*>(smem_tc + WS_SMEM_A(0) + rec_off0);
+            rec1 = *reinterpret_cast<const float4*>(smem_tc + WS_SMEM_A(0) + rec_off1);
+            tc_issue_lines<HALF>(grid, R, __float_as_uint(rec0.x), c, t0);
+            tc_issue_lines<HALF>(grid, R, __float_as_uint(rec1.x), c, t1);
+        }
         for (int T = 0; T < ntiles; ++T) {
-            const int s = T & (WS_STAGES - 1), k = T / WS_STAGES;
+            const int s = T & (WS_STAGES - 1);
             char* a_hi = smem_tc + WS_SMEM_A(s);
             char* a_lo = a_hi + TC_OPERAND_BYTES;
-            mbar_wait(rec_bar(s), (uint32_t)(k & 1));     // records of this tile are in place (and the stage is free)
-            const float4 rec0 = *reinterpret_cast<const float4*>(a_hi + rec_off0);
-            const float4 rec1 = *reinterpret_cast<const float4*>(a_hi + rec_off1);
-            TcLines<HALF> t;
-            tc_issue_lines<HALF>(grid, R, __float_as_uint(rec0.x), c, t);
+            const bool more = T + 1 < ntiles;
+            float4 nrec0 = make_float4(0.f, 0.f, 0.f, 0.f), nrec1 = nrec0;
+            if (more) {                                   // records of the next tile (set up three tiles ahead of the epilogue)
+                const int s1 = (T + 1) & (WS_STAGES - 1), k1 = (T + 1) / WS_STAGES;
+                mbar_wait(rec_bar(s1), (uint32_t)(k1 & 1));
+                nrec0 = *reinterpret_cast<const float4*>(smem_tc + WS_SMEM_A(s1) + rec_off0);
+                nrec1 = *reinterpret_cast<const float4*>(smem_tc + WS_SMEM_A(s1) + rec_off1);
+            }
             {
                 uint64_t acc01 = 0ull, acc23 = 0ull;
-                tc_consume_lines<HALF>(rec0, t, acc01, acc23);
-                tc_issue_lines<HALF>(grid, R, __float_as_uint(rec1.x), c, t);
+                tc_consume_lines<HALF>(rec0, t0, acc01, acc23);
+                if (more) tc_issue_lines<HALF>(grid, R, __float_as_uint(nrec0.x), c, t0);
                 float4 acc;
                 f2_unpack(acc01, acc.x, acc.y); f2_unpack(acc23, acc.z, acc.w);
                 tc_store_split4(a_hi, a_lo, st_off0, acc);
             }
             {
                 uint64_t acc01 = 0ull, acc23 = 0ull;
-                tc_consume_lines<HALF>(rec1, t, acc01, acc23);
+                tc_consume_lines<HALF>(rec1, t1, acc01, acc23);
+                if (more) tc_issue_lines<HALF>(grid, R, __float_as_uint(nrec1.x), c, t1);
                 float4 acc;
                 f2_unpack(acc01, acc.x, acc.y); f2_unpack(acc23, acc.z, acc.w);
                 tc_store_split4(a_hi, a_lo, st_off1, acc);
             }
+            rec0 = nrec0; rec1 = nrec1;
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
