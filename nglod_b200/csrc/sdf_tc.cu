@@ -72,32 +72,37 @@ int launch_fwd(const NetDev& nd, const float* x, long long n, float* out, cudaSt
 // epilogue serially inside each 4-warp group, so a warp has loads in flight only ~40 % of the time and the SM pulls
 // ~35 B/clk out of L2 where the probe (probe.cu) measures ~69 B/clk for the same address stream.  Here the phases run
 // on different warps and overlap tile by tile over a 4-stage ring of A operands / TMEM accumulators:
-//   service (4 warps, the HIGHEST warp ids: the issue arbiter prefers them, and their work is short and latency-critical)
-//       set-up of tile T+3: one query per lane (coalesced coordinate loads, prefetched three tiles further ahead) -> the 16-byte
-//       gather record {corner offset | flags, wx, wy, wz} and the {x, y, z, 1} K-chunk, written straight into the
-//       tile's A rows: the record lives in the K-padding chunk (columns 36..39), which the MMA multiplies by the zero
-//       padding of W0 -- finite x 0, contributes nothing -- so it costs no shared memory     -> mbarrier rec_full[s]
-//       epilogue of tile T: waits mma_done[s], tcgen05.ld its 32 rows, d = b1 + W1.relu(.), stores out
+//   set-up (4 warps)  : one query per lane (coalesced coordinate loads, prefetched tiles ahead) -> the 16-byte gather
+//       record {corner offset | flags, wx, wy, wz} and the {x, y, z, 1} K-chunk, written straight into the tile's A rows:
+//       the record lives in the K-padding chunk (columns 36..39), which the MMA multiplies by the zero padding of W0 --
+//       finite x 0, contributes nothing -- so it costs no shared memory.  Runs as far ahead as the ring allows (waits
+//       mma_done of the stage's previous tile)                                               -> mbarrier rec_full[s]
+//   epilogue (4 warps, the HIGHEST warp ids: the issue arbiter prefers them and their work is latency-critical):
+//       waits mma_done[s], tcgen05.ld its 32 rows, d = b1 + W1.relu(.), stores out          -> mbarrier acc_free[s]
 //   producers (16 warps): ALL of them work on the same tile: warp p owns rows 8p..8p+7 = two gather rounds of 4 queries
 //       x 8 lanes: record by one LDS.128, 8 corner lines per query as 8 lanes x LDG.128, FFMA2 interpolation, hi/lo split,
 //       A rows.  A tile is filled in two load latencies, so a stage is re-used only four tile times after its MMAs.
 //   MMA issue: whichever producer warp arrives LAST at the tile (monotonic shared counter, 16 arrivals per tile): its
-//       lane 0 issues the 15 tcgen05.mma of the tile into TMEM accumulator s and tcgen05.commit -> mbarrier mma_done[s].
-//       No warp is parked on a barrier for it and the MMAs start the moment the tile is full.
-// Ordering that needs no barrier of its own: the set-up of tile T+4 (same stage, same accumulator as T) is done by the
-// service warps after their own epilogue of tile T, and the producers fill T+4 only after that set-up.
+//       lane 0 (after acc_free[s] of the accumulator's previous tile) issues the 15 tcgen05.mma of the tile into TMEM
+//       accumulator s and tcgen05.commit -> mbarrier mma_done[s].  No warp is parked on a barrier for it and the MMAs
+//       start the moment the tile is full.
+// Registers follow the roles (setmaxnreg): the kernel launches at 80 per thread (24 warps), the set-up warpgroup drops to
+// 40, the epilogue warpgroup to 64, the four producer warpgroups grow to 96 (64 of them hold line loads in flight).
 // Tiles are assigned statically (CTA-local tile T = global tile T*gridDim.x + blockIdx.x): every role derives the same
 // mapping, nothing is communicated but the barriers.  Same arithmetic as the kernel above (tc_setup_record /
 // tc_issue_lines / tc_consume_lines / tc_issue_tile / tc_epilogue): results are bit-identical.
 #define WS_PRODUCERS 16
 #define WS_STAGES 4
-#define WS_WARPS (WS_PRODUCERS + 4)
+#define WS_WARPS (WS_PRODUCERS + 8)
+#define WS_REGS_PRODUCER 96
+#define WS_REGS_SETUP 40
+#define WS_REGS_EPILOGUE 64
 #define WS_THREADS (WS_WARPS * 32)
 #define WS_REC_COL (NGLOD_F + 4)                      // K columns 36..39: zero in W0|b0 -> free 16 bytes per A row
 #define WS_SMEM_A(s) (2 * TC_OPERAND_BYTES + (s) * 2 * TC_OPERAND_BYTES)
 #define WS_SMEM_W1 TC_SMEM_W1(WS_STAGES)
-#define WS_SMEM_BAR (WS_SMEM_W1 + 528)                 // arrival counters[4] (u32, padded to 8 B), mma_done[4], rec_full[4]
-#define WS_SMEM_TMEMPTR (WS_SMEM_BAR + 3 * WS_STAGES * 8)
+#define WS_SMEM_BAR (WS_SMEM_W1 + 528)                 // arrival counters[4] (u32, padded to 8 B), mma_done[4], rec_full[4], acc_free[4]
+#define WS_SMEM_TMEMPTR (WS_SMEM_BAR + 4 * WS_STAGES * 8)
 #define WS_SMEM_BYTES (WS_SMEM_TMEMPTR + 16)
 static_assert(WS_SMEM_BYTES <= 232448, "shared memory budget");
 
@@ -131,7 +136,8 @@ sdf_forward_ws_kernel(const NetDev net, const float* __restrict__ x, const long 
             for (int s = 0; s < WS_STAGES; ++s) {
                 *reinterpret_cast<volatile unsigned long long*>(smem_tc + WS_SMEM_BAR + 8 * s) = 0ull;    // arrival counter
                 mbar_init(smem_u32(smem_tc + WS_SMEM_BAR + 8 * (WS_STAGES + s)), 1);         // mma_done: tcgen05.commit
-                mbar_init(smem_u32(smem_tc + WS_SMEM_BAR + 8 * (2 * WS_STAGES + s)), 4);     // rec_full: 4 service warps
+                mbar_init(smem_u32(smem_tc + WS_SMEM_BAR + 8 * (2 * WS_STAGES + s)), 4);     // rec_full: 4 set-up warps
+                mbar_init(smem_u32(smem_tc + WS_SMEM_BAR + 8 * (3 * WS_STAGES + s)), 4);     // acc_free: 4 epilogue warps
             }
             mbar_fence_init();
         }
@@ -146,6 +152,7 @@ sdf_forward_ws_kernel(const NetDev net, const float* __restrict__ x, const long 
     auto arrive_cnt = [&](int s) { return reinterpret_cast<unsigned*>(smem_tc + WS_SMEM_BAR + 8 * s); };
     auto done_bar = [&](int s) { return bar0 + 8u * (uint32_t)(WS_STAGES + s); };
     auto rec_bar = [&](int s) { return bar0 + 8u * (uint32_t)(2 * WS_STAGES + s); };
+    auto free_bar = [&](int s) { return bar0 + 8u * (uint32_t)(3 * WS_STAGES + s); };
     // CTA-local tiles: global tile gt = T * gridDim.x + blockIdx.x while gt * 128 < n
     const long long total_tiles = (n + TC_TILE_ROWS - 1) / TC_TILE_ROWS;
     const int ntiles = (int)((total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
@@ -153,6 +160,7 @@ sdf_forward_ws_kernel(const NetDev net, const float* __restrict__ x, const long 
 
     if (warp < WS_PRODUCERS) {
         // ------------------------------------------------------------------ producers (the last to arrive issues the MMAs)
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(WS_REGS_PRODUCER));
         const int sub = lane >> 3, c = lane & 7;
         const float* grid = net.grids[0];
         const int R = net.res[0];
@@ -207,6 +215,8 @@ sdf_forward_ws_kernel(const NetDev net, const float* __restrict__ x, const long 
                 const unsigned old = atomicAdd(arrive_cnt(s), 1u);               // monotonic: 16 arrivals per use of the stage
                 if ((old & (WS_PRODUCERS - 1)) == WS_PRODUCERS - 1) {
                     __threadfence_block();                                       // acquire: everybody's A rows
+                    const int k = T / WS_STAGES;
+                    if (k > 0) mbar_wait(free_bar(s), (uint32_t)((k - 1) & 1)); // the accumulator's previous tile has been read
                     tc_fence_after_sync();
                     const uint32_t a_hi_s = smem_u32(a_hi);
                     tc_issue_tile(tmem_base + (uint32_t)(s * TC_N), a_hi_s, a_hi_s + TC_OPERAND_BYTES, b_hi, b_lo);
@@ -215,11 +225,10 @@ sdf_forward_ws_kernel(const NetDev net, const float* __restrict__ x, const long 
             }
             __syncwarp();
         }
-    } else {
-        // ------------------------------------------------------------------ service: set-up two tiles ahead + epilogue
-        const int ew = warp - WS_PRODUCERS;               // TMEM lane quarter = rows 32 ew .. 32 ew + 31
-        const int row = ew * 32 + lane;
-        const float* w1 = reinterpret_cast<const float*>(smem_tc + WS_SMEM_W1);
+    } else if (warp < WS_PRODUCERS + 4) {
+        // ------------------------------------------------------------------ set-up: records + {x, y, z, 1} of the tiles ahead
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(WS_REGS_SETUP));
+        const int row = (warp - WS_PRODUCERS) * 32 + lane;
         const int R = net.res[0];
         const uint32_t rec_off = tc_elem_offset(row, WS_REC_COL), xyz_off = tc_elem_offset(row, NGLOD_F);
         const long long i_first = (long long)blockIdx.x * TC_TILE_ROWS + row;
@@ -228,41 +237,40 @@ sdf_forward_ws_kernel(const NetDev net, const float* __restrict__ x, const long 
             px = py = pz = 0.f;
             if (T < ntiles && i < n) { px = __ldg(x + 3 * i); py = __ldg(x + 3 * i + 1); pz = __ldg(x + 3 * i + 2); }
         };
-        auto setup = [&](int T, float px, float py, float pz) {
-            const int s = T & (WS_STAGES - 1);
+        float ax, ay, az, bx, by, bz, cx, cy, cz;         // coordinates of the next three tiles (DRAM latency)
+        load_xyz(0, ax, ay, az);
+        load_xyz(1, bx, by, bz);
+        load_xyz(2, cx, cy, cz);
+        for (int T = 0; T < ntiles; ++T) {
+            const int s = T & (WS_STAGES - 1), k = T / WS_STAGES;
             char* a_hi = smem_tc + WS_SMEM_A(s);
             char* a_lo = a_hi + TC_OPERAND_BYTES;
             const long long i = i_first + (long long)T * tile_stride;
             // rows past n carry record 0 (corner 0, weights 0): harmless loads, their accumulator rows are never read
-            const float4 rec = i < n ? tc_setup_record<HALF>(px, py, pz, R) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 rec = i < n ? tc_setup_record<HALF>(ax, ay, az, R) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k > 0) mbar_wait(done_bar(s), (uint32_t)((k - 1) & 1));      // the stage's previous tile has been multiplied
             *reinterpret_cast<float4*>(a_hi + rec_off) = rec;
-            tc_store_split4(a_hi, a_lo, xyz_off, make_float4(px, py, pz, 1.f));
+            tc_store_split4(a_hi, a_lo, xyz_off, make_float4(ax, ay, az, 1.f));
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(rec_bar(s));
-        };
-        // set-up runs three tiles ahead of the epilogue: at iteration T the stage of tile T+3 was last used by tile T-1,
-        // whose MMAs (operand reads) and epilogue (accumulator reads) this warp finished in iteration T-1
-        float ax, ay, az, bx, by, bz, cx, cy, cz;         // coordinates of the next three tiles to set up
-        load_xyz(0, ax, ay, az);
-        load_xyz(1, bx, by, bz);
-        load_xyz(2, cx, cy, cz);
-        if (ntiles > 0) setup(0, ax, ay, az);
-        if (ntiles > 1) setup(1, bx, by, bz);
-        if (ntiles > 2) setup(2, cx, cy, cz);
-        load_xyz(3, ax, ay, az);
-        load_xyz(4, bx, by, bz);
-        load_xyz(5, cx, cy, cz);
+            ax = bx; ay = by; az = bz; bx = cx; by = cy; bz = cz;
+            load_xyz(T + 3, cx, cy, cz);
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(WS_REGS_EPILOGUE));
+        const int ew = warp & 3;                          // TMEM lane quarter = rows 32 ew .. 32 ew + 31
+        const float* w1 = reinterpret_cast<const float*>(smem_tc + WS_SMEM_W1);
+        const long long i_first = (long long)blockIdx.x * TC_TILE_ROWS + ew * 32 + lane;
         for (int T = 0; T < ntiles; ++T) {
             const int s = T & (WS_STAGES - 1), k = T / WS_STAGES;
-            if (T + 3 < ntiles) setup(T + 3, ax, ay, az);
-            ax = bx; ay = by; az = bz; bx = cx; by = cy; bz = cz;
-            load_xyz(T + 6, cx, cy, cz);
-            // epilogue of tile T
             mbar_wait(done_bar(s), (uint32_t)(k & 1));
             tc_fence_after_sync();
             const float d = tc_epilogue(tmem_base + (uint32_t)(s * TC_N) + ((uint32_t)(ew * 32) << 16), w1);
             tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(free_bar(s));
             const long long i = i_first + (long long)T * tile_stride;
             if (i < n) out[i] = d;
         }
