@@ -86,8 +86,9 @@ int launch_fwd(const NetDev& nd, const float* x, long long n, float* out, cudaSt
 //       lane 0 (after acc_free[s] of the accumulator's previous tile) issues the 15 tcgen05.mma of the tile into TMEM
 //       accumulator s and tcgen05.commit -> mbarrier mma_done[s].  No warp is parked on a barrier for it and the MMAs
 //       start the moment the tile is full.
-// Registers follow the roles (setmaxnreg): the kernel launches at 80 per thread (24 warps), the set-up warpgroup drops to
-// 40, the epilogue warpgroup to 64, the four producer warpgroups grow to 96 (64 of them hold line loads in flight).
+// Registers follow the roles (setmaxnreg moves registers inside the CTA's own allocation: 24 warps x 80 at launch):
+// the set-up warpgroup drops to 32, the epilogue warpgroup to 56, the four producer warpgroups grow to 96 (64 of
+// them hold line loads in flight): 128 x 32 + 128 x 56 + 512 x 96 = 768 x 80 exactly.
 // Tiles are assigned statically (CTA-local tile T = global tile T*gridDim.x + blockIdx.x): every role derives the same
 // mapping, nothing is communicated but the barriers.  Same arithmetic as the kernel above (tc_setup_record /
 // tc_issue_lines / tc_consume_lines / tc_issue_tile / tc_epilogue): results are bit-identical.
@@ -95,8 +96,8 @@ int launch_fwd(const NetDev& nd, const float* x, long long n, float* out, cudaSt
 #define WS_STAGES 4
 #define WS_WARPS (WS_PRODUCERS + 8)
 #define WS_REGS_PRODUCER 96
-#define WS_REGS_SETUP 40
-#define WS_REGS_EPILOGUE 64
+#define WS_REGS_SETUP 32
+#define WS_REGS_EPILOGUE 56
 #define WS_THREADS (WS_WARPS * 32)
 #define WS_REC_COL (NGLOD_F + 4)                      // K columns 36..39: zero in W0|b0 -> free 16 bytes per A row
 #define WS_SMEM_A(s) (2 * TC_OPERAND_BYTES + (s) * 2 * TC_OPERAND_BYTES)
@@ -105,6 +106,8 @@ int launch_fwd(const NetDev& nd, const float* x, long long n, float* out, cudaSt
 #define WS_SMEM_TMEMPTR (WS_SMEM_BAR + 4 * WS_STAGES * 8)
 #define WS_SMEM_BYTES (WS_SMEM_TMEMPTR + 16)
 static_assert(WS_SMEM_BYTES <= 232448, "shared memory budget");
+static_assert(128 * WS_REGS_SETUP + 128 * WS_REGS_EPILOGUE + 512 * WS_REGS_PRODUCER <= WS_THREADS * 80,
+              "setmaxnreg.inc spins forever when the CTA's register pool cannot cover it");
 
 template <int MODE>
 __global__ void __launch_bounds__(WS_THREADS, 1)
