@@ -72,23 +72,25 @@ int launch_fwd(const NetDev& nd, const float* x, long long n, float* out, cudaSt
 // epilogue serially inside each 4-warp group, so a warp has loads in flight only ~40 % of the time and the SM pulls
 // ~35 B/clk out of L2 where the probe (probe.cu) measures ~69 B/clk for the same address stream.  Here the phases run
 // on different warps and overlap tile by tile over a 4-stage ring of A operands / TMEM accumulators:
-//   set-up (4 warps)  : one query per lane (coalesced coordinate loads, prefetched tiles ahead) -> the 16-byte gather
-//       record {corner offset | flags, wx, wy, wz} and the {x, y, z, 1} K-chunk, written straight into the tile's A rows:
-//       the record lives in the K-padding chunk (columns 36..39), which the MMA multiplies by the zero padding of W0 --
-//       finite x 0, contributes nothing -- so it costs no shared memory.  Runs as far ahead as the ring allows (waits
-//       mma_done of the stage's previous tile)                                               -> mbarrier rec_full[s]
-//   epilogue (4 warps, the HIGHEST warp ids: the issue arbiter prefers them and their work is latency-critical):
-//       waits mma_done[s], tcgen05.ld its 32 rows, d = b1 + W1.relu(.), stores out          -> mbarrier acc_free[s]
+//   service (2 warpgroups of 4 warps, the HIGHEST warp ids: the issue arbiter prefers them and their work is short and
+//       latency-critical; warpgroup g serves the tiles T = g (mod 2)):
+//       epilogue of tile T: waits mma_done[s], tcgen05.ld its 32 rows, d = b1 + W1.relu(.), stores out.  One warpgroup
+//         needs ~2 800 cycles per tile next to the gather warps (measured) -- two of them keep up with the producers;
+//       set-up of tile T+4 (same stage, just freed): one query per lane (coalesced coordinate loads, prefetched) -> the
+//         16-byte gather record {corner offset | flags, wx, wy, wz} and the {x, y, z, 1} K-chunk, written straight into
+//         the tile's A rows: the record lives in the K-padding chunk (columns 36..39), which the MMA multiplies by the
+//         zero padding of W0 -- finite x 0, contributes nothing -- so it costs no shared memory -> mbarrier rec_full[s]
 //   producers (16 warps): ALL of them work on the same tile: warp p owns rows 8p..8p+7 = two gather rounds of 4 queries
 //       x 8 lanes: record by one LDS.128, 8 corner lines per query as 8 lanes x LDG.128, FFMA2 interpolation, hi/lo split,
 //       A rows.  A tile is filled in two load latencies, so a stage is re-used only four tile times after its MMAs.
 //   MMA issue: whichever producer warp arrives LAST at the tile (monotonic shared counter, 16 arrivals per tile): its
-//       lane 0 (after acc_free[s] of the accumulator's previous tile) issues the 15 tcgen05.mma of the tile into TMEM
-//       accumulator s and tcgen05.commit -> mbarrier mma_done[s].  No warp is parked on a barrier for it and the MMAs
-//       start the moment the tile is full.
+//       lane 0 issues the 15 tcgen05.mma of the tile into TMEM accumulator s and tcgen05.commit -> mbarrier mma_done[s].
+//       No warp is parked on a barrier for it and the MMAs start the moment the tile is full.
+// Ordering that needs no barrier of its own: the set-up of tile T+4 (same stage, same accumulator as T) follows the
+// epilogue of tile T in the same warps, and the producers fill T+4 only after that set-up.
 // Registers follow the roles (setmaxnreg moves registers inside the CTA's own allocation: 24 warps x 80 at launch):
-// the set-up warpgroup drops to 32, the epilogue warpgroup to 56, the four producer warpgroups grow to 96 (64 of
-// them hold line loads in flight): 128 x 32 + 128 x 56 + 512 x 96 = 768 x 80 exactly.
+// the two service warpgroups drop to 48, the four producer warpgroups grow to 96 (64 of them hold line loads in flight):
+// 256 x 48 + 512 x 96 = 768 x 80 exactly.
 // Tiles are assigned statically (CTA-local tile T = global tile T*gridDim.x + blockIdx.x): every role derives the same
 // mapping, nothing is communicated but the barriers.  Same arithmetic as the kernel above (tc_setup_record /
 // tc_issue_lines / tc_consume_lines / tc_issue_tile / tc_epilogue): results are bit-identical.
@@ -96,17 +98,16 @@ int launch_fwd(const NetDev& nd, const float* x, long long n, float* out, cudaSt
 #define WS_STAGES 4
 #define WS_WARPS (WS_PRODUCERS + 8)
 #define WS_REGS_PRODUCER 96
-#define WS_REGS_SETUP 32
-#define WS_REGS_EPILOGUE 56
+#define WS_REGS_SERVICE 48
 #define WS_THREADS (WS_WARPS * 32)
 #define WS_REC_COL (NGLOD_F + 4)                      // K columns 36..39: zero in W0|b0 -> free 16 bytes per A row
 #define WS_SMEM_A(s) (2 * TC_OPERAND_BYTES + (s) * 2 * TC_OPERAND_BYTES)
 #define WS_SMEM_W1 TC_SMEM_W1(WS_STAGES)
-#define WS_SMEM_BAR (WS_SMEM_W1 + 528)                 // arrival counters[4] (u32, padded to 8 B), mma_done[4], rec_full[4], acc_free[4]
-#define WS_SMEM_TMEMPTR (WS_SMEM_BAR + 4 * WS_STAGES * 8)
+#define WS_SMEM_BAR (WS_SMEM_W1 + 528)                 // arrival counters[4] (u32, padded to 8 B), mma_done[4], rec_full[4]
+#define WS_SMEM_TMEMPTR (WS_SMEM_BAR + 3 * WS_STAGES * 8)
 #define WS_SMEM_BYTES (WS_SMEM_TMEMPTR + 16)
 static_assert(WS_SMEM_BYTES <= 232448, "shared memory budget");
-static_assert(128 * WS_REGS_SETUP + 128 * WS_REGS_EPILOGUE + 512 * WS_REGS_PRODUCER <= WS_THREADS * 80,
+static_assert(256 * WS_REGS_SERVICE + 512 * WS_REGS_PRODUCER <= WS_THREADS * 80,
               "setmaxnreg.inc spins forever when the CTA's register pool cannot cover it");
 
 template <int MODE>
@@ -139,8 +140,7 @@ sdf_forward_ws_kernel(const NetDev net, const float* __restrict__ x, const long 
             for (int s = 0; s < WS_STAGES; ++s) {
                 *reinterpret_cast<volatile unsigned long long*>(smem_tc + WS_SMEM_BAR + 8 * s) = 0ull;    // arrival counter
                 mbar_init(smem_u32(smem_tc + WS_SMEM_BAR + 8 * (WS_STAGES + s)), 1);         // mma_done: tcgen05.commit
-                mbar_init(smem_u32(smem_tc + WS_SMEM_BAR + 8 * (2 * WS_STAGES + s)), 4);     // rec_full: 4 set-up warps
-                mbar_init(smem_u32(smem_tc + WS_SMEM_BAR + 8 * (3 * WS_STAGES + s)), 4);     // acc_free: 4 epilogue warps
+                mbar_init(smem_u32(smem_tc + WS_SMEM_BAR + 8 * (2 * WS_STAGES + s)), 4);     // rec_full: the tile's 4 service warps
             }
             mbar_fence_init();
         }
@@ -155,7 +155,6 @@ sdf_forward_ws_kernel(const NetDev net, const float* __restrict__ x, const long 
     auto arrive_cnt = [&](int s) { return reinterpret_cast<unsigned*>(smem_tc + WS_SMEM_BAR + 8 * s); };
     auto done_bar = [&](int s) { return bar0 + 8u * (uint32_t)(WS_STAGES + s); };
     auto rec_bar = [&](int s) { return bar0 + 8u * (uint32_t)(2 * WS_STAGES + s); };
-    auto free_bar = [&](int s) { return bar0 + 8u * (uint32_t)(3 * WS_STAGES + s); };
     // CTA-local tiles: global tile gt = T * gridDim.x + blockIdx.x while gt * 128 < n
     const long long total_tiles = (n + TC_TILE_ROWS - 1) / TC_TILE_ROWS;
     const int ntiles = (int)((total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
@@ -218,8 +217,6 @@ sdf_forward_ws_kernel(const NetDev net, const float* __restrict__ x, const long 
                 const unsigned old = atomicAdd(arrive_cnt(s), 1u);               // monotonic: 16 arrivals per use of the stage
                 if ((old & (WS_PRODUCERS - 1)) == WS_PRODUCERS - 1) {
                     __threadfence_block();                                       // acquire: everybody's A rows
-                    const int k = T / WS_STAGES;
-                    if (k > 0) mbar_wait(free_bar(s), (uint32_t)((k - 1) & 1)); // the accumulator's previous tile has been read
                     tc_fence_after_sync();
                     const uint32_t a_hi_s = smem_u32(a_hi);
                     tc_issue_tile(tmem_base + (uint32_t)(s * TC_N), a_hi_s, a_hi_s + TC_OPERAND_BYTES, b_hi, b_lo);
@@ -228,11 +225,14 @@ sdf_forward_ws_kernel(const NetDev net, const float* __restrict__ x, const long 
             }
             __syncwarp();
         }
-    } else if (warp < WS_PRODUCERS + 4) {
-        // ------------------------------------------------------------------ set-up: records + {x, y, z, 1} of the tiles ahead
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(WS_REGS_SETUP));
-        const int row = (warp - WS_PRODUCERS) * 32 + lane;
+    } else {
+        // ------------------------------------------------------------------ service: epilogue of tile T, set-up of tile T+4
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(WS_REGS_SERVICE));
+        const int wg = (warp - WS_PRODUCERS) >> 2;        // serves tiles T = wg (mod 2)
+        const int ew = warp & 3;                          // TMEM lane quarter = rows 32 ew .. 32 ew + 31
+        const int row = ew * 32 + lane;
         const int R = net.res[0];
+        const float* w1 = reinterpret_cast<const float*>(smem_tc + WS_SMEM_W1);
         const uint32_t rec_off = tc_elem_offset(row, WS_REC_COL), xyz_off = tc_elem_offset(row, NGLOD_F);
         const long long i_first = (long long)blockIdx.x * TC_TILE_ROWS + row;
         auto load_xyz = [&](int T, float& px, float& py, float& pz) {
@@ -240,42 +240,37 @@ sdf_forward_ws_kernel(const NetDev net, const float* __restrict__ x, const long 
             px = py = pz = 0.f;
             if (T < ntiles && i < n) { px = __ldg(x + 3 * i); py = __ldg(x + 3 * i + 1); pz = __ldg(x + 3 * i + 2); }
         };
-        float ax, ay, az, bx, by, bz, cx, cy, cz;         // coordinates of the next three tiles (DRAM latency)
-        load_xyz(0, ax, ay, az);
-        load_xyz(1, bx, by, bz);
-        load_xyz(2, cx, cy, cz);
-        for (int T = 0; T < ntiles; ++T) {
-            const int s = T & (WS_STAGES - 1), k = T / WS_STAGES;
+        auto setup = [&](int T, float px, float py, float pz) {
+            const int s = T & (WS_STAGES - 1);
             char* a_hi = smem_tc + WS_SMEM_A(s);
             char* a_lo = a_hi + TC_OPERAND_BYTES;
             const long long i = i_first + (long long)T * tile_stride;
             // rows past n carry record 0 (corner 0, weights 0): harmless loads, their accumulator rows are never read
-            const float4 rec = i < n ? tc_setup_record<HALF>(ax, ay, az, R) : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (k > 0) mbar_wait(done_bar(s), (uint32_t)((k - 1) & 1));      // the stage's previous tile has been multiplied
+            const float4 rec = i < n ? tc_setup_record<HALF>(px, py, pz, R) : make_float4(0.f, 0.f, 0.f, 0.f);
             *reinterpret_cast<float4*>(a_hi + rec_off) = rec;
-            tc_store_split4(a_hi, a_lo, xyz_off, make_float4(ax, ay, az, 1.f));
+            tc_store_split4(a_hi, a_lo, xyz_off, make_float4(px, py, pz, 1.f));
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(rec_bar(s));
-            ax = bx; ay = by; az = bz; bx = cx; by = cy; bz = cz;
-            load_xyz(T + 3, cx, cy, cz);
-        }
-    } else {
-        // ------------------------------------------------------------------ epilogue
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(WS_REGS_EPILOGUE));
-        const int ew = warp & 3;                          // TMEM lane quarter = rows 32 ew .. 32 ew + 31
-        const float* w1 = reinterpret_cast<const float*>(smem_tc + WS_SMEM_W1);
-        const long long i_first = (long long)blockIdx.x * TC_TILE_ROWS + ew * 32 + lane;
-        for (int T = 0; T < ntiles; ++T) {
+        };
+        float ax, ay, az, bx, by, bz;                     // coordinates of this warpgroup's next two tiles (DRAM latency)
+        load_xyz(wg, ax, ay, az);
+        load_xyz(wg + 2, bx, by, bz);
+        if (wg < ntiles) setup(wg, ax, ay, az);
+        if (wg + 2 < ntiles) setup(wg + 2, bx, by, bz);
+        load_xyz(wg + 4, ax, ay, az);
+        for (int T = wg; T < ntiles; T += 2) {
             const int s = T & (WS_STAGES - 1), k = T / WS_STAGES;
+            load_xyz(T + 6, bx, by, bz);
             mbar_wait(done_bar(s), (uint32_t)(k & 1));
             tc_fence_after_sync();
-            const float d = tc_epilogue(tmem_base + (uint32_t)(s * TC_N) + ((uint32_t)(ew * 32) << 16), w1);
+            const float d = tc_epilogue_pipelined(tmem_base + (uint32_t)(s * TC_N) + ((uint32_t)(ew * 32) << 16), w1);
             tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(free_bar(s));
             const long long i = i_first + (long long)T * tile_stride;
             if (i < n) out[i] = d;
+            // the stage and the accumulator of tile T are free now: set up tile T+4 in them
+            if (T + 4 < ntiles) setup(T + 4, ax, ay, az);
+            ax = bx; ay = by; az = bz;
         }
     }
     tc_epilogue_free(tmem_base);

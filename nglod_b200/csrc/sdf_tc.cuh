@@ -336,6 +336,32 @@ __device__ __forceinline__ float tc_epilogue(uint32_t taddr_row, const float* __
     return w1[NGLOD_H] + ((d0 + d1) + (d2 + d3));
 }
 
+// Same sums in the same order (partial sum j mod 4 over the columns, then (d0 + d1) + (d2 + d3): bit-identical to
+// tc_epilogue), arranged for a warp that shares its scheduler with gather warps: 16 columns per tcgen05.ld, the next
+// chunk's load in flight while the current one is folded in, the two multiply-adds of a column pair as one FFMA2.
+__device__ __forceinline__ float tc_epilogue_pipelined(uint32_t taddr_row, const float* __restrict__ w1) {
+    uint64_t d01 = 0ull, d23 = 0ull;
+    uint32_t v[2][16];
+    tmem_ld16_async(taddr_row, v[0]);
+#pragma unroll
+    for (int cb = 0; cb < NGLOD_H / 16; ++cb) {
+        tmem_ld_wait();
+        if (cb + 1 < NGLOD_H / 16) tmem_ld16_async(taddr_row + (cb + 1) * 16, v[(cb + 1) & 1]);
+        const uint32_t* u = v[cb & 1];
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 w = *reinterpret_cast<const float4*>(w1 + cb * 16 + 4 * j4);
+            const float a0 = fmaxf(__uint_as_float(u[4 * j4]), 0.f), a1 = fmaxf(__uint_as_float(u[4 * j4 + 1]), 0.f);
+            const float a2 = fmaxf(__uint_as_float(u[4 * j4 + 2]), 0.f), a3 = fmaxf(__uint_as_float(u[4 * j4 + 3]), 0.f);
+            d01 = f2_fma(f2_pack(w.x, w.y), f2_pack(a0, a1), d01);
+            d23 = f2_fma(f2_pack(w.z, w.w), f2_pack(a2, a3), d23);
+        }
+    }
+    float d0, d1, d2, d3;
+    f2_unpack(d01, d0, d1); f2_unpack(d23, d2, d3);
+    return w1[NGLOD_H] + ((d0 + d1) + (d2 + d3));
+}
+
 // Per-group context + one full tile evaluation: gather -> MMA -> epilogue.  All 128 threads of the group call.
 struct TcGroup {
     char* a_hi; char* a_lo;
