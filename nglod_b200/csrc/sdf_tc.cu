@@ -199,7 +199,7 @@ sdf_forward_ws_kernel(const NetDev net, const float* __restrict__ x, const long 
                 if (more) tc_issue_lines<HALF>(grid, R, __float_as_uint(nrec0.x), c, t0);
                 float4 acc;
                 f2_unpack(acc01, acc.x, acc.y); f2_unpack(acc23, acc.z, acc.w);
-                tc_store_split4(a_hi, a_lo, st_off0, acc);
+                tc_store_split4_finite(a_hi, a_lo, st_off0, acc);
             }
             {
                 uint64_t acc01 = 0ull, acc23 = 0ull;
@@ -207,7 +207,7 @@ sdf_forward_ws_kernel(const NetDev net, const float* __restrict__ x, const long 
                 if (more) tc_issue_lines<HALF>(grid, R, __float_as_uint(nrec1.x), c, t1);
                 float4 acc;
                 f2_unpack(acc01, acc.x, acc.y); f2_unpack(acc23, acc.z, acc.w);
-                tc_store_split4(a_hi, a_lo, st_off1, acc);
+                tc_store_split4_finite(a_hi, a_lo, st_off1, acc);
             }
             rec0 = nrec0; rec1 = nrec1;
             fence_proxy_async_smem();

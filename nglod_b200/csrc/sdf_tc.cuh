@@ -90,6 +90,15 @@ __device__ __forceinline__ void tc_store_split4(char* a_hi, char* a_lo, uint32_t
     *reinterpret_cast<float4*>(a_lo + off) = l;
 }
 
+// Same values for finite v (see tf32_hi_finite): the warp-specialised kernel's version of tc_store_split4.
+__device__ __forceinline__ void tc_store_split4_finite(char* a_hi, char* a_lo, uint32_t off, float4 v) {
+    float4 h, l;
+    h.x = tf32_hi_finite(v.x); h.y = tf32_hi_finite(v.y); h.z = tf32_hi_finite(v.z); h.w = tf32_hi_finite(v.w);
+    l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+    *reinterpret_cast<float4*>(a_hi + off) = h;
+    *reinterpret_cast<float4*>(a_lo + off) = l;
+}
+
 // One axis of the trilinear set-up (PyTorch grid_sampler arithmetic, see sdf_core.cuh::lod_axis).
 // Returns floor index, the upper weight w1 = u - floor(u) and whether the +1 corner exists.
 __device__ __forceinline__ void tc_axis(float p, int R, int& i0, float& w1, bool& has1) {
@@ -337,24 +346,31 @@ __device__ __forceinline__ float tc_epilogue(uint32_t taddr_row, const float* __
 }
 
 // Same sums in the same order (partial sum j mod 4 over the columns, then (d0 + d1) + (d2 + d3): bit-identical to
-// tc_epilogue), arranged for a warp that shares its scheduler with gather warps: 16 columns per tcgen05.ld, the next
-// chunk's load in flight while the current one is folded in, the two multiply-adds of a column pair as one FFMA2.
+// tc_epilogue), arranged for a warp that shares its scheduler with gather warps: 8 columns per tcgen05.ld, the next
+// chunk's load (and its W1 values) in flight while the current one is folded in, the two multiply-adds of a column pair as one FFMA2.
 __device__ __forceinline__ float tc_epilogue_pipelined(uint32_t taddr_row, const float* __restrict__ w1) {
     uint64_t d01 = 0ull, d23 = 0ull;
-    uint32_t v[2][16];
-    tmem_ld16_async(taddr_row, v[0]);
+    uint32_t v[2][8];
+    float4 w[2][2];
+    tmem_ld8_async(taddr_row, v[0]);
+    w[0][0] = *reinterpret_cast<const float4*>(w1);
+    w[0][1] = *reinterpret_cast<const float4*>(w1 + 4);
 #pragma unroll
-    for (int cb = 0; cb < NGLOD_H / 16; ++cb) {
+    for (int cb = 0; cb < NGLOD_H / 8; ++cb) {
         tmem_ld_wait();
-        if (cb + 1 < NGLOD_H / 16) tmem_ld16_async(taddr_row + (cb + 1) * 16, v[(cb + 1) & 1]);
+        if (cb + 1 < NGLOD_H / 8) {                      // next chunk: accumulator columns and W1 in flight during this one
+            tmem_ld8_async(taddr_row + (cb + 1) * 8, v[(cb + 1) & 1]);
+            w[(cb + 1) & 1][0] = *reinterpret_cast<const float4*>(w1 + (cb + 1) * 8);
+            w[(cb + 1) & 1][1] = *reinterpret_cast<const float4*>(w1 + (cb + 1) * 8 + 4);
+        }
         const uint32_t* u = v[cb & 1];
 #pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 w = *reinterpret_cast<const float4*>(w1 + cb * 16 + 4 * j4);
+        for (int j4 = 0; j4 < 2; ++j4) {
+            const float4 ww = w[cb & 1][j4];
             const float a0 = fmaxf(__uint_as_float(u[4 * j4]), 0.f), a1 = fmaxf(__uint_as_float(u[4 * j4 + 1]), 0.f);
             const float a2 = fmaxf(__uint_as_float(u[4 * j4 + 2]), 0.f), a3 = fmaxf(__uint_as_float(u[4 * j4 + 3]), 0.f);
-            d01 = f2_fma(f2_pack(w.x, w.y), f2_pack(a0, a1), d01);
-            d23 = f2_fma(f2_pack(w.z, w.w), f2_pack(a2, a3), d23);
+            d01 = f2_fma(f2_pack(ww.x, ww.y), f2_pack(a0, a1), d01);
+            d23 = f2_fma(f2_pack(ww.z, ww.w), f2_pack(a2, a3), d23);
         }
     }
     float d0, d1, d2, d3;
