@@ -199,7 +199,15 @@ sdf_forward_ws_kernel(const NetDev net, const float* __restrict__ x, const long 
                 if (more) tc_issue_lines<HALF>(grid, R, __float_as_uint(nrec0.x), c, t0);
                 float4 acc;
                 f2_unpack(acc01, acc.x, acc.y); f2_unpack(acc23, acc.z, acc.w);
-                tc_store_split4_finite(a_hi, a_lo, st_off0, acc);
+#ifndef NGLOD_WS_FASTSPLIT
+#define NGLOD_WS_FASTSPLIT 1
+#endif
+#if NGLOD_WS_FASTSPLIT
+#define WS_STORE_SPLIT tc_store_split4_finite
+#else
+#define WS_STORE_SPLIT tc_store_split4
+#endif
+                WS_STORE_SPLIT(a_hi, a_lo, st_off0, acc);
             }
             {
                 uint64_t acc01 = 0ull, acc23 = 0ull;
@@ -207,7 +215,7 @@ sdf_forward_ws_kernel(const NetDev net, const float* __restrict__ x, const long 
                 if (more) tc_issue_lines<HALF>(grid, R, __float_as_uint(nrec1.x), c, t1);
                 float4 acc;
                 f2_unpack(acc01, acc.x, acc.y); f2_unpack(acc23, acc.z, acc.w);
-                tc_store_split4_finite(a_hi, a_lo, st_off1, acc);
+                WS_STORE_SPLIT(a_hi, a_lo, st_off1, acc);
             }
             rec0 = nrec0; rec1 = nrec1;
             fence_proxy_async_smem();
@@ -264,7 +272,16 @@ sdf_forward_ws_kernel(const NetDev net, const float* __restrict__ x, const long 
             load_xyz(T + 6, bx, by, bz);
             mbar_wait(done_bar(s), (uint32_t)(k & 1));
             tc_fence_after_sync();
-            const float d = tc_epilogue_pipelined(tmem_base + (uint32_t)(s * TC_N) + ((uint32_t)(ew * 32) << 16), w1);
+#ifndef NGLOD_WS_EPI
+#define NGLOD_WS_EPI 16
+#endif
+#if NGLOD_WS_EPI == 8
+            const float d = tc_epilogue_pipelined8(tmem_base + (uint32_t)(s * TC_N) + ((uint32_t)(ew * 32) << 16), w1);
+#elif NGLOD_WS_EPI == 16
+            const float d = tc_epilogue_pipelined16(tmem_base + (uint32_t)(s * TC_N) + ((uint32_t)(ew * 32) << 16), w1);
+#else
+            const float d = tc_epilogue(tmem_base + (uint32_t)(s * TC_N) + ((uint32_t)(ew * 32) << 16), w1);
+#endif
             tc_fence_before_sync();
             const long long i = i_first + (long long)T * tile_stride;
             if (i < n) out[i] = d;

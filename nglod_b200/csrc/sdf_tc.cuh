@@ -277,7 +277,14 @@ __device__ __forceinline__ void tc_gather_single(const NetDev& net, const float4
             if ((live >> q) & 1u) {
                 float4 acc;
                 f2_unpack(acc01, acc.x, acc.y); f2_unpack(acc23, acc.z, acc.w);
+#ifndef NGLOD_TC_FASTSPLIT
+#define NGLOD_TC_FASTSPLIT 1
+#endif
+#if NGLOD_TC_FASTSPLIT
+                tc_store_split4_finite(a_hi, a_lo, tc_elem_offset(row0 + q, 4 * c), acc);
+#else
                 tc_store_split4(a_hi, a_lo, tc_elem_offset(row0 + q, 4 * c), acc);
+#endif
             }
         }
         if (r + DEPTH < 8) {
@@ -328,6 +335,26 @@ __device__ __forceinline__ void tc_gather_rows(const NetDev& net, float px, floa
 // Four interleaved partial sums: one 128-long dependent FFMA chain is 512 cycles of pure latency per tile, which is
 // what a sparsely occupied tracer tile (the frame's straggler rays) waits for every round.
 __device__ __forceinline__ float tc_epilogue(uint32_t taddr_row, const float* __restrict__ w1) {
+#ifndef NGLOD_TC_EPI_F2
+#define NGLOD_TC_EPI_F2 1           // the two multiply-adds of a column pair as one FFMA2 (each half rounds like the scalar fmaf)
+#endif
+#if NGLOD_TC_EPI_F2
+    uint64_t d01 = 0ull, d23 = 0ull;
+#pragma unroll
+    for (int cb = 0; cb < NGLOD_H / 32; ++cb) {
+        float v[32];
+        tmem_ld32(taddr_row + cb * 32, v);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 w = *reinterpret_cast<const float4*>(w1 + cb * 32 + 4 * j4);
+            d01 = f2_fma(f2_pack(w.x, w.y), f2_pack(fmaxf(v[4 * j4], 0.f), fmaxf(v[4 * j4 + 1], 0.f)), d01);
+            d23 = f2_fma(f2_pack(w.z, w.w), f2_pack(fmaxf(v[4 * j4 + 2], 0.f), fmaxf(v[4 * j4 + 3], 0.f)), d23);
+        }
+    }
+    float d0, d1, d2, d3;
+    f2_unpack(d01, d0, d1); f2_unpack(d23, d2, d3);
+    return w1[NGLOD_H] + ((d0 + d1) + (d2 + d3));
+#else
     float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
 #pragma unroll
     for (int cb = 0; cb < NGLOD_H / 32; ++cb) {
@@ -343,12 +370,13 @@ __device__ __forceinline__ float tc_epilogue(uint32_t taddr_row, const float* __
         }
     }
     return w1[NGLOD_H] + ((d0 + d1) + (d2 + d3));
+#endif
 }
 
 // Same sums in the same order (partial sum j mod 4 over the columns, then (d0 + d1) + (d2 + d3): bit-identical to
 // tc_epilogue), arranged for a warp that shares its scheduler with gather warps: 8 columns per tcgen05.ld, the next
 // chunk's load (and its W1 values) in flight while the current one is folded in, the two multiply-adds of a column pair as one FFMA2.
-__device__ __forceinline__ float tc_epilogue_pipelined(uint32_t taddr_row, const float* __restrict__ w1) {
+__device__ __forceinline__ float tc_epilogue_pipelined8(uint32_t taddr_row, const float* __restrict__ w1) {
     uint64_t d01 = 0ull, d23 = 0ull;
     uint32_t v[2][8];
     float4 w[2][2];
@@ -371,6 +399,29 @@ __device__ __forceinline__ float tc_epilogue_pipelined(uint32_t taddr_row, const
             const float a2 = fmaxf(__uint_as_float(u[4 * j4 + 2]), 0.f), a3 = fmaxf(__uint_as_float(u[4 * j4 + 3]), 0.f);
             d01 = f2_fma(f2_pack(ww.x, ww.y), f2_pack(a0, a1), d01);
             d23 = f2_fma(f2_pack(ww.z, ww.w), f2_pack(a2, a3), d23);
+        }
+    }
+    float d0, d1, d2, d3;
+    f2_unpack(d01, d0, d1); f2_unpack(d23, d2, d3);
+    return w1[NGLOD_H] + ((d0 + d1) + (d2 + d3));
+}
+
+__device__ __forceinline__ float tc_epilogue_pipelined16(uint32_t taddr_row, const float* __restrict__ w1) {
+    uint64_t d01 = 0ull, d23 = 0ull;
+    uint32_t v[2][16];
+    tmem_ld16_async(taddr_row, v[0]);
+#pragma unroll
+    for (int cb = 0; cb < NGLOD_H / 16; ++cb) {
+        tmem_ld_wait();
+        if (cb + 1 < NGLOD_H / 16) tmem_ld16_async(taddr_row + (cb + 1) * 16, v[(cb + 1) & 1]);
+        const uint32_t* u = v[cb & 1];
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 w = *reinterpret_cast<const float4*>(w1 + cb * 16 + 4 * j4);
+            const float a0 = fmaxf(__uint_as_float(u[4 * j4]), 0.f), a1 = fmaxf(__uint_as_float(u[4 * j4 + 1]), 0.f);
+            const float a2 = fmaxf(__uint_as_float(u[4 * j4 + 2]), 0.f), a3 = fmaxf(__uint_as_float(u[4 * j4 + 3]), 0.f);
+            d01 = f2_fma(f2_pack(w.x, w.y), f2_pack(a0, a1), d01);
+            d23 = f2_fma(f2_pack(w.z, w.w), f2_pack(a2, a3), d23);
         }
     }
     float d0, d1, d2, d3;
