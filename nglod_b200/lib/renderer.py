@@ -41,6 +41,9 @@ class Renderer():
             self.device = "cuda"
         self.width, self.height = self.render_res
         self._matcap = None
+        # optional [N,3] tensor used as the shadow rays' direction jitter instead of a fresh N(0, 0.01) draw
+        # (renderer.py:151 draws it from torch's global generator); lets a caller reproduce a frame exactly
+        self.shadow_jitter = None
         if self.shadow:
             gh = setparam(args, ground_height, "ground_height")
             if not gh:
@@ -88,7 +91,9 @@ class Renderer():
 
                 light_o = torch.tensor([[-1.5, 4.5, -1.5]], device=ray_o.device)
                 s_o = rb.x + 0.1 * rb.normal
-                s_d = F.normalize(torch.zeros_like(rb.x).normal_(0.0, 0.01) + light_o - s_o, dim=1)
+                jitter = torch.zeros_like(rb.x).normal_(0.0, 0.01) if self.shadow_jitter is None \
+                    else self.shadow_jitter.to(rb.x.device, rb.x.dtype)
+                s_d = F.normalize(jitter + light_o - s_o, dim=1)
                 lit = (s_d * rb.normal).sum(-1) > 0.0
                 rb.shadow = self.tracer(net, s_o, s_d).hit
                 rb.shadow[~lit] = 0

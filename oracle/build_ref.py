@@ -61,7 +61,26 @@ def build(verbose=False):
             ok = False
             print(f"[build_ref] FAILED {name}: {e}")
     ok = build_solr(verbose) and ok
+    ok = stage_python() and ok
     return ok
+
+
+PY_STAGE = os.path.join(OUT, "sdf-net")
+
+
+def stage_python():
+    """The reference's host side is Python and cannot travel to the GPU box any other way: stage sdf-net/lib (unmodified)
+    next to the compiled extensions, under the git-ignored oracle/_ref/.  oracle/ref_python.py imports it from there, for
+    INTEGRATION.md's route A test (unmodified reference Python over our shims) and bench.py's reference-on-this-B200 leg."""
+    import shutil
+    src = os.path.join(REF, "sdf-net", "lib")
+    dst = os.path.join(PY_STAGE, "lib")
+    if os.path.isdir(dst):
+        print(f"[build_ref] {dst} already staged")
+        return True
+    shutil.copytree(src, dst, ignore=shutil.ignore_patterns("__pycache__", "*.pyc", "extensions"))
+    print(f"[build_ref] staged {src} -> {dst}")
+    return True
 
 
 def build_solr(verbose=False):

@@ -32,3 +32,8 @@ def rand5():
 @pytest.fixture(scope="session")
 def fit3():
     return dict(np.load(os.path.join(GOLDEN, "fit3.npz")))
+
+
+@pytest.fixture(scope="session")
+def fit5():
+    return dict(np.load(os.path.join(GOLDEN, "fit5.npz")))

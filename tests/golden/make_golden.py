@@ -14,6 +14,12 @@ Outputs (small .npz files next to this script):
   fit3.npz   a 3-LOD model fitted for a few hundred Adam steps to a torus (weights stored):
              sdf, 96x54 trace at lod 2, Renderer.render with AO
   samplers.npz  lib/torchgp's host sampling recipe under fixed torch seeds
+  fit5.npz   BASELINE config 2's model shape: 5 LODs (base-lod 2: R = 4..64), feature-dim 32, fitted to a torus, evaluated
+             at lod 4: sdf, a 96x54 SphereTracer frame, SphereTracer.get_min, Renderer.render with --shadow
+             --ground-height -0.3 --ao (shadow-ray jitter stored).  To keep the fixture small the two fine grids start
+             at ZERO and are trained only on near-surface samples in a second phase (Adam leaves untouched nodes at
+             exactly 0, which compresses away), and every weight is rounded to an fp16-exact value before the reference
+             is evaluated (stored as fp16: ~1.5 MB instead of 40 MB).
 """
 import os
 import sys
@@ -198,6 +204,106 @@ def fit3():
 
 
 
+def fit5():
+    out = {}
+    args = make_args(["--num-lods", "5"])
+    torch.manual_seed(5)
+    net = OctreeSDF(args)
+    with torch.no_grad():
+        net.features[3].fm.zero_()
+        net.features[4].fm.zero_()
+    g = torch.Generator().manual_seed(13)
+
+    def near_surface(nb):
+        """points within a few hundredths of the torus surface (the 'near' / 'trace' sample modes of MeshDataset)"""
+        u = torch.rand(nb, generator=g) * 2 * np.pi
+        v = torch.rand(nb, generator=g) * 2 * np.pi
+        ring = torch.stack([0.6 * torch.cos(u), torch.zeros(nb), 0.6 * torch.sin(u)], 1)
+        nrm = torch.stack([torch.cos(v) * torch.cos(u), torch.sin(v), torch.cos(v) * torch.sin(u)], 1)
+        return ring + nrm * (0.25 + 0.02 * torch.randn(nb, 1, generator=g))
+
+    net.train()
+    # phase 1: the three coarse grids + every decoder, uniform + near-surface samples
+    p1 = [net.features[i].fm for i in range(3)] + list(net.louts.parameters())
+    opt = torch.optim.Adam(p1, lr=1e-3)
+    for it in range(250):
+        pts = torch.cat([torch.rand(4096, 3, generator=g) * 2 - 1, near_surface(4096)])
+        gt = torus_sdf(pts).unsqueeze(1)
+        opt.zero_grad()
+        preds = net.sdf(pts, return_lst=True)
+        loss = sum(((p - gt) ** 2).sum() for p in preds) / pts.shape[0]
+        loss.backward()
+        net.features[3].fm.grad = None
+        net.features[4].fm.grad = None
+        opt.step()
+        if it % 50 == 0:
+            print("fit5 phase 1 it", it, loss.item(), flush=True)
+    # phase 2: everything, near-surface samples only -> the fine grids change in a thin band, the rest stays 0
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    for it in range(250):
+        pts = near_surface(8192)
+        gt = torus_sdf(pts).unsqueeze(1)
+        opt.zero_grad()
+        preds = net.sdf(pts, return_lst=True)
+        loss = sum(((p - gt) ** 2).sum() for p in preds) / pts.shape[0]
+        loss.backward()
+        opt.step()
+        if it % 50 == 0:
+            print("fit5 phase 2 it", it, loss.item(), flush=True)
+    net.eval()
+    with torch.no_grad():
+        for p in net.parameters():
+            p.copy_(p.half().float())                           # fp16-exact weights: what is stored is what was evaluated
+    for k, v in net.state_dict().items():
+        out["sd." + k] = v.half().numpy()
+    print("fit5: non-zero fraction of the fine grids",
+          [float((net.features[i].fm != 0).float().mean()) for i in (3, 4)], flush=True)
+    x = torch.cat([torch.rand(2048, 3, generator=g) * 2 - 1, near_surface(2048)])
+    out["x"] = x.numpy()
+    with torch.no_grad():
+        for l in range(5):
+            out[f"sdf_lod{l}"] = net.sdf(x, lod=l).numpy()
+    net.lod = 4
+    tracer = SphereTracer(args)
+    torch.manual_seed(654)
+    ray_o, ray_d = look_at([-2.8, 2.8, -2.8], [0, 0, 0], 96, 54, fov=30.0, mode="persp", device="cpu")
+    out["t1_ray_o"], out["t1_ray_d"] = ray_o.numpy(), ray_d.numpy()
+    rb = tracer(net, ray_o, ray_d)
+    trace_pack("t1", rb, out)
+    with torch.no_grad():
+        conv = (net(rb.x).abs() < 0.0003)[:, 0] & rb.hit
+    out["t1_converged"] = conv.numpy()
+    print("fit5: hits", int(rb.hit.sum()), "converged", int(conv.sum()), "of", rb.hit.numel(), flush=True)
+    # SphereTracer.get_min (SphereTracer.py:134-218).  As shipped it ends in RenderBuffer(minx=...), a keyword the buffer
+    # does not have (its field is min_x) -> TypeError; the golden run swaps in a buffer class that accepts it.
+    ST = sys.modules["lib.tracer.SphereTracer"]      # the module (lib.tracer re-exports the class under the same name)
+
+    class _AnyBuffer:
+        def __init__(self, **kw):
+            self.__dict__.update(kw)
+    keep = ST.RenderBuffer
+    ST.RenderBuffer = _AnyBuffer
+    try:
+        gm = SphereTracer(args, num_steps=48).get_min(net, ray_o, ray_d)
+    finally:
+        ST.RenderBuffer = keep
+    for k in ("x", "depth", "hit", "normal", "minx"):
+        out["gm_" + k] = getattr(gm, k).detach().numpy()
+    # Renderer.render with the shadow pass and AO (renderer.py:131-209); the only random draw inside is the shadow-ray
+    # jitter normal_(0, 0.01), replayed here from the same seed and stored
+    rargs = make_args(["--num-lods", "5", "--render-res", "96", "54", "--shadow", "--ground-height", "-0.3", "--ao"])
+    renderer = Renderer(SphereTracer(rargs), args=rargs, device="cpu")
+    torch.manual_seed(777)
+    rb2 = renderer.render(net, ray_o, ray_d)
+    torch.manual_seed(777)
+    out["r2_shadow_jitter"] = torch.zeros(ray_o.shape[0], 3).normal_(0.0, 0.01).numpy()
+    for k in ("x", "depth", "hit", "normal", "shadow", "ao", "relative_depth"):
+        out["r2_" + k] = getattr(rb2, k).detach().numpy()
+    np.savez_compressed(os.path.join(HERE, "fit5.npz"), **out)
+    print("fit5: shadow pixels", int(rb2.shadow.sum()), "plane+surface hits", int(rb2.hit.sum()),
+          "file", os.path.getsize(os.path.join(HERE, "fit5.npz")) // 1024, "KB", flush=True)
+
+
 def spc_golden():
     """Octree bytes / points / pyramid / point queries from the reference's numpy SPC (sdf-net/lib/spc3d.py), for a
     sphere of radius 0.6 at level 4 (recursive construction :128-137, binary encoding :224-255, decoding :273-304,
@@ -251,7 +357,7 @@ def samplers():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["rand5", "fit3", "spc", "samplers"]
+    which = sys.argv[1:] or ["rand5", "fit3", "spc", "samplers", "fit5"]
     if "samplers" in which:
         samplers()
     if "rand5" in which:
@@ -260,3 +366,5 @@ if __name__ == "__main__":
         fit3()
     if "spc" in which:
         spc_golden()
+    if "fit5" in which:
+        fit5()

@@ -26,6 +26,15 @@ def fit3_model(fit3, device="cpu"):
     return net.to(device), args
 
 
+def fit5_model(fit5, device="cpu"):
+    """BASELINE config 2's shape (5 LODs, feature-dim 32) with the fitted, fp16-exact weights of tests/golden/fit5.npz."""
+    args = make_args(["--num-lods", "5"])
+    net = OctreeSDF(args)
+    sd = {k[3:]: torch.from_numpy(v.astype(np.float32)) for k, v in fit5.items() if k.startswith("sd.")}
+    net.load_state_dict(sd)
+    return net.to(device), args
+
+
 def weights_checksum(net):
     ps = list(net.parameters())
     return np.array([float(sum(p.detach().double().sum() for p in ps)),
