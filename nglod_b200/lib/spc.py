@@ -251,7 +251,70 @@ class SparseOctreeSDF:
         self.math_mode = getattr(net, "math_mode", "tc")
 
     def _decoder_params(self, lod):
+        if self.net is None:
+            return self._decoders[lod]
         return self.net.decoder_params(lod)
+
+    @classmethod
+    def load(cls, path, device="cuda", math_mode="tc"):
+        """Read the real-time renderer's model file back (what sol-renderer/SDF.cu:65-139 `loadWeights` + :141-216
+        `initTrinkets` do): `octree` bytes -> SPC; `cc` (uint8 corner coordinates, all LODs concatenated, `pyramid[l]`
+        rows each) + `cf` (fp16 corner features) -> corner table; voxel -> 8 corner rows (`trinkets`) and the parent
+        link are re-derived from the coordinates -- the reference searches `cc` linearly per corner (index_trinket.cuh),
+        here: sort the corner keys once, binary-search every voxel corner.  Decoders come back as fp32 copies of the
+        stored fp16 values.  The file format fixes base_lod = 2 (LOD l <-> octree level l + 2, SDF.cu:155-158)."""
+        import numpy as np
+        z = np.load(path)
+        dev = torch.device(device)
+        self = cls.__new__(cls)
+        self.net, self.math_mode = None, math_mode
+        self.spc = SPC(torch.from_numpy(z["octree"].astype(np.uint8)).to(dev))
+        counts = [int(c) for c in z["pyramid"]]
+        self.num_lods, self.base_lod = len(counts), 2
+        if self.spc.level < self.num_lods + 1:
+            raise ValueError("octree is shallower than the file's finest LOD")
+        cc = torch.from_numpy(z["cc"].astype(np.int64)).to(dev)
+        if cc.shape[0] != sum(counts) or z["cf"].shape[0] != sum(counts):
+            raise ValueError("cc / cf / pyramid disagree on the number of corner rows")
+        self.corner_feats = torch.from_numpy(z["cf"].astype(np.float32)).to(dev).contiguous()
+        off = torch.tensor([[k & 1, (k >> 1) & 1, (k >> 2) & 1] for k in range(8)], device=dev)
+        trinkets, parents, voxels, lod_offset = [], [], [], [0]
+        base, prev_morton = 0, None
+        for l, cnt in enumerate(counts):
+            level = l + 2
+            S = (1 << level) + 1
+            c = cc[base:base + cnt]
+            ckey = (c[:, 2] * S + c[:, 1]) * S + c[:, 0]
+            skey, order = torch.sort(ckey)
+            vox = self.spc.level_points(level)[:, :3].long()
+            cor = vox.unsqueeze(1) + off.unsqueeze(0)
+            vkey = ((cor[..., 2] * S + cor[..., 1]) * S + cor[..., 0]).reshape(-1)
+            pos = torch.searchsorted(skey, vkey).clamp(max=cnt - 1)
+            if not bool((skey[pos] == vkey).all()):
+                raise ValueError(f"LOD {l}: a voxel corner is missing from cc (file and octree disagree)")
+            trinkets.append((order[pos].reshape(-1, 8) + base).int())
+            morton = points_to_morton(vox)
+            if l == 0:
+                parents.append(torch.full((vox.shape[0],), -1, dtype=torch.int32, device=dev))
+            else:
+                parents.append((torch.searchsorted(prev_morton, morton >> 3) + lod_offset[l - 1]).int())
+            prev_morton = morton
+            v4 = torch.zeros(vox.shape[0], 4, dtype=torch.int16, device=dev)
+            v4[:, :3] = vox.short()
+            voxels.append(v4)
+            base += cnt
+            lod_offset.append(lod_offset[-1] + vox.shape[0])
+        self.trinkets = torch.cat(trinkets).contiguous()
+        self.parents = torch.cat(parents).contiguous()
+        self.voxels = torch.cat(voxels).contiguous()
+        self.lod_offset = lod_offset
+        f32 = lambda a: torch.from_numpy(a.astype(np.float32)).to(dev).contiguous()
+        self._decoders = [(f32(z["w0"][i]), f32(z["b0"][i]), f32(z["w1"][i]), f32(z["b1"][i])) for i in range(self.num_lods)]
+        self.pos_invariant = self._decoders[0][0].shape[1] == self.corner_feats.shape[1]
+        self.sum_lods = dev.type == "cuda"
+        self.corner_feats_summed = summed_corner_rows(self.corner_feats, self.trinkets, self.parents, self.voxels,
+                                                      self.lod_offset, self.num_lods) if self.sum_lods else None
+        return self
 
     def save(self, path):
         """Write the reference's real-time renderer format (SOL_NGLOD.save, lib/models/SOL_NGLOD.py:80-100; read by
@@ -272,7 +335,7 @@ class SparseOctreeSDF:
             cc.append(coords)
             counts.append(nrows)
             row += nrows
-        dec = [self.net.decoder_params(i) for i in range(self.num_lods)]
+        dec = [self._decoder_params(i) for i in range(self.num_lods)]
         np.savez_compressed(
             path, octree=self.spc.octree.cpu().numpy(), cc=torch.cat(cc).cpu().numpy(),
             cf=self.corner_feats.half().cpu().numpy(),
@@ -371,6 +434,32 @@ def build_sparse_tables(spc, num_lods, base_lod):
             lod_offset, torch.cat(cxyz).contiguous())
 
 
+def summed_corner_rows(cf, trinkets, parents, voxels, lod_offset, num_lods):
+    """Prefix-summed corner rows (nglod_sparse_net_t.corner_feats_summed): row of a LOD-l corner = sum over k <= l of the
+    level-k interpolant at that corner, built level by level (each corner is evaluated in the parent of a voxel that
+    owns it; voxels sharing a corner agree because the coarser field is continuous across occupied voxels)."""
+    out = cf.clone()
+    dev = cf.device
+    off = torch.tensor([[k & 1, (k >> 1) & 1, (k >> 2) & 1] for k in range(8)], device=dev)
+    for l in range(1, num_lods):
+        v0, v1 = lod_offset[l], lod_offset[l + 1]
+        tr = trinkets[v0:v1].long()
+        par = parents[v0:v1].long()
+        vox = voxels[v0:v1, :3].long()
+        pvox = voxels[par, :3].long()
+        ptr = trinkets[par].long()                                    # parent's 8 corner rows (already summed)
+        pval = out[ptr]                                               # [nv, 8, F]
+        for k in range(8):
+            f = ((vox + off[k]) - 2 * pvox).float() * 0.5             # position of corner k in the parent, in {0, .5, 1}^3
+            g = 1.0 - f
+            acc = 0
+            for j in range(8):
+                w = (f[:, 0] if j & 1 else g[:, 0]) * (f[:, 1] if j & 2 else g[:, 1]) * (f[:, 2] if j & 4 else g[:, 2])
+                acc = acc + w.unsqueeze(1) * pval[:, j]
+            out[tr[:, k]] = cf[tr[:, k]] + acc
+    return out
+
+
 class _SparseSdfFunction(torch.autograd.Function):
     """d = NeuralSPC.sdf(x, lod, pidx): sparse forward kernel; the backward recomputes it in-kernel and scatters
     dL/d(corner features) along each query's parent chain (nglod_sparse_sdf_backward)."""
@@ -432,30 +521,8 @@ class NeuralSPC(torch.nn.Module, SparseOctreeSDF):
         return (seq[0].weight, seq[0].bias, seq[2].weight, seq[2].bias)
 
     def summed_rows(self):
-        """Prefix-summed corner rows (nglod_sparse_net_t.corner_feats_summed): row of a LOD-l corner = sum over k <= l of the
-        level-k interpolant at that corner, built level by level (each corner is evaluated in the parent of a voxel that
-        owns it; voxels sharing a corner agree because the coarser field is continuous across occupied voxels)."""
-        cf = self.corner_feats.data
-        out = cf.clone()
-        dev = cf.device
-        off = torch.tensor([[k & 1, (k >> 1) & 1, (k >> 2) & 1] for k in range(8)], device=dev)
-        for l in range(1, self.num_lods):
-            v0, v1 = self.lod_offset[l], self.lod_offset[l + 1]
-            tr = self.trinkets[v0:v1].long()
-            par = self.parents[v0:v1].long()
-            vox = self.voxels[v0:v1, :3].long()
-            pvox = self.voxels[par, :3].long()
-            ptr = self.trinkets[par].long()                               # parent's 8 corner rows (already summed)
-            pval = out[ptr]                                               # [nv, 8, F]
-            for k in range(8):
-                f = ((vox + off[k]) - 2 * pvox).float() * 0.5             # position of corner k in the parent, in {0, .5, 1}^3
-                g = 1.0 - f
-                acc = 0
-                for j in range(8):
-                    w = (f[:, 0] if j & 1 else g[:, 0]) * (f[:, 1] if j & 2 else g[:, 1]) * (f[:, 2] if j & 4 else g[:, 2])
-                    acc = acc + w.unsqueeze(1) * pval[:, j]
-                out[tr[:, k]] = cf[tr[:, k]] + acc
-        return out
+        """Prefix-summed corner rows (nglod_sparse_net_t.corner_feats_summed), see summed_corner_rows."""
+        return summed_corner_rows(self.corner_feats.data, self.trinkets, self.parents, self.voxels, self.lod_offset, self.num_lods)
 
     def struct(self):
         # inference (eval mode, no autograd): sample ONE level from the prefix-summed rows, rebuilt when the features change

@@ -393,6 +393,24 @@ def test_neural_spc_fused_loss_backward_equals_autograd(pos_invariant):
     # accumulates: a second call doubles the gradient
     net.loss_backward(x, gt, lods=lods)
     assert (net.corner_feats.grad - 2 * ref["corner_feats"]).abs().max() / ref["corner_feats"].abs().max() < 6e-4
+    # points outside the octree (SPC.query -> -1) are inert rows: no table is read for them, they add no loss and no
+    # gradient (the reference's Python indexing would wrap to the last voxel; reading trinkets[-8..] is not an option)
+    xo = torch.cat([x, torch.rand(999, 3, device="cuda") * 0.02 - 0.01])          # the shell's centre: unoccupied
+    gto = torch.cat([gt, torch.zeros(999, 1, device="cuda")])
+    assert (net.query(xo[-999:], 2) < 0).all()
+    d_in = net.sdf(x, 2)
+    d_all = net.sdf(xo, 2)
+    assert torch.equal(d_all[:x.shape[0]], d_in) and (d_all[x.shape[0]:] == 0).all()
+    for p in net.parameters():
+        p.grad = None
+    losses_o = net.loss_backward(xo, gto, lods=lods, global_batch=x.shape[0])
+    for a, b in zip(losses_o.tolist(), ref_losses):
+        assert abs(a - b) < 1e-5 * max(1.0, abs(b))
+    assert (net.corner_feats.grad - ref["corner_feats"]).abs().max() / ref["corner_feats"].abs().max() < 3e-4
+    for p in net.parameters():
+        p.grad = None
+    ((net.sdf(xo, 2) - gto) ** 2).sum().backward()                                   # autograd path, same guard
+    assert torch.isfinite(net.corner_feats.grad).all()
 
 
 @pytest.mark.gpu
@@ -438,3 +456,72 @@ def test_neural_spc_trains_and_traces():
         x2, depth2, hit2, normal2, _ = net.trace(ro.cuda(), rd.cuda(), 2)
     assert (a - b).abs().max() < 2e-6
     assert int((hit2 != hit).sum()) <= 2
+
+
+# ------------------------------------------------------------------------------------------------ sparse model file (f2)
+def test_sparse_model_file_roundtrip_tables(fit3, tmp_path):
+    """SparseOctreeSDF.save -> .load (the real-time renderer's npz, SOL_NGLOD.py:80-100 / SDF.cu:65-216): the tables the
+    reader re-derives from `cc` are the writer's tables; features and decoders come back as their fp16 roundings."""
+    net, args, spc, sp = _fit3_sparse(fit3, "cpu")
+    path = str(tmp_path / "torus3.npz")
+    sp.save(path)
+    z = np.load(path)
+    assert z["cc"].dtype == np.uint8 and z["cf"].dtype == np.float16 and z["w0"].dtype == np.float16
+    assert z["octree"].dtype == np.uint8 and z["pyramid"].shape == (3,) and z["w0"].shape == (3, 128, 35)
+    sp2 = S.SparseOctreeSDF.load(path, device="cpu")
+    assert sp2.num_lods == 3 and sp2.base_lod == 2 and sp2.lod_offset == sp.lod_offset
+    assert torch.equal(sp2.trinkets, sp.trinkets) and torch.equal(sp2.parents, sp.parents)
+    assert torch.equal(sp2.voxels, sp.voxels) and torch.equal(sp2.spc.octree, spc.octree)
+    assert torch.equal(sp2.corner_feats, sp.corner_feats.half().float())
+    for i in range(3):
+        for a, b in zip(sp2._decoder_params(i), net.decoder_params(i)):
+            assert torch.equal(a, b.detach().half().float())
+    # a file whose corner table does not cover the octree is rejected
+    bad = dict(z)
+    bad["cc"] = bad["cc"].copy()
+    bad["cc"][5] = [255, 255, 255]
+    np.savez_compressed(str(tmp_path / "bad.npz"), **bad)
+    with pytest.raises(ValueError):
+        S.SparseOctreeSDF.load(str(tmp_path / "bad.npz"), device="cpu")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("math_mode", ["fp32", "tc"])
+def test_sparse_model_file_save_load_trace_identity(fit5, tmp_path, math_mode):
+    """fit5's weights are fp16-exact, so the file holds exactly the model that wrote it: the loaded model traces the same
+    frame bit for bit (x, depth, hit, normal, last voxel) and evaluates the same sdf."""
+    from helpers import fit5_model, torus_sdf
+    net, args = fit5_model(fit5, "cuda")
+    net.math_mode = math_mode
+    level = 6
+    n = 1 << level
+    ax = torch.arange(n)
+    g = torch.stack(torch.meshgrid(ax, ax, ax, indexing="ij"), dim=-1).reshape(-1, 3)
+    lo = g.float() / n * 2 - 1
+    d = torch.stack([torus_sdf(lo + torch.tensor([i >> 2, (i >> 1) & 1, i & 1]).float() * (2.0 / n)) for i in range(8)], 0)
+    occ = (d.min(0)[0] <= 0.01) & (d.max(0)[0] >= -0.01)
+    spc = S.SPC(S.points_to_octree(g[occ], level).cuda())
+    sp = S.SparseOctreeSDF(net, spc)
+    sp.math_mode = math_mode
+    path = str(tmp_path / "torus5.npz")
+    sp.save(path)
+    sp2 = S.SparseOctreeSDF.load(path, device="cuda", math_mode=math_mode)
+    assert torch.equal(sp2.corner_feats, sp.corner_feats) and torch.equal(sp2.trinkets, sp.trinkets)
+    torch.manual_seed(9)
+    ro, rd = O.look_at([-2.8, 2.8, -2.8], [0, 0, 0], 320, 180, fov=30.0)
+    for lod in (4, 2):
+        a = sp.trace(ro.cuda(), rd.cuda(), lod)
+        b = sp2.trace(ro.cuda(), rd.cuda(), lod)
+        assert int(a[2].sum()) > 3000
+        for u, v in zip(a, b):
+            assert torch.equal(u, v)
+        x, pidx = _points_in_voxels(spc, lod + 2, 5000, 3)
+        assert torch.equal(sp.sdf(x.cuda(), lod, pidx.cuda()), sp2.sdf(x.cuda(), lod, pidx.cuda()))
+    # points outside every voxel (pidx = -1): inert rows, no out-of-bounds table reads (ADVICE r1)
+    x, pidx = _points_in_voxels(spc, 6, 1000, 5)
+    pidx = pidx.clone()
+    pidx[::3] = -1
+    out = sp2.sdf(x.cuda(), 4, pidx.cuda())
+    assert (out[::3] == 0).all() and torch.isfinite(out).all()
+    ok = pidx >= 0
+    assert torch.equal(out[ok], sp2.sdf(x[ok].cuda(), 4, pidx[ok].cuda()))
