@@ -421,6 +421,7 @@ sdf_backward_mma_kernel(const NetDev net, const GradDev grad, const float* __res
             if (active) pv = __ldg(sp.pidx + i);
             active = active && pv >= 0;
         }
+        const unsigned live_rows = __ballot_sync(0xffffffffu, active);
         float px = 0.f, py = 0.f, pz = 0.f;
         if (active) { px = __ldg(x + 3 * i); py = __ldg(x + 3 * i + 1); pz = __ldg(x + 3 * i + 2); }
         // ---- A: gather
@@ -520,18 +521,21 @@ sdf_backward_mma_kernel(const NetDev net, const GradDev grad, const float* __res
                 }
             }
             // d of the two rows (sum over the 4 lanes that share a row), upstream gradients
-            const long long iA = rA < lpw ? base0 + warp * lpw + rA : n, iB = rB < lpw ? base0 + warp * lpw + rB : n;
+            const long long iA = base0 + warp * lpw + rA, iB = base0 + warp * lpw + rB;
+            // a row takes part iff its lane is active (in range and, on the sparse path, inside the octree): inert rows add
+            // no loss, no upstream gradient, hence no parameter gradient
+            const bool okA = (live_rows >> rA) & 1u, okB = (live_rows >> rB) & 1u;
             float gdA = 0.f, gdB = 0.f;
             if (FUSED_LOSS) {
                 dA += __shfl_xor_sync(0xffffffffu, dA, 1); dA += __shfl_xor_sync(0xffffffffu, dA, 2);
                 dB += __shfl_xor_sync(0xffffffffu, dB, 1); dB += __shfl_xor_sync(0xffffffffu, dB, 2);
-                if (iA < n) { const float diff = (dA + sb1) - __ldg(gt + iA); gdA = 2.f * diff * loss_scale;
-                              if (t == 0) acc_loss = fmaf(diff * diff, loss_scale, acc_loss); }
-                if (iB < n) { const float diff = (dB + sb1) - __ldg(gt + iB); gdB = 2.f * diff * loss_scale;
-                              if (t == 0) acc_loss = fmaf(diff * diff, loss_scale, acc_loss); }
+                if (okA) { const float diff = (dA + sb1) - __ldg(gt + iA); gdA = 2.f * diff * loss_scale;
+                           if (t == 0) acc_loss = fmaf(diff * diff, loss_scale, acc_loss); }
+                if (okB) { const float diff = (dB + sb1) - __ldg(gt + iB); gdB = 2.f * diff * loss_scale;
+                           if (t == 0) acc_loss = fmaf(diff * diff, loss_scale, acc_loss); }
             } else {
-                if (iA < n) gdA = __ldg(grad_out + iA);
-                if (iB < n) gdB = __ldg(grad_out + iB);
+                if (okA) gdA = __ldg(grad_out + iA);
+                if (okB) gdB = __ldg(grad_out + iB);
             }
             if (t == 0) { acc_b1 += gdA + gdB; sgd[rA] = gdA; sgd[rB] = gdB; }
             // ReLU mask words for phase C: word w = hidden [32w, 32w+32); this lane holds the bit pairs (2t, 2t+1) of

@@ -554,8 +554,8 @@ class NeuralSPC(torch.nn.Module, SparseOctreeSDF):
         d = sdf(x, lod), adds sum((d - gt)^2) / global_batch to the loss and accumulates dL/d(corner_feats) and
         dL/d(decoder of that head) into the parameters' `.grad` (nglod_sparse_sdf_train_step) -- what
         `sum(((net.sdf(x, l) - gt) ** 2).sum() for l in lods) / B` followed by `.backward()` computes through autograd,
-        minus the separate forward launch, the loss kernels and the saved tensors.  Points outside the octree (pidx < 0)
-        must be filtered by the caller, as for `sdf`.  Returns the per-head losses [len(lods)]."""
+        minus the separate forward launch, the loss kernels and the saved tensors.  Points outside the octree (pidx < 0) are
+        inert rows: they add no loss and no gradient (and `sdf` returns 0 for them).  Returns the per-head losses [len(lods)]."""
         lods = list(range(self.num_lods)) if lods is None else list(lods)
         lib = _lib.load()
         xx = _f32c(x, "x")
