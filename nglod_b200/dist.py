@@ -32,6 +32,34 @@ def init_from_env(backend=None):
     return rank, world, local
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Best effort: pin this process to the CPU cores of the NUMA node its GPU hangs off, BEFORE it page-locks host
+    buffers (first touch places the pages).  With one process per GPU the eight ranks of a box otherwise allocate
+    their pinned frame buffers wherever the launcher left them, and every D2H copy crosses the socket interconnect.
+    Returns the node id, or None when the topology cannot be read (then nothing is changed)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local_rank)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:                       # 00000000:1b:00.0 -> 0000:1b:00.0
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
 def shard_range(n, rank, world, align=1):
     """[start, end) of the contiguous shard `rank` of `n` items; boundaries are multiples of `align`
     (use align=H to cut an x-major image on column boundaries).  Shards differ by at most one `align` unit."""
@@ -75,6 +103,31 @@ def gather_shards(local, n_total, rank, world, dst=0, align=1):
     if rank != dst:
         return None
     return torch.cat([b[: e - s] for b, (s, e) in zip(bufs, sizes)], dim=0)
+
+
+def gather_strips(local, strips_by_rank, rows_per_col, rank, world, dst=0):
+    """Final gather of a frame rendered in interleaved column strips (interleaved_strips): `local` holds this rank's
+    strips back to back ([cols_local * rows_per_col, C], x-major like the rays); rank `dst` gets the whole frame
+    [total_cols * rows_per_col, C] in image order, the others None.  One NCCL gather of equal-size padded buffers."""
+    if world == 1 or not dist.is_initialized():
+        return local
+    cols = [sum(c1 - c0 for c0, c1 in s) for s in strips_by_rank]
+    longest = max(cols) * rows_per_col
+    pad = torch.zeros((longest,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    bufs = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+    dist.gather(pad, bufs, dst=dst)
+    if rank != dst:
+        return None
+    total = sum(cols)
+    full = torch.empty((total * rows_per_col,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    for r in range(world):
+        pos = 0
+        for c0, c1 in strips_by_rank[r]:
+            nrow = (c1 - c0) * rows_per_col
+            full[c0 * rows_per_col:c1 * rows_per_col] = bufs[r][pos:pos + nrow]
+            pos += nrow
+    return full
 
 
 def max_over_ranks(value, device):

@@ -45,17 +45,74 @@ class SphereTracer(BaseTracer):
         +40 % (measured).  3 ranges on 2 streams measured best for a 720p frame (profiles/exp_e2e_chunks.py); `fractions`
         gives explicit cumulative split points instead of equal ranges.  Returns a RenderBuffer of CPU tensors (`out`, if given, is reused: a dict
         with pinned x [N,3], depth [N,1], hit [N] bool, normal [N,3]).  Synchronises before returning."""
-        if not (_is_octree(net) and self.grad_method == "finitediff" and getattr(net, "interpolate", None) is None):
-            raise RuntimeError("trace_host: only the fused OctreeSDF tracer has a pipelined host path")
         if ray_o.is_cuda or ray_d.is_cuda:
             raise RuntimeError("trace_host: ray_o / ray_d are expected in host memory (use forward() for device tensors)")
-        dev = next(net.parameters()).device
         n = ray_o.shape[0]
         ray_o = ray_o.contiguous().float()
         ray_d = ray_d.contiguous().float()
+
+        def stage(ws, bounds, s_in):
+            evs = []
+            with torch.cuda.stream(s_in):
+                for a, b in zip(bounds[:-1], bounds[1:]):
+                    ws["o"][a:b].copy_(ray_o[a:b], non_blocking=True)
+                    ws["d"][a:b].copy_(ray_d[a:b], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(s_in)
+                    evs.append(ev)
+            return evs
+        return self._host_pipeline(net, n, stage, out, ("x", "depth", "hit", "normal"), chunks, streams, fractions)
+
+    def trace_lookat_host(self, net, f, t, width, height, fov=30.0, mode="persp", window=None, out=None,
+                          fields=("depth", "hit", "normal"), chunks=3, streams=2):
+        """The camera-driven host call: what `Renderer.render_lookat` + `.cpu()` amounts to for a user of the reference
+        (renderer.py:89-107: rays come from `look_at(f, t, W, H, fov)`, never from host ray buffers).  Inputs are the
+        camera pose (host floats) and the jittered window coordinates `window = (wx [W], wy [H])` in pinned host memory
+        (None: drawn on the device as `look_at` does); the W*H rays are generated on the device (nglod_generate_rays,
+        x-major like the reference), traced in `chunks` ranges on alternating streams, and the requested RenderBuffer
+        `fields` (any of x, depth, hit, normal) are copied into pinned host memory as each range finishes.
+        Per frame over PCIe: (W + H) * 4 bytes up, 17 B/ray down for the default fields (no ray upload, no `x`)."""
+        import numpy as np
+        from ..geoutils import _window
+        dev = next(net.parameters()).device
+        n = width * height
+        origin = torch.tensor(list(f), dtype=torch.float32)
+        view = F.normalize(torch.tensor(list(t), dtype=torch.float32) - origin, dim=0)
+        right = F.normalize(torch.linalg.cross(view, torch.tensor([0.0, 1.0, 0.0])), dim=0)
+        up = F.normalize(torch.linalg.cross(right, view), dim=0)
+        tan = np.float32(np.tan(np.radians(fov / 2)))
+
+        def stage(ws, bounds, s_in):
+            with torch.cuda.stream(s_in):
+                if window is None:
+                    with torch.cuda.device(dev):
+                        wx, wy = _window(width, height, dev)
+                else:
+                    if "wx" not in ws or ws["wx"].shape[0] != width or ws["wy"].shape[0] != height:
+                        ws["wx"], ws["wy"] = torch.empty(width, device=dev), torch.empty(height, device=dev)
+                    ws["wx"].copy_(window[0], non_blocking=True)
+                    ws["wy"].copy_(window[1], non_blocking=True)
+                    wx, wy = ws["wx"], ws["wy"]
+                ops.generate_rays(origin.tolist(), view.tolist(), right.tolist(), up.tolist(), tan, mode == "ortho", wx, wy,
+                                  out=(ws["o"], ws["d"]))
+                ev = torch.cuda.Event()
+                ev.record(s_in)
+            return [ev] * (len(bounds) - 1)
+        return self._host_pipeline(net, n, stage, out, tuple(fields), chunks, streams, None)
+
+    def _host_pipeline(self, net, n, stage, out, fields, chunks, streams, fractions):
+        """Shared body of trace_host / trace_lookat_host: `stage(ws, bounds, s_in)` puts the rays of every range into the
+        device workspace (ws["o"], ws["d"]) on stream s_in and returns one event per range."""
+        if not (_is_octree(net) and self.grad_method == "finitediff" and getattr(net, "interpolate", None) is None):
+            raise RuntimeError("trace_host: only the fused OctreeSDF tracer has a pipelined host path")
+        dev = next(net.parameters()).device
+        shapes = {"x": ((n, 3), torch.float32), "depth": ((n, 1), torch.float32), "hit": ((n,), torch.bool),
+                  "normal": ((n, 3), torch.float32)}
+        for k in fields:
+            if k not in shapes:
+                raise ValueError(f"unknown RenderBuffer field {k!r}")
         if out is None:
-            out = {"x": torch.empty(n, 3).pin_memory(), "depth": torch.empty(n, 1).pin_memory(),
-                   "hit": torch.empty(n, dtype=torch.bool).pin_memory(), "normal": torch.empty(n, 3).pin_memory()}
+            out = {k: torch.empty(shapes[k][0], dtype=shapes[k][1]).pin_memory() for k in fields}
         ws = getattr(self, "_host_ws", None)
         if ws is None or ws["n"] != n or ws["dev"] != dev:
             ws = {"n": n, "dev": dev,
@@ -80,15 +137,7 @@ class SphereTracer(BaseTracer):
             bounds = [(n * i) // chunks for i in range(chunks + 1)]
         if ws["queue"].numel() < chunks:
             ws["queue"] = torch.empty(chunks, dtype=torch.int32, device=dev)
-        ev_in = []
-        with torch.cuda.stream(s_in):
-            for i in range(chunks):
-                a, b = bounds[i], bounds[i + 1]
-                ws["o"][a:b].copy_(ray_o[a:b], non_blocking=True)
-                ws["d"][a:b].copy_(ray_d[a:b], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(s_in)
-                ev_in.append(ev)
+        ev_in = stage(ws, bounds, s_in)
         for i in range(chunks):
             a, b = bounds[i], bounds[i + 1]
             if b == a:
@@ -104,10 +153,10 @@ class SphereTracer(BaseTracer):
             ev.record(sc)
             s_out.wait_event(ev)
             with torch.cuda.stream(s_out):
-                for k in ("x", "depth", "hit", "normal"):
+                for k in fields:
                     out[k][a:b].copy_(ws[k][a:b], non_blocking=True)
         s_out.synchronize()             # every range's results are in host memory; all streams are idle again
-        return RenderBuffer(x=out["x"], depth=out["depth"], hit=out["hit"], normal=out["normal"])
+        return RenderBuffer(**{k: out[k] for k in fields})
 
     def get_min(self, net, ray_o, ray_d):
         """Min-distance variant (reference :134-218): the aabb mask is discarded, the live mask is

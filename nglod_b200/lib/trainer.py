@@ -5,8 +5,11 @@ checkpoint naming are the caller's business.
 FusedTrainer keeps ALL parameters in one flat fp32 buffer (each nn.Parameter is a view into it; grids stay
 channels-last), with a matching flat gradient buffer and flat Adam moments:
   * step = zero the flat gradient, one fused forward+loss+backward launch per loss LOD writing straight into
-    the gradient views (no autograd graph, no saved activations), ONE all-reduce over the flat buffer when
-    data-parallel, one Adam kernel over the flat buffer;
+    the gradient views (no autograd graph, no saved activations), then -- data-parallel -- the optimiser is SHARDED:
+    reduce-scatter of the flat gradient (each rank receives the sum of its 1/N slice), the Adam kernel over that
+    slice only (moments exist only for it), all-gather of the updated parameters.  Same bytes over NVLink as one
+    all-reduce, 1/N of the optimiser's HBM traffic and state per rank; `shard_optimizer=False` keeps the replicated
+    all-reduce + full Adam;
   * loss = sum_{lod in loss_lods} sum_i (sdf_lod(x_i) - gt_i)^2 / global_batch        (trainer.py:325-336);
   * small batches (the reference trains with --batch-size 512) are launch-bound: ~20 launches and ~0.4 ms of Python per
     step against ~0.2 ms of GPU work.  Everything up to the all-reduce is therefore captured ONCE per (batch size, loss
@@ -21,7 +24,7 @@ from .. import dist as ndist
 
 class FusedTrainer:
     def __init__(self, net, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, loss_lods=None, use_graph=True,
-                 graph_max_batch=131072, summed_min_batch=32768):
+                 graph_max_batch=131072, summed_min_batch=32768, shard_optimizer=True):
         self.net = net
         self.use_graph, self.graph_max_batch, self.summed_min_batch = use_graph, graph_max_batch, summed_min_batch
         self._graphs = {}
@@ -33,14 +36,25 @@ class FusedTrainer:
             raise RuntimeError("FusedTrainer needs the model on a CUDA device (no CPU path)")
         sizes = [((p.numel() + 3) // 4) * 4 for p in params]          # keep every view 16-byte aligned
         total = sum(sizes)
+        self.world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
+        self.rank = torch.distributed.get_rank() if self.world > 1 else 0
+        self.sharded = bool(shard_optimizer) and self.world > 1
+        if self.sharded:                                               # equal 16-byte aligned slices
+            total = ((total + 4 * self.world - 1) // (4 * self.world)) * (4 * self.world)
         self.flat = torch.zeros(total, device=dev)
         self.flat_grad = torch.zeros(total, device=dev)
-        self.exp_avg = torch.zeros(total, device=dev)
-        self.exp_avg_sq = torch.zeros(total, device=dev)
+        self.shard_len = total // self.world if self.sharded else total
+        self.shard_off = self.rank * self.shard_len if self.sharded else 0
+        self.grad_shard = torch.zeros(self.shard_len, device=dev) if self.sharded else self.flat_grad
+        self.exp_avg = torch.zeros(self.shard_len, device=dev)          # moments only for the slice this rank updates
+        self.exp_avg_sq = torch.zeros(self.shard_len, device=dev)
         self.step_count = 0
+        self.comm_ms = None                                            # set by step(time_comm=True)
         off = 0
         self._grad_views = {}
+        self._param_ranges = []                                        # (parameter, offset, padded length) in the flat buffers
         for p, sz in zip(params, sizes):
+            self._param_ranges.append((p, off, sz))
             n = p.numel()
             if p.dim() == 5:      # feature grid: logical [1,F,D,H,W], physical channels-last [D,H,W,F]
                 _, f, d, h, w = p.shape
@@ -108,6 +122,49 @@ class FusedTrainer:
             torch.cuda.synchronize(pts.device)
             return False
 
+    def _trainable_ranges(self):
+        """[start, end) runs of the flat buffers that belong to parameters with requires_grad=True (merged).  Frozen
+        parameters (`net.freeze()`, `--freeze`, trainer.py:247-251) get no Adam update -- torch.optim skips parameters
+        without a gradient; with NOTHING left to train the step raises like `loss.backward()` does in the reference."""
+        key = tuple(p.requires_grad for p, _, _ in self._param_ranges)
+        if getattr(self, "_ranges_key", None) != key:
+            runs = []
+            for p, off, sz in self._param_ranges:
+                if p.requires_grad:
+                    if runs and runs[-1][1] == off:
+                        runs[-1][1] = off + sz
+                    else:
+                        runs.append([off, off + sz])
+            self._ranges_key, self._ranges = key, [tuple(r) for r in runs]
+        if not self._ranges:
+            raise RuntimeError("FusedTrainer.step: no parameter requires grad (the network is frozen)")
+        return self._ranges
+
+    def _adam(self, lo, hi, base):
+        """Adam over flat[lo:hi); `base` = flat offset of element 0 of the gradient / moment buffers in use."""
+        ops.adam_step(self.flat[lo:hi], self.grad_shard[lo - base:hi - base], self.exp_avg[lo - base:hi - base],
+                      self.exp_avg_sq[lo - base:hi - base], self.step_count, lr=self.lr, beta1=self.betas[0],
+                      beta2=self.betas[1], eps=self.eps)
+
+    def _reduce_and_update(self):
+        """Gradient exchange + Adam.  Replicated: all-reduce(flat gradient), Adam over everything.  Sharded: reduce-scatter,
+        Adam over this rank's slice, all-gather of the parameters."""
+        dist = torch.distributed
+        runs = self._trainable_ranges()
+        self.step_count += 1
+        if self.sharded:
+            dist.reduce_scatter_tensor(self.grad_shard, self.flat_grad, op=dist.ReduceOp.SUM)
+            s0, s1 = self.shard_off, self.shard_off + self.shard_len
+            for lo, hi in runs:
+                lo, hi = max(lo, s0), min(hi, s1)
+                if hi > lo:
+                    self._adam(lo, hi, s0)
+            dist.all_gather_into_tensor(self.flat, self.flat[s0:s1].clone())
+        else:
+            ndist.allreduce_sum_(self.flat_grad)
+            for lo, hi in runs:
+                self._adam(lo, hi, 0)
+
     def step(self, pts, gts, global_batch=None, loss_lods=None):
         """One optimisation step on this rank's slice (pts [B,3], gts [B,1] on the device).
         Returns the device scalar holding this rank's share of the loss (already divided by global_batch);
@@ -127,10 +184,7 @@ class FusedTrainer:
             g["graph"].replay()
         else:
             self._compute_grads(pts, gts, batch, lods)
-        ndist.allreduce_sum_(self.flat_grad)
-        self.step_count += 1
-        ops.adam_step(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count, lr=self.lr,
-                      beta1=self.betas[0], beta2=self.betas[1], eps=self.eps)
+        self._reduce_and_update()
         net.mark_grids_dirty()      # the Adam kernel writes the parameters behind torch's version counters
         return self.loss
 

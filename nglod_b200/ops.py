@@ -333,13 +333,20 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, step, lr=1e-3, beta1=0.9, beta2=
 
 
 # --------------------------------------------------------------------------- renderer helpers
-def generate_rays(origin, view, right, up, tan_half_fov, ortho, window_x, window_y):
-    """[W*H,3] ray origins / directions (x-major) from a camera basis (host 3-vectors) and device window coordinates."""
+def generate_rays(origin, view, right, up, tan_half_fov, ortho, window_x, window_y, out=None):
+    """[W*H,3] ray origins / directions (x-major) from a camera basis (host 3-vectors) and device window coordinates.
+    out=(ray_o, ray_d): caller-provided contiguous fp32 device buffers."""
     lib = _lib.load()
     w, h = window_x.shape[0], window_y.shape[0]
     dev = window_x.device
-    ray_o = torch.empty(w * h, 3, device=dev, dtype=torch.float32)
-    ray_d = torch.empty(w * h, 3, device=dev, dtype=torch.float32)
+    if out is None:
+        ray_o = torch.empty(w * h, 3, device=dev, dtype=torch.float32)
+        ray_d = torch.empty(w * h, 3, device=dev, dtype=torch.float32)
+    else:
+        ray_o, ray_d = out
+        for t_ in (ray_o, ray_d):
+            if tuple(t_.shape) != (w * h, 3) or t_.dtype != torch.float32 or t_.device != dev or not t_.is_contiguous():
+                raise RuntimeError("generate_rays: out buffers must be contiguous fp32 [W*H,3] tensors on the window's device")
     vec = [(ctypes.c_float * 3)(*[float(c) for c in v]) for v in (origin, view, right, up)]
     with torch.cuda.device(dev):
         _lib.check(lib.nglod_generate_rays(vec[0], vec[1], vec[2], vec[3], float(tan_half_fov), 1 if ortho else 0,

@@ -37,6 +37,17 @@ def _worker(rank, world, port, q):
     out = nd.gather_shards(torch.arange(s, e).float().unsqueeze(1), 7, rank, world)
     if rank == 0:
         assert out[:, 0].tolist() == [0, 1, 2, 3, 4, 5, 6]
+    # a frame rendered in interleaved column strips, gathered back into image order on rank 0
+    ncols, h2 = 37, 5
+    strips = [nd.interleaved_strips(ncols, r, world, strips_per_rank=3) for r in range(world)]
+    assert sorted(c for s_ in strips for c0, c1 in s_ for c in range(c0, c1)) == list(range(ncols))
+    frame = torch.arange(ncols * h2, dtype=torch.float32).reshape(-1, 1)
+    mine = torch.cat([frame[c0 * h2:c1 * h2] for c0, c1 in strips[rank]]) + 0.5
+    got = nd.gather_strips(mine, strips, h2, rank, world, dst=0)
+    if rank == 0:
+        assert torch.equal(got, frame + 0.5)
+    else:
+        assert got is None
     # data-parallel gradient: each rank contributes its slice's gradient, scaled by the GLOBAL batch
     g = torch.full((10,), float(rank + 1))
     nd.allreduce_sum_(g)

@@ -82,3 +82,32 @@ def test_train_checkpoint_export_roundtrip():
         cc0 = torch.from_numpy(z["cc"][:n0].astype(np.int64))
         fm0 = tr.net.features[0].fm.detach().cpu()
         assert np.array_equal(z["cf"][:n0], fm0[0][:, cc0[:, 2], cc0[:, 1], cc0[:, 0]].t().half().numpy())
+
+
+@pytest.mark.gpu
+def test_fused_trainer_respects_requires_grad():
+    """`net.freeze()` / requires_grad=False (reference: BaseSDF.freeze, trainer.py:247-251): frozen parameters get no Adam
+    update -- not even from stale momentum --, the others keep training; a fully frozen network raises like
+    `loss.backward()` does in the reference."""
+    from nglod_b200.lib.trainer import FusedTrainer
+    from nglod_b200.lib.models import OctreeSDF
+    torch.manual_seed(0)
+    net = OctreeSDF(make_args(["--num-lods", "3"])).cuda()
+    tr = FusedTrainer(net, lr=1e-2)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.rand(70001, 3, device="cuda", generator=g) * 2 - 1
+    gt = (x.norm(dim=1, keepdim=True) - 0.5)
+    for _ in range(3):
+        tr.step(x, gt)                                              # builds momentum everywhere
+    for f in net.features:
+        f.fm.requires_grad_(False)                                  # freeze the grids, keep the decoders
+    grids = [f.fm.detach().clone() for f in net.features]
+    w = net.louts[2][0].weight.detach().clone()
+    for _ in range(2):
+        tr.step(x, gt)
+    for f, before in zip(net.features, grids):
+        assert torch.equal(f.fm.detach(), before)
+    assert not torch.equal(net.louts[2][0].weight.detach(), w)
+    net.freeze()
+    with pytest.raises(RuntimeError):
+        tr.step(x, gt)
