@@ -4,12 +4,16 @@
   python bench.py --gpus 1 --steps 20 --warmup 3
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
          bench.py --gpus N --steps K --warmup W
-  python bench.py --impl reference ...      # the reference's CPU path (oracle port) on the host cores
+  python bench.py --impl reference ...      # the UNMODIFIED reference's CPU path on the box's host cores
 
 Workload (BASELINE.json configs[1]): SphereTracer.forward over a 1280x720 perspective frame at lod 4 of a 5-LOD
-OctreeSDF (feature-dim 32, hidden 128) fitted IN-RUN to a procedural torus mesh (mesh2sdf-labelled samples).
-A "step" is one full frame (921 600 rays) per GPU; with N GPUs every rank traces its own frame (a different
-camera azimuth), no data-path collective -> "scaling": "weak"; value = N * 921600 / max-over-ranks time.
+OctreeSDF (feature-dim 32, hidden 128) fitted IN-RUN to a torus.  Both arms trace the SAME net and the SAME rays: the fit
+is a seeded plain-torch Adam fit (no kernel of this repo, nothing from oracle/) whose result is cached in
+baseline/_fit_cache.pt by whichever arm runs first on the box; the rays come from look_at on the host under one seed.
+A "step" is one full frame (921 600 rays) per GPU; with N GPUs every rank traces its own frame (a different camera
+azimuth), no data-path collective -> "scaling": "weak"; value = N * 921600 / max-over-ranks time.  The partitionings
+north_star names (one 4K frame in screen strips with the final gather; the data-parallel training step with its gradient
+exchange) are strong-scaling measurements and ride along under "strong_scaling" at every N.
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
 """
 import argparse
@@ -32,7 +36,7 @@ W, H = 1280, 720
 LOD = 4
 NUM_LODS = 5
 CAM_FROM, CAM_TO, FOV = [-2.8, 2.8, -2.8], [0.0, 0.0, 0.0], 30.0
-FIT_STEPS, FIT_BATCH = 300, 65536
+FIT_STEPS, FIT_BATCH, FIT_SEED = 300, 65536, 7
 SDF_N = 1 << 20
 MATH_MODE = os.environ.get("NGLOD_MATH", "tc")      # "tc" = tcgen05 3xTF32 decoder, "fp32" = CUDA cores
 GRID_STORAGE = os.environ.get("NGLOD_GRID_STORAGE", "fp32")   # "fp32" (headline) | "fp16" x-pair lines (extras)
@@ -44,11 +48,27 @@ GATHER_BYTES_PER_QUERY_PER_LOD = (LOD + 1) * 8 * 32 * 4
 GATHER_BYTES_PER_QUERY = 8 * 32 * 4 if SUM_LODS else GATHER_BYTES_PER_QUERY_PER_LOD
 IO_BYTES_PER_QUERY = 16
 RAY_IO_BYTES = 24 + 12 + 4 + 1 + 12                        # ray_o, ray_d in; x, depth, hit, normal out
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE sphere_trace_kernel / sdf_forward_tc_kernel launch (single-grid
-# fp32 instances), from the `ncu --set full` captures summarised in profiles/sphere_trace_sum_r1_v4.txt and
-# profiles/sdf_forward_sum_r1_v4.txt
-NCU_TRAFFIC_TRACE_BYTES = 38498048 + 2459392
-NCU_TRAFFIC_SDF_FWD_BYTES = 47828992 + 575744
+TENSOR_FLOP_PER_EVAL = 2 * 32 * 128 * 3                    # the tensor-eligible 32x128 contraction, 3 TF32 passes
+WORKLOAD = ("SphereTracer.forward 1280x720 persp fov30 lod4, OctreeSDF num-lods=5 feature-dim=32 hidden=128 fitted in-run "
+            "to a torus (BASELINE.json configs[1])")
+
+
+def fit_plan():
+    """(device, steps, batch, cache path) of the shared fit; the cache name carries the plan, so a fit made under another
+    plan (a CPU-only box, a test's shortened set-up) is never mistaken for this one."""
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    steps, batch = (FIT_STEPS, FIT_BATCH) if dev == "cuda" else (60, 8192)
+    steps = int(os.environ.get("NGLOD_FIT_STEPS", steps))               # tests shrink the (untimed) set-up
+    return dev, steps, batch, os.path.join(ROOT, "baseline", f"_fit_cache_{dev}_s{steps}_b{batch}_seed{FIT_SEED}.pt")
+
+
+def shared_config(world):
+    """The `config` both arms print (identical by construction: same workload, same net, same rays)."""
+    return {"workload": WORKLOAD, "rays_per_gpu_step": W * H, "num_steps": 256, "lod": LOD,
+            "fit": "seeded plain-torch Adam fit ({} steps x {} points), analytic torus SDF labels, shared between the arms "
+                   "through baseline/_fit_cache*.pt".format(*fit_plan()[1:3]),
+            "rays": "look_at([-2.8,2.8,-2.8] rotated about y by 360*rank/N, [0,0,0], 1280, 720, fov 30) on the host, seed 1000+rank",
+            "l2": "flushed between timed iterations (256 MB memset)", "parallelism": f"one frame per GPU x{world}, no collective"}
 
 
 def load_peaks():
@@ -56,10 +76,21 @@ def load_peaks():
     if os.path.exists(p):
         try:
             j = json.load(open(p))
-            return float(j["hbm_gbs"]), "measured"
+            return float(j["hbm_gbs"]), float(j.get("bf16_tflops_sustained", 1400.9)), "measured"
         except Exception:  # noqa: BLE001
             pass
-    return 6650.0, "fallback"
+    return 6650.0, 1400.0, "fallback"
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed `ncu --set full` summary
+    (profiles/ncu_traffic.json, written by profiles/ncu_traffic.py from the .ncu-rep of the same build); None if absent."""
+    try:
+        j = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        e = j[kernel]
+        return int(e["dram_bytes_read"]) + int(e["dram_bytes_write"])
+    except Exception:  # noqa: BLE001
+        return None
 
 
 # ----------------------------------------------------------------------------------------------- clocks
@@ -124,54 +155,144 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-# ----------------------------------------------------------------------------------------------- set-up
-def make_rays(device, azimuth_deg=0.0, seed=0):
-    """look_at rays for the 720p frame; the camera is rotated about y by `azimuth_deg` (rank-dependent)."""
-    from nglod_b200.lib.geoutils import look_at
+# ----------------------------------------------------------------------------------------------- shared set-up (both arms)
+def torch_reference_sdf_all(sd, x, num_lods):
+    """Plain-torch statement of OctreeSDF.sdf(x, return_lst=True) on a state_dict (F.grid_sample per LOD, running sum,
+    cat [x, feat], Linear-ReLU-Linear of each head; sdf-net/lib/models/OctreeSDF.py:46-57,94-153).  Used ONLY for the untimed
+    in-run fit, by both arms -- it calls no kernel of this repository and imports nothing from oracle/."""
+    import torch.nn.functional as F
+    grid = x.reshape(1, -1, 1, 1, 3)
+    feat = 0
+    outs = []
+    for l in range(num_lods):
+        s = F.grid_sample(sd[f"features.{l}.fm"], grid, align_corners=True, padding_mode="border")[0, :, :, 0, 0].t()
+        feat = feat + s
+        h = torch.relu(F.linear(torch.cat([x, feat], dim=-1), sd[f"louts.{l}.0.weight"], sd[f"louts.{l}.0.bias"]))
+        outs.append(F.linear(h, sd[f"louts.{l}.2.weight"], sd[f"louts.{l}.2.bias"]))
+    return outs
+
+
+def fit_shared(init_state_dict, log):
+    """The in-run fit both arms trace: seeded Adam (lr 1e-3) on all LOD heads (trainer.py:317-339's loss) against the
+    analytic torus SDF (R .6, r .25), half of every batch pulled near the surface like MeshDataset's near / trace modes.
+    Cached on disk so that the second arm on the same box traces bit-identical weights."""
+    dev, steps, batch, FIT_CACHE = fit_plan()
+    if os.path.exists(FIT_CACHE):
+        try:
+            sd = torch.load(FIT_CACHE, map_location="cpu")
+            if set(sd) == set(init_state_dict) and all(sd[k].shape == init_state_dict[k].shape for k in sd):
+                log(f"fit: loaded {FIT_CACHE} (fitted by the arm that ran first on this box)")
+                return sd, "cache"
+        except Exception:  # noqa: BLE001
+            pass
+    sd = {k: v.detach().clone().to(dev).contiguous().requires_grad_(True) for k, v in init_state_dict.items()}
+    opt = torch.optim.Adam(list(sd.values()), lr=1e-3)
+    g = torch.Generator(device=dev).manual_seed(FIT_SEED)
+    t0 = time.time()
+    last = 0.0
+    for _ in range(steps):
+        p = torch.rand(batch, 3, device=dev, generator=g) * 2 - 1
+        surf = p[: batch // 2]
+        q = torch.sqrt(surf[:, 0] ** 2 + surf[:, 2] ** 2)
+        ring = torch.stack([surf[:, 0] / q * 0.6, torch.zeros_like(q), surf[:, 2] / q * 0.6], dim=1)
+        dirv = torch.nn.functional.normalize(surf - ring, dim=1)
+        p = torch.cat([ring + dirv * (0.25 + 0.01 * torch.randn(batch // 2, 1, device=dev, generator=g)), p[batch // 2:]])
+        qq = torch.sqrt(p[:, 0] ** 2 + p[:, 2] ** 2) - 0.6
+        gt = (torch.sqrt(qq * qq + p[:, 1] ** 2) - 0.25).unsqueeze(1)
+        opt.zero_grad(set_to_none=True)
+        loss = sum(((d - gt) ** 2).sum() for d in torch_reference_sdf_all(sd, p, NUM_LODS)) / batch
+        loss.backward()
+        opt.step()
+        last = loss.detach()
+    out = {k: v.detach().cpu().contiguous() for k, v in sd.items()}
+    log(f"fit: {steps} Adam steps x {batch} pts on {dev} in {time.time() - t0:.1f}s, final loss {float(last):.3e}")
+    try:
+        os.makedirs(os.path.dirname(FIT_CACHE), exist_ok=True)
+        tmp = FIT_CACHE + f".{os.getpid()}"
+        torch.save(out, tmp)
+        os.replace(tmp, FIT_CACHE)
+    except Exception:  # noqa: BLE001
+        pass
+    return out, "fitted"
+
+
+def camera_from(azimuth_deg):
     a = math.radians(azimuth_deg)
-    f = [CAM_FROM[0] * math.cos(a) + CAM_FROM[2] * math.sin(a), CAM_FROM[1],
-         -CAM_FROM[0] * math.sin(a) + CAM_FROM[2] * math.cos(a)]
+    return [CAM_FROM[0] * math.cos(a) + CAM_FROM[2] * math.sin(a), CAM_FROM[1],
+            -CAM_FROM[0] * math.sin(a) + CAM_FROM[2] * math.cos(a)]
+
+
+def make_rays(device, azimuth_deg=0.0, seed=0):
+    """look_at rays for the 720p frame, generated ON THE HOST under torch.manual_seed(1000 + seed) so that both arms (and
+    the reference's own look_at, which draws the same torch.rand sequence) get the same rays; moved to `device`."""
+    from nglod_b200.lib.geoutils import look_at
     torch.manual_seed(1000 + seed)
-    return look_at(f, CAM_TO, W, H, mode="persp", fov=FOV, device=device)
+    o, d = look_at(camera_from(azimuth_deg), CAM_TO, W, H, mode="persp", fov=FOV, device="cpu")
+    return o.to(device).contiguous(), d.to(device).contiguous()
 
 
 def build_and_fit(device, log):
-    """5-LOD OctreeSDF fitted in-run to a procedural torus mesh: samples from the MeshDataset recipe
-    (rand/near/near/trace/trace), labels from the mesh2sdf kernel, fused training step + Adam kernel."""
+    """5-LOD OctreeSDF carrying the shared in-run fit (fit_shared), on `device`."""
     from nglod_b200.lib.options import parse_options
     from nglod_b200.lib.models import OctreeSDF
-    from nglod_b200.lib.datasets import MeshDataset
-    from nglod_b200.lib.trainer import FusedTrainer
-    from nglod_b200.lib.torchgp import torus
     args = parse_options(return_parser=True).parse_args(
         ["--net", "OctreeSDF", "--num-lods", str(NUM_LODS), "--feature-dim", "32", "--lod", str(LOD),
          "--render-res", str(W), str(H)])
     torch.manual_seed(0)
-    net = OctreeSDF(args).to(device)
+    net = OctreeSDF(args)
+    sd, how = fit_shared({k: v.detach().clone().contiguous() for k, v in net.state_dict().items()}, log)
+    net.load_state_dict(sd)
+    net = net.to(device)
     net.math_mode = MATH_MODE
     net.grid_storage, net.sum_lods = GRID_STORAGE, SUM_LODS
-    t0 = time.time()
-    ds = MeshDataset(args, mesh=torus(0.6, 0.25, 128, 64), device=device)       # 500 000 labelled points
-    torch.cuda.synchronize()
-    t_ds = time.time() - t0
-    trainer = FusedTrainer(net, lr=1e-3)
-    n = len(ds)
-    g = torch.Generator(device=device).manual_seed(7)
-    t0 = time.time()
-    last = None
-    for it in range(FIT_STEPS):
-        idx = torch.randint(0, n, (FIT_BATCH,), device=device, generator=g)
-        last = trainer.step(ds.pts[idx], ds.d[idx])
-    torch.cuda.synchronize()
-    log(f"fit: dataset {n} pts in {t_ds:.2f}s, {FIT_STEPS} steps x {FIT_BATCH} pts in {time.time() - t0:.2f}s, "
-        f"final loss {float(last):.3e}")
     net.lod = LOD
     net.eval()
+    net.fit_source = how
     return net, args
 
 
 def flush_l2(buf):
     buf.zero_()
+
+
+def measure_l2_gather_peak(device):
+    """The roofline denominator of the gather-bound kernels, measured on this box in this run (nglod_probe_gather): the
+    address stream of the SDF gather (8 corner lines of a pseudo-random cell of a 35 MB channels-last grid, 8 lanes x
+    LDG.128 per line), no arithmetic.  `best` = the launch shape that delivers most (no shared-memory carve-out, full
+    occupancy); `kernel_shape` = one 512-thread CTA per SM next to a 225 KB carve-out, i.e. what is left to a kernel that
+    keeps its tcgen05 operand ring in shared memory."""
+    import ctypes
+    from nglod_b200 import _lib
+    lib = _lib.load()
+    R = 64
+    buf = torch.randn((R + 1) ** 3 * 32, device=device)
+    sink = torch.zeros(4, dtype=torch.int32, device=device)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    nq = 1 << 22
+
+    def run(infl, smem, ctas):
+        def call(seed):
+            _lib.check(lib.nglod_probe_gather(ctypes.c_void_p(buf.data_ptr()), R, nq, infl, 1, smem, ctas, seed,
+                                              ctypes.c_void_p(sink.data_ptr()),
+                                              ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "nglod_probe_gather")
+        for i in range(2):
+            call(i)
+        torch.cuda.synchronize()
+        ts = []
+        for i in range(5):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            call(100 + i)
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return nq * 1024 / (float(np.median(ts)) * 1e-3) / 1e9
+    with torch.cuda.device(device):
+        best = max(run(2, 0, 0), run(3, 0, 0))
+        shape = max(run(2, 225 << 10, 1), run(1, 225 << 10, 1))
+    return {"best_GBs": best, "kernel_shape_GBs": shape,
+            "how": "nglod_probe_gather, 2^22 cells x 8 lines x 128 B from a 35 MB grid, L2 flushed before each launch, median of 5"}
 
 
 # ----------------------------------------------------------------------------------------------- ours
@@ -180,6 +301,7 @@ def run_ours(ns):
     from nglod_b200 import ops
     from nglod_b200.lib.tracer import SphereTracer
     rank, world, local = ndist.init_from_env()
+    numa = ndist.bind_to_gpu_numa_node(local)        # before any pinned allocation (first touch)
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
 
@@ -187,12 +309,18 @@ def run_ours(ns):
         if rank == 0:
             print("[bench] " + msg, file=sys.stderr, flush=True)
 
+    if world > 1 and rank != 0:                       # one rank fits (or loads the cache), the others take its weights
+        torch.distributed.barrier()
     net, args = build_and_fit(device, log)
-    if world > 1:                       # identical weights on every rank
+    if world > 1 and rank == 0:
+        torch.distributed.barrier()
+    if world > 1:                       # identical weights on every rank, whatever the cache state
         for p in net.parameters():
             torch.distributed.broadcast(p.data, src=0)
+        net.mark_grids_dirty()
     tracer = SphereTracer(args)
-    ray_o, ray_d = make_rays(device, azimuth_deg=360.0 * rank / max(world, 1), seed=rank)
+    azimuth = 360.0 * rank / max(world, 1)
+    ray_o, ray_d = make_rays(device, azimuth_deg=azimuth, seed=rank)
     n_rays = ray_o.shape[0]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)      # 256 MB > 126 MB L2
     view = net.net_view()
@@ -232,25 +360,39 @@ def run_ours(ns):
     total_ms = ndist.max_over_ranks(sum(step_ms), device)
     kernel_ms = float(np.mean(step_ms))          # the step IS one sphere_trace_kernel launch (+ a 4-byte memset)
 
-    # ---- e2e: same frame through the public API with HOST buffers (pinned), copies inside the timed region
+    # ---- e2e, the call a user makes (Renderer.render_lookat + .cpu() in the reference): camera + jittered window in
+    #      pinned host memory -> rays generated on the device -> trace -> depth / hit / normal into pinned host memory
+    from nglod_b200.lib.geoutils import _window
+    torch.manual_seed(1000 + rank)
+    wx, wy = _window(W, H, "cpu")
+    wx, wy = wx.pin_memory(), wy.pin_memory()
+    cam_fields = ("depth", "hit", "normal")
+    cam_out = {k: torch.empty(s, dtype=dt).pin_memory() for k, s, dt in
+               (("depth", (n_rays, 1), torch.float32), ("hit", (n_rays,), torch.bool), ("normal", (n_rays, 3), torch.float32))}
+    cam_f = camera_from(azimuth)
+
+    def e2e_step():
+        tracer.trace_lookat_host(net, cam_f, CAM_TO, W, H, fov=FOV, mode="persp", window=(wx, wy), out=cam_out, fields=cam_fields)
+
+    def wall(fn, iters):
+        for _ in range(3):
+            fn()
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            fn()
+        return ndist.max_over_ranks(time.perf_counter() - t0, device)
+    e2e_s = wall(e2e_step, ns.steps)
+    cam_hits = int(cam_out["hit"].sum())
+
+    # ---- the same frame with HOST RAY BUFFERS in and every RenderBuffer field out (round 1's e2e leg): 22 MB up, 27 MB down
     ho, hd = ray_o.cpu().pin_memory(), ray_d.cpu().pin_memory()
     out_host = {k: torch.empty(s, dtype=dt).pin_memory() for k, s, dt in
                 (("x", (n_rays, 3), torch.float32), ("depth", (n_rays, 1), torch.float32),
                  ("hit", (n_rays,), torch.bool), ("normal", (n_rays, 3), torch.float32))}
-
-    def e2e_step():
-        # the user-facing host call: pinned rays in, pinned RenderBuffer fields out, copies pipelined with the trace
-        tracer.trace_host(net, ho, hd, out=out_host)
-
-    for _ in range(3):
-        e2e_step()
-    if world > 1:
-        torch.distributed.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(ns.steps):
-        e2e_step()
-    e2e_s = ndist.max_over_ranks(time.perf_counter() - t0, device)
+    e2e_rays_s = wall(lambda: tracer.trace_host(net, ho, hd, out=out_host), ns.steps)
     clock_info = clocks.stop()
 
     # ---- SDF query throughput (BASELINE.json configs[0]): 2^20 random points, lod 4, forward and forward+backward
@@ -258,14 +400,16 @@ def run_ours(ns):
     xq = torch.rand(SDF_N, 3, device=device, generator=g) * 2 - 1
     gq = torch.rand(SDF_N, device=device, generator=g)
 
-    def time_kernel(fn, iters):
+    def time_kernel(fn, iters, do_flush=True):
         for _ in range(3):
-            flush_l2(flush)
+            if do_flush:
+                flush_l2(flush)
             fn()
         torch.cuda.synchronize()
         ev = []
         for _ in range(iters):
-            flush_l2(flush)
+            if do_flush:
+                flush_l2(flush)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             fn()
@@ -282,6 +426,18 @@ def run_ours(ns):
                          max(ns.steps // 2, 5))
     fwd_ms = ndist.max_over_ranks(fwd_ms, device)
     bwd_ms = ndist.max_over_ranks(bwd_ms, device)
+    # inputs larger than L2 instead of a flush: 16 distinct 2^20-point batches (201 MB of coordinates) in rotation --
+    # the 35 MB summed grid then stays L2-resident between launches, which is the steady state of a query server
+    xs_rot = [torch.rand(SDF_N, 3, device=device, generator=g) * 2 - 1 for _ in range(16)]
+    rot = {"i": 0}
+
+    def fwd_rot():
+        ops.sdf_forward(view, LOD, xs_rot[rot["i"] % 16])
+        rot["i"] += 1
+    fwd_rot_ms = ndist.max_over_ranks(time_kernel(fwd_rot, 32, do_flush=False), device)
+    del xs_rot
+
+    l2peak = measure_l2_gather_peak(device) if rank == 0 else None
 
     variants = {}
     if not ns.no_extras:
@@ -322,17 +478,23 @@ def run_ours(ns):
         big_ms = ndist.max_over_ranks(time_kernel(lambda: ops.sdf_forward(view, LOD, xbig), 5), device)
         variants["forward_2^23_queries"] = {"forward_qps": world * (1 << 23) / (big_ms / 1e3), "forward_ms": big_ms}
         del xbig
+    strong = run_strong_scaling(net, args, device, rank, world, flush, log)
     extras = {} if ns.no_extras else run_extras(net, args, device, rank, world, flush, log)
     if variants:
         extras["inference_variants"] = variants
+    if rank == 0 and world == 1 and not ns.no_extras and not ns.no_cpu_baseline:
+        extras["reference_on_this_gpu"] = reference_on_this_gpu(net, log)
     if rank != 0:
         return
-    peak, peak_src = load_peaks()
+    hbm_peak, tensor_peak, peak_src = load_peaks()
     value = world * n_rays * ns.steps / (total_ms / 1e3)
+    ks = kernel_ms / 1e3
+    gather_GBs = n_eval * GATHER_BYTES_PER_QUERY / ks / 1e9                  # L2 -> SM bytes the gather has to move
     alg_bytes = n_eval * (GATHER_BYTES_PER_QUERY + IO_BYTES_PER_QUERY) + n_rays * RAY_IO_BYTES
-    achieved = alg_bytes / (kernel_ms / 1e3) / 1e9
-    compulsory = (n_rays * RAY_IO_BYTES + sum(f.fm.numel() * 4 for f in net.features)) / (kernel_ms / 1e3) / 1e9
-    q_bytes = SDF_N * (GATHER_BYTES_PER_QUERY + IO_BYTES_PER_QUERY)
+    traffic = ncu_traffic("sphere_trace_kernel")
+    q_gather_GBs = SDF_N * GATHER_BYTES_PER_QUERY / (fwd_ms / 1e3) / 1e9
+    fwd_kernel = "sdf_forward_ws_kernel" if MATH_MODE == "tc" else "sdf_forward_kernel"
+    fwd_traffic = ncu_traffic(fwd_kernel)
     line = {
         "metric": "sphere_traced_rays_per_sec_1280x720_lod4",
         "value": value,
@@ -346,41 +508,56 @@ def run_ours(ns):
         "vs_baseline": None,
         "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "SphereTracer.forward 1280x720 persp fov30 lod4, OctreeSDF num-lods=5 feature-dim=32 "
-                               "hidden=128 fitted in-run to a procedural torus mesh (BASELINE.json configs[1])",
-                   "rays_per_gpu_step": n_rays, "fps_per_gpu": 1e3 / (total_ms / ns.steps),
-                   "sdf_evals_per_ray": n_eval / n_rays, "hit_fraction": n_hit / n_rays,
-                   "num_steps": 256, "math_mode": MATH_MODE, "grid_storage": GRID_STORAGE,
-                   "lod_sum": "prefix-summed grid (one 8-corner gather per evaluation)" if SUM_LODS else "per-LOD gather",
-                   "l2": "flushed between timed iterations (256 MB memset)",
-                   "parallelism": f"one frame per GPU x{world}, no collective"},
+        "config": shared_config(world),
+        "sdf_queries_per_sec": world * SDF_N / (fwd_ms / 1e3),          # the other half of BASELINE.json's metric
+        "sdf_forward_backward_queries_per_sec": world * SDF_N / ((fwd_ms + bwd_ms) / 1e3),
+        "fps_per_gpu": 1e3 / (total_ms / ns.steps),
+        "details": {"sdf_evals_per_ray": n_eval / n_rays, "hit_fraction": n_hit / n_rays, "math_mode": MATH_MODE,
+                    "grid_storage": GRID_STORAGE, "fit_source": net.fit_source, "numa_node": numa,
+                    "lod_sum": "prefix-summed grid (one 8-corner gather per evaluation)" if SUM_LODS else "per-LOD gather"},
         "e2e": {"value": world * n_rays * ns.steps / e2e_s, "unit": "rays/s",
-                "h2d_bytes_per_step": n_rays * 24, "d2h_bytes_per_step": n_rays * (12 + 4 + 1 + 12),
-                "ms_per_step": e2e_s / ns.steps * 1e3},
+                "h2d_bytes_per_step": (W + H) * 4 + 64, "d2h_bytes_per_step": n_rays * (4 + 1 + 12),
+                "ms_per_step": e2e_s / ns.steps * 1e3, "hits": cam_hits,
+                "api": "SphereTracer.trace_lookat_host: camera pose + jittered window (pinned host) in, depth / hit / normal "
+                       "(pinned host) out; rays are generated on the device, as the reference's Renderer.render_lookat does"},
+        "e2e_ray_buffers": {"value": world * n_rays * ns.steps / e2e_rays_s, "unit": "rays/s",
+                            "h2d_bytes_per_step": n_rays * 24, "d2h_bytes_per_step": n_rays * (12 + 4 + 1 + 12),
+                            "ms_per_step": e2e_rays_s / ns.steps * 1e3,
+                            "api": "SphereTracer.trace_host: ray_o / ray_d from pinned host memory, x / depth / hit / normal back"},
         "gpu_launches": ns.steps,
         "clocks": clock_info,
-        "roofline": {"bound": "hbm", "kernel": "sphere_trace_kernel", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_TRACE_BYTES, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms,
-                     "compulsory_GBs": compulsory,
+        "roofline": {"bound": "l2", "kernel": "sphere_trace_kernel", "achieved": gather_GBs, "peak": l2peak["best_GBs"],
+                     "unit": "GB/s", "frac": gather_GBs / l2peak["best_GBs"], "traffic": traffic,
+                     "peak_source": "measured in this run: " + l2peak["how"],
+                     "peak_at_kernel_launch_shape_GBs": l2peak["kernel_shape_GBs"],
+                     "frac_of_kernel_shape_peak": gather_GBs / l2peak["kernel_shape_GBs"],
+                     "kernel_ms": kernel_ms, "sdf_evals_per_launch": n_eval,
+                     "tensor": {"achieved_TFLOPs": n_eval * TENSOR_FLOP_PER_EVAL / ks / 1e12, "peak_TFLOPs": tensor_peak,
+                                "frac": n_eval * TENSOR_FLOP_PER_EVAL / ks / 1e12 / tensor_peak,
+                                "note": "SURVEY 8d form: evals x 2*32*128 x 3 TF32 passes over the measured bf16 GEMM peak"},
+                     "dram": {"traffic_GBs": (traffic / ks / 1e9) if traffic else None, "peak_GBs": hbm_peak,
+                              "frac": (traffic / ks / 1e9 / hbm_peak) if traffic else None, "peak_source": peak_src},
+                     "hbm_form_GBs": alg_bytes / ks / 1e9,
                      "per_lod_formulation_GBs": (n_eval * (GATHER_BYTES_PER_QUERY_PER_LOD + IO_BYTES_PER_QUERY)
-                                                 + n_rays * RAY_IO_BYTES) / (kernel_ms / 1e3) / 1e9,
-                     "note": f"algorithmic bytes = sdf_evals x ({GATHER_BYTES_PER_QUERY} B gather + 16 B io) + rays x 53 B; "
-                             "per_lod_formulation_GBs is the same count with SURVEY 8d's 5120 B (the reference's 5 "
-                             "separate gathers, which the summed grid replaces); the gather is "
-                             "served by L2/L1 (summed grid 35 MB < L2), so frac may exceed 1 (SURVEY.md 8d); DRAM traffic "
-                             "(ncu) is the compulsory ~40 MB: the grid once + ray I/O. The kernel is latency/sync "
-                             "bound (issue 37 %, L1 34 %, L2 8 %, tensor 24 %), see DESIGN.md section 4"},
+                                                 + n_rays * RAY_IO_BYTES) / ks / 1e9,
+                     "note": f"achieved = sdf_evals x {GATHER_BYTES_PER_QUERY} B (the 8 corner lines of the prefix-summed grid, DESIGN "
+                             "4.0) / kernel time: the gather is served by L2 (the 35 MB grid is resident; DRAM traffic is the "
+                             "grid once + ray I/O), so the roof is the L2 -> SM path measured by the probe, not HBM. "
+                             "hbm_form_GBs / per_lod_formulation_GBs keep round 1's and SURVEY 8d's byte counts for "
+                             "comparison. The frame is bound by the latency of its longest rays (256 dependent steps), "
+                             "not by throughput: DESIGN.md section 4"},
         "sdf_queries": {"n": SDF_N, "lod": LOD,
                         "forward_qps": world * SDF_N / (fwd_ms / 1e3), "forward_ms": fwd_ms,
                         "forward_backward_qps": world * SDF_N / ((fwd_ms + bwd_ms) / 1e3), "backward_ms": bwd_ms,
-                        "roofline": {"bound": "hbm", "kernel": "sdf_forward_tc_kernel" if MATH_MODE == "tc" else "sdf_forward_kernel",
-                                     "achieved": q_bytes / (fwd_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
-                                     "frac": q_bytes / (fwd_ms / 1e3) / 1e9 / peak,
-                                     "traffic": NCU_TRAFFIC_SDF_FWD_BYTES,
-                                     "l2_to_sm_GBs": SDF_N * GATHER_BYTES_PER_QUERY / (fwd_ms / 1e3) / 1e9,
-                                     "note": "random queries miss L1 (hit 3 %), so the 1024 B/query gather is L2->SM "
-                                             "traffic; the L2 fabric tops out near 6300 B/clk (~11 TB/s at 1.8 GHz)"}},
+                        "forward_qps_inputs_rotating": world * SDF_N / (fwd_rot_ms / 1e3), "forward_ms_inputs_rotating": fwd_rot_ms,
+                        "l2": "forward_ms: L2 flushed before every launch; *_inputs_rotating: no flush, 16 distinct input "
+                              "batches (201 MB) in rotation, the summed grid stays L2-resident",
+                        "roofline": {"bound": "l2", "kernel": fwd_kernel, "achieved": q_gather_GBs, "peak": l2peak["best_GBs"],
+                                     "unit": "GB/s", "frac": q_gather_GBs / l2peak["best_GBs"],
+                                     "frac_of_kernel_shape_peak": q_gather_GBs / l2peak["kernel_shape_GBs"],
+                                     "traffic": fwd_traffic,
+                                     "tensor_frac": SDF_N * TENSOR_FLOP_PER_EVAL / (fwd_ms / 1e3) / 1e12 / tensor_peak}},
+        "strong_scaling": strong,
     }
     line["extras"] = extras
     if world == 1 and not ns.no_cpu_baseline:
@@ -388,18 +565,132 @@ def run_ours(ns):
     print(json.dumps(line), flush=True)
 
 
-# ----------------------------------------------------------------------------------------------- other configs
-def run_extras(net, args, device, rank, world, flush, log):
-    """Side measurements for BASELINE.json configs 3-5 (device-timed, L2 flushed, a few iterations each).  They are
-    reported under "extras"; the headline value / roofline above are untouched by them."""
+# ----------------------------------------------------------------------------------------------- strong scaling (configs 3, 5)
+def run_strong_scaling(net, args, device, rank, world, flush, log):
+    """The two partitionings north_star names, at this N, total work fixed (divide the N=1 time by this one for the
+    speed-up): (a) ONE 3840x2160 frame with shadows in interleaved screen strips, final NCCL gather to rank 0 inside the
+    timed region; (b) the data-parallel training step on a 500 000-point batch: per-rank sampling + mesh2sdf labels
+    (prefetched on a second stream), fused 5-head step, reduce-scatter / Adam on 1/N / all-gather."""
+    import copy
     from nglod_b200 import dist as ndist
     from nglod_b200 import ops
-    from nglod_b200.lib import spc as S
-    from nglod_b200.lib.datasets import MeshDataset
     from nglod_b200.lib.renderer import Renderer
     from nglod_b200.lib.tracer import SphereTracer
     from nglod_b200.lib.trainer import FusedTrainer
     from nglod_b200.lib.torchgp import torus, point_sample, normalize
+    out = {"n_gpus": world}
+
+    def timed(fn, iters=5, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        ts = []
+        for _ in range(iters):
+            flush_l2(flush)
+            torch.cuda.synchronize()
+            if world > 1:
+                torch.distributed.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return ndist.max_over_ranks(float(np.mean(ts)), device)
+
+    # ---- (a) config 5: 3840x2160, shadows + normals; 4 interleaved strips per rank (silhouette columns cost more than empty
+    #      ones); every rank renders its strips as one batch; depth / hit / normal / shadow (18 B per ray) gathered to rank 0
+    w4, h4 = 3840, 2160
+    torch.manual_seed(5)
+    from nglod_b200.lib.geoutils import look_at
+    ro, rd = look_at(CAM_FROM, CAM_TO, w4, h4, mode="persp", fov=FOV, device=device)
+    strips_all = [ndist.interleaved_strips(w4, r, world, strips_per_rank=4) for r in range(world)]
+    mine = strips_all[rank]
+    ro = torch.cat([ro[c0 * h4:c1 * h4] for c0, c1 in mine]).contiguous()
+    rd = torch.cat([rd[c0 * h4:c1 * h4] for c0, c1 in mine]).contiguous()
+    rargs = copy.copy(args)
+    rargs.shadow, rargs.ground_height, rargs.render_res = True, -0.4, [ro.shape[0] // h4, h4]
+    renderer = Renderer(SphereTracer(rargs), args=rargs, device=device)
+    frame = {}
+
+    def render_and_gather():
+        rb = renderer.render(net, ro, rd)
+        packed = torch.cat([rb.depth.reshape(-1, 1), rb.normal.reshape(-1, 3), rb.hit.reshape(-1, 1).float(),
+                            rb.shadow.reshape(-1, 1).float()], dim=1)
+        frame["full"] = ndist.gather_strips(packed, strips_all, h4, rank, world, dst=0)
+    r4_ms = timed(render_and_gather, iters=3, warm=1)
+    render_only_ms = timed(lambda: renderer.render(net, ro, rd), iters=3, warm=1)
+    out["render_4k_shadow"] = {"rays": w4 * h4, "rays_this_rank": int(ro.shape[0]), "ms": r4_ms, "fps": 1e3 / r4_ms,
+                               "rays_per_s": w4 * h4 / (r4_ms / 1e3), "render_only_ms": render_only_ms,
+                               "gathered_bytes": int((w4 * h4 - ro.shape[0]) * 6 * 4),
+                               "note": "ONE 3840x2160 frame: primary trace + ground plane + shadow trace + normals "
+                                       "(Renderer.render) over 4 interleaved column strips per rank, then the final gather of "
+                                       "depth / normal / hit / shadow to rank 0 (NCCL gather) inside the timed region"}
+    if rank == 0 and frame.get("full") is not None:
+        out["render_4k_shadow"]["gathered_frame_hits"] = int(frame["full"][:, 4].sum())
+    del ro, rd, renderer, frame
+
+    # ---- (b) config 3: 500 000 points per step over the ranks
+    V, F = normalize(*[t.to(device) for t in torus(0.6, 0.25, 128, 64)])
+    per_rank = 500000 // world
+    modes = ["rand", "near", "near", "trace", "trace"]
+    tri = V[F].contiguous()
+
+    def make_batch():
+        pts = point_sample(V, F, modes, per_rank // 5)
+        return pts, ops.mesh2sdf_gpu(pts, tri)[0].unsqueeze(1)
+    sample_ms = timed(make_batch, iters=5, warm=2)
+    tnet = copy.deepcopy(net)
+    tnet.train()
+    trainer = FusedTrainer(tnet, lr=1e-3)
+    pts, gts = make_batch()
+    step_ms = timed(lambda: trainer.step(pts, gts, global_batch=per_rank * world), iters=5, warm=2)
+    # the whole config-3 step with the next batch produced on a second stream while this one trains
+    side = torch.cuda.Stream(device)
+    state = {"batch": make_batch()}
+
+    def pipelined_step():
+        cur = torch.cuda.current_stream(device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            nxt = make_batch()
+        p, g_ = state["batch"]
+        trainer.step(p, g_, global_batch=per_rank * world)
+        cur.wait_stream(side)
+        state["batch"] = nxt
+    pipe_ms = timed(pipelined_step, iters=6, warm=2)
+    comm = {}
+    if world > 1:
+        dist = torch.distributed
+        comm["reduce_scatter_plus_all_gather_ms"] = timed(lambda: (
+            dist.reduce_scatter_tensor(trainer.grad_shard, trainer.flat_grad, op=dist.ReduceOp.SUM),
+            dist.all_gather_into_tensor(trainer.flat_grad, trainer.grad_shard)), iters=5, warm=2)
+        comm["all_reduce_ms"] = timed(lambda: dist.all_reduce(trainer.flat_grad), iters=5, warm=2)
+        comm["bytes"] = int(trainer.flat_grad.numel() * 4)
+    out["train_step_500k"] = {"points_per_rank": per_rank, "step_ms": step_ms, "sample_and_label_ms": sample_ms,
+                              "config3_step_ms_serial": step_ms + sample_ms, "config3_step_ms": pipe_ms,
+                              "config3_points_per_s": per_rank * world / (pipe_ms / 1e3),
+                              "optimizer": "sharded (reduce-scatter, Adam on 1/N, all-gather)" if trainer.sharded else "replicated",
+                              "comm": comm, "mesh_triangles": int(tri.shape[0]),
+                              "note": "step_ms: fused fwd+loss+bwd for 5 LODs + gradient exchange + Adam on a resident batch; "
+                                      "config3_step_ms: the same with a FRESH batch per step (sampler kernel + mesh2sdf labels) "
+                                      "produced on a second stream while the previous batch trains"}
+    log(f"strong scaling @N={world}: 4K+shadow+gather {r4_ms:.2f} ms (render {render_only_ms:.2f}), train step {step_ms:.2f} ms, "
+        f"sample+label {sample_ms:.2f} ms, config-3 pipelined {pipe_ms:.2f} ms, comm {comm}")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- other configs
+def run_extras(net, args, device, rank, world, flush, log):
+    """Side measurements (device-timed, L2 flushed, a few iterations each).  They are reported under "extras"; the headline
+    value / roofline above are untouched by them."""
+    from nglod_b200 import dist as ndist
+    from nglod_b200.lib import spc as S
+    from nglod_b200.lib.renderer import Renderer
+    from nglod_b200.lib.tracer import SphereTracer
+    from nglod_b200.lib.torchgp import torus, normalize
     from nglod_b200.lib.geoutils import look_at
     out = {}
     import copy
@@ -436,35 +727,9 @@ def run_extras(net, args, device, rank, world, flush, log):
                                 "note": "Renderer.shade_images end to end, steady state (after the host buffers are page-locked): look_at "
                                         "rays, sphere trace, matcap shading, all RenderBuffer fields to host, (H,W,C) layout"}
 
-    # ---- config 3: training step on a 500 000-point batch sharded over the ranks (fused 5-head fwd+bwd, one
-    #      all-reduce of the flat gradient, Adam kernel) + the cost of producing the batch (sampling + mesh2sdf labels)
+    # ---- config 4 as BASELINE.json states it: 1920x1080, octree level 7, a 6-LOD natively sparse model (base-lod 2, so LOD l
+    #      lives on level l + 2), lods 1..5: traversal + first voxel + in-voxel tracing with re-location + normals
     V, F = normalize(*[t.to(device) for t in torus(0.6, 0.25, 128, 64)])
-    per_rank = 500000 // world
-    modes = ["rand", "near", "near", "trace", "trace"]
-    tri = V[F].contiguous()
-
-    def make_batch():
-        pts = point_sample(V, F, modes, per_rank // 5)
-        return pts, ops.mesh2sdf_gpu(pts, tri)[0].unsqueeze(1)
-
-    sample_ms = timed(make_batch, iters=5, warm=2)
-    pts, gts = make_batch()
-    tnet = copy.deepcopy(net)
-    tnet.train()
-    trainer = FusedTrainer(tnet, lr=1e-3)
-    step_ms = timed(lambda: trainer.step(pts, gts, global_batch=per_rank * world), iters=5, warm=2)
-    out["train_step_500k"] = {"points_per_rank": pts.shape[0], "ms_per_step": step_ms,
-                              "points_per_s": world * pts.shape[0] / (step_ms / 1e3),
-                              "sample_and_label_ms": sample_ms, "mesh_triangles": int(tri.shape[0]),
-                              "mesh2sdf_pairs_per_s": world * pts.shape[0] * tri.shape[0] / (sample_ms / 1e3),
-                              "config3_step_ms": step_ms + sample_ms,
-                              "config3_points_per_s": world * pts.shape[0] / ((step_ms + sample_ms) / 1e3),
-                              "note": "fused fwd+loss+bwd for 5 LODs + flat-gradient all-reduce + Adam; a fresh batch per step "
-                                      "(SURVEY 8d config 3) adds sample_and_label_ms: the sampler kernel + mesh2sdf labels; "
-                                      "mesh2sdf_pairs_per_s counts all N x T pairs although the large-batch path visits few of them"}
-    del trainer, tnet
-
-    # ---- config 4 (traversal half): sparse-octree ray traversal at 1920x1080, octree level 7 of the same mesh
     torch.manual_seed(77 + rank)
     octree = S.mesh_to_octree(V, F, 7, num_samples=1 << 22)
     spc = S.SPC(octree)
@@ -475,53 +740,38 @@ def run_extras(net, args, device, rank, world, flush, log):
                                         "ms": trav_ms, "rays_per_s": world * ro.shape[0] / (trav_ms / 1e3),
                                         "note": "count + scan + fill, includes the one 4-byte host read of the total"}
     del nug
-
-    # ---- config 4 (tracing half): sparse OctreeSDF of the fitted net over the level-6 octree, in-voxel sphere tracing
-    #      with voxel re-location, lods 1-4 (lod l <-> octree level l+2), 1920x1080
-    octree6 = S.mesh_to_octree(V, F, 6, num_samples=1 << 22)
-    sp = S.SparseOctreeSDF(net, S.SPC(octree6))
-    sweep = {}
-    for lod in (1, 2, 3, 4):
-        st = torch.zeros(2, dtype=torch.int64, device=device)
-        x_, t_, hit_, n_, p_ = sp.trace(ro, rd, lod, stats=st)
-        ms = timed(lambda: sp.trace(ro, rd, lod), iters=3, warm=1)
-        sweep[f"lod{lod}"] = {"ms": ms, "rays_per_s": world * ro.shape[0] / (ms / 1e3), "hits": int(hit_.sum()),
-                              "sdf_evals_per_ray": int(st[0]) / ro.shape[0]}
-    out["spc_sphere_trace_1080p"] = {"rays": ro.shape[0], "octree_level": 6, "voxels": int(sp.spc.pyramid[0, 6]),
-                                     "corner_rows": int(sp.corner_feats.shape[0]), "lods": sweep,
-                                     "note": "traverse + first voxel + in-voxel trace (50 steps, far 5) + normals, one "
-                                             "host read per frame (nugget total)"}
-    del ro, rd, sp
-
-    # ---- config 5: 3840x2160, shadows + normals, image cut into column strips over the ranks (x-major rays)
-    w4, h4 = 3840, 2160
-    torch.manual_seed(5)
-    ro, rd = look_at(CAM_FROM, CAM_TO, w4, h4, mode="persp", fov=FOV, device=device)
-    s0, s1 = ndist.shard_range(w4 * h4, rank, world, align=h4)
-    ro, rd = ro[s0:s1].contiguous(), rd[s0:s1].contiguous()
-    rargs = copy.copy(args)
-    rargs.shadow, rargs.ground_height, rargs.render_res = True, -0.4, [(s1 - s0) // h4, h4]
-    renderer = Renderer(SphereTracer(rargs), args=rargs, device=device)
-    r4_ms = timed(lambda: renderer.render(net, ro, rd), iters=3, warm=1)
-    out["render_4k_shadow"] = {"rays": w4 * h4, "rays_this_rank": s1 - s0, "ms": r4_ms, "fps": 1e3 / r4_ms,
-                               "note": "primary trace + ground plane + shadow trace + normals via Renderer.render; "
-                                       "ranks take contiguous column strips, no collective"}
-    # ---- a natively sparse model (features on the corners of the level-7 octree only: 128^3 has no dense grid
-    #      here) trained with autograd through the sparse kernels + torch Adam, 500 000 points inside occupied voxels
     nspc = S.NeuralSPC(spc, num_lods=6, base_lod=2)
+    # a short in-run fit of the sparse model (fused sparse step, all six heads, analytic torus labels inside occupied voxels)
     opt = torch.optim.Adam(nspc.parameters(), lr=1e-3)
-    lp7 = spc.level_points(7)[:, :3].float()
     gs = torch.Generator(device=device).manual_seed(11 + rank)
+    lp7 = spc.level_points(7)[:, :3].float()
+    for it in range(120):
+        pv = torch.randint(0, lp7.shape[0], (65536,), device=device, generator=gs)
+        xs7 = ((lp7[pv] + torch.rand(pv.shape[0], 3, device=device, generator=gs)) / 128 * 2 - 1).contiguous()
+        gt7 = (torch.sqrt((torch.sqrt(xs7[:, 0] ** 2 + xs7[:, 2] ** 2) - 0.6) ** 2 + xs7[:, 1] ** 2) - 0.25).unsqueeze(1)
+        opt.zero_grad(set_to_none=False)
+        nspc.loss_backward(xs7, gt7)
+        opt.step()
+    nspc.eval()
+    sweep = {}
+    with torch.no_grad():
+        for lod in (1, 2, 3, 4, 5):
+            st = torch.zeros(2, dtype=torch.int64, device=device)
+            x_, t_, hit_, n_, p_ = nspc.trace(ro, rd, lod, stats=st)
+            ms = timed(lambda: nspc.trace(ro, rd, lod), iters=3, warm=1)
+            sweep[f"lod{lod}"] = {"ms": ms, "rays_per_s": world * ro.shape[0] / (ms / 1e3), "hits": int(hit_.sum()),
+                                  "octree_level": lod + 2, "sdf_evals_per_ray": int(st[0]) / ro.shape[0]}
+    out["spc_sphere_trace_1080p"] = {"rays": ro.shape[0], "octree_level": 7, "voxels": int(spc.pyramid[0, 7]), "num_lods": 6,
+                                     "corner_rows": int(nspc.corner_feats.shape[0]), "lods": sweep,
+                                     "note": "BASELINE configs[3]: NeuralSPC num_lods=6 over the level-7 octree, fitted in-run "
+                                             "(120 fused sparse steps x 65 536 points x 6 heads); per LOD: traverse at level "
+                                             "lod+2 + first voxel + in-voxel trace (50 steps, far 5) + normals, one host read "
+                                             "per frame (nugget total)"}
+    # ---- the sparse training step itself, 500 000 points in occupied level-7 voxels, head 5
     pv = torch.randint(0, lp7.shape[0], (500000 // world,), device=device, generator=gs)
     xs7 = ((lp7[pv] + torch.rand(pv.shape[0], 3, device=device, generator=gs)) / 128 * 2 - 1).contiguous()
     gt7 = (torch.sqrt((torch.sqrt(xs7[:, 0] ** 2 + xs7[:, 2] ** 2) - 0.6) ** 2 + xs7[:, 1] ** 2) - 0.25).unsqueeze(1)
-
-    def sparse_step():
-        opt.zero_grad(set_to_none=True)
-        loss = ((nspc.sdf(xs7, 5, pv) - gt7) ** 2).mean()
-        loss.backward()
-        opt.step()
-    sp_ms = timed(sparse_step, iters=5, warm=2)
+    nspc.train()
 
     def sparse_step_fused():          # one kernel: forward + loss + backward of the head (NeuralSPC.loss_backward)
         opt.zero_grad(set_to_none=False)
@@ -529,13 +779,11 @@ def run_extras(net, args, device, rank, world, flush, log):
         opt.step()
     spf_ms = timed(sparse_step_fused, iters=5, warm=2)
     out["neural_spc_train_step_500k"] = {"ms_per_step": spf_ms, "points_per_s": world * pv.shape[0] / (spf_ms / 1e3),
-                                         "autograd_ms_per_step": sp_ms,
                                          "voxels_level7": int(lp7.shape[0]), "corner_rows": int(nspc.corner_feats.shape[0]),
-                                         "note": "NeuralSPC (6 LODs, levels 2-7), head 5: fused sparse forward + loss + gen-2 "
-                                                 "backward through the parent chain (nglod_sparse_sdf_train_step) + torch Adam; "
-                                                 "autograd_ms_per_step = the same step as separate forward / loss / backward; "
-                                                 "no gradient all-reduce"}
-    del nspc, opt
+                                         "note": "NeuralSPC (6 LODs, levels 2-7), head 5: fused sparse forward + loss + backward "
+                                                 "through the parent chain (nglod_sparse_sdf_train_step) + torch Adam; no "
+                                                 "gradient all-reduce"}
+    del nspc, opt, ro, rd
 
     # ---- the headless real-time loop (ray generation -> trace -> matcap shading, frame stays on the device)
     from nglod_b200.app import realtime
@@ -547,9 +795,82 @@ def run_extras(net, args, device, rank, world, flush, log):
                    "hit_pixels_last_frame": int(r["hit"].sum())}
     out["realtime_loop"] = dict(rt, note="app/realtime.py: orbiting camera, nglod_generate_rays -> tracer -> "
                                          "nglod_shade_matcap into a device RGB buffer; CUDA-event time per frame, no L2 flush")
-    log(f"extras: train {step_ms:.2f} ms/500k-pt step, sample+label {sample_ms:.1f} ms, spc 1080p {trav_ms:.2f} ms, "
-        f"4K+shadow {r4_ms:.1f} ms")
+    log(f"extras: spc traversal 1080p/level 7 {trav_ms:.2f} ms, sparse trace lods 1-5 "
+        f"{[round(v['ms'], 2) for v in sweep.values()]} ms, sparse step {spf_ms:.2f} ms")
     return out
+
+
+REF_GPU_SCRIPT = r'''
+import json, sys, time, numpy as np, torch
+sys.path.insert(0, %(root)r)
+from oracle import ref_python
+ref = ref_python.import_reference("reference")
+dev = "cuda"
+args = ref.parse_options(return_parser=True).parse_args(["--net", "OctreeSDF", "--num-lods", "5", "--feature-dim", "32", "--lod", "4"])
+net = ref.OctreeSDF(args)
+net.load_state_dict(torch.load(%(weights)r, map_location="cpu"))
+net = net.to(dev).eval(); net.lod = 4
+tracer = ref.SphereTracer(args)
+torch.manual_seed(1000)
+o, d = ref.look_at(%(cam)r, [0.0, 0.0, 0.0], 1280, 720, fov=30.0, mode="persp", device="cpu")
+o, d = o.to(dev), d.to(dev)
+def timed(fn, it, warm):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(it): fn()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / it
+res = {}
+with torch.no_grad():
+    rb = tracer(net, o, d)
+    res["trace_720p_ms"] = timed(lambda: tracer(net, o, d), 5, 2)
+    res["hits"] = int(rb.hit.sum())
+g = torch.Generator(device=dev).manual_seed(1)
+x = torch.rand(1 << 20, 3, device=dev, generator=g) * 2 - 1
+gt = torch.rand(1 << 20, 1, device=dev, generator=g)
+with torch.no_grad():
+    res["sdf_forward_2^20_ms"] = timed(lambda: net.sdf(x, lod=4), 20, 5)
+def fb():
+    net.zero_grad(set_to_none=True)
+    (((net.sdf(x, lod=4) - gt) ** 2).sum() / x.shape[0]).backward()
+res["sdf_forward_backward_2^20_ms"] = timed(fb, 10, 3)
+import mesh2sdf
+sys.path.insert(0, %(root)r)
+from nglod_b200.lib.torchgp import torus
+V, F = ref.torchgp.normalize(*torus(0.6, 0.25, 128, 64))
+tri = V[F].to(dev).contiguous()
+pts = ref.torchgp.point_sample(V, F, ["rand", "near", "near", "trace", "trace"], 100000).to(dev).contiguous()
+res["mesh2sdf_500k_x_16k_ms"] = timed(lambda: mesh2sdf.mesh2sdf_gpu(pts, tri), 3, 1)
+print("RESULT " + json.dumps(res))
+'''
+
+
+def reference_on_this_gpu(net, log):
+    """SURVEY 8d's second baseline: the UNMODIFIED reference (its Python from oracle/_ref/sdf-net, its own two CUDA
+    extensions from oracle/_ref) on THIS B200, same weights, same rays, CUDA-event timed -- in a subprocess, because the
+    reference binds its extension modules at import.  Reported next to ours; not a target."""
+    import tempfile
+    try:
+        with tempfile.TemporaryDirectory() as td:
+            wpath = os.path.join(td, "w.pt")
+            torch.save({k: v.detach().cpu() for k, v in net.state_dict().items()}, wpath)
+            script = REF_GPU_SCRIPT % {"root": ROOT, "weights": wpath, "cam": CAM_FROM}
+            r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=600)
+        if r.returncode != 0:
+            return {"unavailable": r.stderr.strip().splitlines()[-1][:300] if r.stderr.strip() else "failed"}
+        res = json.loads([l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])
+        res["rays_per_s"] = W * H / (res["trace_720p_ms"] / 1e3)
+        res["sdf_forward_qps"] = SDF_N / (res["sdf_forward_2^20_ms"] / 1e3)
+        res["sdf_forward_backward_qps"] = SDF_N / (res["sdf_forward_backward_2^20_ms"] / 1e3)
+        res["note"] = ("the unmodified reference classes (oracle/_ref/sdf-net) + the reference's own compiled sol_nglod / mesh2sdf "
+                       "kernels (oracle/_ref) on this GPU, same fitted weights and rays as ours; no L2 flush")
+        log(f"reference on this GPU: trace {res['trace_720p_ms']:.1f} ms, sdf fwd {res['sdf_forward_2^20_ms']:.2f} ms, "
+            f"fwd+bwd {res['sdf_forward_backward_2^20_ms']:.2f} ms, mesh2sdf {res['mesh2sdf_500k_x_16k_ms']:.1f} ms")
+        return res
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": str(e)[:300]}
 
 
 # ----------------------------------------------------------------------------------------------- CPU legs
@@ -560,13 +881,39 @@ def subsample_rays(ray_o, ray_d, stride):
     return o, d
 
 
-def cpu_trace_rate(onet, ray_o, ray_d, budget_s, log):
-    """Time the oracle's batch-loop tracer on the host; picks the largest sub-frame that fits the budget."""
-    from oracle import nglod_oracle as O
+def cpu_reference_tracer(state_dict, log):
+    """(trace(o, d) -> RenderBuffer-like, kind): the UNMODIFIED reference's OctreeSDF + SphereTracer on the host cores
+    (oracle/ref_python: reference Python from /root/reference or its staged copy under oracle/_ref, sol_nglod.aabb from
+    oracle.c, which the GPU tests pin bit for bit to the reference's CUDA aabb).  Falls back to the oracle port."""
     torch.set_num_threads(os.cpu_count() or 1)
+    try:
+        from oracle import ref_python
+        ref = ref_python.import_reference("cpu")
+        rargs = ref.parse_options(return_parser=True).parse_args(
+            ["--net", "OctreeSDF", "--num-lods", str(NUM_LODS), "--feature-dim", "32", "--lod", str(LOD)])
+        rnet = ref.OctreeSDF(rargs)
+        rnet.load_state_dict(state_dict)
+        rnet.eval()
+        rnet.lod = LOD
+        tracer = ref.SphereTracer(rargs)
+
+        def trace(o, d):
+            with torch.no_grad():
+                return tracer(rnet, o, d)
+        return trace, "reference"
+    except Exception as e:  # noqa: BLE001
+        log(f"reference Python unavailable ({e}); timing the oracle port instead")
+        from oracle import nglod_oracle as O
+        onet = O.OracleNet(state_dict)
+        onet.lod = LOD
+        return (lambda o, d: O.sphere_trace(onet, o, d)), "port"
+
+
+def cpu_trace_rate(trace, ray_o, ray_d, budget_s, log):
+    """Time the CPU tracer on the largest sub-frame (every s-th row and column of the same rays) that fits the budget."""
     o, d = subsample_rays(ray_o, ray_d, 32)                 # 40x23 probe
     t0 = time.perf_counter()
-    O.sphere_trace(onet, o, d)
+    trace(o, d)
     probe = max(time.perf_counter() - t0, 1e-3)
     per_ray = probe / o.shape[0]
     stride = 32
@@ -574,86 +921,67 @@ def cpu_trace_rate(onet, ray_o, ray_d, budget_s, log):
         if per_ray * (W // s) * (H // s) * 0.6 <= budget_s:   # batches get more efficient as they grow
             stride = s
     o, d = subsample_rays(ray_o, ray_d, stride)
-    cnt = {}
     t0 = time.perf_counter()
-    O.sphere_trace(onet, o, d, count=cnt)
+    trace(o, d)
     dt = time.perf_counter() - t0
     log(f"cpu tracer: {o.shape[0]} rays ({W // stride}x{H // stride}) in {dt:.2f}s on {torch.get_num_threads()} threads")
-    return o.shape[0] / dt, f"{W // stride}x{H // stride} sub-frame (every {stride}th row/col) of the same rays, {o.shape[0]} rays, 1 pass", dt
+    return o.shape[0] / dt, stride, f"{W // stride}x{H // stride} sub-frame (every {stride}th row/col) of the same rays, {o.shape[0]} rays, 1 pass"
 
 
 def cpu_baseline_trace(net, ray_o, ray_d, budget_s, log):
-    from oracle import nglod_oracle as O
-    onet = O.OracleNet({k: v.detach().cpu() for k, v in net.state_dict().items()})
-    onet.lod = LOD
-    rate, sample, _ = cpu_trace_rate(onet, ray_o, ray_d, budget_s, log)
-    return {"value": rate, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample}
+    trace, kind = cpu_reference_tracer({k: v.detach().cpu() for k, v in net.state_dict().items()}, log)
+    rate, _, sample = cpu_trace_rate(trace, ray_o, ray_d, budget_s, log)
+    return {"value": rate, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": kind, "sample": sample}
 
 
 def run_reference(ns):
-    """The reference's CPU path for the same metric/config: the oracle port (same ATen calls as the reference's
-    PyTorch path; the reference itself is Python under /root/reference, which does not exist on the GPU box)."""
+    """The reference arm: the UNMODIFIED reference's own CPU implementation of the path (its OctreeSDF + SphereTracer classes,
+    PyTorch on the host cores) on the SAME fitted net and the SAME rays as our arm; each step a bounded sub-frame."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import nglod_oracle as O
 
     def log(msg):
         print("[bench-ref] " + msg, file=sys.stderr, flush=True)
 
     torch.set_num_threads(os.cpu_count() or 1)
-    fit_dev = "cuda" if torch.cuda.is_available() else "cpu"
-    # untimed set-up: fit the same architecture to the same torus with plain torch autograd (on the GPU if present)
-    from nglod_b200.lib.options import parse_options
-    from nglod_b200.lib.models import OctreeSDF
-    args = parse_options(return_parser=True).parse_args(["--net", "OctreeSDF", "--num-lods", str(NUM_LODS)])
-    torch.manual_seed(0)
-    sd = OctreeSDF(args).state_dict()                     # parameter container only; no kernel is touched
-    onet = O.OracleNet(sd, device=fit_dev, requires_grad=True)
-    opt = torch.optim.Adam(onet.parameters(), lr=1e-3)
-    g = torch.Generator(device=fit_dev).manual_seed(7)
-    steps, batch = (FIT_STEPS, FIT_BATCH) if fit_dev == "cuda" else (60, 8192)
-    steps = int(os.environ.get("NGLOD_REF_FIT_STEPS", steps))       # tests shrink the (untimed) set-up
-    for _ in range(steps):
-        p = torch.rand(batch, 3, device=fit_dev, generator=g) * 2 - 1
-        surf = p[: batch // 2]
-        q = torch.sqrt(surf[:, 0] ** 2 + surf[:, 2] ** 2)
-        # half of the batch is pulled onto / near the torus surface, like the near/trace sample modes
-        ring = torch.stack([surf[:, 0] / q * 0.6, torch.zeros_like(q), surf[:, 2] / q * 0.6], dim=1)
-        dirv = torch.nn.functional.normalize(surf - ring, dim=1)
-        p = torch.cat([ring + dirv * (0.25 + 0.01 * torch.randn(batch // 2, 1, device=fit_dev, generator=g)), p[batch // 2:]])
-        qq = torch.sqrt(p[:, 0] ** 2 + p[:, 2] ** 2) - 0.6
-        gt = (torch.sqrt(qq * qq + p[:, 1] ** 2) - 0.25).unsqueeze(1)
-        O.l2_loss_and_grads(onet, p, gt, list(range(NUM_LODS)))
-        opt.step()
-    cpu_net = O.OracleNet({f"features.{i}.fm": t.detach().cpu() for i, t in enumerate(onet.fm)} |
-                          {f"louts.{i}.{k}": t.detach().cpu() for i, dct in enumerate(onet.dec)
-                           for k, t in zip(("0.weight", "0.bias", "2.weight", "2.bias"), dct)})
-    cpu_net.lod = LOD
-    # rays: the oracle's own look_at (same camera, seeded jitter)
-    torch.manual_seed(1000)
-    ray_o, ray_d = O.look_at(CAM_FROM, CAM_TO, W, H, mode="persp", fov=FOV)
+    # the parameter container comes from the reference's own class when its Python is available (same seed, same init order)
+    try:
+        from oracle import ref_python
+        ref = ref_python.import_reference("cpu")
+        rargs = ref.parse_options(return_parser=True).parse_args(["--net", "OctreeSDF", "--num-lods", str(NUM_LODS), "--feature-dim", "32"])
+        torch.manual_seed(0)
+        init = {k: v.detach().clone().contiguous() for k, v in ref.OctreeSDF(rargs).state_dict().items()}
+        torch.manual_seed(1000)
+        ray_o, ray_d = ref.look_at(camera_from(0.0), CAM_TO, W, H, mode="persp", fov=FOV, device="cpu")
+    except Exception as e:  # noqa: BLE001
+        log(f"reference Python unavailable ({e}); parameter container and rays from the package's mirror classes")
+        from nglod_b200.lib.options import parse_options
+        from nglod_b200.lib.models import OctreeSDF
+        torch.manual_seed(0)
+        init = {k: v.detach().clone().contiguous() for k, v in
+                OctreeSDF(parse_options(return_parser=True).parse_args(["--net", "OctreeSDF", "--num-lods", str(NUM_LODS)])).state_dict().items()}
+        ray_o, ray_d = make_rays("cpu")
+    sd, how = fit_shared(init, log)
+    trace, kind = cpu_reference_tracer(sd, log)
     total_steps = ns.steps + ns.warmup
     budget = float(os.environ.get("NGLOD_REF_BUDGET_S", max(2.0, min(20.0, 150.0 / max(total_steps, 1)))))
-    rate, sample, dt = cpu_trace_rate(cpu_net, ray_o, ray_d, budget, log)
-    o, d = None, None
-    # timed: W warm-up + K steps of the bounded sample
-    stride = W // int(sample.split("x")[0])
+    _, stride, sample = cpu_trace_rate(trace, ray_o, ray_d, budget, log)
     o, d = subsample_rays(ray_o, ray_d, stride)
     for _ in range(ns.warmup):
-        O.sphere_trace(cpu_net, o, d)
+        trace(o, d)
     t0 = time.perf_counter()
     for _ in range(ns.steps):
-        O.sphere_trace(cpu_net, o, d)
+        trace(o, d)
     el = time.perf_counter() - t0
     value = o.shape[0] * ns.steps / el
     line = {
         "impl": "reference", "metric": "sphere_traced_rays_per_sec_1280x720_lod4", "value": value, "unit": "rays/s",
         "n_gpus": ns.gpus, "steps": ns.steps, "warmup": ns.warmup, "ms_per_step": el / ns.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "SphereTracer.forward 1280x720 persp fov30 lod4, OctreeSDF num-lods=5 feature-dim=32 "
-                               "hidden=128 fitted in-run to a torus (BASELINE.json configs[1]); CPU: " + sample},
-        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
+        "config": shared_config(ns.gpus),
+        "details": {"fit_source": how},
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": kind,
                          "sample": sample + f", x{ns.steps} steps"},
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -667,7 +995,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the config 3/4/5 side measurements")
+    ap.add_argument("--no-extras", action="store_true", help="skip the side measurements (sparse path, real-time loop, variants)")
     ns = ap.parse_args()
     # stdout carries exactly ONE line, the JSON: libraries that write to fd 1 (NCCL prints its version banner there)
     # are sent to stderr for the duration of the run; print() below still reaches the real stdout

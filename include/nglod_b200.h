@@ -65,8 +65,10 @@ typedef struct nglod_net {
     const float* b0[NGLOD_MAX_LODS];
     const float* w1[NGLOD_MAX_LODS];
     const float* b1[NGLOD_MAX_LODS];
-    /* OPTIONAL inference accelerators, read by nglod_sdf_forward / nglod_sdf_finitediff / nglod_sphere_trace only
-     * (null = not provided; training, features and backward always use grids[]).
+    /* OPTIONAL inference accelerators, read by nglod_sdf_forward / nglod_sdf_finitediff / nglod_sphere_trace and -- for the
+     * forward recompute of the single-grid backward, together with nglod_net_grad_t.summed -- by nglod_sdf_backward /
+     * nglod_sdf_train_step (null = not provided: every kernel then gathers grids[]).  They are DERIVED data: whoever
+     * writes grids[] must rebuild them (nglod_build_summed_grid) before the next call.
      * summed[i]:      the "prefix-summed" grid of LOD i, same layout and resolution as grids[i]:
      *                   summed[i][node] = sum_{l<=i} trilinear(grids[l], position of that node)
      *                 (nglod_build_summed_grid).  The LOD grids nest (grid_res[i] is a multiple of every coarser

@@ -265,7 +265,9 @@ extern "C" int nglod_sdf_features(const nglod_net_t* net, int32_t lod, const flo
     for (int i = 0; i < NGLOD_MAX_LODS; ++i) {
         nd.res[i] = i <= lod ? net->grid_res[i] : 1;
         nd.grids[i] = i <= lod ? net->grids[i] : nullptr;
-        if (i <= lod && (!nd.grids[i] || nd.res[i] < 1 || (reinterpret_cast<uintptr_t>(nd.grids[i]) & 15u))) return NGLOD_EINVAL;
+        // res <= 256: lod_setup works with 32-bit element offsets of (R+1)^3 * 32 (same bound as nglod_check_net)
+        if (i <= lod && (!nd.grids[i] || nd.res[i] < 1 || nd.res[i] > 256 || (reinterpret_cast<uintptr_t>(nd.grids[i]) & 15u)))
+            return NGLOD_EINVAL;
     }
     if (n == 0) return 0;
     NGLOD_CUDA_TRY(cudaFuncSetAttribute(sdf_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SDF_SMEM_BYTES));

@@ -114,10 +114,24 @@ class OctreeSDF(BaseLOD):
         return all(res[i] % res[j] == 0 for i in range(len(res)) for j in range(i))
 
     def mark_grids_dirty(self):
-        """Call after writing the grids behind torch's back (`.data` / raw pointers, e.g. the fused Adam kernel).  The
-        derived buffers themselves are kept (a captured CUDA graph of the training step rebuilds them in place)."""
+        """MUST be called after writing the grids behind torch's back -- `fm.data.copy_(...)`, raw pointers, a custom
+        kernel such as the fused Adam step: such writes do not bump the tensors' version counters, and the inference
+        kernels read DERIVED prefix-summed grids that are rebuilt only when a version counter or an address changes.
+        `load_state_dict` and device / dtype moves call it themselves.  The derived buffers are kept (a captured CUDA
+        graph of the training step rebuilds them in place)."""
         if self._derived is not None:
             self._derived[0] = None
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.mark_grids_dirty()
+        return out
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        if getattr(self, "_derived", None) is not None:
+            self._derived = None            # moved / cast: the derived buffers belong to the old placement
+        return out
 
     def _derived_grids(self, want_half=False):
         """(summed, summed_half) rebuilt when a grid was written or moved; the fp16 copy only when asked for."""
