@@ -569,27 +569,11 @@ m2s_proj_bin_kernel(const float* __restrict__ x, const long long n, const int G,
     }
 }
 
-// EXPERIMENT, off by default (the default build compiles none of it; profiles/NEXT.md item 4): the stab kernel reads the
-// points under a triangle's projection through an index, as 3 scattered 4-byte loads (L1 data pipe 73 % busy).  With
-// NGLOD_M2S_PTS4 the sorted points are copied once into a float4 array and fetched with one 16-byte load.
-#ifndef NGLOD_M2S_PTS4
-#define NGLOD_M2S_PTS4 0
-#endif
-#if NGLOD_M2S_PTS4
-__global__ void __launch_bounds__(256)
-m2s_pack4_kernel(const float* __restrict__ x, const long long n, float4* __restrict__ x4) {
-    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (i < n) x4[i] = make_float4(__ldg(x + 3 * i), __ldg(x + 3 * i + 1), __ldg(x + 3 * i + 2), 0.f);
-}
-#endif
 
 __global__ void __launch_bounds__(M2S_WARP_THREADS)
 mesh2sdf_stab_kernel(const float* __restrict__ points, const TriRecord* __restrict__ recs, const long long num_tris,
                      const int G, const unsigned* __restrict__ ext2_bits, const int* __restrict__ cell_end,
                      const int* __restrict__ pidx, uint3* __restrict__ partial
-#if NGLOD_M2S_PTS4
-                     , const float4* __restrict__ points4
-#endif
                      ) {
     const int lane = threadIdx.x & 31;
     const long long task = (long long)blockIdx.x * (M2S_WARP_THREADS / 32) + (threadIdx.x >> 5);
@@ -624,12 +608,7 @@ mesh2sdf_stab_kernel(const float* __restrict__ points, const TriRecord* __restri
         const int end = __ldg(cell_end + c1);
         for (int jj = begin + lane; jj < end; jj += 32) {
             const long long i = __ldg(pidx + jj);
-#if NGLOD_M2S_PTS4
-            const float4 P4 = __ldg(points4 + i);
-            const float P[3] = {P4.x, P4.y, P4.z};
-#else
             const float P[3] = {__ldg(points + 3 * i), __ldg(points + 3 * i + 1), __ldg(points + 3 * i + 2)};
-#endif
             float p0[3];
 #pragma unroll
             for (int q = 0; q < 3; ++q) p0[q] = P[q] - a[q];
@@ -864,13 +843,14 @@ extern "C" int nglod_mesh2sdf(const float* points, int64_t n, const float* tris,
     const size_t pbin_off = reserve(hier ? (size_t)proj_bins * 4 : 0);
     const size_t pidx_off = reserve(hier ? (size_t)n * M2S_NDIR * 4 : 0);
     const size_t ext_off = reserve(hier ? 4 : 0);
-#if NGLOD_M2S_PTS4
-    const size_t p4_off = reserve(hier ? (size_t)n * 16 : 0);
-#endif
     const int bsum_n = (int)((std::max<long long>(proj_bins, M2S_BINS) / 1024 + 1023) / 1024 * 1024);
     const size_t bsum_off = reserve((size_t)bsum_n * 4);
-    long long dist_slices = num_patches / 32;                                 // >= 32 patches (one round of level 1) per slice
-    if (dist_slices > 32) dist_slices = 32;                                   // sweep 4 .. 64 in profiles/README.md: 16-32 is the flat optimum
+    // slices of the patch range for the distance kernel.  500 k points: 4 / 8 / 16 / 32 / 64 slices measured 3.3 / 2.7 / 2.5 /
+    // 2.6 / 3.0 ms (profiles/README.md); a data-parallel rank's 62.5 k points: 16 / 32 / 64 / 128 slices 0.87 / 0.74 / 0.67 /
+    // 0.67 ms -- a small batch has too few warps to hide the long walks of its medial-axis points, so it is cut finer
+    long long dist_slices = num_patches / 8;                                  // >= 8 patches per slice
+    const long long slice_cap = n < 200000 ? 64 : 32;
+    if (dist_slices > slice_cap) dist_slices = slice_cap;
     if (dist_slices < 1) dist_slices = 1;
     char* ws = nullptr;
     cudaMemPool_t pool = nullptr;
@@ -946,15 +926,8 @@ extern "C" int nglod_mesh2sdf(const float* points, int64_t n, const float* tris,
             m2s_proj_bin_kernel<<<nb, 256, 0, st>>>(pts, (long long)n, G, ext, pbin, pidx);
             const long long tasks = (long long)num_tris * M2S_NDIR;
             const long long wpc = M2S_WARP_THREADS / 32;
-#if NGLOD_M2S_PTS4
-            float4* p4 = reinterpret_cast<float4*>(ws + p4_off);
-            m2s_pack4_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(pts, (long long)n, p4);
-            mesh2sdf_stab_kernel<<<(int)((tasks + wpc - 1) / wpc), M2S_WARP_THREADS, 0, st>>>(
-                pts, recs, (long long)num_tris, G, ext, pbin, pidx, partial, p4);
-#else
             mesh2sdf_stab_kernel<<<(int)((tasks + wpc - 1) / wpc), M2S_WARP_THREADS, 0, st>>>(
                 pts, recs, (long long)num_tris, G, ext, pbin, pidx, partial);
-#endif
             err = (int)cudaGetLastError();
         }
     } else if (!err) {

@@ -108,19 +108,33 @@ def gather_shards(local, n_total, rank, world, dst=0, align=1):
 def gather_strips(local, strips_by_rank, rows_per_col, rank, world, dst=0):
     """Final gather of a frame rendered in interleaved column strips (interleaved_strips): `local` holds this rank's
     strips back to back ([cols_local * rows_per_col, C], x-major like the rays); rank `dst` gets the whole frame
-    [total_cols * rows_per_col, C] in image order, the others None.  One NCCL gather of equal-size padded buffers."""
+    [total_cols * rows_per_col, C] in image order, the others None.  ONE NCCL gather; when every strip has the same
+    width (the usual case: the image width divides by world * strips_per_rank) the receive buffer is a single
+    [world, strips_per_rank, ...] tensor and the frame is one transposed copy of it, otherwise shards are padded to
+    the longest and copied strip by strip."""
     if world == 1 or not dist.is_initialized():
         return local
+    widths = {c1 - c0 for s in strips_by_rank for c0, c1 in s}
+    counts = {len(s) for s in strips_by_rank}
+    tail = tuple(local.shape[1:])
+    if len(widths) == 1 and len(counts) == 1:
+        # strip s of the image belongs to rank s % world and is that rank's strip s // world
+        big = torch.empty((world,) + tuple(local.shape), dtype=local.dtype, device=local.device) if rank == dst else None
+        dist.gather(local.contiguous(), list(big.unbind(0)) if rank == dst else None, dst=dst)
+        if rank != dst:
+            return None
+        spr, rows = counts.pop(), widths.pop() * rows_per_col
+        return big.view((world, spr, rows) + tail).transpose(0, 1).reshape((world * spr * rows,) + tail)
     cols = [sum(c1 - c0 for c0, c1 in s) for s in strips_by_rank]
     longest = max(cols) * rows_per_col
-    pad = torch.zeros((longest,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad = torch.zeros((longest,) + tail, dtype=local.dtype, device=local.device)
     pad[: local.shape[0]] = local
     bufs = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
     dist.gather(pad, bufs, dst=dst)
     if rank != dst:
         return None
     total = sum(cols)
-    full = torch.empty((total * rows_per_col,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    full = torch.empty((total * rows_per_col,) + tail, dtype=local.dtype, device=local.device)
     for r in range(world):
         pos = 0
         for c0, c1 in strips_by_rank[r]:

@@ -48,6 +48,16 @@ def _worker(rank, world, port, q):
         assert torch.equal(got, frame + 0.5)
     else:
         assert got is None
+    # ... and with equal strips (the single-buffer path): 40 columns = 2 ranks x 4 strips x 5
+    ncols = 40
+    strips = [nd.interleaved_strips(ncols, r, world, strips_per_rank=4) for r in range(world)]
+    frame = torch.arange(ncols * h2 * 3, dtype=torch.float32).reshape(-1, 3)
+    mine = torch.cat([frame[c0 * h2:c1 * h2] for c0, c1 in strips[rank]])
+    got = nd.gather_strips(mine, strips, h2, rank, world, dst=0)
+    if rank == 0:
+        assert torch.equal(got, frame)
+    else:
+        assert got is None
     # data-parallel gradient: each rank contributes its slice's gradient, scaled by the GLOBAL batch
     g = torch.full((10,), float(rank + 1))
     nd.allreduce_sum_(g)
