@@ -3,7 +3,9 @@
  *
  * One shared library (libnglod_b200.so), every entry point `extern "C"`, plain
  * device pointers and sizes, an explicit cudaStream_t (passed as void*), no
- * allocation, no hidden global state, no torch types.  Every function returns
+ * torch types.  Outputs are caller-allocated and the library reads no environment
+ * variables; its only process-wide state is the mesh2sdf scratch pool (see
+ * nglod_mesh2sdf / nglod_release_scratch).  Every function returns
  * 0 on success or a non-zero code (a cudaError_t, or one of the NGLOD_E*
  * values below for argument errors) -- it never prints and never aborts.  The
  * host side (nglod_b200/_lib.py -> lib/...) converts a non-zero return into a
@@ -26,7 +28,7 @@
 extern "C" {
 #endif
 
-#define NGLOD_ABI_VERSION 7
+#define NGLOD_ABI_VERSION 8
 #define NGLOD_MAX_LODS 8
 
 /* nglod_net_t.math_mode */
@@ -235,9 +237,18 @@ int nglod_sphere_trace(const nglod_net_t* net, int32_t lod,
  * batches >= 16 k points take an output-sensitive path (nearest triangle through a sphere hierarchy over
  * Morton-sorted triangles, sign through 13 projected point grids) whose results are bit-identical to the walk.
  * Scratch (records, bins: ~100 B per point + 400 B per triangle) is stream-ordered, from a memory pool the
- * library keeps per device; no host synchronisation. */
+ * library keeps per device -- the one piece of process-wide state behind this ABI (a cudaMemPool_t per device,
+ * created on first use, mutex-guarded, never trimmed by synchronisation); nglod_release_scratch() hands its
+ * unused memory back to the driver.  No host synchronisation.
+ * nglod_mesh2sdf_ex: flags = NGLOD_M2S_FORCE_WALK makes every batch take the brute-force walk (the A/B reference of
+ * the large-batch path; results are bit-identical either way). */
+#define NGLOD_M2S_FORCE_WALK 1u
 int nglod_mesh2sdf(const float* points, int64_t n, const float* tris,
                    int64_t num_tris, float* dist, void* stream);
+int nglod_mesh2sdf_ex(const float* points, int64_t n, const float* tris,
+                      int64_t num_tris, float* dist, uint32_t flags, void* stream);
+/* Trim the current device's mesh2sdf scratch pool to zero retained bytes (work still in flight keeps its memory). */
+int nglod_release_scratch(void);
 
 /* ---- training-point sampler -------------------------------------------------
  * Replaces the host-side torch samplers of sdf-net/lib/torchgp/: area_weighted_distribution.py:26-45,

@@ -10,10 +10,11 @@ import ctypes
 import os
 
 MAX_LODS = 8
-EXPECTED_ABI = 7        # include/nglod_b200.h NGLOD_ABI_VERSION the ctypes structs below were written against
+EXPECTED_ABI = 8        # include/nglod_b200.h NGLOD_ABI_VERSION the ctypes structs below were written against
 LOSS_PER_LOD = 0x80000000
 MATH_TC3XTF32 = 0
 MATH_FP32 = 1
+M2S_FORCE_WALK = 1
 EINVAL = 10001
 EUNSUPPORTED = 10002
 
@@ -135,6 +136,8 @@ SIGNATURES = {
     "nglod_shade_matcap": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int64,
                                           c_void_p, c_void_p]),
     "nglod_mesh2sdf": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
+    "nglod_mesh2sdf_ex": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, ctypes.c_uint32, c_void_p]),
+    "nglod_release_scratch": (ctypes.c_int, []),
     "nglod_mesh_area_cdf": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "nglod_sample_mesh": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.c_int,
                                          c_int64, ctypes.c_float, ctypes.c_uint64, c_void_p, c_void_p, c_void_p]),

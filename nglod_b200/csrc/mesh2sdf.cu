@@ -796,8 +796,19 @@ static void m2s_scan(int* bins, long long nbins, int* bsum, int bsum_n, cudaStre
     m2s_scan_add_kernel<<<nblk, 1024, 0, st>>>(bins, bsum);
 }
 
+extern "C" int nglod_release_scratch(void) {
+    cudaMemPool_t pool = nullptr;
+    if (int e = m2s_scratch_pool(&pool)) return e;
+    return (int)cudaMemPoolTrimTo(pool, 0);
+}
+
 extern "C" int nglod_mesh2sdf(const float* points, int64_t n, const float* tris, int64_t num_tris, float* dist,
                               void* stream) {
+    return nglod_mesh2sdf_ex(points, n, tris, num_tris, dist, 0u, stream);
+}
+
+extern "C" int nglod_mesh2sdf_ex(const float* points, int64_t n, const float* tris, int64_t num_tris, float* dist,
+                                 uint32_t flags, void* stream) {
     if (n < 0 || num_tris < 0 || (n > 0 && (!points || !dist)) || (num_tris > 0 && !tris)) return NGLOD_EINVAL;
     if (n == 0) return 0;
     const long long grid = (n + M2S_THREADS - 1) / M2S_THREADS;
@@ -810,8 +821,8 @@ extern "C" int nglod_mesh2sdf(const float* points, int64_t n, const float* tris,
     const bool sort = !(n < 4096 || n >= 2000000000ll || num_tris < 64);      // else too small for the sort to pay
     // Large batches: distance and sign by the two output-sensitive kernels.  Their set-up (two more counting sorts, the
     // 13 projected grids) costs a fixed ~0.5 ms, so small batches keep the sliced brute-force walk.
-    // NGLOD_M2S_BRUTE=1 forces the walk: the A/B switch of the parity test.
-    const bool hier = getenv("NGLOD_M2S_BRUTE") == nullptr && sort && n >= M2S_HIER_MIN_POINTS &&
+    // NGLOD_M2S_FORCE_WALK forces the walk: the A/B switch of the parity test.
+    const bool hier = !(flags & NGLOD_M2S_FORCE_WALK) && sort && n >= M2S_HIER_MIN_POINTS &&
                       num_tris >= 4 * M2S_PATCH && num_tris < 100000000ll && n * M2S_NDIR < 2000000000ll;
     const long long num_patches = (num_tris + M2S_PATCH - 1) / M2S_PATCH;
     int G = 32;                                                              // projected grid: ~2 sqrt(#triangles) cells a side

@@ -819,9 +819,8 @@ int launch_backward(const nglod_net_t* net, int lod, const nglod_net_grad_t* gra
     gdv.b1 = grad ? grad->b1[lod] : nullptr;
     long long grid = nglod_sm_count();
     if constexpr (!WITH_GX) {
-        // second-generation kernel: 16 warps, head gradients on the tensor cores (NGLOD_BWD_GEN1=1 keeps the first)
-        static const bool gen1 = getenv("NGLOD_BWD_GEN1") != nullptr;
-        if (!gen1) {
+        // second-generation kernel: 16 warps, head gradients on the tensor cores (the first generation below serves dL/dx)
+        {
             auto k2 = sdf_backward_mma_kernel<FUSED_LOSS, false>;
             NGLOD_CUDA_TRY(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, BW2_SMEM_BYTES + BW2_SMEM_GRID_MAX * 4));
             const int lpw = n > (long long)grid * BW2_WARPS * 8 ? 32 : 8;     // 128-query batches only while they fit one wave

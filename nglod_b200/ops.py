@@ -272,8 +272,9 @@ def sphere_trace(view, lod, ray_o, ray_d, num_steps=256, step_size=1.0, min_dis=
 
 
 # --------------------------------------------------------------------------- mesh2sdf / adam
-def mesh2sdf_gpu(points, mesh):
-    """Drop-in for `mesh2sdf.mesh2sdf_gpu(points, mesh)` (mesh2sdf_kernel.cu:895-927,1008): returns [dist [N]]."""
+def mesh2sdf_gpu(points, mesh, force_walk=False):
+    """Drop-in for `mesh2sdf.mesh2sdf_gpu(points, mesh)` (mesh2sdf_kernel.cu:895-927,1008): returns [dist [N]].
+    force_walk=True takes the brute-force walk whatever the batch size (the A/B reference of the large-batch path)."""
     lib = _lib.load()
     points = _f32c(points, "points")
     mesh = _f32c(mesh, "mesh")
@@ -281,8 +282,14 @@ def mesh2sdf_gpu(points, mesh):
     t = mesh.shape[0]
     dist = torch.empty(n, device=points.device, dtype=torch.float32)
     with torch.cuda.device(points.device):
-        _lib.check(lib.nglod_mesh2sdf(_ptr(points), n, _ptr(mesh), t, _ptr(dist), _stream()), "nglod_mesh2sdf")
+        _lib.check(lib.nglod_mesh2sdf_ex(_ptr(points), n, _ptr(mesh), t, _ptr(dist), _lib.M2S_FORCE_WALK if force_walk else 0,
+                                         _stream()), "nglod_mesh2sdf")
     return [dist]
+
+
+def release_scratch():
+    """Hand the mesh2sdf scratch pool's unused memory of the current device back to the driver."""
+    _lib.check(_lib.load().nglod_release_scratch(), "nglod_release_scratch")
 
 
 SAMPLE_CODES = {"rand": 0, "near": 1, "trace": 2}

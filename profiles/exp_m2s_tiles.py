@@ -12,11 +12,8 @@ def t(fn, it=3):
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / it
 def both(pts, tri):
-    os.environ.pop("NGLOD_M2S_BRUTE", None)
     d1 = ops.mesh2sdf_gpu(pts, tri)[0]; ms1 = t(lambda: ops.mesh2sdf_gpu(pts, tri))
-    os.environ["NGLOD_M2S_BRUTE"] = "1"
-    d0 = ops.mesh2sdf_gpu(pts, tri)[0]; ms0 = t(lambda: ops.mesh2sdf_gpu(pts, tri))
-    os.environ.pop("NGLOD_M2S_BRUTE", None)
+    d0 = ops.mesh2sdf_gpu(pts, tri, force_walk=True)[0]; ms0 = t(lambda: ops.mesh2sdf_gpu(pts, tri, force_walk=True))
     return ms1, ms0, torch.equal(d1.view(torch.int32), d0.view(torch.int32)), int((d1 < 0).sum())
 modes = ["rand", "near", "near", "trace", "trace"]
 for name, (V, F) in (("torus128x64", torus(0.6, 0.25, 128, 64)), ("ico5", icosphere(5)), ("ico3", icosphere(3))):

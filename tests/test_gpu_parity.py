@@ -350,14 +350,7 @@ def test_mesh2sdf_hierarchy_is_bit_identical():
     pts = torch.cat([near, box], 0)[torch.randperm(200000, generator=g).to(DEV)].contiguous()
 
     def run(p, cull):
-        if cull:
-            os.environ.pop("NGLOD_M2S_BRUTE", None)
-        else:
-            os.environ["NGLOD_M2S_BRUTE"] = "1"
-        try:
-            return ops.mesh2sdf_gpu(p, tri)[0]
-        finally:
-            os.environ.pop("NGLOD_M2S_BRUTE", None)
+        return ops.mesh2sdf_gpu(p, tri, force_walk=not cull)[0]
 
     for n in (200000, 30000, 3000, 37):
         p = pts[:n].contiguous()
@@ -400,14 +393,7 @@ def test_mesh2sdf_hierarchy_grazing_and_grid_sizes():
     g = torch.Generator().manual_seed(9)
 
     def both(p, tri):
-        os.environ.pop("NGLOD_M2S_BRUTE", None)
-        a = ops.mesh2sdf_gpu(p, tri)[0]
-        os.environ["NGLOD_M2S_BRUTE"] = "1"
-        try:
-            b = ops.mesh2sdf_gpu(p, tri)[0]
-        finally:
-            os.environ.pop("NGLOD_M2S_BRUTE", None)
-        return a, b
+        return ops.mesh2sdf_gpu(p, tri)[0], ops.mesh2sdf_gpu(p, tri, force_walk=True)[0]
 
     cube = _cube_mesh(8)
     pts = (torch.rand(40000, 3, generator=g) * 2 - 1).to(DEV)
@@ -897,3 +883,20 @@ def test_model_variants_forward_backward_trace(flags, kw):
     with torch.no_grad():
         ref = O.sphere_trace(onet, o, d, num_steps=24)
     assert int((rb.hit.cpu() != ref["hit"]).sum()) <= 2
+
+
+def test_mesh2sdf_scratch_pool_can_be_released():
+    """nglod_release_scratch: the library's one piece of process-wide state (the per-device mesh2sdf scratch pool) hands
+    its memory back on request, and the next call simply re-grows it with identical results."""
+    from nglod_b200 import ops
+    from nglod_b200.lib.torchgp import icosphere, point_sample, normalize
+    V, F = normalize(*[t.to(DEV) for t in icosphere(4)])
+    tri = V[F].contiguous()
+    torch.manual_seed(1)
+    pts = point_sample(V, F, ["rand", "near", "trace"], 20000)
+    a = ops.mesh2sdf_gpu(pts, tri)[0].clone()
+    torch.cuda.synchronize()
+    ops.release_scratch()
+    b = ops.mesh2sdf_gpu(pts, tri)[0]
+    assert torch.equal(a, b)
+    ops.release_scratch()
