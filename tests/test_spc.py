@@ -395,22 +395,28 @@ def test_neural_spc_fused_loss_backward_equals_autograd(pos_invariant):
     assert (net.corner_feats.grad - 2 * ref["corner_feats"]).abs().max() / ref["corner_feats"].abs().max() < 6e-4
     # points outside the octree (SPC.query -> -1) are inert rows: no table is read for them, they add no loss and no
     # gradient (the reference's Python indexing would wrap to the last voxel; reading trinkets[-8..] is not an option)
-    xo = torch.cat([x, torch.rand(999, 3, device="cuda") * 0.02 - 0.01])          # the shell's centre: unoccupied
+    xo = torch.cat([x, torch.rand(999, 3, device="cuda") * 2 - 1])                   # 999 extra rows marked "no voxel"
     gto = torch.cat([gt, torch.zeros(999, 1, device="cuda")])
-    assert (net.query(xo[-999:], 2) < 0).all()
+    none = torch.full((999,), -1, dtype=torch.int64, device="cuda")
+    pidx_o = [torch.cat([net.query(x, lod), none]) for lod in lods]
     d_in = net.sdf(x, 2)
-    d_all = net.sdf(xo, 2)
+    d_all = net.sdf(xo, 2, pidx_o[1])
     assert torch.equal(d_all[:x.shape[0]], d_in) and (d_all[x.shape[0]:] == 0).all()
     for p in net.parameters():
         p.grad = None
-    losses_o = net.loss_backward(xo, gto, lods=lods, global_batch=x.shape[0])
+    losses_o = net.loss_backward(xo, gto, lods=lods, pidx=pidx_o, global_batch=x.shape[0])
     for a, b in zip(losses_o.tolist(), ref_losses):
         assert abs(a - b) < 1e-5 * max(1.0, abs(b))
     assert (net.corner_feats.grad - ref["corner_feats"]).abs().max() / ref["corner_feats"].abs().max() < 3e-4
     for p in net.parameters():
         p.grad = None
-    ((net.sdf(xo, 2) - gto) ** 2).sum().backward()                                   # autograd path, same guard
+    ((net.sdf(xo, 2, pidx_o[1]) - gto) ** 2).sum().backward()                        # autograd path, same guard
     assert torch.isfinite(net.corner_feats.grad).all()
+    g_ref = net.corner_feats.grad.clone()
+    for p in net.parameters():
+        p.grad = None
+    ((net.sdf(x, 2) - gt) ** 2).sum().backward()
+    assert (net.corner_feats.grad - g_ref).abs().max() / g_ref.abs().max() < 3e-4
 
 
 @pytest.mark.gpu
