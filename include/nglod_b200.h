@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define NGLOD_ABI_VERSION 8
+#define NGLOD_ABI_VERSION 9
 #define NGLOD_MAX_LODS 8
 
 /* nglod_net_t.math_mode */
@@ -124,6 +124,11 @@ int nglod_debug_tc_gemm(const float* A, const float* B, float* D, void* stream);
 int nglod_probe_gather(const void* buf, int32_t grid_res, int64_t n_queries, int32_t in_flight,
                        int32_t structured, int32_t smem_bytes, int32_t ctas_per_sm, uint32_t seed,
                        uint32_t* sink, void* stream);
+/* The scatter twin of nglod_probe_gather: adds a small value to the 8 corner lines of n_queries pseudo-random cells of
+ * `buf` with 8 lanes x red.global.add.v4.f32 per line -- the address stream of the backward's grid-gradient scatter,
+ * no arithmetic.  Bytes reduced into L2: n_queries * 1024.  Same launch-shape arguments.  `buf` is modified. */
+int nglod_probe_scatter(void* buf, int32_t grid_res, int64_t n_queries, int32_t smem_bytes, int32_t ctas_per_sm,
+                        uint32_t seed, void* stream);
 
 /* ---- ray vs unit cube ---------------------------------------------------
  * Replaces: f_aabb / aabb_kernel, sdf-net/lib/extensions/sol_nglod/

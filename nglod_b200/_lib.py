@@ -10,7 +10,7 @@ import ctypes
 import os
 
 MAX_LODS = 8
-EXPECTED_ABI = 8        # include/nglod_b200.h NGLOD_ABI_VERSION the ctypes structs below were written against
+EXPECTED_ABI = 9        # include/nglod_b200.h NGLOD_ABI_VERSION the ctypes structs below were written against
 LOSS_PER_LOD = 0x80000000
 MATH_TC3XTF32 = 0
 MATH_FP32 = 1
@@ -99,6 +99,7 @@ SIGNATURES = {
     "nglod_debug_tc_gemm": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "nglod_probe_gather": (ctypes.c_int, [c_void_p, c_int32, c_int64, c_int32, c_int32, c_int32, c_int32, ctypes.c_uint32,
                                           c_void_p, c_void_p]),
+    "nglod_probe_scatter": (ctypes.c_int, [c_void_p, c_int32, c_int64, c_int32, c_int32, ctypes.c_uint32, c_void_p]),
     "nglod_aabb": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "nglod_sdf_forward": (ctypes.c_int, [ctypes.POINTER(NetStruct), c_int32, c_void_p, c_int64, c_void_p, c_void_p]),
     "nglod_sdf_forward_all": (ctypes.c_int, [ctypes.POINTER(NetStruct), c_void_p, c_int64, c_void_p, c_void_p]),

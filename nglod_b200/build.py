@@ -15,7 +15,7 @@ CSRC = os.path.join(PKG, "csrc")
 OUT = os.path.join(PKG, "libnglod_b200.so")
 OBJ = os.path.join(CSRC, "_build")
 
-SOURCES = ["aabb.cu", "sdf_forward.cu", "sdf_tc.cu", "sdf_backward.cu", "tracer.cu", "mesh2sdf.cu", "sample_mesh.cu", "spc.cu", "spc_trace.cu", "render.cu", "probe.cu"]
+SOURCES = ["aabb.cu", "sdf_forward.cu", "sdf_tc.cu", "sdf_backward.cu", "sdf_backward_tc.cu", "tracer.cu", "mesh2sdf.cu", "sample_mesh.cu", "spc.cu", "spc_trace.cu", "render.cu", "probe.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-diag-suppress", "550",

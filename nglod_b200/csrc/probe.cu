@@ -72,6 +72,30 @@ probe_lines_kernel(const uint4* __restrict__ buf, const long long n_lines_buf, c
     if (acc == 0x9e3779b9u) sink[0] = acc;
 }
 
+
+// The backward's address stream: per query 8 corner lines, 8 lanes x red.global.add.v4.f32 per line, no arithmetic.
+// What the L2 atomic units take is the roof of the grid-gradient scatter.
+__global__ void __launch_bounds__(512)
+probe_scatter_kernel(float* __restrict__ grid, const int R, const long long n_queries, const uint32_t seed) {
+    const int S = R + 1;
+    const int c = threadIdx.x & 7;
+    const long long sub = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const long long nsub = ((long long)gridDim.x * blockDim.x) >> 3;
+    for (long long q = sub; q < n_queries; q += nsub) {
+        const uint32_t h = probe_hash((uint32_t)q * 2654435761u + seed);
+        const int x0 = (int)((h & 0x3ffu) * (uint32_t)R >> 10);
+        const int y0 = (int)(((h >> 10) & 0x3ffu) * (uint32_t)R >> 10);
+        const int z0 = (int)(((h >> 20) & 0x3ffu) * (uint32_t)R >> 10);
+        float* g = grid + ((size_t)((z0 * S + y0) * S + x0) * 32 + 4 * c);
+        const int dx = 32, dy = S * 32, dz = S * S * 32;
+        const float v = __uint_as_float((h & 0x007fffffu) | 0x3f000000u) * 1e-6f;
+        red_add_v4(g, v, v, v, v);                     red_add_v4(g + dx, v, v, v, v);
+        red_add_v4(g + dy, v, v, v, v);                red_add_v4(g + dy + dx, v, v, v, v);
+        red_add_v4(g + dz, v, v, v, v);                red_add_v4(g + dz + dx, v, v, v, v);
+        red_add_v4(g + dz + dy, v, v, v, v);           red_add_v4(g + dz + dy + dx, v, v, v, v);
+    }
+}
+
 // Launch shape: as many 512-thread CTAs per SM as fit next to `smem` bytes of (unused) dynamic shared memory each -- the
 // carve-out decides how much of the 228 KB is left to L1, which is where the in-flight lines of a gather live.
 template <typename K>
@@ -117,5 +141,16 @@ extern "C" int nglod_probe_gather(const void* buf, int32_t grid_res, int64_t n_q
             default: return NGLOD_EINVAL;
         }
     }
+    return (int)cudaGetLastError();
+}
+
+extern "C" int nglod_probe_scatter(void* buf, int32_t grid_res, int64_t n_queries, int32_t smem_bytes, int32_t ctas_per_sm,
+                                   uint32_t seed, void* stream) {
+    if (!buf || grid_res < 1 || grid_res > 256 || n_queries < 0) return NGLOD_EINVAL;
+    if (smem_bytes < 0 || smem_bytes > 232448 || ctas_per_sm < 0) return NGLOD_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(buf) & 127u) != 0) return NGLOD_EINVAL;
+    if (n_queries == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    PROBE_LAUNCH(probe_scatter_kernel, reinterpret_cast<float*>(buf), grid_res, n_queries, seed);
     return (int)cudaGetLastError();
 }

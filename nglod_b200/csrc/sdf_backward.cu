@@ -18,6 +18,7 @@
 //      optional dL/dx with PyTorch's border-clip rule.
 #include "sdf_core.cuh"
 #include "sparse_core.cuh"
+#include "internal.h"
 #include <cstdlib>
 
 namespace {
@@ -819,7 +820,17 @@ int launch_backward(const nglod_net_t* net, int lod, const nglod_net_grad_t* gra
     gdv.b1 = grad ? grad->b1[lod] : nullptr;
     long long grid = nglod_sm_count();
     if constexpr (!WITH_GX) {
-        // second-generation kernel: 16 warps, head gradients on the tensor cores (the first generation below serves dL/dx)
+#ifndef NGLOD_BWD_TC
+#define NGLOD_BWD_TC 1          // 0: the mma.sync kernel for the single-grid path too (A/B experiments)
+#endif
+#if NGLOD_BWD_TC
+        // third generation (sdf_backward_tc.cu): tcgen05 GEMMs, warp-specialised; single-grid path
+        if (single) {
+            if (int e = nglod_launch_sdf_backward_tc(nd, gdv, x, (long long)n, grad_out, gt, loss_scale, loss_out, FUSED_LOSS, st)) return e;
+            return cascade ? restrict_cascade(net, lod, grad, st) : 0;
+        }
+#endif
+        // second-generation kernel: 16 warps, head gradients on mma.sync tensor cores (the first generation below serves dL/dx)
         {
             auto k2 = sdf_backward_mma_kernel<FUSED_LOSS, false>;
             NGLOD_CUDA_TRY(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, BW2_SMEM_BYTES + BW2_SMEM_GRID_MAX * 4));

@@ -1,0 +1,473 @@
+// nglod_b200 -- backward of OctreeSDF.sdf(x, lod) and the fused L2 training step on the tcgen05 tensor cores.
+//
+// Reference behaviour: autograd through sdf-net/lib/models/OctreeSDF.py:94-146 (grid_sampler_3d_backward scatter +
+// Linear grads), loss of sdf-net/lib/trainer.py:317-339.  Same mathematics as sdf_backward_mma_kernel (sdf_backward.cu,
+// which keeps the per-LOD and the sparse variants): the forward is recomputed, nothing is saved per query, and the only
+// state a query leaves behind for the head gradients is g_d and its 128 ReLU mask bits.  Per tile of 128 queries:
+//
+//   GEMM1  pre[q][h]  = in[q][.] . W0ext[h][.]          kind::tf32, 3xTF32, M=128 N=128 K=40   (the forward's tile)
+//   epi1   d = b1 + W1.relu(pre)  (the forward's sums in the forward's order), g_d = dL/dd,
+//          MASK[q][h] = [pre > 0] as bf16 0/1 (exact) -> shared memory,   S[q][k] = g_d(q) in[q][k] as bf16 hi + lo
+//   GEMM2  D2[q][f]   = MASK[q][.] . (W1 o W0)[.][f]    kind::f16 (bf16), B split in three bf16 terms (24 bits), M=128 N=32 K=128
+//          -> dL/dfeat[q][f] = g_d(q) D2[q][f]
+//   GEMM3  T[h][k]   += MASK^T[h][.] . S[.][k]          kind::f16 (bf16), two terms, M=128 N=48 K=128, BOTH operands MN-major:
+//          MASK as stored for GEMM2 (K-major, K = h) IS the MN-major operand of GEMM3 (MN = h, K = q), byte for byte;
+//          T lives in TMEM for the whole kernel and is read once per CTA:
+//          dW0[h][k] = w1[h] T[h][k],  db0[h] = w1[h] T[h][35],  dW1[h] = sum_k W0ext[h][k] T[h][k]
+//   epi2   dL/dfeat rows -> shared memory -> 8 lanes per corner line: 8 x red.global.add.v4.f32 per lane into ONE grid
+//          (dL/d(prefix-summed grid), pushed down the LOD chain by the restriction cascade afterwards)
+//
+// Warp-specialised over a 2-stage ring (16 warps x 128 registers, one CTA per SM):
+//   producers (8 warps): gather the tile's A rows exactly like the warp-specialised forward (sdf_tc.cu): records from the
+//       K padding of the A rows, 8 lanes x LDG.128 per corner line, FFMA2 interpolation, hi/lo split; the last producer
+//       to arrive issues GEMM1.
+//   service (2 warpgroups; warpgroup g owns stage g and the tiles T = g mod 2): epi1 -> barrier -> one thread issues
+//       GEMM2 + GEMM3 -> set-up of tile T+2 in the freed stage (releases the producers) -> epi2 + scatter.
+// The roof of this kernel is the L2 atomic units: nglod_probe_scatter measures 6.2 TB/s of reduced bytes for this
+// address stream (0.18 ms per 2^20 queries) whatever the launch shape; everything else is arranged to hide behind it.
+#include "sdf_tc.cuh"
+#include "internal.h"
+#include <cuda_bf16.h>
+
+namespace {
+
+#define BT_PRODUCERS 8
+#define BT_WARPS 16
+#define BT_THREADS (BT_WARPS * 32)
+#define BT_REC_COL (NGLOD_F + 4)                    // K columns 36..39 of an A row: zero in W0|b0 -> 16 free bytes per row
+// shared memory (bytes)
+#define BT_MASK_BYTES (128 * 128 * 2)               // MASK[q][h] bf16: (q/8)*2048 + (h/8)*128 + (q%8)*16 + (h%8)*2
+#define BT_S_TERM_BYTES (6 * 2048)                  // S[q][k] bf16, k padded to 48: (k/8)*2048 + q*16 + (k%8)*2
+#define BT_S_PAD (2 * BT_S_TERM_BYTES - TC_OPERAND_BYTES)     // S_hi + S_lo overwrite A_lo and run 1536 B past it
+#define BT_STAGE_BYTES (2 * TC_OPERAND_BYTES + BT_S_PAD + BT_MASK_BYTES)
+#define BT_SMEM_STAGE(s) (2 * TC_OPERAND_BYTES + (s) * BT_STAGE_BYTES)            // A_hi | A_lo (later S_hi S_lo) | pad | MASK
+#define BT_SMEM_MASK(s) (BT_SMEM_STAGE(s) + 2 * TC_OPERAND_BYTES + BT_S_PAD)
+#define BT_SMEM_B2 (BT_SMEM_STAGE(2))               // (W1 o W0)^T [f][h] bf16 x 3 terms: (f/8)*2048 + (h/8)*128 + (f%8)*16 + (h%8)*2
+#define BT_B2_TERM_BYTES (4 * 2048)
+#define BT_SMEM_W1 (BT_SMEM_B2 + 3 * BT_B2_TERM_BYTES)      // 128 floats + b1 (+ pad) = 528 B
+#define BT_SMEM_BAR (BT_SMEM_W1 + 528)              // arrival counters[2], done1[2], done2[2], rec_full[2] (8 B each)
+#define BT_SMEM_TMEMPTR (BT_SMEM_BAR + 8 * 8)
+#define BT_SMEM_BYTES (BT_SMEM_TMEMPTR + 16)
+static_assert(BT_S_PAD >= 0, "S must cover A_lo");
+static_assert(BT_SMEM_BYTES <= 232448, "shared memory budget");
+#define BT_STAGING_STRIDE 144                       // bytes per dL/dfeat row in the staging area (128 + 16: conflict-free row writes)
+static_assert(128 * BT_STAGING_STRIDE <= BT_MASK_BYTES, "staging area lives in the MASK region");
+// tensor memory (columns)
+#define BT_TMEM_D1(s) ((uint32_t)(s) * 128u)
+#define BT_TMEM_D2(s) (256u + (uint32_t)(s) * 32u)
+#define BT_TMEM_T(g) (320u + (uint32_t)(g) * 64u)
+
+// instruction descriptors, kind::f16 with bf16 operands and an fp32 accumulator, M = 128
+#define BT_IDESC_BF16(N, AMN, BMN) ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(AMN) << 15) | ((uint32_t)(BMN) << 16) | \
+                                    ((uint32_t)((N) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24))
+
+// shared-memory matrix descriptor, SWIZZLE_NONE: K-major -> lbo = stride between the two 16-byte K chunks of an instruction,
+// sbo = stride between 8-row groups; MN-major -> lbo = stride between groups of 8 K rows, sbo = stride between 16-byte MN chunks
+__device__ __forceinline__ uint64_t bt_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
+    d |= 1ull << 46;
+    return d;
+}
+__device__ __forceinline__ void bt_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// two fp32 -> one word of two bf16 (round to nearest even), `lo` at the lower address
+__device__ __forceinline__ uint32_t bt_pack_bf16(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ float bt_bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bt_bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+// v (8 floats) -> bf16 hi words and bf16 words of the remainder
+__device__ __forceinline__ void bt_split8(const float (&v)[8], uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        h[p] = bt_pack_bf16(v[2 * p], v[2 * p + 1]);
+        l[p] = bt_pack_bf16(v[2 * p] - bt_bf16_lo(h[p]), v[2 * p + 1] - bt_bf16_hi(h[p]));
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+template <bool FUSED_LOSS>
+__global__ void __launch_bounds__(BT_THREADS, 1)
+sdf_backward_tc_kernel(const NetDev net, const GradDev grad, const float* __restrict__ x, const long long n,
+                       const float* __restrict__ grad_out, const float* __restrict__ gt, const float loss_scale,
+                       float* __restrict__ loss_out) {
+    extern __shared__ __align__(128) char smem_tc[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* w1s = reinterpret_cast<float*>(smem_tc + BT_SMEM_W1);
+    // ---- prologue: zero the operand ring, stage W0|b0 (tf32 hi/lo), (W1 o W0)^T (3 x bf16), W1, b1; barriers; TMEM
+    {
+        float wv[16];
+        tc_load_weights(net, 0, wv);
+        for (int e = threadIdx.x; e < BT_SMEM_TMEMPTR / 16; e += blockDim.x)
+            reinterpret_cast<float4*>(smem_tc)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncthreads();
+        tc_scatter_weights_to(net, smem_tc, w1s, 0, wv);
+        for (int base = 16 * blockDim.x; base < NGLOD_H * (NGLOD_F + 3) + 2 * NGLOD_H + 1; base += 16 * blockDim.x) {
+            tc_load_weights(net, base, wv);
+            tc_scatter_weights_to(net, smem_tc, w1s, base, wv);
+        }
+        const int in_dim = net.pos_invariant ? NGLOD_F : NGLOD_F + 3;
+        for (int e = threadIdx.x; e < NGLOD_H * NGLOD_F; e += blockDim.x) {
+            const int h = e >> 5, f = e & 31;
+            const float v = __ldg(net.w0 + h * in_dim + (net.pos_invariant ? f : f + 3)) * __ldg(net.w1 + h);
+            const __nv_bfloat16 t0 = __float2bfloat16_rn(v);
+            const float r1 = v - __bfloat162float(t0);
+            const __nv_bfloat16 t1 = __float2bfloat16_rn(r1);
+            const __nv_bfloat16 t2 = __float2bfloat16_rn(r1 - __bfloat162float(t1));
+            char* dst = smem_tc + BT_SMEM_B2 + (f >> 3) * 2048 + (h >> 3) * 128 + (f & 7) * 16 + (h & 7) * 2;
+            *reinterpret_cast<__nv_bfloat16*>(dst) = t0;
+            *reinterpret_cast<__nv_bfloat16*>(dst + BT_B2_TERM_BYTES) = t1;
+            *reinterpret_cast<__nv_bfloat16*>(dst + 2 * BT_B2_TERM_BYTES) = t2;
+        }
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < 2; ++s) {
+                mbar_init(smem_u32(smem_tc + BT_SMEM_BAR + 8 * (2 + s)), 1);      // done1: GEMM1 committed
+                mbar_init(smem_u32(smem_tc + BT_SMEM_BAR + 8 * (4 + s)), 1);      // done2: GEMM2 + GEMM3 committed
+                mbar_init(smem_u32(smem_tc + BT_SMEM_BAR + 8 * (6 + s)), 4);      // rec_full: the stage's 4 service warps
+            }
+            mbar_fence_init();
+        }
+        if (warp == 0) tmem_alloc(smem_u32(smem_tc + BT_SMEM_TMEMPTR), 512);
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        __syncthreads();
+        tc_fence_after_sync();
+    }
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_tc + BT_SMEM_TMEMPTR);
+    const uint32_t bar0 = smem_u32(smem_tc + BT_SMEM_BAR);
+    auto arrive_cnt = [&](int s) { return reinterpret_cast<unsigned*>(smem_tc + BT_SMEM_BAR + 8 * s); };
+    auto done1_bar = [&](int s) { return bar0 + 8u * (uint32_t)(2 + s); };
+    auto done2_bar = [&](int s) { return bar0 + 8u * (uint32_t)(4 + s); };
+    auto rec_bar = [&](int s) { return bar0 + 8u * (uint32_t)(6 + s); };
+    // CTA-local tiles: global tile gt = T * gridDim.x + blockIdx.x while gt * 128 < n; tile T lives in stage T & 1
+    const long long total_tiles = (n + TC_TILE_ROWS - 1) / TC_TILE_ROWS;
+    const int ntiles = (int)((total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+    const long long tile_stride = (long long)gridDim.x * TC_TILE_ROWS;
+    const int R = net.res[0];
+
+    if (warp < BT_PRODUCERS) {
+        // ------------------------------------------------------------------ producers (the last to arrive issues GEMM1)
+        // warp p owns rows 16p .. 16p+15 of every tile = two "items" of two gather rounds (4 queries x 8 lanes) each;
+        // the 16 line loads of the next item are in flight while the current one is interpolated, split and stored
+        const int sub = lane >> 3, c = lane & 7;
+        const float* grid = net.grids[0];
+        const uint32_t b_hi = smem_u32(smem_tc + TC_SMEM_B_HI), b_lo = smem_u32(smem_tc + TC_SMEM_B_LO);
+        const int nitems = 2 * ntiles;
+        auto row_of = [&](int item) { return warp * 16 + (item & 1) * 8 + sub; };      // and row + 4
+        float4 rec0 = make_float4(0.f, 0.f, 0.f, 0.f), rec1 = rec0;
+        TcLines<false> t0, t1;
+        if (nitems > 0) {
+            mbar_wait(rec_bar(0), 0u);
+            const char* a = smem_tc + BT_SMEM_STAGE(0);
+            rec0 = *reinterpret_cast<const float4*>(a + tc_elem_offset(row_of(0), BT_REC_COL));
+            rec1 = *reinterpret_cast<const float4*>(a + tc_elem_offset(row_of(0) + 4, BT_REC_COL));
+            tc_issue_lines<false>(grid, R, __float_as_uint(rec0.x), c, t0);
+            tc_issue_lines<false>(grid, R, __float_as_uint(rec1.x), c, t1);
+        }
+        for (int it = 0; it < nitems; ++it) {
+            const int T = it >> 1, s = T & 1;
+            char* a_hi = smem_tc + BT_SMEM_STAGE(s);
+            char* a_lo = a_hi + TC_OPERAND_BYTES;
+            const int row = row_of(it);
+            const bool more = it + 1 < nitems;
+            float4 nrec0 = make_float4(0.f, 0.f, 0.f, 0.f), nrec1 = nrec0;
+            if (more) {
+                const int T1 = (it + 1) >> 1, s1 = T1 & 1;
+                if (((it + 1) & 1) == 0) mbar_wait(rec_bar(s1), (uint32_t)((T1 >> 1) & 1));       // first item of the next tile
+                const char* a = smem_tc + BT_SMEM_STAGE(s1);
+                nrec0 = *reinterpret_cast<const float4*>(a + tc_elem_offset(row_of(it + 1), BT_REC_COL));
+                nrec1 = *reinterpret_cast<const float4*>(a + tc_elem_offset(row_of(it + 1) + 4, BT_REC_COL));
+            }
+            {
+                uint64_t acc01 = 0ull, acc23 = 0ull;
+                tc_consume_lines<false>(rec0, t0, acc01, acc23);
+                if (more) tc_issue_lines<false>(grid, R, __float_as_uint(nrec0.x), c, t0);
+                float4 acc;
+                f2_unpack(acc01, acc.x, acc.y); f2_unpack(acc23, acc.z, acc.w);
+                tc_store_split4_finite(a_hi, a_lo, tc_elem_offset(row, 4 * c), acc);
+            }
+            {
+                uint64_t acc01 = 0ull, acc23 = 0ull;
+                tc_consume_lines<false>(rec1, t1, acc01, acc23);
+                if (more) tc_issue_lines<false>(grid, R, __float_as_uint(nrec1.x), c, t1);
+                float4 acc;
+                f2_unpack(acc01, acc.x, acc.y); f2_unpack(acc23, acc.z, acc.w);
+                tc_store_split4_finite(a_hi, a_lo, tc_elem_offset(row + 4, 4 * c), acc);
+            }
+            rec0 = nrec0; rec1 = nrec1;
+            if (it & 1) {                                                            // this warp's 16 rows of tile T are in place
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence_block();
+                    const unsigned old = atomicAdd(arrive_cnt(s), 1u);
+                    if ((old & (BT_PRODUCERS - 1)) == BT_PRODUCERS - 1) {
+                        __threadfence_block();
+                        tc_fence_after_sync();
+                        const uint32_t a_hi_s = smem_u32(a_hi);
+                        tc_issue_tile(tmem_base + BT_TMEM_D1(s), a_hi_s, a_hi_s + TC_OPERAND_BYTES, b_hi, b_lo);
+                        tc_commit(done1_bar(s));
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ service warpgroup g: stage g, tiles T = g (mod 2)
+        const int g = (warp - BT_PRODUCERS) >> 2;
+        const int ew = warp & 3;                          // TMEM lane quarter = rows 32 ew .. 32 ew + 31
+        const int row = ew * 32 + lane;
+        char* a_hi = smem_tc + BT_SMEM_STAGE(g);
+        char* a_lo = a_hi + TC_OPERAND_BYTES;
+        char* s_hi = a_lo;                                // S overwrites A_lo (dead once GEMM1 has completed)
+        char* s_lo = a_lo + BT_S_TERM_BYTES;
+        char* mask = smem_tc + BT_SMEM_MASK(g);
+        char* staging = mask;                             // dL/dfeat rows (the MASK is dead once GEMM2 / GEMM3 have completed)
+        const uint32_t rec_off = tc_elem_offset(row, BT_REC_COL), xyz_off = tc_elem_offset(row, NGLOD_F);
+        const uint32_t lane_sel = (uint32_t)(ew * 32) << 16;
+        const uint32_t t_d1 = tmem_base + BT_TMEM_D1(g) + lane_sel, t_d2 = tmem_base + BT_TMEM_D2(g) + lane_sel;
+        const long long i_first = (long long)blockIdx.x * TC_TILE_ROWS + row;
+        float* ggrid = grad.grids[0];
+        float acc_b1 = 0.f, acc_loss = 0.f;
+        auto load_xyz = [&](int T, float& px, float& py, float& pz) {
+            const long long i = i_first + (long long)T * tile_stride;
+            px = py = pz = 0.f;
+            if (T < ntiles && i < n) { px = __ldg(x + 3 * i); py = __ldg(x + 3 * i + 1); pz = __ldg(x + 3 * i + 2); }
+        };
+        auto setup = [&](int T, float px, float py, float pz) -> float4 {
+            const long long i = i_first + (long long)T * tile_stride;
+            // rows past n carry record 0 (corner 0, weights 0): harmless loads; their g_d is 0, so they add nothing
+            const float4 rec = i < n ? tc_setup_record<false>(px, py, pz, R) : make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(a_hi + rec_off) = rec;
+            tc_store_split4(a_hi, a_lo, xyz_off, make_float4(px, py, pz, 1.f));
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(rec_bar(g));
+            return rec;
+        };
+        float nx, ny, nz;
+        float4 rec_cur = make_float4(0.f, 0.f, 0.f, 0.f);
+        load_xyz(g, nx, ny, nz);
+        if (g < ntiles) rec_cur = setup(g, nx, ny, nz);
+        for (int T = g; T < ntiles; T += 2) {
+            const uint32_t par = (uint32_t)((T >> 1) & 1);
+            const long long i = i_first + (long long)T * tile_stride;
+            const bool active = i < n;
+            float up = 0.f;                                // the label (fused loss) or the upstream gradient
+            if (active) up = __ldg((FUSED_LOSS ? gt : grad_out) + i);
+            load_xyz(T + 2, nx, ny, nz);
+            mbar_wait(done1_bar(g), par);
+            tc_fence_after_sync();
+            // ---- epi1: d (the forward kernel's sums in the forward kernel's order), ReLU mask -> MASK rows
+            float d;
+            {
+                uint64_t d01 = 0ull, d23 = 0ull;
+                uint32_t v[2][16];
+                tmem_ld16_async(t_d1, v[0]);
+                char* mrow = mask + (row >> 3) * 2048 + (row & 7) * 16;
+#pragma unroll
+                for (int cb = 0; cb < NGLOD_H / 16; ++cb) {
+                    tmem_ld_wait();
+                    if (cb + 1 < NGLOD_H / 16) tmem_ld16_async(t_d1 + (cb + 1) * 16, v[(cb + 1) & 1]);
+                    const uint32_t* u = v[cb & 1];
+                    uint32_t mw[8];
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        const float4 w = *reinterpret_cast<const float4*>(w1s + cb * 16 + 4 * j4);
+                        const float p0 = __uint_as_float(u[4 * j4]), p1 = __uint_as_float(u[4 * j4 + 1]);
+                        const float p2 = __uint_as_float(u[4 * j4 + 2]), p3 = __uint_as_float(u[4 * j4 + 3]);
+                        d01 = f2_fma(f2_pack(w.x, w.y), f2_pack(fmaxf(p0, 0.f), fmaxf(p1, 0.f)), d01);
+                        d23 = f2_fma(f2_pack(w.z, w.w), f2_pack(fmaxf(p2, 0.f), fmaxf(p3, 0.f)), d23);
+                        mw[2 * j4] = (p0 > 0.f ? 0x3F80u : 0u) | (p1 > 0.f ? 0x3F800000u : 0u);
+                        mw[2 * j4 + 1] = (p2 > 0.f ? 0x3F80u : 0u) | (p3 > 0.f ? 0x3F800000u : 0u);
+                    }
+                    *reinterpret_cast<uint4*>(mrow + (2 * cb) * 128) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+                    *reinterpret_cast<uint4*>(mrow + (2 * cb + 1) * 128) = make_uint4(mw[4], mw[5], mw[6], mw[7]);
+                }
+                float d0, d1, d2, d3;
+                f2_unpack(d01, d0, d1); f2_unpack(d23, d2, d3);
+                d = w1s[NGLOD_H] + ((d0 + d1) + (d2 + d3));
+            }
+            float gd = 0.f;
+            if (active) {
+                if (FUSED_LOSS) {
+                    const float diff = d - up;
+                    acc_loss = fmaf(diff * diff, loss_scale, acc_loss);
+                    gd = 2.f * diff * loss_scale;
+                } else {
+                    gd = up;
+                }
+            }
+            acc_b1 += gd;
+            // ---- S[q][k] = g_d in[q][k] (in as GEMM1 saw its leading term: the TF32 high part), bf16 hi + lo, k padded to 48
+#pragma unroll
+            for (int c5 = 0; c5 < 5; ++c5) {
+                const float4 a = *reinterpret_cast<const float4*>(a_hi + tc_elem_offset(row, 8 * c5));
+                float4 b = make_float4(0.f, 0.f, 0.f, 0.f);             // columns 36..39 hold the gather record, not data
+                if (c5 < 4) b = *reinterpret_cast<const float4*>(a_hi + tc_elem_offset(row, 8 * c5 + 4));
+                const float v[8] = {gd * a.x, gd * a.y, gd * a.z, gd * a.w, gd * b.x, gd * b.y, gd * b.z, gd * b.w};
+                uint4 hi, lo;
+                bt_split8(v, hi, lo);
+                *reinterpret_cast<uint4*>(s_hi + c5 * 2048 + row * 16) = hi;
+                *reinterpret_cast<uint4*>(s_lo + c5 * 2048 + row * 16) = lo;
+            }
+            *reinterpret_cast<uint4*>(s_hi + 5 * 2048 + row * 16) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(s_lo + 5 * 2048 + row * 16) = make_uint4(0u, 0u, 0u, 0u);
+            fence_proxy_async_smem();
+            tc_fence_before_sync();
+            named_bar_sync(1 + g, 128);
+            if (ew == 0 && lane == 0) {
+                tc_fence_after_sync();
+                const uint32_t m_s = smem_u32(mask), b2_s = smem_u32(smem_tc + BT_SMEM_B2);
+                const uint32_t s_hi_s = smem_u32(s_hi), s_lo_s = smem_u32(s_lo);
+                // GEMM2: D2[q][f] = MASK (K-major: 8-row groups 2048 B apart, K chunks 128 B apart) x B2 terms
+                uint32_t acc = 0;
+#pragma unroll
+                for (int term = 0; term < 3; ++term)
+#pragma unroll
+                    for (int ks = 0; ks < NGLOD_H / 16; ++ks) {
+                        bt_mma_bf16(tmem_base + BT_TMEM_D2(g), bt_desc(m_s + ks * 256, 128, 2048),
+                                    bt_desc(b2_s + term * BT_B2_TERM_BYTES + ks * 256, 128, 2048), BT_IDESC_BF16(32, 0, 0), acc);
+                        acc = 1;
+                    }
+                // GEMM3: T[h][k] += MASK^T (MN-major: h chunks 128 B apart, groups of 8 queries 2048 B apart)
+                //                   x S (MN-major: k chunks 2048 B apart, groups of 8 queries 128 B apart)
+                acc = T != g;
+#pragma unroll
+                for (int term = 0; term < 2; ++term)
+#pragma unroll
+                    for (int ks = 0; ks < TC_TILE_ROWS / 16; ++ks) {
+                        bt_mma_bf16(tmem_base + BT_TMEM_T(g), bt_desc(m_s + ks * 4096, 2048, 128),
+                                    bt_desc((term ? s_lo_s : s_hi_s) + ks * 256, 128, 2048), BT_IDESC_BF16(48, 1, 1), acc);
+                        acc = 1;
+                    }
+                tc_commit(done2_bar(g));
+            }
+            mbar_wait(done2_bar(g), par);
+            tc_fence_after_sync();
+            // ---- the stage's operands are dead: set up tile T+2 in it (the producers fill it while this warpgroup scatters)
+            float4 rec_next = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (T + 2 < ntiles) rec_next = setup(T + 2, nx, ny, nz);
+            // ---- epi2: dL/dfeat[q][.] = g_d D2[q][.] -> staging rows
+            {
+                float v[32];
+                tmem_ld32(t_d2, v);
+                tc_fence_before_sync();
+                float4* dst = reinterpret_cast<float4*>(staging + row * BT_STAGING_STRIDE);
+#pragma unroll
+                for (int k4 = 0; k4 < 8; ++k4)
+                    dst[k4] = make_float4(gd * v[4 * k4], gd * v[4 * k4 + 1], gd * v[4 * k4 + 2], gd * v[4 * k4 + 3]);
+            }
+            __syncwarp();
+            // ---- scatter: this warp's 32 rows, 4 queries per round x 8 lanes per corner line
+            if (ggrid) {
+                const unsigned live = __ballot_sync(0xffffffffu, active && gd != 0.f);
+                const int sub = lane >> 3, c = lane & 7;
+                const int S = R + 1;
+#pragma unroll 2
+                for (int r = 0; r < 8; ++r) {
+                    if (!((live >> (4 * r)) & 0xFu)) continue;             // warp-uniform
+                    const int q = 4 * r + sub;
+                    const uint32_t pk = __float_as_uint(__shfl_sync(0xffffffffu, rec_cur.x, q));
+                    const float wx1 = __shfl_sync(0xffffffffu, rec_cur.y, q);
+                    const float wy1 = __shfl_sync(0xffffffffu, rec_cur.z, q);
+                    const float wz1 = __shfl_sync(0xffffffffu, rec_cur.w, q);
+                    if ((live >> q) & 1u) {
+                        const float4 gq = *reinterpret_cast<const float4*>(staging + (ew * 32 + q) * BT_STAGING_STRIDE + 16 * c);
+                        const float wx0 = 1.f - wx1, wy0 = 1.f - wy1, wz0 = 1.f - wz1;
+                        const float w00 = wx0 * wy0, w10 = wx1 * wy0, w01 = wx0 * wy1, w11 = wx1 * wy1;
+                        const float w[8] = {w00 * wz0, w10 * wz0, w01 * wz0, w11 * wz0, w00 * wz1, w10 * wz1, w01 * wz1, w11 * wz1};
+                        float* base = ggrid + (pk & ~31u) + 4 * c;
+                        const int dx = (pk & 1u) ? NGLOD_F : 0;
+                        const int dy = (pk & 2u) ? S * NGLOD_F : 0;
+                        const int dz = (pk & 4u) ? S * S * NGLOD_F : 0;
+                        const int offs[8] = {0, dx, dy, dy + dx, dz, dz + dx, dz + dy, dz + dy + dx};
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            red_add_v4(base + offs[k], gq.x * w[k], gq.y * w[k], gq.z * w[k], gq.w * w[k]);
+                    }
+                }
+            }
+            rec_cur = rec_next;
+            named_bar_sync(1 + g, 128);        // every warp is done with the staging rows before epi1 of T+2 rewrites the MASK
+        }
+        // ---- flush the head gradients of this warpgroup's tiles: thread = hidden unit
+        if (g < ntiles) {
+            const int h = row;
+            const uint32_t t_T = tmem_base + BT_TMEM_T(g) + lane_sel;
+            float tv[40];
+            {
+                float v[32];
+                tmem_ld32(t_T, v);
+                uint32_t u[8];
+                tmem_ld8_async(t_T + 32, u);
+                tmem_ld_wait();
+#pragma unroll
+                for (int k = 0; k < 32; ++k) tv[k] = v[k];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) tv[32 + k] = __uint_as_float(u[k]);
+            }
+            tc_fence_before_sync();
+            const int in_dim = net.pos_invariant ? NGLOD_F : NGLOD_F + 3;
+            const float w1h = w1s[h];
+            float dw1 = 0.f;
+#pragma unroll
+            for (int k = 0; k < NGLOD_KPAD; ++k) {
+                const uint32_t off = tc_elem_offset(h, k);
+                const float w0e = *reinterpret_cast<const float*>(smem_tc + TC_SMEM_B_HI + off) +
+                                  *reinterpret_cast<const float*>(smem_tc + TC_SMEM_B_LO + off);       // W0ext[h][k], exactly
+                dw1 = fmaf(w0e, tv[k], dw1);
+                const float v = w1h * tv[k];
+                if (k < NGLOD_F) {
+                    if (grad.w0) atomicAdd(grad.w0 + h * in_dim + (net.pos_invariant ? k : k + 3), v);
+                } else if (k < NGLOD_F + 3) {
+                    if (grad.w0 && !net.pos_invariant) atomicAdd(grad.w0 + h * in_dim + (k - NGLOD_F), v);
+                } else {
+                    if (grad.b0) atomicAdd(grad.b0 + h, v);
+                }
+            }
+            if (grad.w1) atomicAdd(grad.w1 + h, dw1);
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            acc_b1 += __shfl_xor_sync(0xffffffffu, acc_b1, o);
+            acc_loss += __shfl_xor_sync(0xffffffffu, acc_loss, o);
+        }
+        if (lane == 0 && g < ntiles) {
+            if (grad.b1) atomicAdd(grad.b1, acc_b1);
+            if (FUSED_LOSS && loss_out) atomicAdd(loss_out, acc_loss);
+        }
+    }
+    tc_epilogue_free(tmem_base);
+}
+
+}  // namespace
+
+int nglod_launch_sdf_backward_tc(const NetDev& nd, const GradDev& gd, const float* x, long long n, const float* grad_out,
+                                 const float* gt, float loss_scale, float* loss_out, bool fused_loss, cudaStream_t st) {
+    long long grid = nglod_sm_count();
+    const long long want = (n + TC_TILE_ROWS - 1) / TC_TILE_ROWS;
+    if (want < grid) grid = want;
+    if (fused_loss) {
+        auto kern = sdf_backward_tc_kernel<true>;
+        NGLOD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM_BYTES));
+        kern<<<(int)grid, BT_THREADS, BT_SMEM_BYTES, st>>>(nd, gd, x, n, grad_out, gt, loss_scale, loss_out);
+    } else {
+        auto kern = sdf_backward_tc_kernel<false>;
+        NGLOD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM_BYTES));
+        kern<<<(int)grid, BT_THREADS, BT_SMEM_BYTES, st>>>(nd, gd, x, n, grad_out, gt, loss_scale, loss_out);
+    }
+    return (int)cudaGetLastError();
+}

@@ -55,10 +55,9 @@ __device__ __forceinline__ void tc_load_weights(const NetDev& net, int base, flo
         v[i] = x;
     }
 }
-__device__ __forceinline__ void tc_scatter_weights(const NetDev& net, char* smem, int G, int base, const float (&v)[16]) {
+__device__ __forceinline__ void tc_scatter_weights_to(const NetDev& net, char* smem, float* w1, int base, const float (&v)[16]) {
     const int in_dim = net.pos_invariant ? NGLOD_F : NGLOD_F + 3;
     const int n_w0 = NGLOD_H * in_dim;
-    float* w1 = reinterpret_cast<float*>(smem + TC_SMEM_W1(G));
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         const int e = base + threadIdx.x + i * blockDim.x;
@@ -97,6 +96,10 @@ __device__ __forceinline__ void tc_store_split4_finite(char* a_hi, char* a_lo, u
     l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
     *reinterpret_cast<float4*>(a_hi + off) = h;
     *reinterpret_cast<float4*>(a_lo + off) = l;
+}
+
+__device__ __forceinline__ void tc_scatter_weights(const NetDev& net, char* smem, int G, int base, const float (&v)[16]) {
+    tc_scatter_weights_to(net, smem, reinterpret_cast<float*>(smem + TC_SMEM_W1(G)), base, v);
 }
 
 // One axis of the trilinear set-up (PyTorch grid_sampler arithmetic, see sdf_core.cuh::lod_axis).
