@@ -102,6 +102,13 @@ typedef struct nglod_net_grad {
      * prefix sum (dense restriction kernels, level by level -- the hat functions nest), adding into grids[0..lod]:
      * the same gradients as the per-LOD scatter, to fp32 rounding. */
     float* summed[NGLOD_MAX_LODS];
+    /* OPTIONAL scratch for the scatter into SMALL grids (single-grid path, grid_res <= 8): scatter_scratch_floats floats,
+     * 16-byte aligned, ALL ZERO on entry and all zero again on return.  A grid of 125 or 729 nodes takes half a million
+     * reductions per node and the L2 atomic units serialise per address (nglod_probe_scatter: 1.09 / 0.49 ms per 2^20
+     * queries at grid_res 4 / 8 against 0.18 ms from grid_res 16 on); with this buffer the CTAs scatter into as many
+     * private copies of the grid as fit (up to 64) and one small kernel folds them into summed[lod].  Null: one copy. */
+    float* scatter_scratch;
+    int64_t scatter_scratch_floats;
 } nglod_net_grad_t;
 
 /* ---- introspection ------------------------------------------------------ */

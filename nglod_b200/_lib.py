@@ -77,6 +77,8 @@ class NetGradStruct(ctypes.Structure):
         ("w1", c_void_p * MAX_LODS),
         ("b1", c_void_p * MAX_LODS),
         ("summed", c_void_p * MAX_LODS),
+        ("scatter_scratch", c_void_p),
+        ("scatter_scratch_floats", c_int64),
     ]
 
 

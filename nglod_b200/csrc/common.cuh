@@ -33,6 +33,10 @@ struct GradDev {
     float* b0;
     float* w1;
     float* b1;
+    // tcgen05 backward only: CTA b scatters into priv + (b % priv_copies) * priv_stride instead of grids[0] when priv is set
+    float* priv = nullptr;
+    int priv_copies = 0;
+    int priv_stride = 0;        // floats
 };
 
 static inline int nglod_check_net(const nglod_net_t* net, int lod) {

@@ -774,6 +774,24 @@ accumulate_and_clear_kernel(float4* __restrict__ T, float4* __restrict__ g, cons
     }
 }
 
+// target += sum of the private scatter copies; the copies are zero again afterwards
+__global__ void __launch_bounds__(256)
+fold_copies_kernel(float4* __restrict__ priv, const int copies, const long long n4, float4* __restrict__ target) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n4) return;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < copies; ++c) {
+        const float4 v = priv[c * n4 + e];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        priv[c * n4 + e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (target) {
+        float4 t = target[e];
+        t.x += acc.x; t.y += acc.y; t.z += acc.z; t.w += acc.w;
+        target[e] = t;
+    }
+}
+
 int restrict_cascade(const nglod_net_t* net, int lod, const nglod_net_grad_t* grad, cudaStream_t st) {
     const long long cap = (long long)nglod_sm_count() * 16;
     for (int l = lod; l >= 0; --l) {
@@ -826,7 +844,22 @@ int launch_backward(const nglod_net_t* net, int lod, const nglod_net_grad_t* gra
 #if NGLOD_BWD_TC
         // third generation (sdf_backward_tc.cu): tcgen05 GEMMs, warp-specialised; single-grid path
         if (single) {
+            // a grid of <= 729 nodes: scatter into private copies (enough of them to spread the batch over ~5000 nodes)
+            const long long grid_floats = (long long)(nd.res[0] + 1) * (nd.res[0] + 1) * (nd.res[0] + 1) * NGLOD_F;
+            if (grad->scatter_scratch && !(reinterpret_cast<uintptr_t>(grad->scatter_scratch) & 15u) && nd.res[0] <= 8 &&
+                n >= 4 * grid_floats) {
+                long long copies = (160000 + grid_floats - 1) / grid_floats;
+                if (copies > grad->scatter_scratch_floats / grid_floats) copies = grad->scatter_scratch_floats / grid_floats;
+                if (copies > 64) copies = 64;
+                if (copies > 1) { gdv.priv = grad->scatter_scratch; gdv.priv_copies = (int)copies; gdv.priv_stride = (int)grid_floats; }
+            }
             if (int e = nglod_launch_sdf_backward_tc(nd, gdv, x, (long long)n, grad_out, gt, loss_scale, loss_out, FUSED_LOSS, st)) return e;
+            if (gdv.priv) {
+                const long long n4 = grid_floats / 4;
+                fold_copies_kernel<<<(int)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<float4*>(gdv.priv), gdv.priv_copies, n4,
+                                                                            reinterpret_cast<float4*>(gdv.grids[0]));
+                if (int e = (int)cudaGetLastError()) return e;
+            }
             return cascade ? restrict_cascade(net, lod, grad, st) : 0;
         }
 #endif

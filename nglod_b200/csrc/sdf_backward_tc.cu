@@ -8,12 +8,14 @@
 //   GEMM1  pre[q][h]  = in[q][.] . W0ext[h][.]          kind::tf32, 3xTF32, M=128 N=128 K=40   (the forward's tile)
 //   epi1   d = b1 + W1.relu(pre)  (the forward's sums in the forward's order), g_d = dL/dd,
 //          MASK[q][h] = [pre > 0] as bf16 0/1 (exact) -> shared memory,   S[q][k] = g_d(q) in[q][k] as bf16 hi + lo
-//   GEMM2  D2[q][f]   = MASK[q][.] . (W1 o W0)[.][f]    kind::f16 (bf16), B split in three bf16 terms (24 bits), M=128 N=32 K=128
-//          -> dL/dfeat[q][f] = g_d(q) D2[q][f]
-//   GEMM3  T[h][k]   += MASK^T[h][.] . S[.][k]          kind::f16 (bf16), two terms, M=128 N=48 K=128, BOTH operands MN-major:
-//          MASK as stored for GEMM2 (K-major, K = h) IS the MN-major operand of GEMM3 (MN = h, K = q), byte for byte;
-//          T lives in TMEM for the whole kernel and is read once per CTA:
+//   GEMM2  D2[q][t,f] = MASK[q][.] . (W1 o W0)_t[.][f]  kind::f16 (bf16), M=128 N=96 K=128: B = W1 o W0 split in three bf16 terms
+//          t (24 bits) stacked along N   -> dL/dfeat[q][f] = g_d(q) (D2[q][2,f] + D2[q][1,f] + D2[q][0,f])
+//   GEMM3  T[h][t,k] += MASK^T[h][.] . S_t[.][k]        kind::f16 (bf16), M=128 N=80 K=128, BOTH operands MN-major, S = hi | lo
+//          stacked along N: MASK as stored for GEMM2 (K-major, K = h) IS the MN-major operand of GEMM3 (MN = h, K = q),
+//          byte for byte; T lives in TMEM for the whole kernel and is read once per CTA:
 //          dW0[h][k] = w1[h] T[h][k],  db0[h] = w1[h] T[h][35],  dW1[h] = sum_k W0ext[h][k] T[h][k]
+//          (a chain of accumulating MMAs into one accumulator costs ~75 cycles per instruction whatever N is -- measured --
+//          so the terms ride on N, 8 instructions per GEMM, and the two chains are issued interleaved)
 //   epi2   dL/dfeat rows -> shared memory -> 8 lanes per corner line: 8 x red.global.add.v4.f32 per lane into ONE grid
 //          (dL/d(prefix-summed grid), pushed down the LOD chain by the restriction cascade afterwards)
 //
@@ -28,34 +30,37 @@
 #include "sdf_tc.cuh"
 #include "internal.h"
 #include <cuda_bf16.h>
+#include <cstdio>
 
 namespace {
 
-#define BT_PRODUCERS 8
-#define BT_WARPS 16
+#ifndef BT_PRODUCERS
+#define BT_PRODUCERS 8                       // 4, 8 or 16 gather warps
+#endif
+#define BT_IPT (16 / BT_PRODUCERS)             // items (8 rows = two gather rounds) per producer warp per tile
+#define BT_WARPS (BT_PRODUCERS + 8)
 #define BT_THREADS (BT_WARPS * 32)
 #define BT_REC_COL (NGLOD_F + 4)                    // K columns 36..39 of an A row: zero in W0|b0 -> 16 free bytes per row
 // shared memory (bytes)
 #define BT_MASK_BYTES (128 * 128 * 2)               // MASK[q][h] bf16: (q/8)*2048 + (h/8)*128 + (q%8)*16 + (h%8)*2
-#define BT_S_TERM_BYTES (6 * 2048)                  // S[q][k] bf16, k padded to 48: (k/8)*2048 + q*16 + (k%8)*2
-#define BT_S_PAD (2 * BT_S_TERM_BYTES - TC_OPERAND_BYTES)     // S_hi + S_lo overwrite A_lo and run 1536 B past it
-#define BT_STAGE_BYTES (2 * TC_OPERAND_BYTES + BT_S_PAD + BT_MASK_BYTES)
-#define BT_SMEM_STAGE(s) (2 * TC_OPERAND_BYTES + (s) * BT_STAGE_BYTES)            // A_hi | A_lo (later S_hi S_lo) | pad | MASK
-#define BT_SMEM_MASK(s) (BT_SMEM_STAGE(s) + 2 * TC_OPERAND_BYTES + BT_S_PAD)
-#define BT_SMEM_B2 (BT_SMEM_STAGE(2))               // (W1 o W0)^T [f][h] bf16 x 3 terms: (f/8)*2048 + (h/8)*128 + (f%8)*16 + (h%8)*2
+#define BT_S_TERM_BYTES (5 * 2048)                  // S_t[q][k] bf16, k = 0..39: (k/8)*2048 + q*16 + (k%8)*2; S_lo follows S_hi
+#define BT_STAGE_BYTES (2 * TC_OPERAND_BYTES + BT_MASK_BYTES)
+#define BT_SMEM_STAGE(s) (2 * TC_OPERAND_BYTES + (s) * BT_STAGE_BYTES)            // A_hi | A_lo (later S_hi S_lo) | MASK
+#define BT_SMEM_MASK(s) (BT_SMEM_STAGE(s) + 2 * TC_OPERAND_BYTES)
+#define BT_SMEM_B2 (BT_SMEM_STAGE(2))               // (W1 o W0)^T [t,f][h] bf16, 3 terms t: ((32t+f)/8)*2048 + (h/8)*128 + (f%8)*16 + (h%8)*2
 #define BT_B2_TERM_BYTES (4 * 2048)
 #define BT_SMEM_W1 (BT_SMEM_B2 + 3 * BT_B2_TERM_BYTES)      // 128 floats + b1 (+ pad) = 528 B
 #define BT_SMEM_BAR (BT_SMEM_W1 + 528)              // arrival counters[2], done1[2], done2[2], rec_full[2] (8 B each)
 #define BT_SMEM_TMEMPTR (BT_SMEM_BAR + 8 * 8)
 #define BT_SMEM_BYTES (BT_SMEM_TMEMPTR + 16)
-static_assert(BT_S_PAD >= 0, "S must cover A_lo");
+static_assert(2 * BT_S_TERM_BYTES <= TC_OPERAND_BYTES, "S overwrites A_lo");
 static_assert(BT_SMEM_BYTES <= 232448, "shared memory budget");
 #define BT_STAGING_STRIDE 144                       // bytes per dL/dfeat row in the staging area (128 + 16: conflict-free row writes)
 static_assert(128 * BT_STAGING_STRIDE <= BT_MASK_BYTES, "staging area lives in the MASK region");
 // tensor memory (columns)
 #define BT_TMEM_D1(s) ((uint32_t)(s) * 128u)
-#define BT_TMEM_D2(s) (256u + (uint32_t)(s) * 32u)
-#define BT_TMEM_T(g) (320u + (uint32_t)(g) * 64u)
+#define BT_TMEM_D2(s) BT_TMEM_D1(s)                 // 96 columns: D1 is dead once epi1 has read it
+#define BT_TMEM_T(g) (256u + (uint32_t)(g) * 128u)  // 80 columns
 
 // instruction descriptors, kind::f16 with bf16 operands and an fp32 accumulator, M = 128
 #define BT_IDESC_BF16(N, AMN, BMN) ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(AMN) << 15) | ((uint32_t)(BMN) << 16) | \
@@ -75,6 +80,17 @@ __device__ __forceinline__ void bt_mma_bf16(uint32_t d_tmem, uint64_t adesc, uin
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// non-blocking: has the phase with this parity completed?
+__device__ __forceinline__ bool bt_mbar_test(uint32_t saddr, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(saddr), "r"(parity) : "memory");
+    return ok != 0;
 }
 
 // two fp32 -> one word of two bf16 (round to nearest even), `lo` at the lower address
@@ -97,6 +113,14 @@ __device__ __forceinline__ void bt_split8(const float (&v)[8], uint4& hi, uint4&
     hi = make_uint4(h[0], h[1], h[2], h[3]);
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
+
+// Phase timing for experiments (profiles/exp_bwd_timing.sh, "-DBT_TIMING"): block 0 prints the clock64() cycles one producer
+// warp and one service warp of each warpgroup spent per phase; compiled out otherwise.
+#ifdef BT_TIMING
+#define BT_TICK(i) do { const long long _t = clock64(); tm[i] += _t - t_last; t_last = _t; } while (0)
+#else
+#define BT_TICK(i) do { } while (0)
+#endif
 
 template <bool FUSED_LOSS>
 __global__ void __launch_bounds__(BT_THREADS, 1)
@@ -156,6 +180,11 @@ sdf_backward_tc_kernel(const NetDev net, const GradDev grad, const float* __rest
     const int ntiles = (int)((total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
     const long long tile_stride = (long long)gridDim.x * TC_TILE_ROWS;
     const int R = net.res[0];
+#ifdef BT_TIMING
+    long long tm[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long t_last = clock64();
+    const long long t_begin = t_last;
+#endif
 
     if (warp < BT_PRODUCERS) {
         // ------------------------------------------------------------------ producers (the last to arrive issues GEMM1)
@@ -164,8 +193,8 @@ sdf_backward_tc_kernel(const NetDev net, const GradDev grad, const float* __rest
         const int sub = lane >> 3, c = lane & 7;
         const float* grid = net.grids[0];
         const uint32_t b_hi = smem_u32(smem_tc + TC_SMEM_B_HI), b_lo = smem_u32(smem_tc + TC_SMEM_B_LO);
-        const int nitems = 2 * ntiles;
-        auto row_of = [&](int item) { return warp * 16 + (item & 1) * 8 + sub; };      // and row + 4
+        const int nitems = BT_IPT * ntiles;
+        auto row_of = [&](int item) { return warp * (8 * BT_IPT) + (item % BT_IPT) * 8 + sub; };      // and row + 4
         float4 rec0 = make_float4(0.f, 0.f, 0.f, 0.f), rec1 = rec0;
         TcLines<false> t0, t1;
         if (nitems > 0) {
@@ -177,23 +206,29 @@ sdf_backward_tc_kernel(const NetDev net, const GradDev grad, const float* __rest
             tc_issue_lines<false>(grid, R, __float_as_uint(rec1.x), c, t1);
         }
         for (int it = 0; it < nitems; ++it) {
-            const int T = it >> 1, s = T & 1;
+            const int T = it / BT_IPT, s = T & 1;
             char* a_hi = smem_tc + BT_SMEM_STAGE(s);
             char* a_lo = a_hi + TC_OPERAND_BYTES;
             const int row = row_of(it);
             const bool more = it + 1 < nitems;
+            const int T1 = (it + 1) / BT_IPT, s1 = T1 & 1;
+            const char* a_next = smem_tc + BT_SMEM_STAGE(s1);
             float4 nrec0 = make_float4(0.f, 0.f, 0.f, 0.f), nrec1 = nrec0;
-            if (more) {
-                const int T1 = (it + 1) >> 1, s1 = T1 & 1;
-                if (((it + 1) & 1) == 0) mbar_wait(rec_bar(s1), (uint32_t)((T1 >> 1) & 1));       // first item of the next tile
-                const char* a = smem_tc + BT_SMEM_STAGE(s1);
-                nrec0 = *reinterpret_cast<const float4*>(a + tc_elem_offset(row_of(it + 1), BT_REC_COL));
-                nrec1 = *reinterpret_cast<const float4*>(a + tc_elem_offset(row_of(it + 1) + 4, BT_REC_COL));
+            // the next item's loads are issued while this one is consumed -- unless it opens a tile whose set-up has not
+            // arrived yet: this tile must not wait for that (its GEMM1 would, and with it the set-up it is waiting for)
+            bool ahead = more;
+            if (more && (it + 1) % BT_IPT == 0) {
+                BT_TICK(0);
+                ahead = __shfl_sync(0xffffffffu, (int)bt_mbar_test(rec_bar(s1), (uint32_t)((T1 >> 1) & 1)), 0) != 0;
+            }
+            if (ahead) {
+                nrec0 = *reinterpret_cast<const float4*>(a_next + tc_elem_offset(row_of(it + 1), BT_REC_COL));
+                nrec1 = *reinterpret_cast<const float4*>(a_next + tc_elem_offset(row_of(it + 1) + 4, BT_REC_COL));
             }
             {
                 uint64_t acc01 = 0ull, acc23 = 0ull;
                 tc_consume_lines<false>(rec0, t0, acc01, acc23);
-                if (more) tc_issue_lines<false>(grid, R, __float_as_uint(nrec0.x), c, t0);
+                if (ahead) tc_issue_lines<false>(grid, R, __float_as_uint(nrec0.x), c, t0);
                 float4 acc;
                 f2_unpack(acc01, acc.x, acc.y); f2_unpack(acc23, acc.z, acc.w);
                 tc_store_split4_finite(a_hi, a_lo, tc_elem_offset(row, 4 * c), acc);
@@ -201,13 +236,12 @@ sdf_backward_tc_kernel(const NetDev net, const GradDev grad, const float* __rest
             {
                 uint64_t acc01 = 0ull, acc23 = 0ull;
                 tc_consume_lines<false>(rec1, t1, acc01, acc23);
-                if (more) tc_issue_lines<false>(grid, R, __float_as_uint(nrec1.x), c, t1);
+                if (ahead) tc_issue_lines<false>(grid, R, __float_as_uint(nrec1.x), c, t1);
                 float4 acc;
                 f2_unpack(acc01, acc.x, acc.y); f2_unpack(acc23, acc.z, acc.w);
                 tc_store_split4_finite(a_hi, a_lo, tc_elem_offset(row + 4, 4 * c), acc);
             }
-            rec0 = nrec0; rec1 = nrec1;
-            if (it & 1) {                                                            // this warp's 16 rows of tile T are in place
+            if (it % BT_IPT == BT_IPT - 1) {                                         // this warp's rows of tile T are in place
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
@@ -223,6 +257,16 @@ sdf_backward_tc_kernel(const NetDev net, const GradDev grad, const float* __rest
                 }
                 __syncwarp();
             }
+            if (more && !ahead) {
+                BT_TICK(0);
+                mbar_wait(rec_bar(s1), (uint32_t)((T1 >> 1) & 1));
+                BT_TICK(1);
+                nrec0 = *reinterpret_cast<const float4*>(a_next + tc_elem_offset(row_of(it + 1), BT_REC_COL));
+                nrec1 = *reinterpret_cast<const float4*>(a_next + tc_elem_offset(row_of(it + 1) + 4, BT_REC_COL));
+                tc_issue_lines<false>(grid, R, __float_as_uint(nrec0.x), c, t0);
+                tc_issue_lines<false>(grid, R, __float_as_uint(nrec1.x), c, t1);
+            }
+            rec0 = nrec0; rec1 = nrec1;
         }
     } else {
         // ------------------------------------------------------------------ service warpgroup g: stage g, tiles T = g (mod 2)
@@ -239,7 +283,8 @@ sdf_backward_tc_kernel(const NetDev net, const GradDev grad, const float* __rest
         const uint32_t lane_sel = (uint32_t)(ew * 32) << 16;
         const uint32_t t_d1 = tmem_base + BT_TMEM_D1(g) + lane_sel, t_d2 = tmem_base + BT_TMEM_D2(g) + lane_sel;
         const long long i_first = (long long)blockIdx.x * TC_TILE_ROWS + row;
-        float* ggrid = grad.grids[0];
+        // small grids: private copies per CTA group (the L2 atomic units serialise per address), folded by the launcher
+        float* ggrid = grad.priv ? grad.priv + (size_t)(blockIdx.x % grad.priv_copies) * grad.priv_stride : grad.grids[0];
         float acc_b1 = 0.f, acc_loss = 0.f;
         auto load_xyz = [&](int T, float& px, float& py, float& pz) {
             const long long i = i_first + (long long)T * tile_stride;
@@ -268,8 +313,10 @@ sdf_backward_tc_kernel(const NetDev net, const GradDev grad, const float* __rest
             float up = 0.f;                                // the label (fused loss) or the upstream gradient
             if (active) up = __ldg((FUSED_LOSS ? gt : grad_out) + i);
             load_xyz(T + 2, nx, ny, nz);
+            BT_TICK(0);
             mbar_wait(done1_bar(g), par);
             tc_fence_after_sync();
+            BT_TICK(1);
             // ---- epi1: d (the forward kernel's sums in the forward kernel's order), ReLU mask -> MASK rows
             float d;
             {
@@ -300,6 +347,7 @@ sdf_backward_tc_kernel(const NetDev net, const GradDev grad, const float* __rest
                 f2_unpack(d01, d0, d1); f2_unpack(d23, d2, d3);
                 d = w1s[NGLOD_H] + ((d0 + d1) + (d2 + d3));
             }
+            BT_TICK(2);
             float gd = 0.f;
             if (active) {
                 if (FUSED_LOSS) {
@@ -311,7 +359,7 @@ sdf_backward_tc_kernel(const NetDev net, const GradDev grad, const float* __rest
                 }
             }
             acc_b1 += gd;
-            // ---- S[q][k] = g_d in[q][k] (in as GEMM1 saw its leading term: the TF32 high part), bf16 hi + lo, k padded to 48
+            // ---- S[q][k] = g_d in[q][k] (in as GEMM1 saw its leading term: the TF32 high part), bf16 hi + lo
 #pragma unroll
             for (int c5 = 0; c5 < 5; ++c5) {
                 const float4 a = *reinterpret_cast<const float4*>(a_hi + tc_elem_offset(row, 8 * c5));
@@ -323,55 +371,58 @@ sdf_backward_tc_kernel(const NetDev net, const GradDev grad, const float* __rest
                 *reinterpret_cast<uint4*>(s_hi + c5 * 2048 + row * 16) = hi;
                 *reinterpret_cast<uint4*>(s_lo + c5 * 2048 + row * 16) = lo;
             }
-            *reinterpret_cast<uint4*>(s_hi + 5 * 2048 + row * 16) = make_uint4(0u, 0u, 0u, 0u);
-            *reinterpret_cast<uint4*>(s_lo + 5 * 2048 + row * 16) = make_uint4(0u, 0u, 0u, 0u);
             fence_proxy_async_smem();
             tc_fence_before_sync();
+            BT_TICK(3);
             named_bar_sync(1 + g, 128);
+            BT_TICK(4);
             if (ew == 0 && lane == 0) {
                 tc_fence_after_sync();
                 const uint32_t m_s = smem_u32(mask), b2_s = smem_u32(smem_tc + BT_SMEM_B2);
-                const uint32_t s_hi_s = smem_u32(s_hi), s_lo_s = smem_u32(s_lo);
-                // GEMM2: D2[q][f] = MASK (K-major: 8-row groups 2048 B apart, K chunks 128 B apart) x B2 terms
-                uint32_t acc = 0;
+                const uint32_t s_hi_s = smem_u32(s_hi);
+                // GEMM2: D2[q][t,f] = MASK (K-major: 8-row groups 2048 B apart, K chunks 128 B apart) x B2 (K-major, same strides)
+                // GEMM3: T[h][t,k] += MASK^T (MN-major: h chunks 128 B apart, groups of 8 queries 2048 B apart)
+                //                     x S (MN-major: k chunks 2048 B apart, groups of 8 queries 128 B apart)
+                // two independent accumulation chains, issued alternately
 #pragma unroll
-                for (int term = 0; term < 3; ++term)
-#pragma unroll
-                    for (int ks = 0; ks < NGLOD_H / 16; ++ks) {
-                        bt_mma_bf16(tmem_base + BT_TMEM_D2(g), bt_desc(m_s + ks * 256, 128, 2048),
-                                    bt_desc(b2_s + term * BT_B2_TERM_BYTES + ks * 256, 128, 2048), BT_IDESC_BF16(32, 0, 0), acc);
-                        acc = 1;
-                    }
-                // GEMM3: T[h][k] += MASK^T (MN-major: h chunks 128 B apart, groups of 8 queries 2048 B apart)
-                //                   x S (MN-major: k chunks 2048 B apart, groups of 8 queries 128 B apart)
-                acc = T != g;
-#pragma unroll
-                for (int term = 0; term < 2; ++term)
-#pragma unroll
-                    for (int ks = 0; ks < TC_TILE_ROWS / 16; ++ks) {
-                        bt_mma_bf16(tmem_base + BT_TMEM_T(g), bt_desc(m_s + ks * 4096, 2048, 128),
-                                    bt_desc((term ? s_lo_s : s_hi_s) + ks * 256, 128, 2048), BT_IDESC_BF16(48, 1, 1), acc);
-                        acc = 1;
-                    }
+                for (int ks = 0; ks < NGLOD_H / 16; ++ks) {
+                    bt_mma_bf16(tmem_base + BT_TMEM_D2(g), bt_desc(m_s + ks * 256, 128, 2048),
+                                bt_desc(b2_s + ks * 256, 128, 2048), BT_IDESC_BF16(96, 0, 0), ks != 0);
+                    bt_mma_bf16(tmem_base + BT_TMEM_T(g), bt_desc(m_s + ks * 4096, 2048, 128),
+                                bt_desc(s_hi_s + ks * 256, 128, 2048), BT_IDESC_BF16(80, 1, 1), (T != g) | (ks != 0));
+                }
                 tc_commit(done2_bar(g));
             }
+            BT_TICK(5);
             mbar_wait(done2_bar(g), par);
             tc_fence_after_sync();
+            BT_TICK(6);
+            // ---- epi2: dL/dfeat[q][.] = g_d (D2 term 2 + term 1 + term 0), read before the stage is handed back (D2 lives in
+            //      D1's columns, which GEMM1 of tile T+2 overwrites)
+            float gin[32];
+            {
+                float v[32];
+                tmem_ld32(t_d2 + 64, gin);
+                tmem_ld32(t_d2 + 32, v);
+#pragma unroll
+                for (int k = 0; k < 32; ++k) gin[k] += v[k];
+                tmem_ld32(t_d2, v);
+#pragma unroll
+                for (int k = 0; k < 32; ++k) gin[k] = gd * (gin[k] + v[k]);
+                tc_fence_before_sync();
+            }
             // ---- the stage's operands are dead: set up tile T+2 in it (the producers fill it while this warpgroup scatters)
             float4 rec_next = make_float4(0.f, 0.f, 0.f, 0.f);
             if (T + 2 < ntiles) rec_next = setup(T + 2, nx, ny, nz);
-            // ---- epi2: dL/dfeat[q][.] = g_d D2[q][.] -> staging rows
             {
-                float v[32];
-                tmem_ld32(t_d2, v);
-                tc_fence_before_sync();
                 float4* dst = reinterpret_cast<float4*>(staging + row * BT_STAGING_STRIDE);
 #pragma unroll
-                for (int k4 = 0; k4 < 8; ++k4)
-                    dst[k4] = make_float4(gd * v[4 * k4], gd * v[4 * k4 + 1], gd * v[4 * k4 + 2], gd * v[4 * k4 + 3]);
+                for (int k4 = 0; k4 < 8; ++k4) dst[k4] = make_float4(gin[4 * k4], gin[4 * k4 + 1], gin[4 * k4 + 2], gin[4 * k4 + 3]);
             }
             __syncwarp();
+            BT_TICK(7);
             // ---- scatter: this warp's 32 rows, 4 queries per round x 8 lanes per corner line
+#ifndef BT_EXP_NOSCATTER
             if (ggrid) {
                 const unsigned live = __ballot_sync(0xffffffffu, active && gd != 0.f);
                 const int sub = lane >> 3, c = lane & 7;
@@ -400,9 +451,12 @@ sdf_backward_tc_kernel(const NetDev net, const GradDev grad, const float* __rest
                     }
                 }
             }
+#endif
             rec_cur = rec_next;
+            BT_TICK(8);
             named_bar_sync(1 + g, 128);        // every warp is done with the staging rows before epi1 of T+2 rewrites the MASK
         }
+        BT_TICK(9);
         // ---- flush the head gradients of this warpgroup's tiles: thread = hidden unit
         if (g < ntiles) {
             const int h = row;
@@ -410,14 +464,23 @@ sdf_backward_tc_kernel(const NetDev net, const GradDev grad, const float* __rest
             float tv[40];
             {
                 float v[32];
-                tmem_ld32(t_T, v);
-                uint32_t u[8];
-                tmem_ld8_async(t_T + 32, u);
+                uint32_t u[2][8], w[16];
+                tmem_ld32(t_T, v);                       // hi part, k = 0..31
+                tmem_ld8_async(t_T + 32, u[0]);          // hi part, k = 32..39
+                tmem_ld8_async(t_T + 40, u[1]);          // lo part, k = 0..7
                 tmem_ld_wait();
 #pragma unroll
                 for (int k = 0; k < 32; ++k) tv[k] = v[k];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) tv[32 + k] = __uint_as_float(u[k]);
+                for (int k = 0; k < 8; ++k) { tv[32 + k] = __uint_as_float(u[0][k]); tv[k] += __uint_as_float(u[1][k]); }
+                tmem_ld16_async(t_T + 48, w);            // lo part, k = 8..23
+                tmem_ld_wait();
+#pragma unroll
+                for (int k = 0; k < 16; ++k) tv[8 + k] += __uint_as_float(w[k]);
+                tmem_ld16_async(t_T + 64, w);            // lo part, k = 24..39
+                tmem_ld_wait();
+#pragma unroll
+                for (int k = 0; k < 16; ++k) tv[24 + k] += __uint_as_float(w[k]);
             }
             tc_fence_before_sync();
             const int in_dim = net.pos_invariant ? NGLOD_F : NGLOD_F + 3;
@@ -450,6 +513,16 @@ sdf_backward_tc_kernel(const NetDev net, const GradDev grad, const float* __rest
             if (FUSED_LOSS && loss_out) atomicAdd(loss_out, acc_loss);
         }
     }
+#ifdef BT_TIMING
+    if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == BT_PRODUCERS || warp == BT_PRODUCERS + 4)) {
+        const long long tot = clock64() - t_begin;
+        if (warp == 0)
+            printf("producer: tiles %d total %lld | work %lld wait_rec %lld\n", ntiles, tot, tm[0], tm[1]);
+        else
+            printf("service %d: total %lld | other %lld wait_done1 %lld epi1 %lld S %lld bar %lld issue %lld wait_done2 %lld setup+epi2 %lld "
+                   "scatter %lld endbar %lld\n", (warp - BT_PRODUCERS) >> 2, tot, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm[6], tm[7], tm[8], tm[9]);
+    }
+#endif
     tc_epilogue_free(tmem_base);
 }
 

@@ -65,7 +65,8 @@ class _SdfFunction(torch.autograd.Function):
         dec_grads = [torch.zeros_like(p) if needs[3 + n_grids + k] else None for k, p in enumerate(dec_params)]
         gx = ops.sdf_backward(view, lod, x, grad_out.contiguous(), grid_grads + [None] * (view.num_lods - n_grids),
                               tuple(dec_grads), want_grad_x=needs[0],
-                              summed_scratch=module.summed_grad_scratch() if view.summed is not None else None)
+                              summed_scratch=module.summed_grad_scratch() if view.summed is not None else None,
+                              scatter_scratch=module.scatter_scratch() if view.summed is not None else None)
         return (gx, None, None, *grid_grads, *dec_grads)
 
 
@@ -161,6 +162,16 @@ class OctreeSDF(BaseLOD):
         if sc is None or any(t.device != f.fm.device for t, f in zip(sc, self.features)):
             sc = [torch.zeros_like(f.fm.data, memory_format=torch.preserve_format) for f in self.features]
             self._summed_scratch = sc
+        return sc
+
+    def scatter_scratch(self):
+        """Zero-filled 1 MB buffer for the private scatter copies of the small grids (nglod_net_grad_t.scatter_scratch);
+        the kernels leave it zero, so it is allocated once."""
+        sc = getattr(self, "_scatter_scratch", None)
+        dev = self.features[0].fm.device
+        if sc is None or sc.device != dev:
+            sc = torch.zeros(1 << 18, dtype=torch.float32, device=dev)
+            self._scatter_scratch = sc
         return sc
 
     def summed_state_dict(self, lod=None):

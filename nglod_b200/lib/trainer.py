@@ -92,7 +92,7 @@ class FusedTrainer:
         for l in lods:
             mask |= 1 << l
         ops.sdf_train_step(view, mask | _lib.LOSS_PER_LOD, pts, gts, 1.0 / batch, grid_grads, dec_grads, self.lod_loss,
-                           summed_scratch=scratch)
+                           summed_scratch=scratch, scatter_scratch=net.scatter_scratch() if scratch is not None else None)
         torch.sum(self.lod_loss, dim=0, keepdim=True, out=self.loss)
 
     def _signature(self):

@@ -104,10 +104,17 @@ class NetView:
         return self.struct.num_lods
 
 
-def make_grad_struct(view, grid_grads, dec_grads, summed_scratch=None):
+def make_grad_struct(view, grid_grads, dec_grads, summed_scratch=None, scatter_scratch=None):
     """grid_grads[i] / dec_grads[i] = (gw0, gb0, gw1, gb1) or None entries.  summed_scratch[i]: all-zero buffers shaped
-    like the grids (nglod_net_grad_t.summed) that enable the single-grid backward; zero again when the call returns."""
+    like the grids (nglod_net_grad_t.summed) that enable the single-grid backward; zero again when the call returns.
+    scatter_scratch: an all-zero flat fp32 buffer (nglod_net_grad_t.scatter_scratch) for private scatter copies of the
+    small grids; zero again when the call returns."""
     g = NetGradStruct()
+    if scatter_scratch is not None:
+        if scatter_scratch.dtype != torch.float32 or not scatter_scratch.is_cuda or not scatter_scratch.is_contiguous():
+            raise RuntimeError("scatter_scratch must be a contiguous fp32 CUDA tensor (zero-filled)")
+        g.scatter_scratch = scatter_scratch.data_ptr()
+        g.scatter_scratch_floats = scatter_scratch.numel()
     for i, t in enumerate(summed_scratch or []):
         if t is not None:
             if t.shape != view.grids[i].shape or t.dtype != torch.float32 or not t.is_cuda or \
@@ -200,7 +207,7 @@ def sdf_features(view, lod, x):
     return out
 
 
-def sdf_backward(view, lod, x, grad_out, grid_grads, dec_grad, want_grad_x=False, summed_scratch=None):
+def sdf_backward(view, lod, x, grad_out, grid_grads, dec_grad, want_grad_x=False, summed_scratch=None, scatter_scratch=None):
     """Accumulate into grid_grads[0..lod] (channels_last_3d, like the params) and dec_grad=(gw0,gb0,gw1,gb1)."""
     lib = _lib.load()
     x = _f32c(x, "x")
@@ -208,7 +215,7 @@ def sdf_backward(view, lod, x, grad_out, grid_grads, dec_grad, want_grad_x=False
     n = x.shape[0]
     dec = [None] * view.num_lods
     dec[lod] = dec_grad
-    gs = make_grad_struct(view, grid_grads, dec, summed_scratch)
+    gs = make_grad_struct(view, grid_grads, dec, summed_scratch, scatter_scratch)
     gx = torch.empty_like(x) if want_grad_x else None
     with torch.cuda.device(x.device):
         _lib.check(lib.nglod_sdf_backward(ctypes.byref(view.struct), lod, _ptr(x), n, _ptr(grad_out),
@@ -216,12 +223,13 @@ def sdf_backward(view, lod, x, grad_out, grid_grads, dec_grad, want_grad_x=False
     return gx
 
 
-def sdf_train_step(view, lod_mask, x, gt, loss_scale, grid_grads, dec_grads, loss_out=None, summed_scratch=None):
+def sdf_train_step(view, lod_mask, x, gt, loss_scale, grid_grads, dec_grads, loss_out=None, summed_scratch=None,
+                   scatter_scratch=None):
     lib = _lib.load()
     x = _f32c(x, "x")
     gt = _f32c(gt, "gt").reshape(-1)
     n = x.shape[0]
-    gs = make_grad_struct(view, grid_grads, dec_grads, summed_scratch)
+    gs = make_grad_struct(view, grid_grads, dec_grads, summed_scratch, scatter_scratch)
     with torch.cuda.device(x.device):
         _lib.check(lib.nglod_sdf_train_step(ctypes.byref(view.struct), lod_mask, _ptr(x), _ptr(gt), n,
                                             float(loss_scale), ctypes.byref(gs), _ptr(loss_out), _stream()),

@@ -22,6 +22,7 @@ for n in (1 << 20, 500000, 65536, 4096, 512):
     view = net.net_view(inference=False)
     grid_grads = [torch.zeros_like(f.fm.data, memory_format=torch.preserve_format) for f in net.features]
     scratch = [torch.zeros_like(f.fm.data, memory_format=torch.preserve_format) for f in net.features]
+    ss = torch.zeros(1 << 18, device=dev)
     dec_grads = [tuple(torch.zeros_like(p) for p in net.decoder_params(l)) for l in range(5)]
     t_full = timeit(lambda: ops.sdf_backward(view, 4, xq, gq, grid_grads, dec_grads[4], summed_scratch=scratch))
     summed = view.summed[4]
@@ -32,6 +33,6 @@ for n in (1 << 20, 500000, 65536, 4096, 512):
     t_k = timeit(lambda: ops.sdf_backward(v1s, 0, xq, gq, gg, dec_grads[4], summed_scratch=sc))
     t_nog = timeit(lambda: ops.sdf_backward(v1s, 0, xq, gq, [None], dec_grads[4], summed_scratch=sc))
     loss = torch.zeros(1, device=dev)
-    t_step = timeit(lambda: ops.sdf_train_step(view, 0x1f, xq, gq, 1.0 / n, grid_grads, dec_grads, loss, summed_scratch=scratch))
+    t_step = timeit(lambda: ops.sdf_train_step(view, 0x1f, xq, gq, 1.0 / n, grid_grads, dec_grads, loss, summed_scratch=scratch, scatter_scratch=ss))
     print(f"n={n:8d}: backward lod4 + cascade {t_full:.3f} ms | one-grid kernel + copy-out {t_k:.3f} | no grid grads {t_nog:.3f} | "
           f"5-head train step {t_step:.3f} ms", flush=True)

@@ -169,6 +169,34 @@ def test_autograd_backward_vs_golden(rand5, sum_lods):
             assert all(float(t.abs().max()) == 0.0 for t in net.summed_grad_scratch())
 
 
+def test_small_grid_private_scatter_copies(rand5):
+    """Heads of the 4^3 / 8^3 levels: with nglod_net_grad_t.scatter_scratch the CTAs scatter into private copies that a fold
+    kernel sums -- same gradients as the single-copy scatter (fp32 summation order aside), scratch handed back zeroed."""
+    net, _ = rand5_model(DEV)
+    g = torch.Generator(device=DEV).manual_seed(5)
+    n = 120000
+    x = torch.rand(n, 3, device=DEV, generator=g) * 2 - 1
+    go = torch.randn(n, device=DEV, generator=g) / n
+    view = net.net_view(inference=False)
+    assert view.summed is not None
+    ss = net.scatter_scratch()
+    for lod in (0, 1):
+        res = []
+        for scratch in (None, ss):
+            gg = [torch.zeros_like(f.fm.data, memory_format=torch.preserve_format) for f in net.features]
+            dg = tuple(torch.zeros_like(p) for p in net.decoder_params(lod))
+            ops.sdf_backward(view, lod, x, go, gg, dg, summed_scratch=net.summed_grad_scratch(), scatter_scratch=scratch)
+            res.append((gg, dg))
+        for i in range(lod + 1):
+            a, b = res[0][0][i], res[1][0][i]
+            assert float(a.abs().max()) > 0
+            assert float((a - b).abs().max()) <= 2e-6 * float(a.abs().max())
+        for a, b in zip(res[0][1], res[1][1]):
+            assert float((a - b).abs().max()) <= 1e-5 * float(a.abs().max())
+        assert float(ss.abs().max()) == 0.0
+        assert all(float(t.abs().max()) == 0.0 for t in net.summed_grad_scratch())
+
+
 def test_grad_x_autodiff_and_finitediff_vs_golden(rand5):
     from nglod_b200.lib.diffutils import gradient
     net, _ = rand5_model(DEV)
