@@ -330,399 +330,6 @@ sdf_backward_kernel(const NetDev net, const GradDev grad, const float* __restric
     }
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// Backward, second generation (no dL/dx): 16 warps per CTA, head gradients on the tensor cores.
-//
-// The first-generation kernel above keeps dW0|db0 as 144 register accumulators per lane (255 registers -> 8 warps per
-// SM, latency-bound at 39 % issue).  Here the only state a query leaves behind for the head gradients is its upstream
-// gradient g_d and the 128 ReLU mask bits:
-//     T[h][k]  = sum_q g_d(q) [pre_qh > 0] in_qk           (k = 0..35, in_q35 = 1)       <- one GEMM over the queries
-//     dW0[h][k] = w1[h] T[h][k],  db0[h] = w1[h] T[h][35],  dW1[h] = sum_k W0ext[h][k] T[h][k]   (pre = W0ext . in)
-// and T is accumulated CTA-wide with mma.sync.m16n8k8 TF32 (rna-rounded operands, fp32 accumulate): warp w owns hidden
-// units [16 (w%8), +16) and the queries of warps [8 (w/8), +8) of the batch -> 20 accumulator registers.  The two
-// per-query GEMMs run on mma.sync as well, 16 queries at a time per warp: the forward recompute pre = in . W0ext^T in
-// 3xTF32 (d feeds the loss gradient, so it keeps fp32-level accuracy), dL/d(features) = g_h . W0 likewise (its terms cancel heavily),
-// with its A fragments built in registers from the mask bits of the pre fragments.  128 registers, 16 warps per SM.
-#define BW2_WARPS 16
-#define BW2_THREADS (BW2_WARPS * 32)
-#define BW2_PER_WARP (SDF_SMEM_PER_WARP + 32 * 4 + 32)           // tile, idx, mask words [32][4], gd[32]
-#define BW2_WLO_OFF (SDF_SMEM_WARP_OFF + BW2_WARPS * BW2_PER_WARP)   // TF32 low parts of W0ext (the staged copy keeps the high parts)
-#define BW2_SMEM_BYTES ((BW2_WLO_OFF + SDF_W0_FLOATS) * 4)
-#ifndef BW2_SMEM_GRID_MAX           // -DBW2_SMEM_GRID_MAX=23328 also takes R = 8 (93 KB): untested, see profiles/NEXT.md
-#define BW2_SMEM_GRID_MAX 4000      // floats: a 5^3 x 32 grid (R = 4) accumulated per CTA in shared memory
-#endif
-
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-    uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r;
-}
-__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
-
-// SPARSE: the features come from (and their gradients go to) the corner rows of a sparse octree model -- gather and
-// scatter walk the query's parent chain (sparse_core.cuh); `net` is then sp.sn.dec, the decoder of the LOD.
-struct SparseBwd {
-    SparseDev sn;
-    const int* pidx;        // [n] voxel index within the LOD's level
-    float* grad_cf;         // [NC, F]
-};
-
-template <bool FUSED_LOSS, bool SPARSE>
-__global__ void __launch_bounds__(BW2_THREADS, 1)
-sdf_backward_mma_kernel(const NetDev net, const GradDev grad, const float* __restrict__ x, const long long n,
-                        const float* __restrict__ grad_out, const float* __restrict__ gt, const float loss_scale,
-                        float* __restrict__ loss_out, const SparseBwd sp, const int lpw, const int smem_grid_floats) {
-    // lpw = queries per warp per batch: 32, or 8 when the whole call is too small to give every SM a 512-query batch
-    // (a batch is then 128 queries: the kernel's serial phases are 3-4x shorter and 4x as many CTAs share the work)
-    extern __shared__ __align__(16) float smem[];
-    sdf_stage_weights(net, smem);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* wbase = smem + SDF_SMEM_WARP_OFF + warp * BW2_PER_WARP;
-    float* tile = wbase;
-    int* idx = reinterpret_cast<int*>(wbase + SDF_TILE_FLOATS);
-    uint32_t* maskw = reinterpret_cast<uint32_t*>(wbase + SDF_SMEM_PER_WARP);
-    float* sgd = wbase + SDF_SMEM_PER_WARP + 32 * 4;
-    for (int e = lane; e < BW2_PER_WARP; e += 32) wbase[e] = 0.f;
-    // A grid of R = 4 has 125 nodes: half a million queries scattering into its 16 KB serialise in the L2 atomic units (the
-    // LOD-0 launch of a training step took 0.79 ms against 0.37 ms for every other level).  Such a grid (smem_grid_floats
-    // > 0, level 0 only) is accumulated in shared memory and flushed once per CTA.
-    float* sgrid = smem + BW2_SMEM_BYTES / 4;
-    for (int e = threadIdx.x; e < smem_grid_floats; e += blockDim.x) sgrid[e] = 0.f;
-    __syncthreads();
-    // split the staged W0ext once: smem[e] = TF32 high part, wlo[e] = TF32 of the remainder (B fragments of the 3xTF32 GEMMs)
-    float* wlo = smem + BW2_WLO_OFF;
-    for (int e = threadIdx.x; e < SDF_W0_FLOATS; e += blockDim.x) {
-        const float w = smem[e];
-        const float hi = __uint_as_float(to_tf32(w));
-        smem[e] = hi;
-        wlo[e] = __uint_as_float(to_tf32(w - hi));
-    }
-    __syncthreads();
-    const float* sw1 = smem + SDF_SMEM_W1_OFF;
-    const float sb1 = smem[SDF_SMEM_B1_OFF];
-
-    // phase-C ownership: hidden units [16 mt, 16 mt + 16), queries of warps [8 qh, 8 qh + 8) of every CTA batch
-    const int mt = warp & 7, qh = warp >> 3;
-    const int g = lane >> 2, t = lane & 3;
-    float accT[5][4];
-#pragma unroll
-    for (int nt = 0; nt < 5; ++nt)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) accT[nt][i] = 0.f;
-    float acc_b1 = 0.f, acc_loss = 0.f;
-
-    const long long batch = (long long)BW2_WARPS * lpw;
-    for (long long base0 = (long long)blockIdx.x * batch; base0 < n; base0 += (long long)gridDim.x * batch) {
-        const long long i = base0 + warp * lpw + lane;
-        bool active = lane < lpw && i < n;
-        int pv = 0;
-        if constexpr (SPARSE) {      // pidx < 0 (point outside the octree): the row is inert -- no gather, no loss, no gradient
-            if (active) pv = __ldg(sp.pidx + i);
-            active = active && pv >= 0;
-        }
-        const unsigned live_rows = __ballot_sync(0xffffffffu, active);
-        float px = 0.f, py = 0.f, pz = 0.f;
-        if (active) { px = __ldg(x + 3 * i); py = __ldg(x + 3 * i + 1); pz = __ldg(x + 3 * i + 2); }
-        // ---- A: gather
-        int vrow = 0;
-        if constexpr (SPARSE) {
-            vrow = sp.sn.vox_off + (active ? pv : 0);
-            const unsigned live = __ballot_sync(0xffffffffu, active);
-            const int n_live = __popc(live);
-            if (active) {
-                idx[__popc(live & ((1u << lane) - 1u))] = lane;
-                *reinterpret_cast<float4*>(tile + lane * NGLOD_KPAD + NGLOD_F) = make_float4(px, py, pz, 1.f);
-            }
-            __syncwarp();
-            const int sub = lane >> 3, c = lane & 7;
-            for (int r = 0; r * 4 < n_live; ++r) {
-                const int slot = r * 4 + sub;
-                const bool valid = slot < n_live;
-                const int q = idx[valid ? slot : 0];
-                const float qx = __shfl_sync(0xffffffffu, px, q), qy = __shfl_sync(0xffffffffu, py, q);
-                const float qz = __shfl_sync(0xffffffffu, pz, q);
-                const int qv = __shfl_sync(0xffffffffu, vrow, q);
-                if (valid) *reinterpret_cast<float4*>(tile + q * NGLOD_KPAD + 4 * c) = sparse_gather4(sp.sn, qx, qy, qz, qv, c);
-            }
-            __syncwarp();
-        } else {
-            warp_gather_tile(net, px, py, pz, active, tile, idx, lane);
-        }
-        if (!active) {   // keep inactive rows finite and inert
-#pragma unroll
-            for (int k4 = 0; k4 < NGLOD_KPAD / 4; ++k4)
-                *reinterpret_cast<float4*>(tile + lane * NGLOD_KPAD + 4 * k4) = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        // ---- B: the decoder's two GEMMs on the tensor cores (mma.sync m16n8k8 TF32), 16 queries (one m-tile) at a time:
-        //      pre[q][h] = in[q] . W0ext[h]   3xTF32 (A_lo B_hi + A_hi B_lo + A_hi B_hi: d feeds the loss gradient)
-        //      g_in[q][f] = sum_h g_h[q][h] W0[h][f]   single TF32 pass; its A fragments are built in registers from the
-        //      ReLU mask bits of the pre fragments (hidden units of a k-step permuted identically in A and B)
-        __syncwarp();
-        float ginf[2][4][4];
-#pragma unroll
-        for (int m = 0; m < 2; ++m) {
-            if (16 * m >= lpw) {                                      // no query rows in this m-tile (warp-uniform)
-#pragma unroll
-                for (int nf = 0; nf < 4; ++nf)
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) ginf[m][nf][e] = 0.f;
-                continue;
-            }
-            const int rA = 16 * m + g, rB = rA + 8;                   // this lane's two query rows of the m-tile
-            uint32_t ahi[5][4], alo[5][4];
-#pragma unroll
-            for (int ks = 0; ks < 5; ++ks) {
-                const int k0 = 8 * ks + t, k1 = k0 + 4;
-                const float v[4] = {tile[rA * NGLOD_KPAD + k0], tile[rB * NGLOD_KPAD + k0],
-                                    k1 < NGLOD_KPAD ? tile[rA * NGLOD_KPAD + k1] : 0.f,
-                                    k1 < NGLOD_KPAD ? tile[rB * NGLOD_KPAD + k1] : 0.f};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    ahi[ks][e] = to_tf32(v[e]);
-                    alo[ks][e] = to_tf32(v[e] - __uint_as_float(ahi[ks][e]));
-                }
-            }
-            uint32_t bitsA = 0u, bitsB = 0u;                          // bit 2n+e: pre(row, hidden 8n + 2t + e) > 0
-            float dA = 0.f, dB = 0.f;
-#pragma unroll
-            for (int nc = 0; nc < 2; ++nc) {
-                float acc[8][4];
-#pragma unroll
-                for (int n8 = 0; n8 < 8; ++n8)
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) acc[n8][e] = 0.f;
-#pragma unroll
-                for (int ks = 0; ks < 5; ++ks) {
-                    const int k0 = 8 * ks + t, k1 = k0 + 4;
-#pragma unroll
-                    for (int n8 = 0; n8 < 8; ++n8) {
-                        const int h = 8 * (8 * nc + n8) + g;
-                        uint32_t bhi[2], blo[2];
-                        bhi[0] = __float_as_uint(smem[h * NGLOD_KPAD + k0]);
-                        blo[0] = __float_as_uint(wlo[h * NGLOD_KPAD + k0]);
-                        bhi[1] = k1 < NGLOD_KPAD ? __float_as_uint(smem[h * NGLOD_KPAD + k1]) : 0u;
-                        blo[1] = k1 < NGLOD_KPAD ? __float_as_uint(wlo[h * NGLOD_KPAD + k1]) : 0u;
-                        mma_tf32_16x8x8(acc[n8], alo[ks], bhi);
-                        mma_tf32_16x8x8(acc[n8], ahi[ks], blo);
-                        mma_tf32_16x8x8(acc[n8], ahi[ks], bhi);
-                    }
-                }
-#pragma unroll
-                for (int n8 = 0; n8 < 8; ++n8) {
-                    const int n = 8 * nc + n8;
-                    const float2 w1p = *reinterpret_cast<const float2*>(sw1 + 8 * n + 2 * t);
-                    if (FUSED_LOSS) {
-                        dA = fmaf(w1p.x, fmaxf(acc[n8][0], 0.f), dA); dA = fmaf(w1p.y, fmaxf(acc[n8][1], 0.f), dA);
-                        dB = fmaf(w1p.x, fmaxf(acc[n8][2], 0.f), dB); dB = fmaf(w1p.y, fmaxf(acc[n8][3], 0.f), dB);
-                    }
-                    bitsA |= ((acc[n8][0] > 0.f ? 1u : 0u) | (acc[n8][1] > 0.f ? 2u : 0u)) << (2 * n);
-                    bitsB |= ((acc[n8][2] > 0.f ? 1u : 0u) | (acc[n8][3] > 0.f ? 2u : 0u)) << (2 * n);
-                }
-            }
-            // d of the two rows (sum over the 4 lanes that share a row), upstream gradients
-            const long long iA = base0 + warp * lpw + rA, iB = base0 + warp * lpw + rB;
-            // a row takes part iff its lane is active (in range and, on the sparse path, inside the octree): inert rows add
-            // no loss, no upstream gradient, hence no parameter gradient
-            const bool okA = (live_rows >> rA) & 1u, okB = (live_rows >> rB) & 1u;
-            float gdA = 0.f, gdB = 0.f;
-            if (FUSED_LOSS) {
-                dA += __shfl_xor_sync(0xffffffffu, dA, 1); dA += __shfl_xor_sync(0xffffffffu, dA, 2);
-                dB += __shfl_xor_sync(0xffffffffu, dB, 1); dB += __shfl_xor_sync(0xffffffffu, dB, 2);
-                if (okA) { const float diff = (dA + sb1) - __ldg(gt + iA); gdA = 2.f * diff * loss_scale;
-                           if (t == 0) acc_loss = fmaf(diff * diff, loss_scale, acc_loss); }
-                if (okB) { const float diff = (dB + sb1) - __ldg(gt + iB); gdB = 2.f * diff * loss_scale;
-                           if (t == 0) acc_loss = fmaf(diff * diff, loss_scale, acc_loss); }
-            } else {
-                if (okA) gdA = __ldg(grad_out + iA);
-                if (okB) gdB = __ldg(grad_out + iB);
-            }
-            if (t == 0) { acc_b1 += gdA + gdB; sgd[rA] = gdA; sgd[rB] = gdB; }
-            // ReLU mask words for phase C: word w = hidden [32w, 32w+32); this lane holds the bit pairs (2t, 2t+1) of
-            // every 8-wide block; OR over the 4 lanes of the row
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-                uint32_t wa = 0u, wb = 0u;
-#pragma unroll
-                for (int nn = 0; nn < 4; ++nn) {
-                    wa |= ((bitsA >> (8 * w + 2 * nn)) & 3u) << (8 * nn + 2 * t);
-                    wb |= ((bitsB >> (8 * w + 2 * nn)) & 3u) << (8 * nn + 2 * t);
-                }
-                wa |= __shfl_xor_sync(0xffffffffu, wa, 1); wa |= __shfl_xor_sync(0xffffffffu, wa, 2);
-                wb |= __shfl_xor_sync(0xffffffffu, wb, 1); wb |= __shfl_xor_sync(0xffffffffu, wb, 2);
-                if (t == 0) { maskw[rA * 4 + w] = wa; maskw[rB * 4 + w] = wb; }
-            }
-            // g_in of the m-tile
-#pragma unroll
-            for (int nf = 0; nf < 4; ++nf)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) ginf[m][nf][e] = 0.f;
-#pragma unroll 4
-            for (int n = 0; n < 16; ++n) {
-                const int h0 = 8 * n + 2 * t;                                  // A/B "column t" = h0, "column t+4" = h0 + 1
-                const float2 w1p = *reinterpret_cast<const float2*>(sw1 + h0);
-                const float av[4] = {((bitsA >> (2 * n)) & 1u) ? gdA * w1p.x : 0.f, ((bitsB >> (2 * n)) & 1u) ? gdB * w1p.x : 0.f,
-                                     ((bitsA >> (2 * n + 1)) & 1u) ? gdA * w1p.y : 0.f, ((bitsB >> (2 * n + 1)) & 1u) ? gdB * w1p.y : 0.f};
-                uint32_t a[4], al[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) { a[e] = to_tf32(av[e]); al[e] = to_tf32(av[e] - __uint_as_float(a[e])); }
-#pragma unroll
-                for (int nf = 0; nf < 4; ++nf) {
-                    uint32_t bb[2], bl[2];
-                    bb[0] = __float_as_uint(smem[h0 * NGLOD_KPAD + 8 * nf + g]);
-                    bl[0] = __float_as_uint(wlo[h0 * NGLOD_KPAD + 8 * nf + g]);
-                    bb[1] = __float_as_uint(smem[(h0 + 1) * NGLOD_KPAD + 8 * nf + g]);
-                    bl[1] = __float_as_uint(wlo[(h0 + 1) * NGLOD_KPAD + 8 * nf + g]);
-                    mma_tf32_16x8x8(ginf[m][nf], al, bb);        // 3xTF32: the terms of g_in cancel heavily, a single pass
-                    mma_tf32_16x8x8(ginf[m][nf], a, bl);         // left 2.4e-4 of max|grad| on the grid gradients
-                    mma_tf32_16x8x8(ginf[m][nf], a, bb);
-                }
-            }
-        }
-        __syncthreads();
-        // ---- C: T[h][k] += sum_q g_d(q) mask(q,h) in(q,k) on the tensor cores
-#pragma unroll 2
-        for (int ks = 0; ks < 32; ++ks) {
-            const int wq = qh * 8 + (ks >> 2);                        // warp that owns these 8 queries
-            const int r0 = (ks & 3) * 8;                              // their first row in that warp's tile
-            const float* wb = smem + SDF_SMEM_WARP_OFF + wq * BW2_PER_WARP;
-            const uint32_t* mq = reinterpret_cast<const uint32_t*>(wb + SDF_SMEM_PER_WARP);
-            const float* gq = wb + SDF_SMEM_PER_WARP + 32 * 4;
-            const float gd0 = gq[r0 + t], gd1 = gq[r0 + t + 4];
-            const uint32_t m0 = mq[(r0 + t) * 4 + (mt >> 1)] >> ((mt & 1) * 16);
-            const uint32_t m1 = mq[(r0 + t + 4) * 4 + (mt >> 1)] >> ((mt & 1) * 16);
-            uint32_t a[4];
-            a[0] = to_tf32(((m0 >> g) & 1u) ? gd0 : 0.f);
-            a[1] = to_tf32(((m0 >> (g + 8)) & 1u) ? gd0 : 0.f);
-            a[2] = to_tf32(((m1 >> g) & 1u) ? gd1 : 0.f);
-            a[3] = to_tf32(((m1 >> (g + 8)) & 1u) ? gd1 : 0.f);
-            if (!__any_sync(0xffffffffu, (gd0 != 0.f) | (gd1 != 0.f))) continue;       // 8 inert queries (warp-uniform)
-#pragma unroll
-            for (int nt = 0; nt < 5; ++nt) {
-                uint32_t b[2];
-                const int k = 8 * nt + g;
-                const bool ok = k < NGLOD_KPAD;
-                b[0] = to_tf32(ok ? wb[(r0 + t) * NGLOD_KPAD + k] : 0.f);
-                b[1] = to_tf32(ok ? wb[(r0 + t + 4) * NGLOD_KPAD + k] : 0.f);
-                mma_tf32_16x8x8(accT[nt], a, b);
-            }
-        }
-        __syncthreads();
-        // ---- D: scatter g_feat into the grids (fragments -> the warp's tile rows -> 8 lanes per corner line)
-#pragma unroll
-        for (int m = 0; m < 2; ++m)
-#pragma unroll
-            for (int nf = 0; nf < 4; ++nf) {
-                *reinterpret_cast<float2*>(tile + (16 * m + g) * NGLOD_KPAD + 8 * nf + 2 * t) = make_float2(ginf[m][nf][0], ginf[m][nf][1]);
-                *reinterpret_cast<float2*>(tile + (16 * m + g + 8) * NGLOD_KPAD + 8 * nf + 2 * t) = make_float2(ginf[m][nf][2], ginf[m][nf][3]);
-            }
-        __syncwarp();
-        {
-            const unsigned live = __ballot_sync(0xffffffffu, active);
-            const int n_live = __popc(live);
-            const int sub = lane >> 3, c = lane & 7;
-            for (int r = 0; r * 4 < n_live; ++r) {
-                const int slot = r * 4 + sub;
-                const bool valid = slot < n_live;
-                const int q = idx[valid ? slot : 0];
-                const float qx = __shfl_sync(0xffffffffu, px, q);
-                const float qy = __shfl_sync(0xffffffffu, py, q);
-                const float qz = __shfl_sync(0xffffffffu, pz, q);
-                const int qv = __shfl_sync(0xffffffffu, vrow, q);
-                if (valid && SPARSE) {
-                    const float4 gq4 = *reinterpret_cast<const float4*>(tile + q * NGLOD_KPAD + 4 * c);
-                    if (sp.grad_cf) sparse_scatter4(sp.sn, sp.grad_cf, qx, qy, qz, qv, c, gq4);
-                }
-                if (valid && !SPARSE) {
-                    const float4 gq4 = *reinterpret_cast<const float4*>(tile + q * NGLOD_KPAD + 4 * c);
-#pragma unroll
-                    for (int l = 0; l < NGLOD_MAX_LODS; ++l) {
-                        if (l >= net.num_lods) break;
-                        const int R = net.res[l], S = R + 1;
-                        const BwdAxis ax = bwd_axis(qx, R), ay = bwd_axis(qy, R), az = bwd_axis(qz, R);
-                        float* gg = grad.grids[l];
-                        if (!gg) continue;
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            const int ix = (k & 1) ? ax.i1 : ax.i0;
-                            const int iy = (k & 2) ? ay.i1 : ay.i0;
-                            const int iz = (k & 4) ? az.i1 : az.i0;
-                            const float wx = (k & 1) ? ax.w1 : ax.w0;
-                            const float wy = (k & 2) ? ay.w1 : ay.w0;
-                            const float wz = (k & 4) ? az.w1 : az.w0;
-                            const int off = ((iz * S + iy) * S + ix) * NGLOD_F + 4 * c;
-                            const float w = (wx * wy) * wz;
-                            if (l == 0 && smem_grid_floats > 0) {
-                                atomicAdd(sgrid + off, gq4.x * w); atomicAdd(sgrid + off + 1, gq4.y * w);
-                                atomicAdd(sgrid + off + 2, gq4.z * w); atomicAdd(sgrid + off + 3, gq4.w * w);
-                            } else {
-                                red_add_v4(gg + off, gq4.x * w, gq4.y * w, gq4.z * w, gq4.w * w);
-                            }
-                        }
-                    }
-                }
-            }
-        }
-        __syncthreads();      // tiles / masks are rewritten by the next batch
-    }
-
-    // ---- flush: T fragments -> CTA accumulator in smem -> head gradients -> one RED per CTA per element
-    __syncthreads();
-    if constexpr (!SPARSE) {
-        if (smem_grid_floats > 0 && grad.grids[0])
-            for (int e = threadIdx.x * 4; e < smem_grid_floats; e += blockDim.x * 4) {
-                const float4 v = *reinterpret_cast<const float4*>(sgrid + e);
-                if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) red_add_v4(grad.grids[0] + e, v.x, v.y, v.z, v.w);
-            }
-    }
-    float* cta_T = smem + SDF_SMEM_WARP_OFF;             // [128][40] (per-warp regions are dead now), then db1, loss
-    for (int e = threadIdx.x; e < NGLOD_H * 40 + 4; e += blockDim.x) cta_T[e] = 0.f;
-    __syncthreads();
-#pragma unroll
-    for (int nt = 0; nt < 5; ++nt) {
-        const int h = 16 * mt + g, k = 8 * nt + 2 * t;
-        atomicAdd(cta_T + h * 40 + k, accT[nt][0]);
-        atomicAdd(cta_T + h * 40 + k + 1, accT[nt][1]);
-        atomicAdd(cta_T + (h + 8) * 40 + k, accT[nt][2]);
-        atomicAdd(cta_T + (h + 8) * 40 + k + 1, accT[nt][3]);
-    }
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-        acc_b1 += __shfl_xor_sync(0xffffffffu, acc_b1, o);
-        acc_loss += __shfl_xor_sync(0xffffffffu, acc_loss, o);
-    }
-    if (lane == 0) {
-        atomicAdd(cta_T + NGLOD_H * 40, acc_b1);
-        atomicAdd(cta_T + NGLOD_H * 40 + 1, acc_loss);
-    }
-    __syncthreads();
-    const int in_dim = net.pos_invariant ? NGLOD_F : NGLOD_F + 3;
-    if (threadIdx.x < NGLOD_H) {
-        const int h = threadIdx.x;
-        const float w1h = sw1[h];
-        float dw1 = 0.f;
-#pragma unroll 4
-        for (int k = 0; k < NGLOD_KPAD; ++k) {
-            const float tv = cta_T[h * 40 + k];
-            dw1 = fmaf(smem[h * NGLOD_KPAD + k] + wlo[h * NGLOD_KPAD + k], tv, dw1);   // W0ext row {32 feat, x, y, z, b0} = hi + lo
-            const float v = w1h * tv;
-            if (k < NGLOD_F) {
-                if (grad.w0) atomicAdd(grad.w0 + h * in_dim + (net.pos_invariant ? k : k + 3), v);
-            } else if (k < NGLOD_F + 3) {
-                if (grad.w0 && !net.pos_invariant) atomicAdd(grad.w0 + h * in_dim + (k - NGLOD_F), v);
-            } else {
-                if (grad.b0) atomicAdd(grad.b0 + h, v);
-            }
-        }
-        if (grad.w1) atomicAdd(grad.w1 + h, dw1);
-    }
-    if (threadIdx.x == 0) {
-        if (grad.b1) atomicAdd(grad.b1, cta_T[NGLOD_H * 40]);
-        if (FUSED_LOSS && loss_out) atomicAdd(loss_out, cta_T[NGLOD_H * 40 + 1]);
-    }
-}
-
 // ---- transpose of the prefix sum: push dL/d(summed grid of level l) down to the LOD grids, level by level.
 // restrict: Tc[c] += sum over fine nodes n in the support of coarse node c's hat function of  w(n, c) * Tf[n],
 //           w = prod_axis (1 - |n_a - k c_a| / k), k = Rf / Rc  -- the weights nglod_build_summed_grid used, transposed.
@@ -836,13 +443,8 @@ int launch_backward(const nglod_net_t* net, int lod, const nglod_net_grad_t* gra
     gdv.b0 = grad ? grad->b0[lod] : nullptr;
     gdv.w1 = grad ? grad->w1[lod] : nullptr;
     gdv.b1 = grad ? grad->b1[lod] : nullptr;
-    long long grid = nglod_sm_count();
     if constexpr (!WITH_GX) {
-#ifndef NGLOD_BWD_TC
-#define NGLOD_BWD_TC 1          // 0: the mma.sync kernel for the single-grid path too (A/B experiments)
-#endif
-#if NGLOD_BWD_TC
-        // third generation (sdf_backward_tc.cu): tcgen05 GEMMs, warp-specialised; single-grid path
+        // tcgen05 kernel (sdf_backward_tc.cu); the FP32 kernel above serves dL/dx
         if (single) {
             // a grid of <= 729 nodes: scatter into private copies (enough of them to spread the batch over ~5000 nodes)
             const long long grid_floats = (long long)(nd.res[0] + 1) * (nd.res[0] + 1) * (nd.res[0] + 1) * NGLOD_F;
@@ -853,35 +455,17 @@ int launch_backward(const nglod_net_t* net, int lod, const nglod_net_grad_t* gra
                 if (copies > 64) copies = 64;
                 if (copies > 1) { gdv.priv = grad->scatter_scratch; gdv.priv_copies = (int)copies; gdv.priv_stride = (int)grid_floats; }
             }
-            if (int e = nglod_launch_sdf_backward_tc(nd, gdv, x, (long long)n, grad_out, gt, loss_scale, loss_out, FUSED_LOSS, st)) return e;
-            if (gdv.priv) {
-                const long long n4 = grid_floats / 4;
-                fold_copies_kernel<<<(int)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<float4*>(gdv.priv), gdv.priv_copies, n4,
-                                                                            reinterpret_cast<float4*>(gdv.grids[0]));
-                if (int e = (int)cudaGetLastError()) return e;
-            }
-            return cascade ? restrict_cascade(net, lod, grad, st) : 0;
         }
-#endif
-        // second-generation kernel: 16 warps, head gradients on mma.sync tensor cores (the first generation below serves dL/dx)
-        {
-            auto k2 = sdf_backward_mma_kernel<FUSED_LOSS, false>;
-            NGLOD_CUDA_TRY(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, BW2_SMEM_BYTES + BW2_SMEM_GRID_MAX * 4));
-            const int lpw = n > (long long)grid * BW2_WARPS * 8 ? 32 : 8;     // 128-query batches only while they fit one wave
-            const long long want2 = (n + BW2_WARPS * lpw - 1) / (BW2_WARPS * lpw);
-            if (want2 < grid) grid = want2;
-            // level 0 of the launch small enough (R = 4) and busy enough to be worth a per-CTA copy in shared memory
-            int sg = 0;
-            {
-                const long long nodes = (long long)(nd.res[0] + 1) * (nd.res[0] + 1) * (nd.res[0] + 1) * NGLOD_F;
-                if (gdv.grids[0] && nodes <= BW2_SMEM_GRID_MAX && n >= 16 * nodes) sg = (int)nodes;
-            }
-            k2<<<(int)grid, BW2_THREADS, BW2_SMEM_BYTES + sg * 4, st>>>(nd, gdv, x, (long long)n, grad_out, gt, loss_scale, loss_out,
-                                                                        SparseBwd{}, lpw, sg);
+        if (int e = nglod_launch_sdf_backward_tc(nd, gdv, x, (long long)n, grad_out, gt, loss_scale, loss_out, FUSED_LOSS, st)) return e;
+        if (gdv.priv) {
+            const long long n4 = (long long)gdv.priv_stride / 4;
+            fold_copies_kernel<<<(int)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<float4*>(gdv.priv), gdv.priv_copies, n4,
+                                                                        reinterpret_cast<float4*>(gdv.grids[0]));
             if (int e = (int)cudaGetLastError()) return e;
-            return (single && cascade) ? restrict_cascade(net, lod, grad, st) : 0;
         }
+        return (single && cascade) ? restrict_cascade(net, lod, grad, st) : 0;
     }
+    long long grid = nglod_sm_count();
     auto kern = sdf_backward_kernel<FUSED_LOSS, WITH_GX>;
     NGLOD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM_BYTES));
     const long long want = (n + SDF_THREADS - 1) / SDF_THREADS;
@@ -923,15 +507,8 @@ static int launch_sparse_backward(const nglod_sparse_net_t* net, int32_t lod, co
     GradDev gdv;
     for (int i = 0; i < NGLOD_MAX_LODS; ++i) gdv.grids[i] = nullptr;
     gdv.w0 = gw0; gdv.b0 = gb0; gdv.w1 = gw1; gdv.b1 = gb1;
-    auto k2 = sdf_backward_mma_kernel<FUSED_LOSS, true>;
-    NGLOD_CUDA_TRY(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, BW2_SMEM_BYTES));
-    long long grid = nglod_sm_count();
-    const int lpw = n > (long long)grid * BW2_WARPS * 8 ? 32 : 8;     // 128-query batches only while they fit one wave
-    const long long want = (n + BW2_WARPS * lpw - 1) / (BW2_WARPS * lpw);
-    if (want < grid) grid = want;
-    k2<<<(int)grid, BW2_THREADS, BW2_SMEM_BYTES, (cudaStream_t)stream>>>(sp.sn.dec, gdv, x, (long long)n, grad_out, gt,
-                                                                         loss_scale, loss_out, sp, lpw, 0);
-    return (int)cudaGetLastError();
+    return nglod_launch_sdf_backward_tc(sp.sn.dec, gdv, x, (long long)n, grad_out, gt, loss_scale, loss_out, FUSED_LOSS,
+                                        (cudaStream_t)stream, &sp);
 }
 
 extern "C" int nglod_sparse_sdf_backward(const nglod_sparse_net_t* net, int32_t lod, const float* x, const int32_t* pidx,

@@ -19,6 +19,11 @@
 //   epi2   dL/dfeat rows -> shared memory -> 8 lanes per corner line: 8 x red.global.add.v4.f32 per lane into ONE grid
 //          (dL/d(prefix-summed grid), pushed down the LOD chain by the restriction cascade afterwards)
 //
+// Three gather / scatter flavours share everything else (template GM): BT_SINGLE -- the prefix-summed grid of the LOD (the
+// fast path described here); BT_MULTI -- the per-LOD grids (`--no-sum-lods`, grids that do not nest): gather and scatter loop
+// over the LODs; BT_SPARSE -- corner features of a sparse octree: gather and scatter walk the query's parent chain
+// (sparse_core.cuh).  The two slow flavours gather synchronously (no software pipeline) from a record {x, y, z, voxel row}.
+//
 // Warp-specialised over a 2-stage ring (16 warps x 128 registers, one CTA per SM):
 //   producers (8 warps): gather the tile's A rows exactly like the warp-specialised forward (sdf_tc.cu): records from the
 //       K padding of the A rows, 8 lanes x LDG.128 per corner line, FFMA2 interpolation, hi/lo split; the last producer
@@ -28,6 +33,8 @@
 // The roof of this kernel is the L2 atomic units: nglod_probe_scatter measures 6.2 TB/s of reduced bytes for this
 // address stream (0.18 ms per 2^20 queries) whatever the launch shape; everything else is arranged to hide behind it.
 #include "sdf_tc.cuh"
+#include "sdf_core.cuh"
+#include "sparse_core.cuh"
 #include "internal.h"
 #include <cuda_bf16.h>
 #include <cstdio>
@@ -122,11 +129,13 @@ __device__ __forceinline__ void bt_split8(const float (&v)[8], uint4& hi, uint4&
 #define BT_TICK(i) do { } while (0)
 #endif
 
-template <bool FUSED_LOSS>
+enum : int { BT_SINGLE = 0, BT_MULTI = 1, BT_SPARSE = 2 };
+
+template <bool FUSED_LOSS, int GM>
 __global__ void __launch_bounds__(BT_THREADS, 1)
 sdf_backward_tc_kernel(const NetDev net, const GradDev grad, const float* __restrict__ x, const long long n,
                        const float* __restrict__ grad_out, const float* __restrict__ gt, const float loss_scale,
-                       float* __restrict__ loss_out) {
+                       float* __restrict__ loss_out, const SparseBwd sp) {
     extern __shared__ __align__(128) char smem_tc[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* w1s = reinterpret_cast<float*>(smem_tc + BT_SMEM_W1);
@@ -195,9 +204,46 @@ sdf_backward_tc_kernel(const NetDev net, const GradDev grad, const float* __rest
         const uint32_t b_hi = smem_u32(smem_tc + TC_SMEM_B_HI), b_lo = smem_u32(smem_tc + TC_SMEM_B_LO);
         const int nitems = BT_IPT * ntiles;
         auto row_of = [&](int item) { return warp * (8 * BT_IPT) + (item % BT_IPT) * 8 + sub; };      // and row + 4
+        if constexpr (GM != BT_SINGLE) {
+            // per-LOD / sparse gather: record = {x, y, z, voxel row + 1 (0: inert row)}; synchronous loads
+            for (int it = 0; it < nitems; ++it) {
+                const int T = it / BT_IPT, s = T & 1;
+                char* a_hi = smem_tc + BT_SMEM_STAGE(s);
+                char* a_lo = a_hi + TC_OPERAND_BYTES;
+                if (it % BT_IPT == 0) mbar_wait(rec_bar(s), (uint32_t)((T >> 1) & 1));
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int r = row_of(it) + 4 * j;
+                    const float4 rec = *reinterpret_cast<const float4*>(a_hi + tc_elem_offset(r, BT_REC_COL));
+                    float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const int vrow1 = __float_as_int(rec.w);
+                    if (vrow1 > 0) {
+                        if constexpr (GM == BT_SPARSE) f = sparse_gather4(sp.sn, rec.x, rec.y, rec.z, vrow1 - 1, c);
+                        else f = gather_features(net, rec.x, rec.y, rec.z, c);
+                    }
+                    tc_store_split4_finite(a_hi, a_lo, tc_elem_offset(r, 4 * c), f);
+                }
+                if (it % BT_IPT == BT_IPT - 1) {
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        __threadfence_block();
+                        const unsigned old = atomicAdd(arrive_cnt(s), 1u);
+                        if ((old & (BT_PRODUCERS - 1)) == BT_PRODUCERS - 1) {
+                            __threadfence_block();
+                            tc_fence_after_sync();
+                            const uint32_t a_hi_s = smem_u32(a_hi);
+                            tc_issue_tile(tmem_base + BT_TMEM_D1(s), a_hi_s, a_hi_s + TC_OPERAND_BYTES, b_hi, b_lo);
+                            tc_commit(done1_bar(s));
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
         float4 rec0 = make_float4(0.f, 0.f, 0.f, 0.f), rec1 = rec0;
         TcLines<false> t0, t1;
-        if (nitems > 0) {
+        if (GM == BT_SINGLE && nitems > 0) {
             mbar_wait(rec_bar(0), 0u);
             const char* a = smem_tc + BT_SMEM_STAGE(0);
             rec0 = *reinterpret_cast<const float4*>(a + tc_elem_offset(row_of(0), BT_REC_COL));
@@ -205,7 +251,7 @@ sdf_backward_tc_kernel(const NetDev net, const GradDev grad, const float* __rest
             tc_issue_lines<false>(grid, R, __float_as_uint(rec0.x), c, t0);
             tc_issue_lines<false>(grid, R, __float_as_uint(rec1.x), c, t1);
         }
-        for (int it = 0; it < nitems; ++it) {
+        for (int it = 0; GM == BT_SINGLE && it < nitems; ++it) {
             const int T = it / BT_IPT, s = T & 1;
             char* a_hi = smem_tc + BT_SMEM_STAGE(s);
             char* a_lo = a_hi + TC_OPERAND_BYTES;
@@ -286,15 +332,28 @@ sdf_backward_tc_kernel(const NetDev net, const GradDev grad, const float* __rest
         // small grids: private copies per CTA group (the L2 atomic units serialise per address), folded by the launcher
         float* ggrid = grad.priv ? grad.priv + (size_t)(blockIdx.x % grad.priv_copies) * grad.priv_stride : grad.grids[0];
         float acc_b1 = 0.f, acc_loss = 0.f;
+        int nv = 0;                                       // BT_SPARSE: voxel row of the prefetched query, -1 outside the octree
         auto load_xyz = [&](int T, float& px, float& py, float& pz) {
             const long long i = i_first + (long long)T * tile_stride;
             px = py = pz = 0.f;
-            if (T < ntiles && i < n) { px = __ldg(x + 3 * i); py = __ldg(x + 3 * i + 1); pz = __ldg(x + 3 * i + 2); }
+            if (T < ntiles && i < n) {
+                px = __ldg(x + 3 * i); py = __ldg(x + 3 * i + 1); pz = __ldg(x + 3 * i + 2);
+                if constexpr (GM == BT_SPARSE) nv = __ldg(sp.pidx + i);
+            }
         };
         auto setup = [&](int T, float px, float py, float pz) -> float4 {
             const long long i = i_first + (long long)T * tile_stride;
-            // rows past n carry record 0 (corner 0, weights 0): harmless loads; their g_d is 0, so they add nothing
-            const float4 rec = i < n ? tc_setup_record<false>(px, py, pz, R) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 rec = make_float4(0.f, 0.f, 0.f, 0.f);
+            if constexpr (GM == BT_SINGLE) {
+                // rows past n carry record 0 (corner 0, weights 0): harmless loads; their g_d is 0, so they add nothing
+                if (i < n) rec = tc_setup_record<false>(px, py, pz, R);
+            } else {
+                // {x, y, z, voxel row + 1}; 0 = inert row (past n, or a point outside the octree): no gather, no loss, no gradient.
+                // The word is a small integer, i.e. a finite (denormal) float: the MMA multiplies it by W0's zero padding
+                int vrow1 = 0;
+                if (i < n) vrow1 = GM == BT_SPARSE ? (nv >= 0 ? sp.sn.vox_off + nv + 1 : 0) : 1;
+                rec = make_float4(px, py, pz, __int_as_float(vrow1));
+            }
             *reinterpret_cast<float4*>(a_hi + rec_off) = rec;
             tc_store_split4(a_hi, a_lo, xyz_off, make_float4(px, py, pz, 1.f));
             fence_proxy_async_smem();
@@ -309,7 +368,7 @@ sdf_backward_tc_kernel(const NetDev net, const GradDev grad, const float* __rest
         for (int T = g; T < ntiles; T += 2) {
             const uint32_t par = (uint32_t)((T >> 1) & 1);
             const long long i = i_first + (long long)T * tile_stride;
-            const bool active = i < n;
+            const bool active = i < n && (GM == BT_SINGLE || __float_as_int(rec_cur.w) > 0);
             float up = 0.f;                                // the label (fused loss) or the upstream gradient
             if (active) up = __ldg((FUSED_LOSS ? gt : grad_out) + i);
             load_xyz(T + 2, nx, ny, nz);
@@ -423,7 +482,7 @@ sdf_backward_tc_kernel(const NetDev net, const GradDev grad, const float* __rest
             BT_TICK(7);
             // ---- scatter: this warp's 32 rows, 4 queries per round x 8 lanes per corner line
 #ifndef BT_EXP_NOSCATTER
-            if (ggrid) {
+            if (GM == BT_SPARSE ? sp.grad_cf != nullptr : (GM == BT_MULTI || ggrid != nullptr)) {
                 const unsigned live = __ballot_sync(0xffffffffu, active && gd != 0.f);
                 const int sub = lane >> 3, c = lane & 7;
                 const int S = R + 1;
@@ -431,23 +490,41 @@ sdf_backward_tc_kernel(const NetDev net, const GradDev grad, const float* __rest
                 for (int r = 0; r < 8; ++r) {
                     if (!((live >> (4 * r)) & 0xFu)) continue;             // warp-uniform
                     const int q = 4 * r + sub;
-                    const uint32_t pk = __float_as_uint(__shfl_sync(0xffffffffu, rec_cur.x, q));
-                    const float wx1 = __shfl_sync(0xffffffffu, rec_cur.y, q);
-                    const float wy1 = __shfl_sync(0xffffffffu, rec_cur.z, q);
-                    const float wz1 = __shfl_sync(0xffffffffu, rec_cur.w, q);
+                    const float rx = __shfl_sync(0xffffffffu, rec_cur.x, q);
+                    const float ry = __shfl_sync(0xffffffffu, rec_cur.y, q);
+                    const float rz = __shfl_sync(0xffffffffu, rec_cur.z, q);
+                    const float rw = __shfl_sync(0xffffffffu, rec_cur.w, q);
                     if ((live >> q) & 1u) {
                         const float4 gq = *reinterpret_cast<const float4*>(staging + (ew * 32 + q) * BT_STAGING_STRIDE + 16 * c);
-                        const float wx0 = 1.f - wx1, wy0 = 1.f - wy1, wz0 = 1.f - wz1;
-                        const float w00 = wx0 * wy0, w10 = wx1 * wy0, w01 = wx0 * wy1, w11 = wx1 * wy1;
-                        const float w[8] = {w00 * wz0, w10 * wz0, w01 * wz0, w11 * wz0, w00 * wz1, w10 * wz1, w01 * wz1, w11 * wz1};
-                        float* base = ggrid + (pk & ~31u) + 4 * c;
-                        const int dx = (pk & 1u) ? NGLOD_F : 0;
-                        const int dy = (pk & 2u) ? S * NGLOD_F : 0;
-                        const int dz = (pk & 4u) ? S * S * NGLOD_F : 0;
-                        const int offs[8] = {0, dx, dy, dy + dx, dz, dz + dx, dz + dy, dz + dy + dx};
+                        if constexpr (GM == BT_SINGLE) {
+                            const uint32_t pk = __float_as_uint(rx);
+                            const float wx1 = ry, wy1 = rz, wz1 = rw;
+                            const float wx0 = 1.f - wx1, wy0 = 1.f - wy1, wz0 = 1.f - wz1;
+                            const float w00 = wx0 * wy0, w10 = wx1 * wy0, w01 = wx0 * wy1, w11 = wx1 * wy1;
+                            const float w[8] = {w00 * wz0, w10 * wz0, w01 * wz0, w11 * wz0, w00 * wz1, w10 * wz1, w01 * wz1, w11 * wz1};
+                            float* base = ggrid + (pk & ~31u) + 4 * c;
+                            const int dx = (pk & 1u) ? NGLOD_F : 0;
+                            const int dy = (pk & 2u) ? S * NGLOD_F : 0;
+                            const int dz = (pk & 4u) ? S * S * NGLOD_F : 0;
+                            const int offs[8] = {0, dx, dy, dy + dx, dz, dz + dx, dz + dy, dz + dy + dx};
 #pragma unroll
-                        for (int k = 0; k < 8; ++k)
-                            red_add_v4(base + offs[k], gq.x * w[k], gq.y * w[k], gq.z * w[k], gq.w * w[k]);
+                            for (int k = 0; k < 8; ++k)
+                                red_add_v4(base + offs[k], gq.x * w[k], gq.y * w[k], gq.z * w[k], gq.w * w[k]);
+                        } else if constexpr (GM == BT_SPARSE) {
+                            sparse_scatter4(sp.sn, sp.grad_cf, rx, ry, rz, __float_as_int(rw) - 1, c, gq);
+                        } else {
+#pragma unroll
+                            for (int l = 0; l < NGLOD_MAX_LODS; ++l) {
+                                if (l >= net.num_lods) break;
+                                float* gg = grad.grids[l];
+                                if (!gg) continue;
+                                LodSetup ls;
+                                lod_setup(rx, ry, rz, net.res[l], ls);
+#pragma unroll
+                                for (int k = 0; k < 8; ++k)
+                                    red_add_v4(gg + ls.off[k] + 4 * c, gq.x * ls.w[k], gq.y * ls.w[k], gq.z * ls.w[k], gq.w * ls.w[k]);
+                            }
+                        }
                     }
                 }
             }
@@ -526,21 +603,32 @@ sdf_backward_tc_kernel(const NetDev net, const GradDev grad, const float* __rest
     tc_epilogue_free(tmem_base);
 }
 
-}  // namespace
-
-int nglod_launch_sdf_backward_tc(const NetDev& nd, const GradDev& gd, const float* x, long long n, const float* grad_out,
-                                 const float* gt, float loss_scale, float* loss_out, bool fused_loss, cudaStream_t st) {
+template <bool FUSED_LOSS, int GM>
+int launch_bt(const NetDev& nd, const GradDev& gd, const float* x, long long n, const float* grad_out, const float* gt,
+              float loss_scale, float* loss_out, const SparseBwd& sp, cudaStream_t st) {
     long long grid = nglod_sm_count();
     const long long want = (n + TC_TILE_ROWS - 1) / TC_TILE_ROWS;
     if (want < grid) grid = want;
-    if (fused_loss) {
-        auto kern = sdf_backward_tc_kernel<true>;
-        NGLOD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM_BYTES));
-        kern<<<(int)grid, BT_THREADS, BT_SMEM_BYTES, st>>>(nd, gd, x, n, grad_out, gt, loss_scale, loss_out);
-    } else {
-        auto kern = sdf_backward_tc_kernel<false>;
-        NGLOD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM_BYTES));
-        kern<<<(int)grid, BT_THREADS, BT_SMEM_BYTES, st>>>(nd, gd, x, n, grad_out, gt, loss_scale, loss_out);
-    }
+    auto kern = sdf_backward_tc_kernel<FUSED_LOSS, GM>;
+    NGLOD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM_BYTES));
+    kern<<<(int)grid, BT_THREADS, BT_SMEM_BYTES, st>>>(nd, gd, x, n, grad_out, gt, loss_scale, loss_out, sp);
     return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+int nglod_launch_sdf_backward_tc(const NetDev& nd, const GradDev& gd, const float* x, long long n, const float* grad_out,
+                                 const float* gt, float loss_scale, float* loss_out, bool fused_loss, cudaStream_t st,
+                                 const SparseBwd* sp) {
+    const SparseBwd none{};
+    if (sp) {
+        return fused_loss ? launch_bt<true, BT_SPARSE>(sp->sn.dec, gd, x, n, grad_out, gt, loss_scale, loss_out, *sp, st)
+                          : launch_bt<false, BT_SPARSE>(sp->sn.dec, gd, x, n, grad_out, gt, loss_scale, loss_out, *sp, st);
+    }
+    if (nd.num_lods == 1) {         // one grid to gather from and scatter into: the prefix-summed grid, or a one-level net
+        return fused_loss ? launch_bt<true, BT_SINGLE>(nd, gd, x, n, grad_out, gt, loss_scale, loss_out, none, st)
+                          : launch_bt<false, BT_SINGLE>(nd, gd, x, n, grad_out, gt, loss_scale, loss_out, none, st);
+    }
+    return fused_loss ? launch_bt<true, BT_MULTI>(nd, gd, x, n, grad_out, gt, loss_scale, loss_out, none, st)
+                      : launch_bt<false, BT_MULTI>(nd, gd, x, n, grad_out, gt, loss_scale, loss_out, none, st);
 }

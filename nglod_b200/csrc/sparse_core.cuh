@@ -16,6 +16,13 @@ struct SparseDev {
     int vox_off;                // first voxel row of `lod`
 };
 
+// Sparse backward: the features come from (and their gradients go to) the corner rows of a sparse octree model.
+struct SparseBwd {
+    SparseDev sn;
+    const int* pidx;        // [n] voxel index within the LOD's level (< 0: point outside the octree, inert row)
+    float* grad_cf;         // [NC, F]
+};
+
 // 4 channels [4c,4c+4) of sum_{l<=lod} trilinear(corner features) for a point in voxel row `vrow` of LOD sn.lod.
 __device__ __forceinline__ float4 sparse_gather4(const SparseDev& sn, float qx, float qy, float qz, int vrow, int c) {
     int chain[NGLOD_MAX_LODS];

