@@ -137,7 +137,7 @@ sdf_backward_tc_kernel(const NetDev net, const GradDev grad, const float* __rest
                        const float* __restrict__ grad_out, const float* __restrict__ gt, const float loss_scale,
                        float* __restrict__ loss_out, const SparseBwd sp) {
     extern __shared__ __align__(128) char smem_tc[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = tc_warp_uniform(threadIdx.x >> 5), lane = threadIdx.x & 31;
     float* w1s = reinterpret_cast<float*>(smem_tc + BT_SMEM_W1);
     // ---- prologue: zero the operand ring, stage W0|b0 (tf32 hi/lo), (W1 o W0)^T (3 x bf16), W1, b1; barriers; TMEM
     {
@@ -203,6 +203,26 @@ sdf_backward_tc_kernel(const NetDev net, const GradDev grad, const float* __rest
         const float* grid = net.grids[0];
         const uint32_t b_hi = smem_u32(smem_tc + TC_SMEM_B_HI), b_lo = smem_u32(smem_tc + TC_SMEM_B_LO);
         const int nitems = BT_IPT * ntiles;
+        // this warp's rows of the tile in stage s are in place; the LAST warp to say so issues GEMM1 (whole warp in the
+        // branch, one elected lane issues: the descriptors stay in uniform registers)
+        auto arrive_and_issue = [&](int s) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            unsigned old = 0;
+            if (lane == 0) {
+                __threadfence_block();
+                old = atomicAdd(arrive_cnt(s), 1u);
+            }
+            old = __shfl_sync(0xffffffffu, old, 0);
+            if ((old & (BT_PRODUCERS - 1)) == BT_PRODUCERS - 1) {
+                __threadfence_block();
+                tc_fence_after_sync();
+                const uint32_t a_hi_s = smem_u32(smem_tc + BT_SMEM_STAGE(s));
+                tc_issue_tile_warp(tmem_base + BT_TMEM_D1(s), a_hi_s, a_hi_s + TC_OPERAND_BYTES, b_hi, b_lo);
+                if (tc_elect_one()) tc_commit(done1_bar(s));
+            }
+            __syncwarp();
+        };
         auto row_of = [&](int item) { return warp * (8 * BT_IPT) + (item % BT_IPT) * 8 + sub; };      // and row + 4
         if constexpr (GM != BT_SINGLE) {
             // per-LOD / sparse gather: record = {x, y, z, voxel row + 1 (0: inert row)}; synchronous loads
@@ -223,22 +243,7 @@ sdf_backward_tc_kernel(const NetDev net, const GradDev grad, const float* __rest
                     }
                     tc_store_split4_finite(a_hi, a_lo, tc_elem_offset(r, 4 * c), f);
                 }
-                if (it % BT_IPT == BT_IPT - 1) {
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) {
-                        __threadfence_block();
-                        const unsigned old = atomicAdd(arrive_cnt(s), 1u);
-                        if ((old & (BT_PRODUCERS - 1)) == BT_PRODUCERS - 1) {
-                            __threadfence_block();
-                            tc_fence_after_sync();
-                            const uint32_t a_hi_s = smem_u32(a_hi);
-                            tc_issue_tile(tmem_base + BT_TMEM_D1(s), a_hi_s, a_hi_s + TC_OPERAND_BYTES, b_hi, b_lo);
-                            tc_commit(done1_bar(s));
-                        }
-                    }
-                    __syncwarp();
-                }
+                if (it % BT_IPT == BT_IPT - 1) arrive_and_issue(s);
             }
         }
         float4 rec0 = make_float4(0.f, 0.f, 0.f, 0.f), rec1 = rec0;
@@ -287,22 +292,7 @@ sdf_backward_tc_kernel(const NetDev net, const GradDev grad, const float* __rest
                 f2_unpack(acc01, acc.x, acc.y); f2_unpack(acc23, acc.z, acc.w);
                 tc_store_split4_finite(a_hi, a_lo, tc_elem_offset(row + 4, 4 * c), acc);
             }
-            if (it % BT_IPT == BT_IPT - 1) {                                         // this warp's rows of tile T are in place
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                    __threadfence_block();
-                    const unsigned old = atomicAdd(arrive_cnt(s), 1u);
-                    if ((old & (BT_PRODUCERS - 1)) == BT_PRODUCERS - 1) {
-                        __threadfence_block();
-                        tc_fence_after_sync();
-                        const uint32_t a_hi_s = smem_u32(a_hi);
-                        tc_issue_tile(tmem_base + BT_TMEM_D1(s), a_hi_s, a_hi_s + TC_OPERAND_BYTES, b_hi, b_lo);
-                        tc_commit(done1_bar(s));
-                    }
-                }
-                __syncwarp();
-            }
+            if (it % BT_IPT == BT_IPT - 1) arrive_and_issue(s);                      // this warp's rows of tile T are in place
             if (more && !ahead) {
                 BT_TICK(0);
                 mbar_wait(rec_bar(s1), (uint32_t)((T1 >> 1) & 1));
@@ -435,7 +425,7 @@ sdf_backward_tc_kernel(const NetDev net, const GradDev grad, const float* __rest
             BT_TICK(3);
             named_bar_sync(1 + g, 128);
             BT_TICK(4);
-            if (ew == 0 && lane == 0) {
+            if (ew == 0) {                                 // the whole warp; one elected lane issues
                 tc_fence_after_sync();
                 const uint32_t m_s = smem_u32(mask), b2_s = smem_u32(smem_tc + BT_SMEM_B2);
                 const uint32_t s_hi_s = smem_u32(s_hi);
@@ -445,12 +435,14 @@ sdf_backward_tc_kernel(const NetDev net, const GradDev grad, const float* __rest
                 // two independent accumulation chains, issued alternately
 #pragma unroll
                 for (int ks = 0; ks < NGLOD_H / 16; ++ks) {
-                    bt_mma_bf16(tmem_base + BT_TMEM_D2(g), bt_desc(m_s + ks * 256, 128, 2048),
-                                bt_desc(b2_s + ks * 256, 128, 2048), BT_IDESC_BF16(96, 0, 0), ks != 0);
-                    bt_mma_bf16(tmem_base + BT_TMEM_T(g), bt_desc(m_s + ks * 4096, 2048, 128),
-                                bt_desc(s_hi_s + ks * 256, 128, 2048), BT_IDESC_BF16(80, 1, 1), (T != g) | (ks != 0));
+                    const uint64_t a2 = bt_desc(m_s + ks * 256, 128, 2048), b2 = bt_desc(b2_s + ks * 256, 128, 2048);
+                    const uint64_t a3 = bt_desc(m_s + ks * 4096, 2048, 128), b3 = bt_desc(s_hi_s + ks * 256, 128, 2048);
+                    if (tc_elect_one()) {
+                        bt_mma_bf16(tmem_base + BT_TMEM_D2(g), a2, b2, BT_IDESC_BF16(96, 0, 0), ks != 0);
+                        bt_mma_bf16(tmem_base + BT_TMEM_T(g), a3, b3, BT_IDESC_BF16(80, 1, 1), (T != g) | (ks != 0));
+                    }
                 }
-                tc_commit(done2_bar(g));
+                if (tc_elect_one()) tc_commit(done2_bar(g));
             }
             BT_TICK(5);
             mbar_wait(done2_bar(g), par);

@@ -74,6 +74,34 @@ __device__ __forceinline__ void tc_issue_tile(uint32_t d_tmem, uint32_t a_hi, ui
     }
 }
 
+// One lane of a CONVERGED warp (the same one every time).  tcgen05.mma takes its descriptors from uniform registers: issued
+// from a lane-divergent branch (`if (lane == 0)`) every descriptor is computed in vector registers and moved over with
+// R2UR, ~90 cycles per instruction (measured: 16 MMAs = 1500 cycles); with the whole warp in the branch and only the
+// instruction itself under the elected predicate, the descriptor arithmetic stays in the uniform datapath.
+__device__ __forceinline__ bool tc_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// v is the same in every lane: tell the compiler (values derived from it can live in uniform registers)
+__device__ __forceinline__ int tc_warp_uniform(int v) { return __shfl_sync(0xffffffffu, v, 0); }
+
+// tc_issue_tile for a converged warp: every lane calls, one elected lane issues.
+__device__ __forceinline__ void tc_issue_tile_warp(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo) {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t a = pass == 0 ? a_lo : a_hi;
+        const uint32_t b = pass == 1 ? b_lo : b_hi;
+#pragma unroll
+        for (int ks = 0; ks < TC_K / 8; ++ks) {
+            const uint64_t ad = tc_smem_desc(a + ks * 2 * TC_LBO), bd = tc_smem_desc(b + ks * 2 * TC_LBO);
+            if (tc_elect_one()) tc_mma_tf32(d_tmem, ad, bd, acc);
+            acc = 1;
+        }
+    }
+}
+
 __device__ __forceinline__ void tc_commit(uint32_t mbar_saddr) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(mbar_saddr) : "memory");
 }
