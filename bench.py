@@ -295,6 +295,34 @@ def measure_l2_gather_peak(device):
             "how": "nglod_probe_gather, 2^22 cells x 8 lines x 128 B from a 35 MB grid, L2 flushed before each launch, median of 5"}
 
 
+def measure_scatter_peak(device):
+    """The roofline denominator of the backward's grid-gradient scatter, measured on this box in this run
+    (nglod_probe_scatter): the backward's address stream (8 corner lines of a pseudo-random cell of the 35 MB grid, 8 lanes x
+    red.global.add.v4.f32 per line), no arithmetic.  What the L2 atomic units take does not depend on the launch shape."""
+    import ctypes
+    from nglod_b200 import _lib
+    lib = _lib.load()
+    R = 64
+    buf = torch.zeros((R + 1) ** 3 * 32, device=device)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    nq = 1 << 22
+    ts = []
+    with torch.cuda.device(device):
+        for i in range(7):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            _lib.check(lib.nglod_probe_scatter(ctypes.c_void_p(buf.data_ptr()), R, nq, 0, 0, 100 + i,
+                                               ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "nglod_probe_scatter")
+            b.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                ts.append(a.elapsed_time(b))
+    return {"GBs": nq * 1024 / (float(np.median(ts)) * 1e-3) / 1e9,
+            "how": "nglod_probe_scatter, 2^22 cells x 8 lines x 128 B of red.global.add.v4.f32 into a 35 MB grid, L2 flushed "
+                   "before each launch, median of 5"}
+
+
 # ----------------------------------------------------------------------------------------------- ours
 def run_ours(ns):
     from nglod_b200 import dist as ndist
@@ -438,6 +466,7 @@ def run_ours(ns):
     del xs_rot
 
     l2peak = measure_l2_gather_peak(device) if rank == 0 else None
+    scatter_peak = measure_scatter_peak(device) if rank == 0 else None
 
     variants = {}
     if not ns.no_extras:
@@ -556,7 +585,17 @@ def run_ours(ns):
                                      "unit": "GB/s", "frac": q_gather_GBs / l2peak["best_GBs"],
                                      "frac_of_kernel_shape_peak": q_gather_GBs / l2peak["kernel_shape_GBs"],
                                      "traffic": fwd_traffic,
-                                     "tensor_frac": SDF_N * TENSOR_FLOP_PER_EVAL / (fwd_ms / 1e3) / 1e12 / tensor_peak}},
+                                     "tensor_frac": SDF_N * TENSOR_FLOP_PER_EVAL / (fwd_ms / 1e3) / 1e12 / tensor_peak},
+                        "backward_roofline": {
+                            "bound": "l2_atomics", "kernel": "sdf_backward_tc_kernel",
+                            "achieved": SDF_N * GATHER_BYTES_PER_QUERY / (bwd_ms / 1e3) / 1e9, "peak": scatter_peak["GBs"],
+                            "unit": "GB/s", "frac": SDF_N * GATHER_BYTES_PER_QUERY / (bwd_ms / 1e3) / 1e9 / scatter_peak["GBs"],
+                            "traffic": ncu_traffic("sdf_backward_tc_kernel"),
+                            "peak_source": "measured in this run: " + scatter_peak["how"],
+                            "note": "achieved = queries x 1024 B reduced into the gradient of the prefix-summed grid (8 corner "
+                                    "lines x 128 B of red.global.add.v4.f32 per query) / backward_ms, which also contains the "
+                                    "restriction cascade (~0.07 ms); the same 1024 B per query are gathered for the forward "
+                                    "recompute on top of that"}},
         "strong_scaling": strong,
     }
     line["extras"] = extras

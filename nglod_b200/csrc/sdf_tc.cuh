@@ -484,11 +484,25 @@ __device__ __forceinline__ bool tc_group_issue(const NetDev& net, TcGroup& g, fl
     if (!tc_group_any(g.bar_id, keep)) return false;
     TC_TICK(2);
 #ifndef NGLOD_EXP_NO_MMA
+#ifndef NGLOD_TC_ISSUE_WARP
+#define NGLOD_TC_ISSUE_WARP 0       // 1: the group's first warp issues as a converged warp (elect.sync); 0: lane 0 in a divergent
+                                    // branch.  Measured (profiles/README.md part 4): 1 costs the 720p frame 0.90 -> 0.96 ms
+#endif
+#if NGLOD_TC_ISSUE_WARP
+    if (g.wq == 0) {                              // warp-uniform; every warp of a group leaves the barrier converged
+        tc_fence_after_sync();
+        // broadcast: the addresses are the same in every lane, and the compiler keeps what derives from them uniform
+        tc_issue_tile_warp(tc_warp_uniform(g.tmem_acc), tc_warp_uniform(g.a_hi_s), tc_warp_uniform(g.a_lo_s),
+                           tc_warp_uniform(g.b_hi_s), tc_warp_uniform(g.b_lo_s));
+        if (tc_elect_one()) tc_commit(g.mbar_s);
+    }
+#else
     if (g.wq == 0 && g.lane == 0) {
         tc_fence_after_sync();
         tc_issue_tile(g.tmem_acc, g.a_hi_s, g.a_lo_s, g.b_hi_s, g.b_lo_s);
         tc_commit(g.mbar_s);
     }
+#endif
 #endif
     return true;
 }

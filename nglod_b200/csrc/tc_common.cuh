@@ -76,8 +76,12 @@ __device__ __forceinline__ void tc_issue_tile(uint32_t d_tmem, uint32_t a_hi, ui
 
 // One lane of a CONVERGED warp (the same one every time).  tcgen05.mma takes its descriptors from uniform registers: issued
 // from a lane-divergent branch (`if (lane == 0)`) every descriptor is computed in vector registers and moved over with
-// R2UR, ~90 cycles per instruction (measured: 16 MMAs = 1500 cycles); with the whole warp in the branch and only the
-// instruction itself under the elected predicate, the descriptor arithmetic stays in the uniform datapath.
+// R2UR; with the whole warp in the branch and only the instruction itself under the elected predicate the descriptor
+// arithmetic stays in the uniform datapath (SASS: UMOV / ULOP3 / UIADD3 between back-to-back UTCHMMA).  Measured: it buys
+// nothing -- the issuing thread is paced by the tensor pipe accepting the instruction (~80-90 cycles per MMA of a chain
+// into one accumulator), not by its operand arithmetic: neutral in the backward kernel (which uses it), a LOSS in the
+// forward (124 -> 133 us) and the tracer (0.90 -> 0.96 ms per frame), where the 31 idle lanes of the issuing warp delay
+// that warp's own gather / epilogue work.
 __device__ __forceinline__ bool tc_elect_one() {
     uint32_t pred;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
