@@ -333,31 +333,59 @@ sdf_backward_kernel(const NetDev net, const GradDev grad, const float* __restric
 // ---- transpose of the prefix sum: push dL/d(summed grid of level l) down to the LOD grids, level by level.
 // restrict: Tc[c] += sum over fine nodes n in the support of coarse node c's hat function of  w(n, c) * Tf[n],
 //           w = prod_axis (1 - |n_a - k c_a| / k), k = Rf / Rc  -- the weights nglod_build_summed_grid used, transposed.
+// KT = the ratio Rf / Rc when it is the octree's 2 (27 taps, fully unrolled: 27 independent loads in flight -- the runtime
+// loops walked them one L2 latency at a time, ~10 us even for the 9^3 level), 0 = any ratio (runtime loops).
+template <int KT>
 __global__ void __launch_bounds__(256)
-restrict_add_kernel(const float4* __restrict__ Tf, const int Rf, float4* __restrict__ Tc, const int Rc, const long long n_chunks) {
-    const int Sc = Rc + 1, Sf = Rf + 1, k = Rf / Rc;
+restrict_add_kernel(const float4* __restrict__ Tf, const int Rf, float4* __restrict__ Tc, const int Rc, const int n_chunks) {
+    const int Sc = Rc + 1, Sf = Rf + 1, k = KT ? KT : Rf / Rc;
     const float inv_k = 1.f / (float)k;           // exact for the power-of-two ratios of an octree
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_chunks; e += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(e & 7);
-        long long node = e >> 3;
-        const int cx = (int)(node % Sc); node /= Sc;
-        const int cy = (int)(node % Sc);
-        const int cz = (int)(node / Sc);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_chunks; e += gridDim.x * blockDim.x) {
+        const int c = e & 7;
+        int node = e >> 3;
+        const int cx = node % Sc; node /= Sc;
+        const int cy = node % Sc;
+        const int cz = node / Sc;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int dz = -(k - 1); dz <= k - 1; ++dz) {
-            const int fz = cz * k + dz;
-            if (fz < 0 || fz > Rf) continue;
-            const float wz = 1.f - (float)abs(dz) * inv_k;
-            for (int dy = -(k - 1); dy <= k - 1; ++dy) {
-                const int fy = cy * k + dy;
-                if (fy < 0 || fy > Rf) continue;
-                const float wzy = wz * (1.f - (float)abs(dy) * inv_k);
-                for (int dx = -(k - 1); dx <= k - 1; ++dx) {
-                    const int fx = cx * k + dx;
-                    if (fx < 0 || fx > Rf) continue;
-                    const float w = wzy * (1.f - (float)abs(dx) * inv_k);
-                    const float4 v = __ldg(Tf + ((long long)(fz * Sf + fy) * Sf + fx) * 8 + c);
-                    acc.x = fmaf(v.x, w, acc.x); acc.y = fmaf(v.y, w, acc.y); acc.z = fmaf(v.z, w, acc.z); acc.w = fmaf(v.w, w, acc.w);
+        if constexpr (KT == 2) {
+            float4 v[27];
+            float w[27];
+#pragma unroll
+            for (int t = 0; t < 27; ++t) {
+                const int dx = t % 3 - 1, dy = (t / 3) % 3 - 1, dz = t / 9 - 1;
+                const int fx = 2 * cx + dx, fy = 2 * cy + dy, fz = 2 * cz + dz;
+                const bool ok = fx >= 0 && fx <= Rf && fy >= 0 && fy <= Rf && fz >= 0 && fz <= Rf;
+                w[t] = ok ? (dx ? 0.5f : 1.f) * (dy ? 0.5f : 1.f) * (dz ? 0.5f : 1.f) : 0.f;
+                v[t] = ok ? __ldg(Tf + ((long long)(fz * Sf + fy) * Sf + fx) * 8 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int dz = 0; dz < 3; ++dz)           // same order as the runtime loops: z outer, x inner
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                        const int t = dz * 9 + dy * 3 + dx;
+                        if (w[t] != 0.f) {
+                            acc.x = fmaf(v[t].x, w[t], acc.x); acc.y = fmaf(v[t].y, w[t], acc.y);
+                            acc.z = fmaf(v[t].z, w[t], acc.z); acc.w = fmaf(v[t].w, w[t], acc.w);
+                        }
+                    }
+        } else {
+            for (int dz = -(k - 1); dz <= k - 1; ++dz) {
+                const int fz = cz * k + dz;
+                if (fz < 0 || fz > Rf) continue;
+                const float wz = 1.f - (float)abs(dz) * inv_k;
+                for (int dy = -(k - 1); dy <= k - 1; ++dy) {
+                    const int fy = cy * k + dy;
+                    if (fy < 0 || fy > Rf) continue;
+                    const float wzy = wz * (1.f - (float)abs(dy) * inv_k);
+                    for (int dx = -(k - 1); dx <= k - 1; ++dx) {
+                        const int fx = cx * k + dx;
+                        if (fx < 0 || fx > Rf) continue;
+                        const float w = wzy * (1.f - (float)abs(dx) * inv_k);
+                        const float4 v = __ldg(Tf + ((long long)(fz * Sf + fy) * Sf + fx) * 8 + c);
+                        acc.x = fmaf(v.x, w, acc.x); acc.y = fmaf(v.y, w, acc.y); acc.z = fmaf(v.z, w, acc.z); acc.w = fmaf(v.w, w, acc.w);
+                    }
                 }
             }
         }
@@ -382,17 +410,25 @@ accumulate_and_clear_kernel(float4* __restrict__ T, float4* __restrict__ g, cons
 }
 
 // target += sum of the private scatter copies; the copies are zero again afterwards
+// 8 lanes per float4 element, each over every 8th copy, then a shuffle reduction (one thread per element walked up to 64
+// copies serially: 21 us for 1000 elements)
 __global__ void __launch_bounds__(256)
 fold_copies_kernel(float4* __restrict__ priv, const int copies, const long long n4, float4* __restrict__ target) {
-    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n4) return;
+    const long long e = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int part = threadIdx.x & 7;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int c = 0; c < copies; ++c) {
-        const float4 v = priv[c * n4 + e];
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-        priv[c * n4 + e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (e < n4)
+        for (int c = part; c < copies; c += 8) {
+            const float4 v = priv[c * n4 + e];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            priv[c * n4 + e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+    for (int o = 4; o >= 1; o >>= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
     }
-    if (target) {
+    if (e < n4 && part == 0 && target) {
         float4 t = target[e];
         t.x += acc.x; t.y += acc.y; t.z += acc.z; t.w += acc.w;
         target[e] = t;
@@ -409,8 +445,12 @@ int restrict_cascade(const nglod_net_t* net, int lod, const nglod_net_grad_t* gr
             const long long nc = Sc * Sc * Sc * 8;
             long long blocks = (nc + 255) / 256;
             if (blocks > cap) blocks = cap;
-            restrict_add_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(grad->summed[l]), net->grid_res[l],
-                                                             reinterpret_cast<float4*>(grad->summed[l - 1]), net->grid_res[l - 1], nc);
+            if (net->grid_res[l] == 2 * net->grid_res[l - 1])
+                restrict_add_kernel<2><<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(grad->summed[l]), net->grid_res[l],
+                                                                    reinterpret_cast<float4*>(grad->summed[l - 1]), net->grid_res[l - 1], (int)nc);
+            else
+                restrict_add_kernel<0><<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(grad->summed[l]), net->grid_res[l],
+                                                                    reinterpret_cast<float4*>(grad->summed[l - 1]), net->grid_res[l - 1], (int)nc);
         }
         long long blocks = (n4 + 255) / 256;
         if (blocks > cap) blocks = cap;
@@ -459,7 +499,7 @@ int launch_backward(const nglod_net_t* net, int lod, const nglod_net_grad_t* gra
         if (int e = nglod_launch_sdf_backward_tc(nd, gdv, x, (long long)n, grad_out, gt, loss_scale, loss_out, FUSED_LOSS, st)) return e;
         if (gdv.priv) {
             const long long n4 = (long long)gdv.priv_stride / 4;
-            fold_copies_kernel<<<(int)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<float4*>(gdv.priv), gdv.priv_copies, n4,
+            fold_copies_kernel<<<(int)((n4 * 8 + 255) / 256), 256, 0, st>>>(reinterpret_cast<float4*>(gdv.priv), gdv.priv_copies, n4,
                                                                         reinterpret_cast<float4*>(gdv.grids[0]));
             if (int e = (int)cudaGetLastError()) return e;
         }
