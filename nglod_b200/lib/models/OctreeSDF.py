@@ -18,6 +18,16 @@ from .BaseLOD import BaseLOD
 from ... import ops, _lib
 
 
+KERNEL_F, KERNEL_H = 32, 128     # the shape libnglod_b200.so is built for (csrc/common.cuh NGLOD_F / NGLOD_H)
+
+
+def _pad_grid(fm):
+    """[1,F,S,S,S] channels-last -> [1,32,S,S,S] channels-last, channels F.. zero."""
+    out = torch.zeros(1, KERNEL_F, *fm.shape[2:], device=fm.device, dtype=fm.dtype).contiguous(memory_format=torch.channels_last_3d)
+    out[:, :fm.shape[1]] = fm
+    return out
+
+
 class FeatureVolume(nn.Module):
     """Dense (fsize+1)^3 x fdim feature grid (reference: OctreeSDF.py:38-57)."""
 
@@ -37,8 +47,10 @@ class FeatureVolume(nn.Module):
 
     def forward(self, x):
         """Trilinear sample of this LOD alone: [N,3] -> [N,fdim] ([N,K,3] -> [N,K,fdim])."""
-        view = ops.NetView.grids_only([self.fm.data])
-        return ops.sdf_features(view, 0, x.reshape(-1, 3)).reshape(*x.shape[:-1], self.fdim)
+        if self.fdim > KERNEL_F:
+            raise RuntimeError(f"feature-dim {self.fdim}: the kernels are built for at most {KERNEL_F} channels")
+        view = ops.NetView.grids_only([self.fm.data if self.fdim == KERNEL_F else _pad_grid(self.fm.data)])
+        return ops.sdf_features(view, 0, x.reshape(-1, 3))[:, :self.fdim].reshape(*x.shape[:-1], self.fdim)
 
 
 class _SdfFunction(torch.autograd.Function):
@@ -59,14 +71,16 @@ class _SdfFunction(torch.autograd.Function):
         view = module.net_view(inference=False)
         needs = ctx.needs_input_grad
         n_grids = lod + 1
-        grid_grads = [torch.zeros_like(module.features[i].fm, memory_format=torch.preserve_format)
+        # gradients in the kernels' shapes (== the parameters' shapes unless the model is zero-padded, see OctreeSDF.padded)
+        grid_grads = [torch.zeros_like(view.grids[i], memory_format=torch.preserve_format)
                       if needs[3 + i] else None for i in range(n_grids)]
-        dec_params = module.decoder_params(lod)
-        dec_grads = [torch.zeros_like(p) if needs[3 + n_grids + k] else None for k, p in enumerate(dec_params)]
+        dec_grads = [torch.zeros_like(p) if needs[3 + n_grids + k] else None for k, p in enumerate(view.decoders[lod])]
         gx = ops.sdf_backward(view, lod, x, grad_out.contiguous(), grid_grads + [None] * (view.num_lods - n_grids),
                               tuple(dec_grads), want_grad_x=needs[0],
                               summed_scratch=module.summed_grad_scratch() if view.summed is not None else None,
                               scatter_scratch=module.scatter_scratch() if view.summed is not None else None)
+        if module.padded:
+            grid_grads, dec_grads = module._unpad_grads(grid_grads, dec_grads)
         return (gx, None, None, *grid_grads, *dec_grads)
 
 
@@ -77,6 +91,16 @@ class OctreeSDF(BaseLOD):
         self.fsize = self.args.feature_size
         self.hidden_dim = self.args.hidden_dim
         self.pos_invariant = self.args.pos_invariant
+        # The library is built for feature-dim 32 / hidden-dim 128 (the reference's defaults and every published
+        # configuration).  SMALLER models (`--feature-dim 16`, README.md:109 of the reference) run through the same kernels
+        # zero-padded: channels F..31 of the grids and the matching W0 columns are zero, hidden units H..127 have
+        # W0 = b0 = W1 = 0 -- the padded net is the same function exactly (every extra term is 0 * 0 or W1 = 0 times
+        # relu(0)), and its gradients restricted to the real entries are the real gradients.  Larger shapes raise.
+        if self.fdim > KERNEL_F or self.hidden_dim > KERNEL_H:
+            raise RuntimeError(f"feature-dim {self.fdim} / hidden-dim {self.hidden_dim}: the kernels are built for at most "
+                               f"{KERNEL_F} / {KERNEL_H} (smaller models are zero-padded, larger ones are not supported)")
+        self.padded = self.fdim != KERNEL_F or self.hidden_dim != KERNEL_H
+        self._padded_cache = None
 
         self.features = nn.ModuleList(
             [FeatureVolume(self.fdim, 2 ** (i + self.args.base_lod)) for i in range(self.args.num_lods)])
@@ -110,6 +134,40 @@ class OctreeSDF(BaseLOD):
         seq = self.louts[0 if self.num_decoder == 1 else lod]
         return (seq[0].weight, seq[0].bias, seq[2].weight, seq[2].bias)
 
+    # ------------------------------------------------------------------ zero-padding to the kernels' shape
+    def _kernel_params(self):
+        """(grids, decoders) as the kernels take them: the parameters themselves, or -- for a model smaller than 32 / 128 --
+        zero-padded copies, rebuilt when a parameter was written (version counters; mark_grids_dirty())."""
+        grids = [f.fm.data for f in self.features]
+        decs = [tuple(p.data for p in self.decoder_params(i)) for i in range(self.num_lods)]
+        if not self.padded:
+            return grids, decs
+        key = [(p._version, p.data_ptr()) for p in self.parameters()]
+        if self._padded_cache is None or self._padded_cache[0] != key:
+            F_, H_ = self.fdim, self.hidden_dim
+            xyz = 0 if self.pos_invariant else 3
+            pg = [_pad_grid(g) for g in grids]
+            pd = []
+            for i in range(self.num_decoder):
+                w0, b0, w1, b1 = (p.data for p in self.decoder_params(i))
+                w0p = torch.zeros(KERNEL_H, xyz + KERNEL_F, device=w0.device)
+                w0p[:H_, :xyz + F_] = w0
+                b0p = torch.zeros(KERNEL_H, device=w0.device); b0p[:H_] = b0
+                w1p = torch.zeros(1, KERNEL_H, device=w0.device); w1p[:, :H_] = w1
+                pd.append((w0p, b0p, w1p, b1.clone()))
+            self._padded_cache = [key, pg, pd]
+        pd = self._padded_cache[2]
+        return self._padded_cache[1], [pd[0 if self.num_decoder == 1 else i] for i in range(self.num_lods)]
+
+    def _unpad_grads(self, grid_grads, dec_grads):
+        F_, H_ = self.fdim, self.hidden_dim
+        xyz = 0 if self.pos_invariant else 3
+        gg = [None if g is None else g[:, :F_].contiguous(memory_format=torch.channels_last_3d) for g in grid_grads]
+        gw0, gb0, gw1, gb1 = dec_grads
+        dg = [None if gw0 is None else gw0[:H_, :xyz + F_].contiguous(), None if gb0 is None else gb0[:H_].contiguous(),
+              None if gw1 is None else gw1[:, :H_].contiguous(), gb1]
+        return gg, dg
+
     def _grids_nest(self):
         res = [f.fsize for f in self.features]
         return all(res[i] % res[j] == 0 for i in range(len(res)) for j in range(i))
@@ -122,6 +180,7 @@ class OctreeSDF(BaseLOD):
         graph of the training step rebuilds them in place)."""
         if self._derived is not None:
             self._derived[0] = None
+        self._padded_cache = None
 
     def load_state_dict(self, *args, **kwargs):
         out = super().load_state_dict(*args, **kwargs)
@@ -138,7 +197,7 @@ class OctreeSDF(BaseLOD):
         """(summed, summed_half) rebuilt when a grid was written or moved; the fp16 copy only when asked for."""
         key = [(f.fm._version, f.fm.data_ptr()) for f in self.features]
         if self._derived is None or self._derived[0] != key:
-            grids = [f.fm.data for f in self.features]
+            grids = self._kernel_params()[0]
             base = ops.NetView.grids_only(grids)
             old = self._derived[1] if self._derived is not None else [None] * len(grids)
             old_half = self._derived[2] if self._derived is not None else None
@@ -160,7 +219,7 @@ class OctreeSDF(BaseLOD):
         kernels leave them zero, so they are allocated once."""
         sc = getattr(self, "_summed_scratch", None)
         if sc is None or any(t.device != f.fm.device for t, f in zip(sc, self.features)):
-            sc = [torch.zeros_like(f.fm.data, memory_format=torch.preserve_format) for f in self.features]
+            sc = [torch.zeros_like(g, memory_format=torch.preserve_format) for g in self._kernel_params()[0]]
             self._summed_scratch = sc
         return sc
 
@@ -183,7 +242,7 @@ class OctreeSDF(BaseLOD):
         sd = {k: v.detach().clone() for k, v in self.state_dict().items()}
         for i in range(self.num_lods):
             sd[f"features.{i}.fm"] = torch.zeros_like(sd[f"features.{i}.fm"])
-        top = summed[lod].detach().clone()
+        top = summed[lod][:, :self.fdim].detach().clone()
         sd[f"features.{lod}.fm"] = top.half().float() if self.grid_storage == "fp16" else top
         return sd
 
@@ -191,8 +250,7 @@ class OctreeSDF(BaseLOD):
         """Borrow the current parameters as an nglod_net_t (rebuilt per call: pointers may move).  inference=False (the
         autograd / training kernels) never attaches the half-precision copy; use_summed=False leaves the prefix-summed
         grids out (small training batches: rebuilding them costs more than five short gathers)."""
-        grids = [f.fm.data for f in self.features]
-        decs = [tuple(p.data for p in self.decoder_params(i)) for i in range(self.num_lods)]
+        grids, decs = self._kernel_params()
         summed = half = None
         if use_summed and self.sum_lods and self._grids_nest():
             summed, half = self._derived_grids(want_half=inference and self.grid_storage == "fp16" and self.math_mode == "tc")

@@ -25,6 +25,10 @@ from .. import dist as ndist
 class FusedTrainer:
     def __init__(self, net, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, loss_lods=None, use_graph=True,
                  graph_max_batch=131072, summed_min_batch=32768, shard_optimizer=True):
+        if getattr(net, "padded", False):
+            raise RuntimeError("FusedTrainer writes gradients straight into the parameters' flat buffer: the model must have the "
+                               "kernels' own shape (feature-dim 32, hidden-dim 128); smaller models train through autograd "
+                               "(Trainer falls back to torch.optim.Adam)")
         self.net = net
         self.use_graph, self.graph_max_batch, self.summed_min_batch = use_graph, graph_max_batch, summed_min_batch
         self._graphs = {}
@@ -246,7 +250,10 @@ class Trainer(object):
         log.info("Total number of parameters: {}".format(sum(p.numel() for p in self.net.parameters())))
 
     def set_optimizer(self):
-        if self.args.optimizer == "adam":
+        if self.args.optimizer == "adam" and getattr(self.net, "padded", False):
+            # a model smaller than the kernels' 32 / 128 runs zero-padded: autograd step (same kernels), torch's Adam
+            self.optimizer = torch.optim.Adam(self.net.parameters(), lr=self.args.lr)
+        elif self.args.optimizer == "adam":
             self.optimizer = FusedTrainer(self.net, lr=self.args.lr)
         elif self.args.optimizer == "sgd":
             self.optimizer = torch.optim.SGD(self.net.parameters(), lr=self.args.lr, momentum=0.8)

@@ -858,6 +858,10 @@ def test_realtime_loop_dense_and_sparse(fit3):
     (["--num-lods", "3", "--base-lod", "1"], {}),
     (["--num-lods", "2", "--base-lod", "3"], {}),
     (["--num-lods", "7", "--base-lod", "0"], {}),         # R = 1 .. 64: more grids than one set-up batch (TC_PACK_LODS = 5)
+    # models smaller than the kernels' 32 / 128 (the reference README's `--feature-dim 16`): run zero-padded, exactly
+    (["--num-lods", "3", "--feature-dim", "16"], {}),
+    (["--num-lods", "3", "--feature-dim", "16", "--hidden-dim", "64", "--joint-decoder"], {}),
+    (["--num-lods", "2", "--feature-dim", "8", "--hidden-dim", "32", "--pos-invariant"], dict(pos_invariant=True)),
 ])
 def test_model_variants_forward_backward_trace(flags, kw):
     """The reference's other OctreeSDF shapes (--pos-invariant, --joint-decoder, --base-lod, up to 7 LODs) through every

@@ -111,3 +111,36 @@ def test_fused_trainer_respects_requires_grad():
     net.freeze()
     with pytest.raises(RuntimeError):
         tr.step(x, gt)
+
+
+@pytest.mark.gpu
+def test_trainer_smaller_model_trains_through_autograd():
+    """`--feature-dim 16 --hidden-dim 64` (the reference README's example of a smaller model): the kernels run it zero-padded,
+    the Trainer steps it with torch's Adam through autograd (FusedTrainer needs the kernels' own shape and says so)."""
+    from nglod_b200.lib.trainer import Trainer, FusedTrainer
+    from nglod_b200.lib.torchgp import icosphere, write_obj
+    with tempfile.TemporaryDirectory() as td:
+        V, F = icosphere(3)
+        obj = os.path.join(td, "ball.obj")
+        write_obj(obj, V * 0.7, F)
+        args = make_args(["--num-lods", "3", "--feature-dim", "16", "--hidden-dim", "64", "--dataset-path", obj, "--epochs", "5",
+                          "--batch-size", "2048", "--num-samples", "8000", "--exp-name", "unit/small",
+                          "--model-path", os.path.join(td, "models"), "--logs", os.path.join(td, "logs"),
+                          "--render-every", "100", "--lr", "0.005"])
+        torch.manual_seed(0)
+        tr = Trainer(args, "```args```")
+        assert tr.net.padded and isinstance(tr.optimizer, torch.optim.Adam)
+        assert tr.net.features[0].fm.shape[1] == 16 and tr.net.louts[0][0].weight.shape == (64, 19)
+        with pytest.raises(RuntimeError):
+            FusedTrainer(tr.net)
+        losses = []
+        for epoch in range(args.epochs):
+            tr.pre_epoch(epoch)
+            tr.iterate(epoch)
+            tr.post_epoch(epoch)
+            losses.append(tr.log_dict["l2_loss"])
+        assert losses[-1] < 0.5 * losses[0]
+        x = torch.rand(1000, 3, device="cuda") * 2 - 1
+        with torch.no_grad():
+            d = tr.net.sdf(x, lod=2)[:, 0]
+        assert (d - (x.norm(dim=1) - 1.0)).abs().mean() < 0.15
