@@ -637,7 +637,7 @@ def run_strong_scaling(net, args, device, rank, world, flush, log):
             b.record()
             torch.cuda.synchronize()
             ts.append(a.elapsed_time(b))
-        return ndist.max_over_ranks(float(np.mean(ts)), device)
+        return ndist.max_over_ranks(float(np.median(ts)), device)
 
     # ---- (a) config 5: 3840x2160, shadows + normals; 4 interleaved strips per rank (silhouette columns cost more than empty
     #      ones); every rank renders its strips as one batch; depth / hit / normal / shadow (18 B per ray) gathered to rank 0
@@ -660,8 +660,8 @@ def run_strong_scaling(net, args, device, rank, world, flush, log):
         frame["full"] = [ndist.gather_strips(t, strips_all, h4, rank, world, dst=0) for t in
                          (rb.depth.reshape(-1, 1), rb.normal.reshape(-1, 3), rb.hit.reshape(-1, 1).view(torch.uint8),
                           rb.shadow.reshape(-1, 1).view(torch.uint8))]
-    r4_ms = timed(render_and_gather, iters=3, warm=1)
-    render_only_ms = timed(lambda: renderer.render(net, ro, rd), iters=3, warm=1)
+    r4_ms = timed(render_and_gather, iters=5, warm=3)          # 3 warm-ups: the first 4K frames grow the allocator's pools
+    render_only_ms = timed(lambda: renderer.render(net, ro, rd), iters=5, warm=1)
     out["render_4k_shadow"] = {"rays": w4 * h4, "rays_this_rank": int(ro.shape[0]), "ms": r4_ms, "fps": 1e3 / r4_ms,
                                "rays_per_s": w4 * h4 / (r4_ms / 1e3), "render_only_ms": render_only_ms,
                                "gathered_bytes": int((w4 * h4 - ro.shape[0]) * 18),
