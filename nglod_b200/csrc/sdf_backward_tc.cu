@@ -30,6 +30,19 @@
 //       to arrive issues GEMM1.
 //   service (2 warpgroups; warpgroup g owns stage g and the tiles T = g mod 2): epi1 -> barrier -> one thread issues
 //       GEMM2 + GEMM3 -> set-up of tile T+2 in the freed stage (releases the producers) -> epi2 + scatter.
+// Who orders what (every hand-off is an mbarrier; `compute-sanitizer --tool racecheck` does not model mbarrier arrive /
+// try_wait or tcgen05.commit and reports each of these pairs -- as it does for the forward's identical record hand-off;
+// memcheck, synccheck and initcheck are clean, profiles/README.md part 4):
+//   set-up writes {record, xyz} of tile T   -> producers read them              rec_full[s]  (4 service warps arrive, release)
+//   producers write the A rows of tile T    -> GEMM1 reads them (async proxy)   fence.proxy.async + arrival counter, last arriver issues
+//   GEMM1 done (reads of A, writes of D1)   -> epi1 reads D1, reads A_hi, overwrites A_lo with S, writes MASK     done1[s]  (tcgen05.commit)
+//   epi1's MASK / S writes (all 128 threads) -> GEMM2 / GEMM3 read them          fence.proxy.async + named barrier, then one warp issues
+//   GEMM2 / GEMM3 done                      -> D2 read, stage handed back (set-up of T+2 writes A rows), MASK region re-used
+//                                              as the staging area                done2[s]  (tcgen05.commit)
+//   staging rows: written and read by the SAME warp (__syncwarp); the next tile's epi1 rewrites the MASK only after the
+//   named barrier that closes the iteration.  D1[s] / D2[s] of tile T+2 are written by MMAs issued after rec_full(T+2),
+//   i.e. after every service thread's tcgen05.ld of tile T (tcgen05.fence::before_thread_sync precedes the arrive).
+//
 // The roof of this kernel is the L2 atomic units: nglod_probe_scatter measures 6.2 TB/s of reduced bytes for this
 // address stream (0.18 ms per 2^20 queries) whatever the launch shape; everything else is arranged to hide behind it.
 #include "sdf_tc.cuh"

@@ -31,6 +31,14 @@ net.grid_storage = "fp32"
 d = net.sdf(x, lod=2); ((d - 0.1) ** 2).mean().backward()
 d = net.sdf(x[:700], lod=1); d.sum().backward()
 tr = FusedTrainer(net); tr.step(x, torch.rand(1500, 1, device=dev)); tr.step(x[:513], torch.rand(513, 1, device=dev))
+# tcgen05 backward, single-grid flavour with several tiles per CTA (stage re-use, barrier parities), private scatter copies
+# of the 4^3 / 8^3 heads, fold kernel, octree summed-grid build, unrolled restriction
+xb = torch.rand(60001, 3, device=dev) * 2 - 1
+tr2 = FusedTrainer(net, summed_min_batch=0, use_graph=False)
+tr2.step(xb, torch.rand(60001, 1, device=dev)); tr2.step(xb[:40000], torch.rand(40000, 1, device=dev))
+net.sum_lods = False                      # per-LOD flavour, several tiles per CTA
+d = net.sdf(xb[:30000], lod=2); d.sum().backward()
+net.sum_lods = True
 V, F = icosphere(2)
 sp = S.SparseOctreeSDF(net, S.SPC(S.mesh_to_octree(V.to(dev), F.to(dev), 4, num_samples=1 << 16)))
 sp.trace(ro, rd, 2)
@@ -40,5 +48,9 @@ lp = sp.spc.level_points(4)[:, :3].float()
 pidx = torch.randint(0, lp.shape[0], (700,), device=dev)
 xs = (lp[pidx] + torch.rand(700, 3, device=dev)) / 16 * 2 - 1
 nspc.sdf(xs, 2, pidx).sum().backward()
+pidx2 = torch.randint(0, lp.shape[0], (30000,), device=dev)
+xs2 = (lp[pidx2] + torch.rand(30000, 3, device=dev)) / 16 * 2 - 1
+pidx2[::7] = -1                           # inert rows
+nspc.sdf(xs2, 2, pidx2).sum().backward()
 torch.cuda.synchronize()
 print("sanitize target done")
