@@ -100,7 +100,10 @@ typedef struct nglod_net_grad {
      * nglod_sdf_train_step recompute the forward from the prefix-summed grid, scatter dL/d(summed[lod]) (8 corners per
      * query instead of 8*(lod+1)) into summed[lod] and then push it down the LOD chain with the transpose of the
      * prefix sum (dense restriction kernels, level by level -- the hat functions nest), adding into grids[0..lod]:
-     * the same gradients as the per-LOD scatter, to fp32 rounding. */
+     * the same gradients as the per-LOD scatter, to fp32 rounding.
+     * summed[i] MAY ALIAS grids[i] when grids[i] holds no other contribution on entry (the usual case: gradients zeroed
+     * before the step): the level's gradient is then accumulated in place and the copy-out pass (140 MB of traffic
+     * at the 65^3 level) is skipped; such a buffer is of course not zero on return. */
     float* summed[NGLOD_MAX_LODS];
     /* OPTIONAL scratch for the scatter into SMALL grids (single-grid path, grid_res <= 8): scatter_scratch_floats floats,
      * 16-byte aligned, ALL ZERO on entry and all zero again on return.  A grid of 125 or 729 nodes takes half a million

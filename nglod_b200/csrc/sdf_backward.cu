@@ -452,6 +452,7 @@ int restrict_cascade(const nglod_net_t* net, int lod, const nglod_net_grad_t* gr
                 restrict_add_kernel<0><<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(grad->summed[l]), net->grid_res[l],
                                                                     reinterpret_cast<float4*>(grad->summed[l - 1]), net->grid_res[l - 1], (int)nc);
         }
+        if (grad->summed[l] == grad->grids[l]) continue;      // aliased: the level's gradient was accumulated in place
         long long blocks = (n4 + 255) / 256;
         if (blocks > cap) blocks = cap;
         accumulate_and_clear_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<float4*>(grad->summed[l]),

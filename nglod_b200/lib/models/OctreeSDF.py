@@ -75,9 +75,12 @@ class _SdfFunction(torch.autograd.Function):
         grid_grads = [torch.zeros_like(view.grids[i], memory_format=torch.preserve_format)
                       if needs[3 + i] else None for i in range(n_grids)]
         dec_grads = [torch.zeros_like(p) if needs[3 + n_grids + k] else None for k, p in enumerate(view.decoders[lod])]
+        scratch = None
+        if view.summed is not None:       # fresh zero gradients double as the scratch (aliased: no copy-out pass)
+            own = module.summed_grad_scratch()
+            scratch = [g if g is not None else own[i] for i, g in enumerate(grid_grads)] + own[n_grids:]
         gx = ops.sdf_backward(view, lod, x, grad_out.contiguous(), grid_grads + [None] * (view.num_lods - n_grids),
-                              tuple(dec_grads), want_grad_x=needs[0],
-                              summed_scratch=module.summed_grad_scratch() if view.summed is not None else None,
+                              tuple(dec_grads), want_grad_x=needs[0], summed_scratch=scratch,
                               scatter_scratch=module.scatter_scratch() if view.summed is not None else None)
         if module.padded:
             grid_grads, dec_grads = module._unpad_grads(grid_grads, dec_grads)

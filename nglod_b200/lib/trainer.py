@@ -89,7 +89,12 @@ class FusedTrainer:
         grid_grads, dec_grads = self._grad_lists()
         # big batches: rebuild the prefix-summed grids from this step's weights (~0.1 ms) and scatter into ONE grid
         view = net.net_view(inference=False, use_summed=pts.shape[0] >= self.summed_min_batch)
-        scratch = net.summed_grad_scratch() if view.summed is not None else None
+        # the gradient buffers were just zeroed: they double as the single-grid path's scratch (summed[i] aliases grids[i],
+        # no copy-out pass); a frozen grid (no gradient view) keeps the model's own zero-filled scratch
+        scratch = None
+        if view.summed is not None:
+            own = net.summed_grad_scratch()
+            scratch = [g if g is not None else own[i] for i, g in enumerate(grid_grads)]
         # one call: a fused forward+loss+backward launch per LOD head (each with its own loss cell), then ONE restriction
         # cascade for all of them
         mask = 0

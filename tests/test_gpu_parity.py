@@ -584,9 +584,14 @@ def test_fails_loudly_instead_of_falling_back():
     net = OctreeSDF(make_args(["--num-lods", "2"]))               # parameters on the CPU
     with pytest.raises(RuntimeError):
         net.sdf(torch.zeros(4, 3, device=DEV), lod=1)
-    net16 = OctreeSDF(make_args(["--num-lods", "2", "--hidden-dim", "64"])).to(DEV)
+    # the library itself takes feature-dim 32 / hidden-dim 128 only (smaller models are zero-padded by the host class, see
+    # test_model_variants_forward_backward_trace); anything else is refused, nothing is silently approximated
+    with pytest.raises(RuntimeError, match="not supported"):
+        OctreeSDF(make_args(["--num-lods", "2", "--hidden-dim", "256"]))
+    net64 = OctreeSDF(make_args(["--num-lods", "2", "--hidden-dim", "64"])).to(DEV)
+    raw = ops.NetView([f.fm.data for f in net64.features], [tuple(p.data for p in net64.decoder_params(i)) for i in range(2)])
     with pytest.raises(RuntimeError, match="unsupported"):
-        net16.sdf(torch.zeros(4, 3, device=DEV), lod=1)
+        ops.sdf_forward(raw, 1, torch.zeros(4, 3, device=DEV))
     lib = _lib.load()
     assert lib.nglod_aabb(None, None, 5, None, None, None, None) == _lib.EINVAL
     assert lib.nglod_mesh2sdf(None, -1, None, 0, None, None) == _lib.EINVAL
