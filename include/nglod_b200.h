@@ -136,7 +136,8 @@ int nglod_probe_gather(const void* buf, int32_t grid_res, int64_t n_queries, int
                        uint32_t* sink, void* stream);
 /* The scatter twin of nglod_probe_gather: adds a small value to the 8 corner lines of n_queries pseudo-random cells of
  * `buf` with 8 lanes x red.global.add.v4.f32 per line -- the address stream of the backward's grid-gradient scatter,
- * no arithmetic.  Bytes reduced into L2: n_queries * 1024.  Same launch-shape arguments.  `buf` is modified. */
+ * no arithmetic.  Bytes reduced into L2: n_queries * 1024.  Same launch-shape arguments, plus: ctas_per_sm < 0 launches
+ * exactly -ctas_per_sm CTAs (fewer than one per SM: is the limit per SM or chip-wide?).  `buf` is modified. */
 int nglod_probe_scatter(void* buf, int32_t grid_res, int64_t n_queries, int32_t smem_bytes, int32_t ctas_per_sm,
                         uint32_t seed, void* stream);
 

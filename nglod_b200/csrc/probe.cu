@@ -147,10 +147,14 @@ extern "C" int nglod_probe_gather(const void* buf, int32_t grid_res, int64_t n_q
 extern "C" int nglod_probe_scatter(void* buf, int32_t grid_res, int64_t n_queries, int32_t smem_bytes, int32_t ctas_per_sm,
                                    uint32_t seed, void* stream) {
     if (!buf || grid_res < 1 || grid_res > 256 || n_queries < 0) return NGLOD_EINVAL;
-    if (smem_bytes < 0 || smem_bytes > 232448 || ctas_per_sm < 0) return NGLOD_EINVAL;
+    if (smem_bytes < 0 || smem_bytes > 232448) return NGLOD_EINVAL;
     if ((reinterpret_cast<uintptr_t>(buf) & 127u) != 0) return NGLOD_EINVAL;
     if (n_queries == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
+    if (ctas_per_sm < 0) {          // exactly -ctas_per_sm CTAs: is the limit per SM or chip-wide?
+        probe_scatter_kernel<<<-ctas_per_sm, 512, 0, st>>>(reinterpret_cast<float*>(buf), grid_res, n_queries, seed);
+        return (int)cudaGetLastError();
+    }
     PROBE_LAUNCH(probe_scatter_kernel, reinterpret_cast<float*>(buf), grid_res, n_queries, seed);
     return (int)cudaGetLastError();
 }

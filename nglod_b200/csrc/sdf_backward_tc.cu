@@ -43,8 +43,10 @@
 //   named barrier that closes the iteration.  D1[s] / D2[s] of tile T+2 are written by MMAs issued after rec_full(T+2),
 //   i.e. after every service thread's tcgen05.ld of tile T (tcgen05.fence::before_thread_sync precedes the arrive).
 //
-// The roof of this kernel is the L2 atomic units: nglod_probe_scatter measures 6.2 TB/s of reduced bytes for this
-// address stream (0.18 ms per 2^20 queries) whatever the launch shape; everything else is arranged to hide behind it.
+// The roof of this kernel is the reduction path: nglod_probe_scatter measures 6.2 TB/s of reduced bytes for this address
+// stream (0.18 ms per 2^20 queries) whatever the launch shape -- a per-SM limit (one 512-byte RED.v4 warp instruction per
+// 20-26 cycles: 50 GB/s from one CTA alone, 39 GB/s per SM with all of them busy); everything else is arranged to hide
+// behind it, as far as the gather -- which shares the SM's load / store path -- lets it.
 #include "sdf_tc.cuh"
 #include "sdf_core.cuh"
 #include "sparse_core.cuh"

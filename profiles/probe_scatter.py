@@ -28,3 +28,7 @@ for R in (64, 32, 16, 8, 4):
         for smem, ctas in ((0, 0), (0, 1), (200 << 10, 1)):
             t, g = run(R, nq, smem, ctas)
             print(f"{R:3d} {nq:9d} {smem >> 10:5d} KB {ctas:3d}   {t:7.3f} {g:9.0f}", flush=True)
+print("-- exactly k CTAs of 512 threads (R = 64, 2^20 queries): per-SM or chip-wide limit?")
+for k in (148, 111, 74, 37, 18):
+    t, g = run(64, 1 << 20, 0, -k)
+    print(f"  {k:4d} CTAs  {t:7.3f} ms {g:9.0f} GB/s   {g / k:7.1f} GB/s per CTA", flush=True)
