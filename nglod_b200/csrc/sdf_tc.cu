@@ -2,6 +2,7 @@
 // See sdf_tc.cuh / tc_common.cuh for the scheme.  Reference behaviour: sdf-net/lib/models/OctreeSDF.py:94-146.
 #include "sdf_tc.cuh"
 #include "internal.h"
+#include <cstdio>
 
 namespace {
 
@@ -290,6 +291,15 @@ sdf_forward_ws_kernel(const NetDev net, const float* __restrict__ x, const long 
             ax = bx; ay = by; az = bz;
         }
     }
+#ifdef NGLOD_WS_TIMING      // experiment: when does every CTA finish?  (profiles/exp_ws_spread.py)
+    if (threadIdx.x == 0) {
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+        unsigned smid;
+        asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+        printf("WSCTA %d sm %u tiles %d end_ns %llu\n", (int)blockIdx.x, smid, ntiles, t1);
+    }
+#endif
     tc_epilogue_free(tmem_base);
 }
 
