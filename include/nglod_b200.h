@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define NGLOD_ABI_VERSION 9
+#define NGLOD_ABI_VERSION 10
 #define NGLOD_MAX_LODS 8
 
 /* nglod_net_t.math_mode */
@@ -384,6 +384,23 @@ int nglod_spc_sphere_trace(const nglod_sparse_net_t* net, int32_t lod, const int
                            const float* ray_o, const float* ray_d, int64_t n, const nglod_trace_opts_t* opts,
                            float* x, float* depth, uint8_t* hit, float* normal, int32_t* pidx_out,
                            int32_t* queue, unsigned long long* stats, void* stream);
+/* The frame's own fast path (no reference counterpart: the reference renderer takes the two-pass nugget list above).
+ * nglod_spc_raytrace_runs: ONE pass over the rays -- walk, reserve the ray's run with a warp-aggregated atomicAdd, write
+ * it.  nuggets [capacity, 2] holds the runs in arbitrary ray order, each run in the reference's front-to-back order:
+ * the run of ray i is nuggets[run_begin[i] .. run_end[i]).  cursor: device int32[2], set by the call: cursor[0] = slots
+ * reserved, cursor[1] = 1 if capacity was too small (some runs were dropped: take nglod_spc_raytrace_count / _fill).
+ * No scan, no second traversal launch, no host read between traversal and tracing.
+ * nglod_spc_sphere_trace_runs: nglod_spc_sphere_trace over such runs (nglod_spc_sphere_trace(.., offsets, ..) is this
+ * call with run_begin = offsets, run_end = offsets + 1). */
+int nglod_spc_raytrace_runs(const uint8_t* octree, const int32_t* prefix, const int16_t* points,
+                            const int32_t* pyramid_sum, int32_t level, int32_t target_level,
+                            const float* ray_o, const float* ray_d, int64_t n, int64_t capacity,
+                            int32_t* nuggets, int32_t* run_begin, int32_t* run_end, int32_t* cursor, void* stream);
+int nglod_spc_sphere_trace_runs(const nglod_sparse_net_t* net, int32_t lod, const int32_t* nuggets,
+                                const int32_t* run_begin, const int32_t* run_end, const float* ray_o,
+                                const float* ray_d, int64_t n, const nglod_trace_opts_t* opts, float* x,
+                                float* depth, uint8_t* hit, float* normal, int32_t* pidx_out, int32_t* queue,
+                                unsigned long long* stats, void* stream);
 
 /* ---- renderer entry-point helpers ------------------------------------------------
  * Camera rays, x-major (ray = ix*height + iy).  origin/view/right/up: HOST float[3] (already normalised, as computed

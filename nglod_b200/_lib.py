@@ -10,7 +10,7 @@ import ctypes
 import os
 
 MAX_LODS = 8
-EXPECTED_ABI = 9        # include/nglod_b200.h NGLOD_ABI_VERSION the ctypes structs below were written against
+EXPECTED_ABI = 10        # include/nglod_b200.h NGLOD_ABI_VERSION the ctypes structs below were written against
 LOSS_PER_LOD = 0x80000000
 MATH_TC3XTF32 = 0
 MATH_FP32 = 1
@@ -121,6 +121,9 @@ SIGNATURES = {
                                                 c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "nglod_spc_raytrace_fill": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_int32), c_int32, c_int32,
                                                c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "nglod_spc_raytrace_runs": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_int32), c_int32, c_int32,
+                                               c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                               c_void_p]),
     "nglod_spc_mark_first_hit": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "nglod_spc_ray_aabb": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_void_p, c_void_p,
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -134,6 +137,9 @@ SIGNATURES = {
     "nglod_spc_sphere_trace": (ctypes.c_int, [ctypes.POINTER(SparseNetStruct), c_int32, c_void_p, c_void_p, c_void_p,
                                               c_void_p, c_int64, ctypes.POINTER(TraceOpts), c_void_p, c_void_p, c_void_p,
                                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "nglod_spc_sphere_trace_runs": (ctypes.c_int, [ctypes.POINTER(SparseNetStruct), c_int32, c_void_p, c_void_p, c_void_p,
+                                                   c_void_p, c_void_p, c_int64, ctypes.POINTER(TraceOpts), c_void_p, c_void_p,
+                                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "nglod_generate_rays": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float)] * 4 + [ctypes.c_float, c_int32, c_void_p, c_void_p,
                                            c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "nglod_shade_matcap": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int64,

@@ -41,11 +41,10 @@ __constant__ unsigned c_order[8] = {
 __device__ __forceinline__ bool face_eval(float i, float j, float a, float b, float c) {
     const float r0 = __fadd_rn(__fmaf_rn(b, j, __fmul_rn(a, i)), c);
     const float r1 = __fadd_rn(r0, a), r2 = __fadd_rn(r0, b), r3 = __fadd_rn(r1, b);
-    float mn = 1.0f, mx = -1.0f;
-    if (r0 < mn) mn = r0; if (r0 > mx) mx = r0;
-    if (r1 < mn) mn = r1; if (r1 > mx) mx = r1;
-    if (r2 < mn) mn = r2; if (r2 > mx) mx = r2;
-    if (r3 < mn) mn = r3; if (r3 > mx) mx = r3;
+    // the reference starts its running min / max at 1 / -1 and compares with `<` / `>` (a NaN never wins); the test below
+    // only asks for the signs, for which min(1, r..) <= 0 <=> min(r..) <= 0 and fminf / fmaxf skip NaNs the same way:
+    // 6 FMNMX instead of 16 compare-and-select (the traversal is instruction-bound, profiles/README.md part 4)
+    const float mn = fminf(fminf(r0, r1), fminf(r2, r3)), mx = fmaxf(fmaxf(r0, r1), fmaxf(r2, r3));
     return mn <= 0.0f && mx >= 0.0f;
 }
 
@@ -53,18 +52,13 @@ struct RayPre { float ox, oy, oz, dx, dy, dz, cx, cy, cz; };
 
 // d_Decide (:108-138): infinite-line vs voxel overlap from three projected tests
 __device__ __forceinline__ bool decide(const RayPre& r, short4 p, int level) {
-    const float s1 = 1.0f / (float)(1 << level), s2 = s1 * s1;
+    const float s1 = __int_as_float((127 - level) << 23), s2 = s1 * s1;      // 2^-level, exactly what 1.0f / (1 << level) gives
     const float px = (float)(unsigned short)p.x, py = (float)(unsigned short)p.y, pz = (float)(unsigned short)p.z;
     return face_eval(py, pz, -s2 * r.dz, s2 * r.dy, s1 * r.cx) && face_eval(px, pz, s2 * r.dz, -s2 * r.dx, s1 * r.cy) &&
            face_eval(px, py, -s2 * r.dy, s2 * r.dx, s1 * r.cz);
 }
 
-template <bool WRITE>
-__global__ void __launch_bounds__(SPC_THREADS)
-spc_raytrace_kernel(const SpcTree tree, const float* __restrict__ ray_o, const float* __restrict__ ray_d, const int n,
-                    int* __restrict__ counts, const int* __restrict__ offsets, int2* __restrict__ nuggets) {
-    const int ray = blockIdx.x * SPC_THREADS + threadIdx.x;
-    if (ray >= n) return;
+__device__ __forceinline__ RayPre ray_pre(const float* __restrict__ ray_o, const float* __restrict__ ray_d, int ray) {
     RayPre r;
     const float o0 = __ldg(ray_o + 3 * ray), o1 = __ldg(ray_o + 3 * ray + 1), o2 = __ldg(ray_o + 3 * ray + 2);
     r.ox = __fmaf_rn(0.5f, o0, 0.5f); r.oy = __fmaf_rn(0.5f, o1, 0.5f); r.oz = __fmaf_rn(0.5f, o2, 0.5f);
@@ -72,22 +66,21 @@ spc_raytrace_kernel(const SpcTree tree, const float* __restrict__ ray_o, const f
     r.cx = __fmaf_rn(r.oy, r.dz, -__fmul_rn(r.dy, r.oz));
     r.cy = __fmaf_rn(r.oz, r.dx, -__fmul_rn(r.dz, r.ox));
     r.cz = __fmaf_rn(r.ox, r.dy, -__fmul_rn(r.dx, r.oy));
+    return r;
+}
 
-    int count = 0;
-    int wpos = WRITE ? offsets[ray] : 0;
-    // per-level frame: global node index, child-prefix, {mask, order row, next position}
+// Depth-first walk of one ray; emit(pidx) is called for every leaf of the target level the ray's line overlaps, in the
+// reference's order (front to back).
+template <typename Emit>
+__device__ __forceinline__ void spc_walk(const SpcTree& tree, const RayPre& r, Emit emit) {
+    // per-level frame: child-prefix of the node, {mask, remaining order nibbles}, children still to try
     int f_s[SPC_MAX_LEVELS];
     unsigned f_state[SPC_MAX_LEVELS];       // bits 0-7 mask, 8-31 remaining order nibbles (3 bits each), consumed from the low end
     unsigned char f_left[SPC_MAX_LEVELS];   // children still to try
-
-    auto emit = [&](int pidx) {
-        if (WRITE) nuggets[wpos++] = make_int2(ray, pidx);
-        ++count;
-    };
     auto push = [&](int level, int g, short4 p) {     // node (level, g) passed Decide and is above the target level
         const unsigned mask = __ldg(tree.octree + g);
         f_s[level] = __ldg(tree.prefix + g);
-        const float scale = 1.0f / (float)(1 << level);
+        const float scale = __int_as_float((127 - level) << 23);
         // octant of the ray origin relative to the voxel centre (:160-167); exact in double like the reference
         const double x = (double)r.ox - (double)scale * ((double)(unsigned short)p.x + 0.5);
         const double y = (double)r.oy - (double)scale * ((double)(unsigned short)p.y + 0.5);
@@ -99,7 +92,6 @@ spc_raytrace_kernel(const SpcTree tree, const float* __restrict__ ray_o, const f
         f_state[level] = mask | (c_order[code] << 8);
         f_left[level] = 8;
     };
-
     const short4 proot = __ldg(tree.points);
     int sp = -1;
     if (decide(r, proot, 0)) {
@@ -121,7 +113,77 @@ spc_raytrace_kernel(const SpcTree tree, const float* __restrict__ ray_o, const f
         if (level == tree.target) emit(g - tree.pyrsum[level]);
         else { push(level, g, p); sp = level; }
     }
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(SPC_THREADS)
+spc_raytrace_kernel(const SpcTree tree, const float* __restrict__ ray_o, const float* __restrict__ ray_d, const int n,
+                    int* __restrict__ counts, const int* __restrict__ offsets, int2* __restrict__ nuggets) {
+    const int ray = blockIdx.x * SPC_THREADS + threadIdx.x;
+    if (ray >= n) return;
+    const RayPre r = ray_pre(ray_o, ray_d, ray);
+    int count = 0;
+    int wpos = WRITE ? offsets[ray] : 0;
+    spc_walk(tree, r, [&](int pidx) {
+        if (WRITE) nuggets[wpos++] = make_int2(ray, pidx);
+        ++count;
+    });
     if (!WRITE) counts[ray] = count;
+}
+
+// One pass for a consumer that only needs every ray's OWN run (the in-voxel tracer): walk, keep the first RUN_BUF leaves
+// in registers, reserve the run with one atomicAdd per warp (runs of different rays land in arbitrary order; inside a
+// run the order is the reference's), write from the buffer -- or walk again when the run is longer.  No scan, no second
+// launch, no host read of the total; cursor[1] is set when `capacity` is too small (the caller then takes the exact
+// two-pass path).  The average run of a 1080p frame over a level-7 shell is 2.2 nuggets, the longest a few dozen.
+constexpr int RUN_BUF = 8;
+__global__ void __launch_bounds__(SPC_THREADS)
+spc_raytrace_runs_kernel(const SpcTree tree, const float* __restrict__ ray_o, const float* __restrict__ ray_d, const int n,
+                         const int capacity, int2* __restrict__ nuggets, int* __restrict__ run_begin,
+                         int* __restrict__ run_end, int* __restrict__ cursor) {
+    const int ray = blockIdx.x * SPC_THREADS + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool live = ray < n;
+    RayPre r = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int count = 0;
+    int buf[RUN_BUF];
+    if (live) {
+        r = ray_pre(ray_o, ray_d, ray);
+        spc_walk(tree, r, [&](int pidx) {
+#pragma unroll
+            for (int k = 0; k < RUN_BUF; ++k)
+                if (k == count) buf[k] = pidx;
+            ++count;
+        });
+    }
+    // warp-aggregated reservation
+    int incl = count;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    int base = 0;
+    if (lane == 31 && total > 0) base = atomicAdd(cursor, total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    if (!live) return;
+    int begin = base + incl - count;
+    if (count > 0 && (long long)begin + count > (long long)capacity) {
+        atomicExch(cursor + 1, 1);
+        count = 0;
+    }
+    if (count == 0) begin = 0;
+    run_begin[ray] = begin;
+    run_end[ray] = begin + count;
+    if (count <= RUN_BUF) {
+#pragma unroll
+        for (int k = 0; k < RUN_BUF; ++k)
+            if (k < count) nuggets[begin + k] = make_int2(ray, buf[k]);
+    } else {
+        int wpos = begin;
+        spc_walk(tree, r, [&](int pidx) { nuggets[wpos++] = make_int2(ray, pidx); });
+    }
 }
 
 // ---- exclusive scan of int32 counts (n up to 2^31): block scan -> scan of block sums -> add
@@ -300,6 +362,24 @@ extern "C" int nglod_spc_raytrace_fill(const uint8_t* octree, const int32_t* pre
     const int nb = (int)((n + SPC_THREADS - 1) / SPC_THREADS);
     spc_raytrace_kernel<true><<<nb, SPC_THREADS, 0, (cudaStream_t)stream>>>(tree, ray_o, ray_d, (int)n, nullptr, offsets,
                                                                             reinterpret_cast<int2*>(nuggets));
+    return (int)cudaGetLastError();
+}
+
+extern "C" int nglod_spc_raytrace_runs(const uint8_t* octree, const int32_t* prefix, const int16_t* points,
+                                       const int32_t* pyramid_sum, int32_t level, int32_t target_level,
+                                       const float* ray_o, const float* ray_d, int64_t n, int64_t capacity,
+                                       int32_t* nuggets, int32_t* run_begin, int32_t* run_end, int32_t* cursor, void* stream) {
+    SpcTree tree;
+    if (int e = make_tree(tree, octree, prefix, points, pyramid_sum, level, target_level)) return e;
+    if (n < 0 || n > 2000000000ll || capacity < 0 || capacity > 2000000000ll || !cursor) return NGLOD_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    NGLOD_CUDA_TRY(cudaMemsetAsync(cursor, 0, 2 * sizeof(int32_t), st));
+    if (n == 0) return 0;
+    if (!ray_o || !ray_d || !run_begin || !run_end || (capacity > 0 && !nuggets)) return NGLOD_EINVAL;
+    if (reinterpret_cast<uintptr_t>(nuggets) & 7u) return NGLOD_EINVAL;
+    const int nb = (int)((n + SPC_THREADS - 1) / SPC_THREADS);
+    spc_raytrace_runs_kernel<<<nb, SPC_THREADS, 0, st>>>(tree, ray_o, ray_d, (int)n, (int)capacity,
+                                                         reinterpret_cast<int2*>(nuggets), run_begin, run_end, cursor);
     return (int)cudaGetLastError();
 }
 

@@ -158,8 +158,8 @@ enum : int { SP_EMPTY = 0, SP_MARCH = 1, SP_N0 = 2 };     // SP_N0..SP_N0+5: nor
 
 template <bool TC>
 __global__ void __launch_bounds__(TC ? SP_TC_THREADS : SDF_THREADS, TC ? 1 : 2)
-spc_sphere_trace_kernel(const SparseDev sn, const int2* __restrict__ nuggets, const int* __restrict__ offsets,
-                        const float* __restrict__ ray_o, const float* __restrict__ ray_d, const long long n,
+spc_sphere_trace_kernel(const SparseDev sn, const int2* __restrict__ nuggets, const int* __restrict__ run_begin,
+                        const int* __restrict__ run_end, const float* __restrict__ ray_o, const float* __restrict__ ray_d, const long long n,
                         const SpTraceParams tp, float* __restrict__ out_x, float* __restrict__ out_t,
                         uint8_t* __restrict__ out_hit, float* __restrict__ out_n, int* __restrict__ out_pidx,
                         int* __restrict__ queue, unsigned long long* __restrict__ stats) {
@@ -169,7 +169,7 @@ spc_sphere_trace_kernel(const SparseDev sn, const int2* __restrict__ nuggets, co
     const int lane = threadIdx.x & 31;
     const float vr = 1.0f / (float)(1 << (sn.lod + sn.base_lod));       // voxel "radius" in [-1,1] units
 
-    int phase = SP_EMPTY, iter = 0, pidx = -1, beg = 0, end = 0;
+    int phase = SP_EMPTY, iter = 0, pidx = -1, beg = 0, end = 0, cur = 0;
     long long ray = -1;
     float ox = 0.f, oy = 0.f, oz = 0.f;
     RayConst rc = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -186,9 +186,14 @@ spc_sphere_trace_kernel(const SparseDev sn, const int2* __restrict__ nuggets, co
         if (out_pidx) out_pidx[ray] = pidx;
         phase = SP_EMPTY;
     };
-    // walk the run front to back from (x,y,z); returns false (and parks the ray at t = 100) when no voxel is left
-    auto locate = [&]() -> bool {
-        for (int i = beg; i < end; ++i) {
+    // walk the run front to back from (x,y,z); returns false (and parks the ray at t = 100) when no voxel is left.
+    // The reference walks the whole run from its first nugget at every step (ray_aabb.cuh:104-192).  The run is ordered
+    // along the ray, so after a FORWARD step every nugget in front of the voxel the point was in lies behind the point and
+    // answers 0 ("not inside, entry plane behind"): the walk may resume at that voxel (`cur`) with the same result -- at
+    // level 7 a run that crosses the surface shell is ~15 nuggets of two dependent loads each, per march step.  A backward
+    // step (d < 0, the point is inside the surface) restarts at the first nugget.
+    auto locate = [&](bool resume) -> bool {
+        for (int i = resume ? cur : beg; i < end; ++i) {
             const int pi = nuggets[i].y;
             const short4 p = __ldg(sn.voxels + sn.vox_off + pi);
             const float vx = __fmaf_rn(vr, __fmaf_rn(2.0f, (float)p.x, 1.0f), -1.0f);
@@ -197,6 +202,7 @@ spc_sphere_trace_kernel(const SparseDev sn, const int2* __restrict__ nuggets, co
             const float d = aabb_voxel(rc, x, y, z, vx, vy, vz, vr);
             if (d != 0.0f) {
                 pidx = pi;
+                cur = i;
                 if (d > 0.0f) {
                     t = t + d;
                     x = __fmaf_rn(rc.dx, t, ox); y = __fmaf_rn(rc.dy, t, oy); z = __fmaf_rn(rc.dz, t, oz);
@@ -227,10 +233,10 @@ spc_sphere_trace_kernel(const SparseDev sn, const int2* __restrict__ nuggets, co
                     rc.dx = __ldg(ray_d + 3 * i); rc.dy = __ldg(ray_d + 3 * i + 1); rc.dz = __ldg(ray_d + 3 * i + 2);
                     rc.ix = 1.0f / rc.dx; rc.iy = 1.0f / rc.dy; rc.iz = 1.0f / rc.dz;
                     rc.sx = signbit(rc.dx) ? 1.0f : -1.0f; rc.sy = signbit(rc.dy) ? 1.0f : -1.0f; rc.sz = signbit(rc.dz) ? 1.0f : -1.0f;
-                    beg = offsets[i]; end = offsets[i + 1];
-                    x = ox; y = oy; z = oz; t = 0.f; dprev = 0.f; iter = 0; pidx = -1;
+                    beg = run_begin[i]; end = run_end[i];
+                    x = ox; y = oy; z = oz; t = 0.f; dprev = 0.f; iter = 0; pidx = -1; cur = beg;
                     if (beg == end) retire(false, 0.f, 0.f, 0.f);                 // never entered the octree
-                    else if (tp.num_steps > 0 && locate()) phase = SP_MARCH;
+                    else if (tp.num_steps > 0 && locate(false)) phase = SP_MARCH;
                     else retire(false, 0.f, 0.f, 0.f);
                 }
             }
@@ -261,7 +267,7 @@ spc_sphere_trace_kernel(const SparseDev sn, const int2* __restrict__ nuggets, co
             x = __fmaf_rn(rc.dx, t, ox); y = __fmaf_rn(rc.dy, t, oy); z = __fmaf_rn(rc.dz, t, oz);
             dprev = d;
             ++iter;
-            if (cond) cond = locate();                      // SDF.cu:442-460: re-locate the voxel from the new x
+            if (cond) cond = locate(d >= 0.f);              // SDF.cu:442-460: re-locate the voxel from the new x
             if (hit) {
                 if (tp.compute_normals) phase = SP_N0; else retire(true, 0.f, 0.f, 0.f);
             } else if (!cond || iter >= tp.num_steps) {
@@ -316,11 +322,21 @@ extern "C" int nglod_spc_sphere_trace(const nglod_sparse_net_t* net, int32_t lod
                                       const int32_t* offsets, const float* ray_o, const float* ray_d, int64_t n,
                                       const nglod_trace_opts_t* opts, float* x, float* depth, uint8_t* hit, float* normal,
                                       int32_t* pidx_out, int32_t* queue, unsigned long long* stats, void* stream) {
+    if (n > 0 && !offsets) return NGLOD_EINVAL;
+    return nglod_spc_sphere_trace_runs(net, lod, nuggets, offsets, offsets ? offsets + 1 : nullptr, ray_o, ray_d, n, opts, x,
+                                       depth, hit, normal, pidx_out, queue, stats, stream);
+}
+
+extern "C" int nglod_spc_sphere_trace_runs(const nglod_sparse_net_t* net, int32_t lod, const int32_t* nuggets,
+                                           const int32_t* run_begin, const int32_t* run_end, const float* ray_o,
+                                           const float* ray_d, int64_t n, const nglod_trace_opts_t* opts, float* x,
+                                           float* depth, uint8_t* hit, float* normal, int32_t* pidx_out, int32_t* queue,
+                                           unsigned long long* stats, void* stream) {
     SparseDev sn;
     if (int e = make_sparse_dev(net, lod, sn)) return e;
     if (!opts || n < 0 || n > 2000000000ll || opts->num_steps < 0) return NGLOD_EINVAL;
     if (n == 0) return 0;
-    if (!offsets || !ray_o || !ray_d || !x || !depth || !hit || !normal || !queue) return NGLOD_EINVAL;
+    if (!run_begin || !run_end || !ray_o || !ray_d || !x || !depth || !hit || !normal || !queue) return NGLOD_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     NGLOD_CUDA_TRY(cudaMemsetAsync(queue, 0, sizeof(int32_t), st));
     SpTraceParams tp;
@@ -337,7 +353,7 @@ extern "C" int nglod_spc_sphere_trace(const nglod_sparse_net_t* net, int32_t lod
         long long grid = nglod_sm_count();
         const long long want = (n + SP_TC_THREADS - 1) / SP_TC_THREADS;
         if (want < grid) grid = want;
-        kern<<<(int)grid, SP_TC_THREADS, SP_TC_SMEM, st>>>(sn, nug, offsets, ray_o, ray_d, (long long)n, tp, x, depth, hit,
+        kern<<<(int)grid, SP_TC_THREADS, SP_TC_SMEM, st>>>(sn, nug, run_begin, run_end, ray_o, ray_d, (long long)n, tp, x, depth, hit,
                                                            normal, pidx_out, queue, stats);
     } else {
         auto kern = spc_sphere_trace_kernel<false>;
@@ -345,7 +361,7 @@ extern "C" int nglod_spc_sphere_trace(const nglod_sparse_net_t* net, int32_t lod
         long long grid = (long long)nglod_sm_count() * 2;
         const long long want = (n + SDF_THREADS - 1) / SDF_THREADS;
         if (want < grid) grid = want;
-        kern<<<(int)grid, SDF_THREADS, SDF_SMEM_BYTES, st>>>(sn, nug, offsets, ray_o, ray_d, (long long)n, tp, x, depth, hit,
+        kern<<<(int)grid, SDF_THREADS, SDF_SMEM_BYTES, st>>>(sn, nug, run_begin, run_end, ray_o, ray_d, (long long)n, tp, x, depth, hit,
                                                              normal, pidx_out, queue, stats);
     }
     return (int)cudaGetLastError();

@@ -162,6 +162,28 @@ class SPC:
         return (nuggets, offsets) if return_offsets else nuggets
 
 
+def _raytrace_runs(spc, ray_o, ray_d, target_level, capacity=None):
+    """One-pass traversal for the in-voxel tracer (nglod_spc_raytrace_runs): per-ray runs in a re-used buffer of
+    `capacity` nuggets (default 4 per ray, at least 2^20).  Returns (nuggets, run_begin, run_end, cursor); cursor[1] != 0
+    means the buffer was too small (read it AFTER queueing the work that uses the runs, then fall back)."""
+    lib = _lib.load()
+    n, dev = ray_o.shape[0], ray_o.device
+    explicit = capacity is not None
+    capacity = max(1 << 20, 4 * n) if capacity is None else int(capacity)
+    ws = getattr(spc, "_runs_ws", None)
+    if ws is None or ws["n"] != n or ws["dev"] != dev or (ws["cap"] != capacity if explicit else ws["cap"] < capacity):
+        ws = {"n": n, "cap": capacity, "dev": dev, "nuggets": torch.empty(capacity, 2, dtype=torch.int32, device=dev),
+              "begin": torch.empty(n, dtype=torch.int32, device=dev), "end": torch.empty(n, dtype=torch.int32, device=dev),
+              "cursor": torch.zeros(2, dtype=torch.int32, device=dev)}
+        spc._runs_ws = ws
+    with torch.cuda.device(dev):
+        _lib.check(lib.nglod_spc_raytrace_runs(_ptr(spc.octree), _ptr(spc.prefix), _ptr(spc.points), spc._pyrsum, spc.level,
+                                               int(target_level), _ptr(ray_o), _ptr(ray_d), n, ws["cap"], _ptr(ws["nuggets"]),
+                                               _ptr(ws["begin"]), _ptr(ws["end"]), _ptr(ws["cursor"]), _stream()),
+                   "nglod_spc_raytrace_runs")
+    return ws["nuggets"], ws["begin"], ws["end"], ws["cursor"]
+
+
 def mark_first_hit(nuggets):
     lib = _lib.load()
     m = nuggets.shape[0]
@@ -375,13 +397,23 @@ class SparseOctreeSDF:
                        "nglod_sparse_sdf_forward")
         return out
 
-    def trace(self, ray_o, ray_d, lod, num_steps=50, min_dis=0.0003, far=5.0, normal_h=0.001, stats=None):
+    def trace(self, ray_o, ray_d, lod, num_steps=50, min_dis=0.0003, far=5.0, normal_h=0.001, stats=None, one_pass=True,
+              runs_capacity=None):
         """The reference renderer's frame: traverse -> first voxel -> in-voxel sphere trace with re-location
-        (sol-renderer/sdfRenderer.cu:176-260 + SDF.cu:297-472).  Returns (x, depth, hit, normal, pidx)."""
+        (sol-renderer/sdfRenderer.cu:176-260 + SDF.cu:297-472).  Returns (x, depth, hit, normal, pidx).
+        one_pass (default): the traversal writes per-ray runs in one pass (nglod_spc_raytrace_runs) and the tracer starts
+        without a host read in between; the "buffer too small" flag is read after the frame has been queued, and the frame
+        is redone through the exact two-pass list (`spc.raytrace`, the reference's nugget order) if it was set.
+        one_pass=False: always the two-pass list.  Same result either way (the tracer only ever walks a ray's own run)."""
         lib = _lib.load()
         ray_o, ray_d = _f32c(ray_o, "ray_o"), _f32c(ray_d, "ray_d")
         n, dev = ray_o.shape[0], ray_o.device
-        nuggets, offsets = self.spc.raytrace(ray_o, ray_d, lod + self.base_lod, return_offsets=True)
+        cursor = None
+        if one_pass and n > 0:
+            nuggets, run_begin, run_end, cursor = _raytrace_runs(self.spc, ray_o, ray_d, lod + self.base_lod, runs_capacity)
+        else:
+            nuggets, offsets = self.spc.raytrace(ray_o, ray_d, lod + self.base_lod, return_offsets=True)
+            run_begin, run_end = offsets[:-1], offsets[1:]
         x = torch.empty(n, 3, device=dev)
         depth = torch.empty(n, 1, device=dev)
         hit = torch.empty(n, dtype=torch.bool, device=dev)
@@ -391,10 +423,14 @@ class SparseOctreeSDF:
         opts = _lib.TraceOpts(int(num_steps), 1, 1.0, float(min_dis), float(far), float(normal_h))
         s = self.struct()
         with torch.cuda.device(dev):
-            _lib.check(lib.nglod_spc_sphere_trace(ctypes.byref(s), int(lod), _ptr(nuggets), _ptr(offsets), _ptr(ray_o),
-                                                  _ptr(ray_d), n, ctypes.byref(opts), _ptr(x), _ptr(depth), _ptr(hit),
-                                                  _ptr(normal), _ptr(pidx), _ptr(queue), _ptr(stats), _stream()),
-                       "nglod_spc_sphere_trace")
+            _lib.check(lib.nglod_spc_sphere_trace_runs(ctypes.byref(s), int(lod), _ptr(nuggets), _ptr(run_begin), _ptr(run_end),
+                                                       _ptr(ray_o), _ptr(ray_d), n, ctypes.byref(opts), _ptr(x), _ptr(depth),
+                                                       _ptr(hit), _ptr(normal), _ptr(pidx), _ptr(queue), _ptr(stats), _stream()),
+                       "nglod_spc_sphere_trace_runs")
+        if cursor is not None and int(cursor[1]) != 0:       # read after everything is queued: no bubble in the common case
+            if stats is not None:
+                stats.zero_()
+            return self.trace(ray_o, ray_d, lod, num_steps, min_dis, far, normal_h, stats, one_pass=False)
         return x, depth, hit, normal, pidx
 
 

@@ -271,6 +271,38 @@ def _shell_octree(level, device):
 
 
 @pytest.mark.gpu
+def test_one_pass_runs_equal_the_two_pass_nugget_list(fit3):
+    """nglod_spc_raytrace_runs (one pass, per-ray runs in arbitrary ray order) against the two-pass list that is pinned to the
+    reference's spc_raytrace: every ray's run holds the same voxels in the same order; the tracer over the runs returns
+    the two-pass frame bit for bit; a buffer that is too small is reported and the frame is redone through the list."""
+    net, args, spc, sp = _fit3_sparse(fit3, "cuda")
+    torch.manual_seed(8)
+    ro, rd = O.look_at([-2.8, 2.8, -2.8], [0, 0, 0], 160, 90, fov=30.0)
+    ro, rd = ro.cuda().contiguous(), rd.cuda().contiguous()
+    nug, off = spc.raytrace(ro, rd, 4, return_offsets=True)
+    rn, rb, re, cur = S._raytrace_runs(spc, ro, rd, 4)
+    assert int(cur[1]) == 0 and int(cur[0]) == nug.shape[0]
+    assert torch.equal((re - rb), (off[1:] - off[:-1]))
+    nz = (re > rb).nonzero(as_tuple=True)[0]
+    assert nz.numel() > 1000
+    longest = int((re - rb).max())
+    assert longest > 8                                   # runs longer than the register buffer take the second walk
+    for k in range(longest):                             # k-th nugget of every run that has one
+        sel = nz[(re - rb)[nz] > k]
+        a = rn[(rb[sel] + k).long()]
+        b = nug[(off[sel] + k).long()]
+        assert torch.equal(a, b)
+    f2 = sp.trace(ro, rd, 2, one_pass=False)
+    f1 = sp.trace(ro, rd, 2, one_pass=True)
+    for a, b in zip(f1, f2):
+        assert torch.equal(a, b)
+    small = sp.trace(ro, rd, 2, one_pass=True, runs_capacity=1000)      # overflows -> falls back to the list
+    assert int(spc._runs_ws["cursor"][1]) == 1
+    for a, b in zip(small, f2):
+        assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("pos_invariant", [False, True])
 def test_neural_spc_forward_backward_vs_oracle(pos_invariant):
     """NeuralSPC (features only on the corners of occupied voxels; the reference's app/spc model): sdf and its gradients
