@@ -154,16 +154,12 @@ class Renderer():
                 mm = mm.to(view.device)
                 view = torch.mm(view.reshape(-1, 3), mm.transpose(1, 0)).reshape(self.width, self.height, 3)
             matcap = self._get_matcap(view.device)
-            if view.is_cuda:
-                # envmap + bilinear lookup + "misses are white" (normals of misses -> 1) in one kernel
-                rb.normal = rb.normal.contiguous()
-                rb.rgb = ops.shade_matcap(view, rb.normal, rb.hit, matcap.tex)
-            else:
-                uv = spherical_envmap(view.clone(), rb.normal.clone())
-                rb.rgb = matcap(uv).reshape(self.width, self.height, -1)[..., :3] / 255.0
-                miss = ~rb.hit[..., 0]
-                rb.normal[miss] = 1.0
-                rb.rgb[miss] = 1.0
+            if not view.is_cuda:
+                raise RuntimeError("Renderer.shade_tensor: the render buffers must live on a CUDA device (no CPU path)")
+            # envmap + bilinear lookup + "misses are white" (normals of misses -> 1) in one kernel (the scipy-pinned host
+            # recipe it is tested against is geoutils.spherical_envmap + matcap_sampler, tests/test_gpu_parity.py)
+            rb.normal = rb.normal.contiguous()
+            rb.rgb = ops.shade_matcap(view, rb.normal, rb.hit, matcap.tex)
         elif self.shading_mode == "rb":
             assert rb.rgb is not None, "No rgb in buffer; change shading-mode"
             miss = ~rb.hit[..., 0]
