@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define NGLOD_ABI_VERSION 10
+#define NGLOD_ABI_VERSION 11
 #define NGLOD_MAX_LODS 8
 
 /* nglod_net_t.math_mode */
@@ -242,6 +242,29 @@ int nglod_sphere_trace(const nglod_net_t* net, int32_t lod,
                        const nglod_trace_opts_t* opts,
                        float* x, float* depth, uint8_t* hit, float* normal,
                        int32_t* queue, unsigned long long* stats, void* stream);
+/* The same frame as packed per-ray records, each written with 16-byte stores when the ray retires.  Meant for a PINNED
+ * HOST buffer (cudaHostAlloc memory is device-addressable under unified addressing): the results cross PCIe as posted
+ * writes while the kernel runs, so a host caller needs no device->host copy of the frame after the trace and no
+ * chunking -- SphereTracer.trace_lookat_host(packed=True).
+ *   hit == NULL: packed is [n][8] fp32 (32-byte aligned) = {depth, nx, ny, nz, hit (uint32 0 / 1), x, y, z};
+ *   hit != NULL: packed is [n][4] fp32 (16-byte aligned) = {depth, nx, ny, nz} and the hit flags go to hit [n] (bytes,
+ *                normally DEVICE memory: n bytes to copy afterwards instead of 17 n).
+ * No reference counterpart (the reference's `.cpu()` copies every RenderBuffer field after the frame). */
+int nglod_sphere_trace_packed(const nglod_net_t* net, int32_t lod, const float* ray_o, const float* ray_d,
+                              int64_t n, const nglod_trace_opts_t* opts, float* packed, uint8_t* hit, int32_t* queue,
+                              unsigned long long* stats, void* stream);
+
+/* One camera frame, host to host, in ONE call: window coordinates (width + height floats, pinned host or device memory)
+ * -> nglod_generate_rays -> nglod_sphere_trace_packed -> (hit_copy != NULL) the n hit bytes copied to hit_copy, all
+ * queued on `stream`; the caller synchronises the stream and reads `packed` / `hit_copy`.  workspace: device memory,
+ * (6 n + width + height) floats (the rays and the window), n = width * height.  packed / hit as in
+ * nglod_sphere_trace_packed.  Replaces, for a host caller, Renderer.render_lookat + `.cpu()`
+ * (sdf-net/lib/renderer.py:89-107: look_at -> tracer -> RenderBuffer fields copied back one by one). */
+int nglod_sphere_trace_camera(const nglod_net_t* net, int32_t lod, const float* origin, const float* view,
+                              const float* right, const float* up, float tan_half_fov, int32_t ortho,
+                              const float* window_x, const float* window_y, int32_t width, int32_t height,
+                              const nglod_trace_opts_t* opts, float* workspace, float* packed, uint8_t* hit,
+                              uint8_t* hit_copy, int32_t* queue, unsigned long long* stats, void* stream);
 
 /* ---- mesh -> signed distance ----------------------------------------------
  * Replaces: mesh2sdf_gpu_fast_nopre -> kernel_mesh2sdf_quad + kernel_quad_aggr,

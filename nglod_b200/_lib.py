@@ -10,7 +10,7 @@ import ctypes
 import os
 
 MAX_LODS = 8
-EXPECTED_ABI = 10        # include/nglod_b200.h NGLOD_ABI_VERSION the ctypes structs below were written against
+EXPECTED_ABI = 11        # include/nglod_b200.h NGLOD_ABI_VERSION the ctypes structs below were written against
 LOSS_PER_LOD = 0x80000000
 MATH_TC3XTF32 = 0
 MATH_FP32 = 1
@@ -117,6 +117,13 @@ SIGNATURES = {
     "nglod_sphere_trace": (ctypes.c_int, [ctypes.POINTER(NetStruct), c_int32, c_void_p, c_void_p, c_int64,
                                           ctypes.POINTER(TraceOpts), c_void_p, c_void_p, c_void_p, c_void_p,
                                           c_void_p, c_void_p, c_void_p]),
+    "nglod_sphere_trace_packed": (ctypes.c_int, [ctypes.POINTER(NetStruct), c_int32, c_void_p, c_void_p, c_int64,
+                                                 ctypes.POINTER(TraceOpts), c_void_p, c_void_p, c_void_p, c_void_p,
+                                                 c_void_p]),
+    "nglod_sphere_trace_camera": (ctypes.c_int, [ctypes.POINTER(NetStruct), c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                 ctypes.c_float, c_int32, c_void_p, c_void_p, c_int32, c_int32,
+                                                 ctypes.POINTER(TraceOpts), c_void_p, c_void_p, c_void_p, c_void_p,
+                                                 c_void_p, c_void_p, c_void_p]),
     "nglod_spc_raytrace_count": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_int32), c_int32, c_int32,
                                                 c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "nglod_spc_raytrace_fill": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_int32), c_int32, c_int32,

@@ -84,10 +84,25 @@ sphere_trace_kernel(const NetDev net, const float* __restrict__ ray_o, const flo
     const unsigned lt_mask = (1u << lane) - 1u;
 
     auto retire = [&](bool hit, float nx, float ny, float nz) {
-        out_x[3 * ray] = x; out_x[3 * ray + 1] = y; out_x[3 * ray + 2] = z;
-        out_t[ray] = t;
-        out_hit[ray] = hit ? 1 : 0;
-        out_n[3 * ray] = nx; out_n[3 * ray + 1] = ny; out_n[3 * ray + 2] = nz;
+        if (out_t == nullptr) {
+            // packed records (nglod_sphere_trace_packed) -- what a pinned HOST buffer wants: posted PCIe writes as the rays
+            // retire (the eight scalar stores of the field layout cost the kernel 0.87 -> 1.33 ms when they cross PCIe).
+            // out_hit == nullptr: out_x is [n][8] = {depth, nx, ny, nz | hit (u32 0/1), x, y, z}, two 16-byte stores per ray;
+            // otherwise out_x is [n][4] = {depth, nx, ny, nz}, one 16-byte store, and the hit byte goes to out_hit
+            if (out_hit == nullptr) {
+                float4* rec = reinterpret_cast<float4*>(out_x) + 2 * ray;
+                rec[0] = make_float4(t, nx, ny, nz);
+                rec[1] = make_float4(__uint_as_float(hit ? 1u : 0u), x, y, z);
+            } else {
+                reinterpret_cast<float4*>(out_x)[ray] = make_float4(t, nx, ny, nz);
+                out_hit[ray] = hit ? 1 : 0;
+            }
+        } else {
+            out_x[3 * ray] = x; out_x[3 * ray + 1] = y; out_x[3 * ray + 2] = z;
+            out_t[ray] = t;
+            out_hit[ray] = hit ? 1 : 0;
+            out_n[3 * ray] = nx; out_n[3 * ray + 1] = ny; out_n[3 * ray + 2] = nz;
+        }
         phase = PH_EMPTY;
     };
     auto finish_march = [&]() {
@@ -226,14 +241,58 @@ sphere_trace_kernel(const NetDev net, const float* __restrict__ ray_o, const flo
 
 }  // namespace
 
+static int trace_launch(const nglod_net_t* net, int32_t lod, const float* ray_o, const float* ray_d, int64_t n,
+                        const nglod_trace_opts_t* opts, float* x, float* depth, uint8_t* hit, float* normal, int32_t* queue,
+                        unsigned long long* stats, void* stream);
+
 extern "C" int nglod_sphere_trace(const nglod_net_t* net, int32_t lod, const float* ray_o, const float* ray_d,
                                   int64_t n, const nglod_trace_opts_t* opts, float* x, float* depth,
                                   uint8_t* hit, float* normal, int32_t* queue, unsigned long long* stats,
                                   void* stream) {
+    if (n > 0 && (!x || !depth || !hit || !normal)) return NGLOD_EINVAL;
+    return trace_launch(net, lod, ray_o, ray_d, n, opts, x, depth, hit, normal, queue, stats, stream);
+}
+
+extern "C" int nglod_sphere_trace_packed(const nglod_net_t* net, int32_t lod, const float* ray_o, const float* ray_d,
+                                         int64_t n, const nglod_trace_opts_t* opts, float* packed, uint8_t* hit,
+                                         int32_t* queue, unsigned long long* stats, void* stream) {
+    if (n > 0 && (!packed || (reinterpret_cast<uintptr_t>(packed) & (hit ? 15u : 31u)))) return NGLOD_EINVAL;
+    return trace_launch(net, lod, ray_o, ray_d, n, opts, packed, nullptr, hit, nullptr, queue, stats, stream);
+}
+
+extern "C" int nglod_sphere_trace_camera(const nglod_net_t* net, int32_t lod, const float* origin, const float* view,
+                                         const float* right, const float* up, float tan_half_fov, int32_t ortho,
+                                         const float* window_x, const float* window_y, int32_t width, int32_t height,
+                                         const nglod_trace_opts_t* opts, float* workspace, float* packed, uint8_t* hit,
+                                         uint8_t* hit_copy, int32_t* queue, unsigned long long* stats, void* stream) {
+    if (width < 0 || height < 0) return NGLOD_EINVAL;
+    const long long n = (long long)width * height;
+    if (n == 0) return 0;
+    if (!workspace || !window_x || !window_y || !packed || (hit_copy && !hit)) return NGLOD_EINVAL;
+    if (reinterpret_cast<uintptr_t>(packed) & (hit ? 15u : 31u)) return NGLOD_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    float* ray_o = workspace;
+    float* ray_d = workspace + 3 * n;
+    float* wx = workspace + 6 * n;
+    float* wy = wx + width;
+    // the window may live in (pinned) host memory or on the device: 4 (W + H) bytes
+    NGLOD_CUDA_TRY(cudaMemcpyAsync(wx, window_x, sizeof(float) * width, cudaMemcpyDefault, st));
+    NGLOD_CUDA_TRY(cudaMemcpyAsync(wy, window_y, sizeof(float) * height, cudaMemcpyDefault, st));
+    if (int e = nglod_generate_rays(origin, view, right, up, tan_half_fov, ortho, wx, wy, width, height, ray_o, ray_d, stream))
+        return e;
+    if (int e = trace_launch(net, lod, ray_o, ray_d, n, opts, packed, nullptr, hit, nullptr, queue, stats, stream)) return e;
+    if (hit_copy) NGLOD_CUDA_TRY(cudaMemcpyAsync(hit_copy, hit, (size_t)n, cudaMemcpyDefault, st));
+    return 0;
+}
+
+// depth == nullptr: x is the packed record buffer (32-byte records if hit == nullptr too, else 16-byte records + hit bytes)
+static int trace_launch(const nglod_net_t* net, int32_t lod, const float* ray_o, const float* ray_d, int64_t n,
+                        const nglod_trace_opts_t* opts, float* x, float* depth, uint8_t* hit, float* normal, int32_t* queue,
+                        unsigned long long* stats, void* stream) {
     if (int e = nglod_check_net(net, lod)) return e;
     if (!opts || n < 0 || n > 2000000000ll) return NGLOD_EINVAL;
     if (n == 0) return 0;
-    if (!ray_o || !ray_d || !x || !depth || !hit || !normal || !queue) return NGLOD_EINVAL;
+    if (!ray_o || !ray_d || !x || !queue) return NGLOD_EINVAL;
     if (opts->num_steps < 0) return NGLOD_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     NGLOD_CUDA_TRY(cudaMemsetAsync(queue, 0, sizeof(int32_t), st));

@@ -64,14 +64,22 @@ class SphereTracer(BaseTracer):
         return self._host_pipeline(net, n, stage, out, ("x", "depth", "hit", "normal"), chunks, streams, fractions)
 
     def trace_lookat_host(self, net, f, t, width, height, fov=30.0, mode="persp", window=None, out=None,
-                          fields=("depth", "hit", "normal"), chunks=3, streams=2):
+                          fields=("depth", "hit", "normal"), chunks=3, streams=2, packed=False):
         """The camera-driven host call: what `Renderer.render_lookat` + `.cpu()` amounts to for a user of the reference
         (renderer.py:89-107: rays come from `look_at(f, t, W, H, fov)`, never from host ray buffers).  Inputs are the
         camera pose (host floats) and the jittered window coordinates `window = (wx [W], wy [H])` in pinned host memory
         (None: drawn on the device as `look_at` does); the W*H rays are generated on the device (nglod_generate_rays,
         x-major like the reference), traced in `chunks` ranges on alternating streams, and the requested RenderBuffer
         `fields` (any of x, depth, hit, normal) are copied into pinned host memory as each range finishes.
-        Per frame over PCIe: (W + H) * 4 bytes up, 17 B/ray down for the default fields (no ray upload, no `x`)."""
+        Per frame over PCIe: (W + H) * 4 bytes up, 17 B/ray down for the default fields (no ray upload, no `x`).
+        packed=True: ONE tracer launch that writes every ray's record straight into a pinned host buffer as the ray
+        retires (nglod_sphere_trace_packed) -- no device->host copy of the frame, no chunking.  Without "x" in `fields` the
+        records are 16 bytes {depth, normal} + one hit byte per ray, both written to pinned host memory by the kernel
+        (17 B/ray over PCIe, nothing to copy afterwards); with "x" they are 32 bytes {depth, normal, hit, x}.  Returns a RenderBuffer whose fields are VIEWS of the pinned
+        buffers (`out`: a dict {"packed": [W*H, 4 or 8] fp32, "hit": [W*H] bool} of pinned tensors to re-use).  The call
+        returns after the frame has arrived.  Measured per 720p frame (profiles/exp_e2e_packed.py): see DESIGN.md section 5;
+        also tried there: copies by idle warps of the kernel itself, and DMA chunks released by the running kernel through
+        stream wait values (a chunk of the image completes only when its longest ray does)."""
         import numpy as np
         from ..geoutils import _window
         dev = next(net.parameters()).device
@@ -81,6 +89,30 @@ class SphereTracer(BaseTracer):
         right = F.normalize(torch.linalg.cross(view, torch.tensor([0.0, 1.0, 0.0])), dim=0)
         up = F.normalize(torch.linalg.cross(right, view), dim=0)
         tan = np.float32(np.tan(np.radians(fov / 2)))
+
+        if packed:
+            if not (_is_octree(net) and self.grad_method == "finitediff" and getattr(net, "interpolate", None) is None):
+                raise RuntimeError("trace_lookat_host: only the fused OctreeSDF tracer has a host path")
+            ws = getattr(self, "_packed_ws", None)
+            if ws is None or ws["n"] != n or ws["dev"] != dev or ws["wh"] != (width, height):
+                ws = {"n": n, "dev": dev, "wh": (width, height), "rays": torch.empty(6 * n + width + height, device=dev),
+                      "queue": torch.empty(1, dtype=torch.int32, device=dev)}
+                self._packed_ws = ws
+            with_x = "x" in fields
+            out = {} if out is None else out
+            if "packed" not in out:
+                out["packed"] = torch.empty(n, 8 if with_x else 4).pin_memory()
+            if not with_x and "hit" not in out:
+                out["hit"] = torch.empty(n, dtype=torch.bool).pin_memory()
+            with torch.cuda.device(dev):
+                wx, wy = _window(width, height, dev) if window is None else window
+                ops.sphere_trace_camera(net.net_view(), _trace_lod(net), origin.tolist(), view.tolist(), right.tolist(),
+                                        up.tolist(), tan, mode == "ortho", wx, wy, ws["rays"], out["packed"],
+                                        hit=None if with_x else out["hit"],
+                                        num_steps=self.num_steps, step_size=self.step_size, min_dis=self.min_dis,
+                                        far=self.camera_clamp[1], queue=ws["queue"])
+                torch.cuda.current_stream(dev).synchronize()
+            return RenderBuffer(**ops.unpack_trace(out["packed"], None if with_x else out["hit"]))
 
         def stage(ws, bounds, s_in):
             with torch.cuda.stream(s_in):

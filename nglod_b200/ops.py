@@ -279,6 +279,84 @@ def sphere_trace(view, lod, ray_o, ray_d, num_steps=256, step_size=1.0, min_dis=
     return x, depth, hit, normal
 
 
+def sphere_trace_packed(view, lod, ray_o, ray_d, packed, hit=None, num_steps=256, step_size=1.0, min_dis=0.0003, far=10.0,
+                        normal_h=1.0 / (64.0 * 3.0), compute_normals=True, stats=None, queue=None):
+    """The frame as packed per-ray records (nglod_sphere_trace_packed).  `packed` may be a device tensor or a PINNED HOST
+    tensor: host memory is written by the kernel itself (posted PCIe writes as rays retire), so a host caller needs no
+    copy of the frame after the trace.
+      hit is None : packed is [N, 8] fp32, 32-byte records {depth, nx, ny, nz, hit (u32), x, y, z};
+      hit [N] bool / uint8 on the rays' device: packed is [N, 4] fp32, 16-byte records {depth, nx, ny, nz}."""
+    lib = _lib.load()
+    ray_o = _f32c(ray_o, "ray_o")
+    ray_d = _f32c(ray_d, "ray_d")
+    n, dev = ray_o.shape[0], ray_o.device
+    width = 8 if hit is None else 4
+    if tuple(packed.shape) != (n, width) or packed.dtype != torch.float32 or not packed.is_contiguous() or \
+            not (packed.device == dev or (packed.device.type == "cpu" and packed.is_pinned())):
+        raise RuntimeError(f"sphere_trace_packed: packed must be a contiguous fp32 [N, {width}] tensor on the rays' device or in "
+                           "pinned host memory")
+    if hit is not None and (tuple(hit.shape) != (n,) or hit.dtype not in (torch.bool, torch.uint8) or not hit.is_contiguous()
+                            or not (hit.device == dev or (hit.device.type == "cpu" and hit.is_pinned()))):
+        raise RuntimeError("sphere_trace_packed: hit must be a contiguous bool / uint8 [N] tensor on the rays' device or in pinned "
+                           "host memory")
+    if queue is None:
+        queue = torch.empty(1, device=dev, dtype=torch.int32)
+    opts = TraceOpts(int(num_steps), 1 if compute_normals else 0, float(step_size), float(min_dis), float(far),
+                     float(normal_h))
+    with torch.cuda.device(dev):
+        _lib.check(lib.nglod_sphere_trace_packed(ctypes.byref(view.struct), lod, _ptr(ray_o), _ptr(ray_d), n,
+                                                 ctypes.byref(opts), _ptr(packed), _ptr(hit), _ptr(queue), _ptr(stats),
+                                                 _stream()),
+                   "nglod_sphere_trace_packed")
+    return packed
+
+
+def sphere_trace_camera(view, lod, origin, cam_view, right, up, tan_half_fov, ortho, window_x, window_y, workspace, packed,
+                        hit=None, hit_copy=None, num_steps=256, step_size=1.0, min_dis=0.0003, far=10.0,
+                        normal_h=1.0 / (64.0 * 3.0), compute_normals=True, stats=None, queue=None):
+    """One camera frame, host to host, in ONE library call (nglod_sphere_trace_camera): window (pinned host or device)
+    -> rays -> packed records -> optional copy of the hit bytes, all queued on the current stream.  The caller
+    synchronises.  workspace: fp32 device tensor of at least 6 W H + W + H elements."""
+    lib = _lib.load()
+    w, h = window_x.shape[0], window_y.shape[0]
+    n, dev = w * h, workspace.device
+    width = 8 if hit is None else 4
+    ok_mem = lambda t: t.is_contiguous() and (t.device == dev or (t.device.type == "cpu" and t.is_pinned()))
+    if workspace.dtype != torch.float32 or workspace.numel() < 6 * n + w + h or not workspace.is_contiguous() or not workspace.is_cuda:
+        raise RuntimeError("sphere_trace_camera: workspace must be a contiguous fp32 device tensor of >= 6 W H + W + H elements")
+    if tuple(packed.shape) != (n, width) or packed.dtype != torch.float32 or not ok_mem(packed):
+        raise RuntimeError(f"sphere_trace_camera: packed must be a contiguous fp32 [W*H, {width}] tensor on the device or in pinned "
+                           "host memory")
+    for t_ in (hit, hit_copy):
+        if t_ is not None and (tuple(t_.shape) != (n,) or t_.dtype not in (torch.bool, torch.uint8) or not ok_mem(t_)):
+            raise RuntimeError("sphere_trace_camera: hit / hit_copy must be contiguous bool / uint8 [W*H] tensors on the device or in "
+                               "pinned host memory")
+    for t_ in (window_x, window_y):
+        if t_.dtype != torch.float32 or not ok_mem(t_):
+            raise RuntimeError("sphere_trace_camera: the window must be contiguous fp32, on the device or in pinned host memory")
+    if queue is None:
+        queue = torch.empty(1, device=dev, dtype=torch.int32)
+    opts = TraceOpts(int(num_steps), 1 if compute_normals else 0, float(step_size), float(min_dis), float(far),
+                     float(normal_h))
+    vec = [(ctypes.c_float * 3)(*[float(c) for c in v]) for v in (origin, cam_view, right, up)]
+    with torch.cuda.device(dev):
+        _lib.check(lib.nglod_sphere_trace_camera(ctypes.byref(view.struct), lod, vec[0], vec[1], vec[2], vec[3],
+                                                 float(tan_half_fov), 1 if ortho else 0, _ptr(window_x), _ptr(window_y), w, h,
+                                                 ctypes.byref(opts), _ptr(workspace), _ptr(packed), _ptr(hit), _ptr(hit_copy),
+                                                 _ptr(queue), _ptr(stats), _stream()), "nglod_sphere_trace_camera")
+    return packed
+
+
+def unpack_trace(packed, hit=None):
+    """Views (no copies) of a packed frame: {x [N,3], depth [N,1], hit [N] bool, normal [N,3]} for 32-byte records,
+    {depth, hit, normal} for 16-byte records + the separate hit flags."""
+    n = packed.shape[0]
+    if packed.shape[1] == 4:
+        return {"depth": packed[:, 0:1], "hit": hit.view(torch.bool), "normal": packed[:, 1:4]}
+    hit = packed.view(torch.uint8).view(n, 32)[:, 16].view(torch.bool)
+    return {"x": packed[:, 5:8], "depth": packed[:, 0:1], "hit": hit, "normal": packed[:, 1:4]}
+
+
 # --------------------------------------------------------------------------- mesh2sdf / adam
 def mesh2sdf_gpu(points, mesh, force_walk=False):
     """Drop-in for `mesh2sdf.mesh2sdf_gpu(points, mesh)` (mesh2sdf_kernel.cu:895-927,1008): returns [dist [N]].

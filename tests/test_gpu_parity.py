@@ -791,6 +791,62 @@ def test_trace_host_pipelined_equals_forward(fit3):
         tr.trace_host(net3, o.to(DEV), d.to(DEV))
 
 
+def test_trace_lookat_host_chunked_and_packed_equal_forward(fit3):
+    """SphereTracer.trace_lookat_host (camera in, pinned host RenderBuffer out): the chunked pipeline, the 32-byte packed
+    records and the 16-byte packed records + hit bytes (nglod_sphere_trace_packed writes PINNED HOST memory from the
+    kernel) all return, bit for bit, what forward() returns for the rays `look_at` builds from the same window."""
+    from nglod_b200.lib.tracer import SphereTracer
+    from nglod_b200.lib.geoutils import _window
+    from nglod_b200 import ops
+    net3, args3 = fit3_model(fit3, DEV)
+    net3.lod = 2
+    W, H, cam, to = 160, 90, [-2.8, 2.8, -2.8], [0.0, 0.0, 0.0]
+    torch.manual_seed(11)
+    wx, wy = _window(W, H, "cpu")
+    wx, wy = wx.pin_memory(), wy.pin_memory()
+    tr = SphereTracer(args3)
+    chunked = tr.trace_lookat_host(net3, cam, to, W, H, fov=30.0, window=(wx, wy), fields=("x", "depth", "hit", "normal"))
+    # the same rays through forward(): regenerate them on the device from the same window
+    origin = torch.tensor(cam)
+    view = torch.nn.functional.normalize(torch.tensor(to) - origin, dim=0)
+    right = torch.nn.functional.normalize(torch.linalg.cross(view, torch.tensor([0.0, 1.0, 0.0])), dim=0)
+    up = torch.nn.functional.normalize(torch.linalg.cross(right, view), dim=0)
+    o, d = ops.generate_rays(origin.tolist(), view.tolist(), right.tolist(), up.tolist(), np.float32(np.tan(np.radians(15.0))),
+                             False, wx.to(DEV), wy.to(DEV))
+    ref = tr(net3, o, d)
+    assert int(ref.hit.sum()) > 500
+    for k in ("x", "depth", "hit", "normal"):
+        assert torch.equal(getattr(chunked, k), getattr(ref, k).cpu()), k
+    p32 = tr.trace_lookat_host(net3, cam, to, W, H, fov=30.0, window=(wx, wy), fields=("x", "depth", "hit", "normal"),
+                               packed=True)
+    for k in ("x", "depth", "hit", "normal"):
+        assert not getattr(p32, k).is_cuda and torch.equal(getattr(p32, k), getattr(ref, k).cpu()), k
+    out16 = {}
+    for _ in range(2):                      # second call re-uses the pinned buffers
+        p16 = tr.trace_lookat_host(net3, cam, to, W, H, fov=30.0, window=(wx, wy), out=out16, packed=True)
+        assert p16.x is None and p16.depth.data_ptr() == out16["packed"].data_ptr() and out16["packed"].is_pinned()
+        for k in ("depth", "hit", "normal"):
+            assert torch.equal(getattr(p16, k), getattr(ref, k).cpu()), k
+    # device-resident packed buffers give the same records; argument checks of the C entry point
+    view3 = net3.net_view()
+    rec = ops.sphere_trace_packed(view3, 2, o, d, torch.empty(W * H, 8, device=DEV))
+    assert torch.equal(rec.cpu(), out_packed32(ref))
+    with pytest.raises(RuntimeError):
+        ops.sphere_trace_packed(view3, 2, o, d, torch.empty(W * H, 8))                 # pageable host memory
+    with pytest.raises(RuntimeError):
+        ops.sphere_trace_packed(view3, 2, o, d, torch.empty(W * H, 4, device=DEV))     # 16-byte records need hit
+    with pytest.raises(RuntimeError):
+        ops.sphere_trace_packed(view3, 2, o, d, torch.empty(W * H * 8 + 1, device=DEV)[1:].view(W * H, 8))   # misaligned
+
+
+def out_packed32(rb):
+    n = rb.hit.shape[0]
+    rec = torch.zeros(n, 8)
+    rec[:, 0:1], rec[:, 1:4], rec[:, 5:8] = rb.depth.cpu(), rb.normal.cpu(), rb.x.cpu()
+    rec.view(torch.int32)[:, 4] = rb.hit.cpu().to(torch.int32)
+    return rec
+
+
 # ------------------------------------------------------------------------------------------------ full-size properties
 def test_full_size_properties_2pow20(rand5):
     """BASELINE configs[0] size (2^20 random points, lod 4), checked through size-independent properties:
