@@ -425,6 +425,12 @@ int nglod_spc_sphere_trace_runs(const nglod_sparse_net_t* net, int32_t lod, cons
                                 float* depth, uint8_t* hit, float* normal, int32_t* pidx_out, int32_t* queue,
                                 unsigned long long* stats, void* stream);
 
+/* Host-only (no device work): the camera frame of look_at -- basis [4][3] = origin, view, right, up from the eye `from`
+ * and the target `to` (3 floats each), in the float32 arithmetic torch's CPU kernels use, so that it equals
+ *   view = F.normalize(to - from); right = F.normalize(cross(view, (0,1,0))); up = F.normalize(cross(right, view))
+ * (sdf-net/lib/geoutils.py:180-188) bit for bit.  Feeds nglod_generate_rays / nglod_sphere_trace_camera. */
+int nglod_camera_basis(const float* from, const float* to, float* basis);
+
 /* ---- renderer entry-point helpers ------------------------------------------------
  * Camera rays, x-major (ray = ix*height + iy).  origin/view/right/up: HOST float[3] (already normalised, as computed
  * by look_at, sdf-net/lib/geoutils.py:180-188); window_x [width] / window_y [height]: DEVICE window coordinates

@@ -120,6 +120,7 @@ SIGNATURES = {
     "nglod_sphere_trace_packed": (ctypes.c_int, [ctypes.POINTER(NetStruct), c_int32, c_void_p, c_void_p, c_int64,
                                                  ctypes.POINTER(TraceOpts), c_void_p, c_void_p, c_void_p, c_void_p,
                                                  c_void_p]),
+    "nglod_camera_basis": (ctypes.c_int, [c_void_p, c_void_p, c_void_p]),
     "nglod_sphere_trace_camera": (ctypes.c_int, [ctypes.POINTER(NetStruct), c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
                                                  ctypes.c_float, c_int32, c_void_p, c_void_p, c_int32, c_int32,
                                                  ctypes.POINTER(TraceOpts), c_void_p, c_void_p, c_void_p, c_void_p,

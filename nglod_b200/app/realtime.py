@@ -31,11 +31,8 @@ from ..lib.models import *  # noqa: F401,F403
 
 def camera_basis(eye, target):
     """view / right / up of look_at (geoutils.py:180-188), on the host."""
-    origin = torch.tensor(list(eye), dtype=torch.float32)
-    view = F.normalize(torch.tensor(list(target), dtype=torch.float32) - origin, dim=0)
-    right = F.normalize(torch.linalg.cross(view, torch.tensor([0.0, 1.0, 0.0])), dim=0)
-    up = F.normalize(torch.linalg.cross(right, view), dim=0)
-    return origin.tolist(), view.tolist(), right.tolist(), up.tolist()
+    from ..lib.geoutils import camera_basis as _basis
+    return _basis(eye, target)
 
 
 def run(net, width, height, frames=60, lod=None, spc_level=None, fov=30.0, radius=None, height_y=2.8, device=None,

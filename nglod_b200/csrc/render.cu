@@ -80,6 +80,34 @@ shade_matcap_kernel(const float* __restrict__ view, float* __restrict__ normal, 
 
 }  // namespace
 
+// Host-only: the camera frame of look_at (geoutils.py:180-188) in the float32 arithmetic torch's CPU kernels use for
+// 3-vectors -- norm = sqrt(fma(z, z, fma(y, y, x * x))), cross component = fma(a1, b2, -(a2 * b1)), F.normalize's
+// v / max(norm, 1e-12) -- so that the basis is the one `F.normalize(torch.linalg.cross(...))` returns on the host bit
+// for bit (tests/test_host_logic.py pins that on random poses) at 1/30 of the cost of eight torch calls.
+static void basis_normalize(float* v) {
+    const float n = sqrtf(fmaf(v[2], v[2], fmaf(v[1], v[1], v[0] * v[0])));
+    const float d = n > 1e-12f ? n : 1e-12f;
+    v[0] = v[0] / d; v[1] = v[1] / d; v[2] = v[2] / d;
+}
+static void basis_cross(const float* a, const float* b, float* c) {
+    const float p0 = a[2] * b[1], p1 = a[0] * b[2], p2 = a[1] * b[0];
+    c[0] = fmaf(a[1], b[2], -p0);
+    c[1] = fmaf(a[2], b[0], -p1);
+    c[2] = fmaf(a[0], b[1], -p2);
+}
+extern "C" int nglod_camera_basis(const float* from, const float* to, float* basis) {
+    if (!from || !to || !basis) return NGLOD_EINVAL;
+    float* origin = basis; float* view = basis + 3; float* right = basis + 6; float* up = basis + 9;
+    const float world_up[3] = {0.f, 1.f, 0.f};
+    for (int k = 0; k < 3; ++k) { origin[k] = from[k]; view[k] = to[k] - from[k]; }
+    basis_normalize(view);
+    basis_cross(view, world_up, right);
+    basis_normalize(right);
+    basis_cross(right, view, up);
+    basis_normalize(up);
+    return 0;
+}
+
 extern "C" int nglod_generate_rays(const float* origin, const float* view, const float* right, const float* up,
                                    float tan_half_fov, int32_t ortho, const float* window_x, const float* window_y,
                                    int32_t width, int32_t height, float* ray_o, float* ray_d, void* stream) {

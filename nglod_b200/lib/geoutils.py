@@ -44,6 +44,19 @@ def _window(width, height, device):
     return wx, wy
 
 
+def camera_basis(f, t):
+    """(origin, view, right, up) of look_at (reference :180-188) as four lists of Python floats, computed on the host by
+    the library (nglod_camera_basis: the float32 arithmetic of torch's CPU kernels, equal bit for bit to
+    `F.normalize(torch.linalg.cross(...))` on the host -- tests/test_host_logic.py) in ~3 us instead of eight torch calls."""
+    import ctypes
+    from .. import _lib
+    lib = _lib.load()
+    a, b, out = (ctypes.c_float * 3)(*f), (ctypes.c_float * 3)(*t), (ctypes.c_float * 12)()
+    _lib.check(lib.nglod_camera_basis(a, b, out), "nglod_camera_basis")
+    v = list(out)
+    return v[0:3], v[3:6], v[6:9], v[9:12]
+
+
 def look_at(f, t, width, height, mode="ortho", fov=90.0, device="cuda"):
     """Ray origins / directions [W*H, 3] for a camera at `f` looking at `t` (reference :180-206).
     On a CUDA device the [W,H] expansion is one kernel (nglod_generate_rays); the jitter is still drawn with
@@ -53,14 +66,11 @@ def look_at(f, t, width, height, mode="ortho", fov=90.0, device="cuda"):
     dev = torch.device(device)
     if dev.type == "cuda":
         from .. import ops
-        origin = torch.tensor(list(f), dtype=torch.float32)
-        view = F.normalize(torch.tensor(list(t), dtype=torch.float32) - origin, dim=0)
-        right = F.normalize(torch.linalg.cross(view, torch.tensor([0.0, 1.0, 0.0])), dim=0)
-        up = F.normalize(torch.linalg.cross(right, view), dim=0)
+        origin, view, right, up = camera_basis(f, t)
         with torch.cuda.device(dev):
             wx, wy = _window(width, height, dev)
         tan = np.float32(np.tan(np.radians(fov / 2)))
-        return ops.generate_rays(origin.tolist(), view.tolist(), right.tolist(), up.tolist(), tan, mode == "ortho", wx, wy)
+        return ops.generate_rays(origin, view, right, up, tan, mode == "ortho", wx, wy)
     origin = torch.tensor(list(f), dtype=torch.float32, device=device)
     view = F.normalize(torch.tensor(list(t), dtype=torch.float32, device=device) - origin, dim=0)
     world_up = torch.tensor([0.0, 1.0, 0.0], device=device)

@@ -184,6 +184,7 @@ class OctreeSDF(BaseLOD):
         if self._derived is not None:
             self._derived[0] = None
         self._padded_cache = None
+        self._views = {}
 
     def load_state_dict(self, *args, **kwargs):
         out = super().load_state_dict(*args, **kwargs)
@@ -194,6 +195,7 @@ class OctreeSDF(BaseLOD):
         out = super()._apply(fn, *args, **kwargs)
         if getattr(self, "_derived", None) is not None:
             self._derived = None            # moved / cast: the derived buffers belong to the old placement
+        self._views = {}
         return out
 
     def _derived_grids(self, want_half=False):
@@ -250,16 +252,31 @@ class OctreeSDF(BaseLOD):
         return sd
 
     def net_view(self, inference=True, use_summed=True):
-        """Borrow the current parameters as an nglod_net_t (rebuilt per call: pointers may move).  inference=False (the
-        autograd / training kernels) never attaches the half-precision copy; use_summed=False leaves the prefix-summed
-        grids out (small training batches: rebuilding them costs more than five short gathers)."""
+        """Borrow the current parameters as an nglod_net_t.  inference=False (the autograd / training kernels) never
+        attaches the half-precision copy; use_summed=False leaves the prefix-summed grids out (small training batches:
+        rebuilding them costs more than five short gathers).  The view is re-used while no parameter was written or
+        moved (version counters + addresses, the same key the derived grids use; mark_grids_dirty() drops it): building
+        one costs ~50 us of host time, which a 1 ms frame notices."""
+        ps = [f._parameters["fm"] for f in self.features._modules.values()]     # direct: Module.parameters() costs 25 us
+        for seq in self.louts._modules.values():
+            for lin in (seq._modules["0"], seq._modules["2"]):
+                ps.append(lin._parameters["weight"])
+                ps.append(lin._parameters["bias"])
+        key = (self.math_mode, self.grid_storage, self.sum_lods, self.pos_invariant,
+               tuple([(p._version, p.data_ptr()) for p in ps]))
+        views = self.__dict__.setdefault("_views", {})
+        hit = views.get((inference, use_summed))
+        if hit is not None and hit[0] == key:
+            return hit[1]
         grids, decs = self._kernel_params()
         summed = half = None
         if use_summed and self.sum_lods and self._grids_nest():
             summed, half = self._derived_grids(want_half=inference and self.grid_storage == "fp16" and self.math_mode == "tc")
-        return ops.NetView(grids, decs, pos_invariant=self.pos_invariant,
+        view = ops.NetView(grids, decs, pos_invariant=self.pos_invariant,
                            math_mode=_lib.MATH_TC3XTF32 if self.math_mode == "tc" else _lib.MATH_FP32,
                            summed=summed, summed_half=half)
+        views[(inference, use_summed)] = (key, view)
+        return view
 
     def _eval_lod(self, x, lod):
         shape = x.shape

@@ -81,13 +81,10 @@ class SphereTracer(BaseTracer):
         also tried there: copies by idle warps of the kernel itself, and DMA chunks released by the running kernel through
         stream wait values (a chunk of the image completes only when its longest ray does)."""
         import numpy as np
-        from ..geoutils import _window
+        from ..geoutils import _window, camera_basis
         dev = next(net.parameters()).device
         n = width * height
-        origin = torch.tensor(list(f), dtype=torch.float32)
-        view = F.normalize(torch.tensor(list(t), dtype=torch.float32) - origin, dim=0)
-        right = F.normalize(torch.linalg.cross(view, torch.tensor([0.0, 1.0, 0.0])), dim=0)
-        up = F.normalize(torch.linalg.cross(right, view), dim=0)
+        origin, view, right, up = camera_basis(f, t)
         tan = np.float32(np.tan(np.radians(fov / 2)))
 
         if packed:
@@ -106,8 +103,8 @@ class SphereTracer(BaseTracer):
                 out["hit"] = torch.empty(n, dtype=torch.bool).pin_memory()
             with torch.cuda.device(dev):
                 wx, wy = _window(width, height, dev) if window is None else window
-                ops.sphere_trace_camera(net.net_view(), _trace_lod(net), origin.tolist(), view.tolist(), right.tolist(),
-                                        up.tolist(), tan, mode == "ortho", wx, wy, ws["rays"], out["packed"],
+                ops.sphere_trace_camera(net.net_view(), _trace_lod(net), origin, view, right,
+                                        up, tan, mode == "ortho", wx, wy, ws["rays"], out["packed"],
                                         hit=None if with_x else out["hit"],
                                         num_steps=self.num_steps, step_size=self.step_size, min_dis=self.min_dis,
                                         far=self.camera_clamp[1], queue=ws["queue"])
@@ -125,7 +122,7 @@ class SphereTracer(BaseTracer):
                     ws["wx"].copy_(window[0], non_blocking=True)
                     ws["wy"].copy_(window[1], non_blocking=True)
                     wx, wy = ws["wx"], ws["wy"]
-                ops.generate_rays(origin.tolist(), view.tolist(), right.tolist(), up.tolist(), tan, mode == "ortho", wx, wy,
+                ops.generate_rays(origin, view, right, up, tan, mode == "ortho", wx, wy,
                                   out=(ws["o"], ws["d"]))
                 ev = torch.cuda.Event()
                 ev.record(s_in)

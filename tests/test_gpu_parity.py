@@ -807,11 +807,9 @@ def test_trace_lookat_host_chunked_and_packed_equal_forward(fit3):
     tr = SphereTracer(args3)
     chunked = tr.trace_lookat_host(net3, cam, to, W, H, fov=30.0, window=(wx, wy), fields=("x", "depth", "hit", "normal"))
     # the same rays through forward(): regenerate them on the device from the same window
-    origin = torch.tensor(cam)
-    view = torch.nn.functional.normalize(torch.tensor(to) - origin, dim=0)
-    right = torch.nn.functional.normalize(torch.linalg.cross(view, torch.tensor([0.0, 1.0, 0.0])), dim=0)
-    up = torch.nn.functional.normalize(torch.linalg.cross(right, view), dim=0)
-    o, d = ops.generate_rays(origin.tolist(), view.tolist(), right.tolist(), up.tolist(), np.float32(np.tan(np.radians(15.0))),
+    from nglod_b200.lib.geoutils import camera_basis
+    origin, view, right, up = camera_basis(cam, to)
+    o, d = ops.generate_rays(origin, view, right, up, np.float32(np.tan(np.radians(15.0))),
                              False, wx.to(DEV), wy.to(DEV))
     ref = tr(net3, o, d)
     assert int(ref.hit.sum()) > 500

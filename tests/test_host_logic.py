@@ -266,3 +266,25 @@ def test_bench_reference_arm_prints_one_json_line():
     # host cores; "port" = the oracle restatement, only when neither is present
     assert j["cpu_baseline"]["kind"] in ("reference", "port") and j["e2e"]["h2d_bytes_per_step"] == 0
     assert j["config"]["workload"].startswith("SphereTracer.forward 1280x720") and "details" in j
+
+
+def test_camera_basis_equals_torch_recipe():
+    """geoutils.camera_basis (nglod_camera_basis, host-only C) == look_at's torch recipe on the host bit for bit
+    (reference geoutils.py:180-188), on random poses and the degenerate straight-down view."""
+    import torch.nn.functional as F
+    from nglod_b200.lib.geoutils import camera_basis
+
+    def recipe(f, t):
+        origin = torch.tensor(list(f), dtype=torch.float32)
+        view = F.normalize(torch.tensor(list(t), dtype=torch.float32) - origin, dim=0)
+        right = F.normalize(torch.linalg.cross(view, torch.tensor([0.0, 1.0, 0.0])), dim=0)
+        up = F.normalize(torch.linalg.cross(right, view), dim=0)
+        return origin.tolist(), view.tolist(), right.tolist(), up.tolist()
+
+    rng = np.random.default_rng(3)
+    poses = [((rng.standard_normal(3) * 3).tolist(), (rng.standard_normal(3) * 0.3).tolist()) for _ in range(3000)]
+    poses += [([-2.8, 2.8, -2.8], [0, 0, 0]), ([0.0, 3.0, 0.0], [0.0, 0.0, 0.0]), ([1.0, 1.0, 1.0], [1.0, 1.0, 1.0])]
+    for f, t in poses:
+        got, want = camera_basis(f, t), recipe(f, t)
+        for g, w in zip(got, want):
+            assert np.array_equal(np.array(g, dtype=np.float32), np.array(w, dtype=np.float32), equal_nan=True), (f, t, got, want)
