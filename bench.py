@@ -844,6 +844,52 @@ def run_extras(net, args, device, rank, world, flush, log):
                                                  "gradient all-reduce"}
     del nspc, opt, ro, rd
 
+    # ---- the streaming (HBM-bound) kernels around the hot path, each timed alone against the measured copy bandwidth:
+    #      algorithmic bytes (every operand read once, every result written once) / launch time, L2 flushed before each launch
+    from nglod_b200 import ops as _ops
+    from nglod_b200.lib.geoutils import camera_basis, procedural_matcap
+    hbm_peak, _, peak_src = load_peaks()
+    stream = {}
+
+    def stream_entry(name, nbytes, fn, what):
+        ms = timed(fn, iters=7, warm=3)
+        stream[name] = {"ms": ms, "bytes": int(nbytes), "achieved_GBs": nbytes / ms / 1e6, "peak_GBs": hbm_peak,
+                        "frac": nbytes / ms / 1e6 / hbm_peak, "what": what}
+    n_par = sum(p.numel() for p in net.parameters())
+    flat = [torch.zeros(n_par, device=device) for _ in range(4)]
+    flat[1].normal_()
+    stream_entry("nglod_adam_step", 28 * n_par, lambda: _ops.adam_step(flat[0], flat[1], flat[2], flat[3], 1),
+                 f"Adam over the {n_par} parameters of the model as one flat buffer: reads p, g, m, v, writes p, m, v")
+    del flat
+    o4, v4, r4, u4 = camera_basis(CAM_FROM, CAM_TO)
+    wx4 = torch.linspace(-1, 1, 3840, device=device) * (3840 / 2160)
+    wy4 = torch.linspace(1, -1, 2160, device=device)
+    rays4 = (torch.empty(3840 * 2160, 3, device=device), torch.empty(3840 * 2160, 3, device=device))
+    tan4 = np.float32(np.tan(np.radians(FOV / 2)))
+    stream_entry("nglod_generate_rays", 24 * 3840 * 2160,
+                 lambda: _ops.generate_rays(o4, v4, r4, u4, tan4, False, wx4, wy4, out=rays4), "3840x2160 rays: writes ray_o, ray_d")
+    nrm4 = torch.nn.functional.normalize(torch.randn(3840 * 2160, 3, device=device), dim=-1)
+    hit4 = torch.rand(3840 * 2160, device=device) < 0.5
+    mat = procedural_matcap(device=device).tex.float().contiguous()
+    stream_entry("nglod_shade_matcap", (12 + 12 + 1 + 12 + 6) * 3840 * 2160, lambda: _ops.shade_matcap(rays4[1], nrm4, hit4, mat),
+                 "3840x2160 pixels, half of them hits: reads view, normal, hit, writes rgb and the normals of the misses")
+    del rays4, nrm4, hit4
+    top = net.features[LOD].fm.data
+    view4 = net.net_view()
+    half_out = _ops.pack_grid_fp16(view4.summed[LOD])
+    stream_entry("nglod_pack_grid_fp16", top.numel() * 6, lambda: _ops.pack_grid_fp16(view4.summed[LOD], out=half_out),
+                 "the 65^3 x 32 prefix-summed grid to fp16 x-pair lines: reads fp32, writes fp16")
+    del half_out
+    sum_out = torch.empty_like(view4.summed[LOD])
+    coarse = net.features[LOD - 1].fm.data.numel()
+    stream_entry("nglod_build_summed_grid", top.numel() * 8 + coarse * 4,
+                 lambda: _ops.build_summed_grid(view4, LOD, out=sum_out),
+                 "level 4 of the prefix-summed grid = prolongation of level 3 + grid 4: reads both, writes 65^3 x 32 fp32")
+    del sum_out
+    out["streaming_kernels"] = dict(stream, note="HBM-bound kernels of the path (optimiser, ray generation, shading, derived-grid "
+                                                 "builds); peak = MEASURED_PEAKS.json hbm_gbs (" + peak_src + ")")
+    log("extras: streaming kernels " + ", ".join(f"{k} {v['frac']:.2f}" for k, v in stream.items()))
+
     # ---- the headless real-time loop (ray generation -> trace -> matcap shading, frame stays on the device)
     from nglod_b200.app import realtime
     rt = {}

@@ -742,20 +742,43 @@ m2s_scatter_kernel(const float* __restrict__ x, const long long n, int* __restri
     }
 }
 
-// Adam on a flat buffer (torch.optim.Adam semantics, no amsgrad / weight decay).
+// Adam on a flat buffer (torch.optim.Adam semantics, no amsgrad / weight decay).  HBM-bound: 28 bytes per parameter (reads
+// p, g, m, v, writes p, m, v), moved as 16-byte vectors, 4 independent loads in flight per operand and thread.
+struct AdamK { float b1, b2, eps, bc2_sqrt, step_size; };
+__device__ __forceinline__ void adam_one(float& p, const float g, float& m, float& v, const AdamK& k) {
+    const float mi = m + (g - m) * (1.f - k.b1);                       // lerp, as torch's single-tensor Adam
+    const float vi = v * k.b2 + g * g * (1.f - k.b2);
+    m = mi; v = vi;
+    const float denom = sqrtf(vi) / k.bc2_sqrt + k.eps;
+    p = p - k.step_size * (mi / denom);
+}
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
             const long long n, const float lr, const float b1, const float b2, const float eps,
             const float bc1, const float bc2_sqrt) {
+    const AdamK k = {b1, b2, eps, bc2_sqrt, lr / bc1};
     const long long stride = (long long)gridDim.x * blockDim.x;
-    const float step_size = lr / bc1;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const float gi = g[i];
-        const float mi = m[i] + (gi - m[i]) * (1.f - b1);           // lerp, as torch's single-tensor Adam
-        const float vi = v[i] * b2 + gi * gi * (1.f - b2);
-        m[i] = mi; v[i] = vi;
-        const float denom = sqrtf(vi) / bc2_sqrt + eps;
-        p[i] = p[i] - step_size * (mi / denom);
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // 16-byte vectors when all four buffers are 16-byte aligned (torch allocations and 4-element-aligned slices of them);
+    // otherwise, and for the last n % 4 elements, the scalar loop
+    const bool aligned = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                           reinterpret_cast<uintptr_t>(v)) & 15u) == 0;
+    const long long n4 = aligned ? n >> 2 : 0;
+    float4* p4 = reinterpret_cast<float4*>(p);
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    float4* m4 = reinterpret_cast<float4*>(m);
+    float4* v4 = reinterpret_cast<float4*>(v);
+    for (long long i = tid; i < n4; i += stride) {
+        float4 pp = p4[i], mm = m4[i], vv = v4[i];
+        const float4 gg = __ldcs(g4 + i);                            // gradients are dead after this step
+        adam_one(pp.x, gg.x, mm.x, vv.x, k); adam_one(pp.y, gg.y, mm.y, vv.y, k);
+        adam_one(pp.z, gg.z, mm.z, vv.z, k); adam_one(pp.w, gg.w, mm.w, vv.w, k);
+        p4[i] = pp; m4[i] = mm; v4[i] = vv;
+    }
+    for (long long i = (n4 << 2) + tid; i < n; i += stride) {
+        float pi = p[i], mi = m[i], vi = v[i];
+        adam_one(pi, g[i], mi, vi, k);
+        p[i] = pi; m[i] = mi; v[i] = vi;
     }
 }
 
@@ -958,7 +981,7 @@ extern "C" int nglod_adam_step(float* param, const float* grad, float* exp_avg, 
                                float lr, float beta1, float beta2, float eps, float bc1, float bc2, void* stream) {
     if (n < 0 || (n > 0 && (!param || !grad || !exp_avg || !exp_avg_sq))) return NGLOD_EINVAL;
     if (n == 0) return 0;
-    long long grid = (n + 255) / 256;
+    long long grid = (n / 4 + 255) / 256 + 1;
     const long long cap = (long long)nglod_sm_count() * 16;
     if (grid > cap) grid = cap;
     adam_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, (long long)n, lr,

@@ -10,6 +10,8 @@ format (one corner = one 128-byte line) and `sdf()` is ONE fused kernel
 (multi-LOD trilinear gather + running sum + decoder), with a recompute-based
 backward -- instead of the per-LOD grid_sample / cat / Linear launch chain.
 """
+import weakref
+
 import torch
 import torch.nn as nn
 from torch.autograd.function import once_differentiable
@@ -85,6 +87,10 @@ class _SdfFunction(torch.autograd.Function):
         if module.padded:
             grid_grads, dec_grads = module._unpad_grads(grid_grads, dec_grads)
         return (gx, None, None, *grid_grads, *dec_grads)
+
+
+# net -> {(inference, use_summed): (key, NetView)}: the borrowed views of net_view(), see there
+_VIEWS = weakref.WeakKeyDictionary()
 
 
 class OctreeSDF(BaseLOD):
@@ -184,7 +190,7 @@ class OctreeSDF(BaseLOD):
         if self._derived is not None:
             self._derived[0] = None
         self._padded_cache = None
-        self._views = {}
+        _VIEWS.pop(self, None)
 
     def load_state_dict(self, *args, **kwargs):
         out = super().load_state_dict(*args, **kwargs)
@@ -195,7 +201,7 @@ class OctreeSDF(BaseLOD):
         out = super()._apply(fn, *args, **kwargs)
         if getattr(self, "_derived", None) is not None:
             self._derived = None            # moved / cast: the derived buffers belong to the old placement
-        self._views = {}
+        _VIEWS.pop(self, None)
         return out
 
     def _derived_grids(self, want_half=False):
@@ -264,7 +270,7 @@ class OctreeSDF(BaseLOD):
                 ps.append(lin._parameters["bias"])
         key = (self.math_mode, self.grid_storage, self.sum_lods, self.pos_invariant,
                tuple([(p._version, p.data_ptr()) for p in ps]))
-        views = self.__dict__.setdefault("_views", {})
+        views = _VIEWS.setdefault(self, {})     # kept off the module: a view holds ctypes pointers (no deepcopy / pickle)
         hit = views.get((inference, use_summed))
         if hit is not None and hit[0] == key:
             return hit[1]

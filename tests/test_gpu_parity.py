@@ -837,6 +837,32 @@ def test_trace_lookat_host_chunked_and_packed_equal_forward(fit3):
         ops.sphere_trace_packed(view3, 2, o, d, torch.empty(W * H * 8 + 1, device=DEV)[1:].view(W * H, 8))   # misaligned
 
 
+def test_net_view_is_reused_and_never_stale():
+    """OctreeSDF.net_view() hands the same borrowed view back while no parameter was written or moved, a fresh one after an
+    optimiser step / mark_grids_dirty() / load_state_dict, and keeps the module deep-copyable and picklable."""
+    import copy, io
+    net, _ = rand5_model(DEV)
+    x = torch.rand(4096, 3, device=DEV) * 2 - 1
+    v0 = net.net_view()
+    d0 = net.sdf(x, lod=4)
+    assert net.net_view() is v0
+    with torch.no_grad():
+        net.features[4].fm.mul_(1.5)                       # version counter bumps
+    v1 = net.net_view()
+    assert v1 is not v0 and not torch.equal(net.sdf(x, lod=4), d0)
+    net.features[4].fm.data.mul_(1.0 / 1.5)                # behind torch's back: needs mark_grids_dirty()
+    net.mark_grids_dirty()
+    assert net.net_view() is not v1
+    assert (net.sdf(x, lod=4) - d0).abs().max().item() < 1e-6
+    twin = copy.deepcopy(net)
+    assert torch.equal(twin.sdf(x, lod=4), net.sdf(x, lod=4)) and twin.net_view() is not net.net_view()
+    buf = io.BytesIO()
+    torch.save(net, buf)
+    buf.seek(0)
+    back = torch.load(buf, weights_only=False)
+    assert torch.equal(back.sdf(x, lod=4), net.sdf(x, lod=4))
+
+
 def out_packed32(rb):
     n = rb.hit.shape[0]
     rec = torch.zeros(n, 8)
