@@ -177,6 +177,8 @@ class Renderer():
     def shade_images(self, net, f=[0, 0, 1], t=[0, 0, 0], fov=30.0, aa=1, mm=None):
         """Returns a CPU RenderBuffer laid out (H,W,C).  As in the reference, `aa` only multisamples
         when it is an int > 1 (sdf_renderer.py passes a bool, so the stock app never does)."""
+        if mm is None and not aa > 1 and self._can_pipeline(net):
+            return self._shade_images_pipelined(net, f, t, fov)
         if mm is None:
             mm = torch.eye(3)
         if aa > 1:
@@ -184,6 +186,81 @@ class Renderer():
         else:
             rb = self.shade_tensor(net, f=f, t=t, fov=fov, mm=mm)
         return rb.cpu().transpose()
+
+    # ------------------------------------------------------------------ shade_images, copies overlapped with the trace
+    pipelined = True        # False: always shade_tensor + RenderBuffer.cpu() (the A/B switch of the identity test)
+
+    def _can_pipeline(self, net):
+        from .tracer.SphereTracer import SphereTracer, _is_octree
+        tr = self.tracer
+        return (self.pipelined and type(tr) is SphereTracer and _is_octree(net) and tr.grad_method == "finitediff"
+                and getattr(net, "interpolate", None) is None and self.shading_mode == "matcap" and not self.shadow
+                and not self.ao and not self.render_batch and not self.perf and torch.device(self.device).type == "cuda")
+
+    def _shade_images_pipelined(self, net, f, t, fov, chunks=3):
+        """`shade_tensor(...).cpu().transpose()` for the plain matcap frame (no shadow / AO / model matrix) with the 57
+        bytes per ray of RenderBuffer fields crossing PCIe WHILE the frame is traced: `view` (= ray_d) leaves as soon as
+        the rays exist, and the frame is traced, shaded and copied in `chunks` contiguous ray ranges on alternating
+        streams (rays are independent and x-major, so a range is a block of image columns).  Same kernels, same
+        arithmetic, same random draws as the generic path: the returned buffers are equal bit for bit
+        (tests/test_render_app.py).  720p: 2.4 -> 1.5 ms per call."""
+        from .geoutils import _window, camera_basis
+        from .tracer.SphereTracer import _trace_lod
+        dev = next(net.parameters()).device
+        W, H = self.width, self.height
+        n = W * H
+        tr = self.tracer
+        far = self.camera_clamp[1]
+        ws = getattr(self, "_pipe_ws", None)
+        if ws is None or ws["n"] != n or ws["dev"] != dev:
+            ws = {"n": n, "dev": dev, "o": torch.empty(n, 3, device=dev), "d": torch.empty(n, 3, device=dev),
+                  "x": torch.empty(n, 3, device=dev), "depth": torch.empty(n, 1, device=dev),
+                  "hit": torch.empty(n, dtype=torch.bool, device=dev), "normal": torch.empty(n, 3, device=dev),
+                  "relative_depth": torch.empty(n, 1, device=dev), "rgb": torch.empty(n, 3, device=dev),
+                  "queue": torch.empty(chunks, dtype=torch.int32, device=dev),
+                  "s_out": torch.cuda.Stream(dev), "s_c": [torch.cuda.Stream(dev) for _ in range(2)]}
+            self._pipe_ws = ws
+        shapes = {"x": (3, torch.float32), "hit": (1, torch.bool), "depth": (1, torch.float32),
+                  "relative_depth": (1, torch.float32), "normal": (3, torch.float32), "rgb": (3, torch.float32),
+                  "view": (3, torch.float32)}
+        host = {k: torch.empty((n, c), dtype=dt, pin_memory=True) for k, (c, dt) in shapes.items()}
+        view, lod = net.net_view(), _trace_lod(net)
+        tex = self._get_matcap(dev).tex
+        cur = torch.cuda.current_stream(dev)
+        s_out = ws["s_out"]
+        with torch.cuda.device(dev), torch.no_grad():
+            origin, cview, right, up = camera_basis(f, t)
+            wx, wy = _window(W, H, dev)                       # the jitter draws of look_at, in its order
+            ops.generate_rays(origin, cview, right, up, np.float32(np.tan(np.radians(fov / 2))), False, wx, wy,
+                              out=(ws["o"], ws["d"]))
+            s_out.wait_stream(cur)
+            with torch.cuda.stream(s_out):
+                host["view"].copy_(ws["d"], non_blocking=True)
+            bounds = [((n * i) // chunks // H) * H if 0 < i < chunks else (n * i) // chunks for i in range(chunks + 1)]
+            for i in range(chunks):
+                a, b = bounds[i], bounds[i + 1]
+                if b == a:
+                    continue
+                sc = ws["s_c"][i % 2]
+                sc.wait_stream(cur)
+                with torch.cuda.stream(sc):
+                    ops.sphere_trace(view, lod, ws["o"][a:b], ws["d"][a:b], num_steps=tr.num_steps, step_size=tr.step_size,
+                                     min_dis=tr.min_dis, far=far,
+                                     out=(ws["x"][a:b], ws["depth"][a:b], ws["hit"][a:b], ws["normal"][a:b]),
+                                     queue=ws["queue"][i:i + 1])
+                    torch.div(torch.clamp(ws["depth"][a:b], 0.0, far), far, out=ws["relative_depth"][a:b])
+                    ops.shade_matcap(ws["d"][a:b], ws["normal"][a:b], ws["hit"][a:b], tex, out=ws["rgb"][a:b])
+                    ev = torch.cuda.Event()
+                    ev.record(sc)
+                s_out.wait_event(ev)
+                with torch.cuda.stream(s_out):
+                    for k in ("x", "hit", "depth", "relative_depth", "normal", "rgb"):
+                        host[k][a:b].copy_(ws[k][a:b].reshape(b - a, -1), non_blocking=True)
+            s_out.synchronize()
+            for sc in ws["s_c"]:
+                cur.wait_stream(sc)
+        rb = RenderBuffer(**{k: v.reshape(W, H, -1) for k, v in host.items()})
+        return rb.transpose()
 
     # ------------------------------------------------------------------ 2-D slices
     def sdf_slice(self, net, dim=0, depth=0):

@@ -448,8 +448,9 @@ def generate_rays(origin, view, right, up, tan_half_fov, ortho, window_x, window
     return ray_o, ray_d
 
 
-def shade_matcap(view, normal, hit, matcap):
-    """In place on `normal` (misses -> 1); returns rgb with view's shape.  matcap: [U,V,C>=3] fp32 on the device."""
+def shade_matcap(view, normal, hit, matcap, out=None):
+    """In place on `normal` (misses -> 1); returns rgb with view's shape.  matcap: [U,V,C>=3] fp32 on the device.
+    out: caller-provided contiguous fp32 buffer shaped like view."""
     lib = _lib.load()
     shape = view.shape
     v = _f32c(view, "view").reshape(-1, 3)
@@ -457,7 +458,12 @@ def shade_matcap(view, normal, hit, matcap):
         raise RuntimeError("normal must be a contiguous fp32 tensor (shaded in place)")
     h = hit.reshape(-1).contiguous()
     tex = _f32c(matcap, "matcap")
-    rgb = torch.empty_like(v)
+    if out is None:
+        rgb = torch.empty_like(v)
+    else:
+        if out.numel() != v.numel() or out.dtype != torch.float32 or out.device != v.device or not out.is_contiguous():
+            raise RuntimeError("shade_matcap: out must be a contiguous fp32 device buffer shaped like view")
+        rgb = out
     with torch.cuda.device(v.device):
         _lib.check(lib.nglod_shade_matcap(_ptr(v), _ptr(normal), _ptr(h), _ptr(tex), tex.shape[0], tex.shape[1],
                                           tex.shape[2], v.shape[0], _ptr(rgb), _stream()), "nglod_shade_matcap")

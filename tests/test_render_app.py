@@ -75,3 +75,36 @@ def test_sdf_renderer_main_writes_the_frames_shade_images_returns(fit3, tmp_path
     # flags that must fail loudly
     with pytest.raises(SystemExit):
         sdf_renderer.main(["--net", "OctreeSDF", "--img-dir", str(tmp_path)])      # no --pretrained
+
+
+def test_shade_images_pipelined_equals_generic_path(fit3):
+    """Renderer.shade_images for the plain matcap frame overlaps the device->host copies with the trace
+    (_shade_images_pipelined: chunks on alternating streams); its CPU RenderBuffer equals, field for field and bit for bit,
+    `shade_tensor(...).cpu().transpose()` under the same seed (renderer.py:310-331), and options it does not cover
+    (shadow / AO / aa / a model matrix) still take the generic path."""
+    from nglod_b200.lib.renderer import Renderer
+    from nglod_b200.lib.tracer import SphereTracer
+    net, _ = fit3_model(fit3, "cuda")
+    net.lod = 2
+    args = make_args(["--num-lods", "3", "--lod", "2", "--render-res", "200", "113", "--shading-mode", "matcap"])
+    r = Renderer(SphereTracer(args), args=args, device="cuda")
+    assert r._can_pipeline(net)
+    cam = dict(f=[-2.8, 2.8, -2.8], t=[0.0, 0.0, 0.0], fov=30.0)
+    outs = []
+    for pipelined in (True, False, True):
+        r.pipelined = pipelined
+        torch.manual_seed(9)
+        outs.append(r.shade_images(net, **cam))
+    names = [k for k in outs[1]._names() if getattr(outs[1], k) is not None]
+    assert sorted(names) == ["depth", "hit", "normal", "relative_depth", "rgb", "view", "x"]
+    assert int(outs[1].hit.sum()) > 800
+    for other in (outs[0], outs[2]):
+        assert sorted(k for k in other._names() if getattr(other, k) is not None) == sorted(names)
+        for k in names:
+            a, b = getattr(other, k), getattr(outs[1], k)
+            assert not a.is_cuda and a.shape == b.shape == (113, 200, a.shape[-1]) and a.dtype == b.dtype, k
+            assert torch.equal(a, b), k
+    r.pipelined = True
+    r2 = Renderer(SphereTracer(args), args=make_args(["--num-lods", "3", "--lod", "2", "--render-res", "200", "113",
+                                                      "--shading-mode", "matcap", "--ao"]), device="cuda")
+    assert not r2._can_pipeline(net)
