@@ -288,3 +288,33 @@ def test_camera_basis_equals_torch_recipe():
         got, want = camera_basis(f, t), recipe(f, t)
         for g, w in zip(got, want):
             assert np.array_equal(np.array(g, dtype=np.float32), np.array(w, dtype=np.float32), equal_nan=True), (f, t, got, want)
+
+
+def test_header_is_plain_c_and_a_c_client_links(tmp_path):
+    """include/nglod_b200.h compiles as C99 (what a cgo / JNI / ctypes-less client sees), a C program links against
+    libnglod_b200.so and calls the entry points that do no device work, and the struct sizes the C compiler sees are the
+    ones the ctypes mirror in nglod_b200/_lib.py declares (a layout drift would make the kernels read wrong pointers)."""
+    import subprocess
+    from nglod_b200 import _lib
+    from nglod_b200.build import build_library
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = build_library()
+    exe = tmp_path / "client"
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(root, "include"),
+           os.path.join(root, "tests", "c_client", "client.c"), "-o", str(exe), so, "-lm", f"-Wl,-rpath,{os.path.dirname(so)}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    m = re.search(r"ok abi (\d+) sizeof\(nglod_net_t\) (\d+) sizeof\(nglod_net_grad_t\) (\d+) sizeof\(nglod_trace_opts_t\) (\d+) sizeof\(nglod_sparse_net_t\) (\d+)", r.stdout)
+    assert m, r.stdout
+    assert int(m.group(1)) == _lib.EXPECTED_ABI
+    assert int(m.group(2)) == ctypes.sizeof(_lib.NetStruct)
+    assert int(m.group(3)) == ctypes.sizeof(_lib.NetGradStruct)
+    assert int(m.group(4)) == ctypes.sizeof(_lib.TraceOpts)
+    assert int(m.group(5)) == ctypes.sizeof(_lib.SparseNetStruct)
+    offs = [int(v) for v in re.search(r"offsets ([\d ]+)", r.stdout).group(1).split()]
+    assert offs == [_lib.NetStruct.grid_res.offset, _lib.NetStruct.grids.offset, _lib.NetStruct.w0.offset,
+                    _lib.NetStruct.summed_fp16.offset, _lib.NetGradStruct.summed.offset,
+                    _lib.NetGradStruct.scatter_scratch_floats.offset, _lib.TraceOpts.step_size.offset,
+                    _lib.TraceOpts.normal_h.offset]
