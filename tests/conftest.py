@@ -37,3 +37,17 @@ def fit3():
 @pytest.fixture(scope="session")
 def fit5():
     return dict(np.load(os.path.join(GOLDEN, "fit5.npz")))
+
+
+@pytest.fixture(autouse=True)
+def _gpu_state_is_clean(request):
+    """Every GPU test starts and ends on torch's default stream with no pending CUDA error: a test (or a library path) that
+    leaks a stream context or a sticky error would otherwise fail a LATER test, far from its cause."""
+    import torch
+    if "gpu" not in request.keywords or not torch.cuda.is_available():
+        yield
+        return
+    assert torch.cuda.current_stream() == torch.cuda.default_stream(), "a previous test left a side stream current"
+    yield
+    torch.cuda.synchronize()
+    assert torch.cuda.current_stream() == torch.cuda.default_stream(), f"{request.node.name} left a side stream current"

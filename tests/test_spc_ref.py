@@ -64,8 +64,29 @@ def _rays(w, h, seed, extra=501):
 
 
 def _ref_raytrace(ref_spc, spc, ro, rd, target):
-    pyr = spc.pyramid.to(torch.int32).contiguous().cpu()
-    return ref_spc.spc_raytrace(spc.octree, spc.points.contiguous(), pyr, ro.contiguous(), rd.contiguous(), int(target))
+    """The reference's own spc_raytrace.  When targetLevel == the octree's level, its d_Decide reads `D[offset + pidx]` with
+    offset = PyramidSum[Level] = the SIZE of D (spc_raytrace_cuda_kernel.cu:126: the leaf level has no child-mask bytes; the
+    value is unused there, `info = notDone ? dd : 1`) -- up to 4 bytes x #leaf voxels past the end of a buffer the reference
+    allocates itself, which faults or not depending on where torch's allocator happened to put it (seen as an illegal memory
+    access late in the full suite, never in isolation).  The harness therefore hands the reference the same octree extended
+    by ONE level in which every leaf has a single child: the read stays inside D, and nuggets at levels <= Level do not
+    depend on anything below them."""
+    octree, points, pyramid = spc.octree, spc.points, spc.pyramid.to(torch.int32)
+    if int(target) == spc.level:
+        L = spc.level
+        leaf = points[int(pyramid[1, L]):int(pyramid[1, L + 1])]
+        child = leaf.clone()
+        child[:, :3] *= 2                                                   # child 0 of every leaf voxel
+        octree = torch.cat([octree, torch.ones(leaf.shape[0], dtype=torch.uint8, device=octree.device)])
+        points = torch.cat([points, child])
+        ext = torch.zeros(2, L + 3, dtype=torch.int32)
+        ext[0, :L + 1] = pyramid[0, :L + 1]
+        ext[0, L + 1] = leaf.shape[0]
+        ext[1, :L + 2] = pyramid[1, :L + 2]
+        ext[1, L + 2] = pyramid[1, L + 1] + leaf.shape[0]
+        pyramid = ext
+    pyr = pyramid.contiguous().cpu()
+    return ref_spc.spc_raytrace(octree.contiguous(), points.contiguous(), pyr, ro.contiguous(), rd.contiguous(), int(target))
 
 
 # ---------------------------------------------------------------------------------------------------- a17: traversal
