@@ -98,9 +98,9 @@ class SphereTracer(BaseTracer):
             with_x = "x" in fields
             out = {} if out is None else out
             if "packed" not in out:
-                out["packed"] = torch.empty(n, 8 if with_x else 4).pin_memory()
+                out["packed"] = torch.empty(n, 8 if with_x else 4, pin_memory=True)      # torch's caching host allocator
             if not with_x and "hit" not in out:
-                out["hit"] = torch.empty(n, dtype=torch.bool).pin_memory()
+                out["hit"] = torch.empty(n, dtype=torch.bool, pin_memory=True)
             with torch.cuda.device(dev):
                 wx, wy = _window(width, height, dev) if window is None else window
                 ops.sphere_trace_camera(net.net_view(), _trace_lod(net), origin, view, right,
@@ -141,7 +141,7 @@ class SphereTracer(BaseTracer):
             if k not in shapes:
                 raise ValueError(f"unknown RenderBuffer field {k!r}")
         if out is None:
-            out = {k: torch.empty(shapes[k][0], dtype=shapes[k][1]).pin_memory() for k in fields}
+            out = {k: torch.empty(shapes[k][0], dtype=shapes[k][1], pin_memory=True) for k in fields}
         ws = getattr(self, "_host_ws", None)
         if ws is None or ws["n"] != n or ws["dev"] != dev:
             ws = {"n": n, "dev": dev,
