@@ -318,3 +318,33 @@ def test_header_is_plain_c_and_a_c_client_links(tmp_path):
                     _lib.NetStruct.summed_fp16.offset, _lib.NetGradStruct.summed.offset,
                     _lib.NetGradStruct.scatter_scratch_floats.offset, _lib.TraceOpts.step_size.offset,
                     _lib.TraceOpts.normal_h.offset]
+
+
+def test_committed_bench_record_has_the_contract_keys():
+    """The last bench line committed under profiles/ carries every key of the measurement contract (driver-parsed fields, the
+    roofline / cpu_baseline / e2e objects, clocks, launches), with the relations between them that the contract states."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = json.loads(open(os.path.join(root, "profiles", "bench_r2_n1.json")).read().strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["higher_is_better"] is True and d["vs_baseline"] is None and d["data"] == "synthetic"
+    assert "workload" in d["config"] and "l2" in d["config"] and "model" not in d["config"]
+    assert d["warmup"] >= 3 and d["gpu_launches"] >= d["steps"]
+    rays = d["config"]["rays_per_gpu_step"]
+    assert abs(d["value"] - rays / (d["ms_per_step"] / 1e3)) / d["value"] < 1e-6          # value = rays / device time per step
+    r = d["roofline"]
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in r, k
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and 0.0 < r["frac"] < 1.2
+    c = d["cpu_baseline"]
+    for k in ("value", "unit", "cores", "kind", "sample"):
+        assert k in c, k
+    assert c["kind"] in ("reference", "port") and c["unit"] == d["unit"]
+    e = d["e2e"]
+    for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+        assert k in e, k
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] >= rays * 17 and e["value"] < d["value"]
+    assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(d["clocks"])
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
