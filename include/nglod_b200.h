@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define NGLOD_ABI_VERSION 11
+#define NGLOD_ABI_VERSION 12
 #define NGLOD_MAX_LODS 8
 
 /* nglod_net_t.math_mode */
@@ -235,6 +235,11 @@ typedef struct nglod_trace_opts {
     double min_dis;          /* options.py:221  default 3e-4                    */
     double far;              /* camera_clamp[1], options.py:209 default 10      */
     double normal_h;         /* diffutils.py:62  1/(64*3)                       */
+    /* 0: the persistent dense tracer takes every SM (one CTA each: a CTA holds the SM's whole register file and shared
+     * memory, so no kernel of another stream runs beside it).  > 0: at most this many CTAs -- leaves SMs to concurrent
+     * work, e.g. the shading of the previous ray range (Renderer.shade_images).  Results do not depend on it. */
+    int32_t max_ctas;
+    int32_t reserved_;       /* 0 */
 } nglod_trace_opts_t;
 
 int nglod_sphere_trace(const nglod_net_t* net, int32_t lod,

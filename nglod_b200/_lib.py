@@ -10,7 +10,7 @@ import ctypes
 import os
 
 MAX_LODS = 8
-EXPECTED_ABI = 11        # include/nglod_b200.h NGLOD_ABI_VERSION the ctypes structs below were written against
+EXPECTED_ABI = 12        # include/nglod_b200.h NGLOD_ABI_VERSION the ctypes structs below were written against
 LOSS_PER_LOD = 0x80000000
 MATH_TC3XTF32 = 0
 MATH_FP32 = 1
@@ -91,6 +91,8 @@ class TraceOpts(ctypes.Structure):
         ("min_dis", ctypes.c_double),
         ("far", ctypes.c_double),
         ("normal_h", ctypes.c_double),
+        ("max_ctas", c_int32),
+        ("reserved_", c_int32),
     ]
 
 

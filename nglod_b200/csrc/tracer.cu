@@ -293,7 +293,7 @@ static int trace_launch(const nglod_net_t* net, int32_t lod, const float* ray_o,
     if (!opts || n < 0 || n > 2000000000ll) return NGLOD_EINVAL;
     if (n == 0) return 0;
     if (!ray_o || !ray_d || !x || !queue) return NGLOD_EINVAL;
-    if (opts->num_steps < 0) return NGLOD_EINVAL;
+    if (opts->num_steps < 0 || opts->max_ctas < 0) return NGLOD_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     NGLOD_CUDA_TRY(cudaMemsetAsync(queue, 0, sizeof(int32_t), st));
     TraceParams tp;
@@ -315,6 +315,7 @@ static int trace_launch(const nglod_net_t* net, int32_t lod, const float* ray_o,
         long long grid = nglod_sm_count();
         const long long want = (n + threads - 1) / threads;
         if (want < grid) grid = want;
+        if (opts->max_ctas > 0 && opts->max_ctas < grid) grid = opts->max_ctas;
         kern<<<(int)grid, threads, smem, st>>>(nd, ray_o, ray_d, (long long)n, tp, x, depth, hit, normal, queue, stats);
         return (int)cudaGetLastError();
     }
@@ -326,6 +327,7 @@ static int trace_launch(const nglod_net_t* net, int32_t lod, const float* ray_o,
     long long grid = (long long)nglod_sm_count() * per_sm;
     const long long want = (n + SDF_THREADS - 1) / SDF_THREADS;
     if (want < grid) grid = want;
+    if (opts->max_ctas > 0 && (long long)opts->max_ctas * per_sm < grid) grid = (long long)opts->max_ctas * per_sm;
     kern<<<(int)grid, SDF_THREADS, SDF_SMEM_BYTES, st>>>(nd, ray_o, ray_d, (long long)n, tp, x, depth, hit, normal,
                                                          queue, stats
                                                          );

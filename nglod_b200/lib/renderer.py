@@ -189,6 +189,7 @@ class Renderer():
 
     # ------------------------------------------------------------------ shade_images, copies overlapped with the trace
     pipelined = True        # False: always shade_tensor + RenderBuffer.cpu() (the A/B switch of the identity test)
+    pipe_reserve_sms = 8    # SMs the 2nd, 3rd, ... range's tracer launch leaves to the previous range's shading kernels
 
     def _can_pipeline(self, net):
         from .tracer.SphereTracer import SphereTracer, _is_octree
@@ -217,8 +218,10 @@ class Renderer():
                   "x": torch.empty(n, 3, device=dev), "depth": torch.empty(n, 1, device=dev),
                   "hit": torch.empty(n, dtype=torch.bool, device=dev), "normal": torch.empty(n, 3, device=dev),
                   "relative_depth": torch.empty(n, 1, device=dev), "rgb": torch.empty(n, 3, device=dev),
-                  "queue": torch.empty(chunks, dtype=torch.int32, device=dev),
-                  "s_out": torch.cuda.Stream(dev), "s_c": [torch.cuda.Stream(dev) for _ in range(2)]}
+                  "queue": torch.empty(16, dtype=torch.int32, device=dev),
+                  "s_out": torch.cuda.Stream(dev), "s_c": [torch.cuda.Stream(dev) for _ in range(2)],
+                  "max_ctas": max(1, torch.cuda.get_device_properties(dev).multi_processor_count - self.pipe_reserve_sms)
+                  if self.pipe_reserve_sms > 0 else 0}
             self._pipe_ws = ws
         shapes = {"x": (3, torch.float32), "hit": (1, torch.bool), "depth": (1, torch.float32),
                   "relative_depth": (1, torch.float32), "normal": (3, torch.float32), "rgb": (3, torch.float32),
@@ -236,7 +239,11 @@ class Renderer():
             s_out.wait_stream(cur)
             with torch.cuda.stream(s_out):
                 host["view"].copy_(ws["d"], non_blocking=True)
-            bounds = [((n * i) // chunks // H) * H if 0 < i < chunks else (n * i) // chunks for i in range(chunks + 1)]
+            if isinstance(chunks, (tuple, list)):           # cumulative split points in (0, 1)
+                bounds = [0] + [(int(n * f_) // H) * H for f_ in chunks] + [n]
+                chunks = len(bounds) - 1
+            else:
+                bounds = [((n * i) // chunks // H) * H if 0 < i < chunks else (n * i) // chunks for i in range(chunks + 1)]
             for i in range(chunks):
                 a, b = bounds[i], bounds[i + 1]
                 if b == a:
@@ -244,10 +251,12 @@ class Renderer():
                 sc = ws["s_c"][i % 2]
                 sc.wait_stream(cur)
                 with torch.cuda.stream(sc):
+                    # ranges after the first leave a few SMs free: the previous range's shading kernels run beside this
+                    # trace instead of waiting for it (a tracer CTA holds its SM's whole register file)
                     ops.sphere_trace(view, lod, ws["o"][a:b], ws["d"][a:b], num_steps=tr.num_steps, step_size=tr.step_size,
                                      min_dis=tr.min_dis, far=far,
                                      out=(ws["x"][a:b], ws["depth"][a:b], ws["hit"][a:b], ws["normal"][a:b]),
-                                     queue=ws["queue"][i:i + 1])
+                                     queue=ws["queue"][i:i + 1], max_ctas=ws["max_ctas"] if i > 0 else 0)
                     torch.div(torch.clamp(ws["depth"][a:b], 0.0, far), far, out=ws["relative_depth"][a:b])
                     ops.shade_matcap(ws["d"][a:b], ws["normal"][a:b], ws["hit"][a:b], tex, out=ws["rgb"][a:b])
                     ev = torch.cuda.Event()

@@ -249,9 +249,10 @@ def sdf_finitediff(view, lod, x, h=1.0 / (64.0 * 3.0)):
 
 # --------------------------------------------------------------------------- tracer
 def sphere_trace(view, lod, ray_o, ray_d, num_steps=256, step_size=1.0, min_dis=0.0003, far=10.0,
-                 normal_h=1.0 / (64.0 * 3.0), compute_normals=True, stats=None, out=None, queue=None):
+                 normal_h=1.0 / (64.0 * 3.0), compute_normals=True, stats=None, out=None, queue=None, max_ctas=0):
     """One persistent kernel: returns x [N,3], depth [N,1], hit [N] bool, normal [N,3].
-    out=(x, depth, hit, normal): caller-provided contiguous device buffers (e.g. slices of a frame buffer)."""
+    out=(x, depth, hit, normal): caller-provided contiguous device buffers (e.g. slices of a frame buffer).
+    max_ctas > 0: at most that many CTAs (one per SM) -- leaves SMs to kernels of other streams; same results."""
     lib = _lib.load()
     ray_o = _f32c(ray_o, "ray_o")
     ray_d = _f32c(ray_d, "ray_d")
@@ -271,7 +272,7 @@ def sphere_trace(view, lod, ray_o, ray_d, num_steps=256, step_size=1.0, min_dis=
     if queue is None:
         queue = torch.empty(1, device=dev, dtype=torch.int32)
     opts = TraceOpts(int(num_steps), 1 if compute_normals else 0, float(step_size), float(min_dis), float(far),
-                     float(normal_h))
+                     float(normal_h), int(max_ctas), 0)
     with torch.cuda.device(dev):
         _lib.check(lib.nglod_sphere_trace(ctypes.byref(view.struct), lod, _ptr(ray_o), _ptr(ray_d), n,
                                           ctypes.byref(opts), _ptr(x), _ptr(depth), _ptr(hit), _ptr(normal),

@@ -19,7 +19,8 @@ shapes = {"x": (3, torch.float32), "hit": (1, torch.bool), "depth": (1, torch.fl
           "normal": (3, torch.float32), "rgb": (3, torch.float32), "view": (3, torch.float32)}
 host = {k: torch.empty((n, c), dtype=dt, pin_memory=True) for k, (c, dt) in shapes.items()}
 cur = torch.cuda.current_stream(dev); s_out = ws["s_out"]
-def frame(chunks, shade_on, copy_on):
+queue = torch.empty(16, dtype=torch.int32, device=dev)
+def frame(chunks, shade_on, copy_on, reserve=0):
     marks = []
     def mark(name, stream):
         e = torch.cuda.Event(enable_timing=True); e.record(stream); marks.append((name, e))
@@ -39,7 +40,8 @@ def frame(chunks, shade_on, copy_on):
         sc = ws["s_c"][i % 2]; sc.wait_stream(cur)
         with torch.cuda.stream(sc):
             ops.sphere_trace(view, lod, ws["o"][a:b], ws["d"][a:b], num_steps=tr.num_steps, step_size=tr.step_size, min_dis=tr.min_dis, far=far,
-                             out=(ws["x"][a:b], ws["depth"][a:b], ws["hit"][a:b], ws["normal"][a:b]), queue=ws["queue"][i:i + 1])
+                             out=(ws["x"][a:b], ws["depth"][a:b], ws["hit"][a:b], ws["normal"][a:b]), queue=queue[i:i + 1],
+                             max_ctas=(148 - reserve) if (reserve and i > 0) else 0)
             mark(f"trace {i}", sc)
             if shade_on:
                 torch.div(torch.clamp(ws["depth"][a:b], 0.0, far), far, out=ws["relative_depth"][a:b])
@@ -54,7 +56,7 @@ def frame(chunks, shade_on, copy_on):
                 mark(f"copies {i}", s_out)
     torch.cuda.synchronize()
     return [(nm, marks[0][1].elapsed_time(e)) for nm, e in marks[1:]]
-for chunks, shade_on, copy_on in ((3, True, True), (3, True, False), (3, False, False), (1, True, True)):
-    for _ in range(3): frame(chunks, shade_on, copy_on)
-    tl = frame(chunks, shade_on, copy_on)
-    print(f"chunks {chunks} shade {shade_on} copies {copy_on}: " + ", ".join(f"{nm} {t:.3f}" for nm, t in tl))
+for chunks, shade_on, copy_on, reserve in ((3, True, True, 0), (3, True, True, 8), (3, True, False, 8), (4, True, True, 8)):
+    for _ in range(3): frame(chunks, shade_on, copy_on, reserve)
+    tl = frame(chunks, shade_on, copy_on, reserve)
+    print(f"chunks {chunks} shade {shade_on} copies {copy_on} reserve {reserve}: " + ", ".join(f"{nm} {t:.3f}" for nm, t in tl))

@@ -21,3 +21,7 @@ r.pipelined = True
 for c in (1, 2, 3, 4, 6, 8):
     r._pipe_ws = None
     print("pipelined, %d chunks: %.3f ms" % (c, wall(lambda: r._shade_images_pipelined(net, bench.CAM_FROM, bench.CAM_TO, bench.FOV, chunks=c))))
+r.pipe_reserve_sms = 8
+for fr in ((0.4, 0.8), (0.45, 0.85), (0.5, 0.9), (0.35, 0.65, 0.9), (0.4, 0.7, 0.92), (0.3, 0.6, 0.85, 0.95), (0.5, 0.8, 0.95), (0.6, 0.9)):
+    r._pipe_ws = None
+    print("reserve 8, split %s: %.3f ms" % (fr, wall(lambda: r._shade_images_pipelined(net, bench.CAM_FROM, bench.CAM_TO, bench.FOV, chunks=fr))))

@@ -825,6 +825,10 @@ def test_trace_lookat_host_chunked_and_packed_equal_forward(fit3):
         assert p16.x is None and p16.depth.data_ptr() == out16["packed"].data_ptr() and out16["packed"].is_pinned()
         for k in ("depth", "hit", "normal"):
             assert torch.equal(getattr(p16, k), getattr(ref, k).cpu()), k
+    # a capped grid (nglod_trace_opts_t.max_ctas: SMs left to other streams) traces the same frame
+    capped = ops.sphere_trace(net3.net_view(), 2, o, d, max_ctas=5)
+    for got, k in zip(capped, ("x", "depth", "hit", "normal")):
+        assert torch.equal(got, getattr(ref, k)), k
     # device-resident packed buffers give the same records; argument checks of the C entry point
     view3 = net3.net_view()
     rec = ops.sphere_trace_packed(view3, 2, o, d, torch.empty(W * H, 8, device=DEV))

@@ -26,7 +26,7 @@ def test_cabi_library_exports_every_declared_symbol():
     # struct layouts agree with the header (sizes computed from the declarations)
     assert ctypes.sizeof(_lib.NetStruct) == 6 * 4 + 8 * 4 + 7 * 8 * 8
     assert ctypes.sizeof(_lib.NetGradStruct) == 6 * 8 * 8 + 8 + 8
-    assert ctypes.sizeof(_lib.TraceOpts) == 8 + 4 * 8
+    assert ctypes.sizeof(_lib.TraceOpts) == 8 + 4 * 8 + 8          # + max_ctas, reserved_ (ABI 12)
     # argument validation happens before any CUDA call, so it is testable without a device
     assert lib.nglod_aabb(None, None, -1, None, None, None, None) == _lib.EINVAL
     assert lib.nglod_sdf_forward(None, 0, None, 0, None, None) == _lib.EINVAL
