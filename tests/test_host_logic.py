@@ -348,3 +348,15 @@ def test_committed_bench_record_has_the_contract_keys():
     assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] >= rays * 17 and e["value"] < d["value"]
     assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(d["clocks"])
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+def test_window_cache_draws_and_rounds_like_normalized_grid():
+    """geoutils._window (cached un-jittered coordinates + one torch.rand per axis) == the window vectors of normalized_grid
+    (reference geoutils.py:140-154) under the same seed, bit for bit, on the first (cache miss) and on later (cache hit) calls."""
+    from nglod_b200.lib.geoutils import _window, normalized_grid
+    for w, h in ((160, 90), (33, 57), (160, 90)):
+        torch.manual_seed(5)
+        grid = normalized_grid(w, h, device="cpu")
+        torch.manual_seed(5)
+        wx, wy = _window(w, h, "cpu")
+        assert torch.equal(wx, grid[:, 0, 0]) and torch.equal(wy, grid[0, :, 1])
