@@ -268,6 +268,19 @@ def test_bench_reference_arm_prints_one_json_line():
     assert j["config"]["workload"].startswith("SphereTracer.forward 1280x720") and "details" in j
 
 
+def test_bench_reference_arm_other_ranks_exit_without_work():
+    """Under torchrun (N > 1) rank 0 alone runs and prints the reference arm; every other rank exits 0 with nothing on
+    stdout and without joining a process group."""
+    import subprocess
+    import sys
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29999",
+               CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.strip() == ""
+
+
 def test_camera_basis_equals_torch_recipe():
     """geoutils.camera_basis (nglod_camera_basis, host-only C) == look_at's torch recipe on the host bit for bit
     (reference geoutils.py:180-188), on random poses and the degenerate straight-down view."""
