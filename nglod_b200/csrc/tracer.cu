@@ -41,6 +41,13 @@ struct TraceParams {
 #ifndef NGLOD_TRACE_GROUPS_SINGLE
 #define NGLOD_TRACE_GROUPS_SINGLE 4
 #endif
+// how many times a warp goes back to the queue in one round while it still has empty lanes (rays that miss the box retire on
+// the spot and free their lane again).  Measured on the bench frame (profiles/exp_attempts.sh), device frame / host-to-host
+// frame in ms: 1: 0.864 / 1.048, 2: 0.877 / 1.074, 4: 0.872 / 1.079, 8: 0.886 / 1.096, 32: 0.898 / 1.114 -- draining the
+// box-missing rays faster only lengthens the rounds of the rays that march (and bunches their stores).
+#ifndef NGLOD_TRACE_REFILL_ATTEMPTS
+#define NGLOD_TRACE_REFILL_ATTEMPTS 1
+#endif
 constexpr int trace_groups(int mode) { return mode == TC_MULTI ? NGLOD_TRACE_GROUPS : NGLOD_TRACE_GROUPS_SINGLE; }
 constexpr int trace_tc_threads(int mode) { return trace_groups(mode) * TCG_THREADS; }
 constexpr int trace_tc_smem(int mode) { return TC_SMEM_BYTES_W(trace_groups(mode), tc_mode_scratch(mode)); }
@@ -177,7 +184,7 @@ sphere_trace_kernel(const NetDev net, const float* __restrict__ ray_o, const flo
     // refill empty slots from the global queue (ballot + popc ranks; rays that miss the box retire on the spot)
     auto refill = [&]() {
 #pragma unroll 1
-        for (int attempt = 0; attempt < 4 && !exhausted; ++attempt) {
+        for (int attempt = 0; attempt < NGLOD_TRACE_REFILL_ATTEMPTS && !exhausted; ++attempt) {
             const unsigned free_mask = __ballot_sync(0xffffffffu, phase == PH_EMPTY);
             if (!free_mask) break;
             const int nfree = __popc(free_mask);
