@@ -11,6 +11,13 @@
 #include "sdf_tc.cuh"
 #include "sparse_core.cuh"
 
+// re-fill attempts per round of the in-voxel tracer (see NGLOD_TRACE_REFILL_ATTEMPTS in tracer.cu).  1080p frames over the
+// level-7 torus octree, lods 1-5 (profiles/exp_attempts_spc.sh): 1 attempt 1.90 / 2.28 / 2.28 / 2.76 / 3.64 ms, 4 attempts
+// 2.00 / 2.40 / 2.39 / 2.84 / 3.69 ms
+#ifndef NGLOD_SPC_REFILL_ATTEMPTS
+#define NGLOD_SPC_REFILL_ATTEMPTS 1
+#endif
+
 namespace {
 
 // FP32 path: gather into the warp's [32][36] tile (see sdf_core.cuh::warp_gather_tile), then lane_decoder.
@@ -217,7 +224,7 @@ spc_sphere_trace_kernel(const SparseDev sn, const int2* __restrict__ nuggets, co
 
     for (;;) {
 #pragma unroll 1
-        for (int attempt = 0; attempt < 4 && !exhausted; ++attempt) {
+        for (int attempt = 0; attempt < NGLOD_SPC_REFILL_ATTEMPTS && !exhausted; ++attempt) {
             const unsigned free_mask = __ballot_sync(0xffffffffu, phase == SP_EMPTY);
             if (!free_mask) break;
             const int nfree = __popc(free_mask);
