@@ -17,6 +17,11 @@
 #ifndef NGLOD_SPC_REFILL_ATTEMPTS
 #define NGLOD_SPC_REFILL_ATTEMPTS 1
 #endif
+// empty lanes a warp waits for before it goes back to the queue (NGLOD_TRACE_REFILL_MIN in tracer.cu).  Same frames
+// (profiles/final_check.sh): 1: 1.90 / 2.28 / 2.28 / 2.76 / 3.64 ms, 8: 1.84 / 2.21 / 2.25 / 2.73 / 3.63 ms
+#ifndef NGLOD_SPC_REFILL_MIN
+#define NGLOD_SPC_REFILL_MIN 8
+#endif
 
 namespace {
 
@@ -228,6 +233,9 @@ spc_sphere_trace_kernel(const SparseDev sn, const int2* __restrict__ nuggets, co
             const unsigned free_mask = __ballot_sync(0xffffffffu, phase == SP_EMPTY);
             if (!free_mask) break;
             const int nfree = __popc(free_mask);
+#if NGLOD_SPC_REFILL_MIN > 1
+            if (nfree < NGLOD_SPC_REFILL_MIN) break;
+#endif
             int base = 0;
             if (lane == 0) base = atomicAdd(queue, nfree);
             base = __shfl_sync(0xffffffffu, base, 0);

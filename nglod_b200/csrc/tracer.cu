@@ -48,6 +48,13 @@ struct TraceParams {
 #ifndef NGLOD_TRACE_REFILL_ATTEMPTS
 #define NGLOD_TRACE_REFILL_ATTEMPTS 1
 #endif
+// a warp goes back to the queue only once it has this many empty lanes: the atomic's round trip sits on the round's critical
+// path, so it is paid per batch of rays rather than per retired ray.  Same frame (profiles/exp_refill_min.sh), device / host-to-
+// host (L2 flushed) in ms: 1: 0.864 / 1.060, 4: 0.854 / 1.038, 8: 0.838 / 1.035, 16: 0.858 / 1.040.  Results do not depend on it
+// (a ray's march never looks at its lane or its neighbours).
+#ifndef NGLOD_TRACE_REFILL_MIN
+#define NGLOD_TRACE_REFILL_MIN 8
+#endif
 constexpr int trace_groups(int mode) { return mode == TC_MULTI ? NGLOD_TRACE_GROUPS : NGLOD_TRACE_GROUPS_SINGLE; }
 constexpr int trace_tc_threads(int mode) { return trace_groups(mode) * TCG_THREADS; }
 constexpr int trace_tc_smem(int mode) { return TC_SMEM_BYTES_W(trace_groups(mode), tc_mode_scratch(mode)); }
@@ -188,6 +195,9 @@ sphere_trace_kernel(const NetDev net, const float* __restrict__ ray_o, const flo
             const unsigned free_mask = __ballot_sync(0xffffffffu, phase == PH_EMPTY);
             if (!free_mask) break;
             const int nfree = __popc(free_mask);
+#if NGLOD_TRACE_REFILL_MIN > 1
+            if (nfree < NGLOD_TRACE_REFILL_MIN) break;     // the atomic's round trip is on the round's critical path: batch it
+#endif
             int base = 0;
             if (lane == 0) base = atomicAdd(queue, nfree);
             base = __shfl_sync(0xffffffffu, base, 0);
