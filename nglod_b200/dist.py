@@ -4,8 +4,10 @@ The hot path shards trivially: every query, ray and train
 40 MB model is replicated.  So:
   * queries / rays  -> contiguous ranges per rank, NO data-path collective; an optional final gather of results;
     rays are x-major (ray = ix*H + iy), so a contiguous ray range is a vertical strip of the image;
-  * training        -> each rank takes its slice of the point batch, runs the fused step with the loss scaled by
-    the GLOBAL batch, then ONE all-reduce(sum) over the flat fp32 gradient buffer (40.6 MB), replicated Adam.
+  * training        -> each rank takes its slice of the point batch and runs the fused step with the loss scaled by
+    the GLOBAL batch; then (lib/trainer.py: FusedTrainer) reduce-scatter of the flat fp32 gradient buffer (40.6 MB),
+    Adam on this rank's 1/N of the parameters, all-gather of the parameters -- or, `sharded=False`, ONE all-reduce(sum)
+    of the flat gradient and replicated Adam.
 The reference has no distributed code at all, so nothing here replaces reference lines.
 """
 import os
