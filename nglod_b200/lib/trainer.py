@@ -213,7 +213,8 @@ class Trainer(object):
     What differs is where things live: the dataset stays on the device (no DataLoader / pinned-memory hop per
     512-point batch), a step is the fused forward+loss+backward kernels + one Adam launch over flat buffers, losses
     are accumulated on the device and read once per epoch (the reference calls `.item()` twice per iteration), and
-    with several ranks each takes a slice of every batch and the flat gradient is all-reduced once per step.
+    with several ranks each takes a slice of every batch and the flat gradient is exchanged once per step (reduce-scatter +
+    Adam on 1/N of the parameters + all-gather; `FusedTrainer(sharded=False)`: one all-reduce).
     TensorBoard is used when importable; its absence only disables the image/scalar summaries.
     """
 
