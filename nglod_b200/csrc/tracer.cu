@@ -50,7 +50,7 @@ struct TraceParams {
 #endif
 // a warp goes back to the queue only once it has this many empty lanes: the atomic's round trip sits on the round's critical
 // path, so it is paid per batch of rays rather than per retired ray.  Same frame (profiles/exp_refill_min.sh), device / host-to-
-// host (L2 flushed) in ms: 1: 0.864 / 1.060, 4: 0.854 / 1.038, 8: 0.838 / 1.035, 16: 0.858 / 1.040.  Results do not depend on it
+// host (L2 flushed) in ms: 1: 0.864 / 1.060, 4: 0.854 / 1.038, 8: 0.838 / 1.035, 16: 0.858 / 1.040.  (6 and 12 on a second box: 0.850 / 0.848.)  Results do not depend on it
 // (a ray's march never looks at its lane or its neighbours).
 #ifndef NGLOD_TRACE_REFILL_MIN
 #define NGLOD_TRACE_REFILL_MIN 8
